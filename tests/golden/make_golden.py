@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (mprib/caliscope,
+read-only at /root/reference) on its own fixtures.
+
+Build-container tooling: needs /root/reference, opencv and scipy; it is never run
+on the GPU box (the .npz files travel instead).  Re-run with
+
+    python tests/golden/make_golden.py
+
+What is stored per case: the exact arrays ``CaptureVolume.optimize`` hands to
+scipy (capture_volume.py:346-365), the reference's ``joint_residuals`` /
+``joint_jacobian`` outputs at x0, the scipy results (default and tightened
+tolerances) and the pixel RMSE the reference reports for them.
+"""
+
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+REF = Path("/root/reference")
+sys.path.insert(0, str(HERE / "_refshim"))
+sys.path.insert(0, str(REF / "src"))
+
+import cv2  # noqa: E402
+import numpy as np  # noqa: E402
+from scipy.optimize import least_squares  # noqa: E402
+
+from caliscope.cameras.camera_array import CameraArray, CameraData  # noqa: E402
+from caliscope.core.bundle_parameterization import BundleParameterization  # noqa: E402
+from caliscope.core.capture_volume import CaptureVolume  # noqa: E402
+from caliscope.core.point_data import ImagePoints, WorldPoints  # noqa: E402
+from caliscope.core.reprojection import (  # noqa: E402
+    joint_jacobian,
+    joint_residuals,
+    project_points,
+    reprojection_errors,
+)
+
+
+def blocks_to_arrays(par: BundleParameterization):
+    flags, const = [], []
+    for b in par.blocks:
+        f = (1 if b.free_intrinsics else 0) | (2 if b.fisheye else 0)
+        if b.fisheye:
+            d = list(b.dist_fixed) + [0.0]
+            c = [b.fx_initial, b.fy_initial, b.cx, b.cy, d[0], d[1], d[2], d[3], 0.0]
+        else:
+            d = list(b.dist_fixed)
+            c = [b.fx_initial, b.fy_initial, b.cx, b.cy, b.k1_initial, b.k2_initial, d[0], d[1], d[2]]
+        flags.append(f)
+        const.append(c)
+    return np.array(flags, np.int32), np.array(const, np.float64), np.array([b.cam_id for b in par.blocks], np.int32)
+
+
+def ba_arrays(cv: CaptureVolume):
+    """capture_volume.py:346-358."""
+    matched = cv.img_to_obj_map >= 0
+    posed = cv.image_points.df["cam_id"].isin(set(cv.camera_array.posed_cam_id_to_index)).to_numpy()
+    m = matched & posed
+    df = cv.image_points.df[m]
+    idx = cv.camera_array.posed_cam_id_to_index
+    cam = np.array([idx[c] for c in df["cam_id"]], dtype=np.int16)
+    xy = df[["img_loc_x", "img_loc_y"]].values.astype(np.float64)
+    return cam, xy, cv.img_to_obj_map[m].astype(np.int32), m
+
+
+def px_rmse(cv: CaptureVolume, par: BundleParameterization, x: np.ndarray) -> float:
+    """What reprojection_report.overall_rmse gives after unpack_into(x)."""
+    from copy import deepcopy
+
+    ca = deepcopy(cv.camera_array)
+    pts = par.unpack_into(ca, x)
+    cam, xy, obj, _ = ba_arrays(cv)
+    e = reprojection_errors(ca, cam, xy, pts[obj])
+    return float(np.sqrt(np.mean(np.sum(e * e, axis=1))))
+
+
+def csr_parts(J):
+    J = J.tocsr()
+    J.sort_indices()
+    return {"J_data": J.data, "J_indices": J.indices.astype(np.int64), "J_indptr": J.indptr.astype(np.int64)}
+
+
+def solve_case(cv: CaptureVolume, refine: bool, loss="linear", f_scale=1.0, tight=True, groups=None):
+    cam, xy, obj, _ = ba_arrays(cv)
+    par = BundleParameterization.from_camera_array(
+        cv.camera_array, n_points=len(cv.world_points.points), refine_intrinsics=refine
+    )
+    x0 = par.pack(cv.camera_array, cv.world_points.points)
+    ga = gb = gd = gw = None
+    if groups is not None:
+        ga, gb, gd, gw = groups
+    args = (par, cam, xy, obj, ga, gb, gd, gw)
+    flags, const, cam_ids = blocks_to_arrays(par)
+    out = {
+        "cam_flags": flags,
+        "cam_const": const,
+        "cam_ids": cam_ids,
+        "n_pts": np.int64(par.n_points),
+        "obs_cam": cam.astype(np.int32),
+        "obs_pt": obj,
+        "obs_xy": xy,
+        "x0": x0,
+        "r0": joint_residuals(x0, *args),
+        "rmse0": px_rmse(cv, par, x0),
+        "loss": np.array(loss),
+        "f_scale": np.float64(f_scale),
+    }
+    if groups is not None:
+        out.update(groups_a=ga, groups_b=gb, distances=gd, weights=gw)
+    out.update(csr_parts(joint_jacobian(x0, *args)))
+    kw = dict(jac=joint_jacobian, x_scale="jac", loss=loss, f_scale=f_scale, method="trf", bounds=par.bounds())
+    res = least_squares(joint_residuals, x0, args=args, ftol=1e-8, **kw)
+    out.update(
+        x_default=res.x,
+        cost_default=res.cost,
+        nfev_default=res.nfev,
+        njev_default=res.njev,
+        status_default=res.status,
+        rmse_default=px_rmse(cv, par, res.x),
+    )
+    if tight:
+        rt = least_squares(joint_residuals, x0, args=args, ftol=1e-15, xtol=1e-15, gtol=1e-15, max_nfev=300, **kw)
+        out.update(
+            x_tight=rt.x,
+            cost_tight=rt.cost,
+            nfev_tight=rt.nfev,
+            status_tight=rt.status,
+            rmse_tight=px_rmse(cv, par, rt.x),
+        )
+    return out
+
+
+def filter_case(cv_opt: CaptureVolume, percentile: float, min_per_camera: int = 10):
+    """Keep-mask of filter_by_percentile_error (capture_volume.py:607-646,709-753) in
+    matched-observation order, with the inputs it was computed from."""
+    rep = cv_opt.reprojection_report
+    raw = rep.raw_errors
+    filt = cv_opt.filter_by_percentile_error(percentile, scope="per_camera", min_per_camera=min_per_camera)
+    keys = ["sync_index", "cam_id", "object_id", "keypoint_id"]
+    kept = set(map(tuple, filt.image_points.df[keys].itertuples(index=False, name=None)))
+    mask = np.array([tuple(k) in kept for k in raw[keys].itertuples(index=False, name=None)])
+    idx = cv_opt.camera_array.posed_cam_id_to_index
+    thr = {}
+    for cid in cv_opt.camera_array.posed_cameras:
+        e = raw[raw["cam_id"] == cid]["euclidean_error"]
+        thr[idx[cid]] = float(np.percentile(e, 100 - percentile)) if len(e) else np.inf
+    return {
+        "filt_percentile": np.float64(percentile),
+        "filt_min_per_camera": np.int64(min_per_camera),
+        "filt_err_xy": raw[["error_x", "error_y"]].values,
+        "filt_err": raw["euclidean_error"].values,
+        "filt_cam": np.array([idx[c] for c in raw["cam_id"]], np.int32),
+        "filt_thresholds": np.array([thr[i] for i in range(len(thr))]),
+        "filt_keep": mask,
+        "filt_rmse_after": filt.reprojection_report.overall_rmse,
+    }
+
+
+def session4() -> CaptureVolume:
+    p = REF / "tests/sessions/post_optimization"
+    ca = CameraArray.from_toml(p / "camera_array.toml")
+    ip = ImagePoints.from_csv(p / "calibration/extrinsic/CHARUCO/xy_CHARUCO.csv")
+    wp = WorldPoints.from_csv(p / "calibration/extrinsic/CHARUCO/xyz_CHARUCO.csv")
+    return CaptureVolume(ca, ip, wp)
+
+
+def small_pinhole_scene():
+    """tests/synthetic/test_analytic_jacobian.py:53-69."""
+    from caliscope.synthetic.calibration_object import CalibrationObject
+    from caliscope.synthetic.camera_synthesizer import CameraSynthesizer
+    from caliscope.synthetic.synthetic_scene import SyntheticScene
+    from caliscope.synthetic.trajectory import Trajectory
+
+    camera_array = CameraSynthesizer().add_ring(n=3, radius=2.0, height=0.3).build()
+    obj = CalibrationObject.planar_grid(rows=3, cols=4, spacing=0.05)
+    traj = Trajectory.linear(
+        n_frames=8, start=np.array([0.3, -0.3, -0.2]), end=np.array([-0.3, 0.3, 0.5]), tumble_rate=2.0, origin_frame=0
+    )
+    return SyntheticScene.single(
+        camera_array=camera_array, calibration_object=obj, trajectory=traj, pixel_noise_sigma=0.5
+    )
+
+
+def mixed_fisheye_case():
+    """tests/synthetic/test_analytic_jacobian.py:114-176 (fisheye 6-block + free pinhole 9-block)."""
+    rvec0, tvec0 = np.array([0.1, -0.05, 0.02]), np.array([0.0, 0.1, 3.0])
+    K0 = np.array([[600.0, 0, 320], [0, 590.0, 240], [0, 0, 1]])
+    dist0 = np.array([0.1, -0.05, 0.01, 0.002])
+    rvec1, tvec1 = np.array([-0.08, 0.12, -0.04]), np.array([0.5, -0.1, 3.2])
+    K1 = np.array([[610.0, 0, 315], [0, 605.0, 245], [0, 0, 1]])
+    dist1 = np.array([0.08, -0.03, 0.001, -0.002, 0.005])
+    ca = CameraArray(
+        {
+            0: CameraData(
+                cam_id=0, size=(640, 480), fisheye=True, matrix=K0, distortions=dist0,
+                rotation=cv2.Rodrigues(rvec0)[0], translation=tvec0,
+            ),
+            1: CameraData(
+                cam_id=1, size=(640, 480), matrix=K1, distortions=dist1,
+                rotation=cv2.Rodrigues(rvec1)[0], translation=tvec1,
+            ),
+        }
+    )  # fmt: skip
+    rng = np.random.default_rng(42)
+    points = rng.uniform(-0.6, 0.6, (25, 3))
+    pts = points.reshape(-1, 1, 3)
+    proj0, _ = cv2.fisheye.projectPoints(pts, rvec0.reshape(3, 1), tvec0.reshape(3, 1), K0, dist0.reshape(4, 1))
+    proj1, _ = cv2.projectPoints(pts, rvec1, tvec1, K1, dist1)
+    exact = np.vstack([proj0.reshape(-1, 2), proj1.reshape(-1, 2)])
+    xy = exact + rng.normal(0, 0.5, exact.shape)
+    cam = np.repeat(np.array([0, 1], dtype=np.int16), len(points))
+    obj = np.tile(np.arange(len(points), dtype=np.int32), 2)
+    par = BundleParameterization.from_camera_array(ca, n_points=len(points), refine_intrinsics=True)
+    x0 = par.pack(ca, points)
+    flags, const, cam_ids = blocks_to_arrays(par)
+    out = {
+        "cam_flags": flags, "cam_const": const, "cam_ids": cam_ids, "n_pts": np.int64(len(points)),
+        "obs_cam": cam.astype(np.int32), "obs_pt": obj, "obs_xy": xy, "x0": x0,
+        "r0": joint_residuals(x0, par, cam, xy, obj),
+        "exact_uv": exact,
+    }  # fmt: skip
+    out.update(csr_parts(joint_jacobian(x0, par, cam, xy, obj)))
+    # a perturbed evaluation point too (exercise non-trivial intrinsics values)
+    x1 = x0 + rng.normal(0, 1e-2, x0.shape)
+    out["x1"] = x1
+    out["r1"] = joint_residuals(x1, par, cam, xy, obj)
+    J1 = csr_parts(joint_jacobian(x1, par, cam, xy, obj))
+    out.update({k.replace("J_", "J1_"): v for k, v in J1.items()})
+    return out
+
+
+def projection_case():
+    """reprojection.project_points == cv2 for both camera models (test_reprojection_dispatch.py:13-30)."""
+    rng = np.random.default_rng(7)
+    pts = rng.uniform(-1.0, 1.0, (200, 3)) + np.array([0, 0, 4.0])
+    rvec = np.array([0.21, -0.4, 0.13])
+    tvec = np.array([0.1, -0.2, 0.5])
+    K = np.array([[1394.6, 0, 960.0], [0, 1380.1, 540.0], [0, 0, 1]])
+    d5 = np.array([0.115, -0.219, 0.0012, 0.0086, 0.113])
+    d4 = np.array([0.05, -0.01, 0.003, -0.001])
+    tiny = np.array([1e-14, -2e-14, 5e-15])
+    return {
+        "pts": pts, "rvec": rvec, "tvec": tvec, "K": K, "d5": d5, "d4": d4, "rvec_tiny": tiny,
+        "uv_pinhole": project_points(pts, rvec, tvec, K, d5, False),
+        "uv_fisheye": project_points(pts, rvec, tvec, K, d4, True),
+        "uv_pinhole_tiny": project_points(pts, tiny, tvec, K, d5, False),
+    }  # fmt: skip
+
+
+def main() -> None:
+    np.set_printoptions(precision=12)
+    out_dir = HERE
+
+    cv = session4()
+    for refine in (False, True):
+        g = solve_case(cv, refine)
+        opt = cv.optimize(refine_intrinsics=refine)
+        assert abs(opt.reprojection_report.overall_rmse - g["rmse_default"]) < 1e-12
+        g["optimize_iterations"] = opt.optimization_status.iterations
+        g["optimize_final_cost"] = opt.optimization_status.final_cost
+        if not refine:
+            g.update(filter_case(opt, 50.0))
+        name = f"session4_refine{int(refine)}.npz"
+        np.savez_compressed(out_dir / name, **g)
+        print(name, "rmse0", g["rmse0"], "default", g["rmse_default"], "tight", g["rmse_tight"],
+              "nfev", g["nfev_default"], g["nfev_tight"], "cost", g["cost_default"], g["cost_tight"])  # fmt: skip
+
+    g = solve_case(cv, False, loss="soft_l1", f_scale=cv.pixel_f_scale(1.0), tight=True)
+    np.savez_compressed(out_dir / "session4_softl1.npz", **g)
+    print("session4_softl1", g["cost_default"], g["cost_tight"], g["rmse_default"], g["rmse_tight"])
+
+    scene = small_pinhole_scene()
+    cvs = CaptureVolume.bootstrap(scene.image_points_noisy, scene.intrinsics_only_cameras())
+    for refine in (False, True):
+        g = solve_case(cvs, refine)
+        np.savez_compressed(out_dir / f"small_pinhole_refine{int(refine)}.npz", **g)
+        print("small_pinhole", refine, g["rmse0"], g["rmse_default"], g["rmse_tight"], g["nfev_default"])
+    groups = (
+        np.array([[0, 0, 0, 0], [0, 1, 2, 3]], dtype=np.int32),
+        np.array([[5, 5, 5, 5], [8, 9, 10, 11]], dtype=np.int32),
+        np.array([0.11, 0.07]),
+        np.array([2.0, 3.5]),
+    )
+    g = solve_case(cvs, False, groups=groups, tight=False)
+    np.savez_compressed(out_dir / "small_pinhole_constraints.npz", **g)
+
+    np.savez_compressed(out_dir / "mixed_fisheye.npz", **mixed_fisheye_case())
+    np.savez_compressed(out_dir / "projection.npz", **projection_case())
+
+    # default_ring_scene: exact projections of ground truth (zero residual), and the
+    # reference's pinned noisy CSV (tests/fixtures/synthetic/default_ring_baseline)
+    from caliscope.synthetic.scene_factories import default_ring_scene
+
+    ring = default_ring_scene(pixel_noise_sigma=0.5, random_seed=42)
+    cvr = CaptureVolume(ring.camera_array, ring.image_points_perfect, ring.world_points)
+    g = solve_case(cvr, False, tight=False)
+    assert np.abs(g["r0"]).max() < 1e-10
+    import pandas as pd
+
+    base = pd.read_csv(REF / "tests/fixtures/synthetic/default_ring_baseline/image_points_noisy.csv")
+    dfn = ring.image_points_noisy.df.sort_values(["sync_index", "cam_id", "object_id", "keypoint_id"])
+    assert np.allclose(dfn["img_loc_x"].values, base["img_loc_x"].values, atol=1e-10)
+    cvn = CaptureVolume(ring.camera_array, ring.image_points_noisy, ring.world_points)
+    gn = solve_case(cvn, True)
+    np.savez_compressed(out_dir / "ring_perfect.npz", **g)
+    np.savez_compressed(out_dir / "ring_noisy_refine1.npz", **gn)
+    print("ring_noisy", gn["rmse0"], gn["rmse_default"], gn["rmse_tight"], gn["nfev_default"], gn["nfev_tight"])
+
+
+if __name__ == "__main__":
+    main()
