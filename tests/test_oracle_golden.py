@@ -116,7 +116,7 @@ def test_robust_scaling_matches_scipy_internals(loss):
     assert abs(lf(f, cost_only=True) - O.robust_cost(f, loss, f_scale)) < 1e-12
     Js, fs = scale_for_robust_loss_function(J.copy(), f.copy(), lf(f))
     js, f2 = O.robust_row_scales(f, loss, f_scale)
-    assert np.abs(fs - f2).max() < 1e-13
+    assert np.abs(fs - f2).max() < 1e-11 * np.abs(fs).max()
     assert np.abs(Js - J * js[:, None]).max() < 1e-13
 
 
