@@ -1,0 +1,201 @@
+// Device-side helpers for the caliscope_b200 bundle-adjustment engine (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cb {
+
+// ---------------------------------------------------------------------------------------------
+// camera table (one entry per camera, rebuilt by cam_prep_kernel for every evaluation point)
+// ---------------------------------------------------------------------------------------------
+constexpr int CT_R = 0;      // 9  rotation, row-major
+constexpr int CT_T = 9;      // 3  translation
+constexpr int CT_JR = 12;    // 9  SO(3) right Jacobian: d(R X)/dr = -R [X]x Jr
+constexpr int CT_FX = 21;    // fx = s * fx0
+constexpr int CT_FY = 22;
+constexpr int CT_CX = 23;
+constexpr int CT_CY = 24;
+constexpr int CT_D = 25;     // 5  Brown-Conrady k1 k2 p1 p2 k3 | fisheye k1 k2 k3 k4 -
+constexpr int CT_IFX0 = 30;  // 1 / fx0
+constexpr int CT_SX = 31;    // fx / fx0
+constexpr int CT_SY = 32;    // fy / fx0
+constexpr int CT_FYR = 33;   // fy0 / fx0
+constexpr int CT_FLAGS = 34; // flags as double
+constexpr int CT_SIZE = 36;
+
+constexpr double CB_EPS = 2.220446049250313e-16;
+
+// ---------------------------------------------------------------------------------------------
+// 256-bit global loads/stores (LDG.E.256 / STG.E.256 on sm_100): one full 32-byte sector per thread
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st256(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void ld256(const double* p, double& a, double& b, double& c, double& d) {
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+__device__ __forceinline__ void ld256nc(const double* p, double& a, double& b, double& c, double& d) {
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier + 1-D bulk async copy (TMA engine; SASS: UBLKCP)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(phase)
+      : "memory");
+}
+// global -> shared bulk copy, completion signalled on `bar` (bytes % 16 == 0, 16-byte aligned)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// reductions
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// robust loss: rho(z), rho'(z), rho''(z), z = (f / f_scale)^2   (scipy least_squares.py loss table)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void loss_eval(int loss, double z, double& r0, double& r1, double& r2) {
+  switch (loss) {
+    case 1: {  // soft_l1
+      double t = 1.0 + z, s = sqrt(t);
+      r0 = 2.0 * (s - 1.0);
+      r1 = 1.0 / s;
+      r2 = -0.5 / (t * s);
+    } break;
+    case 2: {  // huber
+      if (z <= 1.0) {
+        r0 = z; r1 = 1.0; r2 = 0.0;
+      } else {
+        double s = sqrt(z);
+        r0 = 2.0 * s - 1.0; r1 = 1.0 / s; r2 = -0.5 / (z * s);
+      }
+    } break;
+    case 3: {  // cauchy
+      double t = 1.0 + z;
+      r0 = log1p(z); r1 = 1.0 / t; r2 = -1.0 / (t * t);
+    } break;
+    case 4: {  // arctan
+      double t = 1.0 + z * z;
+      r0 = atan(z); r1 = 1.0 / t; r2 = -2.0 * z / (t * t);
+    } break;
+    default:
+      r0 = z; r1 = 1.0; r2 = 0.0;
+  }
+}
+
+// Per scalar residual row: returns the cost contribution 0.5 * fs^2 * rho(z) and rescales
+// (f, jacobian-row weight) as scipy's scale_for_robust_loss_function (common.py:720-731):
+//   w = max(rho' + 2 rho'' z, EPS);  J_row *= sqrt(w);  f <- f * rho' / sqrt(w)
+__device__ __forceinline__ double robust_row(int loss, double fs, double& f, double& jscale) {
+  if (loss == 0) {
+    jscale = 1.0;
+    return 0.5 * f * f;
+  }
+  double q = f / fs, z = q * q, r0, r1, r2;
+  loss_eval(loss, z, r0, r1, r2);
+  double w = fmax(r1 + 2.0 * r2 * z, CB_EPS);
+  jscale = sqrt(w);
+  f = f * r1 / jscale;
+  return 0.5 * fs * fs * r0;
+}
+__device__ __forceinline__ double robust_cost_only(int loss, double fs, double f) {
+  if (loss == 0) return 0.5 * f * f;
+  double q = f / fs, z = q * q, r0, r1, r2;
+  loss_eval(loss, z, r0, r1, r2);
+  return 0.5 * fs * fs * r0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// projection of one observation (cv2.projectPoints / cv2.fisheye.projectPoints closed forms)
+// ---------------------------------------------------------------------------------------------
+struct ProjOut {
+  double u, v;         // pixels
+  double a, b, r2;     // normalised coordinates and a^2 + b^2
+  double xd, yd;       // distorted normalised coordinates
+  double xa, xb, ya, yb;  // d(xd,yd)/d(a,b)
+  double iz;
+  double Xc[3];
+};
+
+template <bool JAC>
+__device__ __forceinline__ void project_obs(const double* __restrict__ cam, bool fisheye, double X0, double X1,
+                                            double X2, ProjOut& o) {
+  const double* R = cam + CT_R;
+  o.Xc[0] = fma(R[0], X0, fma(R[1], X1, fma(R[2], X2, cam[CT_T + 0])));
+  o.Xc[1] = fma(R[3], X0, fma(R[4], X1, fma(R[5], X2, cam[CT_T + 1])));
+  o.Xc[2] = fma(R[6], X0, fma(R[7], X1, fma(R[8], X2, cam[CT_T + 2])));
+  double iz = (o.Xc[2] != 0.0) ? 1.0 / o.Xc[2] : 1.0;  // OpenCV: z == 0 -> 1
+  double a = o.Xc[0] * iz, b = o.Xc[1] * iz;
+  double r2 = a * a + b * b;
+  o.iz = iz; o.a = a; o.b = b; o.r2 = r2;
+  const double* d = cam + CT_D;
+  if (!fisheye) {
+    double k1 = d[0], k2 = d[1], p1 = d[2], p2 = d[3], k3 = d[4];
+    double cd = 1.0 + r2 * (k1 + r2 * (k2 + r2 * k3));
+    o.xd = a * cd + 2.0 * p1 * a * b + p2 * (r2 + 2.0 * a * a);
+    o.yd = b * cd + p1 * (r2 + 2.0 * b * b) + 2.0 * p2 * a * b;
+    if (JAC) {
+      double dcd = k1 + r2 * (2.0 * k2 + 3.0 * k3 * r2);
+      o.xa = cd + 2.0 * a * a * dcd + 2.0 * p1 * b + 6.0 * p2 * a;
+      o.xb = 2.0 * a * b * dcd + 2.0 * p1 * a + 2.0 * p2 * b;
+      o.ya = o.xb;
+      o.yb = cd + 2.0 * b * b * dcd + 6.0 * p1 * b + 2.0 * p2 * a;
+    }
+  } else {
+    double rr = sqrt(r2);
+    double th = atan(rr), th2 = th * th;
+    double thd = th * (1.0 + th2 * (d[0] + th2 * (d[1] + th2 * (d[2] + th2 * d[3]))));
+    bool big = rr > 1e-8;
+    double inv_r = big ? 1.0 / rr : 1.0;
+    double cdist = big ? thd * inv_r : 1.0;
+    o.xd = a * cdist;
+    o.yd = b * cdist;
+    if (JAC) {
+      double dthd = 1.0 + th2 * (3.0 * d[0] + th2 * (5.0 * d[1] + th2 * (7.0 * d[2] + th2 * 9.0 * d[3])));
+      double dcdr = big ? (dthd / (1.0 + r2) - cdist) * inv_r : 0.0;
+      double fa = big ? a * inv_r : 0.0, fb = big ? b * inv_r : 0.0;
+      o.xa = cdist + a * dcdr * fa;
+      o.xb = a * dcdr * fb;
+      o.ya = b * dcdr * fa;
+      o.yb = cdist + b * dcdr * fb;
+    }
+  }
+  o.u = fma(cam[CT_FX], o.xd, cam[CT_CX]);
+  o.v = fma(cam[CT_FY], o.yd, cam[CT_CY]);
+}
+
+}  // namespace cb

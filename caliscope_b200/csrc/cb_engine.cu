@@ -1,0 +1,909 @@
+// Host side of the caliscope_b200 bundle-adjustment engine: index build, the Levenberg-Marquardt
+// driver and the C ABI declared in include/caliscope_b200.h.
+//
+// Replaces (behind the seam described in INTEGRATION.md) the call
+//   scipy.optimize.least_squares(joint_residuals, x0, jac=joint_jacobian, method="trf", x_scale="jac", ...)
+// at /root/reference/src/caliscope/core/capture_volume.py:387-411.  Termination tests and status
+// codes follow scipy's (site-packages/scipy/optimize/_lsq/common.py:705-717, trf.py:466-475);
+// the step itself is a damped Gauss-Newton step from the Schur-complement reduced camera system.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <cub/cub.cuh>
+#include <string>
+#include <vector>
+
+#include "../../include/caliscope_b200.h"
+#include "cb_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<long long> g_launches{0};
+
+#define CB_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      g_last_error = std::string(#expr) + ": " + cudaGetErrorString(_e);                           \
+      return CB_E_CUDA;                                                                            \
+    }                                                                                              \
+  } while (0)
+
+#define CB_TRY(expr)                \
+  do {                              \
+    int _r = (expr);                \
+    if (_r != CB_OK) return _r;     \
+  } while (0)
+
+#define CB_LAUNCH(kernel, grid, block, smem, stream, ...)                 \
+  do {                                                                    \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);           \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                   \
+  } while (0)
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+template <typename T>
+int dalloc(T** p, size_t n) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+  if (e != cudaSuccess) {
+    g_last_error = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+    return CB_E_NOMEM;
+  }
+  return CB_OK;
+}
+
+}  // namespace
+
+struct CbBaProblem {
+  int device = 0, num_sms = 148;
+  int n_cams = 0, n_pts = 0, P = 6, nP = 0, n_obs = 0, n_params = 0;
+  int LD = 0, n_blk = 0, n_tiles = 0, n_split = 1, k_chunks = 0, K_pad = 0;
+  int n_chunks = 0, n_pairs = 0, pt_blocks = 0;
+  std::vector<int> h_cam_off;
+  std::vector<void*> allocs;
+  // problem tables
+  int *d_cam_off = nullptr, *d_cam_flags = nullptr;
+  double* d_cam_const = nullptr;
+  double2* d_cm_xy = nullptr;
+  int *d_cm_pt = nullptr, *d_cm_row = nullptr, *d_cm_orig = nullptr, *d_cam_start = nullptr;
+  int *d_chunk_cam = nullptr, *d_chunk_begin = nullptr, *d_chunk_end = nullptr, *d_cam_chunk_start = nullptr;
+  int *d_pt_start = nullptr, *d_pm_orig = nullptr, *d_pair_start = nullptr, *d_pair_cam = nullptr,
+      *d_pt_pair_start = nullptr;
+  int *d_tileI = nullptr, *d_tileJ = nullptr, *d_tile_of = nullptr;
+  unsigned char* d_active = nullptr;
+  double *d_lo = nullptr, *d_hi = nullptr;
+  // work buffers
+  double *d_x = nullptr, *d_xc[2] = {nullptr, nullptr}, *d_xp4[2] = {nullptr, nullptr};
+  double *d_camtab = nullptr, *d_jrows = nullptr, *d_partial = nullptr, *d_Upk = nullptr, *d_gc = nullptr,
+         *d_camcost = nullptr, *d_costsum = nullptr, *d_V6 = nullptr, *d_gp = nullptr, *d_Dp2 = nullptr,
+         *d_Dc2 = nullptr, *d_Linv6 = nullptr, *d_tvec = nullptr, *d_Zt = nullptr, *d_part = nullptr,
+         *d_tpart = nullptr, *d_red = nullptr, *d_Minv = nullptr, *d_dc = nullptr, *d_dp = nullptr,
+         *d_bpart = nullptr, *d_sc = nullptr, *d_red2 = nullptr, *d_out2 = nullptr;
+  unsigned long long* d_gmax = nullptr;
+  double* h_sc = nullptr;  // pinned
+  double* h_x = nullptr;   // pinned staging for x
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  // pcg launch configuration
+  int pcg_cs = 1, pcg_rows = 0, pcg_slab_smem = 1;
+  size_t pcg_smem = 0;
+  int red_slots = 64;
+  size_t red_len() const { return (size_t)nP * nP + 3 * (size_t)nP + 1 + red_slots; }
+};
+
+namespace {
+
+template <typename T>
+int palloc(CbBaProblem* p, T** ptr, size_t n) {
+  CB_TRY(dalloc(ptr, n));
+  p->allocs.push_back((void*)*ptr);
+  return CB_OK;
+}
+
+int bits_for(unsigned long long v) {
+  int b = 1;
+  while (b < 64 && (v >> b) != 0ull) ++b;
+  return b;
+}
+
+// ------------------------------------------------------------------------------------------
+// index build
+// ------------------------------------------------------------------------------------------
+int build_indices(CbBaProblem* p, const int* d_obs_cam, const int* d_obs_pt, const double* d_obs_xy,
+                  cudaStream_t st) {
+  const int n = p->n_obs;
+  const int TB = 256, G = cdiv(std::max(n, 1), TB);
+  int* d_bad;
+  CB_TRY(dalloc(&d_bad, 1));
+  CB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+  CB_LAUNCH(cb::validate_kernel, G, TB, 0, st, d_obs_cam, d_obs_pt, n, p->n_cams, p->n_pts, d_bad);
+  int bad = 0;
+  CB_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d_bad);
+  if (bad) {
+    g_last_error = "obs_cam / obs_pt index out of range in " + std::to_string(bad) + " observations";
+    return CB_E_INVALID;
+  }
+
+  unsigned long long *k_in, *k_out;
+  int *v_in, *v_out, *pm_pt, *pm_cam, *cm_cam, *flag, *pidx;
+  CB_TRY(dalloc(&k_in, n)); CB_TRY(dalloc(&k_out, n));
+  CB_TRY(dalloc(&v_in, n)); CB_TRY(dalloc(&v_out, n));
+  CB_TRY(dalloc(&pm_pt, n)); CB_TRY(dalloc(&pm_cam, n)); CB_TRY(dalloc(&cm_cam, n));
+  CB_TRY(dalloc(&flag, n)); CB_TRY(dalloc(&pidx, n + 1));
+
+  // temp storage for cub (max of sort and scan requirements)
+  size_t tb_sort = 0, tb_scan = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb_sort, k_in, k_out, v_in, v_out, n, 0, 64, st);
+  cub::DeviceScan::ExclusiveSum(nullptr, tb_scan, flag, pidx, n, st);
+  size_t tb = std::max(tb_sort, tb_scan);
+  void* d_tmp;
+  CB_CUDA(cudaMalloc(&d_tmp, std::max<size_t>(tb, 16)));
+
+  // (1) point-major order: key = pt * n_cams + cam, stable -> ties keep caller order
+  CB_LAUNCH(cb::make_keys_kernel, G, TB, 0, st, d_obs_pt, d_obs_cam, (long long)p->n_cams, n, k_in, v_in);
+  const int kb = bits_for((unsigned long long)p->n_pts * (unsigned long long)p->n_cams);
+  CB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb, k_in, k_out, v_in, p->d_pm_orig, n, 0, kb, st));
+  g_launches.fetch_add(4);
+  CB_LAUNCH(cb::split_keys_kernel, G, TB, 0, st, k_out, (long long)p->n_cams, n, pm_pt, pm_cam);
+  CB_LAUNCH(cb::lower_bound_kernel, cdiv(p->n_pts + 1, TB), TB, 0, st, pm_pt, n, p->n_pts, p->d_pt_start);
+  // (2) unique (point, camera) pairs
+  CB_LAUNCH(cb::pair_flag_kernel, G, TB, 0, st, k_out, n, flag);
+  CB_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tb, flag, pidx, n, st));
+  g_launches.fetch_add(2);
+  int last_flag = 0, last_idx = 0;
+  if (n > 0) {
+    CB_CUDA(cudaMemcpyAsync(&last_flag, flag + n - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CB_CUDA(cudaMemcpyAsync(&last_idx, pidx + n - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  }
+  CB_CUDA(cudaStreamSynchronize(st));
+  p->n_pairs = last_flag + last_idx;
+  CB_TRY(palloc(p, &p->d_pair_start, (size_t)p->n_pairs + 1));
+  CB_TRY(palloc(p, &p->d_pair_cam, (size_t)p->n_pairs + 1));
+  CB_LAUNCH(cb::pair_scatter_kernel, G, TB, 0, st, flag, pidx, n, pm_cam, p->d_pair_start, p->d_pair_cam, p->n_pairs);
+  CB_LAUNCH(cb::pt_pair_start_kernel, cdiv(p->n_pts + 1, TB), TB, 0, st, p->d_pt_start, pidx, p->n_pts, n,
+            p->n_pairs, p->d_pt_pair_start);
+  // (3) camera-major order: key = cam * n_pts + pt over the point-major rows (stable)
+  CB_LAUNCH(cb::make_keys_kernel, G, TB, 0, st, pm_cam, pm_pt, (long long)p->n_pts, n, k_in, v_in);
+  CB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb, k_in, k_out, v_in, p->d_cm_row, n, 0, kb, st));
+  g_launches.fetch_add(4);
+  CB_LAUNCH(cb::split_keys_kernel, G, TB, 0, st, k_out, (long long)p->n_pts, n, cm_cam, v_out);
+  CB_LAUNCH(cb::lower_bound_kernel, cdiv(p->n_cams + 1, TB), TB, 0, st, cm_cam, n, p->n_cams, p->d_cam_start);
+  CB_LAUNCH(cb::cm_gather_kernel, G, TB, 0, st, p->d_cm_row, p->d_pm_orig, pm_pt,
+            reinterpret_cast<const double2*>(d_obs_xy), n, p->d_cm_pt, p->d_cm_orig, p->d_cm_xy);
+  // (4) chunk table (host, n_cams + 1 integers)
+  std::vector<int> cam_start(p->n_cams + 1);
+  CB_CUDA(cudaMemcpyAsync(cam_start.data(), p->d_cam_start, sizeof(int) * (p->n_cams + 1), cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  std::vector<int> cc, cbeg, cend, ccs(p->n_cams + 1);
+  for (int c = 0; c < p->n_cams; ++c) {
+    ccs[c] = (int)cc.size();
+    for (int b = cam_start[c]; b < cam_start[c + 1]; b += cb::RJ_CHUNK) {
+      cc.push_back(c);
+      cbeg.push_back(b);
+      cend.push_back(std::min(b + cb::RJ_CHUNK, cam_start[c + 1]));
+    }
+  }
+  ccs[p->n_cams] = (int)cc.size();
+  p->n_chunks = (int)cc.size();
+  CB_TRY(palloc(p, &p->d_chunk_cam, cc.size()));
+  CB_TRY(palloc(p, &p->d_chunk_begin, cc.size()));
+  CB_TRY(palloc(p, &p->d_chunk_end, cc.size()));
+  if (!cc.empty()) {
+    CB_CUDA(cudaMemcpyAsync(p->d_chunk_cam, cc.data(), sizeof(int) * cc.size(), cudaMemcpyHostToDevice, st));
+    CB_CUDA(cudaMemcpyAsync(p->d_chunk_begin, cbeg.data(), sizeof(int) * cc.size(), cudaMemcpyHostToDevice, st));
+    CB_CUDA(cudaMemcpyAsync(p->d_chunk_end, cend.data(), sizeof(int) * cc.size(), cudaMemcpyHostToDevice, st));
+  }
+  CB_CUDA(cudaMemcpyAsync(p->d_cam_chunk_start, ccs.data(), sizeof(int) * ccs.size(), cudaMemcpyHostToDevice, st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d_tmp); cudaFree(k_in); cudaFree(k_out); cudaFree(v_in); cudaFree(v_out);
+  cudaFree(pm_pt); cudaFree(pm_cam); cudaFree(cm_cam); cudaFree(flag); cudaFree(pidx);
+  return CB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// one evaluation / linearisation / damped system / step
+// ------------------------------------------------------------------------------------------
+template <int P>
+int run_cam_prep(CbBaProblem* p, const double* xc, cudaStream_t st) {
+  CB_LAUNCH(cb::cam_prep_kernel, cdiv(p->n_cams, 64), 64, 0, st, xc, p->d_cam_flags, p->d_cam_const, p->n_cams, P,
+            p->d_camtab);
+  return CB_OK;
+}
+
+template <int P, int MODE>
+void launch_resjac(CbBaProblem* p, const double* xp4, int loss, double fscale, double* out2, cudaStream_t st) {
+  if (p->n_chunks == 0) return;
+  CB_LAUNCH((cb::resjac_kernel<P, MODE>), p->n_chunks, cb::RJ_THREADS, 0, st, p->d_chunk_cam, p->d_chunk_begin,
+            p->d_chunk_end, p->d_cm_xy, p->d_cm_pt, p->d_cm_row, p->d_cm_orig, p->d_camtab, xp4, loss, fscale,
+            p->d_jrows, p->d_partial, out2);
+}
+
+// residual + Jacobian rows + per-camera / per-point normal-equation blocks at (xc, xp4)
+template <int P>
+int linearize(CbBaProblem* p, const double* xc, const double* xp4, int loss, double fscale, cudaStream_t st,
+              bool time_rj, float* rj_ms) {
+  using RT = cb::RowT<P>;
+  CB_TRY(run_cam_prep<P>(p, xc, st));
+  if (time_rj) CB_CUDA(cudaEventRecord(p->ev2, st));
+  launch_resjac<P, 0>(p, xp4, loss, fscale, nullptr, st);
+  if (time_rj) {
+    CB_CUDA(cudaEventRecord(p->ev3, st));
+  }
+  CB_LAUNCH((cb::cam_reduce_kernel<P>), p->n_cams, 64, 0, st, p->d_cam_chunk_start, p->d_partial, p->d_Upk, p->d_gc,
+            p->d_camcost);
+  static_assert(RT::NACC <= 64, "cam_reduce block too small");
+  CB_LAUNCH(cb::sum_kernel, 1, 256, 0, st, p->d_camcost, p->n_cams, p->d_costsum);
+  CB_CUDA(cudaMemsetAsync(p->d_gmax, 0, sizeof(unsigned long long), st));
+  CB_LAUNCH((cb::pt_reduce_kernel<P>), p->pt_blocks, cb::PT_WARPS * 32, 0, st, p->d_pt_start, p->n_pts, p->d_jrows,
+            p->d_V6, p->d_gp, p->d_Dp2, p->d_gmax);
+  (void)rj_ms;
+  return CB_OK;
+}
+
+template <int P>
+int build_system(CbBaProblem* p, double lam, bool new_lin, const CbBaOptions* opt, cudaStream_t st) {
+  CB_LAUNCH((cb::pt_zbuild_kernel<P>), p->pt_blocks, cb::PT_WARPS * 32, 0, st, p->d_pt_pair_start, p->d_pair_start,
+            p->d_pair_cam, p->n_pts, p->d_jrows, p->d_V6, p->d_gp, p->d_Dp2, lam, p->d_Linv6, p->d_tvec, p->d_Zt,
+            (size_t)p->LD);
+  CB_LAUNCH(cb::schur_syrk_kernel, p->n_tiles * p->n_split, cb::SY_THREADS, sizeof(cb::SyrkSmem), st, p->d_Zt,
+            (size_t)p->LD, p->d_tvec, p->k_chunks, p->n_split, p->d_tileI, p->d_tileJ, p->n_tiles, p->d_part,
+            p->d_tpart);
+  const size_t nfin = (size_t)p->nP * p->nP + p->nP + 1;
+  CB_LAUNCH((cb::schur_finalize_kernel<P>), cdiv((long long)nfin, 256), 256, 0, st, p->nP, p->n_blk, p->n_tiles,
+            p->n_split, p->d_tile_of, p->d_part, p->d_tpart, p->d_Upk, p->d_gc, p->d_costsum, p->d_red);
+  // gradient inf-norm over points: one slot per rank so a SUM all-reduce carries the max
+  const size_t slot0 = (size_t)p->nP * p->nP + 3 * (size_t)p->nP + 1;
+  CB_CUDA(cudaMemsetAsync(p->d_red + slot0, 0, sizeof(double) * p->red_slots, st));
+  const int rank = (opt && opt->allreduce) ? std::min(std::max(opt->rank, 0), p->red_slots - 1) : 0;
+  CB_CUDA(cudaMemcpyAsync(p->d_red + slot0 + rank, p->d_gmax, sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if (opt && opt->allreduce) {
+    if (opt->allreduce(opt->allreduce_user, p->d_red, (long long)p->red_len(), (void*)st) != 0) {
+      g_last_error = "all-reduce callback failed";
+      return CB_E_CALLBACK;
+    }
+  }
+  CB_LAUNCH(cb::post_reduce_kernel, 1, 256, 0, st, p->nP, lam, new_lin ? 1 : 0, p->d_red, p->d_Dc2, p->d_active,
+            p->d_sc);
+  return CB_OK;
+}
+
+int launch_pcg(CbBaProblem* p, double tol2, int max_iter, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p->pcg_cs);
+  cfg.blockDim = dim3(cb::PCG_THREADS);
+  cfg.dynamicSmemBytes = p->pcg_smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = p->pcg_cs;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  const double* S = p->d_red;
+  const double* b = p->d_red + (size_t)p->nP * p->nP;
+  CB_CUDA(cudaLaunchKernelEx(&cfg, cb::pcg_cluster_kernel, S, b, (const double*)p->d_Minv, p->nP, p->P, p->pcg_rows,
+                             p->pcg_slab_smem, tol2, max_iter, p->d_dc, p->d_sc));
+  g_launches.fetch_add(1);
+  return CB_OK;
+}
+
+template <int P>
+int solve_step(CbBaProblem* p, double lam, int cur, const CbBaOptions* opt, double* dp_out, cudaStream_t st) {
+  CB_LAUNCH((cb::block_inverse_kernel<P>), cdiv(p->n_cams, 64), 64, 0, st, p->d_red, p->nP, p->n_cams, p->d_Minv);
+  const double tol = (opt && opt->pcg_tol > 0) ? opt->pcg_tol : 1e-10;
+  const int mit = (opt && opt->pcg_max_iter > 0) ? opt->pcg_max_iter : 4 * p->nP;
+  CB_TRY(launch_pcg(p, tol * tol, mit, st));
+  const size_t nn = (size_t)p->nP * p->nP;
+  CB_LAUNCH(cb::cam_update_kernel, 1, 256, 0, st, p->nP, lam, p->d_xc[cur], p->d_dc, p->d_lo, p->d_hi,
+            p->d_red + nn + p->nP, p->d_Dc2, p->d_active, p->d_xc[cur ^ 1], p->d_sc);
+  CB_LAUNCH(cb::pt_backsub_kernel, p->pt_blocks, cb::PT_WARPS * 32, sizeof(double) * p->nP, st, p->n_pts, p->nP, lam,
+            p->d_Zt, (size_t)p->LD, p->d_dc, p->d_Linv6, p->d_tvec, p->d_gp, p->d_Dp2, p->d_xp4[cur],
+            p->d_xp4[cur ^ 1], dp_out, p->d_bpart);
+  CB_LAUNCH(cb::sum3_kernel, 3, 256, 0, st, p->d_bpart, p->pt_blocks, p->d_red2 + 1);
+  return CB_OK;
+}
+
+template <int P>
+int trial_cost(CbBaProblem* p, int nxt, int loss, double fscale, const CbBaOptions* opt, cudaStream_t st) {
+  CB_TRY(run_cam_prep<P>(p, p->d_xc[nxt], st));
+  launch_resjac<P, 1>(p, p->d_xp4[nxt], loss, fscale, nullptr, st);
+  CB_LAUNCH(cb::sum_kernel, 1, 256, 0, st, p->d_partial, p->n_chunks, p->d_red2);
+  if (opt && opt->allreduce) {
+    if (opt->allreduce(opt->allreduce_user, p->d_red2, 4, (void*)st) != 0) {
+      g_last_error = "all-reduce callback failed";
+      return CB_E_CALLBACK;
+    }
+  }
+  return CB_OK;
+}
+
+struct HostScalars {
+  double sc[cb::SC_COUNT];
+  double red2[4];
+  double slots[64];
+};
+
+int readback(CbBaProblem* p, HostScalars* h, cudaStream_t st) {
+  const size_t slot0 = (size_t)p->nP * p->nP + 3 * (size_t)p->nP + 1;
+  CB_CUDA(cudaMemcpyAsync(p->h_sc, p->d_sc, sizeof(double) * cb::SC_COUNT, cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaMemcpyAsync(p->h_sc + cb::SC_COUNT, p->d_red2, sizeof(double) * 4, cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaMemcpyAsync(p->h_sc + cb::SC_COUNT + 4, p->d_red + slot0, sizeof(double) * p->red_slots,
+                          cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  std::memcpy(h->sc, p->h_sc, sizeof(double) * cb::SC_COUNT);
+  std::memcpy(h->red2, p->h_sc + cb::SC_COUNT, sizeof(double) * 4);
+  std::memcpy(h->slots, p->h_sc + cb::SC_COUNT + 4, sizeof(double) * p->red_slots);
+  return CB_OK;
+}
+
+int upload_x(CbBaProblem* p, const double* x, cudaStream_t st) {
+  std::memcpy(p->h_x, x, sizeof(double) * p->n_params);
+  CB_CUDA(cudaMemcpyAsync(p->d_x, p->h_x, sizeof(double) * p->n_params, cudaMemcpyHostToDevice, st));
+  const int n = std::max(p->n_cams * p->P, p->n_pts);
+  CB_LAUNCH(cb::unpack_x_kernel, cdiv(std::max(n, 1), 256), 256, 0, st, p->d_x, p->d_cam_off, p->d_cam_flags,
+            p->d_cam_const, p->n_cams, p->P, p->n_pts, p->d_xc[0], p->d_xp4[0]);
+  return CB_OK;
+}
+
+int download_x(CbBaProblem* p, int cur, double* x, cudaStream_t st) {
+  const int n = std::max(p->n_cams * p->P, p->n_pts);
+  CB_LAUNCH(cb::pack_x_kernel, cdiv(std::max(n, 1), 256), 256, 0, st, p->d_x, p->d_cam_off, p->n_cams, p->P, p->n_pts,
+            p->d_xc[cur], p->d_xp4[cur]);
+  CB_CUDA(cudaMemcpyAsync(p->h_x, p->d_x, sizeof(double) * p->n_params, cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  std::memcpy(x, p->h_x, sizeof(double) * p->n_params);
+  return CB_OK;
+}
+
+int set_bounds(CbBaProblem* p, bool use_bounds, cudaStream_t st) {
+  std::vector<double> lo((size_t)p->nP, -1e300), hi((size_t)p->nP, 1e300);
+  if (use_bounds && p->P == 9) {
+    for (int c = 0; c < p->n_cams; ++c)
+      if (p->h_cam_off[c + 1] - p->h_cam_off[c] == 9) {
+        lo[c * 9 + 6] = 0.5; hi[c * 9 + 6] = 2.0;
+        lo[c * 9 + 7] = -1.0; hi[c * 9 + 7] = 1.0;
+        lo[c * 9 + 8] = -2.0; hi[c * 9 + 8] = 2.0;
+      }
+  }
+  CB_CUDA(cudaMemcpyAsync(p->d_lo, lo.data(), sizeof(double) * p->nP, cudaMemcpyHostToDevice, st));
+  CB_CUDA(cudaMemcpyAsync(p->d_hi, hi.data(), sizeof(double) * p->nP, cudaMemcpyHostToDevice, st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  return CB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Levenberg-Marquardt driver
+// ------------------------------------------------------------------------------------------
+template <int P>
+int lm_solve(CbBaProblem* p, const CbBaOptions* opt, double* x_inout, CbBaResult* res, cudaStream_t st) {
+  const int loss = opt->loss;
+  const double fscale = opt->f_scale > 0 ? opt->f_scale : 1.0;
+  const double ftol = opt->ftol, xtol = opt->xtol, gtol = opt->gtol;
+  const long long max_nfev = opt->max_nfev > 0 ? opt->max_nfev : 100ll * p->n_params;
+  const bool verbose = opt->verbose >= 2 && opt->rank == 0;
+  const long long launches0 = g_launches.load();
+  std::memset(res, 0, sizeof(*res));
+
+  CB_TRY(set_bounds(p, opt->use_bounds != 0, st));
+  CB_CUDA(cudaMemsetAsync(p->d_Dc2, 0, sizeof(double) * p->nP, st));
+  CB_CUDA(cudaMemsetAsync(p->d_Dp2, 0, sizeof(double) * 3 * (size_t)std::max(p->n_pts, 1), st));
+  CB_CUDA(cudaMemsetAsync(p->d_sc, 0, sizeof(double) * cb::SC_COUNT, st));
+  CB_TRY(upload_x(p, x_inout, st));
+  CB_CUDA(cudaEventRecord(p->ev0, st));
+
+  int cur = 0;
+  double lam = opt->lambda0 > 0 ? opt->lambda0 : 1e-4, nu = 2.0;
+  long long nfev = 1, njev = 1, nit = 0, pcg_total = 0;
+  double rj_ms_total = 0.0;
+  long long rj_launches = 0;
+  float ms = 0.f;
+  CB_TRY(linearize<P>(p, p->d_xc[cur], p->d_xp4[cur], loss, fscale, st, true, nullptr));
+  bool rj_pending = true;  // ev2/ev3 bracket the last residual+Jacobian launch; read after the next sync
+
+  bool new_lin = true;
+  int status = 0;
+  double cost = 0.0, gnorm = 0.0;
+  HostScalars h;
+  if (verbose)
+    std::fprintf(stderr, "%5s %5s %22s %22s %9s %10s %10s %10s %5s\n", "nit", "nfev", "cost", "cost_new", "ratio",
+                 "lambda", "|step|", "|g|inf", "pcg");
+  while (true) {
+    if (nfev >= max_nfev && !new_lin) { status = 0; break; }
+    CB_TRY(build_system<P>(p, lam, new_lin, opt, st));
+    if (nfev >= max_nfev) {
+      // out of evaluations: only refresh cost / gradient norm for the report
+      CB_TRY(readback(p, &h, st));
+      cost = h.sc[cb::SC_COST];
+      gnorm = h.sc[cb::SC_GNORM_C];
+      for (int s = 0; s < p->red_slots; ++s) gnorm = std::max(gnorm, h.slots[s]);
+      if (res->initial_cost == 0.0 && njev == 1) res->initial_cost = cost;
+      status = (gnorm < gtol) ? 1 : 0;
+      break;
+    }
+    CB_TRY(solve_step<P>(p, lam, cur, opt, nullptr, st));
+    CB_TRY(trial_cost<P>(p, cur ^ 1, loss, fscale, opt, st));
+    CB_TRY(readback(p, &h, st));
+    if (rj_pending) {
+      CB_CUDA(cudaEventElapsedTime(&ms, p->ev2, p->ev3));
+      rj_ms_total += ms; ++rj_launches; rj_pending = false;
+    }
+    if (new_lin) {
+      cost = h.sc[cb::SC_COST];
+      gnorm = h.sc[cb::SC_GNORM_C];
+      for (int s = 0; s < p->red_slots; ++s) gnorm = std::max(gnorm, h.slots[s]);
+      if (njev == 1) res->initial_cost = cost;
+      if (gnorm < gtol) { status = 1; break; }
+      ++nit;
+    }
+    ++nfev;
+    pcg_total += (long long)h.sc[cb::SC_PCG_ITS];
+    const double cost_new = h.red2[0];
+    const double pred = h.sc[cb::SC_PRED_C] + h.red2[1];
+    const double step2 = h.sc[cb::SC_STEP2_C] + h.red2[2];
+    const double x2 = h.sc[cb::SC_X2_C] + h.red2[3];
+    const bool pcg_bad = h.sc[cb::SC_PCG_FLAG] != 0.0;
+    const bool finite = std::isfinite(cost_new) && std::isfinite(pred) && !pcg_bad;
+    const double actual = finite ? cost - cost_new : -1.0;
+    const double ratio = (finite && pred > 0) ? actual / pred : -1.0;
+    const double step_norm = std::sqrt(step2), x_norm = std::sqrt(x2);
+    const bool ft = finite && actual < ftol * cost && ratio > 0.25;
+    const bool xt = finite && step_norm < xtol * (xtol + x_norm);
+    const int term = (ft && xt) ? 4 : ft ? 2 : xt ? 3 : 0;
+    if (verbose)
+      std::fprintf(stderr, "%5lld %5lld %22.15e %22.15e %+9.3f %10.2e %10.2e %10.2e %5d\n", nit, nfev, cost, cost_new,
+                   ratio, lam, step_norm, gnorm, (int)h.sc[cb::SC_PCG_ITS]);
+    if (finite && actual > 0) {
+      cur ^= 1;
+      const double t = 2.0 * ratio - 1.0;
+      lam = lam * std::max(1.0 / 3.0, 1.0 - t * t * t);
+      lam = std::max(lam, 1e-15);
+      nu = 2.0;
+      CB_TRY(linearize<P>(p, p->d_xc[cur], p->d_xp4[cur], loss, fscale, st, true, nullptr));
+      rj_pending = true;
+      ++njev;
+      new_lin = true;
+      cost = cost_new;
+    } else {
+      lam = std::min(lam * nu, 1e12);
+      nu *= 2.0;
+      new_lin = false;
+    }
+    if (term) { status = term; break; }
+  }
+  CB_CUDA(cudaEventRecord(p->ev1, st));
+  CB_TRY(download_x(p, cur, x_inout, st));
+  if (rj_pending) {
+    CB_CUDA(cudaEventElapsedTime(&ms, p->ev2, p->ev3));
+    rj_ms_total += ms; ++rj_launches;
+  }
+  CB_CUDA(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
+  res->status = status;
+  res->nfev = nfev;
+  res->njev = njev;
+  res->nit = nit;
+  res->cost = cost;
+  res->optimality = gnorm;
+  res->lambda_final = lam;
+  res->pcg_iterations = pcg_total;
+  res->kernel_launches = g_launches.load() - launches0;
+  res->solve_ms = ms;
+  res->rj_ms = rj_ms_total;
+  res->rj_launches = rj_launches;
+  if (opt->verbose >= 1 && opt->rank == 0)
+    std::fprintf(stderr,
+                 "[caliscope_b200] status %d nfev %lld njev %lld nit %lld cost %.15e -> %.15e |g| %.2e  %.3f ms\n", status,
+                 nfev, njev, nit, res->initial_cost, cost, gnorm, ms);
+  return CB_OK;
+}
+
+int choose_pcg_config(CbBaProblem* p) {
+  const int nP = p->nP, P = p->P;
+  const size_t nPa = (size_t)((nP + 7) & ~7);
+  const size_t fixed = (6 * nPa + 32 + (((size_t)(nP / P) * P * P + 7) & ~(size_t)7)) * sizeof(double);
+  int max_optin = 0;
+  cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device);
+  const size_t budget = (size_t)std::max(max_optin, 48 * 1024);
+  cudaFuncSetAttribute(cb::pcg_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  const int cands[5] = {1, 2, 4, 8, 16};
+  for (int pass = 0; pass < 2; ++pass) {  // pass 0: slab in shared memory, pass 1: slab streamed from L2
+    for (int ci = 0; ci < 5; ++ci) {
+      const int cs = cands[ci];
+      if (pass == 1 && cs != 8) continue;
+      const int rows = (nP + cs - 1) / cs;
+      const size_t smem = fixed + (pass == 0 ? (size_t)rows * nP * sizeof(double) : 0);
+      if (smem > budget) continue;
+      if (cudaFuncSetAttribute(cb::pcg_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+          cudaSuccess) {
+        cudaGetLastError();
+        continue;
+      }
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(cs);
+      cfg.blockDim = dim3(cb::PCG_THREADS);
+      cfg.dynamicSmemBytes = smem;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int ncl = 0;
+      if (cudaOccupancyMaxActiveClusters(&ncl, cb::pcg_cluster_kernel, &cfg) != cudaSuccess || ncl < 1) {
+        cudaGetLastError();
+        continue;
+      }
+      p->pcg_cs = cs; p->pcg_rows = rows; p->pcg_slab_smem = (pass == 0); p->pcg_smem = smem;
+      return CB_OK;
+    }
+  }
+  g_last_error = "no feasible PCG cluster configuration for n_camera_params = " + std::to_string(nP);
+  return CB_E_UNSUPPORTED;
+}
+
+}  // namespace
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+extern "C" {
+
+int cb_ba_abi_version(void) { return CB_BA_ABI_VERSION; }
+
+const char* cb_ba_error_string(int code) {
+  switch (code) {
+    case CB_OK: return "ok";
+    case CB_E_INVALID: return "invalid argument";
+    case CB_E_CUDA: return "CUDA runtime error";
+    case CB_E_NO_DEVICE: return "no CUDA device";
+    case CB_E_UNSUPPORTED: return "unsupported configuration";
+    case CB_E_CALLBACK: return "all-reduce callback failed";
+    case CB_E_NOMEM: return "out of device memory";
+    default: return "unknown error";
+  }
+}
+
+const char* cb_ba_last_error(void) { return g_last_error.c_str(); }
+
+void cb_ba_default_options(CbBaOptions* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  o->ftol = 1e-8; o->xtol = 1e-8; o->gtol = 1e-8;
+  o->max_nfev = 0;
+  o->loss = CB_LOSS_LINEAR;
+  o->f_scale = 1.0;
+  o->verbose = 0;
+  o->use_bounds = 1;
+  o->lambda0 = 1e-4;
+  o->pcg_tol = 1e-10;
+  o->pcg_max_iter = 0;
+  o->allreduce = nullptr;
+  o->allreduce_user = nullptr;
+  o->rank = 0;
+  o->world_size = 1;
+}
+
+int64_t cb_ba_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int cb_ba_problem_destroy(CbBaProblem* p) {
+  if (!p) return CB_OK;
+  cudaSetDevice(p->device);
+  for (void* a : p->allocs) cudaFree(a);
+  if (p->h_sc) cudaFreeHost(p->h_sc);
+  if (p->h_x) cudaFreeHost(p->h_x);
+  if (p->ev0) cudaEventDestroy(p->ev0);
+  if (p->ev1) cudaEventDestroy(p->ev1);
+  if (p->ev2) cudaEventDestroy(p->ev2);
+  if (p->ev3) cudaEventDestroy(p->ev3);
+  delete p;
+  return CB_OK;
+}
+
+int64_t cb_ba_problem_n_params(const CbBaProblem* p) { return p ? p->n_params : -1; }
+int cb_ba_cam_stride(const CbBaProblem* p) { return p ? p->P : -1; }
+
+static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_t st, CbBaProblem* p) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    g_last_error = "no CUDA device visible";
+    return CB_E_NO_DEVICE;
+  }
+  if (device < 0 || device >= ndev) { g_last_error = "device index out of range"; return CB_E_INVALID; }
+  CB_CUDA(cudaSetDevice(device));
+  p->device = device;
+  cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, device);
+  p->n_cams = d->n_cams; p->n_pts = d->n_pts; p->n_obs = (int)d->n_obs;
+  p->h_cam_off.assign(p->n_cams + 1, 0);
+  bool any_free = false;
+  for (int c = 0; c < p->n_cams; ++c) {
+    const int f = d->cam_flags[c];
+    if ((f & CB_CAM_FREE_INTRINSICS) && (f & CB_CAM_FISHEYE)) {
+      g_last_error = "fisheye cameras cannot have free intrinsics (bundle_parameterization.py:76-94)";
+      return CB_E_INVALID;
+    }
+    any_free = any_free || (f & CB_CAM_FREE_INTRINSICS);
+    p->h_cam_off[c + 1] = p->h_cam_off[c] + ((f & CB_CAM_FREE_INTRINSICS) ? 9 : 6);
+    if (!(d->cam_const[c * 9] != 0.0)) { g_last_error = "fx_initial must be non-zero"; return CB_E_INVALID; }
+  }
+  p->P = any_free ? 9 : 6;
+  p->nP = p->n_cams * p->P;
+  p->n_params = p->h_cam_off[p->n_cams] + 3 * p->n_pts;
+  p->n_blk = cdiv(p->nP, cb::SY_TILE);
+  p->LD = p->n_blk * cb::SY_TILE;
+  p->n_tiles = p->n_blk * (p->n_blk + 1) / 2;
+  p->K_pad = cdiv(3ll * std::max(p->n_pts, 1), cb::SY_KC) * cb::SY_KC;
+  p->k_chunks = p->K_pad / cb::SY_KC;
+  p->n_split = std::max(1, std::min(p->k_chunks, p->num_sms / std::max(p->n_tiles, 1)));
+  p->pt_blocks = cdiv(std::max(p->n_pts, 1), cb::PT_WARPS);
+
+  const int n = p->n_obs;
+  // tables
+  CB_TRY(palloc(p, &p->d_cam_off, p->n_cams + 1));
+  CB_TRY(palloc(p, &p->d_cam_flags, p->n_cams));
+  CB_TRY(palloc(p, &p->d_cam_const, (size_t)p->n_cams * 9));
+  CB_CUDA(cudaMemcpyAsync(p->d_cam_off, p->h_cam_off.data(), sizeof(int) * (p->n_cams + 1), cudaMemcpyHostToDevice, st));
+  CB_CUDA(cudaMemcpyAsync(p->d_cam_flags, d->cam_flags, sizeof(int) * p->n_cams, cudaMemcpyHostToDevice, st));
+  CB_CUDA(cudaMemcpyAsync(p->d_cam_const, d->cam_const, sizeof(double) * 9 * p->n_cams, cudaMemcpyHostToDevice, st));
+  CB_TRY(palloc(p, &p->d_cm_xy, n)); CB_TRY(palloc(p, &p->d_cm_pt, n)); CB_TRY(palloc(p, &p->d_cm_row, n));
+  CB_TRY(palloc(p, &p->d_cm_orig, n)); CB_TRY(palloc(p, &p->d_cam_start, p->n_cams + 1));
+  CB_TRY(palloc(p, &p->d_cam_chunk_start, p->n_cams + 1));
+  CB_TRY(palloc(p, &p->d_pt_start, p->n_pts + 1)); CB_TRY(palloc(p, &p->d_pm_orig, n));
+  CB_TRY(palloc(p, &p->d_pt_pair_start, p->n_pts + 1));
+  // observation list: host -> device if needed
+  const int *d_cam = d->obs_cam, *d_pt = d->obs_pt;
+  const double* d_xy = d->obs_xy;
+  int *t_cam = nullptr, *t_pt = nullptr;
+  double* t_xy = nullptr;
+  if (!d->obs_on_device) {
+    CB_TRY(dalloc(&t_cam, n)); CB_TRY(dalloc(&t_pt, n)); CB_TRY(dalloc(&t_xy, 2 * (size_t)n));
+    CB_CUDA(cudaMemcpyAsync(t_cam, d->obs_cam, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    CB_CUDA(cudaMemcpyAsync(t_pt, d->obs_pt, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    CB_CUDA(cudaMemcpyAsync(t_xy, d->obs_xy, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, st));
+    d_cam = t_cam; d_pt = t_pt; d_xy = t_xy;
+  }
+  int rc = build_indices(p, d_cam, d_pt, d_xy, st);
+  if (t_cam) { cudaFree(t_cam); cudaFree(t_pt); cudaFree(t_xy); }
+  CB_TRY(rc);
+
+  // Schur tile tables
+  std::vector<int> tI, tJ, tof((size_t)p->n_blk * p->n_blk, -1);
+  for (int I = 0; I < p->n_blk; ++I)
+    for (int J = I; J < p->n_blk; ++J) {
+      tof[(size_t)I * p->n_blk + J] = (int)tI.size();
+      tI.push_back(I); tJ.push_back(J);
+    }
+  CB_TRY(palloc(p, &p->d_tileI, tI.size())); CB_TRY(palloc(p, &p->d_tileJ, tI.size()));
+  CB_TRY(palloc(p, &p->d_tile_of, tof.size()));
+  CB_CUDA(cudaMemcpyAsync(p->d_tileI, tI.data(), sizeof(int) * tI.size(), cudaMemcpyHostToDevice, st));
+  CB_CUDA(cudaMemcpyAsync(p->d_tileJ, tJ.data(), sizeof(int) * tJ.size(), cudaMemcpyHostToDevice, st));
+  CB_CUDA(cudaMemcpyAsync(p->d_tile_of, tof.data(), sizeof(int) * tof.size(), cudaMemcpyHostToDevice, st));
+  std::vector<unsigned char> act((size_t)p->nP, 0);
+  for (int c = 0; c < p->n_cams; ++c)
+    for (int a = 0; a < p->h_cam_off[c + 1] - p->h_cam_off[c]; ++a) act[(size_t)c * p->P + a] = 1;
+  CB_TRY(palloc(p, &p->d_active, p->nP));
+  CB_CUDA(cudaMemcpyAsync(p->d_active, act.data(), p->nP, cudaMemcpyHostToDevice, st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  CB_TRY(palloc(p, &p->d_lo, p->nP)); CB_TRY(palloc(p, &p->d_hi, p->nP));
+
+  // work buffers
+  const int ROWD = (p->P == 6) ? 20 : 28, NACC = (p->P == 6) ? 28 : 55, NU = (p->P == 6) ? 21 : 45;
+  const size_t npts = (size_t)std::max(p->n_pts, 1);
+  CB_TRY(palloc(p, &p->d_x, (size_t)p->n_params + 1));
+  for (int k = 0; k < 2; ++k) { CB_TRY(palloc(p, &p->d_xc[k], p->nP)); CB_TRY(palloc(p, &p->d_xp4[k], 4 * npts)); }
+  CB_TRY(palloc(p, &p->d_camtab, (size_t)p->n_cams * cb::CT_SIZE));
+  CB_TRY(palloc(p, &p->d_jrows, (size_t)std::max(n, 1) * ROWD));
+  CB_TRY(palloc(p, &p->d_partial, (size_t)std::max(p->n_chunks, 1) * NACC));
+  CB_TRY(palloc(p, &p->d_Upk, (size_t)p->n_cams * NU)); CB_TRY(palloc(p, &p->d_gc, p->nP));
+  CB_TRY(palloc(p, &p->d_camcost, p->n_cams)); CB_TRY(palloc(p, &p->d_costsum, 4));
+  CB_TRY(palloc(p, &p->d_V6, 6 * npts)); CB_TRY(palloc(p, &p->d_gp, 3 * npts)); CB_TRY(palloc(p, &p->d_Dp2, 3 * npts));
+  CB_TRY(palloc(p, &p->d_Dc2, p->nP)); CB_TRY(palloc(p, &p->d_Linv6, 6 * npts));
+  CB_TRY(palloc(p, &p->d_tvec, (size_t)p->K_pad));
+  CB_TRY(palloc(p, &p->d_Zt, (size_t)p->K_pad * p->LD));
+  CB_TRY(palloc(p, &p->d_part, (size_t)p->n_split * p->n_tiles * cb::SY_TILE * cb::SY_TILE));
+  CB_TRY(palloc(p, &p->d_tpart, (size_t)p->n_split * p->n_tiles * cb::SY_TILE));
+  CB_TRY(palloc(p, &p->d_red, p->red_len()));
+  CB_TRY(palloc(p, &p->d_Minv, (size_t)p->n_cams * p->P * p->P));
+  CB_TRY(palloc(p, &p->d_dc, p->nP)); CB_TRY(palloc(p, &p->d_dp, 3 * npts));
+  CB_TRY(palloc(p, &p->d_bpart, 3 * (size_t)p->pt_blocks));
+  CB_TRY(palloc(p, &p->d_sc, cb::SC_COUNT)); CB_TRY(palloc(p, &p->d_red2, 8));
+  CB_TRY(palloc(p, &p->d_gmax, 2));
+  CB_TRY(palloc(p, &p->d_out2, 2 * (size_t)std::max(n, 1)));
+  CB_CUDA(cudaMemsetAsync(p->d_Zt, 0, sizeof(double) * (size_t)p->K_pad * p->LD, st));
+  CB_CUDA(cudaMemsetAsync(p->d_tvec, 0, sizeof(double) * p->K_pad, st));
+  CB_CUDA(cudaMemsetAsync(p->d_tpart, 0, sizeof(double) * (size_t)p->n_split * p->n_tiles * cb::SY_TILE, st));
+  CB_CUDA(cudaMemsetAsync(p->d_red2, 0, sizeof(double) * 8, st));
+  CB_CUDA(cudaMemsetAsync(p->d_jrows, 0, sizeof(double) * (size_t)std::max(n, 1) * ROWD, st));
+  CB_CUDA(cudaMallocHost((void**)&p->h_sc, sizeof(double) * (cb::SC_COUNT + 4 + p->red_slots)));
+  CB_CUDA(cudaMallocHost((void**)&p->h_x, sizeof(double) * ((size_t)p->n_params + 1)));
+  CB_CUDA(cudaEventCreate(&p->ev0)); CB_CUDA(cudaEventCreate(&p->ev1));
+  CB_CUDA(cudaEventCreate(&p->ev2)); CB_CUDA(cudaEventCreate(&p->ev3));
+  CB_CUDA(cudaFuncSetAttribute(cb::schur_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)sizeof(cb::SyrkSmem)));
+  CB_TRY(choose_pcg_config(p));
+  CB_CUDA(cudaStreamSynchronize(st));
+  return CB_OK;
+}
+
+int cb_ba_problem_create(const CbBaProblemDesc* d, int device, void* stream, CbBaProblem** out) {
+  if (!d || !out || d->n_cams <= 0 || d->n_pts < 0 || d->n_obs < 0 || d->n_obs > (1ll << 30) || !d->cam_flags ||
+      !d->cam_const || (d->n_obs > 0 && (!d->obs_cam || !d->obs_pt || !d->obs_xy))) {
+    g_last_error = "cb_ba_problem_create: bad descriptor";
+    return CB_E_INVALID;
+  }
+  *out = nullptr;
+  CbBaProblem* p = new CbBaProblem();
+  int rc = problem_create_impl(d, device, (cudaStream_t)stream, p);
+  if (rc != CB_OK) {
+    std::string keep = g_last_error;
+    cb_ba_problem_destroy(p);
+    g_last_error = keep;
+    return rc;
+  }
+  *out = p;
+  return CB_OK;
+}
+
+int cb_ba_solve(CbBaProblem* p, const CbBaOptions* opt, double* x_inout, CbBaResult* result, void* stream) {
+  if (!p || !opt || !x_inout || !result) { g_last_error = "cb_ba_solve: null argument"; return CB_E_INVALID; }
+  if (opt->loss < 0 || opt->loss > CB_LOSS_ARCTAN) { g_last_error = "unknown loss id"; return CB_E_INVALID; }
+  CB_CUDA(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  return p->P == 6 ? lm_solve<6>(p, opt, x_inout, result, st) : lm_solve<9>(p, opt, x_inout, result, st);
+}
+
+}  // extern "C"
+namespace {
+template <int P, int MODE>
+int eval_mode(CbBaProblem* p, const double* x, cudaStream_t st) {
+  CB_TRY(upload_x(p, x, st));
+  CB_TRY(run_cam_prep<P>(p, p->d_xc[0], st));
+  launch_resjac<P, MODE>(p, p->d_xp4[0], 0, 1.0, p->d_out2, st);
+  return CB_OK;
+}
+}  // namespace
+extern "C" {
+
+int cb_ba_residuals(CbBaProblem* p, const double* x, double* r_out, void* stream) {
+  if (!p || !x || !r_out) { g_last_error = "cb_ba_residuals: null argument"; return CB_E_INVALID; }
+  CB_CUDA(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  CB_TRY(p->P == 6 ? (eval_mode<6, 2>(p, x, st)) : (eval_mode<9, 2>(p, x, st)));
+  CB_CUDA(cudaMemcpyAsync(r_out, p->d_out2, sizeof(double) * 2 * (size_t)p->n_obs, cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  return CB_OK;
+}
+
+int cb_ba_reproj_errors_px(CbBaProblem* p, const double* x, double* err_xy, void* stream) {
+  if (!p || !x || !err_xy) { g_last_error = "cb_ba_reproj_errors_px: null argument"; return CB_E_INVALID; }
+  CB_CUDA(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  CB_TRY(p->P == 6 ? (eval_mode<6, 3>(p, x, st)) : (eval_mode<9, 3>(p, x, st)));
+  CB_CUDA(cudaMemcpyAsync(err_xy, p->d_out2, sizeof(double) * 2 * (size_t)p->n_obs, cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  return CB_OK;
+}
+
+int cb_ba_jacobian_blocks(CbBaProblem* p, const double* x, double* Jc, double* Jp, void* stream) {
+  if (!p || !x || !Jc || !Jp) { g_last_error = "cb_ba_jacobian_blocks: null argument"; return CB_E_INVALID; }
+  CB_CUDA(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = p->n_obs;
+  CB_TRY(upload_x(p, x, st));
+  double *dJc, *dJp;
+  CB_TRY(dalloc(&dJc, 18 * (size_t)std::max(n, 1)));
+  CB_TRY(dalloc(&dJp, 6 * (size_t)std::max(n, 1)));
+  if (p->P == 6) {
+    CB_TRY(run_cam_prep<6>(p, p->d_xc[0], st));
+    launch_resjac<6, 0>(p, p->d_xp4[0], 0, 1.0, nullptr, st);
+    if (n) CB_LAUNCH((cb::rows_to_blocks_kernel<6>), cdiv(n, 256), 256, 0, st, p->d_jrows, p->d_pm_orig, n, dJc, dJp);
+  } else {
+    CB_TRY(run_cam_prep<9>(p, p->d_xc[0], st));
+    launch_resjac<9, 0>(p, p->d_xp4[0], 0, 1.0, nullptr, st);
+    if (n) CB_LAUNCH((cb::rows_to_blocks_kernel<9>), cdiv(n, 256), 256, 0, st, p->d_jrows, p->d_pm_orig, n, dJc, dJp);
+  }
+  cudaError_t e1 = cudaMemcpyAsync(Jc, dJc, sizeof(double) * 18 * (size_t)n, cudaMemcpyDeviceToHost, st);
+  cudaError_t e2 = cudaMemcpyAsync(Jp, dJp, sizeof(double) * 6 * (size_t)n, cudaMemcpyDeviceToHost, st);
+  cudaError_t e3 = cudaStreamSynchronize(st);
+  cudaFree(dJc); cudaFree(dJp);
+  CB_CUDA(e1); CB_CUDA(e2); CB_CUDA(e3);
+  return CB_OK;
+}
+
+}  // extern "C"
+namespace {
+template <int P>
+int normal_eq_impl(CbBaProblem* p, const double* x, double lam, int loss, double fs, double* cost, double* U,
+                          double* gc, double* V, double* gp, double* S, double* b, double* dc, double* dp,
+                          cudaStream_t st) {
+  using RT = cb::RowT<P>;
+  CbBaOptions opt;
+  cb_ba_default_options(&opt);
+  CB_TRY(set_bounds(p, false, st));
+  CB_CUDA(cudaMemsetAsync(p->d_Dc2, 0, sizeof(double) * p->nP, st));
+  CB_CUDA(cudaMemsetAsync(p->d_Dp2, 0, sizeof(double) * 3 * (size_t)std::max(p->n_pts, 1), st));
+  CB_TRY(upload_x(p, x, st));
+  CB_TRY(linearize<P>(p, p->d_xc[0], p->d_xp4[0], loss, fs, st, false, nullptr));
+  CB_TRY(build_system<P>(p, lam, true, &opt, st));
+  const size_t nn = (size_t)p->nP * p->nP;
+  std::vector<double> hS(nn + 3 * (size_t)p->nP + 1);
+  CB_CUDA(cudaMemcpyAsync(hS.data(), p->d_red, sizeof(double) * hS.size(), cudaMemcpyDeviceToHost, st));
+  CB_TRY(solve_step<P>(p, lam, 0, &opt, p->d_dp, st));
+  std::vector<double> hU((size_t)p->n_cams * RT::NU), hV(6 * (size_t)std::max(p->n_pts, 1));
+  CB_CUDA(cudaMemcpyAsync(hU.data(), p->d_Upk, sizeof(double) * hU.size(), cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaMemcpyAsync(hV.data(), p->d_V6, sizeof(double) * hV.size(), cudaMemcpyDeviceToHost, st));
+  if (gc) CB_CUDA(cudaMemcpyAsync(gc, p->d_gc, sizeof(double) * p->nP, cudaMemcpyDeviceToHost, st));
+  if (gp) CB_CUDA(cudaMemcpyAsync(gp, p->d_gp, sizeof(double) * 3 * (size_t)p->n_pts, cudaMemcpyDeviceToHost, st));
+  if (dc) CB_CUDA(cudaMemcpyAsync(dc, p->d_dc, sizeof(double) * p->nP, cudaMemcpyDeviceToHost, st));
+  if (dp) CB_CUDA(cudaMemcpyAsync(dp, p->d_dp, sizeof(double) * 3 * (size_t)p->n_pts, cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  if (cost) *cost = hS[nn + 3 * (size_t)p->nP];
+  if (S) std::memcpy(S, hS.data(), sizeof(double) * nn);
+  if (b) std::memcpy(b, hS.data() + nn, sizeof(double) * p->nP);
+  if (U)
+    for (int c = 0; c < p->n_cams; ++c) {
+      int u = 0;
+      for (int a = 0; a < P; ++a)
+        for (int bb = a; bb < P; ++bb, ++u) {
+          U[((size_t)c * P + a) * P + bb] = hU[(size_t)c * RT::NU + u];
+          U[((size_t)c * P + bb) * P + a] = hU[(size_t)c * RT::NU + u];
+        }
+    }
+  if (V)
+    for (int j = 0; j < p->n_pts; ++j) {
+      const double* v = &hV[6 * (size_t)j];
+      double* o = V + 9 * (size_t)j;
+      o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; o[3] = v[1]; o[4] = v[3]; o[5] = v[4]; o[6] = v[2]; o[7] = v[4]; o[8] = v[5];
+    }
+  return CB_OK;
+}
+}  // namespace
+extern "C" {
+
+int cb_ba_normal_equations(CbBaProblem* p, const double* x, double lambda, int32_t loss, double f_scale, double* cost,
+                           double* U, double* gc, double* V, double* gp, double* S, double* b, double* dc, double* dp,
+                           void* stream) {
+  if (!p || !x) { g_last_error = "cb_ba_normal_equations: null argument"; return CB_E_INVALID; }
+  CB_CUDA(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  return p->P == 6 ? normal_eq_impl<6>(p, x, lambda, loss, f_scale, cost, U, gc, V, gp, S, b, dc, dp, st)
+                   : normal_eq_impl<9>(p, x, lambda, loss, f_scale, cost, U, gc, V, gp, S, b, dc, dp, st);
+}
+
+int cb_ba_error_order_stats(CbBaProblem* p, const double* x, double q_percent, double* err, double* lo, double* hi,
+                            int64_t* count, void* stream) {
+  if (!p || !x || !lo || !hi || !count) { g_last_error = "cb_ba_error_order_stats: null argument"; return CB_E_INVALID; }
+  if (!(q_percent >= 0.0 && q_percent <= 100.0)) { g_last_error = "q_percent outside [0, 100]"; return CB_E_INVALID; }
+  CB_CUDA(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = p->n_obs;
+  CB_TRY(p->P == 6 ? (eval_mode<6, 4>(p, x, st)) : (eval_mode<9, 4>(p, x, st)));
+  double *d_lo, *d_hi;
+  long long* d_cnt;
+  CB_TRY(dalloc(&d_lo, p->n_cams)); CB_TRY(dalloc(&d_hi, p->n_cams)); CB_TRY(dalloc(&d_cnt, p->n_cams));
+  CB_LAUNCH(cb::order_stats_kernel, p->n_cams, 256, 0, st, p->d_out2, p->d_cam_start, q_percent / 100.0, d_lo, d_hi,
+            d_cnt);
+  if (err && n) {
+    CB_LAUNCH(cb::cm_to_orig_kernel, cdiv(n, 256), 256, 0, st, p->d_out2, p->d_cm_orig, n, p->d_out2 + n);
+    cudaMemcpyAsync(err, p->d_out2 + n, sizeof(double) * n, cudaMemcpyDeviceToHost, st);
+  }
+  std::vector<long long> hc(p->n_cams);
+  cudaMemcpyAsync(lo, d_lo, sizeof(double) * p->n_cams, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(hi, d_hi, sizeof(double) * p->n_cams, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(hc.data(), d_cnt, sizeof(long long) * p->n_cams, cudaMemcpyDeviceToHost, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(d_lo); cudaFree(d_hi); cudaFree(d_cnt);
+  CB_CUDA(e);
+  for (int c = 0; c < p->n_cams; ++c) count[c] = hc[c];
+  return CB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1010 @@
+// CUDA kernels of the caliscope_b200 bundle-adjustment engine (sm_100a, fp64 throughout).
+//
+// Per LM linearisation (reference analogues in brackets, paths relative to /root/reference):
+//   cam_prep_kernel     Rodrigues + SO(3) right Jacobian + intrinsics per camera
+//                       [bundle_parameterization.py:166-186 trial_projection_inputs]
+//   resjac_kernel       residual + analytic 2x(P+3) Jacobian row per observation, camera-major,
+//                       fused per-camera U = Jc^T Jc, g = Jc^T r and cost accumulation
+//                       [src/caliscope/core/reprojection.py:75-119 and :128-234]
+//   cam_reduce_kernel   chunk partials -> U_c, g_c, cost_c
+//   pt_reduce_kernel    per point V = Jp^T Jp, g = Jp^T r from the point-major Jacobian rows
+//   pt_zbuild_kernel    3x3 damped Cholesky per point, Z = (Jc^T Jp) L^-T scattered to the k-major Zt
+//   schur_syrk_kernel   Z Z^T (+ Z t) with bulk-async (TMA) staged shared-memory tiles, split-K
+//   schur_finalize_kernel  S = U - Z Z^T, b = g_c - Z t into the all-reduce buffer
+//   post_reduce_kernel  Marquardt scaling (running max of diag U, scipy x_scale='jac' analogue,
+//                       site-packages/scipy/optimize/_lsq/common.py:598-610) and damping
+//   block_inverse_kernel / pcg_cluster_kernel   block-Jacobi PCG on the dense reduced system
+//   cam_update_kernel / pt_backsub_kernel       step, bounds clamp, predicted reduction
+//   cost_kernel         trial-point cost only                      [reprojection.py:75-119]
+#pragma once
+#include <cooperative_groups.h>
+
+#include "cb_device.cuh"
+
+namespace cb {
+namespace cg = cooperative_groups;
+
+constexpr int RJ_THREADS = 128;   // resjac / cost block size
+constexpr int RJ_CHUNK = 1024;    // observations per block (all of one camera)
+constexpr int PT_WARPS = 8;       // warps (points) per block in the point-centric kernels
+constexpr int SY_TILE = 96;       // Schur tile edge
+constexpr int SY_KC = 32;         // k rows per pipeline stage
+constexpr int SY_STAGES = 4;
+constexpr int SY_THREADS = 256;
+constexpr int PCG_THREADS = 512;
+
+template <int P>
+struct RowT {
+  static constexpr int NU = P * (P + 1) / 2;
+  static constexpr int NACC = NU + P + 1;                 // U packed, g, cost
+  static constexpr int ROWD = (P == 6) ? 20 : 28;         // doubles per Jacobian row (32 B multiple)
+};
+
+// scalar slots (device double array `sc`)
+enum {
+  SC_COST = 0, SC_GNORM_C, SC_COST_NEW, SC_PRED_C, SC_STEP2_C, SC_X2_C, SC_PRED_P, SC_STEP2_P, SC_X2_P,
+  SC_PCG_ITS, SC_PCG_REL, SC_PCG_FLAG, SC_GNORM_P, SC_COUNT = 16
+};
+
+// ---------------------------------------------------------------------------------------------
+__global__ void unpack_x_kernel(const double* __restrict__ x, const int* __restrict__ cam_off,
+                                const int* __restrict__ cam_flags, const double* __restrict__ cam_const,
+                                int n_cams, int P, int n_pts, double* __restrict__ xc, double* __restrict__ xp4) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int ncp = cam_off[n_cams];
+  if (i < n_cams * P) {
+    int c = i / P, p = i % P;
+    int w = cam_off[c + 1] - cam_off[c];
+    double v;
+    if (p < w) v = x[cam_off[c] + p];
+    else v = (p == 6) ? 1.0 : cam_const[c * 9 + 4 + (p - 7)];  // s = 1, k1_initial, k2_initial
+    xc[i] = v;
+  }
+  if (i < n_pts) {
+    xp4[4 * (size_t)i + 0] = x[ncp + 3 * (size_t)i + 0];
+    xp4[4 * (size_t)i + 1] = x[ncp + 3 * (size_t)i + 1];
+    xp4[4 * (size_t)i + 2] = x[ncp + 3 * (size_t)i + 2];
+    xp4[4 * (size_t)i + 3] = 0.0;
+  }
+}
+
+__global__ void pack_x_kernel(double* __restrict__ x, const int* __restrict__ cam_off, int n_cams, int P, int n_pts,
+                              const double* __restrict__ xc, const double* __restrict__ xp4) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int ncp = cam_off[n_cams];
+  if (i < n_cams * P) {
+    int c = i / P, p = i % P;
+    if (p < cam_off[c + 1] - cam_off[c]) x[cam_off[c] + p] = xc[i];
+  }
+  if (i < n_pts) {
+    x[ncp + 3 * (size_t)i + 0] = xp4[4 * (size_t)i + 0];
+    x[ncp + 3 * (size_t)i + 1] = xp4[4 * (size_t)i + 1];
+    x[ncp + 3 * (size_t)i + 2] = xp4[4 * (size_t)i + 2];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void cam_prep_kernel(const double* __restrict__ xc, const int* __restrict__ cam_flags,
+                                const double* __restrict__ cam_const, int n_cams, int P,
+                                double* __restrict__ camtab) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cams) return;
+  const double* q = xc + (size_t)c * P;
+  const double* k = cam_const + (size_t)c * 9;
+  double* o = camtab + (size_t)c * CT_SIZE;
+  int flags = cam_flags[c];
+  bool free_i = (flags & 1) != 0, fish = (flags & 2) != 0;
+  double r0 = q[0], r1 = q[1], r2 = q[2];
+  double th2 = r0 * r0 + r1 * r1 + r2 * r2, th = sqrt(th2);
+  double R[9];
+  if (th < 1e-12) {
+    R[0] = 1; R[1] = -r2; R[2] = r1; R[3] = r2; R[4] = 1; R[5] = -r0; R[6] = -r1; R[7] = r0; R[8] = 1;
+  } else {
+    double s, co;
+    sincos(th, &s, &co);
+    double it = 1.0 / th, kx = r0 * it, ky = r1 * it, kz = r2 * it, c1 = 1.0 - co;
+    R[0] = co + c1 * kx * kx;      R[1] = c1 * kx * ky - s * kz; R[2] = c1 * kx * kz + s * ky;
+    R[3] = c1 * ky * kx + s * kz;  R[4] = co + c1 * ky * ky;     R[5] = c1 * ky * kz - s * kx;
+    R[6] = c1 * kz * kx - s * ky;  R[7] = c1 * kz * ky + s * kx; R[8] = co + c1 * kz * kz;
+  }
+  double B, C;
+  if (th < 1e-4) {
+    B = 0.5 - th2 / 24.0 + th2 * th2 / 720.0;
+    C = 1.0 / 6.0 - th2 / 120.0 + th2 * th2 / 5040.0;
+  } else {
+    double s, co;
+    sincos(th, &s, &co);
+    B = (1.0 - co) / th2;
+    C = (th - s) / (th2 * th);
+  }
+  // K = [r]x ; K^2 = r r^T - |r|^2 I ; Jr = I - B K + C K^2
+  double K2[9] = {r0 * r0 - th2, r0 * r1, r0 * r2, r1 * r0, r1 * r1 - th2, r1 * r2, r2 * r0, r2 * r1, r2 * r2 - th2};
+  double Km[9] = {0, -r2, r1, r2, 0, -r0, -r1, r0, 0};
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    o[CT_R + i] = R[i];
+    o[CT_JR + i] = ((i % 4 == 0) ? 1.0 : 0.0) - B * Km[i] + C * K2[i];
+  }
+  o[CT_T + 0] = q[3]; o[CT_T + 1] = q[4]; o[CT_T + 2] = q[5];
+  double s = 1.0, k1 = k[4], k2 = k[5];
+  if (free_i) { s = q[6]; k1 = q[7]; k2 = q[8]; }
+  double fx = s * k[0], fy = s * k[1];
+  o[CT_FX] = fx; o[CT_FY] = fy; o[CT_CX] = k[2]; o[CT_CY] = k[3];
+  o[CT_D + 0] = k1; o[CT_D + 1] = k2; o[CT_D + 2] = k[6]; o[CT_D + 3] = k[7]; o[CT_D + 4] = k[8];
+  (void)fish;
+  o[CT_IFX0] = 1.0 / k[0];
+  o[CT_SX] = fx / k[0];
+  o[CT_SY] = fy / k[0];
+  o[CT_FYR] = k[1] / k[0];
+  o[CT_FLAGS] = (double)flags;
+  o[35] = k[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Residual + Jacobian, camera-major.  One block = one chunk of <= RJ_CHUNK observations of ONE
+// camera: the camera table entry is block-uniform (shared memory broadcast) and the per-camera
+// normal-equation blocks reduce in registers -> warp shuffles -> one partial per chunk.
+//
+// MODE 0: write the scaled Jacobian row [r(2) | Jp(2x3) | Jc(2xP)] at the observation's point-major
+//         slot (full 32-byte sectors, STG.256) and accumulate U_c, g_c, cost.
+// MODE 1: cost only (trial point).
+// MODE 2: raw residuals to out2[orig*2]      (== joint_residuals order)
+// MODE 3: pixel errors to out2[orig*2]       (== reprojection_errors)
+// MODE 4: euclidean pixel error to out2[q]   (camera-major, for the percentile filter)
+// ---------------------------------------------------------------------------------------------
+template <int P, int MODE>
+__global__ void __launch_bounds__(RJ_THREADS)
+resjac_kernel(const int* __restrict__ chunk_cam, const int* __restrict__ chunk_begin,
+              const int* __restrict__ chunk_end, const double2* __restrict__ cm_xy,
+              const int* __restrict__ cm_pt, const int* __restrict__ cm_row, const int* __restrict__ cm_orig,
+              const double* __restrict__ camtab, const double* __restrict__ xp4, int loss, double fscale,
+              double* __restrict__ jrows, double* __restrict__ partial, double* __restrict__ out2) {
+  using RT = RowT<P>;
+  __shared__ double cam[CT_SIZE];
+  __shared__ double red[(MODE == 0 ? RT::NACC : 1) * (RJ_THREADS / 32)];
+  const int chunk = blockIdx.x;
+  const int c = chunk_cam[chunk];
+  const int begin = chunk_begin[chunk], end = chunk_end[chunk];
+  if (threadIdx.x < CT_SIZE) cam[threadIdx.x] = camtab[(size_t)c * CT_SIZE + threadIdx.x];
+  __syncthreads();
+  const int flags = (int)cam[CT_FLAGS];
+  const bool fish = (flags & 2) != 0;
+  const bool free_i = (P == 9) && (flags & 1) != 0;
+
+  double acc[(MODE == 0) ? RT::NACC : 1];
+#pragma unroll
+  for (int k = 0; k < ((MODE == 0) ? RT::NACC : 1); ++k) acc[k] = 0.0;
+
+  for (int q = begin + threadIdx.x; q < end; q += RJ_THREADS) {
+    const double2 xy = cm_xy[q];
+    const int pt = cm_pt[q];
+    double X0, X1, X2, X3;
+    ld256nc(xp4 + 4 * (size_t)pt, X0, X1, X2, X3);
+    ProjOut o;
+    project_obs<MODE == 0>(cam, fish, X0, X1, X2, o);
+    const double ex = o.u - xy.x, ey = o.v - xy.y;
+    if constexpr (MODE == 3) {
+      const size_t i = (size_t)cm_orig[q];
+      out2[2 * i] = ex; out2[2 * i + 1] = ey;
+      continue;
+    }
+    if constexpr (MODE == 4) {
+      out2[q] = sqrt(ex * ex + ey * ey);
+      continue;
+    }
+    double f0 = ex * cam[CT_IFX0], f1 = ey * cam[CT_IFX0];
+    if constexpr (MODE == 2) {
+      const size_t i = (size_t)cm_orig[q];
+      out2[2 * i] = f0; out2[2 * i + 1] = f1;
+      continue;
+    }
+    if constexpr (MODE == 1) {
+      acc[0] += robust_cost_only(loss, fscale, f0) + robust_cost_only(loss, fscale, f1);
+      continue;
+    }
+    if constexpr (MODE == 0) {
+      double w0, w1;
+      acc[RT::NACC - 1] += robust_row(loss, fscale, f0, w0) + robust_row(loss, fscale, f1, w1);
+      // d(u,v)/dXc / fx0, rows scaled by the robust weights
+      const double sx = cam[CT_SX] * o.iz * w0, sy = cam[CT_SY] * o.iz * w1;
+      double Jt[6];
+      Jt[0] = sx * o.xa; Jt[1] = sx * o.xb; Jt[2] = -(Jt[0] * o.a + Jt[1] * o.b);
+      Jt[3] = sy * o.ya; Jt[4] = sy * o.yb; Jt[5] = -(Jt[3] * o.a + Jt[4] * o.b);
+      const double* R = cam + CT_R;
+      double JX[6];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          JX[3 * i + k] = Jt[3 * i] * R[k] + Jt[3 * i + 1] * R[3 + k] + Jt[3 * i + 2] * R[6 + k];
+      double Jc[2 * P];
+      const double* Jr = cam + CT_JR;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        // (J_X,i x X) Jr, negated
+        const double a0 = JX[3 * i], a1 = JX[3 * i + 1], a2 = JX[3 * i + 2];
+        const double c0 = a1 * X2 - a2 * X1, c1 = a2 * X0 - a0 * X2, c2 = a0 * X1 - a1 * X0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) Jc[P * i + k] = -(c0 * Jr[k] + c1 * Jr[3 + k] + c2 * Jr[6 + k]);
+        Jc[P * i + 3] = Jt[3 * i]; Jc[P * i + 4] = Jt[3 * i + 1]; Jc[P * i + 5] = Jt[3 * i + 2];
+      }
+      if constexpr (P == 9) {
+        if (free_i) {
+          const double ar2 = cam[CT_SX] * o.a * o.r2 * w0, br2 = cam[CT_SY] * o.b * o.r2 * w1;
+          Jc[6] = o.xd * w0;                 Jc[P + 6] = cam[CT_FYR] * o.yd * w1;
+          Jc[7] = ar2;                       Jc[P + 7] = br2;
+          Jc[8] = ar2 * o.r2;                Jc[P + 8] = br2 * o.r2;
+        } else {
+          Jc[6] = Jc[7] = Jc[8] = 0.0;
+          Jc[P + 6] = Jc[P + 7] = Jc[P + 8] = 0.0;
+        }
+      }
+      // U (packed upper), g
+      int u = 0;
+#pragma unroll
+      for (int a = 0; a < P; ++a)
+#pragma unroll
+        for (int b = a; b < P; ++b) {
+          acc[u] = fma(Jc[a], Jc[b], fma(Jc[P + a], Jc[P + b], acc[u]));
+          ++u;
+        }
+#pragma unroll
+      for (int a = 0; a < P; ++a) acc[RT::NU + a] = fma(Jc[a], f0, fma(Jc[P + a], f1, acc[RT::NU + a]));
+      // row store
+      double* dst = jrows + (size_t)cm_row[q] * RT::ROWD;
+      st256(dst, f0, f1, JX[0], JX[1]);
+      st256(dst + 4, JX[2], JX[3], JX[4], JX[5]);
+      if constexpr (P == 6) {
+        st256(dst + 8, Jc[0], Jc[1], Jc[2], Jc[3]);
+        st256(dst + 12, Jc[4], Jc[5], Jc[6], Jc[7]);
+        st256(dst + 16, Jc[8], Jc[9], Jc[10], Jc[11]);
+      } else {
+        st256(dst + 8, Jc[0], Jc[1], Jc[2], Jc[3]);
+        st256(dst + 12, Jc[4], Jc[5], Jc[6], Jc[7]);
+        st256(dst + 16, Jc[8], Jc[9], Jc[10], Jc[11]);
+        st256(dst + 20, Jc[12], Jc[13], Jc[14], Jc[15]);
+        st256(dst + 24, Jc[16], Jc[17], 0.0, 0.0);
+      }
+    }
+  }
+  if constexpr (MODE == 0 || MODE == 1) {
+    constexpr int NA = (MODE == 0) ? RT::NACC : 1;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NA; ++k) {
+      double v = warp_sum(acc[k]);
+      if (lane == 0) red[wid * NA + k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NA) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < RJ_THREADS / 32; ++w) v += red[w * NA + threadIdx.x];
+      partial[(size_t)chunk * NA + threadIdx.x] = v;
+    }
+  }
+}
+
+// chunk partials -> per-camera packed U, g, cost
+template <int P>
+__global__ void cam_reduce_kernel(const int* __restrict__ cam_chunk_start, const double* __restrict__ partial,
+                                  double* __restrict__ Upk, double* __restrict__ gc, double* __restrict__ cam_cost) {
+  using RT = RowT<P>;
+  const int c = blockIdx.x, k = threadIdx.x;
+  if (k >= RT::NACC) return;
+  double v = 0.0;
+  for (int ch = cam_chunk_start[c]; ch < cam_chunk_start[c + 1]; ++ch) v += partial[(size_t)ch * RT::NACC + k];
+  if (k < RT::NU) Upk[(size_t)c * RT::NU + k] = v;
+  else if (k < RT::NU + P) gc[(size_t)c * P + (k - RT::NU)] = v;
+  else cam_cost[c] = v;
+}
+
+// deterministic single-block sum of n doubles -> out[0]
+__global__ void sum_kernel(const double* __restrict__ in, int n, double* __restrict__ out) {
+  __shared__ double sh[32];
+  double v = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v += in[i];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) out[0] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// point-centric: V_j = sum Jp^T Jp (6 unique), gp_j = sum Jp^T r ; one warp per point
+// ---------------------------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(PT_WARPS * 32)
+pt_reduce_kernel(const int* __restrict__ pt_start, int n_pts, const double* __restrict__ jrows,
+                 double* __restrict__ V6, double* __restrict__ gp, double* __restrict__ Dp2,
+                 unsigned long long* __restrict__ gmax_bits) {
+  using RT = RowT<P>;
+  __shared__ double wmax[PT_WARPS];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int j = blockIdx.x * PT_WARPS + wid;
+  double gm = 0.0;
+  if (j < n_pts) {
+    const int s = pt_start[j], e = pt_start[j + 1];
+    double v[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) v[k] = 0.0;
+    for (int row = s + lane; row < e; row += 32) {
+      const double* src = jrows + (size_t)row * RT::ROWD;
+      double f0, f1, a0, a1, a2, b0, b1, b2;
+      ld256(src, f0, f1, a0, a1);
+      ld256(src + 4, a2, b0, b1, b2);
+      v[0] += a0 * a0 + b0 * b0; v[1] += a0 * a1 + b0 * b1; v[2] += a0 * a2 + b0 * b2;
+      v[3] += a1 * a1 + b1 * b1; v[4] += a1 * a2 + b1 * b2; v[5] += a2 * a2 + b2 * b2;
+      v[6] += a0 * f0 + b0 * f1; v[7] += a1 * f0 + b1 * f1; v[8] += a2 * f0 + b2 * f1;
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) v[k] = warp_sum(v[k]);
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) V6[(size_t)j * 6 + k] = v[k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) gp[(size_t)j * 3 + k] = v[6 + k];
+      double* d = Dp2 + (size_t)j * 3;
+      d[0] = fmax(d[0], v[0]); d[1] = fmax(d[1], v[3]); d[2] = fmax(d[2], v[5]);
+      gm = fmax(fabs(v[6]), fmax(fabs(v[7]), fabs(v[8])));
+    }
+  }
+  if (lane == 0) wmax[wid] = gm;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = 0.0;
+    for (int w = 0; w < PT_WARPS; ++w) m = fmax(m, wmax[w]);
+    if (m > 0.0) atomicMax(gmax_bits, (unsigned long long)__double_as_longlong(m));
+  }
+}
+
+// 3x3 SPD: E = V + lam * D ; L = chol(E) ; returns Linv (lower, packed 00,10,11,20,21,22); zero if not PD
+__device__ __forceinline__ void chol3_inv(const double* V6, const double* D2, double lam, double* Li) {
+  const double d0 = D2[0] > 0.0 ? D2[0] : 1.0, d1 = D2[1] > 0.0 ? D2[1] : 1.0, d2 = D2[2] > 0.0 ? D2[2] : 1.0;
+  const double e00 = V6[0] + lam * d0, e01 = V6[1], e02 = V6[2], e11 = V6[3] + lam * d1, e12 = V6[4],
+               e22 = V6[5] + lam * d2;
+  bool ok = e00 > 0.0;
+  const double l00 = sqrt(ok ? e00 : 1.0);
+  const double l10 = e01 / l00, l20 = e02 / l00;
+  const double t11 = e11 - l10 * l10;
+  ok = ok && t11 > 0.0;
+  const double l11 = sqrt(ok ? t11 : 1.0);
+  const double l21 = (e12 - l20 * l10) / l11;
+  const double t22 = e22 - l20 * l20 - l21 * l21;
+  ok = ok && t22 > 0.0;
+  const double l22 = sqrt(ok ? t22 : 1.0);
+  const double i00 = 1.0 / l00, i11 = 1.0 / l11, i22 = 1.0 / l22;
+  const double i10 = -l10 * i00 * i11;
+  const double i21 = -l21 * i11 * i22;
+  const double i20 = -(l20 * i00 + l21 * i10) * i22;
+  if (ok) {
+    Li[0] = i00; Li[1] = i10; Li[2] = i11; Li[3] = i20; Li[4] = i21; Li[5] = i22;
+  } else {
+    Li[0] = Li[1] = Li[2] = Li[3] = Li[4] = Li[5] = 0.0;
+  }
+}
+
+// per point: Linv, t = Linv gp ; per (point, camera) pair: W = sum_rows Jc^T Jp, Z = W Linv^T -> Zt
+template <int P>
+__global__ void __launch_bounds__(PT_WARPS * 32)
+pt_zbuild_kernel(const int* __restrict__ pt_pair_start, const int* __restrict__ pair_start,
+                 const int* __restrict__ pair_cam, int n_pts, const double* __restrict__ jrows,
+                 const double* __restrict__ V6, const double* __restrict__ gp, const double* __restrict__ Dp2,
+                 double lam, double* __restrict__ Linv6, double* __restrict__ tvec, double* __restrict__ Zt,
+                 size_t LD) {
+  using RT = RowT<P>;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int j = blockIdx.x * PT_WARPS + wid;
+  if (j >= n_pts) return;
+  double Li[6];
+  chol3_inv(V6 + (size_t)j * 6, Dp2 + (size_t)j * 3, lam, Li);
+  if (lane == 0) {
+    const double g0 = gp[(size_t)j * 3], g1 = gp[(size_t)j * 3 + 1], g2 = gp[(size_t)j * 3 + 2];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) Linv6[(size_t)j * 6 + k] = Li[k];
+    tvec[3 * (size_t)j + 0] = Li[0] * g0;
+    tvec[3 * (size_t)j + 1] = Li[1] * g0 + Li[2] * g1;
+    tvec[3 * (size_t)j + 2] = Li[3] * g0 + Li[4] * g1 + Li[5] * g2;
+  }
+  const int ps = pt_pair_start[j], pe = pt_pair_start[j + 1];
+  for (int q = ps + lane; q < pe; q += 32) {
+    double W[P * 3];
+#pragma unroll
+    for (int k = 0; k < P * 3; ++k) W[k] = 0.0;
+    for (int row = pair_start[q]; row < pair_start[q + 1]; ++row) {
+      const double* src = jrows + (size_t)row * RT::ROWD;
+      double v[RT::ROWD];
+#pragma unroll
+      for (int k = 0; k < RT::ROWD; k += 4) ld256(src + k, v[k], v[k + 1], v[k + 2], v[k + 3]);
+      // v: [f0 f1 | Jp0(3) Jp1(3) | Jc0(P) Jc1(P)]
+#pragma unroll
+      for (int p = 0; p < P; ++p)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) W[p * 3 + a] = fma(v[8 + p], v[2 + a], fma(v[8 + P + p], v[5 + a], W[p * 3 + a]));
+    }
+    double* z0 = Zt + (3 * (size_t)j) * LD + (size_t)pair_cam[q] * P;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      z0[p] = W[p * 3] * Li[0];
+      z0[LD + p] = W[p * 3] * Li[1] + W[p * 3 + 1] * Li[2];
+      z0[2 * LD + p] = W[p * 3] * Li[3] + W[p * 3 + 1] * Li[4] + W[p * 3 + 2] * Li[5];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Schur product  part[split][tile] = A_I^T A_J  over a slab of k rows (k = 3*point + axis), where
+// Zt is k-major: Zt[k][col], col = camera*P + p.  Tiles are staged through shared memory with
+// 1-D bulk async copies (TMA engine, mbarrier completion), SY_STAGES deep; each thread owns a
+// 6x6 register tile.  Diagonal tiles also accumulate Z t (the reduced right-hand side).
+// ---------------------------------------------------------------------------------------------
+struct SyrkSmem {
+  double A[SY_STAGES][SY_KC * SY_TILE];
+  double B[SY_STAGES][SY_KC * SY_TILE];
+  double t[SY_STAGES][SY_KC];
+  unsigned long long full[SY_STAGES];
+};
+
+__global__ void __launch_bounds__(SY_THREADS, 1)
+schur_syrk_kernel(const double* __restrict__ Zt, size_t LD, const double* __restrict__ tvec, int n_chunks,
+                  int n_split, const int* __restrict__ tileI, const int* __restrict__ tileJ, int n_tiles,
+                  double* __restrict__ part, double* __restrict__ tpart) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SyrkSmem& sm = *reinterpret_cast<SyrkSmem*>(smem_raw);
+  const int tile = blockIdx.x / n_split, split = blockIdx.x % n_split;
+  const int I = tileI[tile], J = tileJ[tile];
+  const bool diag = (I == J);
+  const int c0 = (int)(((long long)n_chunks * split) / n_split);
+  const int c1 = (int)(((long long)n_chunks * (split + 1)) / n_split);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int ty = tid >> 4, tx = tid & 15;
+
+  if (tid == 0) {
+    for (int s = 0; s < SY_STAGES; ++s) mbar_init(&sm.full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const uint32_t tile_bytes = SY_KC * SY_TILE * 8;
+  const uint32_t stage_bytes = tile_bytes * (diag ? 1u : 2u) + (diag ? SY_KC * 8u : 0u);
+  auto issue = [&](int chunk, int stage) {
+    // called by warp 0 only
+    if (lane == 0) mbar_expect_tx(&sm.full[stage], stage_bytes);
+    __syncwarp();
+    const size_t k = (size_t)chunk * SY_KC + lane;
+    bulk_g2s(&sm.A[stage][lane * SY_TILE], Zt + k * LD + (size_t)I * SY_TILE, SY_TILE * 8, &sm.full[stage]);
+    if (!diag)
+      bulk_g2s(&sm.B[stage][lane * SY_TILE], Zt + k * LD + (size_t)J * SY_TILE, SY_TILE * 8, &sm.full[stage]);
+    else if (lane == 0)
+      bulk_g2s(&sm.t[stage][0], tvec + (size_t)chunk * SY_KC, SY_KC * 8, &sm.full[stage]);
+  };
+
+  double acc[6][6];
+#pragma unroll
+  for (int u = 0; u < 6; ++u)
+#pragma unroll
+    for (int v = 0; v < 6; ++v) acc[u][v] = 0.0;
+  double tacc = 0.0;
+
+  if (wid == 0)
+    for (int s = 0; s < SY_STAGES - 1 && c0 + s < c1; ++s) issue(c0 + s, s);
+
+  for (int c = c0; c < c1; ++c) {
+    const int it = c - c0, stage = it % SY_STAGES;
+    mbar_wait(&sm.full[stage], (uint32_t)((it / SY_STAGES) & 1));
+    const double* As = sm.A[stage];
+    const double* Bs = diag ? sm.A[stage] : sm.B[stage];
+#pragma unroll 4
+    for (int k = 0; k < SY_KC; ++k) {
+      const double2* ap = reinterpret_cast<const double2*>(As + k * SY_TILE + ty * 6);
+      const double2* bp = reinterpret_cast<const double2*>(Bs + k * SY_TILE + tx * 6);
+      const double2 a01 = ap[0], a23 = ap[1], a45 = ap[2];
+      const double2 b01 = bp[0], b23 = bp[1], b45 = bp[2];
+      const double a[6] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y};
+      const double b[6] = {b01.x, b01.y, b23.x, b23.y, b45.x, b45.y};
+#pragma unroll
+      for (int u = 0; u < 6; ++u)
+#pragma unroll
+        for (int v = 0; v < 6; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+    }
+    if (diag && tid < SY_TILE) {
+#pragma unroll 8
+      for (int k = 0; k < SY_KC; ++k) tacc = fma(As[k * SY_TILE + tid], sm.t[stage][k], tacc);
+    }
+    __syncthreads();
+    if (wid == 0) {
+      const int nc = c + SY_STAGES - 1;
+      if (nc < c1) issue(nc, (it + SY_STAGES - 1) % SY_STAGES);
+    }
+  }
+  double* out = part + ((size_t)split * n_tiles + tile) * (SY_TILE * SY_TILE);
+#pragma unroll
+  for (int u = 0; u < 6; ++u)
+#pragma unroll
+    for (int v = 0; v < 6; ++v) out[(ty * 6 + u) * SY_TILE + tx * 6 + v] = acc[u][v];
+  if (diag && tid < SY_TILE) tpart[((size_t)split * n_tiles + tile) * SY_TILE + tid] = tacc;
+}
+
+// red = [ S (nP*nP) | b (nP) | gc (nP) | diagU (nP) | cost | gpmax slots ... ]   (local partials)
+template <int P>
+__global__ void schur_finalize_kernel(int nP, int n_blk, int n_tiles, int n_split, const int* __restrict__ tile_of,
+                                      const double* __restrict__ part, const double* __restrict__ tpart,
+                                      const double* __restrict__ Upk, const double* __restrict__ gc,
+                                      const double* __restrict__ cam_cost_sum, double* __restrict__ red) {
+  using RT = RowT<P>;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t nn = (size_t)nP * nP;
+  if (idx < nn) {
+    const int i = (int)(idx / nP), j = (int)(idx % nP);
+    int I = i / SY_TILE, J = j / SY_TILE, li = i % SY_TILE, lj = j % SY_TILE;
+    if (I > J) { int t = I; I = J; J = t; t = li; li = lj; lj = t; }
+    const int tile = tile_of[I * n_blk + J];
+    double s = 0.0;
+    for (int sp = 0; sp < n_split; ++sp) s += part[((size_t)sp * n_tiles + tile) * (SY_TILE * SY_TILE) + li * SY_TILE + lj];
+    double u = 0.0;
+    const int ci = i / P, cj = j / P;
+    if (ci == cj) {
+      int a = i % P, b = j % P;
+      if (a > b) { int t = a; a = b; b = t; }
+      u = Upk[(size_t)ci * RT::NU + (a * P - a * (a - 1) / 2 + (b - a))];
+    }
+    red[idx] = u - s;
+  } else if (idx < nn + (size_t)nP) {
+    const int i = (int)(idx - nn);
+    const int I = i / SY_TILE, li = i % SY_TILE;
+    const int tile = tile_of[I * n_blk + I];
+    double s = 0.0;
+    for (int sp = 0; sp < n_split; ++sp) s += tpart[((size_t)sp * n_tiles + tile) * SY_TILE + li];
+    red[nn + i] = gc[i] - s;
+    red[nn + nP + i] = gc[i];
+    const int c = i / P, a = i % P;
+    red[nn + 2 * (size_t)nP + i] = Upk[(size_t)c * RT::NU + (a * P - a * (a - 1) / 2)];
+  } else if (idx == nn + (size_t)nP) {
+    red[nn + 3 * (size_t)nP] = cam_cost_sum[0];
+  }
+}
+
+// after the all-reduce: Marquardt scaling (running max of diag U), damping, camera gradient norm
+__global__ void post_reduce_kernel(int nP, double lam, int update_scale, double* __restrict__ red,
+                                   double* __restrict__ Dc2, const unsigned char* __restrict__ active,
+                                   double* __restrict__ sc) {
+  __shared__ double sh[32];
+  const size_t nn = (size_t)nP * nP;
+  double gm = 0.0;
+  for (int i = threadIdx.x; i < nP; i += blockDim.x) {
+    double d = Dc2[i];
+    if (update_scale) { d = fmax(d, red[nn + 2 * (size_t)nP + i]); Dc2[i] = d; }
+    red[(size_t)i * nP + i] += lam * (d > 0.0 ? d : 1.0);
+    if (active[i]) gm = fmax(gm, fabs(red[nn + nP + i]));
+  }
+  gm = warp_max(gm);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = gm;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, sh[w]);
+    sc[SC_GNORM_C] = m;
+    sc[SC_COST] = red[nn + 3 * (size_t)nP];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// block-Jacobi preconditioner: inverse of each camera's P x P diagonal block of S (packed symmetric)
+// ---------------------------------------------------------------------------------------------
+template <int P>
+__global__ void block_inverse_kernel(const double* __restrict__ S, int nP, int n_cams, double* __restrict__ Minv) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cams) return;
+  double A[P][P], Li[P][P];
+  for (int i = 0; i < P; ++i)
+    for (int j = 0; j < P; ++j) A[i][j] = S[(size_t)(c * P + i) * nP + c * P + j];
+  bool ok = true;
+  // in-place Cholesky (lower)
+  for (int j = 0; j < P; ++j) {
+    double d = A[j][j];
+    for (int k = 0; k < j; ++k) d -= A[j][k] * A[j][k];
+    if (!(d > 0.0)) { ok = false; d = 1.0; }
+    d = sqrt(d);
+    A[j][j] = d;
+    for (int i = j + 1; i < P; ++i) {
+      double s = A[i][j];
+      for (int k = 0; k < j; ++k) s -= A[i][k] * A[j][k];
+      A[i][j] = s / d;
+    }
+  }
+  // Li = L^-1 (lower)
+  for (int j = 0; j < P; ++j) {
+    Li[j][j] = 1.0 / A[j][j];
+    for (int i = j + 1; i < P; ++i) {
+      double s = 0.0;
+      for (int k = j; k < i; ++k) s -= A[i][k] * Li[k][j];
+      Li[i][j] = s / A[i][i];
+    }
+  }
+  double* out = Minv + (size_t)c * P * P;
+  for (int i = 0; i < P; ++i)
+    for (int j = 0; j < P; ++j) {
+      double s = 0.0;
+      if (ok) {
+        for (int k = (i > j ? i : j); k < P; ++k) s += Li[k][i] * Li[k][j];
+      } else {
+        const double d = S[(size_t)(c * P + i) * nP + c * P + i];
+        s = (i == j) ? (d > 0.0 ? 1.0 / d : 1.0) : 0.0;
+      }
+      out[i * P + j] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// PCG on the dense reduced camera system S x = -b, one thread-block cluster.  Each CTA owns a
+// slab of rows of S (kept in shared memory when it fits), computes its slice of q = S p and
+// writes it into every CTA's q buffer through distributed shared memory; all vector updates and
+// dot products are then done redundantly by every CTA, so one cluster barrier per iteration.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum_512(double v, double* sh) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();  // protect sh reuse
+  if (lane == 0) sh[wid] = v;
+  __syncthreads();
+  double t = (lane < (PCG_THREADS >> 5)) ? sh[lane] : 0.0;
+  t = warp_sum(t);
+  return t;  // same value in every thread
+}
+
+__global__ void __launch_bounds__(PCG_THREADS, 1)
+pcg_cluster_kernel(const double* __restrict__ S, const double* __restrict__ bvec, const double* __restrict__ Minv,
+                   int nP, int P, int rows_per, int slab_in_smem, double tol2, int max_iter,
+                   double* __restrict__ xout, double* __restrict__ sc) {
+  extern __shared__ __align__(16) double psm[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  // layout: x r z p q0 q1 (nPa each) | sh[32] | Minv (n_cams*P*P) | slab
+  const int nPa = (nP + 7) & ~7;
+  double* vx = psm;
+  double* vr = vx + nPa;
+  double* vz = vr + nPa;
+  double* vp = vz + nPa;
+  double* vq = vp + nPa;  // two buffers
+  double* sh = vq + 2 * nPa;
+  double* Mi = sh + 32;
+  double* slab = Mi + (((size_t)(nP / P) * P * P + 7) & ~(size_t)7);
+  const int row0 = rank * rows_per;
+  const int nrows = max(0, min(rows_per, nP - row0));
+  const int n_cams = nP / P;
+
+  for (int i = tid; i < n_cams * P * P; i += PCG_THREADS) Mi[i] = Minv[i];
+  if (slab_in_smem)
+    for (size_t i = tid; i < (size_t)nrows * nP; i += PCG_THREADS) slab[i] = S[(size_t)row0 * nP + i];
+  const double* Srows = slab_in_smem ? slab : (S + (size_t)row0 * nP);
+  for (int i = tid; i < nP; i += PCG_THREADS) {
+    vx[i] = 0.0;
+    vr[i] = -bvec[i];
+  }
+  __syncthreads();
+  for (int i = tid; i < nP; i += PCG_THREADS) {
+    const int c = i / P, a = i % P;
+    double s = 0.0;
+    for (int b = 0; b < P; ++b) s += Mi[(size_t)c * P * P + a * P + b] * vr[c * P + b];
+    vz[i] = s;
+    vp[i] = s;
+  }
+  __syncthreads();
+  double part = 0.0;
+  for (int i = tid; i < nP; i += PCG_THREADS) part += vr[i] * vz[i];
+  double rz = block_sum_512(part, sh);
+  const double rz0 = rz;
+  int it = 0, flag = 0;
+  cluster.sync();
+  if (rz0 > 0.0) {
+    for (it = 0; it < max_iter; ++it) {
+      double* q = vq + (it & 1) * nPa;
+      // q_slab = S_slab p : one warp per row
+      for (int r = wid; r < nrows; r += PCG_THREADS / 32) {
+        const double* srow = Srows + (size_t)r * nP;
+        double s = 0.0;
+        for (int k = lane; k < nP; k += 32) s = fma(srow[k], vp[k], s);
+        s = warp_sum(s);
+        if (lane < csize) {
+          double* dst = cluster.map_shared_rank(q, lane);
+          dst[row0 + r] = s;
+        }
+      }
+      cluster.sync();
+      part = 0.0;
+      for (int i = tid; i < nP; i += PCG_THREADS) part += vp[i] * q[i];
+      const double pq = block_sum_512(part, sh);
+      if (!(pq > 0.0)) { flag = 1; break; }
+      const double alpha = rz / pq;
+      for (int i = tid; i < nP; i += PCG_THREADS) {
+        vx[i] = fma(alpha, vp[i], vx[i]);
+        vr[i] = fma(-alpha, q[i], vr[i]);
+      }
+      __syncthreads();
+      part = 0.0;
+      for (int i = tid; i < nP; i += PCG_THREADS) {
+        const int c = i / P, a = i % P;
+        double s = 0.0;
+        for (int b = 0; b < P; ++b) s += Mi[(size_t)c * P * P + a * P + b] * vr[c * P + b];
+        vz[i] = s;
+        part += vr[i] * s;
+      }
+      const double rz_new = block_sum_512(part, sh);
+      if (!(rz_new == rz_new)) { flag = 2; break; }
+      if (rz_new <= tol2 * rz0) { rz = rz_new; ++it; break; }
+      const double beta = rz_new / rz;
+      rz = rz_new;
+      for (int i = tid; i < nP; i += PCG_THREADS) vp[i] = fma(beta, vp[i], vz[i]);
+      __syncthreads();
+    }
+  }
+  cluster.sync();  // nobody exits while peers may still write into its q buffers
+  if (rank == 0) {
+    for (int i = tid; i < nP; i += PCG_THREADS) xout[i] = vx[i];
+    if (tid == 0) {
+      sc[SC_PCG_ITS] = (double)it;
+      sc[SC_PCG_REL] = (rz0 > 0.0) ? sqrt(fabs(rz) / rz0) : 0.0;
+      sc[SC_PCG_FLAG] = (double)flag;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// camera step: bounds clamp, effective step written back to dc, predicted reduction (camera part)
+// ---------------------------------------------------------------------------------------------
+__global__ void cam_update_kernel(int nP, double lam, const double* __restrict__ xc, double* __restrict__ dc,
+                                  const double* __restrict__ lo, const double* __restrict__ hi,
+                                  const double* __restrict__ gc_total, const double* __restrict__ Dc2,
+                                  const unsigned char* __restrict__ active, double* __restrict__ xc_new,
+                                  double* __restrict__ sc) {
+  __shared__ double sh[3][32];
+  double pred = 0.0, st2 = 0.0, x2 = 0.0;
+  for (int i = threadIdx.x; i < nP; i += blockDim.x) {
+    const double x = xc[i];
+    double xn = x + dc[i];
+    xn = fmin(fmax(xn, lo[i]), hi[i]);
+    if (!active[i]) xn = x;
+    const double de = xn - x;
+    dc[i] = de;
+    xc_new[i] = xn;
+    if (active[i]) {
+      const double d = Dc2[i] > 0.0 ? Dc2[i] : 1.0;
+      pred += 0.5 * de * (lam * d * de - gc_total[i]);
+      st2 += de * de;
+      x2 += x * x;
+    }
+  }
+  pred = warp_sum(pred); st2 = warp_sum(st2); x2 = warp_sum(x2);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { sh[0][wid] = pred; sh[1][wid] = st2; sh[2][wid] = x2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0, c = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += sh[0][w]; b += sh[1][w]; c += sh[2][w]; }
+    sc[SC_PRED_C] = a; sc[SC_STEP2_C] = b; sc[SC_X2_C] = c;
+  }
+}
+
+// point back-substitution: dp = -Linv^T (t + Zt_rows dc), one warp per point; block partial sums
+__global__ void __launch_bounds__(PT_WARPS * 32)
+pt_backsub_kernel(int n_pts, int nP, double lam, const double* __restrict__ Zt, size_t LD,
+                  const double* __restrict__ dc, const double* __restrict__ Linv6, const double* __restrict__ tvec,
+                  const double* __restrict__ gp, const double* __restrict__ Dp2, const double* __restrict__ xp4,
+                  double* __restrict__ xp4_new, double* __restrict__ dp_out, double* __restrict__ bpart) {
+  extern __shared__ double dcs[];
+  __shared__ double wsum[3][PT_WARPS];
+  for (int i = threadIdx.x; i < nP; i += blockDim.x) dcs[i] = dc[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int j = blockIdx.x * PT_WARPS + wid;
+  double pred = 0.0, st2 = 0.0, x2 = 0.0;
+  if (j < n_pts) {
+    const double* z = Zt + 3 * (size_t)j * LD;
+    double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+    for (int k = lane; k < nP; k += 32) {
+      const double d = dcs[k];
+      u0 = fma(z[k], d, u0);
+      u1 = fma(z[LD + k], d, u1);
+      u2 = fma(z[2 * LD + k], d, u2);
+    }
+    u0 = warp_sum(u0); u1 = warp_sum(u1); u2 = warp_sum(u2);
+    if (lane == 0) {
+      const double* Li = Linv6 + (size_t)j * 6;
+      const double v0 = tvec[3 * (size_t)j] + u0, v1 = tvec[3 * (size_t)j + 1] + u1, v2 = tvec[3 * (size_t)j + 2] + u2;
+      const double d0 = -(Li[0] * v0 + Li[1] * v1 + Li[3] * v2);
+      const double d1 = -(Li[2] * v1 + Li[4] * v2);
+      const double d2 = -(Li[5] * v2);
+      const double* xo = xp4 + 4 * (size_t)j;
+      double* xn = xp4_new + 4 * (size_t)j;
+      xn[0] = xo[0] + d0; xn[1] = xo[1] + d1; xn[2] = xo[2] + d2; xn[3] = 0.0;
+      if (dp_out) { dp_out[3 * (size_t)j] = d0; dp_out[3 * (size_t)j + 1] = d1; dp_out[3 * (size_t)j + 2] = d2; }
+      const double* D = Dp2 + 3 * (size_t)j;
+      const double* g = gp + 3 * (size_t)j;
+      const double e0 = D[0] > 0.0 ? D[0] : 1.0, e1 = D[1] > 0.0 ? D[1] : 1.0, e2 = D[2] > 0.0 ? D[2] : 1.0;
+      pred = 0.5 * (d0 * (lam * e0 * d0 - g[0]) + d1 * (lam * e1 * d1 - g[1]) + d2 * (lam * e2 * d2 - g[2]));
+      st2 = d0 * d0 + d1 * d1 + d2 * d2;
+      x2 = xo[0] * xo[0] + xo[1] * xo[1] + xo[2] * xo[2];
+    }
+  }
+  if (lane == 0) { wsum[0][wid] = pred; wsum[1][wid] = st2; wsum[2][wid] = x2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0, c = 0;
+    for (int w = 0; w < PT_WARPS; ++w) { a += wsum[0][w]; b += wsum[1][w]; c += wsum[2][w]; }
+    bpart[blockIdx.x] = a;
+    bpart[gridDim.x + blockIdx.x] = b;
+    bpart[2 * (size_t)gridDim.x + blockIdx.x] = c;
+  }
+}
+
+// three deterministic sums of n values each (laid out back to back) -> out[0..2]
+__global__ void sum3_kernel(const double* __restrict__ in, int n, double* __restrict__ out) {
+  __shared__ double sh[32];
+  const double* src = in + (size_t)blockIdx.x * n;
+  double v = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v += src[i];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) out[blockIdx.x] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// index building helpers (setup)
+// ---------------------------------------------------------------------------------------------
+__global__ void make_keys_kernel(const int* __restrict__ a, const int* __restrict__ b, long long nb, int n,
+                                 unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    keys[i] = (unsigned long long)a[i] * (unsigned long long)nb + (unsigned long long)b[i];
+    vals[i] = i;
+  }
+}
+// sorted keys = major*nb + minor -> major/minor arrays
+__global__ void split_keys_kernel(const unsigned long long* __restrict__ keys, long long nb, int n,
+                                  int* __restrict__ major, int* __restrict__ minor) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    major[i] = (int)(keys[i] / (unsigned long long)nb);
+    minor[i] = (int)(keys[i] % (unsigned long long)nb);
+  }
+}
+// start[j] = first index i with sorted_major[i] >= j, j in [0, nbins]
+__global__ void lower_bound_kernel(const int* __restrict__ sorted_major, int n, int nbins, int* __restrict__ start) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > nbins) return;
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (sorted_major[mid] < j) lo = mid + 1; else hi = mid;
+  }
+  start[j] = lo;
+}
+__global__ void pair_flag_kernel(const unsigned long long* __restrict__ keys, int n, int* __restrict__ flag) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+__global__ void pair_scatter_kernel(const int* __restrict__ flag, const int* __restrict__ pidx, int n,
+                                    const int* __restrict__ pm_cam, int* __restrict__ pair_start,
+                                    int* __restrict__ pair_cam, int n_pairs) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && flag[i]) {
+    pair_start[pidx[i]] = i;
+    pair_cam[pidx[i]] = pm_cam[i];
+  }
+  if (i == 0) pair_start[n_pairs] = n;
+}
+__global__ void pt_pair_start_kernel(const int* __restrict__ pt_start, const int* __restrict__ pidx, int n_pts, int n,
+                                     int n_pairs, int* __restrict__ pt_pair_start) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j <= n_pts) {
+    int s = pt_start[j];
+    pt_pair_start[j] = (s < n) ? pidx[s] : n_pairs;
+  }
+}
+// camera-major gather: q -> row (point-major slot) -> original observation
+__global__ void cm_gather_kernel(const int* __restrict__ cm_row, const int* __restrict__ pm_orig,
+                                 const int* __restrict__ pm_pt, const double2* __restrict__ obs_xy, int n,
+                                 int* __restrict__ cm_pt, int* __restrict__ cm_orig, double2* __restrict__ cm_xy) {
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) {
+    const int row = cm_row[q];
+    const int o = pm_orig[row];
+    cm_pt[q] = pm_pt[row];
+    cm_orig[q] = o;
+    cm_xy[q] = obs_xy[o];
+  }
+}
+__global__ void validate_kernel(const int* __restrict__ cam, const int* __restrict__ pt, int n, int n_cams, int n_pts,
+                                int* __restrict__ bad) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && (cam[i] < 0 || cam[i] >= n_cams || pt[i] < 0 || pt[i] >= n_pts)) atomicAdd(bad, 1);
+}
+
+// Jacobian rows (point-major) -> caller-order dense blocks Jc (n_obs,2,9), Jp (n_obs,2,3)
+template <int P>
+__global__ void rows_to_blocks_kernel(const double* __restrict__ jrows, const int* __restrict__ pm_orig, int n,
+                                      double* __restrict__ Jc, double* __restrict__ Jp) {
+  using RT = RowT<P>;
+  int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  const double* v = jrows + (size_t)row * RT::ROWD;
+  const size_t o = (size_t)pm_orig[row];
+  for (int k = 0; k < 6; ++k) Jp[o * 6 + k] = v[2 + k];
+  for (int i = 0; i < 2; ++i)
+    for (int p = 0; p < 9; ++p) Jc[o * 18 + i * 9 + p] = (p < P) ? v[8 + i * P + p] : 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-camera order statistics of non-negative doubles (camera-major, contiguous per camera):
+// 8-bit radix select on the IEEE bit pattern, one block per camera, two ranks per call
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+order_stats_kernel(const double* __restrict__ err_cm, const int* __restrict__ cam_start, double qfrac,
+                   double* __restrict__ lo_out, double* __restrict__ hi_out, long long* __restrict__ cnt_out) {
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned long long s_prefix;
+  __shared__ long long s_k;
+  const int c = blockIdx.x;
+  const int s = cam_start[c], e = cam_start[c + 1];
+  const long long n = e - s;
+  if (threadIdx.x == 0) cnt_out[c] = n;
+  if (n == 0) {
+    if (threadIdx.x == 0) { lo_out[c] = 0.0; hi_out[c] = 0.0; }
+    return;
+  }
+  const double vidx = (double)(n - 1) * qfrac;
+  long long klo = (long long)floor(vidx);
+  if (klo < 0) klo = 0;
+  if (klo > n - 1) klo = n - 1;
+  long long khi = klo + 1 < n ? klo + 1 : n - 1;
+  for (int which = 0; which < 2; ++which) {
+    if (threadIdx.x == 0) { s_prefix = 0ull; s_k = which ? khi : klo; }
+    __syncthreads();
+    for (int pass = 7; pass >= 0; --pass) {
+      hist[threadIdx.x] = 0u;
+      __syncthreads();
+      const unsigned long long prefix = s_prefix;
+      const int shift = 8 * pass;
+      for (int i = s + threadIdx.x; i < e; i += 256) {
+        const unsigned long long key = (unsigned long long)__double_as_longlong(err_cm[i]);
+        const bool match = (pass == 7) || ((key >> (shift + 8)) == prefix);
+        if (match) atomicAdd(&hist[(unsigned)((key >> shift) & 0xffull)], 1u);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        long long k = s_k;
+        int b = 0;
+        for (; b < 256; ++b) {
+          if (k < (long long)hist[b]) break;
+          k -= hist[b];
+        }
+        s_k = k;
+        s_prefix = (prefix << 8) | (unsigned long long)b;
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      const double v = __longlong_as_double((long long)s_prefix);
+      if (which) hi_out[c] = v; else lo_out[c] = v;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void cm_to_orig_kernel(const double* __restrict__ in_cm, const int* __restrict__ cm_orig, int n,
+                                  double* __restrict__ out) {
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) out[cm_orig[q]] = in_cm[q];
+}
+
+}  // namespace cb

@@ -1,0 +1,173 @@
+/*
+ * caliscope_b200 -- C ABI of the B200 bundle-adjustment engine.
+ *
+ * Drop-in boundary for the bundle-adjustment hot path of mprib/caliscope.  The
+ * reference has no FFI; its seam is the Python call
+ *     scipy.optimize.least_squares(joint_residuals, x0, args=(...), jac=joint_jacobian, ...)
+ * at /root/reference/src/caliscope/core/capture_volume.py:387-411 (inside
+ * CaptureVolume.optimize, :322-444).  The entry points below are what a ctypes
+ * binding behind that seam calls; INTEGRATION.md shows the stub.
+ *
+ * Conventions: plain pointers and sizes, fp64, row-major, no exceptions cross the
+ * ABI.  Every function returns 0 on success or a negative CB_E_* code;
+ * cb_ba_error_string() gives the text, cb_ba_last_error() the detail (CUDA error
+ * string) of the most recent failure on the calling thread.
+ *
+ * Parameter vector layout == BundleParameterization.pack
+ * (/root/reference/src/caliscope/core/bundle_parameterization.py:127-149):
+ *   x = [block_0 | ... | block_{n_cams-1} | X_0 | X_1 | ...],
+ *   block_i = [rvec(3), tvec(3)] (+ [s, k1, k2] iff cam_flags[i] & CB_CAM_FREE_INTRINSICS),
+ *   X_j = xyz of world point j.
+ */
+#ifndef CALISCOPE_B200_H
+#define CALISCOPE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB_BA_ABI_VERSION 1
+
+/* cam_flags bits (CameraBlock.free_intrinsics / .fisheye, bundle_parameterization.py:36-51) */
+#define CB_CAM_FREE_INTRINSICS 1
+#define CB_CAM_FISHEYE 2
+
+/* loss ids: scipy.optimize.least_squares(loss=...) as forwarded by capture_volume.py:405 */
+#define CB_LOSS_LINEAR 0
+#define CB_LOSS_SOFT_L1 1
+#define CB_LOSS_HUBER 2
+#define CB_LOSS_CAUCHY 3
+#define CB_LOSS_ARCTAN 4
+
+/* error codes */
+#define CB_OK 0
+#define CB_E_INVALID (-1)      /* bad argument (null pointer, index out of range, ...) */
+#define CB_E_CUDA (-2)         /* CUDA runtime failure; see cb_ba_last_error() */
+#define CB_E_NO_DEVICE (-3)    /* no usable CUDA device */
+#define CB_E_UNSUPPORTED (-4)  /* feature not implemented by this build */
+#define CB_E_CALLBACK (-5)     /* the all-reduce callback reported failure */
+#define CB_E_NOMEM (-6)
+
+typedef struct CbBaProblem CbBaProblem; /* opaque, device resident */
+
+/*
+ * Problem description == the args tuple CaptureVolume.optimize hands to scipy
+ * (capture_volume.py:390-399) plus BundleParameterization.blocks flattened.
+ *   cam_const[i*9 + 0..8] = fx_initial, fy_initial, cx, cy, c4..c8 where
+ *     Brown-Conrady: (c4..c8) = (k1_initial, k2_initial, p1, p2, k3)
+ *     fisheye      : (c4..c7) = (k1, k2, k3, k4), c8 unused
+ *   obs_cam  = camera_indices          (capture_volume.py:353-355; int16 there, int32 here)
+ *   obs_pt   = image_to_world_indices  (capture_volume.py:358)
+ *   obs_xy   = image_coords            (capture_volume.py:357), n_obs x 2
+ * obs_* may be host pointers (obs_on_device = 0; copied inside the call) or device
+ * pointers on `device` (obs_on_device = 1).  Inputs are never modified.
+ */
+typedef struct {
+  int32_t n_cams;
+  int32_t n_pts;
+  int64_t n_obs;
+  const int32_t* cam_flags; /* host, n_cams */
+  const double* cam_const;  /* host, n_cams*9 */
+  const int32_t* obs_cam;
+  const int32_t* obs_pt;
+  const double* obs_xy;
+  int32_t obs_on_device;
+} CbBaProblemDesc;
+
+/*
+ * Sum-all-reduce hook for observation sharding (one process per GPU).  Called on
+ * the host thread inside cb_ba_solve with a DEVICE buffer of n doubles that must be
+ * summed element-wise across ranks in place, ordered after all work already queued
+ * on `stream` and before any work queued afterwards (torch.distributed.all_reduce on
+ * the current stream satisfies this).  Return 0 on success.
+ */
+typedef int (*CbAllReduceSum)(void* user, double* device_buf, int64_t n, void* stream);
+
+/* least_squares keyword arguments the reference passes (capture_volume.py:403-410)
+ * plus scipy's defaults for the ones it leaves out (xtol = gtol = 1e-8). */
+typedef struct {
+  double ftol;
+  double xtol;
+  double gtol;
+  int64_t max_nfev; /* <= 0: scipy's default 100 * n */
+  int32_t loss;     /* CB_LOSS_* */
+  double f_scale;
+  int32_t verbose;     /* 0 silent, 1 summary, 2 per-iteration table on stderr */
+  int32_t use_bounds;  /* 1: s in [0.5,2], k1 in [-1,1], k2 in [-2,2] (bundle_parameterization.py:151-164) */
+  double lambda0;      /* initial LM damping; <= 0: 1e-4 */
+  double pcg_tol;      /* relative PCG tolerance for the reduced camera system; <= 0: 1e-10 */
+  int32_t pcg_max_iter; /* <= 0: 4 * n_camera_params */
+  CbAllReduceSum allreduce; /* NULL: single GPU */
+  void* allreduce_user;
+  int32_t rank;       /* informational (verbose output only on rank 0) */
+  int32_t world_size; /* 1 if allreduce is NULL */
+} CbBaOptions;
+
+/* mirrors scipy.optimize.OptimizeResult fields the reference reads
+ * (capture_volume.py:413-433): status, nfev, cost; plus njev/nit/optimality. */
+typedef struct {
+  int32_t status; /* scipy codes: 0 max_nfev, 1 gtol, 2 ftol, 3 xtol, 4 ftol&xtol */
+  int64_t nfev;
+  int64_t njev;
+  int64_t nit;       /* LM iterations (linearisations solved) */
+  double cost;       /* 0.5 * sum rho(f^2), scipy's definition */
+  double initial_cost;
+  double optimality; /* inf-norm of the gradient at the solution */
+  double lambda_final;
+  int64_t pcg_iterations; /* total PCG iterations over the solve */
+  int64_t kernel_launches;
+  double solve_ms; /* device time of the LM loop (CUDA events on the solve stream) */
+  double rj_ms;    /* total device time spent in the residual+Jacobian kernel */
+  int64_t rj_launches;
+} CbBaResult;
+
+int cb_ba_abi_version(void);
+const char* cb_ba_error_string(int code);
+const char* cb_ba_last_error(void);
+void cb_ba_default_options(CbBaOptions* opt);
+
+/* Upload + index build (sort by camera / by point, chunk and pair tables). */
+int cb_ba_problem_create(const CbBaProblemDesc* desc, int device, void* stream, CbBaProblem** out);
+int cb_ba_problem_destroy(CbBaProblem* p);
+int64_t cb_ba_problem_n_params(const CbBaProblem* p);
+
+/* Replaces least_squares(joint_residuals, x0, jac=joint_jacobian, method="trf", ...)
+ * (capture_volume.py:387-411).  x_inout: host, n_params doubles, overwritten with result.x. */
+int cb_ba_solve(CbBaProblem* p, const CbBaOptions* opt, double* x_inout, CbBaResult* result, void* stream);
+
+/* == joint_residuals (reprojection.py:75-119), reprojection rows only: r_out host, 2*n_obs,
+ * interleaved (x, y) / fx_initial in the caller's observation order. */
+int cb_ba_residuals(CbBaProblem* p, const double* x, double* r_out, void* stream);
+
+/* Dense blocks of joint_jacobian (reprojection.py:171-205) in the caller's observation order:
+ * Jc host n_obs*2*9 (columns rvec3, tvec3, s, k1, k2; zeros where a block is locked),
+ * Jp host n_obs*2*3; both already divided by fx_initial. */
+int cb_ba_jacobian_blocks(CbBaProblem* p, const double* x, double* Jc, double* Jp, void* stream);
+
+/* == reprojection_errors (reprojection.py:35-72): pixel errors with the intrinsics in x. err_xy host n_obs*2. */
+int cb_ba_reproj_errors_px(CbBaProblem* p, const double* x, double* err_xy, void* stream);
+
+/* Test/diagnostic access to one damped linearisation (all host outputs, any may be NULL):
+ * U n_cams*P*P, gc n_cams*P, V n_pts*9, gp n_pts*3, S (n_cams*P)^2, b n_cams*P,
+ * dc n_cams*P (PCG solution of S dc = -b), dp n_pts*3 (back-substituted), with P = cb_ba_cam_stride(). */
+int cb_ba_cam_stride(const CbBaProblem* p);
+int cb_ba_normal_equations(CbBaProblem* p, const double* x, double lambda, int32_t loss, double f_scale,
+                           double* cost, double* U, double* gc, double* V, double* gp, double* S, double* b,
+                           double* dc, double* dp, void* stream);
+
+/* Per-camera order statistics of the pixel error norm for the percentile filter
+ * (capture_volume.py:709-753): for camera c with n_c observations, lo[c] / hi[c] are the
+ * floor / ceil order statistics of rank (n_c - 1) * q / 100 (numpy's linear interpolation
+ * nodes), count[c] = n_c; err host n_obs (euclidean error per observation, caller order). */
+int cb_ba_error_order_stats(CbBaProblem* p, const double* x, double q_percent, double* err, double* lo,
+                            double* hi, int64_t* count, void* stream);
+
+/* Number of kernel launches issued by this library in the calling process so far. */
+int64_t cb_ba_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CALISCOPE_B200_H */
