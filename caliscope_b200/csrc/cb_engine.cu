@@ -734,7 +734,12 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
 }
 
 int cb_ba_problem_create(const CbBaProblemDesc* d, int device, void* stream, CbBaProblem** out) {
-  if (!d || !out || d->n_cams <= 0 || d->n_pts < 0 || d->n_obs < 0 || d->n_obs > (1ll << 30) || !d->cam_flags ||
+  if (d && d->n_obs == 0) {
+    // CaptureVolume._validate_geometry (capture_volume.py:97-98) rejects this before optimize() can run
+    g_last_error = "No image observations provided";
+    return CB_E_INVALID;
+  }
+  if (!d || !out || d->n_cams <= 0 || d->n_pts <= 0 || d->n_obs < 0 || d->n_obs > (1ll << 30) || !d->cam_flags ||
       !d->cam_const || (d->n_obs > 0 && (!d->obs_cam || !d->obs_pt || !d->obs_xy))) {
     g_last_error = "cb_ba_problem_create: bad descriptor";
     return CB_E_INVALID;
