@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""Bundle-adjustment benchmark (BASELINE.json metric: LM iterations/s on the 64-cam / 50k-point /
+2M-observation rig, final RMS reprojection px).
+
+    python bench.py --gpus N --steps K --warmup W          # caliscope_b200 (CUDA, sm_100a)
+    python bench.py --impl reference --steps K --warmup W  # scipy TRF on the CPU oracle port
+
+A "step" is one complete bundle-adjustment solve of the synthetic rig from the same perturbed
+start: W untimed solves, then exactly K timed solves bracketed by barrier + synchronize, device
+time from CUDA events, max over ranks.  ``value`` has the observation list resident in HBM;
+``e2e`` goes through the public API with pinned HOST buffers (problem upload + index build +
+solve + result download inside the timed region).  N > 1 shards the observations by point with
+one all-reduce of the reduced camera system per LM trial (strong scaling: the rig is fixed).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+METRIC = "lm_iterations_per_sec"
+UNIT = "LM iterations/s"
+
+WORKLOADS = {
+    # name: (n_cams, n_pts, n_obs, refine_intrinsics)
+    "cfg4": (64, 50_000, 2_000_000, False),
+    "cfg4_intrinsics": (64, 50_000, 2_000_000, True),
+    "cfg3": (16, 10_000, 400_000, True),
+    "cfg2": (8, 2_000, 40_000, False),
+}
+
+
+def make_workload(name: str):
+    from caliscope_b200 import synthetic
+
+    n_cams, n_pts, n_obs, refine = WORKLOADS[name]
+    return synthetic.make_rig(n_cams, n_pts, n_obs, refine_intrinsics=refine, seed=0, name=name)
+
+
+def workload_config(name: str, rig, n_gpus: int) -> dict:
+    n_cams, n_pts, n_obs, refine = WORKLOADS[name]
+    return {
+        "workload": f"{name}: synthetic {n_cams}-cam / {n_pts}-point / {n_obs}-observation ring rig, "
+        + ("extrinsics + focal scale + k1 + k2" if refine else "extrinsics only")
+        + ", seed 0, 0.5 px noise (BASELINE.json configs[3])",
+        "n_cams": n_cams,
+        "n_pts": n_pts,
+        "n_obs": n_obs,
+        "n_params": int(len(rig.x0)),
+        "loss": "linear",
+        "ftol": 1e-8,
+        "sharding": "single GPU" if n_gpus == 1 else f"observations sharded by point over {n_gpus} GPUs, "
+        "one NCCL all-reduce of the reduced camera system per LM trial",
+        "l2": "per-iteration working set (Jacobian rows + Schur factor, >500 MB) exceeds the 126 MB L2; no explicit flush",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = (
+        "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+        "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    )
+
+    def __init__(self, gpu_index: int = 0):
+        self.rows: list[list[str]] = []
+        self.proc = None
+        self.gpu = gpu_index
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )  # fmt: skip
+        except Exception:
+            self.proc = None
+            return
+
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {
+            "sm_mhz": float(np.median(sm)) if sm else None,
+            "sm_max_mhz": float(max(smax)) if smax else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the reference's solver call on the oracle port
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step(rig, max_nfev: int):
+    """scipy.optimize.least_squares(method='trf', x_scale='jac', jac=<sparse analytic>) exactly as
+    capture_volume.py:387-411, on the NumPy restatement of joint_residuals/joint_jacobian."""
+    from oracle import ba_oracle as O
+
+    orc = O.Rig(rig.cam_flags, rig.cam_const, rig.n_pts, rig.obs_cam, rig.obs_pt, rig.obs_xy)
+    t0 = time.perf_counter()
+    res = O.solve_scipy(orc, rig.x0, max_nfev=max_nfev if max_nfev and max_nfev > 0 else None)
+    dt = time.perf_counter() - t0
+    nit = max(int(res.nit), 1) if res.nfev > 1 else 1
+    return {"wall_s": dt, "nit": nit, "nfev": int(res.nfev), "njev": int(res.njev), "status": int(res.status),
+            "cost": float(res.cost), "rmse_px": O.overall_rmse_px(res.x, orc)}  # fmt: skip
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rig = make_workload(args.workload)
+    small = make_workload("cfg2")
+    for _ in range(args.warmup):
+        cpu_reference_step(small, 3)
+    budget_s = args.ref_budget_s
+    steps, its, wall, last = 0, 0, 0.0, None
+    for _ in range(args.steps):
+        last = cpu_reference_step(rig, args.ref_max_nfev)
+        steps += 1
+        its += last["nit"]
+        wall += last["wall_s"]
+        if wall > budget_s:
+            break
+    value = its / wall
+    cores = os.cpu_count()
+    sample = (
+        f"{args.workload} full rig, scipy TRF+LSMR "
+        + (f"capped at max_nfev={args.ref_max_nfev}" if args.ref_max_nfev > 0 else "run to convergence (ftol 1e-8)")
+        + f" per step ({last['nit']} LM iteration(s), nfev {last['nfev']}, {last['wall_s']:.1f} s each); "
+        f"{steps} of {args.steps} requested steps "
+        f"timed within the {budget_s:.0f} s budget; warm-up on cfg2"
+    )
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": args.gpus,
+        "steps": steps,
+        "warmup": args.warmup,
+        "ms_per_step": 1e3 * wall / steps,
+        "higher_is_better": True,
+        "scaling": "strong",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": workload_config(args.workload, rig, 1),
+        "obs_residuals_per_sec": rig.n_obs * last["nfev"] / last["wall_s"],
+        "final_rms_px": last["rmse_px"],
+        "gpu_launches": 0,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# the CUDA arm
+# ------------------------------------------------------------------------------------------------
+def algorithmic_bytes_rj(rig) -> int:
+    """n_obs*(24 + 16 + 16*Pc + 48) + 24*n_pts + 8*sum_c(Pc + 9)."""
+    pc = np.where(rig.cam_flags & 1, 9, 6)
+    P = int(pc.max())
+    return int(rig.n_obs * (24 + 16 + 16 * P + 48) + 24 * rig.n_pts + 8 * int((pc + 9).sum()))
+
+
+def load_peaks() -> tuple[float, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_ncu_traffic(workload: str):
+    p = ROOT / "profiles" / "resjac_ncu_summary.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            if d.get("workload") == workload:
+                return d.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    return None
+
+
+def run_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    import caliscope_b200 as cb
+    from caliscope_b200 import distributed as D
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = local_rank if world > 1 else 0
+    torch.cuda.set_device(dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    rig = make_workload(args.workload)
+    ncp = int(np.where(rig.cam_flags & 1, 9, 6).sum())
+    if world > 1:
+        shard = D.shard_points(rig.obs_cam, rig.obs_pt, rig.obs_xy, rig.n_pts, rank, world)
+        l_cam, l_pt, l_xy, l_npts = shard.obs_cam, shard.obs_pt, shard.obs_xy, shard.n_pts
+        x0 = D.local_x(rig.x0, ncp, shard)
+        hook = D.make_allreduce_hook()
+    else:
+        shard = None
+        l_cam, l_pt, l_xy, l_npts = rig.obs_cam, rig.obs_pt, rig.obs_xy, rig.n_pts
+        x0 = rig.x0
+        hook = None
+    solve_kw = dict(ftol=1e-8, allreduce=hook, rank=rank, world_size=world, stream=stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident arm: observation list already in HBM --------------------------------
+    d_cam = torch.from_numpy(l_cam).cuda()
+    d_pt = torch.from_numpy(l_pt).cuda()
+    d_xy = torch.from_numpy(np.ascontiguousarray(l_xy)).cuda()
+    prob = cb.BAProblem(rig.cam_flags, rig.cam_const, l_npts, d_cam, d_pt, d_xy, device=dev, stream=stream)
+    res = None
+    for _ in range(args.warmup):
+        res = prob.solve(x0, **solve_kw)
+    sampler = ClockSampler(dev)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    launches0 = cb._lib.load().cb_ba_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    nit = nfev = 0
+    rj_ms = 0.0
+    rj_n = 0
+    for _ in range(args.steps):
+        res = prob.solve(x0, **solve_kw)
+        nit += res.nit
+        nfev += res.nfev
+        rj_ms += res.rj_ms
+        rj_n += res.rj_launches
+    e1.record()
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = cb._lib.load().cb_ba_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    x_final = res.x
+    if world > 1:
+        x_final = D.gather_points(res.x, ncp, rig.n_pts, shard)
+    prob.close()
+
+    # ---- end-to-end arm: pinned host buffers, upload + index build + solve + download ---------
+    h_cam = torch.from_numpy(l_cam).pin_memory().numpy()
+    h_pt = torch.from_numpy(l_pt).pin_memory().numpy()
+    h_xy = torch.from_numpy(np.ascontiguousarray(l_xy)).pin_memory().numpy()
+
+    def e2e_step():
+        with cb.BAProblem(rig.cam_flags, rig.cam_const, l_npts, h_cam, h_pt, h_xy, device=dev, stream=stream) as p2:
+            return p2.solve(x0, **solve_kw)
+
+    for _ in range(min(args.warmup, 3)):
+        e2e_step()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t1 = time.perf_counter()
+    f0.record()
+    e2e_nit = 0
+    for _ in range(args.steps):
+        e2e_nit += e2e_step().nit
+    f1.record()
+    barrier()
+    e2e_wall_ms = 1e3 * (time.perf_counter() - t1)
+    e2e_ms = max_over_ranks(max(f0.elapsed_time(f1), e2e_wall_ms))
+    h2d = int(l_cam.nbytes + l_pt.nbytes + l_xy.nbytes + x0.nbytes + rig.cam_flags.nbytes + rig.cam_const.nbytes)
+    d2h = int(x0.nbytes + 8 * 32)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- parity and baselines (rank 0) ----------------------------------------------------------
+    from oracle import ba_oracle as O
+
+    orc = O.Rig(rig.cam_flags, rig.cam_const, rig.n_pts, rig.obs_cam, rig.obs_pt, rig.obs_xy)
+    rms_px = O.overall_rmse_px(x_final, orc)
+    peak, peak_src = load_peaks()
+    rj_bytes = algorithmic_bytes_rj(rig) / world  # each rank's launch covers its shard
+    rj_avg_ms = rj_ms / max(rj_n, 1)
+    achieved = rj_bytes / (rj_avg_ms * 1e-3) / 1e9 if rj_avg_ms > 0 else 0.0
+    line = {
+        "metric": METRIC,
+        "value": nit / (dev_ms * 1e-3),
+        "unit": UNIT,
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps,
+        "higher_is_better": True,
+        "scaling": "strong",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": workload_config(args.workload, rig, world),
+        "clocks": clocks,
+        "e2e": {
+            "value": e2e_nit / (e2e_ms * 1e-3),
+            "unit": UNIT,
+            "ms_per_step": e2e_ms / args.steps,
+            "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h,
+        },
+        "gpu_launches": int(launches),
+        "obs_residuals_per_sec": rig.n_obs * nfev / (dev_ms * 1e-3),
+        "lm_iterations_per_step": nit / args.steps,
+        "nfev_per_step": nfev / args.steps,
+        "ms_per_lm_iteration": dev_ms / max(nit, 1),
+        "wall_ms_per_step": wall_ms / args.steps,
+        "final_rms_px": rms_px,
+        "final_cost": res.cost,
+        "status": res.status,
+        "roofline": {
+            "kernel": "resjac_kernel<P,0> (residual + analytic Jacobian rows + per-camera J^T J)",
+            "bound": "hbm",
+            "achieved": achieved,
+            "peak": peak,
+            "unit": "GB/s",
+            "frac": achieved / peak,
+            "traffic": load_ncu_traffic(args.workload),
+            "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": rj_bytes,
+            "avg_launch_ms": rj_avg_ms,
+            "launches_timed": int(rj_n),
+        },
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_step(rig, args.ref_max_nfev)
+        line["cpu_baseline"] = {
+            "value": cpu["nit"] / cpu["wall_s"],
+            "unit": UNIT,
+            "cores": os.cpu_count(),
+            "kind": "port",
+            "sample": f"{args.workload} full rig, one scipy TRF+LSMR solve on the NumPy oracle port "
+            + (f"capped at max_nfev={args.ref_max_nfev}" if args.ref_max_nfev > 0 else "to convergence (ftol 1e-8)")
+            + f": {cpu['nit']} LM iteration(s), nfev {cpu['nfev']}, {cpu['wall_s']:.1f} s "
+            "(scipy.sparse matvec/LSMR are single-threaded)",
+            "final_rms_px": cpu["rmse_px"],
+            "final_cost": cpu["cost"],
+            "obs_residuals_per_sec": rig.n_obs * cpu["nfev"] / cpu["wall_s"],
+        }
+        if args.ref_max_nfev <= 0:
+            line["parity"] = {"rms_px_gpu": rms_px, "rms_px_scipy": cpu["rmse_px"],
+                              "abs_diff_px": abs(rms_px - cpu["rmse_px"]), "bar_px": 1e-6}  # fmt: skip
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg4")
+    ap.add_argument("--ref-max-nfev", type=int, default=0, help="cap on scipy evaluations per reference step (0: run to convergence)")
+    ap.add_argument("--ref-budget-s", type=float, default=240.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
