@@ -1,0 +1,111 @@
+"""GPU-backed mirror of /root/reference/src/caliscope/core/reprojection.py.
+
+Same function names and signatures (``project_points`` :18-32, ``reprojection_errors`` :35-72,
+``joint_residuals`` :75-119, ``joint_jacobian`` :128-234); every number comes from the CUDA
+engine through the C ABI -- there is no NumPy/OpenCV computation path here.
+Distance-constraint rows (reprojection.py:112-117, 207-226) are not implemented on the GPU yet
+and raise ``NotImplementedError``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .problem import BAProblem, blocks_to_arrays
+
+_CACHE: dict = {"key": None, "problem": None}
+
+
+def problem_for(parameterization, camera_indices, image_coords, obj_indices, *, device: int = 0) -> BAProblem:
+    """Device problem for one ``args`` tuple; cached on array identity so scipy-style repeated
+    ``fun(x)`` / ``jac(x)`` calls (e.g. finite-difference tests) re-use the uploaded observation list."""
+    key = (id(parameterization), id(camera_indices), id(image_coords), id(obj_indices), len(camera_indices), device)
+    if _CACHE["key"] == key and _CACHE["problem"] is not None:
+        return _CACHE["problem"]
+    if _CACHE["problem"] is not None:
+        _CACHE["problem"].close()
+    flags, const = blocks_to_arrays(parameterization.blocks)
+    prob = BAProblem(flags, const, parameterization.n_points, np.asarray(camera_indices), np.asarray(obj_indices),
+                     np.asarray(image_coords, dtype=np.float64), device=device)  # fmt: skip
+    # keep the key objects alive so their ids cannot be recycled while the entry is cached
+    _CACHE.update(key=key, problem=prob, refs=(parameterization, camera_indices, image_coords, obj_indices))
+    return prob
+
+
+def clear_cache() -> None:
+    if _CACHE["problem"] is not None:
+        _CACHE["problem"].close()
+    _CACHE.update(key=None, problem=None, refs=None)
+
+
+def _no_constraints(groups_a) -> None:
+    if groups_a is not None and len(groups_a) > 0:
+        raise NotImplementedError(
+            "rigid-distance constraint rows (reprojection.py:112-117) are not implemented in the CUDA engine yet"
+        )
+
+
+def project_points(world, rvec, tvec, K, dist, fisheye: bool) -> np.ndarray:
+    world = np.asarray(world, dtype=np.float64).reshape(-1, 3)
+    d = np.asarray(dist, dtype=np.float64).ravel()
+    K = np.asarray(K, dtype=np.float64)
+    if fisheye:
+        if d.shape[0] != 4:
+            raise ValueError(f"Fisheye projection requires 4 distortion coefficients, got {d.shape[0]}")
+        flags, c = 2, [K[0, 0], K[1, 1], K[0, 2], K[1, 2], d[0], d[1], d[2], d[3], 0.0]
+    else:
+        d5 = np.zeros(5)
+        d5[: min(5, d.size)] = d[:5]
+        flags, c = 0, [K[0, 0], K[1, 1], K[0, 2], K[1, 2], *d5]
+    n = len(world)
+    x = np.concatenate([np.ravel(rvec), np.ravel(tvec), world.ravel()]).astype(np.float64)
+    with BAProblem(np.array([flags], np.int32), np.array([c]), n, np.zeros(n, np.int32), np.arange(n, dtype=np.int32),
+                   np.zeros((n, 2))) as prob:  # fmt: skip
+        return prob.reproj_errors_px(x)  # observed == 0  ->  error == projection
+
+
+def reprojection_errors(camera_array, camera_indices, image_coords, world_coords) -> np.ndarray:
+    """Pixel errors with each camera's stored intrinsics and extrinsics (reprojection.py:35-72)."""
+    from .bundle_parameterization import BundleParameterization
+
+    world_coords = np.asarray(world_coords, dtype=np.float64).reshape(-1, 3)
+    par = BundleParameterization.from_camera_array(camera_array, n_points=len(world_coords), refine_intrinsics=False)
+    x = par.pack(camera_array, world_coords)
+    flags, const = blocks_to_arrays(par.blocks)
+    n = len(world_coords)
+    with BAProblem(flags, const, n, np.asarray(camera_indices), np.arange(n, dtype=np.int32),
+                   np.asarray(image_coords, dtype=np.float64)) as prob:  # fmt: skip
+        return prob.reproj_errors_px(x)
+
+
+def joint_residuals(params, parameterization, camera_indices, image_coords, obj_indices, constraint_groups_a=None,
+                    constraint_groups_b=None, constraint_distances=None, constraint_weights=None) -> np.ndarray:  # fmt: skip
+    _no_constraints(constraint_groups_a)
+    return problem_for(parameterization, camera_indices, image_coords, obj_indices).residuals(params)
+
+
+def joint_jacobian(params, parameterization, camera_indices, image_coords, obj_indices, constraint_groups_a=None,
+                   constraint_groups_b=None, constraint_distances=None, constraint_weights=None):  # fmt: skip
+    """CSR matrix with the reference's row/column layout, assembled from the engine's dense blocks."""
+    from scipy.sparse import csr_matrix
+
+    _no_constraints(constraint_groups_a)
+    prob = problem_for(parameterization, camera_indices, image_coords, obj_indices)
+    Jc, Jp = prob.jacobian_blocks(params)
+    cam = np.asarray(camera_indices, dtype=np.int64)
+    pt = np.asarray(obj_indices, dtype=np.int64)
+    widths = (prob.cam_offsets[1:] - prob.cam_offsets[:-1])[cam]
+    nnz_row = np.repeat(widths + 3, 2)
+    indptr = np.concatenate([[0], np.cumsum(nnz_row)]).astype(np.int64)
+    data = np.empty(int(indptr[-1]))
+    indices = np.empty(int(indptr[-1]), dtype=np.int64)
+    ncp = prob.n_camera_params
+    for w in np.unique(widths) if len(cam) else []:
+        sel = np.nonzero(widths == w)[0]
+        cols = np.concatenate([prob.cam_offsets[cam[sel]][:, None] + np.arange(w)[None],
+                               ncp + 3 * pt[sel][:, None] + np.arange(3)[None]], axis=1)  # fmt: skip
+        vals = np.concatenate([Jc[sel][:, :, :w], Jp[sel]], axis=2)
+        for half in (0, 1):
+            pos = indptr[2 * sel + half][:, None] + np.arange(w + 3)[None]
+            data[pos] = vals[:, half, :]
+            indices[pos] = cols
+    return csr_matrix((data, indices, indptr), shape=(2 * len(cam), prob.n_params))

@@ -1,0 +1,74 @@
+"""Drop-in for the solver call inside ``CaptureVolume.optimize``
+(/root/reference/src/caliscope/core/capture_volume.py:387-411):
+
+    result = least_squares(joint_residuals, x0, args=(parameterization, camera_indices, image_coords,
+                           image_to_world_indices, cga, cgb, cdist, cw), jac=joint_jacobian, verbose=...,
+                           x_scale="jac", loss=..., f_scale=..., ftol=..., max_nfev=..., method="trf", bounds=...)
+
+``least_squares`` below has that signature.  When ``fun`` is a ``joint_residuals`` (the reference's or
+this package's) it never calls ``fun``/``jac``: it hands ``args`` to the CUDA engine and returns an
+object with the fields the reference reads (``x``, ``status``, ``nfev``, ``cost``).  Anything else is
+not this path and raises (or is delegated to the callable given to ``install(fallback=...)``).
+"""
+from __future__ import annotations
+
+import logging
+from typing import Any, Callable
+
+import numpy as np
+
+from .problem import BAProblem, SolveResult, blocks_to_arrays
+
+logger = logging.getLogger(__name__)
+
+_fallback: Callable | None = None  # set by seam.install(fallback=...)
+
+
+def is_bundle_adjustment_call(fun: Any, args: tuple) -> bool:
+    return (
+        callable(fun)
+        and getattr(fun, "__name__", "") == "joint_residuals"
+        and len(args) >= 4
+        and hasattr(args[0], "blocks")
+        and hasattr(args[0], "n_points")
+    )
+
+
+def solve_arrays(cam_flags, cam_const, n_pts, camera_indices, obj_indices, image_coords, x0, *, use_bounds=True,
+                 device: int = 0, **kw) -> SolveResult:  # fmt: skip
+    """Array-level entry: build the device problem, solve, free it."""
+    with BAProblem(cam_flags, cam_const, n_pts, camera_indices, obj_indices, image_coords, device=device) as prob:
+        return prob.solve(x0, use_bounds=use_bounds, **kw)
+
+
+def least_squares(fun, x0, jac="2-point", bounds=(-np.inf, np.inf), method="trf", ftol=1e-8, xtol=1e-8, gtol=1e-8,
+                  x_scale=None, loss="linear", f_scale=1.0, diff_step=None, tr_solver=None, tr_options=None,
+                  jac_sparsity=None, max_nfev=None, verbose=0, args=(), kwargs=None, callback=None, **extra):  # fmt: skip
+    if not is_bundle_adjustment_call(fun, tuple(args)):
+        if _fallback is not None:
+            return _fallback(fun, x0, jac=jac, bounds=bounds, method=method, ftol=ftol, xtol=xtol, gtol=gtol,
+                             x_scale=x_scale if x_scale is not None else 1.0, loss=loss, f_scale=f_scale,
+                             max_nfev=max_nfev, verbose=verbose, args=args, kwargs=kwargs or {})  # fmt: skip
+        raise NotImplementedError("caliscope_b200.least_squares only replaces the bundle-adjustment call "
+                                  "(fun=joint_residuals, args=(parameterization, camera_indices, ...))")  # fmt: skip
+    par, camera_indices, image_coords, obj_indices = args[:4]
+    groups_a = args[4] if len(args) > 4 else None
+    if groups_a is not None and len(groups_a) > 0:
+        if _fallback is not None:
+            logger.info("distance-constraint rows present: delegating this solve to the fallback solver")
+            return _fallback(fun, x0, jac=jac, bounds=bounds, method=method, ftol=ftol, xtol=xtol, gtol=gtol,
+                             x_scale=x_scale if x_scale is not None else 1.0, loss=loss, f_scale=f_scale,
+                             max_nfev=max_nfev, verbose=verbose, args=args, kwargs=kwargs or {})  # fmt: skip
+        raise NotImplementedError("rigid-distance constraint rows are not implemented in the CUDA engine yet; "
+                                  "call optimize(use_constraints=False) or install(fallback=scipy's least_squares)")  # fmt: skip
+    if method != "trf":
+        raise ValueError("caliscope_b200.least_squares replaces method='trf' only")
+    flags, const = blocks_to_arrays(par.blocks)
+    lo, hi = (np.asarray(b, dtype=np.float64) for b in bounds) if isinstance(bounds, (tuple, list)) else (bounds.lb, bounds.ub)
+    use_bounds = bool(np.any(np.isfinite(np.atleast_1d(lo))) or np.any(np.isfinite(np.atleast_1d(hi))))
+    res = solve_arrays(flags, const, par.n_points, np.asarray(camera_indices), np.asarray(obj_indices),
+                       np.asarray(image_coords, dtype=np.float64), np.asarray(x0, dtype=np.float64),
+                       use_bounds=use_bounds, ftol=ftol if ftol is not None else 0.0, xtol=xtol if xtol is not None else 0.0,
+                       gtol=gtol if gtol is not None else 0.0, max_nfev=max_nfev, loss=loss, f_scale=f_scale,
+                       verbose=2 if verbose >= 2 else int(verbose))  # fmt: skip
+    return res

@@ -1,0 +1,91 @@
+"""N > 1 host logic on CPU: point sharding, the all-reduce hook and the point gather under
+torch.distributed (gloo, world_size 2)."""
+from __future__ import annotations
+
+import ctypes
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from caliscope_b200 import distributed as D
+from caliscope_b200 import synthetic
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_point_sharding_partitions_every_observation_once(world):
+    r = synthetic.make_rig(6, 400, 5000, seed=1)
+    seen = np.zeros(r.n_obs, int)
+    prev_hi = 0
+    counts = []
+    for k in range(world):
+        s = D.shard_points(r.obs_cam, r.obs_pt, r.obs_xy, r.n_pts, k, world)
+        assert s.pt_lo == prev_hi
+        prev_hi = s.pt_hi
+        seen[s.obs_index] += 1
+        assert np.array_equal(s.obs_pt + s.pt_lo, r.obs_pt[s.obs_index])
+        assert np.array_equal(s.obs_cam, r.obs_cam[s.obs_index])
+        assert np.array_equal(s.obs_xy, r.obs_xy[s.obs_index])
+        assert s.obs_pt.min() >= 0 and s.obs_pt.max() < s.n_pts
+        counts.append(len(s.obs_index))
+        xl = D.local_x(r.x0, 36, s)
+        assert len(xl) == 36 + 3 * s.n_pts
+        assert np.array_equal(xl[36:], r.x0[36 + 3 * s.pt_lo : 36 + 3 * s.pt_hi])
+    assert prev_hi == r.n_pts and np.all(seen == 1)
+    assert max(counts) - min(counts) <= 0.1 * r.n_obs / world + 50  # balanced by observation count
+
+
+def _worker(rank: int, world: int, port: int, out):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # (1) the C-ABI all-reduce hook on a host buffer
+        hook = D.make_allreduce_hook(device_buffers=False)
+        buf = np.arange(10, dtype=np.float64) * (rank + 1)
+        rc = hook(None, buf.ctypes.data, 10, None)
+        assert rc == 0
+        assert np.array_equal(buf, np.arange(10) * sum(range(1, world + 1)))
+        # through the ctypes function type the engine calls
+        from caliscope_b200 import _lib
+
+        cfn = _lib.ALLREDUCE_FN(hook)
+        buf2 = np.full(4, float(rank))
+        assert cfn(None, buf2.ctypes.data, 4, None) == 0
+        assert np.array_equal(buf2, np.full(4, float(sum(range(world)))))
+        # (2) gather of per-rank points back into the global vector
+        r = synthetic.make_rig(6, 400, 5000, seed=1)
+        s = D.shard_points(r.obs_cam, r.obs_pt, r.obs_xy, r.n_pts, rank, world)
+        xl = D.local_x(r.x0, 36, s) + 0.0
+        full = D.gather_points(xl, 36, r.n_pts, s)
+        assert np.array_equal(full, r.x0)
+        out.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        out.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_allreduce_hook_and_gather_world_size_2():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [out.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, "ok"), (1, "ok")], results
