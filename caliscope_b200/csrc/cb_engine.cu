@@ -12,6 +12,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cub/cub.cuh>
 #include <string>
@@ -66,7 +67,7 @@ struct CbBaProblem {
   int device = 0, num_sms = 148;
   int n_cams = 0, n_pts = 0, P = 6, nP = 0, n_obs = 0, n_params = 0;
   int LD = 0, n_blk = 0, n_tiles = 0, n_split = 1, k_chunks = 0, K_pad = 0;
-  int n_chunks = 0, n_pairs = 0, pt_blocks = 0;
+  int n_chunks = 0, pt_blocks = 0;
   std::vector<int> h_cam_off;
   std::vector<void*> allocs;
   // problem tables
@@ -75,8 +76,7 @@ struct CbBaProblem {
   double2* d_cm_xy = nullptr;
   int *d_cm_pt = nullptr, *d_cm_row = nullptr, *d_cm_orig = nullptr, *d_cam_start = nullptr;
   int *d_chunk_cam = nullptr, *d_chunk_begin = nullptr, *d_chunk_end = nullptr, *d_cam_chunk_start = nullptr;
-  int *d_pt_start = nullptr, *d_pm_orig = nullptr, *d_pair_start = nullptr, *d_pair_cam = nullptr,
-      *d_pt_pair_start = nullptr;
+  int *d_pt_start = nullptr, *d_pm_orig = nullptr, *d_pm_cam = nullptr, *d_pm_row = nullptr;
   int *d_tileI = nullptr, *d_tileJ = nullptr, *d_tile_of = nullptr;
   unsigned char* d_active = nullptr;
   double *d_lo = nullptr, *d_hi = nullptr;
@@ -134,17 +134,14 @@ int build_indices(CbBaProblem* p, const int* d_obs_cam, const int* d_obs_pt, con
   }
 
   unsigned long long *k_in, *k_out;
-  int *v_in, *v_out, *pm_pt, *pm_cam, *cm_cam, *flag, *pidx;
+  int *v_in, *v_out, *pm_pt, *pm_cam, *cm_cam;
   CB_TRY(dalloc(&k_in, n)); CB_TRY(dalloc(&k_out, n));
   CB_TRY(dalloc(&v_in, n)); CB_TRY(dalloc(&v_out, n));
   CB_TRY(dalloc(&pm_pt, n)); CB_TRY(dalloc(&pm_cam, n)); CB_TRY(dalloc(&cm_cam, n));
-  CB_TRY(dalloc(&flag, n)); CB_TRY(dalloc(&pidx, n + 1));
 
   // temp storage for cub (max of sort and scan requirements)
-  size_t tb_sort = 0, tb_scan = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tb_sort, k_in, k_out, v_in, v_out, n, 0, 64, st);
-  cub::DeviceScan::ExclusiveSum(nullptr, tb_scan, flag, pidx, n, st);
-  size_t tb = std::max(tb_sort, tb_scan);
+  size_t tb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in, k_out, v_in, v_out, n, 0, 64, st);
   void* d_tmp;
   CB_CUDA(cudaMalloc(&d_tmp, std::max<size_t>(tb, 16)));
 
@@ -155,41 +152,38 @@ int build_indices(CbBaProblem* p, const int* d_obs_cam, const int* d_obs_pt, con
   g_launches.fetch_add(4);
   CB_LAUNCH(cb::split_keys_kernel, G, TB, 0, st, k_out, (long long)p->n_cams, n, pm_pt, pm_cam);
   CB_LAUNCH(cb::lower_bound_kernel, cdiv(p->n_pts + 1, TB), TB, 0, st, pm_pt, n, p->n_pts, p->d_pt_start);
-  // (2) unique (point, camera) pairs
-  CB_LAUNCH(cb::pair_flag_kernel, G, TB, 0, st, k_out, n, flag);
-  CB_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tb, flag, pidx, n, st));
-  g_launches.fetch_add(2);
-  int last_flag = 0, last_idx = 0;
-  if (n > 0) {
-    CB_CUDA(cudaMemcpyAsync(&last_flag, flag + n - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CB_CUDA(cudaMemcpyAsync(&last_idx, pidx + n - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-  }
-  CB_CUDA(cudaStreamSynchronize(st));
-  p->n_pairs = last_flag + last_idx;
-  CB_TRY(palloc(p, &p->d_pair_start, (size_t)p->n_pairs + 1));
-  CB_TRY(palloc(p, &p->d_pair_cam, (size_t)p->n_pairs + 1));
-  CB_LAUNCH(cb::pair_scatter_kernel, G, TB, 0, st, flag, pidx, n, pm_cam, p->d_pair_start, p->d_pair_cam, p->n_pairs);
-  CB_LAUNCH(cb::pt_pair_start_kernel, cdiv(p->n_pts + 1, TB), TB, 0, st, p->d_pt_start, pidx, p->n_pts, n,
-            p->n_pairs, p->d_pt_pair_start);
-  // (3) camera-major order: key = cam * n_pts + pt over the point-major rows (stable)
-  CB_LAUNCH(cb::make_keys_kernel, G, TB, 0, st, pm_cam, pm_pt, (long long)p->n_pts, n, k_in, v_in);
-  CB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb, k_in, k_out, v_in, p->d_cm_row, n, 0, kb, st));
+  CB_CUDA(cudaMemcpyAsync(p->d_pm_cam, pm_cam, sizeof(int) * n, cudaMemcpyDeviceToDevice, st));
+  // (2) row layout of the Jacobian buffer: (point block of PT_BLOCK points, camera, point).  Within a
+  //     block all rows of one camera are adjacent, so a camera-major warp of resjac_kernel writes runs of
+  //     consecutive 160-byte rows (DRAM page locality; scattered single rows cap at ~2.4 TB/s on B200,
+  //     runs of >= 8 rows reach ~4.5 TB/s -- profiles/microbench/row_scatter.cu), while every point's rows
+  //     stay inside one contiguous block for the point-centric kernels.
+  CB_LAUNCH(cb::make_block_keys_kernel, G, TB, 0, st, pm_pt, pm_cam, p->n_cams, cb::PT_BLOCK, n, k_in, v_in);
+  const int kb2 = bits_for(((unsigned long long)(p->n_pts / cb::PT_BLOCK + 1) * p->n_cams + p->n_cams) * cb::PT_BLOCK);
+  CB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb, k_in, k_out, v_in, v_out, n, 0, kb2, st));
   g_launches.fetch_add(4);
-  CB_LAUNCH(cb::split_keys_kernel, G, TB, 0, st, k_out, (long long)p->n_pts, n, cm_cam, v_out);
+  CB_LAUNCH(cb::invert_perm_kernel, G, TB, 0, st, v_out, n, p->d_pm_row);  // pm position -> row
+  // (3) camera-major order: key = cam * n_pts + pt over the point-major positions (stable)
+  CB_LAUNCH(cb::make_keys_kernel, G, TB, 0, st, pm_cam, pm_pt, (long long)p->n_pts, n, k_in, v_in);
+  CB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb, k_in, k_out, v_in, v_out, n, 0, kb, st));
+  g_launches.fetch_add(4);
+  CB_LAUNCH(cb::split_keys_kernel, G, TB, 0, st, k_out, (long long)p->n_pts, n, cm_cam, v_in);
   CB_LAUNCH(cb::lower_bound_kernel, cdiv(p->n_cams + 1, TB), TB, 0, st, cm_cam, n, p->n_cams, p->d_cam_start);
-  CB_LAUNCH(cb::cm_gather_kernel, G, TB, 0, st, p->d_cm_row, p->d_pm_orig, pm_pt,
-            reinterpret_cast<const double2*>(d_obs_xy), n, p->d_cm_pt, p->d_cm_orig, p->d_cm_xy);
+  CB_LAUNCH(cb::cm_gather_kernel, G, TB, 0, st, v_out, p->d_pm_row, p->d_pm_orig, pm_pt,
+            reinterpret_cast<const double2*>(d_obs_xy), n, p->d_cm_row, p->d_cm_pt, p->d_cm_orig, p->d_cm_xy);
   // (4) chunk table (host, n_cams + 1 integers)
   std::vector<int> cam_start(p->n_cams + 1);
   CB_CUDA(cudaMemcpyAsync(cam_start.data(), p->d_cam_start, sizeof(int) * (p->n_cams + 1), cudaMemcpyDeviceToHost, st));
   CB_CUDA(cudaStreamSynchronize(st));
   std::vector<int> cc, cbeg, cend, ccs(p->n_cams + 1);
+  int chunk = cb::RJ_CHUNK;
+  if (const char* e = std::getenv("CB_RJ_CHUNK")) chunk = std::max(cb::RJ_THREADS, std::atoi(e));
   for (int c = 0; c < p->n_cams; ++c) {
     ccs[c] = (int)cc.size();
-    for (int b = cam_start[c]; b < cam_start[c + 1]; b += cb::RJ_CHUNK) {
+    for (int b = cam_start[c]; b < cam_start[c + 1]; b += chunk) {
       cc.push_back(c);
       cbeg.push_back(b);
-      cend.push_back(std::min(b + cb::RJ_CHUNK, cam_start[c + 1]));
+      cend.push_back(std::min(b + chunk, cam_start[c + 1]));
     }
   }
   ccs[p->n_cams] = (int)cc.size();
@@ -205,7 +199,7 @@ int build_indices(CbBaProblem* p, const int* d_obs_cam, const int* d_obs_pt, con
   CB_CUDA(cudaMemcpyAsync(p->d_cam_chunk_start, ccs.data(), sizeof(int) * ccs.size(), cudaMemcpyHostToDevice, st));
   CB_CUDA(cudaStreamSynchronize(st));
   cudaFree(d_tmp); cudaFree(k_in); cudaFree(k_out); cudaFree(v_in); cudaFree(v_out);
-  cudaFree(pm_pt); cudaFree(pm_cam); cudaFree(cm_cam); cudaFree(flag); cudaFree(pidx);
+  cudaFree(pm_pt); cudaFree(pm_cam); cudaFree(cm_cam);
   return CB_OK;
 }
 
@@ -243,17 +237,20 @@ int linearize(CbBaProblem* p, const double* xc, const double* xp4, int loss, dou
   static_assert(RT::NACC <= 64, "cam_reduce block too small");
   CB_LAUNCH(cb::sum_kernel, 1, 256, 0, st, p->d_camcost, p->n_cams, p->d_costsum);
   CB_CUDA(cudaMemsetAsync(p->d_gmax, 0, sizeof(unsigned long long), st));
-  CB_LAUNCH((cb::pt_reduce_kernel<P>), p->pt_blocks, cb::PT_WARPS * 32, 0, st, p->d_pt_start, p->n_pts, p->d_jrows,
-            p->d_V6, p->d_gp, p->d_Dp2, p->d_gmax);
   (void)rj_ms;
   return CB_OK;
 }
 
 template <int P>
 int build_system(CbBaProblem* p, double lam, bool new_lin, const CbBaOptions* opt, cudaStream_t st) {
-  CB_LAUNCH((cb::pt_zbuild_kernel<P>), p->pt_blocks, cb::PT_WARPS * 32, 0, st, p->d_pt_pair_start, p->d_pair_start,
-            p->d_pair_cam, p->n_pts, p->d_jrows, p->d_V6, p->d_gp, p->d_Dp2, lam, p->d_Linv6, p->d_tvec, p->d_Zt,
-            (size_t)p->LD);
+  if (new_lin)
+    CB_LAUNCH((cb::pt_build_kernel<P, true>), p->pt_blocks, cb::PT_WARPS * 32, 0, st, p->d_pt_start, p->d_pm_cam,
+              p->d_pm_row, p->n_pts, p->d_jrows, p->d_V6, p->d_gp, p->d_Dp2, lam, p->d_Linv6, p->d_tvec, p->d_Zt, (size_t)p->LD,
+              p->d_gmax);
+  else
+    CB_LAUNCH((cb::pt_build_kernel<P, false>), p->pt_blocks, cb::PT_WARPS * 32, 0, st, p->d_pt_start, p->d_pm_cam,
+              p->d_pm_row, p->n_pts, p->d_jrows, p->d_V6, p->d_gp, p->d_Dp2, lam, p->d_Linv6, p->d_tvec, p->d_Zt, (size_t)p->LD,
+              p->d_gmax);
   CB_LAUNCH(cb::schur_syrk_kernel, p->n_tiles * p->n_split, cb::SY_THREADS, sizeof(cb::SyrkSmem), st, p->d_Zt,
             (size_t)p->LD, p->d_tvec, p->k_chunks, p->n_split, p->d_tileI, p->d_tileJ, p->n_tiles, p->d_part,
             p->d_tpart);
@@ -657,7 +654,8 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
   CB_TRY(palloc(p, &p->d_cm_orig, n)); CB_TRY(palloc(p, &p->d_cam_start, p->n_cams + 1));
   CB_TRY(palloc(p, &p->d_cam_chunk_start, p->n_cams + 1));
   CB_TRY(palloc(p, &p->d_pt_start, p->n_pts + 1)); CB_TRY(palloc(p, &p->d_pm_orig, n));
-  CB_TRY(palloc(p, &p->d_pt_pair_start, p->n_pts + 1));
+  CB_TRY(palloc(p, &p->d_pm_cam, n));
+  CB_TRY(palloc(p, &p->d_pm_row, n));
   // observation list: host -> device if needed
   const int *d_cam = d->obs_cam, *d_pt = d->obs_pt;
   const double* d_xy = d->obs_xy;
@@ -809,11 +807,11 @@ int cb_ba_jacobian_blocks(CbBaProblem* p, const double* x, double* Jc, double* J
   if (p->P == 6) {
     CB_TRY(run_cam_prep<6>(p, p->d_xc[0], st));
     launch_resjac<6, 0>(p, p->d_xp4[0], 0, 1.0, nullptr, st);
-    if (n) CB_LAUNCH((cb::rows_to_blocks_kernel<6>), cdiv(n, 256), 256, 0, st, p->d_jrows, p->d_pm_orig, n, dJc, dJp);
+    if (n) CB_LAUNCH((cb::rows_to_blocks_kernel<6>), cdiv(n, 256), 256, 0, st, p->d_jrows, p->d_pm_row, p->d_pm_orig, n, dJc, dJp);
   } else {
     CB_TRY(run_cam_prep<9>(p, p->d_xc[0], st));
     launch_resjac<9, 0>(p, p->d_xp4[0], 0, 1.0, nullptr, st);
-    if (n) CB_LAUNCH((cb::rows_to_blocks_kernel<9>), cdiv(n, 256), 256, 0, st, p->d_jrows, p->d_pm_orig, n, dJc, dJp);
+    if (n) CB_LAUNCH((cb::rows_to_blocks_kernel<9>), cdiv(n, 256), 256, 0, st, p->d_jrows, p->d_pm_row, p->d_pm_orig, n, dJc, dJp);
   }
   cudaError_t e1 = cudaMemcpyAsync(Jc, dJc, sizeof(double) * 18 * (size_t)n, cudaMemcpyDeviceToHost, st);
   cudaError_t e2 = cudaMemcpyAsync(Jp, dJp, sizeof(double) * 6 * (size_t)n, cudaMemcpyDeviceToHost, st);

@@ -25,12 +25,14 @@ namespace cb {
 namespace cg = cooperative_groups;
 
 constexpr int RJ_THREADS = 128;   // resjac / cost block size
-constexpr int RJ_CHUNK = 1024;    // observations per block (all of one camera)
+constexpr int RJ_CHUNK = 2048;    // observations per block (all of one camera)
 constexpr int PT_WARPS = 8;       // warps (points) per block in the point-centric kernels
+constexpr int PT_BLOCK = 16;      // points per block of the Jacobian row layout (block, camera, point)
 constexpr int SY_TILE = 96;       // Schur tile edge
 constexpr int SY_KC = 32;         // k rows per pipeline stage
 constexpr int SY_STAGES = 4;
-constexpr int SY_THREADS = 256;
+constexpr int SY_CONSUMER_WARPS = 8;
+constexpr int SY_THREADS = 32 * (SY_CONSUMER_WARPS + 1);  // + one producer warp
 constexpr int PCG_THREADS = 512;
 
 template <int P>
@@ -153,7 +155,7 @@ __global__ void cam_prep_kernel(const double* __restrict__ xc, const int* __rest
 // MODE 4: euclidean pixel error to out2[q]   (camera-major, for the percentile filter)
 // ---------------------------------------------------------------------------------------------
 template <int P, int MODE>
-__global__ void __launch_bounds__(RJ_THREADS)
+__global__ void __launch_bounds__(RJ_THREADS, (MODE == 0 && P == 6) ? 3 : 1)
 resjac_kernel(const int* __restrict__ chunk_cam, const int* __restrict__ chunk_begin,
               const int* __restrict__ chunk_end, const double2* __restrict__ cm_xy,
               const int* __restrict__ cm_pt, const int* __restrict__ cm_row, const int* __restrict__ cm_orig,
@@ -175,16 +177,39 @@ resjac_kernel(const int* __restrict__ chunk_cam, const int* __restrict__ chunk_b
 #pragma unroll
   for (int k = 0; k < ((MODE == 0) ? RT::NACC : 1); ++k) acc[k] = 0.0;
 
-  for (int q = begin + threadIdx.x; q < end; q += RJ_THREADS) {
-    const double2 xy = cm_xy[q];
-    const int pt = cm_pt[q];
-    double X0, X1, X2, X3;
-    ld256nc(xp4 + 4 * (size_t)pt, X0, X1, X2, X3);
+  // Two-deep software pipeline over this thread's observations: the index triple of iteration
+  // i+2 and the point gather of iteration i+1 are in flight while iteration i computes (the
+  // loads are a dependent chain cm_pt -> xp4[pt], ~2 DRAM/L2 latencies, and only 12-16 warps
+  // fit per SM, so the latency has to be hidden inside the thread).
+  int q = begin + threadIdx.x;
+  double2 xy_a = make_double2(0.0, 0.0), xy_b = xy_a;
+  int pt_a = 0, row_a = 0, org_a = 0, pt_b = 0, row_b = 0, org_b = 0;
+  double Xn0 = 0.0, Xn1 = 0.0, Xn2 = 0.0, Xn3 = 0.0;
+  auto load_idx = [&](int qq, double2& xy, int& pt, int& row, int& org) {
+    if (qq < end) {
+      xy = cm_xy[qq];
+      pt = cm_pt[qq];
+      if constexpr (MODE == 0) row = cm_row[qq];
+      if constexpr (MODE == 2 || MODE == 3) org = cm_orig[qq];
+    }
+  };
+  load_idx(q, xy_a, pt_a, row_a, org_a);
+  load_idx(q + RJ_THREADS, xy_b, pt_b, row_b, org_b);
+  if (q < end) ld256nc(xp4 + 4 * (size_t)pt_a, Xn0, Xn1, Xn2, Xn3);
+  for (; q < end; q += RJ_THREADS) {
+    const double2 xy = xy_a;
+    const int row = row_a, org = org_a;
+    const double X0 = Xn0, X1 = Xn1, X2 = Xn2;
+    (void)row; (void)org;
+    // rotate the pipeline
+    xy_a = xy_b; pt_a = pt_b; row_a = row_b; org_a = org_b;
+    if (q + RJ_THREADS < end) ld256nc(xp4 + 4 * (size_t)pt_a, Xn0, Xn1, Xn2, Xn3);
+    load_idx(q + 2 * RJ_THREADS, xy_b, pt_b, row_b, org_b);
     ProjOut o;
     project_obs<MODE == 0>(cam, fish, X0, X1, X2, o);
     const double ex = o.u - xy.x, ey = o.v - xy.y;
     if constexpr (MODE == 3) {
-      const size_t i = (size_t)cm_orig[q];
+      const size_t i = (size_t)org;
       out2[2 * i] = ex; out2[2 * i + 1] = ey;
       continue;
     }
@@ -194,7 +219,7 @@ resjac_kernel(const int* __restrict__ chunk_cam, const int* __restrict__ chunk_b
     }
     double f0 = ex * cam[CT_IFX0], f1 = ey * cam[CT_IFX0];
     if constexpr (MODE == 2) {
-      const size_t i = (size_t)cm_orig[q];
+      const size_t i = (size_t)org;
       out2[2 * i] = f0; out2[2 * i + 1] = f1;
       continue;
     }
@@ -251,7 +276,7 @@ resjac_kernel(const int* __restrict__ chunk_cam, const int* __restrict__ chunk_b
 #pragma unroll
       for (int a = 0; a < P; ++a) acc[RT::NU + a] = fma(Jc[a], f0, fma(Jc[P + a], f1, acc[RT::NU + a]));
       // row store
-      double* dst = jrows + (size_t)cm_row[q] * RT::ROWD;
+      double* dst = jrows + (size_t)row * RT::ROWD;
       st256(dst, f0, f1, JX[0], JX[1]);
       st256(dst + 4, JX[2], JX[3], JX[4], JX[5]);
       if constexpr (P == 6) {
@@ -314,54 +339,6 @@ __global__ void sum_kernel(const double* __restrict__ in, int n, double* __restr
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// point-centric: V_j = sum Jp^T Jp (6 unique), gp_j = sum Jp^T r ; one warp per point
-// ---------------------------------------------------------------------------------------------
-template <int P>
-__global__ void __launch_bounds__(PT_WARPS * 32)
-pt_reduce_kernel(const int* __restrict__ pt_start, int n_pts, const double* __restrict__ jrows,
-                 double* __restrict__ V6, double* __restrict__ gp, double* __restrict__ Dp2,
-                 unsigned long long* __restrict__ gmax_bits) {
-  using RT = RowT<P>;
-  __shared__ double wmax[PT_WARPS];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int j = blockIdx.x * PT_WARPS + wid;
-  double gm = 0.0;
-  if (j < n_pts) {
-    const int s = pt_start[j], e = pt_start[j + 1];
-    double v[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) v[k] = 0.0;
-    for (int row = s + lane; row < e; row += 32) {
-      const double* src = jrows + (size_t)row * RT::ROWD;
-      double f0, f1, a0, a1, a2, b0, b1, b2;
-      ld256(src, f0, f1, a0, a1);
-      ld256(src + 4, a2, b0, b1, b2);
-      v[0] += a0 * a0 + b0 * b0; v[1] += a0 * a1 + b0 * b1; v[2] += a0 * a2 + b0 * b2;
-      v[3] += a1 * a1 + b1 * b1; v[4] += a1 * a2 + b1 * b2; v[5] += a2 * a2 + b2 * b2;
-      v[6] += a0 * f0 + b0 * f1; v[7] += a1 * f0 + b1 * f1; v[8] += a2 * f0 + b2 * f1;
-    }
-#pragma unroll
-    for (int k = 0; k < 9; ++k) v[k] = warp_sum(v[k]);
-    if (lane == 0) {
-#pragma unroll
-      for (int k = 0; k < 6; ++k) V6[(size_t)j * 6 + k] = v[k];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) gp[(size_t)j * 3 + k] = v[6 + k];
-      double* d = Dp2 + (size_t)j * 3;
-      d[0] = fmax(d[0], v[0]); d[1] = fmax(d[1], v[3]); d[2] = fmax(d[2], v[5]);
-      gm = fmax(fabs(v[6]), fmax(fabs(v[7]), fabs(v[8])));
-    }
-  }
-  if (lane == 0) wmax[wid] = gm;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double m = 0.0;
-    for (int w = 0; w < PT_WARPS; ++w) m = fmax(m, wmax[w]);
-    if (m > 0.0) atomicMax(gmax_bits, (unsigned long long)__double_as_longlong(m));
-  }
-}
-
 // 3x3 SPD: E = V + lam * D ; L = chol(E) ; returns Linv (lower, packed 00,10,11,20,21,22); zero if not PD
 __device__ __forceinline__ void chol3_inv(const double* V6, const double* D2, double lam, double* Li) {
   const double d0 = D2[0] > 0.0 ? D2[0] : 1.0, d1 = D2[1] > 0.0 ? D2[1] : 1.0, d2 = D2[2] > 0.0 ? D2[2] : 1.0;
@@ -388,50 +365,115 @@ __device__ __forceinline__ void chol3_inv(const double* V6, const double* D2, do
   }
 }
 
-// per point: Linv, t = Linv gp ; per (point, camera) pair: W = sum_rows Jc^T Jp, Z = W Linv^T -> Zt
-template <int P>
+// Point-centric build of the Schur factor, one warp per point over its contiguous point-major rows:
+//   FUSED: V = sum Jp^T Jp, gp = sum Jp^T r over the rows (new linearisation), Marquardt scale update
+//   then  : Linv = chol(V + lam D)^-1, t = Linv gp, and per observed camera Z = (Jc^T Jp) Linv^T
+//           written to the k-major Zt (rows 3j..3j+2, columns cam*P..cam*P+P-1).
+// Repeated (camera, point) rows are adjacent (rows are sorted by point, then camera): the first
+// row of a run sums the run, so Z stays one block per (camera, point) pair without atomics.
+template <int P, bool FUSED>
 __global__ void __launch_bounds__(PT_WARPS * 32)
-pt_zbuild_kernel(const int* __restrict__ pt_pair_start, const int* __restrict__ pair_start,
-                 const int* __restrict__ pair_cam, int n_pts, const double* __restrict__ jrows,
-                 const double* __restrict__ V6, const double* __restrict__ gp, const double* __restrict__ Dp2,
-                 double lam, double* __restrict__ Linv6, double* __restrict__ tvec, double* __restrict__ Zt,
-                 size_t LD) {
+pt_build_kernel(const int* __restrict__ pt_start, const int* __restrict__ pm_cam,
+                const int* __restrict__ pm_row, int n_pts,
+                const double* __restrict__ jrows, double* __restrict__ V6, double* __restrict__ gp,
+                double* __restrict__ Dp2, double lam, double* __restrict__ Linv6, double* __restrict__ tvec,
+                double* __restrict__ Zt, size_t LD, unsigned long long* __restrict__ gmax_bits) {
   using RT = RowT<P>;
+  __shared__ double wmax[PT_WARPS];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int j = blockIdx.x * PT_WARPS + wid;
-  if (j >= n_pts) return;
-  double Li[6];
-  chol3_inv(V6 + (size_t)j * 6, Dp2 + (size_t)j * 3, lam, Li);
-  if (lane == 0) {
-    const double g0 = gp[(size_t)j * 3], g1 = gp[(size_t)j * 3 + 1], g2 = gp[(size_t)j * 3 + 2];
+  double gm = 0.0;
+  if (j < n_pts) {
+    const int s = pt_start[j], e = pt_start[j + 1];
+    double v[9], D[3];
+    if constexpr (FUSED) {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) Linv6[(size_t)j * 6 + k] = Li[k];
-    tvec[3 * (size_t)j + 0] = Li[0] * g0;
-    tvec[3 * (size_t)j + 1] = Li[1] * g0 + Li[2] * g1;
-    tvec[3 * (size_t)j + 2] = Li[3] * g0 + Li[4] * g1 + Li[5] * g2;
-  }
-  const int ps = pt_pair_start[j], pe = pt_pair_start[j + 1];
-  for (int q = ps + lane; q < pe; q += 32) {
-    double W[P * 3];
+      for (int k = 0; k < 9; ++k) v[k] = 0.0;
+      for (int pos = s + lane; pos < e; pos += 32) {
+        const double* src = jrows + (size_t)pm_row[pos] * RT::ROWD;
+        double f0, f1, a0, a1, a2, b0, b1, b2;
+        ld256(src, f0, f1, a0, a1);
+        ld256(src + 4, a2, b0, b1, b2);
+        v[0] += a0 * a0 + b0 * b0; v[1] += a0 * a1 + b0 * b1; v[2] += a0 * a2 + b0 * b2;
+        v[3] += a1 * a1 + b1 * b1; v[4] += a1 * a2 + b1 * b2; v[5] += a2 * a2 + b2 * b2;
+        v[6] += a0 * f0 + b0 * f1; v[7] += a1 * f0 + b1 * f1; v[8] += a2 * f0 + b2 * f1;
+      }
 #pragma unroll
-    for (int k = 0; k < P * 3; ++k) W[k] = 0.0;
-    for (int row = pair_start[q]; row < pair_start[q + 1]; ++row) {
-      const double* src = jrows + (size_t)row * RT::ROWD;
-      double v[RT::ROWD];
+      for (int k = 0; k < 9; ++k) v[k] = warp_sum(v[k]);
+      const double* d = Dp2 + (size_t)j * 3;
+      D[0] = fmax(d[0], v[0]); D[1] = fmax(d[1], v[3]); D[2] = fmax(d[2], v[5]);
+      if (lane == 0) {
 #pragma unroll
-      for (int k = 0; k < RT::ROWD; k += 4) ld256(src + k, v[k], v[k + 1], v[k + 2], v[k + 3]);
-      // v: [f0 f1 | Jp0(3) Jp1(3) | Jc0(P) Jc1(P)]
+        for (int k = 0; k < 6; ++k) V6[(size_t)j * 6 + k] = v[k];
 #pragma unroll
-      for (int p = 0; p < P; ++p)
+        for (int k = 0; k < 3; ++k) gp[(size_t)j * 3 + k] = v[6 + k];
+        Dp2[(size_t)j * 3] = D[0]; Dp2[(size_t)j * 3 + 1] = D[1]; Dp2[(size_t)j * 3 + 2] = D[2];
+        gm = fmax(fabs(v[6]), fmax(fabs(v[7]), fabs(v[8])));
+      }
+    } else {
 #pragma unroll
-        for (int a = 0; a < 3; ++a) W[p * 3 + a] = fma(v[8 + p], v[2 + a], fma(v[8 + P + p], v[5 + a], W[p * 3 + a]));
+      for (int k = 0; k < 6; ++k) v[k] = V6[(size_t)j * 6 + k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { v[6 + k] = gp[(size_t)j * 3 + k]; D[k] = Dp2[(size_t)j * 3 + k]; }
     }
-    double* z0 = Zt + (3 * (size_t)j) * LD + (size_t)pair_cam[q] * P;
+    double Li[6];
+    chol3_inv(v, D, lam, Li);
+    if (lane == 0) {
 #pragma unroll
-    for (int p = 0; p < P; ++p) {
-      z0[p] = W[p * 3] * Li[0];
-      z0[LD + p] = W[p * 3] * Li[1] + W[p * 3 + 1] * Li[2];
-      z0[2 * LD + p] = W[p * 3] * Li[3] + W[p * 3 + 1] * Li[4] + W[p * 3 + 2] * Li[5];
+      for (int k = 0; k < 6; ++k) Linv6[(size_t)j * 6 + k] = Li[k];
+      tvec[3 * (size_t)j + 0] = Li[0] * v[6];
+      tvec[3 * (size_t)j + 1] = Li[1] * v[6] + Li[2] * v[7];
+      tvec[3 * (size_t)j + 2] = Li[3] * v[6] + Li[4] * v[7] + Li[5] * v[8];
+    }
+    for (int pos = s + lane; pos < e; pos += 32) {
+      const int cam = pm_cam[pos];
+      if (pos > s && pm_cam[pos - 1] == cam) continue;  // not the first of its (point, camera) run
+      double W[P * 3];
+#pragma unroll
+      for (int k = 0; k < P * 3; ++k) W[k] = 0.0;
+      int r = pos;
+      do {
+        const double* src = jrows + (size_t)pm_row[r] * RT::ROWD;
+        double w[RT::ROWD];
+#pragma unroll
+        for (int k = 0; k < RT::ROWD; k += 4) ld256(src + k, w[k], w[k + 1], w[k + 2], w[k + 3]);
+        // w: [f0 f1 | Jp0(3) Jp1(3) | Jc0(P) Jc1(P)]
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+            W[p * 3 + a] = fma(w[8 + p], w[2 + a], fma(w[8 + P + p], w[5 + a], W[p * 3 + a]));
+        ++r;
+      } while (r < e && pm_cam[r] == cam);
+      double* z0 = Zt + (3 * (size_t)j) * LD + (size_t)cam * P;
+      double z[3][P];
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        z[0][p] = W[p * 3] * Li[0];
+        z[1][p] = W[p * 3] * Li[1] + W[p * 3 + 1] * Li[2];
+        z[2][p] = W[p * 3] * Li[3] + W[p * 3 + 1] * Li[4] + W[p * 3 + 2] * Li[5];
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        if constexpr (P == 6) {
+          double2* dst = reinterpret_cast<double2*>(z0 + a * LD);  // cam*48 B and LD*8 B are 16-byte multiples
+          dst[0] = make_double2(z[a][0], z[a][1]);
+          dst[1] = make_double2(z[a][2], z[a][3]);
+          dst[2] = make_double2(z[a][4], z[a][5]);
+        } else {
+#pragma unroll
+          for (int p = 0; p < P; ++p) z0[a * LD + p] = z[a][p];
+        }
+      }
+    }
+  }
+  if constexpr (FUSED) {
+    if (lane == 0) wmax[wid] = gm;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double m = 0.0;
+      for (int w = 0; w < PT_WARPS; ++w) m = fmax(m, wmax[w]);
+      if (m > 0.0) atomicMax(gmax_bits, (unsigned long long)__double_as_longlong(m));
     }
   }
 }
@@ -442,13 +484,26 @@ pt_zbuild_kernel(const int* __restrict__ pt_pair_start, const int* __restrict__ 
 // 1-D bulk async copies (TMA engine, mbarrier completion), SY_STAGES deep; each thread owns a
 // 6x6 register tile.  Diagonal tiles also accumulate Z t (the reduced right-hand side).
 // ---------------------------------------------------------------------------------------------
+constexpr int SY_LDS = SY_TILE + 4;  // padded smem row stride (doubles): conflict-free DMMA fragment loads
+
 struct SyrkSmem {
-  double A[SY_STAGES][SY_KC * SY_TILE];
-  double B[SY_STAGES][SY_KC * SY_TILE];
+  double A[SY_STAGES][SY_KC * SY_LDS];
+  double B[SY_STAGES][SY_KC * SY_LDS];
   double t[SY_STAGES][SY_KC];
   unsigned long long full[SY_STAGES];
+  unsigned long long empty[SY_STAGES];
 };
 
+// D(8x8) += A(8x4) * B(4x8), fp64 tensor path (SASS: DMMA.8x8x4)
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// 8 warps as 4 (row groups of 24) x 2 (column groups of 48): 3 x 6 DMMA tiles per warp.
+// Fragment ownership (PTX m8n8k4.f64): A[row = lane>>2][k = lane&3], B[k = lane&3][col = lane>>2],
+// C[row = lane>>2][col = 2*(lane&3) + {0,1}];  A[i][k] = Zt[k][I*96 + i], B[k][j] = Zt[k][J*96 + j].
 __global__ void __launch_bounds__(SY_THREADS, 1)
 schur_syrk_kernel(const double* __restrict__ Zt, size_t LD, const double* __restrict__ tvec, int n_chunks,
                   int n_split, const int* __restrict__ tileI, const int* __restrict__ tileJ, int n_tiles,
@@ -461,71 +516,80 @@ schur_syrk_kernel(const double* __restrict__ Zt, size_t LD, const double* __rest
   const int c0 = (int)(((long long)n_chunks * split) / n_split);
   const int c1 = (int)(((long long)n_chunks * (split + 1)) / n_split);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int ty = tid >> 4, tx = tid & 15;
+  const int wr = wid >> 1, wc = wid & 1;  // warp row group (24 rows), column group (48 cols)
+  const int fr = lane >> 2, fk = lane & 3;
 
   if (tid == 0) {
-    for (int s = 0; s < SY_STAGES; ++s) mbar_init(&sm.full[s], 1);
+    for (int s = 0; s < SY_STAGES; ++s) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], SY_CONSUMER_WARPS);
+    }
     mbar_fence_init();
   }
   __syncthreads();
 
-  const uint32_t tile_bytes = SY_KC * SY_TILE * 8;
-  const uint32_t stage_bytes = tile_bytes * (diag ? 1u : 2u) + (diag ? SY_KC * 8u : 0u);
-  auto issue = [&](int chunk, int stage) {
-    // called by warp 0 only
-    if (lane == 0) mbar_expect_tx(&sm.full[stage], stage_bytes);
-    __syncwarp();
-    const size_t k = (size_t)chunk * SY_KC + lane;
-    bulk_g2s(&sm.A[stage][lane * SY_TILE], Zt + k * LD + (size_t)I * SY_TILE, SY_TILE * 8, &sm.full[stage]);
-    if (!diag)
-      bulk_g2s(&sm.B[stage][lane * SY_TILE], Zt + k * LD + (size_t)J * SY_TILE, SY_TILE * 8, &sm.full[stage]);
-    else if (lane == 0)
-      bulk_g2s(&sm.t[stage][0], tvec + (size_t)chunk * SY_KC, SY_KC * 8, &sm.full[stage]);
-  };
+  const uint32_t row_bytes = SY_TILE * 8;
+  const uint32_t stage_bytes = SY_KC * row_bytes * (diag ? 1u : 2u) + (diag ? SY_KC * 8u : 0u);
+  const int n_it = c1 - c0;
 
-  double acc[6][6];
+  double acc[3][6][2];
 #pragma unroll
-  for (int u = 0; u < 6; ++u)
+  for (int u = 0; u < 3; ++u)
 #pragma unroll
-    for (int v = 0; v < 6; ++v) acc[u][v] = 0.0;
+    for (int v = 0; v < 6; ++v) acc[u][v][0] = acc[u][v][1] = 0.0;
   double tacc = 0.0;
 
-  if (wid == 0)
-    for (int s = 0; s < SY_STAGES - 1 && c0 + s < c1; ++s) issue(c0 + s, s);
-
-  for (int c = c0; c < c1; ++c) {
-    const int it = c - c0, stage = it % SY_STAGES;
-    mbar_wait(&sm.full[stage], (uint32_t)((it / SY_STAGES) & 1));
-    const double* As = sm.A[stage];
-    const double* Bs = diag ? sm.A[stage] : sm.B[stage];
-#pragma unroll 4
-    for (int k = 0; k < SY_KC; ++k) {
-      const double2* ap = reinterpret_cast<const double2*>(As + k * SY_TILE + ty * 6);
-      const double2* bp = reinterpret_cast<const double2*>(Bs + k * SY_TILE + tx * 6);
-      const double2 a01 = ap[0], a23 = ap[1], a45 = ap[2];
-      const double2 b01 = bp[0], b23 = bp[1], b45 = bp[2];
-      const double a[6] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y};
-      const double b[6] = {b01.x, b01.y, b23.x, b23.y, b45.x, b45.y};
-#pragma unroll
-      for (int u = 0; u < 6; ++u)
-#pragma unroll
-        for (int v = 0; v < 6; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+  if (wid == SY_CONSUMER_WARPS) {
+    // ---- producer warp: runs ahead, one k row per lane per tile, stage recycled on `empty` ----
+    for (int it = 0; it < n_it; ++it) {
+      const int stage = it % SY_STAGES, round = it / SY_STAGES;
+      if (round > 0) mbar_wait(&sm.empty[stage], (uint32_t)((round - 1) & 1));
+      if (lane == 0) mbar_expect_tx(&sm.full[stage], stage_bytes);
+      __syncwarp();
+      const size_t k = (size_t)(c0 + it) * SY_KC + lane;
+      bulk_g2s(&sm.A[stage][lane * SY_LDS], Zt + k * LD + (size_t)I * SY_TILE, row_bytes, &sm.full[stage]);
+      if (!diag)
+        bulk_g2s(&sm.B[stage][lane * SY_LDS], Zt + k * LD + (size_t)J * SY_TILE, row_bytes, &sm.full[stage]);
+      else if (lane == 0)
+        bulk_g2s(&sm.t[stage][0], tvec + (size_t)(c0 + it) * SY_KC, SY_KC * 8, &sm.full[stage]);
     }
-    if (diag && tid < SY_TILE) {
+  } else {
+    // ---- consumer warps ----
+    for (int it = 0; it < n_it; ++it) {
+      const int stage = it % SY_STAGES;
+      mbar_wait(&sm.full[stage], (uint32_t)((it / SY_STAGES) & 1));
+      const double* As = sm.A[stage] + fk * SY_LDS + wr * 24 + fr;
+      const double* Bs = (diag ? sm.A[stage] : sm.B[stage]) + fk * SY_LDS + wc * 48 + fr;
+#pragma unroll
+      for (int ks = 0; ks < SY_KC / 4; ++ks) {
+        double a[3], b[6];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) a[u] = As[ks * 4 * SY_LDS + u * 8];
+#pragma unroll
+        for (int v = 0; v < 6; ++v) b[v] = Bs[ks * 4 * SY_LDS + v * 8];
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+#pragma unroll
+          for (int v = 0; v < 6; ++v) dmma884(acc[u][v][0], acc[u][v][1], a[u], b[v]);
+      }
+      if (diag && tid < SY_TILE) {
+        const double* Ad = sm.A[stage];
 #pragma unroll 8
-      for (int k = 0; k < SY_KC; ++k) tacc = fma(As[k * SY_TILE + tid], sm.t[stage][k], tacc);
-    }
-    __syncthreads();
-    if (wid == 0) {
-      const int nc = c + SY_STAGES - 1;
-      if (nc < c1) issue(nc, (it + SY_STAGES - 1) % SY_STAGES);
+        for (int k = 0; k < SY_KC; ++k) tacc = fma(Ad[k * SY_LDS + tid], sm.t[stage][k], tacc);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.empty[stage]);
     }
   }
+  if (wid == SY_CONSUMER_WARPS) return;
   double* out = part + ((size_t)split * n_tiles + tile) * (SY_TILE * SY_TILE);
 #pragma unroll
-  for (int u = 0; u < 6; ++u)
+  for (int u = 0; u < 3; ++u)
 #pragma unroll
-    for (int v = 0; v < 6; ++v) out[(ty * 6 + u) * SY_TILE + tx * 6 + v] = acc[u][v];
+    for (int v = 0; v < 6; ++v) {
+      const int r = wr * 24 + u * 8 + fr, cc = wc * 48 + v * 8 + 2 * fk;
+      *reinterpret_cast<double2*>(out + r * SY_TILE + cc) = make_double2(acc[u][v][0], acc[u][v][1]);
+    }
   if (diag && tid < SY_TILE) tpart[((size_t)split * n_tiles + tile) * SY_TILE + tid] = tacc;
 }
 
@@ -869,6 +933,20 @@ __global__ void make_keys_kernel(const int* __restrict__ a, const int* __restric
     vals[i] = i;
   }
 }
+// key = ((pt / blk) * n_cams + cam) * blk + pt % blk over the point-major positions
+__global__ void make_block_keys_kernel(const int* __restrict__ pm_pt, const int* __restrict__ pm_cam, int n_cams,
+                                       int blk, int n, unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const unsigned long long pt = (unsigned long long)pm_pt[i];
+    keys[i] = ((pt / blk) * (unsigned long long)n_cams + (unsigned long long)pm_cam[i]) * blk + pt % blk;
+    vals[i] = i;
+  }
+}
+__global__ void invert_perm_kernel(const int* __restrict__ perm, int n, int* __restrict__ inv) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) inv[perm[i]] = i;
+}
 // sorted keys = major*nb + minor -> major/minor arrays
 __global__ void split_keys_kernel(const unsigned long long* __restrict__ keys, long long nb, int n,
                                   int* __restrict__ major, int* __restrict__ minor) {
@@ -889,37 +967,17 @@ __global__ void lower_bound_kernel(const int* __restrict__ sorted_major, int n, 
   }
   start[j] = lo;
 }
-__global__ void pair_flag_kernel(const unsigned long long* __restrict__ keys, int n, int* __restrict__ flag) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) flag[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
-}
-__global__ void pair_scatter_kernel(const int* __restrict__ flag, const int* __restrict__ pidx, int n,
-                                    const int* __restrict__ pm_cam, int* __restrict__ pair_start,
-                                    int* __restrict__ pair_cam, int n_pairs) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && flag[i]) {
-    pair_start[pidx[i]] = i;
-    pair_cam[pidx[i]] = pm_cam[i];
-  }
-  if (i == 0) pair_start[n_pairs] = n;
-}
-__global__ void pt_pair_start_kernel(const int* __restrict__ pt_start, const int* __restrict__ pidx, int n_pts, int n,
-                                     int n_pairs, int* __restrict__ pt_pair_start) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j <= n_pts) {
-    int s = pt_start[j];
-    pt_pair_start[j] = (s < n) ? pidx[s] : n_pairs;
-  }
-}
-// camera-major gather: q -> row (point-major slot) -> original observation
-__global__ void cm_gather_kernel(const int* __restrict__ cm_row, const int* __restrict__ pm_orig,
-                                 const int* __restrict__ pm_pt, const double2* __restrict__ obs_xy, int n,
+// camera-major gather: q -> point-major position -> (Jacobian row, point, original observation, xy)
+__global__ void cm_gather_kernel(const int* __restrict__ cm_pos, const int* __restrict__ pm_row,
+                                 const int* __restrict__ pm_orig, const int* __restrict__ pm_pt,
+                                 const double2* __restrict__ obs_xy, int n, int* __restrict__ cm_row,
                                  int* __restrict__ cm_pt, int* __restrict__ cm_orig, double2* __restrict__ cm_xy) {
   int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q < n) {
-    const int row = cm_row[q];
-    const int o = pm_orig[row];
-    cm_pt[q] = pm_pt[row];
+    const int pos = cm_pos[q];
+    const int o = pm_orig[pos];
+    cm_row[q] = pm_row[pos];
+    cm_pt[q] = pm_pt[pos];
     cm_orig[q] = o;
     cm_xy[q] = obs_xy[o];
   }
@@ -932,13 +990,14 @@ __global__ void validate_kernel(const int* __restrict__ cam, const int* __restri
 
 // Jacobian rows (point-major) -> caller-order dense blocks Jc (n_obs,2,9), Jp (n_obs,2,3)
 template <int P>
-__global__ void rows_to_blocks_kernel(const double* __restrict__ jrows, const int* __restrict__ pm_orig, int n,
-                                      double* __restrict__ Jc, double* __restrict__ Jp) {
+__global__ void rows_to_blocks_kernel(const double* __restrict__ jrows, const int* __restrict__ pm_row,
+                                      const int* __restrict__ pm_orig, int n, double* __restrict__ Jc,
+                                      double* __restrict__ Jp) {
   using RT = RowT<P>;
-  int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= n) return;
-  const double* v = jrows + (size_t)row * RT::ROWD;
-  const size_t o = (size_t)pm_orig[row];
+  int pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= n) return;
+  const double* v = jrows + (size_t)pm_row[pos] * RT::ROWD;
+  const size_t o = (size_t)pm_orig[pos];
   for (int k = 0; k < 6; ++k) Jp[o * 6 + k] = v[2 + k];
   for (int i = 0; i < 2; ++i)
     for (int p = 0; p < 9; ++p) Jc[o * 18 + i * 9 + p] = (p < P) ? v[8 + i * P + p] : 0.0;
