@@ -15,6 +15,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <cub/cub.cuh>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -49,16 +51,110 @@ std::atomic<long long> g_launches{0};
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
-template <typename T>
-int dalloc(T** p, size_t n) {
-  *p = nullptr;
-  if (n == 0) n = 1;
-  cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+// Process-wide caching allocator: repeated problem_create / destroy cycles (one per
+// CaptureVolume.optimize call: linear -> soft_l1 -> filter -> linear) reuse device and pinned
+// blocks instead of paying cudaMalloc / cudaFree / cudaMallocHost each time.
+struct BlockCache {
+  std::mutex mu;
+  std::multimap<std::pair<int, size_t>, void*> free_dev;  // (device, bytes) -> ptr
+  std::map<void*, std::pair<int, size_t>> live_dev;
+  std::multimap<size_t, void*> free_host;
+  std::map<void*, size_t> live_host;
+  size_t cached_bytes = 0;
+  static constexpr size_t kMaxCached = 16ull << 30;
+};
+BlockCache g_cache;
+
+size_t round_bytes(size_t b) { return (std::max<size_t>(b, 1) + 511) & ~(size_t)511; }
+
+int cached_malloc(void** p, size_t bytes) {
+  bytes = round_bytes(bytes);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  {
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    auto it = g_cache.free_dev.find({dev, bytes});
+    if (it != g_cache.free_dev.end()) {
+      *p = it->second;
+      g_cache.free_dev.erase(it);
+      g_cache.cached_bytes -= bytes;
+      g_cache.live_dev[*p] = {dev, bytes};
+      return CB_OK;
+    }
+  }
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess) {
+    // release the cache and retry once
+    std::vector<void*> drop;
+    {
+      std::lock_guard<std::mutex> lk(g_cache.mu);
+      for (auto& kv : g_cache.free_dev) drop.push_back(kv.second);
+      g_cache.free_dev.clear();
+      g_cache.cached_bytes = 0;
+    }
+    cudaGetLastError();
+    for (void* q : drop) cudaFree(q);
+    e = cudaMalloc(p, bytes);
+  }
   if (e != cudaSuccess) {
     g_last_error = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+    cudaGetLastError();
+    *p = nullptr;
     return CB_E_NOMEM;
   }
+  std::lock_guard<std::mutex> lk(g_cache.mu);
+  g_cache.live_dev[*p] = {dev, bytes};
   return CB_OK;
+}
+
+void cached_free(void* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_cache.mu);
+  auto it = g_cache.live_dev.find(p);
+  if (it == g_cache.live_dev.end()) { cudaFree(p); return; }
+  auto key = it->second;
+  g_cache.live_dev.erase(it);
+  if (g_cache.cached_bytes + key.second > BlockCache::kMaxCached) { cudaFree(p); return; }
+  g_cache.free_dev.insert({key, p});
+  g_cache.cached_bytes += key.second;
+}
+
+int cached_malloc_host(void** p, size_t bytes) {
+  bytes = round_bytes(bytes);
+  {
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    auto it = g_cache.free_host.find(bytes);
+    if (it != g_cache.free_host.end()) {
+      *p = it->second;
+      g_cache.free_host.erase(it);
+      g_cache.live_host[*p] = bytes;
+      return CB_OK;
+    }
+  }
+  cudaError_t e = cudaMallocHost(p, bytes);
+  if (e != cudaSuccess) {
+    g_last_error = std::string("cudaMallocHost: ") + cudaGetErrorString(e);
+    cudaGetLastError();
+    *p = nullptr;
+    return CB_E_NOMEM;
+  }
+  std::lock_guard<std::mutex> lk(g_cache.mu);
+  g_cache.live_host[*p] = bytes;
+  return CB_OK;
+}
+
+void cached_free_host(void* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_cache.mu);
+  auto it = g_cache.live_host.find(p);
+  if (it == g_cache.live_host.end()) { cudaFreeHost(p); return; }
+  g_cache.free_host.insert({it->second, p});
+  g_cache.live_host.erase(it);
+}
+
+template <typename T>
+int dalloc(T** p, size_t n) {
+  return cached_malloc((void**)p, std::max<size_t>(n, 1) * sizeof(T));
 }
 
 }  // namespace
@@ -127,7 +223,7 @@ int build_indices(CbBaProblem* p, const int* d_obs_cam, const int* d_obs_pt, con
   int bad = 0;
   CB_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
   CB_CUDA(cudaStreamSynchronize(st));
-  cudaFree(d_bad);
+  cached_free(d_bad);
   if (bad) {
     g_last_error = "obs_cam / obs_pt index out of range in " + std::to_string(bad) + " observations";
     return CB_E_INVALID;
@@ -143,7 +239,7 @@ int build_indices(CbBaProblem* p, const int* d_obs_cam, const int* d_obs_pt, con
   size_t tb = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in, k_out, v_in, v_out, n, 0, 64, st);
   void* d_tmp;
-  CB_CUDA(cudaMalloc(&d_tmp, std::max<size_t>(tb, 16)));
+  CB_TRY(cached_malloc(&d_tmp, std::max<size_t>(tb, 16)));
 
   // (1) point-major order: key = pt * n_cams + cam, stable -> ties keep caller order
   CB_LAUNCH(cb::make_keys_kernel, G, TB, 0, st, d_obs_pt, d_obs_cam, (long long)p->n_cams, n, k_in, v_in);
@@ -198,8 +294,8 @@ int build_indices(CbBaProblem* p, const int* d_obs_cam, const int* d_obs_pt, con
   }
   CB_CUDA(cudaMemcpyAsync(p->d_cam_chunk_start, ccs.data(), sizeof(int) * ccs.size(), cudaMemcpyHostToDevice, st));
   CB_CUDA(cudaStreamSynchronize(st));
-  cudaFree(d_tmp); cudaFree(k_in); cudaFree(k_out); cudaFree(v_in); cudaFree(v_out);
-  cudaFree(pm_pt); cudaFree(pm_cam); cudaFree(cm_cam);
+  cached_free(d_tmp); cached_free(k_in); cached_free(k_out); cached_free(v_in); cached_free(v_out);
+  cached_free(pm_pt); cached_free(pm_cam); cached_free(cm_cam);
   return CB_OK;
 }
 
@@ -593,9 +689,9 @@ int64_t cb_ba_launch_count(void) { return (int64_t)g_launches.load(); }
 int cb_ba_problem_destroy(CbBaProblem* p) {
   if (!p) return CB_OK;
   cudaSetDevice(p->device);
-  for (void* a : p->allocs) cudaFree(a);
-  if (p->h_sc) cudaFreeHost(p->h_sc);
-  if (p->h_x) cudaFreeHost(p->h_x);
+  for (void* a : p->allocs) cached_free(a);
+  cached_free_host(p->h_sc);
+  cached_free_host(p->h_x);
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
   if (p->ev2) cudaEventDestroy(p->ev2);
@@ -669,7 +765,7 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
     d_cam = t_cam; d_pt = t_pt; d_xy = t_xy;
   }
   int rc = build_indices(p, d_cam, d_pt, d_xy, st);
-  if (t_cam) { cudaFree(t_cam); cudaFree(t_pt); cudaFree(t_xy); }
+  if (t_cam) { cached_free(t_cam); cached_free(t_pt); cached_free(t_xy); }
   CB_TRY(rc);
 
   // Schur tile tables
@@ -720,8 +816,8 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
   CB_CUDA(cudaMemsetAsync(p->d_tpart, 0, sizeof(double) * (size_t)p->n_split * p->n_tiles * cb::SY_TILE, st));
   CB_CUDA(cudaMemsetAsync(p->d_red2, 0, sizeof(double) * 8, st));
   CB_CUDA(cudaMemsetAsync(p->d_jrows, 0, sizeof(double) * (size_t)std::max(n, 1) * ROWD, st));
-  CB_CUDA(cudaMallocHost((void**)&p->h_sc, sizeof(double) * (cb::SC_COUNT + 4 + p->red_slots)));
-  CB_CUDA(cudaMallocHost((void**)&p->h_x, sizeof(double) * ((size_t)p->n_params + 1)));
+  CB_TRY(cached_malloc_host((void**)&p->h_sc, sizeof(double) * (cb::SC_COUNT + 4 + p->red_slots)));
+  CB_TRY(cached_malloc_host((void**)&p->h_x, sizeof(double) * ((size_t)p->n_params + 1)));
   CB_CUDA(cudaEventCreate(&p->ev0)); CB_CUDA(cudaEventCreate(&p->ev1));
   CB_CUDA(cudaEventCreate(&p->ev2)); CB_CUDA(cudaEventCreate(&p->ev3));
   CB_CUDA(cudaFuncSetAttribute(cb::schur_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -816,7 +912,7 @@ int cb_ba_jacobian_blocks(CbBaProblem* p, const double* x, double* Jc, double* J
   cudaError_t e1 = cudaMemcpyAsync(Jc, dJc, sizeof(double) * 18 * (size_t)n, cudaMemcpyDeviceToHost, st);
   cudaError_t e2 = cudaMemcpyAsync(Jp, dJp, sizeof(double) * 6 * (size_t)n, cudaMemcpyDeviceToHost, st);
   cudaError_t e3 = cudaStreamSynchronize(st);
-  cudaFree(dJc); cudaFree(dJp);
+  cached_free(dJc); cached_free(dJp);
   CB_CUDA(e1); CB_CUDA(e2); CB_CUDA(e3);
   return CB_OK;
 }
@@ -903,7 +999,7 @@ int cb_ba_error_order_stats(CbBaProblem* p, const double* x, double q_percent, d
   cudaMemcpyAsync(hi, d_hi, sizeof(double) * p->n_cams, cudaMemcpyDeviceToHost, st);
   cudaMemcpyAsync(hc.data(), d_cnt, sizeof(long long) * p->n_cams, cudaMemcpyDeviceToHost, st);
   cudaError_t e = cudaStreamSynchronize(st);
-  cudaFree(d_lo); cudaFree(d_hi); cudaFree(d_cnt);
+  cached_free(d_lo); cached_free(d_hi); cached_free(d_cnt);
   CB_CUDA(e);
   for (int c = 0; c < p->n_cams; ++c) count[c] = hc[c];
   return CB_OK;

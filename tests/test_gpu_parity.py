@@ -316,3 +316,50 @@ def test_error_order_statistics_match_numpy(q):
         v = (len(ec) - 1) * q / 100.0
         assert lo[c] == ec[int(np.floor(v))]
         assert hi[c] == ec[min(int(np.floor(v)) + 1, len(ec) - 1)]
+
+
+# ---------------------------------------------------------------------------------------------
+# filter + re-solve (capture_volume.py:607-753, calibrate_extrinsics.py:206-250)
+# ---------------------------------------------------------------------------------------------
+def test_percentile_filter_keep_mask_matches_reference_exactly():
+    from caliscope_b200 import filtering
+
+    g, rig = load_golden("session4_refine0.npz")
+    with make_problem(rig) as p:
+        keep, err, thr = filtering.filter_by_percentile_error(p, g["x_default"], rig.obs_cam, float(g["filt_percentile"]))
+    assert np.abs(err - g["filt_err"]).max() < 1e-9
+    assert np.abs(thr - g["filt_thresholds"]).max() < 1e-9
+    assert np.array_equal(keep, g["filt_keep"])  # index-exact keep mask of the reference's filter
+
+
+def test_keep_mask_min_per_camera_floor():
+    from caliscope_b200 import filtering
+
+    err = np.array([5.0, 1.0, 3.0, 2.0, 9.0, 0.5, 0.7])
+    cam = np.array([0, 0, 0, 0, 0, 1, 1])
+    keep = filtering.keep_mask(err, cam, np.array([0.1, 10.0]), min_per_camera=3)
+    assert keep.tolist() == [False, True, True, True, False, True, True]
+    with pytest.raises(ValueError):
+        filtering.keep_mask(err, cam, np.array([0.1, 10.0]), min_per_camera=0)
+
+
+def test_solve_filter_resolve_loop_matches_scipy_stage_by_stage():
+    """BASELINE config 5 at reduced size: outliers -> linear -> soft_l1 -> 2.5 % cull -> linear."""
+    from caliscope_b200 import pipeline, synthetic
+
+    r = synthetic.make_rig(8, 1500, 30000, seed=4, outlier_frac=0.02)
+    out = pipeline.solve_filter_resolve(r.cam_flags, r.cam_const, r.n_pts, r.obs_cam, r.obs_pt, r.obs_xy, r.x0)
+    rig = O.Rig(r.cam_flags, r.cam_const, r.n_pts, r.obs_cam, r.obs_pt, r.obs_xy)
+    s1 = O.solve_scipy(rig, r.x0)
+    assert abs(out.rmse_px[0] - O.overall_rmse_px(s1.x, rig)) < 1e-6
+    fs = 1.0 / float(np.median(r.cam_const[:, 0]))
+    # the robust stage is compared at a tight tolerance (the reference's ftol=1e-4 run is loose)
+    s2 = O.solve_scipy(rig, out.stages[0].x, loss="soft_l1", f_scale=fs, ftol=1e-12, xtol=1e-12, gtol=1e-12, max_nfev=200)
+    assert out.stages[1].cost <= s2.cost * (1 + 1e-4)
+    # cull: most injected outliers removed, nearly all inliers kept
+    assert out.keep.sum() >= 0.97 * r.n_obs
+    assert out.keep[r.outlier_mask].mean() < 0.2
+    rig3 = O.Rig(r.cam_flags, r.cam_const, r.n_pts, r.obs_cam[out.keep], r.obs_pt[out.keep], r.obs_xy[out.keep])
+    s3 = O.solve_scipy(rig3, out.stages[1].x)
+    assert abs(out.rmse_px[2] - O.overall_rmse_px(s3.x, rig3)) < 1e-6
+    assert out.rmse_px[2] < out.rmse_px[0]

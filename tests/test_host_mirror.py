@@ -154,3 +154,28 @@ def test_engine_fails_loudly_without_a_gpu():
     g, rig = load_golden("small_pinhole_refine0.npz")
     with pytest.raises(cb.EngineUnavailable):
         cb.BAProblem(rig.cam_flags, rig.cam_const, rig.n_pts, rig.obs_cam, rig.obs_pt, rig.obs_xy)
+
+
+def test_filter_keep_mask_and_percentile_rule_on_reference_errors():
+    """Host half of the percentile filter against the reference's own filter output (golden)."""
+    from caliscope_b200 import filtering
+    from tests._util import load_golden
+
+    g, rig = load_golden("session4_refine0.npz")
+    keep = filtering.keep_mask(g["filt_err"], g["filt_cam"], g["filt_thresholds"], int(g["filt_min_per_camera"]))
+    assert np.array_equal(keep, g["filt_keep"])
+    q = 100.0 - float(g["filt_percentile"])
+    for c in range(rig.n_cams):
+        e = np.sort(g["filt_err"][g["filt_cam"] == c])
+        v = (len(e) - 1) * (q / 100.0)
+        lo, hi = e[int(np.floor(v))], e[min(int(np.floor(v)) + 1, len(e) - 1)]
+        t = filtering._numpy_linear_interp(np.array([lo]), np.array([hi]), np.array([v - np.floor(v)]))[0]
+        assert t == np.percentile(e, q) == g["filt_thresholds"][c]
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 7, 100, 1001):
+        e = np.sort(rng.uniform(0, 5, n))
+        for q in (0.0, 2.5, 50.0, 97.5, 100.0, 33.3):
+            v = (n - 1) * (q / 100.0)
+            lo, hi = e[int(np.floor(v))], e[min(int(np.floor(v)) + 1, n - 1)]
+            t = filtering._numpy_linear_interp(np.array([lo]), np.array([hi]), np.array([v - np.floor(v)]))[0]
+            assert t == np.percentile(e, q)
