@@ -384,8 +384,12 @@ int launch_pcg(CbBaProblem* p, double tol2, int max_iter, cudaStream_t st) {
   cfg.numAttrs = 1;
   const double* S = p->d_red;
   const double* b = p->d_red + (size_t)p->nP * p->nP;
-  CB_CUDA(cudaLaunchKernelEx(&cfg, cb::pcg_cluster_kernel, S, b, (const double*)p->d_Minv, p->nP, p->P, p->pcg_rows,
-                             p->pcg_slab_smem, tol2, max_iter, p->d_dc, p->d_sc));
+  if (p->pcg_slab_smem)
+    CB_CUDA(cudaLaunchKernelEx(&cfg, cb::pcg_cluster_kernel<true>, S, b, (const double*)p->d_Minv, p->nP, p->P,
+                               p->pcg_rows, tol2, max_iter, p->d_dc, p->d_sc));
+  else
+    CB_CUDA(cudaLaunchKernelEx(&cfg, cb::pcg_cluster_kernel<false>, S, b, (const double*)p->d_Minv, p->nP, p->P,
+                               p->pcg_rows, tol2, max_iter, p->d_dc, p->d_sc));
   g_launches.fetch_add(1);
   return CB_OK;
 }
@@ -602,11 +606,12 @@ int lm_solve(CbBaProblem* p, const CbBaOptions* opt, double* x_inout, CbBaResult
 int choose_pcg_config(CbBaProblem* p) {
   const int nP = p->nP, P = p->P;
   const size_t nPa = (size_t)((nP + 7) & ~7);
-  const size_t fixed = (6 * nPa + 32 + (((size_t)(nP / P) * P * P + 7) & ~(size_t)7)) * sizeof(double);
+  const size_t fixed = (7 * nPa + 2 * (cb::PCG_THREADS / 32) + (((size_t)(nP / P) * P * P + 7) & ~(size_t)7)) * sizeof(double);
   int max_optin = 0;
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device);
   const size_t budget = (size_t)std::max(max_optin, 48 * 1024);
-  cudaFuncSetAttribute(cb::pcg_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaFuncSetAttribute(cb::pcg_cluster_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaFuncSetAttribute(cb::pcg_cluster_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   const int cands[5] = {1, 2, 4, 8, 16};
   for (int pass = 0; pass < 2; ++pass) {  // pass 0: slab in shared memory, pass 1: slab streamed from L2
     for (int ci = 0; ci < 5; ++ci) {
@@ -615,8 +620,8 @@ int choose_pcg_config(CbBaProblem* p) {
       const int rows = (nP + cs - 1) / cs;
       const size_t smem = fixed + (pass == 0 ? (size_t)rows * nP * sizeof(double) : 0);
       if (smem > budget) continue;
-      if (cudaFuncSetAttribute(cb::pcg_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-          cudaSuccess) {
+      const void* fn = pass == 0 ? (const void*)cb::pcg_cluster_kernel<true> : (const void*)cb::pcg_cluster_kernel<false>;
+      if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         continue;
       }
@@ -630,7 +635,7 @@ int choose_pcg_config(CbBaProblem* p) {
       cfg.attrs = at;
       cfg.numAttrs = 1;
       int ncl = 0;
-      if (cudaOccupancyMaxActiveClusters(&ncl, cb::pcg_cluster_kernel, &cfg) != cudaSuccess || ncl < 1) {
+      if (cudaOccupancyMaxActiveClusters(&ncl, fn, &cfg) != cudaSuccess || ncl < 1) {
         cudaGetLastError();
         continue;
       }

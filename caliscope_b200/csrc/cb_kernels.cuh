@@ -344,17 +344,17 @@ __device__ __forceinline__ void chol3_inv(const double* V6, const double* D2, do
   const double d0 = D2[0] > 0.0 ? D2[0] : 1.0, d1 = D2[1] > 0.0 ? D2[1] : 1.0, d2 = D2[2] > 0.0 ? D2[2] : 1.0;
   const double e00 = V6[0] + lam * d0, e01 = V6[1], e02 = V6[2], e11 = V6[3] + lam * d1, e12 = V6[4],
                e22 = V6[5] + lam * d2;
+  // reciprocal square roots instead of sqrt + divide (fp64 div/sqrt expand to long instruction sequences)
   bool ok = e00 > 0.0;
-  const double l00 = sqrt(ok ? e00 : 1.0);
-  const double l10 = e01 / l00, l20 = e02 / l00;
+  const double i00 = rsqrt(ok ? e00 : 1.0);
+  const double l10 = e01 * i00, l20 = e02 * i00;
   const double t11 = e11 - l10 * l10;
   ok = ok && t11 > 0.0;
-  const double l11 = sqrt(ok ? t11 : 1.0);
-  const double l21 = (e12 - l20 * l10) / l11;
+  const double i11 = rsqrt(ok ? t11 : 1.0);
+  const double l21 = (e12 - l20 * l10) * i11;
   const double t22 = e22 - l20 * l20 - l21 * l21;
   ok = ok && t22 > 0.0;
-  const double l22 = sqrt(ok ? t22 : 1.0);
-  const double i00 = 1.0 / l00, i11 = 1.0 / l11, i22 = 1.0 / l22;
+  const double i22 = rsqrt(ok ? t22 : 1.0);
   const double i10 = -l10 * i00 * i11;
   const double i21 = -l21 * i11 * i22;
   const double i20 = -(l20 * i00 + l21 * i10) * i22;
@@ -704,115 +704,157 @@ __global__ void block_inverse_kernel(const double* __restrict__ S, int nP, int n
 }
 
 // ---------------------------------------------------------------------------------------------
-// PCG on the dense reduced camera system S x = -b, one thread-block cluster.  Each CTA owns a
-// slab of rows of S (kept in shared memory when it fits), computes its slice of q = S p and
-// writes it into every CTA's q buffer through distributed shared memory; all vector updates and
-// dot products are then done redundantly by every CTA, so one cluster barrier per iteration.
+// PCG on the dense reduced camera system S x = -b, one thread-block cluster.  Each CTA owns a slab
+// of rows of S (resident in shared memory when it fits), computes its slice of w = S u and writes
+// it into every CTA's w buffer through distributed shared memory; all vector updates and dot
+// products are replicated in every CTA, so the only cluster-wide exchange is that slice.
+// Chronopoulos-Gear single-reduction recurrence: one fused (r.u, w.u) reduction and one cluster
+// barrier per iteration:
+//   u = M^-1 r, w = S u, g = r.u, d = w.u, beta = g/g_old, alpha = g / (d - beta g / alpha_old)
+//   p = u + beta p, q = w + beta q (= S p), x += alpha p, r -= alpha q
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double block_sum_512(double v, double* sh) {
-  v = warp_sum(v);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  __syncthreads();  // protect sh reuse
-  if (lane == 0) sh[wid] = v;
-  __syncthreads();
-  double t = (lane < (PCG_THREADS >> 5)) ? sh[lane] : 0.0;
-  t = warp_sum(t);
-  return t;  // same value in every thread
-}
-
+template <bool SLAB_SMEM>
 __global__ void __launch_bounds__(PCG_THREADS, 1)
 pcg_cluster_kernel(const double* __restrict__ S, const double* __restrict__ bvec, const double* __restrict__ Minv,
-                   int nP, int P, int rows_per, int slab_in_smem, double tol2, int max_iter,
-                   double* __restrict__ xout, double* __restrict__ sc) {
+                   int nP, int P, int rows_per, double tol2, int max_iter, double* __restrict__ xout,
+                   double* __restrict__ sc) {
   extern __shared__ __align__(16) double psm[];
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  // layout: x r z p q0 q1 (nPa each) | sh[32] | Minv (n_cams*P*P) | slab
+  constexpr int NW = PCG_THREADS / 32;
+  // layout: x r u p q w0 w1 (nPa each) | sh[2*NW] | Minv (n_cams*P*P) | slab
   const int nPa = (nP + 7) & ~7;
   double* vx = psm;
   double* vr = vx + nPa;
-  double* vz = vr + nPa;
-  double* vp = vz + nPa;
-  double* vq = vp + nPa;  // two buffers
-  double* sh = vq + 2 * nPa;
-  double* Mi = sh + 32;
+  double* vu = vr + nPa;
+  double* vp = vu + nPa;
+  double* vq = vp + nPa;
+  double* vw = vq + nPa;  // two buffers
+  double* sh = vw + 2 * nPa;
+  double* Mi = sh + 2 * NW;
   double* slab = Mi + (((size_t)(nP / P) * P * P + 7) & ~(size_t)7);
   const int row0 = rank * rows_per;
   const int nrows = max(0, min(rows_per, nP - row0));
   const int n_cams = nP / P;
 
   for (int i = tid; i < n_cams * P * P; i += PCG_THREADS) Mi[i] = Minv[i];
-  if (slab_in_smem)
+  if (SLAB_SMEM)
     for (size_t i = tid; i < (size_t)nrows * nP; i += PCG_THREADS) slab[i] = S[(size_t)row0 * nP + i];
-  const double* Srows = slab_in_smem ? slab : (S + (size_t)row0 * nP);
   for (int i = tid; i < nP; i += PCG_THREADS) {
-    vx[i] = 0.0;
+    vx[i] = 0.0; vp[i] = 0.0; vq[i] = 0.0;
     vr[i] = -bvec[i];
   }
   __syncthreads();
-  for (int i = tid; i < nP; i += PCG_THREADS) {
-    const int c = i / P, a = i % P;
-    double s = 0.0;
-    for (int b = 0; b < P; ++b) s += Mi[(size_t)c * P * P + a * P + b] * vr[c * P + b];
-    vz[i] = s;
-    vp[i] = s;
-  }
-  __syncthreads();
-  double part = 0.0;
-  for (int i = tid; i < nP; i += PCG_THREADS) part += vr[i] * vz[i];
-  double rz = block_sum_512(part, sh);
-  const double rz0 = rz;
-  int it = 0, flag = 0;
-  cluster.sync();
-  if (rz0 > 0.0) {
-    for (it = 0; it < max_iter; ++it) {
-      double* q = vq + (it & 1) * nPa;
-      // q_slab = S_slab p : one warp per row
-      for (int r = wid; r < nrows; r += PCG_THREADS / 32) {
-        const double* srow = Srows + (size_t)r * nP;
-        double s = 0.0;
-        for (int k = lane; k < nP; k += 32) s = fma(srow[k], vp[k], s);
-        s = warp_sum(s);
-        if (lane < csize) {
-          double* dst = cluster.map_shared_rank(q, lane);
-          dst[row0 + r] = s;
+
+  auto precond = [&]() {  // u = M^-1 r (block diagonal), own indices
+    for (int i = tid; i < nP; i += PCG_THREADS) {
+      const int c = i / P, a = i - c * P;
+      const double* m = Mi + (size_t)c * P * P + a * P;
+      const double* rr = vr + c * P;
+      double s = 0.0;
+      for (int b = 0; b < P; ++b) s = fma(m[b], rr[b], s);
+      vu[i] = s;
+    }
+  };
+  auto matvec = [&](double* wbuf) {  // w[row0 + r] = S_row . u for this CTA's rows -> every CTA's wbuf
+    for (int r0 = wid * 3; r0 < nrows; r0 += NW * 3) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+      const bool h1 = r0 + 1 < nrows, h2 = r0 + 2 < nrows;
+      if (SLAB_SMEM) {
+        const double* a0 = slab + (size_t)r0 * nP;
+        const double* a1 = a0 + (h1 ? nP : 0);
+        const double* a2 = a0 + (h2 ? 2 * nP : 0);
+        for (int k = lane; k < nP; k += 32) {
+          const double uk = vu[k];
+          s0 = fma(a0[k], uk, s0); s1 = fma(a1[k], uk, s1); s2 = fma(a2[k], uk, s2);
+        }
+      } else {
+        const double* a0 = S + (size_t)(row0 + r0) * nP;
+        const double* a1 = a0 + (h1 ? nP : 0);
+        const double* a2 = a0 + (h2 ? 2 * nP : 0);
+        for (int k = lane; k < nP; k += 32) {
+          const double uk = vu[k];
+          s0 = fma(__ldg(a0 + k), uk, s0); s1 = fma(__ldg(a1 + k), uk, s1); s2 = fma(__ldg(a2 + k), uk, s2);
         }
       }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      if (lane < csize) {
+        double* dst = cluster.map_shared_rank(wbuf, lane) + row0 + r0;
+        dst[0] = s0;
+        if (h1) dst[1] = s1;
+        if (h2) dst[2] = s2;
+      }
+    }
+  };
+  auto dots = [&](const double* wbuf, double& g, double& d) {  // g = r.u, d = w.u (identical in every thread)
+    double pg = 0.0, pd = 0.0;
+    for (int i = tid; i < nP; i += PCG_THREADS) {
+      const double ui = vu[i];
+      pg = fma(vr[i], ui, pg);
+      pd = fma(wbuf[i], ui, pd);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      pg += __shfl_xor_sync(0xffffffffu, pg, o);
+      pd += __shfl_xor_sync(0xffffffffu, pd, o);
+    }
+    if (lane == 0) { sh[wid] = pg; sh[NW + wid] = pd; }
+    __syncthreads();
+    g = 0.0; d = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) { g += sh[w]; d += sh[NW + w]; }
+  };
+
+  precond();
+  __syncthreads();
+  cluster.sync();  // every CTA of the cluster is running before the first remote write
+  matvec(vw);
+  cluster.sync();
+  double g, d;
+  dots(vw, g, d);
+  const double g0 = g;
+  double alpha = (d > 0.0) ? g / d : 0.0, beta = 0.0;
+  int it = 0, flag = 0;
+  if (g0 > 0.0 && !(d > 0.0)) flag = 1;
+  if (g0 > 0.0 && flag == 0) {
+    for (it = 1; it <= max_iter; ++it) {
+      const double* wcur = vw + ((it - 1) & 1) * nPa;
+      double* wnext = vw + (it & 1) * nPa;
+      for (int i = tid; i < nP; i += PCG_THREADS) {
+        const double pi = fma(beta, vp[i], vu[i]);
+        const double qi = fma(beta, vq[i], wcur[i]);
+        vp[i] = pi; vq[i] = qi;
+        vx[i] = fma(alpha, pi, vx[i]);
+        vr[i] = fma(-alpha, qi, vr[i]);
+      }
+      __syncthreads();
+      precond();
+      __syncthreads();
+      matvec(wnext);
       cluster.sync();
-      part = 0.0;
-      for (int i = tid; i < nP; i += PCG_THREADS) part += vp[i] * q[i];
-      const double pq = block_sum_512(part, sh);
-      if (!(pq > 0.0)) { flag = 1; break; }
-      const double alpha = rz / pq;
-      for (int i = tid; i < nP; i += PCG_THREADS) {
-        vx[i] = fma(alpha, vp[i], vx[i]);
-        vr[i] = fma(-alpha, q[i], vr[i]);
-      }
-      __syncthreads();
-      part = 0.0;
-      for (int i = tid; i < nP; i += PCG_THREADS) {
-        const int c = i / P, a = i % P;
-        double s = 0.0;
-        for (int b = 0; b < P; ++b) s += Mi[(size_t)c * P * P + a * P + b] * vr[c * P + b];
-        vz[i] = s;
-        part += vr[i] * s;
-      }
-      const double rz_new = block_sum_512(part, sh);
-      if (!(rz_new == rz_new)) { flag = 2; break; }
-      if (rz_new <= tol2 * rz0) { rz = rz_new; ++it; break; }
-      const double beta = rz_new / rz;
-      rz = rz_new;
-      for (int i = tid; i < nP; i += PCG_THREADS) vp[i] = fma(beta, vp[i], vz[i]);
-      __syncthreads();
+      double gn, dn;
+      dots(wnext, gn, dn);
+      if (!(gn == gn) || !(dn == dn)) { flag = 2; break; }
+      if (gn <= tol2 * g0) { g = gn; break; }
+      beta = gn / g;
+      const double den = dn - beta * gn / alpha;
+      if (!(den > 0.0)) { flag = 1; g = gn; break; }
+      alpha = gn / den;
+      g = gn;
     }
   }
-  cluster.sync();  // nobody exits while peers may still write into its q buffers
+  cluster.sync();  // nobody exits while peers may still write into its w buffers
   if (rank == 0) {
     for (int i = tid; i < nP; i += PCG_THREADS) xout[i] = vx[i];
     if (tid == 0) {
       sc[SC_PCG_ITS] = (double)it;
-      sc[SC_PCG_REL] = (rz0 > 0.0) ? sqrt(fabs(rz) / rz0) : 0.0;
+      sc[SC_PCG_REL] = (g0 > 0.0) ? sqrt(fabs(g) / g0) : 0.0;
       sc[SC_PCG_FLAG] = (double)flag;
     }
   }

@@ -353,9 +353,14 @@ def test_solve_filter_resolve_loop_matches_scipy_stage_by_stage():
     s1 = O.solve_scipy(rig, r.x0)
     assert abs(out.rmse_px[0] - O.overall_rmse_px(s1.x, rig)) < 1e-6
     fs = 1.0 / float(np.median(r.cam_const[:, 0]))
-    # the robust stage is compared at a tight tolerance (the reference's ftol=1e-4 run is loose)
-    s2 = O.solve_scipy(rig, out.stages[0].x, loss="soft_l1", f_scale=fs, ftol=1e-12, xtol=1e-12, gtol=1e-12, max_nfev=200)
-    assert out.stages[1].cost <= s2.cost * (1 + 1e-4)
+    # the pipeline's robust stage runs at the reference's loose ftol=1e-4 (calibrate_extrinsics.py:236), so its
+    # end point is only required to have improved; the robust optimum itself is compared at tight tolerance
+    assert out.stages[1].cost < out.stages[1].initial_cost
+    s2 = O.solve_scipy(rig, out.stages[0].x, loss="soft_l1", f_scale=fs, ftol=1e-12, xtol=1e-12, gtol=1e-12, max_nfev=300)
+    with make_problem(rig) as p:
+        t2 = p.solve(out.stages[0].x, loss="soft_l1", f_scale=fs, ftol=1e-12, xtol=1e-12, gtol=1e-12, max_nfev=300)
+    print(f"soft_l1 tight: gpu cost {t2.cost:.12e} nfev {t2.nfev} | scipy cost {s2.cost:.12e} nfev {s2.nfev}")
+    assert t2.cost <= s2.cost * (1 + 1e-7)
     # cull: most injected outliers removed, nearly all inliers kept
     assert out.keep.sum() >= 0.97 * r.n_obs
     assert out.keep[r.outlier_mask].mean() < 0.2
