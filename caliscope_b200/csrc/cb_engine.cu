@@ -173,7 +173,9 @@ struct CbBaProblem {
   int *d_cm_pt = nullptr, *d_cm_row = nullptr, *d_cm_orig = nullptr, *d_cam_start = nullptr;
   int *d_chunk_cam = nullptr, *d_chunk_begin = nullptr, *d_chunk_end = nullptr, *d_cam_chunk_start = nullptr;
   int *d_pt_start = nullptr, *d_pm_orig = nullptr, *d_pm_cam = nullptr, *d_pm_row = nullptr;
-  int *d_tileI = nullptr, *d_tileJ = nullptr, *d_tile_of = nullptr;
+  int *d_tile_of = nullptr, *d_tile_slot_start = nullptr, *d_tile_slots = nullptr;
+  cb::SyItem* d_items = nullptr;
+  int n_items = 0, n_slots = 0;
   unsigned char* d_active = nullptr;
   double *d_lo = nullptr, *d_hi = nullptr;
   // work buffers
@@ -347,12 +349,11 @@ int build_system(CbBaProblem* p, double lam, bool new_lin, const CbBaOptions* op
     CB_LAUNCH((cb::pt_build_kernel<P, false>), p->pt_blocks, cb::PT_WARPS * 32, 0, st, p->d_pt_start, p->d_pm_cam,
               p->d_pm_row, p->n_pts, p->d_jrows, p->d_V6, p->d_gp, p->d_Dp2, lam, p->d_Linv6, p->d_tvec, p->d_Zt, (size_t)p->LD,
               p->d_gmax);
-  CB_LAUNCH(cb::schur_syrk_kernel, p->n_tiles * p->n_split, cb::SY_THREADS, sizeof(cb::SyrkSmem), st, p->d_Zt,
-            (size_t)p->LD, p->d_tvec, p->k_chunks, p->n_split, p->d_tileI, p->d_tileJ, p->n_tiles, p->d_part,
-            p->d_tpart);
+  CB_LAUNCH(cb::schur_syrk_kernel, p->n_items, cb::SY_THREADS, sizeof(cb::SyrkSmem), st, p->d_Zt, (size_t)p->LD,
+            p->d_tvec, p->d_items, p->d_part, p->d_tpart);
   const size_t nfin = (size_t)p->nP * p->nP + p->nP + 1;
-  CB_LAUNCH((cb::schur_finalize_kernel<P>), cdiv((long long)nfin, 256), 256, 0, st, p->nP, p->n_blk, p->n_tiles,
-            p->n_split, p->d_tile_of, p->d_part, p->d_tpart, p->d_Upk, p->d_gc, p->d_costsum, p->d_red);
+  CB_LAUNCH((cb::schur_finalize_kernel<P>), cdiv((long long)nfin, 256), 256, 0, st, p->nP, p->n_blk, p->d_tile_of,
+            p->d_tile_slot_start, p->d_tile_slots, p->d_part, p->d_tpart, p->d_Upk, p->d_gc, p->d_costsum, p->d_red);
   // gradient inf-norm over points: one slot per rank so a SUM all-reduce carries the max
   const size_t slot0 = (size_t)p->nP * p->nP + 3 * (size_t)p->nP + 1;
   CB_CUDA(cudaMemsetAsync(p->d_red + slot0, 0, sizeof(double) * p->red_slots, st));
@@ -367,6 +368,12 @@ int build_system(CbBaProblem* p, double lam, bool new_lin, const CbBaOptions* op
   CB_LAUNCH(cb::post_reduce_kernel, 1, 256, 0, st, p->nP, lam, new_lin ? 1 : 0, p->d_red, p->d_Dc2, p->d_active,
             p->d_sc);
   return CB_OK;
+}
+
+using PcgFn = void (*)(const double*, const double*, const double*, int, int, double, int, double*, double*);
+PcgFn pcg_fn(bool slab_smem, int P) {
+  if (P == 6) return slab_smem ? cb::pcg_cluster_kernel<true, 6> : cb::pcg_cluster_kernel<false, 6>;
+  return slab_smem ? cb::pcg_cluster_kernel<true, 9> : cb::pcg_cluster_kernel<false, 9>;
 }
 
 int launch_pcg(CbBaProblem* p, double tol2, int max_iter, cudaStream_t st) {
@@ -384,12 +391,9 @@ int launch_pcg(CbBaProblem* p, double tol2, int max_iter, cudaStream_t st) {
   cfg.numAttrs = 1;
   const double* S = p->d_red;
   const double* b = p->d_red + (size_t)p->nP * p->nP;
-  if (p->pcg_slab_smem)
-    CB_CUDA(cudaLaunchKernelEx(&cfg, cb::pcg_cluster_kernel<true>, S, b, (const double*)p->d_Minv, p->nP, p->P,
-                               p->pcg_rows, tol2, max_iter, p->d_dc, p->d_sc));
-  else
-    CB_CUDA(cudaLaunchKernelEx(&cfg, cb::pcg_cluster_kernel<false>, S, b, (const double*)p->d_Minv, p->nP, p->P,
-                               p->pcg_rows, tol2, max_iter, p->d_dc, p->d_sc));
+  auto fn = pcg_fn(p->pcg_slab_smem != 0, p->P);
+  CB_CUDA(cudaLaunchKernelEx(&cfg, fn, S, b, (const double*)p->d_Minv, p->nP, p->pcg_rows, tol2, max_iter, p->d_dc,
+                             p->d_sc));
   g_launches.fetch_add(1);
   return CB_OK;
 }
@@ -610,17 +614,20 @@ int choose_pcg_config(CbBaProblem* p) {
   int max_optin = 0;
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device);
   const size_t budget = (size_t)std::max(max_optin, 48 * 1024);
-  cudaFuncSetAttribute(cb::pcg_cluster_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-  cudaFuncSetAttribute(cb::pcg_cluster_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaFuncSetAttribute((const void*)pcg_fn(true, P), cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaFuncSetAttribute((const void*)pcg_fn(false, P), cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   const int cands[5] = {1, 2, 4, 8, 16};
+  int min_cs = 1;
+  if (const char* ev = std::getenv("CB_PCG_MIN_CLUSTER")) min_cs = std::max(1, std::atoi(ev));
   for (int pass = 0; pass < 2; ++pass) {  // pass 0: slab in shared memory, pass 1: slab streamed from L2
     for (int ci = 0; ci < 5; ++ci) {
       const int cs = cands[ci];
       if (pass == 1 && cs != 8) continue;
+      if (pass == 0 && cs < min_cs) continue;
       const int rows = (nP + cs - 1) / cs;
       const size_t smem = fixed + (pass == 0 ? (size_t)rows * nP * sizeof(double) : 0);
       if (smem > budget) continue;
-      const void* fn = pass == 0 ? (const void*)cb::pcg_cluster_kernel<true> : (const void*)cb::pcg_cluster_kernel<false>;
+      const void* fn = (const void*)pcg_fn(pass == 0, P);
       if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         continue;
@@ -773,18 +780,67 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
   if (t_cam) { cached_free(t_cam); cached_free(t_pt); cached_free(t_xy); }
   CB_TRY(rc);
 
-  // Schur tile tables
-  std::vector<int> tI, tJ, tof((size_t)p->n_blk * p->n_blk, -1);
-  for (int I = 0; I < p->n_blk; ++I)
-    for (int J = I; J < p->n_blk; ++J) {
-      tof[(size_t)I * p->n_blk + J] = (int)tI.size();
-      tI.push_back(I); tJ.push_back(J);
+  // Schur work items: off-diagonal tiles and pairs of diagonal tiles, each split over k so that the
+  // grid is one CTA per SM with equal DMMA work (a diagonal pair costs 45/36 of a full tile per chunk).
+  {
+    const int nb = p->n_blk;
+    std::vector<int> tof((size_t)nb * nb, -1);
+    int nt = 0;
+    for (int I = 0; I < nb; ++I)
+      for (int J = I; J < nb; ++J) tof[(size_t)I * nb + J] = nt++;
+    struct Group { int kind, I, J; double w; };
+    std::vector<Group> groups;
+    for (int I = 0; I < nb; ++I)
+      for (int J = I + 1; J < nb; ++J) groups.push_back({0, I, J, 1.0});
+    for (int I = 0; I < nb; I += 2) {
+      if (I + 1 < nb) groups.push_back({1, I, I + 1, 1.25});
+      else groups.push_back({1, I, -1, 0.75});
     }
-  CB_TRY(palloc(p, &p->d_tileI, tI.size())); CB_TRY(palloc(p, &p->d_tileJ, tI.size()));
-  CB_TRY(palloc(p, &p->d_tile_of, tof.size()));
-  CB_CUDA(cudaMemcpyAsync(p->d_tileI, tI.data(), sizeof(int) * tI.size(), cudaMemcpyHostToDevice, st));
-  CB_CUDA(cudaMemcpyAsync(p->d_tileJ, tJ.data(), sizeof(int) * tJ.size(), cudaMemcpyHostToDevice, st));
-  CB_CUDA(cudaMemcpyAsync(p->d_tile_of, tof.data(), sizeof(int) * tof.size(), cudaMemcpyHostToDevice, st));
+    double W = 0.0;
+    for (auto& g : groups) W += g.w;
+    std::vector<cb::SyItem> items;
+    std::vector<std::vector<int>> slots_of(nt);
+    int slot = 0;
+    for (auto& g : groups) {
+      int n = (int)std::floor(p->num_sms * g.w / W);
+      n = std::max(1, std::min(n, p->k_chunks));
+      for (int s = 0; s < n; ++s) {
+        cb::SyItem it;
+        it.kind = g.kind; it.I = g.I; it.J = g.J;
+        it.c0 = (int)(((long long)p->k_chunks * s) / n);
+        it.c1 = (int)(((long long)p->k_chunks * (s + 1)) / n);
+        it.slotA = slot++;
+        it.slotB = -1;
+        if (g.kind == 0) {
+          slots_of[tof[(size_t)g.I * nb + g.J]].push_back(it.slotA);
+        } else {
+          slots_of[tof[(size_t)g.I * nb + g.I]].push_back(it.slotA);
+          if (g.J >= 0) {
+            it.slotB = slot++;
+            slots_of[tof[(size_t)g.J * nb + g.J]].push_back(it.slotB);
+          }
+        }
+        items.push_back(it);
+      }
+    }
+    p->n_items = (int)items.size();
+    p->n_slots = slot;
+    std::vector<int> sstart(nt + 1, 0), sflat;
+    for (int t = 0; t < nt; ++t) {
+      sstart[t] = (int)sflat.size();
+      sflat.insert(sflat.end(), slots_of[t].begin(), slots_of[t].end());
+    }
+    sstart[nt] = (int)sflat.size();
+    CB_TRY(palloc(p, &p->d_items, items.size()));
+    CB_TRY(palloc(p, &p->d_tile_of, tof.size()));
+    CB_TRY(palloc(p, &p->d_tile_slot_start, sstart.size()));
+    CB_TRY(palloc(p, &p->d_tile_slots, sflat.size()));
+    CB_CUDA(cudaMemcpyAsync(p->d_items, items.data(), sizeof(cb::SyItem) * items.size(), cudaMemcpyHostToDevice, st));
+    CB_CUDA(cudaMemcpyAsync(p->d_tile_of, tof.data(), sizeof(int) * tof.size(), cudaMemcpyHostToDevice, st));
+    CB_CUDA(cudaMemcpyAsync(p->d_tile_slot_start, sstart.data(), sizeof(int) * sstart.size(), cudaMemcpyHostToDevice, st));
+    CB_CUDA(cudaMemcpyAsync(p->d_tile_slots, sflat.data(), sizeof(int) * sflat.size(), cudaMemcpyHostToDevice, st));
+    CB_CUDA(cudaStreamSynchronize(st));  // the host vectors above go out of scope
+  }
   std::vector<unsigned char> act((size_t)p->nP, 0);
   for (int c = 0; c < p->n_cams; ++c)
     for (int a = 0; a < p->h_cam_off[c + 1] - p->h_cam_off[c]; ++a) act[(size_t)c * p->P + a] = 1;
@@ -807,8 +863,8 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
   CB_TRY(palloc(p, &p->d_Dc2, p->nP)); CB_TRY(palloc(p, &p->d_Linv6, 6 * npts));
   CB_TRY(palloc(p, &p->d_tvec, (size_t)p->K_pad));
   CB_TRY(palloc(p, &p->d_Zt, (size_t)p->K_pad * p->LD));
-  CB_TRY(palloc(p, &p->d_part, (size_t)p->n_split * p->n_tiles * cb::SY_TILE * cb::SY_TILE));
-  CB_TRY(palloc(p, &p->d_tpart, (size_t)p->n_split * p->n_tiles * cb::SY_TILE));
+  CB_TRY(palloc(p, &p->d_part, (size_t)p->n_slots * cb::SY_TILE * cb::SY_TILE));
+  CB_TRY(palloc(p, &p->d_tpart, (size_t)p->n_slots * cb::SY_TILE));
   CB_TRY(palloc(p, &p->d_red, p->red_len()));
   CB_TRY(palloc(p, &p->d_Minv, (size_t)p->n_cams * p->P * p->P));
   CB_TRY(palloc(p, &p->d_dc, p->nP)); CB_TRY(palloc(p, &p->d_dp, 3 * npts));
@@ -818,9 +874,9 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
   CB_TRY(palloc(p, &p->d_out2, 2 * (size_t)std::max(n, 1)));
   CB_CUDA(cudaMemsetAsync(p->d_Zt, 0, sizeof(double) * (size_t)p->K_pad * p->LD, st));
   CB_CUDA(cudaMemsetAsync(p->d_tvec, 0, sizeof(double) * p->K_pad, st));
-  CB_CUDA(cudaMemsetAsync(p->d_tpart, 0, sizeof(double) * (size_t)p->n_split * p->n_tiles * cb::SY_TILE, st));
+  CB_CUDA(cudaMemsetAsync(p->d_tpart, 0, sizeof(double) * (size_t)p->n_slots * cb::SY_TILE, st));
+  CB_CUDA(cudaMemsetAsync(p->d_part, 0, sizeof(double) * (size_t)p->n_slots * cb::SY_TILE * cb::SY_TILE, st));
   CB_CUDA(cudaMemsetAsync(p->d_red2, 0, sizeof(double) * 8, st));
-  CB_CUDA(cudaMemsetAsync(p->d_jrows, 0, sizeof(double) * (size_t)std::max(n, 1) * ROWD, st));
   CB_TRY(cached_malloc_host((void**)&p->h_sc, sizeof(double) * (cb::SC_COUNT + 4 + p->red_slots)));
   CB_TRY(cached_malloc_host((void**)&p->h_x, sizeof(double) * ((size_t)p->n_params + 1)));
   CB_CUDA(cudaEventCreate(&p->ev0)); CB_CUDA(cudaEventCreate(&p->ev1));
@@ -980,6 +1036,28 @@ int cb_ba_normal_equations(CbBaProblem* p, const double* x, double lambda, int32
   cudaStream_t st = (cudaStream_t)stream;
   return p->P == 6 ? normal_eq_impl<6>(p, x, lambda, loss, f_scale, cost, U, gc, V, gp, S, b, dc, dp, st)
                    : normal_eq_impl<9>(p, x, lambda, loss, f_scale, cost, U, gc, V, gp, S, b, dc, dp, st);
+}
+
+// Diagnostic: time `reps` launches of the PCG kernel on the system left by the last
+// cb_ba_normal_equations call, forcing exactly max_iter iterations (tolerance 0).
+int cb_ba_debug_pcg_time(CbBaProblem* p, int max_iter, int reps, double* ms_per_launch, void* stream) {
+  if (!p || !ms_per_launch || reps <= 0) { g_last_error = "cb_ba_debug_pcg_time: bad argument"; return CB_E_INVALID; }
+  CB_CUDA(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  CB_TRY(launch_pcg(p, 0.0, max_iter, st));
+  CB_CUDA(cudaEventRecord(p->ev2, st));
+  for (int r = 0; r < reps; ++r) CB_TRY(launch_pcg(p, 0.0, max_iter, st));
+  CB_CUDA(cudaEventRecord(p->ev3, st));
+  CB_CUDA(cudaEventSynchronize(p->ev3));
+  float ms = 0.f;
+  CB_CUDA(cudaEventElapsedTime(&ms, p->ev2, p->ev3));
+  *ms_per_launch = ms / reps;
+  double t[cb::SC_COUNT];
+  CB_CUDA(cudaMemcpy(t, p->d_sc, sizeof(t), cudaMemcpyDeviceToHost));
+  std::fprintf(stderr, "[pcg profile] cycles/iteration on CTA 0 thread 0: update %.0f precond %.0f matvec %.0f cluster-barrier %.0f dots %.0f\n",
+               t[cb::SC_PCG_T0] / max_iter, t[cb::SC_PCG_T0 + 1] / max_iter, t[cb::SC_PCG_T0 + 2] / max_iter,
+               t[cb::SC_PCG_T0 + 3] / max_iter, t[cb::SC_PCG_T0 + 4] / max_iter);
+  return CB_OK;
 }
 
 int cb_ba_error_order_stats(CbBaProblem* p, const double* x, double q_percent, double* err, double* lo, double* hi,

@@ -45,7 +45,7 @@ struct RowT {
 // scalar slots (device double array `sc`)
 enum {
   SC_COST = 0, SC_GNORM_C, SC_COST_NEW, SC_PRED_C, SC_STEP2_C, SC_X2_C, SC_PRED_P, SC_STEP2_P, SC_X2_P,
-  SC_PCG_ITS, SC_PCG_REL, SC_PCG_FLAG, SC_GNORM_P, SC_COUNT = 16
+  SC_PCG_ITS, SC_PCG_REL, SC_PCG_FLAG, SC_GNORM_P, SC_PCG_T0 = 16, SC_COUNT = 24
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -501,22 +501,36 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
-// 8 warps as 4 (row groups of 24) x 2 (column groups of 48): 3 x 6 DMMA tiles per warp.
+// One CTA of the Schur product: either an off-diagonal 96x96 tile (I < J) or a PAIR of diagonal tiles
+// (I, I) and (I2, I2) whose upper triangles together are one tile's worth of work, over k chunks [c0, c1).
+struct SyItem {
+  int kind;    // 0: off-diagonal tile, 1: diagonal pair (I2 < 0: single diagonal tile)
+  int I, J;    // kind 0: tile (I, J); kind 1: tiles (I, I) and (J, J) with J = I2
+  int c0, c1;  // k-chunk range
+  int slotA, slotB;  // partial-output slots (kind 0 uses slotA only)
+};
+
 // Fragment ownership (PTX m8n8k4.f64): A[row = lane>>2][k = lane&3], B[k = lane&3][col = lane>>2],
 // C[row = lane>>2][col = 2*(lane&3) + {0,1}];  A[i][k] = Zt[k][I*96 + i], B[k][j] = Zt[k][J*96 + j].
+//
+// kind 0: 8 consumer warps as 4 (row groups of 24) x 2 (column groups of 48): 3 x 6 DMMA tiles per warp.
+// kind 1: only the 10 upper-triangular 24x24 blocks of each diagonal tile are formed; the 20 blocks of the
+//         pair are dealt 3/3/3/3/2/2/2/2 to warps 0..7 so every SM sub-partition (warps w and w+4) carries 5.
+__constant__ signed char SY_DIAG_BLOCKS[8][3][3] = {
+    // {tile select, block row, block col}; select -1 = no block
+    {{0, 0, 0}, {0, 0, 1}, {0, 0, 2}}, {{0, 0, 3}, {0, 1, 3}, {0, 2, 3}}, {{0, 1, 1}, {0, 1, 2}, {0, 2, 2}},
+    {{0, 3, 3}, {1, 3, 3}, {1, 2, 2}}, {{1, 0, 0}, {1, 0, 1}, {-1, 0, 0}}, {{1, 0, 2}, {1, 0, 3}, {-1, 0, 0}},
+    {{1, 1, 1}, {1, 1, 2}, {-1, 0, 0}}, {{1, 1, 3}, {1, 2, 3}, {-1, 0, 0}}};
+
 __global__ void __launch_bounds__(SY_THREADS, 1)
-schur_syrk_kernel(const double* __restrict__ Zt, size_t LD, const double* __restrict__ tvec, int n_chunks,
-                  int n_split, const int* __restrict__ tileI, const int* __restrict__ tileJ, int n_tiles,
-                  double* __restrict__ part, double* __restrict__ tpart) {
+schur_syrk_kernel(const double* __restrict__ Zt, size_t LD, const double* __restrict__ tvec,
+                  const SyItem* __restrict__ items, double* __restrict__ part, double* __restrict__ tpart) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SyrkSmem& sm = *reinterpret_cast<SyrkSmem*>(smem_raw);
-  const int tile = blockIdx.x / n_split, split = blockIdx.x % n_split;
-  const int I = tileI[tile], J = tileJ[tile];
-  const bool diag = (I == J);
-  const int c0 = (int)(((long long)n_chunks * split) / n_split);
-  const int c1 = (int)(((long long)n_chunks * (split + 1)) / n_split);
+  const SyItem item = items[blockIdx.x];
+  const bool diag = item.kind == 1;
+  const bool two = diag ? (item.J >= 0) : true;  // second smem tile in use
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int wr = wid >> 1, wc = wid & 1;  // warp row group (24 rows), column group (48 cols)
   const int fr = lane >> 2, fk = lane & 3;
 
   if (tid == 0) {
@@ -529,15 +543,8 @@ schur_syrk_kernel(const double* __restrict__ Zt, size_t LD, const double* __rest
   __syncthreads();
 
   const uint32_t row_bytes = SY_TILE * 8;
-  const uint32_t stage_bytes = SY_KC * row_bytes * (diag ? 1u : 2u) + (diag ? SY_KC * 8u : 0u);
-  const int n_it = c1 - c0;
-
-  double acc[3][6][2];
-#pragma unroll
-  for (int u = 0; u < 3; ++u)
-#pragma unroll
-    for (int v = 0; v < 6; ++v) acc[u][v][0] = acc[u][v][1] = 0.0;
-  double tacc = 0.0;
+  const uint32_t stage_bytes = SY_KC * row_bytes * (two ? 2u : 1u) + (diag ? SY_KC * 8u : 0u);
+  const int n_it = item.c1 - item.c0;
 
   if (wid == SY_CONSUMER_WARPS) {
     // ---- producer warp: runs ahead, one k row per lane per tile, stage recycled on `empty` ----
@@ -546,20 +553,29 @@ schur_syrk_kernel(const double* __restrict__ Zt, size_t LD, const double* __rest
       if (round > 0) mbar_wait(&sm.empty[stage], (uint32_t)((round - 1) & 1));
       if (lane == 0) mbar_expect_tx(&sm.full[stage], stage_bytes);
       __syncwarp();
-      const size_t k = (size_t)(c0 + it) * SY_KC + lane;
-      bulk_g2s(&sm.A[stage][lane * SY_LDS], Zt + k * LD + (size_t)I * SY_TILE, row_bytes, &sm.full[stage]);
-      if (!diag)
-        bulk_g2s(&sm.B[stage][lane * SY_LDS], Zt + k * LD + (size_t)J * SY_TILE, row_bytes, &sm.full[stage]);
-      else if (lane == 0)
-        bulk_g2s(&sm.t[stage][0], tvec + (size_t)(c0 + it) * SY_KC, SY_KC * 8, &sm.full[stage]);
+      const size_t k = (size_t)(item.c0 + it) * SY_KC + lane;
+      bulk_g2s(&sm.A[stage][lane * SY_LDS], Zt + k * LD + (size_t)item.I * SY_TILE, row_bytes, &sm.full[stage]);
+      if (two)
+        bulk_g2s(&sm.B[stage][lane * SY_LDS], Zt + k * LD + (size_t)item.J * SY_TILE, row_bytes, &sm.full[stage]);
+      if (diag && lane == 0)
+        bulk_g2s(&sm.t[stage][0], tvec + (size_t)(item.c0 + it) * SY_KC, SY_KC * 8, &sm.full[stage]);
     }
-  } else {
-    // ---- consumer warps ----
+    return;
+  }
+
+  if (!diag) {
+    // ---------------- off-diagonal tile ----------------
+    const int wr = wid >> 1, wc = wid & 1;
+    double acc[3][6][2];
+#pragma unroll
+    for (int u = 0; u < 3; ++u)
+#pragma unroll
+      for (int v = 0; v < 6; ++v) acc[u][v][0] = acc[u][v][1] = 0.0;
     for (int it = 0; it < n_it; ++it) {
       const int stage = it % SY_STAGES;
       mbar_wait(&sm.full[stage], (uint32_t)((it / SY_STAGES) & 1));
       const double* As = sm.A[stage] + fk * SY_LDS + wr * 24 + fr;
-      const double* Bs = (diag ? sm.A[stage] : sm.B[stage]) + fk * SY_LDS + wc * 48 + fr;
+      const double* Bs = sm.B[stage] + fk * SY_LDS + wc * 48 + fr;
 #pragma unroll
       for (int ks = 0; ks < SY_KC / 4; ++ks) {
         double a[3], b[6];
@@ -572,30 +588,86 @@ schur_syrk_kernel(const double* __restrict__ Zt, size_t LD, const double* __rest
 #pragma unroll
           for (int v = 0; v < 6; ++v) dmma884(acc[u][v][0], acc[u][v][1], a[u], b[v]);
       }
-      if (diag && tid < SY_TILE) {
-        const double* Ad = sm.A[stage];
-#pragma unroll 8
-        for (int k = 0; k < SY_KC; ++k) tacc = fma(Ad[k * SY_LDS + tid], sm.t[stage][k], tacc);
-      }
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.empty[stage]);
     }
+    double* out = part + (size_t)item.slotA * (SY_TILE * SY_TILE);
+#pragma unroll
+    for (int u = 0; u < 3; ++u)
+#pragma unroll
+      for (int v = 0; v < 6; ++v) {
+        const int r = wr * 24 + u * 8 + fr, cc = wc * 48 + v * 8 + 2 * fk;
+        *reinterpret_cast<double2*>(out + r * SY_TILE + cc) = make_double2(acc[u][v][0], acc[u][v][1]);
+      }
+    return;
   }
-  if (wid == SY_CONSUMER_WARPS) return;
-  double* out = part + ((size_t)split * n_tiles + tile) * (SY_TILE * SY_TILE);
+
+  // ---------------- diagonal pair ----------------
+  int bsel[3], brow[3], bcol[3];
 #pragma unroll
-  for (int u = 0; u < 3; ++u)
+  for (int b = 0; b < 3; ++b) {
+    bsel[b] = SY_DIAG_BLOCKS[wid][b][0];
+    brow[b] = SY_DIAG_BLOCKS[wid][b][1];
+    bcol[b] = SY_DIAG_BLOCKS[wid][b][2];
+    if (bsel[b] == 1 && !two) bsel[b] = -1;
+  }
+  double acc[3][3][3][2];
 #pragma unroll
-    for (int v = 0; v < 6; ++v) {
-      const int r = wr * 24 + u * 8 + fr, cc = wc * 48 + v * 8 + 2 * fk;
-      *reinterpret_cast<double2*>(out + r * SY_TILE + cc) = make_double2(acc[u][v][0], acc[u][v][1]);
+  for (int b = 0; b < 3; ++b)
+#pragma unroll
+    for (int u = 0; u < 3; ++u)
+#pragma unroll
+      for (int v = 0; v < 3; ++v) acc[b][u][v][0] = acc[b][u][v][1] = 0.0;
+  double tacc = 0.0;
+  const int trow = tid % SY_TILE, tsel = tid / SY_TILE;  // threads 0..191: one row of Z t each
+  const bool tact = tid < 2 * SY_TILE && (tsel == 0 || two);
+  for (int it = 0; it < n_it; ++it) {
+    const int stage = it % SY_STAGES;
+    mbar_wait(&sm.full[stage], (uint32_t)((it / SY_STAGES) & 1));
+#pragma unroll
+    for (int ks = 0; ks < SY_KC / 4; ++ks) {
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        if (bsel[b] < 0) continue;  // warp-uniform
+        const double* T = (bsel[b] == 0 ? sm.A[stage] : sm.B[stage]) + (ks * 4 + fk) * SY_LDS + fr;
+        double a[3], bb[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) a[u] = T[brow[b] * 24 + u * 8];
+#pragma unroll
+        for (int v = 0; v < 3; ++v) bb[v] = T[bcol[b] * 24 + v * 8];
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+#pragma unroll
+          for (int v = 0; v < 3; ++v) dmma884(acc[b][u][v][0], acc[b][u][v][1], a[u], bb[v]);
+      }
     }
-  if (diag && tid < SY_TILE) tpart[((size_t)split * n_tiles + tile) * SY_TILE + tid] = tacc;
+    if (tact) {
+      const double* Ad = (tsel == 0 ? sm.A[stage] : sm.B[stage]);
+#pragma unroll 8
+      for (int k = 0; k < SY_KC; ++k) tacc = fma(Ad[k * SY_LDS + trow], sm.t[stage][k], tacc);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.empty[stage]);
+  }
+#pragma unroll
+  for (int b = 0; b < 3; ++b) {
+    if (bsel[b] < 0) continue;
+    double* out = part + (size_t)(bsel[b] == 0 ? item.slotA : item.slotB) * (SY_TILE * SY_TILE);
+#pragma unroll
+    for (int u = 0; u < 3; ++u)
+#pragma unroll
+      for (int v = 0; v < 3; ++v) {
+        const int r = brow[b] * 24 + u * 8 + fr, cc = bcol[b] * 24 + v * 8 + 2 * fk;
+        *reinterpret_cast<double2*>(out + r * SY_TILE + cc) = make_double2(acc[b][u][v][0], acc[b][u][v][1]);
+      }
+  }
+  if (tact) tpart[(size_t)(tsel == 0 ? item.slotA : item.slotB) * SY_TILE + trow] = tacc;
 }
 
 // red = [ S (nP*nP) | b (nP) | gc (nP) | diagU (nP) | cost | gpmax slots ... ]   (local partials)
 template <int P>
-__global__ void schur_finalize_kernel(int nP, int n_blk, int n_tiles, int n_split, const int* __restrict__ tile_of,
+__global__ void schur_finalize_kernel(int nP, int n_blk, const int* __restrict__ tile_of,
+                                      const int* __restrict__ tile_slot_start, const int* __restrict__ tile_slots,
                                       const double* __restrict__ part, const double* __restrict__ tpart,
                                       const double* __restrict__ Upk, const double* __restrict__ gc,
                                       const double* __restrict__ cam_cost_sum, double* __restrict__ red) {
@@ -606,9 +678,12 @@ __global__ void schur_finalize_kernel(int nP, int n_blk, int n_tiles, int n_spli
     const int i = (int)(idx / nP), j = (int)(idx % nP);
     int I = i / SY_TILE, J = j / SY_TILE, li = i % SY_TILE, lj = j % SY_TILE;
     if (I > J) { int t = I; I = J; J = t; t = li; li = lj; lj = t; }
+    // diagonal tiles hold only their upper-triangular 24x24 blocks
+    if (I == J && li / 24 > lj / 24) { int t = li; li = lj; lj = t; }
     const int tile = tile_of[I * n_blk + J];
     double s = 0.0;
-    for (int sp = 0; sp < n_split; ++sp) s += part[((size_t)sp * n_tiles + tile) * (SY_TILE * SY_TILE) + li * SY_TILE + lj];
+    for (int q = tile_slot_start[tile]; q < tile_slot_start[tile + 1]; ++q)
+      s += part[(size_t)tile_slots[q] * (SY_TILE * SY_TILE) + li * SY_TILE + lj];
     double u = 0.0;
     const int ci = i / P, cj = j / P;
     if (ci == cj) {
@@ -622,7 +697,8 @@ __global__ void schur_finalize_kernel(int nP, int n_blk, int n_tiles, int n_spli
     const int I = i / SY_TILE, li = i % SY_TILE;
     const int tile = tile_of[I * n_blk + I];
     double s = 0.0;
-    for (int sp = 0; sp < n_split; ++sp) s += tpart[((size_t)sp * n_tiles + tile) * SY_TILE + li];
+    for (int q = tile_slot_start[tile]; q < tile_slot_start[tile + 1]; ++q)
+      s += tpart[(size_t)tile_slots[q] * SY_TILE + li];
     red[nn + i] = gc[i] - s;
     red[nn + nP + i] = gc[i];
     const int c = i / P, a = i % P;
@@ -713,10 +789,10 @@ __global__ void block_inverse_kernel(const double* __restrict__ S, int nP, int n
 //   u = M^-1 r, w = S u, g = r.u, d = w.u, beta = g/g_old, alpha = g / (d - beta g / alpha_old)
 //   p = u + beta p, q = w + beta q (= S p), x += alpha p, r -= alpha q
 // ---------------------------------------------------------------------------------------------
-template <bool SLAB_SMEM>
+template <bool SLAB_SMEM, int P>
 __global__ void __launch_bounds__(PCG_THREADS, 1)
 pcg_cluster_kernel(const double* __restrict__ S, const double* __restrict__ bvec, const double* __restrict__ Minv,
-                   int nP, int P, int rows_per, double tol2, int max_iter, double* __restrict__ xout,
+                   int nP, int rows_per, double tol2, int max_iter, double* __restrict__ xout,
                    double* __restrict__ sc) {
   extern __shared__ __align__(16) double psm[];
   cg::cluster_group cluster = cg::this_cluster();
@@ -753,31 +829,38 @@ pcg_cluster_kernel(const double* __restrict__ S, const double* __restrict__ bvec
       const double* m = Mi + (size_t)c * P * P + a * P;
       const double* rr = vr + c * P;
       double s = 0.0;
+#pragma unroll
       for (int b = 0; b < P; ++b) s = fma(m[b], rr[b], s);
       vu[i] = s;
     }
   };
   auto matvec = [&](double* wbuf) {  // w[row0 + r] = S_row . u for this CTA's rows -> every CTA's wbuf
     for (int r0 = wid * 3; r0 < nrows; r0 += NW * 3) {
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
       const bool h1 = r0 + 1 < nrows, h2 = r0 + 2 < nrows;
-      if (SLAB_SMEM) {
-        const double* a0 = slab + (size_t)r0 * nP;
-        const double* a1 = a0 + (h1 ? nP : 0);
-        const double* a2 = a0 + (h2 ? 2 * nP : 0);
-        for (int k = lane; k < nP; k += 32) {
-          const double uk = vu[k];
-          s0 = fma(a0[k], uk, s0); s1 = fma(a1[k], uk, s1); s2 = fma(a2[k], uk, s2);
-        }
-      } else {
-        const double* a0 = S + (size_t)(row0 + r0) * nP;
-        const double* a1 = a0 + (h1 ? nP : 0);
-        const double* a2 = a0 + (h2 ? 2 * nP : 0);
-        for (int k = lane; k < nP; k += 32) {
-          const double uk = vu[k];
-          s0 = fma(__ldg(a0 + k), uk, s0); s1 = fma(__ldg(a1 + k), uk, s1); s2 = fma(__ldg(a2 + k), uk, s2);
+      const double* a0 = SLAB_SMEM ? slab + (size_t)r0 * nP : S + (size_t)(row0 + r0) * nP;
+      const double* a1 = a0 + (h1 ? nP : 0);
+      const double* a2 = a0 + (h2 ? 2 * nP : 0);
+      // 4 independent partial sums per row: the k loop is a chain of shared-memory loads and fp64 FMAs
+      double t0[4] = {0, 0, 0, 0}, t1[4] = {0, 0, 0, 0}, t2[4] = {0, 0, 0, 0};
+      int k = lane;
+      for (; k + 96 < nP; k += 128) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const double uk = vu[k + 32 * j];
+          t0[j] = fma(SLAB_SMEM ? a0[k + 32 * j] : __ldg(a0 + k + 32 * j), uk, t0[j]);
+          t1[j] = fma(SLAB_SMEM ? a1[k + 32 * j] : __ldg(a1 + k + 32 * j), uk, t1[j]);
+          t2[j] = fma(SLAB_SMEM ? a2[k + 32 * j] : __ldg(a2 + k + 32 * j), uk, t2[j]);
         }
       }
+      for (; k < nP; k += 32) {
+        const double uk = vu[k];
+        t0[0] = fma(SLAB_SMEM ? a0[k] : __ldg(a0 + k), uk, t0[0]);
+        t1[0] = fma(SLAB_SMEM ? a1[k] : __ldg(a1 + k), uk, t1[0]);
+        t2[0] = fma(SLAB_SMEM ? a2[k] : __ldg(a2 + k), uk, t2[0]);
+      }
+      double s0 = (t0[0] + t0[1]) + (t0[2] + t0[3]);
+      double s1 = (t1[0] + t1[1]) + (t1[2] + t1[3]);
+      double s2 = (t2[0] + t2[1]) + (t2[2] + t2[3]);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         s0 += __shfl_xor_sync(0xffffffffu, s0, o);
@@ -806,9 +889,15 @@ pcg_cluster_kernel(const double* __restrict__ S, const double* __restrict__ bvec
     }
     if (lane == 0) { sh[wid] = pg; sh[NW + wid] = pd; }
     __syncthreads();
-    g = 0.0; d = 0.0;
+    g = (lane < NW) ? sh[lane] : 0.0;
+    d = (lane < NW) ? sh[NW + lane] : 0.0;
 #pragma unroll
-    for (int w = 0; w < NW; ++w) { g += sh[w]; d += sh[NW + w]; }
+    for (int o = NW / 2; o > 0; o >>= 1) {
+      g += __shfl_xor_sync(0xffffffffu, g, o);
+      d += __shfl_xor_sync(0xffffffffu, d, o);
+    }
+    g = __shfl_sync(0xffffffffu, g, 0);
+    d = __shfl_sync(0xffffffffu, d, 0);
   };
 
   precond();
@@ -821,11 +910,13 @@ pcg_cluster_kernel(const double* __restrict__ S, const double* __restrict__ bvec
   const double g0 = g;
   double alpha = (d > 0.0) ? g / d : 0.0, beta = 0.0;
   int it = 0, flag = 0;
+  long long tprof[5] = {0, 0, 0, 0, 0};  // cycles: update, precond, matvec, cluster barrier, dots (thread 0)
   if (g0 > 0.0 && !(d > 0.0)) flag = 1;
   if (g0 > 0.0 && flag == 0) {
     for (it = 1; it <= max_iter; ++it) {
       const double* wcur = vw + ((it - 1) & 1) * nPa;
       double* wnext = vw + (it & 1) * nPa;
+      const long long c0 = clock64();
       for (int i = tid; i < nP; i += PCG_THREADS) {
         const double pi = fma(beta, vp[i], vu[i]);
         const double qi = fma(beta, vq[i], wcur[i]);
@@ -834,12 +925,18 @@ pcg_cluster_kernel(const double* __restrict__ S, const double* __restrict__ bvec
         vr[i] = fma(-alpha, qi, vr[i]);
       }
       __syncthreads();
+      const long long c1 = clock64();
       precond();
       __syncthreads();
+      const long long c2 = clock64();
       matvec(wnext);
+      const long long c3 = clock64();
       cluster.sync();
+      const long long c4 = clock64();
       double gn, dn;
       dots(wnext, gn, dn);
+      const long long c5 = clock64();
+      tprof[0] += c1 - c0; tprof[1] += c2 - c1; tprof[2] += c3 - c2; tprof[3] += c4 - c3; tprof[4] += c5 - c4;
       if (!(gn == gn) || !(dn == dn)) { flag = 2; break; }
       if (gn <= tol2 * g0) { g = gn; break; }
       beta = gn / g;
@@ -856,6 +953,7 @@ pcg_cluster_kernel(const double* __restrict__ S, const double* __restrict__ bvec
       sc[SC_PCG_ITS] = (double)it;
       sc[SC_PCG_REL] = (g0 > 0.0) ? sqrt(fabs(g) / g0) : 0.0;
       sc[SC_PCG_FLAG] = (double)flag;
+      for (int k = 0; k < 5; ++k) sc[SC_PCG_T0 + k] = (double)tprof[k];
     }
   }
 }

@@ -164,6 +164,10 @@ int cb_ba_normal_equations(CbBaProblem* p, const double* x, double lambda, int32
 int cb_ba_error_order_stats(CbBaProblem* p, const double* x, double q_percent, double* err, double* lo,
                             double* hi, int64_t* count, void* stream);
 
+/* Diagnostic: mean milliseconds of one PCG-kernel launch forced to run exactly max_iter iterations on the
+ * system left by the last cb_ba_normal_equations call. */
+int cb_ba_debug_pcg_time(CbBaProblem* p, int max_iter, int reps, double* ms_per_launch, void* stream);
+
 /* Number of kernel launches issued by this library in the calling process so far. */
 int64_t cb_ba_launch_count(void);
 
