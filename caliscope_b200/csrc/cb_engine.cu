@@ -172,7 +172,7 @@ struct CbBaProblem {
   double2* d_cm_xy = nullptr;
   int *d_cm_pt = nullptr, *d_cm_row = nullptr, *d_cm_orig = nullptr, *d_cam_start = nullptr;
   int *d_chunk_cam = nullptr, *d_chunk_begin = nullptr, *d_chunk_end = nullptr, *d_cam_chunk_start = nullptr;
-  int *d_pt_start = nullptr, *d_pm_orig = nullptr, *d_pm_cam = nullptr, *d_pm_row = nullptr;
+  int *d_pt_start = nullptr, *d_pm_orig = nullptr, *d_pm_cam = nullptr, *d_pm_row = nullptr, *d_pm_pt = nullptr;
   int *d_tile_of = nullptr, *d_tile_slot_start = nullptr, *d_tile_slots = nullptr;
   cb::SyItem* d_items = nullptr;
   int n_items = 0, n_slots = 0;
@@ -190,7 +190,7 @@ struct CbBaProblem {
   double* h_x = nullptr;   // pinned staging for x
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   // pcg launch configuration
-  int pcg_cs = 1, pcg_rows = 0, pcg_slab_smem = 1;
+  int pcg_cs = 1, pcg_rows = 0, pcg_mode = 0, pcg_cl = 1, pcg_npa = 0;
   size_t pcg_smem = 0;
   int red_slots = 64;
   size_t red_len() const { return (size_t)nP * nP + 3 * (size_t)nP + 1 + red_slots; }
@@ -251,6 +251,7 @@ int build_indices(CbBaProblem* p, const int* d_obs_cam, const int* d_obs_pt, con
   CB_LAUNCH(cb::split_keys_kernel, G, TB, 0, st, k_out, (long long)p->n_cams, n, pm_pt, pm_cam);
   CB_LAUNCH(cb::lower_bound_kernel, cdiv(p->n_pts + 1, TB), TB, 0, st, pm_pt, n, p->n_pts, p->d_pt_start);
   CB_CUDA(cudaMemcpyAsync(p->d_pm_cam, pm_cam, sizeof(int) * n, cudaMemcpyDeviceToDevice, st));
+  CB_CUDA(cudaMemcpyAsync(p->d_pm_pt, pm_pt, sizeof(int) * n, cudaMemcpyDeviceToDevice, st));
   // (2) row layout of the Jacobian buffer: (point block of PT_BLOCK points, camera, point).  Within a
   //     block all rows of one camera are adjacent, so a camera-major warp of resjac_kernel writes runs of
   //     consecutive 160-byte rows (DRAM page locality; scattered single rows cap at ~2.4 TB/s on B200,
@@ -370,10 +371,15 @@ int build_system(CbBaProblem* p, double lam, bool new_lin, const CbBaOptions* op
   return CB_OK;
 }
 
-using PcgFn = void (*)(const double*, const double*, const double*, int, int, double, int, double*, double*);
-PcgFn pcg_fn(bool slab_smem, int P) {
-  if (P == 6) return slab_smem ? cb::pcg_cluster_kernel<true, 6> : cb::pcg_cluster_kernel<false, 6>;
-  return slab_smem ? cb::pcg_cluster_kernel<true, 9> : cb::pcg_cluster_kernel<false, 9>;
+using PcgFn = void (*)(const double*, const double*, const double*, int, int, int, double, int, double*, double*);
+// mode 0: slab in shared memory, 1: slab from global, 2: slab in registers with cl columns per lane
+PcgFn pcg_fn(int mode, int P, int cl) {
+  if (mode == 2) {
+    if (P == 6) return cl == 2 ? cb::pcg_cluster_kernel<2, 6, 2> : cl == 6 ? cb::pcg_cluster_kernel<2, 6, 6> : cb::pcg_cluster_kernel<2, 6, 12>;
+    return cl == 2 ? cb::pcg_cluster_kernel<2, 9, 2> : cl == 6 ? cb::pcg_cluster_kernel<2, 9, 6> : cb::pcg_cluster_kernel<2, 9, 12>;
+  }
+  if (P == 6) return mode == 0 ? cb::pcg_cluster_kernel<0, 6, 1> : cb::pcg_cluster_kernel<1, 6, 1>;
+  return mode == 0 ? cb::pcg_cluster_kernel<0, 9, 1> : cb::pcg_cluster_kernel<1, 9, 1>;
 }
 
 int launch_pcg(CbBaProblem* p, double tol2, int max_iter, cudaStream_t st) {
@@ -391,9 +397,9 @@ int launch_pcg(CbBaProblem* p, double tol2, int max_iter, cudaStream_t st) {
   cfg.numAttrs = 1;
   const double* S = p->d_red;
   const double* b = p->d_red + (size_t)p->nP * p->nP;
-  auto fn = pcg_fn(p->pcg_slab_smem != 0, p->P);
-  CB_CUDA(cudaLaunchKernelEx(&cfg, fn, S, b, (const double*)p->d_Minv, p->nP, p->pcg_rows, tol2, max_iter, p->d_dc,
-                             p->d_sc));
+  auto fn = pcg_fn(p->pcg_mode, p->P, p->pcg_cl);
+  CB_CUDA(cudaLaunchKernelEx(&cfg, fn, S, b, (const double*)p->d_Minv, p->nP, p->pcg_npa, p->pcg_rows, tol2, max_iter,
+                             p->d_dc, p->d_sc));
   g_launches.fetch_add(1);
   return CB_OK;
 }
@@ -609,47 +615,54 @@ int lm_solve(CbBaProblem* p, const CbBaOptions* opt, double* x_inout, CbBaResult
 
 int choose_pcg_config(CbBaProblem* p) {
   const int nP = p->nP, P = p->P;
-  const size_t nPa = (size_t)((nP + 7) & ~7);
-  const size_t fixed = (7 * nPa + 2 * (cb::PCG_THREADS / 32) + (((size_t)(nP / P) * P * P + 7) & ~(size_t)7)) * sizeof(double);
   int max_optin = 0;
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device);
   const size_t budget = (size_t)std::max(max_optin, 48 * 1024);
-  cudaFuncSetAttribute((const void*)pcg_fn(true, P), cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-  cudaFuncSetAttribute((const void*)pcg_fn(false, P), cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-  const int cands[5] = {1, 2, 4, 8, 16};
-  int min_cs = 1;
-  if (const char* ev = std::getenv("CB_PCG_MIN_CLUSTER")) min_cs = std::max(1, std::atoi(ev));
-  for (int pass = 0; pass < 2; ++pass) {  // pass 0: slab in shared memory, pass 1: slab streamed from L2
-    for (int ci = 0; ci < 5; ++ci) {
-      const int cs = cands[ci];
-      if (pass == 1 && cs != 8) continue;
-      if (pass == 0 && cs < min_cs) continue;
-      const int rows = (nP + cs - 1) / cs;
-      const size_t smem = fixed + (pass == 0 ? (size_t)rows * nP * sizeof(double) : 0);
-      if (smem > budget) continue;
-      const void* fn = (const void*)pcg_fn(pass == 0, P);
-      if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-        cudaGetLastError();
-        continue;
-      }
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(cs);
-      cfg.blockDim = dim3(cb::PCG_THREADS);
-      cfg.dynamicSmemBytes = smem;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-      cfg.attrs = at;
-      cfg.numAttrs = 1;
-      int ncl = 0;
-      if (cudaOccupancyMaxActiveClusters(&ncl, fn, &cfg) != cudaSuccess || ncl < 1) {
-        cudaGetLastError();
-        continue;
-      }
-      p->pcg_cs = cs; p->pcg_rows = rows; p->pcg_slab_smem = (pass == 0); p->pcg_smem = smem;
-      return CB_OK;
+  const size_t minv = (((size_t)(nP / P) * P * P + 7) & ~(size_t)7);
+  const int nw = cb::PCG_THREADS / 32;
+  auto try_config = [&](int mode, int cs, int cl) -> bool {
+    const int rows = (nP + cs - 1) / cs;
+    const int npa = std::max((nP + 7) & ~7, mode == 2 ? cl * 32 : 0);
+    const size_t smem = (7 * (size_t)npa + 2 * nw + minv + (mode == 0 ? (size_t)rows * nP : 0)) * sizeof(double);
+    if (smem > budget) return false;
+    if (mode == 2 && rows > 3 * nw) return false;
+    const void* fn = (const void*)pcg_fn(mode, P, cl);
+    cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
     }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cs);
+    cfg.blockDim = dim3(cb::PCG_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int ncl = 0;
+    if (cudaOccupancyMaxActiveClusters(&ncl, fn, &cfg) != cudaSuccess || ncl < 1) {
+      cudaGetLastError();
+      return false;
+    }
+    p->pcg_cs = cs; p->pcg_rows = rows; p->pcg_mode = mode; p->pcg_cl = cl; p->pcg_npa = npa; p->pcg_smem = smem;
+    return true;
+  };
+  int force_mode = -1;
+  if (const char* ev = std::getenv("CB_PCG_MODE")) force_mode = std::atoi(ev);
+  // (1) slab in registers: up to 384 reduced parameters in one portable cluster
+  if (nP <= 384 && (force_mode < 0 || force_mode == 2)) {
+    const int cl = nP <= 64 ? 2 : nP <= 192 ? 6 : 12;
+    const int cs = (nP + 3 * nw - 1) / (3 * nw);
+    if (cs <= 8 && try_config(2, cs, cl)) return CB_OK;
   }
+  // (2) slab in shared memory, smallest cluster that fits
+  if (force_mode < 0 || force_mode == 0)
+    for (int cs : {1, 2, 4, 8, 16})
+      if (try_config(0, cs, 1)) return CB_OK;
+  // (3) slab streamed from L2
+  if (try_config(1, 8, 1)) return CB_OK;
   g_last_error = "no feasible PCG cluster configuration for n_camera_params = " + std::to_string(nP);
   return CB_E_UNSUPPORTED;
 }
@@ -764,6 +777,7 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
   CB_TRY(palloc(p, &p->d_pt_start, p->n_pts + 1)); CB_TRY(palloc(p, &p->d_pm_orig, n));
   CB_TRY(palloc(p, &p->d_pm_cam, n));
   CB_TRY(palloc(p, &p->d_pm_row, n));
+  CB_TRY(palloc(p, &p->d_pm_pt, n));
   // observation list: host -> device if needed
   const int *d_cam = d->obs_cam, *d_pt = d->obs_pt;
   const double* d_xy = d->obs_xy;
@@ -792,8 +806,10 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
     std::vector<Group> groups;
     for (int I = 0; I < nb; ++I)
       for (int J = I + 1; J < nb; ++J) groups.push_back({0, I, J, 1.0});
+    double w_pair = 1.55;  // measured cost of a diagonal-pair CTA per k chunk relative to an off-diagonal one
+    if (const char* ev = std::getenv("CB_SY_PAIR_W")) w_pair = std::atof(ev);
     for (int I = 0; I < nb; I += 2) {
-      if (I + 1 < nb) groups.push_back({1, I, I + 1, 1.25});
+      if (I + 1 < nb) groups.push_back({1, I, I + 1, w_pair});
       else groups.push_back({1, I, -1, 0.75});
     }
     double W = 0.0;

@@ -604,11 +604,16 @@ schur_syrk_kernel(const double* __restrict__ Zt, size_t LD, const double* __rest
 
   // ---------------- diagonal pair ----------------
   int bsel[3], brow[3], bcol[3];
+#ifdef CB_SY_MAP_B
+  const int wmap = (wid & 1) * 4 + (wid >> 1);  // 3-block lists on even warps
+#else
+  const int wmap = wid;
+#endif
 #pragma unroll
   for (int b = 0; b < 3; ++b) {
-    bsel[b] = SY_DIAG_BLOCKS[wid][b][0];
-    brow[b] = SY_DIAG_BLOCKS[wid][b][1];
-    bcol[b] = SY_DIAG_BLOCKS[wid][b][2];
+    bsel[b] = SY_DIAG_BLOCKS[wmap][b][0];
+    brow[b] = SY_DIAG_BLOCKS[wmap][b][1];
+    bcol[b] = SY_DIAG_BLOCKS[wmap][b][2];
     if (bsel[b] == 1 && !two) bsel[b] = -1;
   }
   double acc[3][3][3][2];
@@ -789,18 +794,21 @@ __global__ void block_inverse_kernel(const double* __restrict__ S, int nP, int n
 //   u = M^-1 r, w = S u, g = r.u, d = w.u, beta = g/g_old, alpha = g / (d - beta g / alpha_old)
 //   p = u + beta p, q = w + beta q (= S p), x += alpha p, r -= alpha q
 // ---------------------------------------------------------------------------------------------
-template <bool SLAB_SMEM, int P>
+// MODE 0: S slab in shared memory, 1: slab streamed from global/L2, 2: slab in REGISTERS
+// (3 rows x CL columns-per-lane per warp; n_camera_params <= 32*CL, rows_per <= 48) -- the matvec then
+// touches shared memory only for the vector u, instead of re-reading 147 KB of slab per iteration.
+template <int MODE, int P, int CL>
 __global__ void __launch_bounds__(PCG_THREADS, 1)
 pcg_cluster_kernel(const double* __restrict__ S, const double* __restrict__ bvec, const double* __restrict__ Minv,
-                   int nP, int rows_per, double tol2, int max_iter, double* __restrict__ xout,
+                   int nP, int nPa, int rows_per, double tol2, int max_iter, double* __restrict__ xout,
                    double* __restrict__ sc) {
+  constexpr bool SLAB_SMEM = (MODE == 0);
   extern __shared__ __align__(16) double psm[];
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   constexpr int NW = PCG_THREADS / 32;
   // layout: x r u p q w0 w1 (nPa each) | sh[2*NW] | Minv (n_cams*P*P) | slab
-  const int nPa = (nP + 7) & ~7;
   double* vx = psm;
   double* vr = vx + nPa;
   double* vu = vr + nPa;
@@ -817,9 +825,19 @@ pcg_cluster_kernel(const double* __restrict__ S, const double* __restrict__ bvec
   for (int i = tid; i < n_cams * P * P; i += PCG_THREADS) Mi[i] = Minv[i];
   if (SLAB_SMEM)
     for (size_t i = tid; i < (size_t)nrows * nP; i += PCG_THREADS) slab[i] = S[(size_t)row0 * nP + i];
-  for (int i = tid; i < nP; i += PCG_THREADS) {
-    vx[i] = 0.0; vp[i] = 0.0; vq[i] = 0.0;
-    vr[i] = -bvec[i];
+  double sreg[MODE == 2 ? 3 : 1][MODE == 2 ? CL : 1];
+  if constexpr (MODE == 2) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < CL; ++c) {
+        const int row = wid * 3 + r, col = lane + 32 * c;
+        sreg[r][c] = (row < nrows && col < nP) ? S[(size_t)(row0 + row) * nP + col] : 0.0;
+      }
+  }
+  for (int i = tid; i < nPa; i += PCG_THREADS) {
+    vx[i] = 0.0; vp[i] = 0.0; vq[i] = 0.0; vu[i] = 0.0;
+    vr[i] = (i < nP) ? -bvec[i] : 0.0;
   }
   __syncthreads();
 
@@ -835,6 +853,32 @@ pcg_cluster_kernel(const double* __restrict__ S, const double* __restrict__ bvec
     }
   };
   auto matvec = [&](double* wbuf) {  // w[row0 + r] = S_row . u for this CTA's rows -> every CTA's wbuf
+    if constexpr (MODE == 2) {
+      const int r0 = wid * 3;
+      if (r0 < nrows) {
+        double e0 = 0, e1 = 0, e2 = 0, o0 = 0, o1 = 0, o2 = 0;
+#pragma unroll
+        for (int c = 0; c < CL; ++c) {
+          const double uk = vu[lane + 32 * c];
+          if (c & 1) { o0 = fma(sreg[0][c], uk, o0); o1 = fma(sreg[1][c], uk, o1); o2 = fma(sreg[2][c], uk, o2); }
+          else { e0 = fma(sreg[0][c], uk, e0); e1 = fma(sreg[1][c], uk, e1); e2 = fma(sreg[2][c], uk, e2); }
+        }
+        double s0 = e0 + o0, s1 = e1 + o1, s2 = e2 + o2;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (lane < csize) {
+          double* dst = cluster.map_shared_rank(wbuf, lane) + row0 + r0;
+          dst[0] = s0;
+          if (r0 + 1 < nrows) dst[1] = s1;
+          if (r0 + 2 < nrows) dst[2] = s2;
+        }
+      }
+      return;
+    }
     for (int r0 = wid * 3; r0 < nrows; r0 += NW * 3) {
       const bool h1 = r0 + 1 < nrows, h2 = r0 + 2 < nrows;
       const double* a0 = SLAB_SMEM ? slab + (size_t)r0 * nP : S + (size_t)(row0 + r0) * nP;
