@@ -163,7 +163,7 @@ struct CbBaProblem {
   int device = 0, num_sms = 148;
   int n_cams = 0, n_pts = 0, P = 6, nP = 0, n_obs = 0, n_params = 0;
   int LD = 0, n_blk = 0, n_tiles = 0, n_split = 1, k_chunks = 0, K_pad = 0;
-  int n_chunks = 0, pt_blocks = 0;
+  int n_chunks = 0, pt_blocks = 0, n_dups = 0;
   std::vector<int> h_cam_off;
   std::vector<void*> allocs;
   // problem tables
@@ -231,6 +231,8 @@ int build_indices(CbBaProblem* p, const int* d_obs_cam, const int* d_obs_pt, con
     return CB_E_INVALID;
   }
 
+  int* d_bad2;
+  CB_TRY(dalloc(&d_bad2, 1));
   unsigned long long *k_in, *k_out;
   int *v_in, *v_out, *pm_pt, *pm_cam, *cm_cam;
   CB_TRY(dalloc(&k_in, n)); CB_TRY(dalloc(&k_out, n));
@@ -252,6 +254,9 @@ int build_indices(CbBaProblem* p, const int* d_obs_cam, const int* d_obs_pt, con
   CB_LAUNCH(cb::lower_bound_kernel, cdiv(p->n_pts + 1, TB), TB, 0, st, pm_pt, n, p->n_pts, p->d_pt_start);
   CB_CUDA(cudaMemcpyAsync(p->d_pm_cam, pm_cam, sizeof(int) * n, cudaMemcpyDeviceToDevice, st));
   CB_CUDA(cudaMemcpyAsync(p->d_pm_pt, pm_pt, sizeof(int) * n, cudaMemcpyDeviceToDevice, st));
+  CB_CUDA(cudaMemsetAsync(d_bad2, 0, sizeof(int), st));
+  CB_LAUNCH(cb::count_dups_kernel, G, TB, 0, st, pm_pt, pm_cam, n, d_bad2);
+  CB_CUDA(cudaMemcpyAsync(&p->n_dups, d_bad2, sizeof(int), cudaMemcpyDeviceToHost, st));
   // (2) row layout of the Jacobian buffer: (point block of PT_BLOCK points, camera, point).  Within a
   //     block all rows of one camera are adjacent, so a camera-major warp of resjac_kernel writes runs of
   //     consecutive 160-byte rows (DRAM page locality; scattered single rows cap at ~2.4 TB/s on B200,
@@ -298,7 +303,7 @@ int build_indices(CbBaProblem* p, const int* d_obs_cam, const int* d_obs_pt, con
   CB_CUDA(cudaMemcpyAsync(p->d_cam_chunk_start, ccs.data(), sizeof(int) * ccs.size(), cudaMemcpyHostToDevice, st));
   CB_CUDA(cudaStreamSynchronize(st));
   cached_free(d_tmp); cached_free(k_in); cached_free(k_out); cached_free(v_in); cached_free(v_out);
-  cached_free(pm_pt); cached_free(pm_cam); cached_free(cm_cam);
+  cached_free(pm_pt); cached_free(pm_cam); cached_free(cm_cam); cached_free(d_bad2);
   return CB_OK;
 }
 
@@ -342,14 +347,16 @@ int linearize(CbBaProblem* p, const double* xc, const double* xp4, int loss, dou
 
 template <int P>
 int build_system(CbBaProblem* p, double lam, bool new_lin, const CbBaOptions* opt, cudaStream_t st) {
-  if (new_lin)
-    CB_LAUNCH((cb::pt_build_kernel<P, true>), p->pt_blocks, cb::PT_WARPS * 32, 0, st, p->d_pt_start, p->d_pm_cam,
-              p->d_pm_row, p->n_pts, p->d_jrows, p->d_V6, p->d_gp, p->d_Dp2, lam, p->d_Linv6, p->d_tvec, p->d_Zt, (size_t)p->LD,
-              p->d_gmax);
-  else
-    CB_LAUNCH((cb::pt_build_kernel<P, false>), p->pt_blocks, cb::PT_WARPS * 32, 0, st, p->d_pt_start, p->d_pm_cam,
-              p->d_pm_row, p->n_pts, p->d_jrows, p->d_V6, p->d_gp, p->d_Dp2, lam, p->d_Linv6, p->d_tvec, p->d_Zt, (size_t)p->LD,
-              p->d_gmax);
+#define CB_PT_BUILD(FUSED, DUPS)                                                                                  \
+  CB_LAUNCH((cb::pt_build_kernel<P, FUSED, DUPS>), p->pt_blocks, cb::PT_WARPS * 32, 0, st, p->d_pt_start, p->d_pm_cam, \
+            p->d_pm_row, p->n_pts, p->d_jrows, p->d_V6, p->d_gp, p->d_Dp2, lam, p->d_Linv6, p->d_tvec, p->d_Zt,      \
+            (size_t)p->LD, p->d_gmax)
+  if (new_lin) {
+    if (p->n_dups) CB_PT_BUILD(true, true); else CB_PT_BUILD(true, false);
+  } else {
+    if (p->n_dups) CB_PT_BUILD(false, true); else CB_PT_BUILD(false, false);
+  }
+#undef CB_PT_BUILD
   CB_LAUNCH(cb::schur_syrk_kernel, p->n_items, cb::SY_THREADS, sizeof(cb::SyrkSmem), st, p->d_Zt, (size_t)p->LD,
             p->d_tvec, p->d_items, p->d_part, p->d_tpart);
   const size_t nfin = (size_t)p->nP * p->nP + p->nP + 1;
@@ -407,7 +414,7 @@ int launch_pcg(CbBaProblem* p, double tol2, int max_iter, cudaStream_t st) {
 template <int P>
 int solve_step(CbBaProblem* p, double lam, int cur, const CbBaOptions* opt, double* dp_out, cudaStream_t st) {
   CB_LAUNCH((cb::block_inverse_kernel<P>), cdiv(p->n_cams, 64), 64, 0, st, p->d_red, p->nP, p->n_cams, p->d_Minv);
-  const double tol = (opt && opt->pcg_tol > 0) ? opt->pcg_tol : 1e-10;
+  const double tol = (opt && opt->pcg_tol > 0) ? opt->pcg_tol : 1e-6;
   const int mit = (opt && opt->pcg_max_iter > 0) ? opt->pcg_max_iter : 4 * p->nP;
   CB_TRY(launch_pcg(p, tol * tol, mit, st));
   const size_t nn = (size_t)p->nP * p->nP;
@@ -575,11 +582,15 @@ int lm_solve(CbBaProblem* p, const CbBaOptions* opt, double* x_inout, CbBaResult
       lam = lam * std::max(1.0 / 3.0, 1.0 - t * t * t);
       lam = std::max(lam, 1e-15);
       nu = 2.0;
+      cost = cost_new;
+      new_lin = true;
+      if (term) {  // converged on this step: the Jacobian at the final point is not needed
+        status = term;
+        break;
+      }
       CB_TRY(linearize<P>(p, p->d_xc[cur], p->d_xp4[cur], loss, fscale, st, true, nullptr));
       rj_pending = true;
       ++njev;
-      new_lin = true;
-      cost = cost_new;
     } else {
       lam = std::min(lam * nu, 1e12);
       nu *= 2.0;
@@ -623,7 +634,7 @@ int choose_pcg_config(CbBaProblem* p) {
   auto try_config = [&](int mode, int cs, int cl) -> bool {
     const int rows = (nP + cs - 1) / cs;
     const int npa = std::max((nP + 7) & ~7, mode == 2 ? cl * 32 : 0);
-    const size_t smem = (7 * (size_t)npa + 2 * nw + minv + (mode == 0 ? (size_t)rows * nP : 0)) * sizeof(double);
+    const size_t smem = (9 * (size_t)npa + 2 * nw + 2 * 16 * nw + minv + (mode == 0 ? (size_t)rows * nP : 0)) * sizeof(double);
     if (smem > budget) return false;
     if (mode == 2 && rows > 3 * nw) return false;
     const void* fn = (const void*)pcg_fn(mode, P, cl);
@@ -701,7 +712,7 @@ void cb_ba_default_options(CbBaOptions* o) {
   o->verbose = 0;
   o->use_bounds = 1;
   o->lambda0 = 1e-4;
-  o->pcg_tol = 1e-10;
+  o->pcg_tol = 1e-6;
   o->pcg_max_iter = 0;
   o->allreduce = nullptr;
   o->allreduce_user = nullptr;
@@ -1070,7 +1081,7 @@ int cb_ba_debug_pcg_time(CbBaProblem* p, int max_iter, int reps, double* ms_per_
   *ms_per_launch = ms / reps;
   double t[cb::SC_COUNT];
   CB_CUDA(cudaMemcpy(t, p->d_sc, sizeof(t), cudaMemcpyDeviceToHost));
-  std::fprintf(stderr, "[pcg profile] cycles/iteration on CTA 0 thread 0: update %.0f precond %.0f matvec %.0f cluster-barrier %.0f dots %.0f\n",
+  std::fprintf(stderr, "[pcg profile] cycles/iteration on CTA 0 thread 0: A(update+precond) %.0f block-barrier %.0f B(matvec) %.0f cluster-barrier %.0f C(dots) %.0f\n",
                t[cb::SC_PCG_T0] / max_iter, t[cb::SC_PCG_T0 + 1] / max_iter, t[cb::SC_PCG_T0 + 2] / max_iter,
                t[cb::SC_PCG_T0 + 3] / max_iter, t[cb::SC_PCG_T0 + 4] / max_iter);
   return CB_OK;

@@ -365,13 +365,48 @@ __device__ __forceinline__ void chol3_inv(const double* V6, const double* D2, do
   }
 }
 
+// DUPS path of pt_build_kernel: a (point, camera) pair observed more than once (static objects seen in
+// many frames).  Z = (sum_rows Jc^T Jp) Linv^T = sum_rows Jc^T (Jp Linv^T).  Only instantiated for problems
+// that contain such pairs, so its accumulators do not set the register budget of the common single-row path.
+template <int P>
+__device__ __forceinline__ void pt_build_run(const double* __restrict__ jrows, const int* __restrict__ pm_cam,
+                                          const int* __restrict__ pm_row, int pos, int e, int cam,
+                                          const double* __restrict__ Li, double* __restrict__ z0, size_t LD) {
+  using RT = RowT<P>;
+  double z[3][P];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int p = 0; p < P; ++p) z[a][p] = 0.0;
+  int r = pos;
+  do {
+    const double* src = jrows + (size_t)pm_row[r] * RT::ROWD;
+    double w[RT::ROWD];
+#pragma unroll
+    for (int k = 0; k < RT::ROWD; k += 4) ld256(src + k, w[k], w[k + 1], w[k + 2], w[k + 3]);
+    const double q00 = w[2] * Li[0], q01 = w[2] * Li[1] + w[3] * Li[2], q02 = w[2] * Li[3] + w[3] * Li[4] + w[4] * Li[5];
+    const double q10 = w[5] * Li[0], q11 = w[5] * Li[1] + w[6] * Li[2], q12 = w[5] * Li[3] + w[6] * Li[4] + w[7] * Li[5];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      z[0][p] = fma(w[8 + p], q00, fma(w[8 + P + p], q10, z[0][p]));
+      z[1][p] = fma(w[8 + p], q01, fma(w[8 + P + p], q11, z[1][p]));
+      z[2][p] = fma(w[8 + p], q02, fma(w[8 + P + p], q12, z[2][p]));
+    }
+    ++r;
+  } while (r < e && pm_cam[r] == cam);
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int p = 0; p < P; ++p) z0[a * LD + p] = z[a][p];
+}
+
 // Point-centric build of the Schur factor, one warp per point over its contiguous point-major rows:
 //   FUSED: V = sum Jp^T Jp, gp = sum Jp^T r over the rows (new linearisation), Marquardt scale update
 //   then  : Linv = chol(V + lam D)^-1, t = Linv gp, and per observed camera Z = (Jc^T Jp) Linv^T
 //           written to the k-major Zt (rows 3j..3j+2, columns cam*P..cam*P+P-1).
 // Repeated (camera, point) rows are adjacent (rows are sorted by point, then camera): the first
 // row of a run sums the run, so Z stays one block per (camera, point) pair without atomics.
-template <int P, bool FUSED>
+template <int P, bool FUSED, bool DUPS>
 __global__ void __launch_bounds__(PT_WARPS * 32)
 pt_build_kernel(const int* __restrict__ pt_start, const int* __restrict__ pm_cam,
                 const int* __restrict__ pm_row, int n_pts,
@@ -386,14 +421,30 @@ pt_build_kernel(const int* __restrict__ pt_start, const int* __restrict__ pm_cam
   if (j < n_pts) {
     const int s = pt_start[j], e = pt_start[j + 1];
     double v[9], D[3];
+    // first batch of rows: indices loaded once, used by both phases
+    const int pos0 = s + lane;
+    int row0 = 0, cam0 = -1, prev0 = -2;
+    if (pos0 < e) {
+      row0 = pm_row[pos0];
+      cam0 = pm_cam[pos0];
+      prev0 = (pos0 > s) ? pm_cam[pos0 - 1] : -2;
+    }
     if constexpr (FUSED) {
 #pragma unroll
       for (int k = 0; k < 9; ++k) v[k] = 0.0;
-      for (int pos = s + lane; pos < e; pos += 32) {
-        const double* src = jrows + (size_t)pm_row[pos] * RT::ROWD;
+      for (int pos = pos0; pos < e; pos += 32) {
+        const double* src = jrows + (size_t)(pos == pos0 ? row0 : pm_row[pos]) * RT::ROWD;
         double f0, f1, a0, a1, a2, b0, b1, b2;
         ld256(src, f0, f1, a0, a1);
         ld256(src + 4, a2, b0, b1, b2);
+        // the Jc part of the row is needed in phase 2: start pulling it towards L2 now
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 8));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 12));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 16));
+        if (P == 9) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 20));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 24));
+        }
         v[0] += a0 * a0 + b0 * b0; v[1] += a0 * a1 + b0 * b1; v[2] += a0 * a2 + b0 * b2;
         v[3] += a1 * a1 + b1 * b1; v[4] += a1 * a2 + b1 * b2; v[5] += a2 * a2 + b2 * b2;
         v[6] += a0 * f0 + b0 * f1; v[7] += a1 * f0 + b1 * f1; v[8] += a2 * f0 + b2 * f1;
@@ -425,46 +476,45 @@ pt_build_kernel(const int* __restrict__ pt_start, const int* __restrict__ pm_cam
       tvec[3 * (size_t)j + 1] = Li[1] * v[6] + Li[2] * v[7];
       tvec[3 * (size_t)j + 2] = Li[3] * v[6] + Li[4] * v[7] + Li[5] * v[8];
     }
-    for (int pos = s + lane; pos < e; pos += 32) {
-      const int cam = pm_cam[pos];
-      if (pos > s && pm_cam[pos - 1] == cam) continue;  // not the first of its (point, camera) run
-      double W[P * 3];
-#pragma unroll
-      for (int k = 0; k < P * 3; ++k) W[k] = 0.0;
-      int r = pos;
-      do {
-        const double* src = jrows + (size_t)pm_row[r] * RT::ROWD;
-        double w[RT::ROWD];
-#pragma unroll
-        for (int k = 0; k < RT::ROWD; k += 4) ld256(src + k, w[k], w[k + 1], w[k + 2], w[k + 3]);
-        // w: [f0 f1 | Jp0(3) Jp1(3) | Jc0(P) Jc1(P)]
-#pragma unroll
-        for (int p = 0; p < P; ++p)
-#pragma unroll
-          for (int a = 0; a < 3; ++a)
-            W[p * 3 + a] = fma(w[8 + p], w[2 + a], fma(w[8 + P + p], w[5 + a], W[p * 3 + a]));
-        ++r;
-      } while (r < e && pm_cam[r] == cam);
+    for (int pos = pos0; pos < e; pos += 32) {
+      const int cam = (pos == pos0) ? cam0 : pm_cam[pos];
+      const int prev = (pos == pos0) ? prev0 : pm_cam[pos - 1];
+      if (prev == cam) continue;  // not the first of its (point, camera) run
       double* z0 = Zt + (3 * (size_t)j) * LD + (size_t)cam * P;
-      double z[3][P];
-#pragma unroll
-      for (int p = 0; p < P; ++p) {
-        z[0][p] = W[p * 3] * Li[0];
-        z[1][p] = W[p * 3] * Li[1] + W[p * 3 + 1] * Li[2];
-        z[2][p] = W[p * 3] * Li[3] + W[p * 3 + 1] * Li[4] + W[p * 3 + 2] * Li[5];
-      }
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        if constexpr (P == 6) {
-          double2* dst = reinterpret_cast<double2*>(z0 + a * LD);  // cam*48 B and LD*8 B are 16-byte multiples
-          dst[0] = make_double2(z[a][0], z[a][1]);
-          dst[1] = make_double2(z[a][2], z[a][3]);
-          dst[2] = make_double2(z[a][4], z[a][5]);
-        } else {
-#pragma unroll
-          for (int p = 0; p < P; ++p) z0[a * LD + p] = z[a][p];
+      if constexpr (DUPS) {
+        if (pos + 1 < e && pm_cam[pos + 1] == cam) {
+          pt_build_run<P>(jrows, pm_cam, pm_row, pos, e, cam, Li, z0, LD);
+          continue;
         }
       }
+      // single row: Z = Jc^T (Jp Linv^T), streamed straight to the stores
+      const double* src = jrows + (size_t)((pos == pos0) ? row0 : pm_row[pos]) * RT::ROWD;
+      double f0, f1, a0, a1, a2, b0, b1, b2;
+      ld256(src, f0, f1, a0, a1);
+      ld256(src + 4, a2, b0, b1, b2);
+      const double q00 = a0 * Li[0], q01 = a0 * Li[1] + a1 * Li[2], q02 = a0 * Li[3] + a1 * Li[4] + a2 * Li[5];
+      const double q10 = b0 * Li[0], q11 = b0 * Li[1] + b1 * Li[2], q12 = b0 * Li[3] + b1 * Li[4] + b2 * Li[5];
+      double jc[2 * P + (P == 9 ? 2 : 0)];
+#pragma unroll
+      for (int k = 0; k < RT::ROWD - 8; k += 4) ld256(src + 8 + k, jc[k], jc[k + 1], jc[k + 2], jc[k + 3]);
+      if constexpr (P == 6) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const double qa = a == 0 ? q00 : a == 1 ? q01 : q02, qb = a == 0 ? q10 : a == 1 ? q11 : q12;
+          double2* dst = reinterpret_cast<double2*>(z0 + a * LD);  // cam*48 B and LD*8 B are 16-byte multiples
+#pragma unroll
+          for (int h = 0; h < 3; ++h)
+            dst[h] = make_double2(fma(jc[2 * h], qa, jc[P + 2 * h] * qb), fma(jc[2 * h + 1], qa, jc[P + 2 * h + 1] * qb));
+        }
+      } else {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const double qa = a == 0 ? q00 : a == 1 ? q01 : q02, qb = a == 0 ? q10 : a == 1 ? q11 : q12;
+#pragma unroll
+          for (int pp = 0; pp < P; ++pp) z0[a * LD + pp] = fma(jc[pp], qa, jc[P + pp] * qb);
+        }
+      }
+      (void)f0; (void)f1;
     }
   }
   if constexpr (FUSED) {
@@ -797,26 +847,34 @@ __global__ void block_inverse_kernel(const double* __restrict__ S, int nP, int n
 // MODE 0: S slab in shared memory, 1: slab streamed from global/L2, 2: slab in REGISTERS
 // (3 rows x CL columns-per-lane per warp; n_camera_params <= 32*CL, rows_per <= 48) -- the matvec then
 // touches shared memory only for the vector u, instead of re-reading 147 KB of slab per iteration.
+//
+// Per iteration: [A] replicated vector update + block-Jacobi solve (each thread recomputes the P residual
+// entries of its camera block, so no barrier is needed between the two), __syncthreads, [B] slab matvec,
+// rows of w and this warp's share of d = w.u written into every CTA through DSMEM, cluster barrier,
+// [C] every warp sums the d slots (and the CTA-local g = r.u slots): one block barrier and one cluster
+// barrier per iteration, all loop buffers double-buffered by iteration parity.
 template <int MODE, int P, int CL>
 __global__ void __launch_bounds__(PCG_THREADS, 1)
 pcg_cluster_kernel(const double* __restrict__ S, const double* __restrict__ bvec, const double* __restrict__ Minv,
                    int nP, int nPa, int rows_per, double tol2, int max_iter, double* __restrict__ xout,
                    double* __restrict__ sc) {
   constexpr bool SLAB_SMEM = (MODE == 0);
+  constexpr int NW = PCG_THREADS / 32;
+  constexpr int MAXC = 16;  // largest cluster
   extern __shared__ __align__(16) double psm[];
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  constexpr int NW = PCG_THREADS / 32;
-  // layout: x r u p q w0 w1 (nPa each) | sh[2*NW] | Minv (n_cams*P*P) | slab
+  // layout: x u p | r[2] q[2] w[2] (nPa each) | gslot[2][NW] | dslot[2][MAXC*NW] | Minv | slab
   double* vx = psm;
-  double* vr = vx + nPa;
-  double* vu = vr + nPa;
+  double* vu = vx + nPa;
   double* vp = vu + nPa;
-  double* vq = vp + nPa;
-  double* vw = vq + nPa;  // two buffers
-  double* sh = vw + 2 * nPa;
-  double* Mi = sh + 2 * NW;
+  double* vr = vp + nPa;      // two buffers
+  double* vq = vr + 2 * nPa;  // two buffers
+  double* vw = vq + 2 * nPa;  // two buffers
+  double* gslot = vw + 2 * nPa;
+  double* dslot = gslot + 2 * NW;
+  double* Mi = dslot + 2 * MAXC * NW;
   double* slab = Mi + (((size_t)(nP / P) * P * P + 7) & ~(size_t)7);
   const int row0 = rank * rows_per;
   const int nrows = max(0, min(rows_per, nP - row0));
@@ -836,26 +894,68 @@ pcg_cluster_kernel(const double* __restrict__ S, const double* __restrict__ bvec
       }
   }
   for (int i = tid; i < nPa; i += PCG_THREADS) {
-    vx[i] = 0.0; vp[i] = 0.0; vq[i] = 0.0; vu[i] = 0.0;
-    vr[i] = (i < nP) ? -bvec[i] : 0.0;
+    vx[i] = 0.0; vp[i] = 0.0; vu[i] = 0.0;
+    vq[i] = 0.0; vq[nPa + i] = 0.0;
+    vr[i] = (i < nP) ? -bvec[i] : 0.0;  // buffer 0 = r_0
+    vr[nPa + i] = 0.0;
   }
+  for (int i = tid; i < 2 * MAXC * NW; i += PCG_THREADS) dslot[i] = 0.0;
   __syncthreads();
 
-  auto precond = [&]() {  // u = M^-1 r (block diagonal), own indices
+  // [A] for iteration `it` (it = 0: only u = M^-1 r and g = r.u):  reads r/q buffer (it+1)&1 ... see below
+  auto phase_a = [&](int it, double alpha, double beta) {
+    // buffers: current r, q live in parity `it & 1`; the updated ones go to parity `(it + 1) & 1`
+    const double* rc = vr + (it & 1) * nPa;
+    double* rn = vr + ((it + 1) & 1) * nPa;
+    const double* qc = vq + (it & 1) * nPa;
+    double* qn = vq + ((it + 1) & 1) * nPa;
+    const double* wc = vw + (it & 1) * nPa;
+    double pg = 0.0;
     for (int i = tid; i < nP; i += PCG_THREADS) {
       const int c = i / P, a = i - c * P;
       const double* m = Mi + (size_t)c * P * P + a * P;
-      const double* rr = vr + c * P;
-      double s = 0.0;
+      double s = 0.0, r_own = 0.0;
+      if (it == 0) {
 #pragma unroll
-      for (int b = 0; b < P; ++b) s = fma(m[b], rr[b], s);
-      vu[i] = s;
+        for (int b = 0; b < P; ++b) {
+          const double rb = rc[c * P + b];
+          s = fma(m[b], rb, s);
+          if (b == a) r_own = rb;
+        }
+        rn[i] = r_own;
+        qn[i] = 0.0;
+      } else {
+        const double ui = vu[i];
+        const double pi = fma(beta, vp[i], ui);
+        vp[i] = pi;
+        vx[i] = fma(alpha, pi, vx[i]);
+#pragma unroll
+        for (int b = 0; b < P; ++b) {
+          const int k = c * P + b;
+          const double qb = fma(beta, qc[k], wc[k]);   // q_new of the neighbour, recomputed
+          const double rb = fma(-alpha, qb, rc[k]);    // r_new of the neighbour, recomputed
+          s = fma(m[b], rb, s);
+          if (b == a) { r_own = rb; qn[i] = qb; }
+        }
+        rn[i] = r_own;
+      }
+      vu[i] = s;  // only its owner reads vu[i] in this phase
+      pg = fma(r_own, s, pg);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pg += __shfl_xor_sync(0xffffffffu, pg, o);
+    if (lane == 0) gslot[(it & 1) * NW + wid] = pg;
   };
-  auto matvec = [&](double* wbuf) {  // w[row0 + r] = S_row . u for this CTA's rows -> every CTA's wbuf
-    if constexpr (MODE == 2) {
-      const int r0 = wid * 3;
-      if (r0 < nrows) {
+
+  // [B] w[row0 + r] = S_row . u for this CTA's rows and this warp's share of d = w.u -> every CTA
+  auto phase_b = [&](int it) {
+    double* wbuf = vw + ((it + 1) & 1) * nPa;
+    double* dbuf = dslot + ((it + 1) & 1) * (MAXC * NW);
+    double dpart = 0.0;
+    for (int r0 = wid * 3; r0 < nrows; r0 += NW * 3) {
+      const bool h1 = r0 + 1 < nrows, h2 = r0 + 2 < nrows;
+      double s0, s1, s2;
+      if constexpr (MODE == 2) {
         double e0 = 0, e1 = 0, e2 = 0, o0 = 0, o1 = 0, o2 = 0;
 #pragma unroll
         for (int c = 0; c < CL; ++c) {
@@ -863,54 +963,41 @@ pcg_cluster_kernel(const double* __restrict__ S, const double* __restrict__ bvec
           if (c & 1) { o0 = fma(sreg[0][c], uk, o0); o1 = fma(sreg[1][c], uk, o1); o2 = fma(sreg[2][c], uk, o2); }
           else { e0 = fma(sreg[0][c], uk, e0); e1 = fma(sreg[1][c], uk, e1); e2 = fma(sreg[2][c], uk, e2); }
         }
-        double s0 = e0 + o0, s1 = e1 + o1, s2 = e2 + o2;
+        s0 = e0 + o0; s1 = e1 + o1; s2 = e2 + o2;
+      } else {
+        const double* a0 = SLAB_SMEM ? slab + (size_t)r0 * nP : S + (size_t)(row0 + r0) * nP;
+        const double* a1 = a0 + (h1 ? nP : 0);
+        const double* a2 = a0 + (h2 ? 2 * nP : 0);
+        double t0[4] = {0, 0, 0, 0}, t1[4] = {0, 0, 0, 0}, t2[4] = {0, 0, 0, 0};
+        int k = lane;
+        for (; k + 96 < nP; k += 128) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+          for (int j = 0; j < 4; ++j) {
+            const double uk = vu[k + 32 * j];
+            t0[j] = fma(SLAB_SMEM ? a0[k + 32 * j] : __ldg(a0 + k + 32 * j), uk, t0[j]);
+            t1[j] = fma(SLAB_SMEM ? a1[k + 32 * j] : __ldg(a1 + k + 32 * j), uk, t1[j]);
+            t2[j] = fma(SLAB_SMEM ? a2[k + 32 * j] : __ldg(a2 + k + 32 * j), uk, t2[j]);
+          }
         }
-        if (lane < csize) {
-          double* dst = cluster.map_shared_rank(wbuf, lane) + row0 + r0;
-          dst[0] = s0;
-          if (r0 + 1 < nrows) dst[1] = s1;
-          if (r0 + 2 < nrows) dst[2] = s2;
+        for (; k < nP; k += 32) {
+          const double uk = vu[k];
+          t0[0] = fma(SLAB_SMEM ? a0[k] : __ldg(a0 + k), uk, t0[0]);
+          t1[0] = fma(SLAB_SMEM ? a1[k] : __ldg(a1 + k), uk, t1[0]);
+          t2[0] = fma(SLAB_SMEM ? a2[k] : __ldg(a2 + k), uk, t2[0]);
         }
+        s0 = (t0[0] + t0[1]) + (t0[2] + t0[3]);
+        s1 = (t1[0] + t1[1]) + (t1[2] + t1[3]);
+        s2 = (t2[0] + t2[1]) + (t2[2] + t2[3]);
       }
-      return;
-    }
-    for (int r0 = wid * 3; r0 < nrows; r0 += NW * 3) {
-      const bool h1 = r0 + 1 < nrows, h2 = r0 + 2 < nrows;
-      const double* a0 = SLAB_SMEM ? slab + (size_t)r0 * nP : S + (size_t)(row0 + r0) * nP;
-      const double* a1 = a0 + (h1 ? nP : 0);
-      const double* a2 = a0 + (h2 ? 2 * nP : 0);
-      // 4 independent partial sums per row: the k loop is a chain of shared-memory loads and fp64 FMAs
-      double t0[4] = {0, 0, 0, 0}, t1[4] = {0, 0, 0, 0}, t2[4] = {0, 0, 0, 0};
-      int k = lane;
-      for (; k + 96 < nP; k += 128) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const double uk = vu[k + 32 * j];
-          t0[j] = fma(SLAB_SMEM ? a0[k + 32 * j] : __ldg(a0 + k + 32 * j), uk, t0[j]);
-          t1[j] = fma(SLAB_SMEM ? a1[k + 32 * j] : __ldg(a1 + k + 32 * j), uk, t1[j]);
-          t2[j] = fma(SLAB_SMEM ? a2[k + 32 * j] : __ldg(a2 + k + 32 * j), uk, t2[j]);
-        }
-      }
-      for (; k < nP; k += 32) {
-        const double uk = vu[k];
-        t0[0] = fma(SLAB_SMEM ? a0[k] : __ldg(a0 + k), uk, t0[0]);
-        t1[0] = fma(SLAB_SMEM ? a1[k] : __ldg(a1 + k), uk, t1[0]);
-        t2[0] = fma(SLAB_SMEM ? a2[k] : __ldg(a2 + k), uk, t2[0]);
-      }
-      double s0 = (t0[0] + t0[1]) + (t0[2] + t0[3]);
-      double s1 = (t1[0] + t1[1]) + (t1[2] + t1[3]);
-      double s2 = (t2[0] + t2[1]) + (t2[2] + t2[3]);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         s0 += __shfl_xor_sync(0xffffffffu, s0, o);
         s1 += __shfl_xor_sync(0xffffffffu, s1, o);
         s2 += __shfl_xor_sync(0xffffffffu, s2, o);
       }
+      dpart = fma(s0, vu[row0 + r0], dpart);
+      if (h1) dpart = fma(s1, vu[row0 + r0 + 1], dpart);
+      if (h2) dpart = fma(s2, vu[row0 + r0 + 2], dpart);
       if (lane < csize) {
         double* dst = cluster.map_shared_rank(wbuf, lane) + row0 + r0;
         dst[0] = s0;
@@ -918,67 +1005,49 @@ pcg_cluster_kernel(const double* __restrict__ S, const double* __restrict__ bvec
         if (h2) dst[2] = s2;
       }
     }
+    if (lane < csize) cluster.map_shared_rank(dbuf, lane)[rank * NW + wid] = dpart;
   };
-  auto dots = [&](const double* wbuf, double& g, double& d) {  // g = r.u, d = w.u (identical in every thread)
-    double pg = 0.0, pd = 0.0;
-    for (int i = tid; i < nP; i += PCG_THREADS) {
-      const double ui = vu[i];
-      pg = fma(vr[i], ui, pg);
-      pd = fma(wbuf[i], ui, pd);
-    }
+
+  // [C] g (CTA-local slots of phase A) and d (cluster-wide slots of phase B), identical in every thread
+  auto phase_c = [&](int it, double& g, double& d) {
+    const double* gs = gslot + (it & 1) * NW;
+    const double* ds = dslot + ((it + 1) & 1) * (MAXC * NW);
+    double pg = (lane < NW) ? gs[lane] : 0.0;
+    double pd = 0.0;
+    for (int k = lane; k < csize * NW; k += 32) pd += ds[k];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       pg += __shfl_xor_sync(0xffffffffu, pg, o);
       pd += __shfl_xor_sync(0xffffffffu, pd, o);
     }
-    if (lane == 0) { sh[wid] = pg; sh[NW + wid] = pd; }
-    __syncthreads();
-    g = (lane < NW) ? sh[lane] : 0.0;
-    d = (lane < NW) ? sh[NW + lane] : 0.0;
-#pragma unroll
-    for (int o = NW / 2; o > 0; o >>= 1) {
-      g += __shfl_xor_sync(0xffffffffu, g, o);
-      d += __shfl_xor_sync(0xffffffffu, d, o);
-    }
-    g = __shfl_sync(0xffffffffu, g, 0);
-    d = __shfl_sync(0xffffffffu, d, 0);
+    g = pg; d = pd;
   };
 
-  precond();
+  double g = 0.0, d = 0.0;
+  phase_a(0, 0.0, 0.0);
   __syncthreads();
   cluster.sync();  // every CTA of the cluster is running before the first remote write
-  matvec(vw);
+  phase_b(0);
   cluster.sync();
-  double g, d;
-  dots(vw, g, d);
+  phase_c(0, g, d);
   const double g0 = g;
   double alpha = (d > 0.0) ? g / d : 0.0, beta = 0.0;
   int it = 0, flag = 0;
-  long long tprof[5] = {0, 0, 0, 0, 0};  // cycles: update, precond, matvec, cluster barrier, dots (thread 0)
+  long long tprof[5] = {0, 0, 0, 0, 0};  // cycles: A, block barrier, B, cluster barrier, C (thread 0)
   if (g0 > 0.0 && !(d > 0.0)) flag = 1;
   if (g0 > 0.0 && flag == 0) {
     for (it = 1; it <= max_iter; ++it) {
-      const double* wcur = vw + ((it - 1) & 1) * nPa;
-      double* wnext = vw + (it & 1) * nPa;
       const long long c0 = clock64();
-      for (int i = tid; i < nP; i += PCG_THREADS) {
-        const double pi = fma(beta, vp[i], vu[i]);
-        const double qi = fma(beta, vq[i], wcur[i]);
-        vp[i] = pi; vq[i] = qi;
-        vx[i] = fma(alpha, pi, vx[i]);
-        vr[i] = fma(-alpha, qi, vr[i]);
-      }
-      __syncthreads();
+      phase_a(it, alpha, beta);
       const long long c1 = clock64();
-      precond();
       __syncthreads();
       const long long c2 = clock64();
-      matvec(wnext);
+      phase_b(it);
       const long long c3 = clock64();
       cluster.sync();
       const long long c4 = clock64();
       double gn, dn;
-      dots(wnext, gn, dn);
+      phase_c(it, gn, dn);
       const long long c5 = clock64();
       tprof[0] += c1 - c0; tprof[1] += c2 - c1; tprof[2] += c3 - c2; tprof[3] += c4 - c3; tprof[4] += c5 - c4;
       if (!(gn == gn) || !(dn == dn)) { flag = 2; break; }
@@ -990,9 +1059,9 @@ pcg_cluster_kernel(const double* __restrict__ S, const double* __restrict__ bvec
       g = gn;
     }
   }
-  cluster.sync();  // nobody exits while peers may still write into its w buffers
+  cluster.sync();  // nobody exits while peers may still write into its buffers
   if (rank == 0) {
-    for (int i = tid; i < nP; i += PCG_THREADS) xout[i] = vx[i];
+    for (int i = tid; i < nP; i += PCG_THREADS) xout[i] = vx[i];  // x and r were advanced together in phase A
     if (tid == 0) {
       sc[SC_PCG_ITS] = (double)it;
       sc[SC_PCG_REL] = (g0 > 0.0) ? sqrt(fabs(g) / g0) : 0.0;
@@ -1165,6 +1234,11 @@ __global__ void cm_gather_kernel(const int* __restrict__ cm_pos, const int* __re
     cm_orig[q] = o;
     cm_xy[q] = obs_xy[o];
   }
+}
+__global__ void count_dups_kernel(const int* __restrict__ pm_pt, const int* __restrict__ pm_cam, int n,
+                                  int* __restrict__ count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > 0 && i < n && pm_pt[i] == pm_pt[i - 1] && pm_cam[i] == pm_cam[i - 1]) atomicAdd(count, 1);
 }
 __global__ void validate_kernel(const int* __restrict__ cam, const int* __restrict__ pt, int n, int n_cams, int n_pts,
                                 int* __restrict__ bad) {

@@ -212,7 +212,7 @@ class BAProblem:
         verbose: int = 0,
         use_bounds: bool = True,
         lambda0: float = 1e-4,
-        pcg_tol: float = 1e-10,
+        pcg_tol: float = 1e-6,
         allreduce=None,
         rank: int = 0,
         world_size: int = 1,

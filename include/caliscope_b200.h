@@ -97,7 +97,7 @@ typedef struct {
   int32_t verbose;     /* 0 silent, 1 summary, 2 per-iteration table on stderr */
   int32_t use_bounds;  /* 1: s in [0.5,2], k1 in [-1,1], k2 in [-2,2] (bundle_parameterization.py:151-164) */
   double lambda0;      /* initial LM damping; <= 0: 1e-4 */
-  double pcg_tol;      /* relative PCG tolerance for the reduced camera system; <= 0: 1e-10 */
+  double pcg_tol;      /* relative PCG tolerance for the reduced camera system; <= 0: 1e-6 */
   int32_t pcg_max_iter; /* <= 0: 4 * n_camera_params */
   CbAllReduceSum allreduce; /* NULL: single GPU */
   void* allreduce_user;

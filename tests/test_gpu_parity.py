@@ -164,7 +164,7 @@ def test_normal_equation_stages(name, loss, lam):
     assert close(ne["b"], b, 1e-9)
     assert np.abs(ne["S"] - ne["S"].T).max() <= 1e-12 * np.abs(S).max()
     dc = np.linalg.solve(S, -b).reshape(rig.n_cams, P)
-    assert close(ne["dc"], dc, 1e-6)  # PCG to 1e-10 relative residual
+    assert close(ne["dc"], dc, 1e-3)  # PCG stops at 1e-6 relative (preconditioned) residual
     dp = -np.einsum("jab,jb->ja", Einv, lin.gp + np.einsum("jcpa,cp->ja", Wd, ne["dc"]))
     assert close(ne["dp"], dp, 1e-9)
 
