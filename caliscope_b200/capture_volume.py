@@ -1,0 +1,123 @@
+"""Seam S2: a replacement for ``CaptureVolume.optimize`` and for the observation ->
+world-point map that runs on every ``CaptureVolume`` construction, with the host preparation
+vectorised (the reference's per-row Python loops cost ~30 s at 2 M observations and would otherwise
+dwarf a 4 ms GPU solve).
+
+Mirrors /root/reference/src/caliscope/core/capture_volume.py:
+  * ``fast_img_to_obj_map``  == ``_compute_img_to_obj_map`` (:119-139)
+  * ``optimize``             == ``CaptureVolume.optimize``   (:322-444), same signature, same result type,
+                                same errors (``CalibrationError`` iff ``strict`` and not converged).
+
+Everything except the solve itself is the reference's own classes (imported from ``caliscope`` at call
+time); the solve goes to the CUDA engine through ``caliscope_b200.solver.solve_arrays``.
+"""
+from __future__ import annotations
+
+import logging
+from copy import deepcopy
+
+import numpy as np
+import pandas as pd
+
+from . import solver
+from .problem import blocks_to_arrays
+
+logger = logging.getLogger(__name__)
+
+_KEYS = ["sync_index", "object_id", "keypoint_id"]
+
+
+def fast_img_to_obj_map(self) -> np.ndarray:
+    """Row index into ``world_points.df`` for every image observation, -1 if unmatched.  Observations of
+    static objects are looked up at ``STATIC_SYNC_INDEX`` (capture_volume.py:124-132).  A dict keeps the
+    LAST row for a duplicated key; ``drop_duplicates(keep='last')`` reproduces that."""
+    from caliscope.core.point_data import STATIC_SYNC_INDEX
+
+    wdf = self.world_points.df
+    # the reference maps to the frame's index LABELS (reset_index().rename(index -> world_idx), :121)
+    world = wdf[_KEYS].reset_index(drop=True).assign(world_idx=np.asarray(wdf.index, dtype=np.int64))
+    world = world.drop_duplicates(subset=_KEYS, keep="last")
+    img = self.image_points.df[_KEYS].copy()
+    static_ids = self.constraints.static_object_ids if self.constraints else frozenset()
+    if static_ids:
+        is_static = img["object_id"].astype(np.int64).isin([int(s) for s in static_ids]).to_numpy()
+        img.loc[is_static, "sync_index"] = STATIC_SYNC_INDEX
+    for c in _KEYS:
+        img[c] = img[c].astype(np.int64)
+        world[c] = world[c].astype(np.int64)
+    merged = img.merge(world, on=_KEYS, how="left", sort=False)
+    out = merged["world_idx"].fillna(-1).to_numpy().astype(np.int32)
+    n_unmatched = int(np.sum(out == -1))
+    if n_unmatched > 0:
+        logger.info(f"{n_unmatched} of {len(out)} image observations have no world point")
+    return out
+
+
+def ba_arrays(self):
+    """capture_volume.py:346-358 without the per-row ``posed_cam_id_to_index`` property calls."""
+    cam_index = self.camera_array.posed_cam_id_to_index  # built once
+    cam_ids = self.image_points.df["cam_id"].to_numpy()
+    lut_keys = np.fromiter(cam_index.keys(), dtype=np.int64, count=len(cam_index))
+    lut_vals = np.fromiter(cam_index.values(), dtype=np.int64, count=len(cam_index))
+    order = np.argsort(lut_keys)
+    lut_keys, lut_vals = lut_keys[order], lut_vals[order]
+    pos = np.searchsorted(lut_keys, cam_ids)
+    pos_c = np.clip(pos, 0, max(len(lut_keys) - 1, 0))
+    posed = (lut_keys[pos_c] == cam_ids) if len(lut_keys) else np.zeros(len(cam_ids), bool)
+    mask = (self.img_to_obj_map >= 0) & posed
+    camera_indices = lut_vals[pos_c[mask]].astype(np.int16)
+    image_coords = self.image_points.df[["img_loc_x", "img_loc_y"]].to_numpy(dtype=np.float64)[mask]
+    return camera_indices, image_coords, self.img_to_obj_map[mask], mask
+
+
+def optimize(self, ftol: float = 1e-8, max_nfev: int | None = None, verbose: int = 0, strict: bool = True,
+             use_constraints: bool = True, pixel_sigma: float = 1.0, *, refine_intrinsics: bool = False,
+             loss: str = "linear", f_scale: float = 1.0):  # fmt: skip
+    """Bundle adjustment via pixel-space residuals on the B200 (drop-in for CaptureVolume.optimize)."""
+    from caliscope.core.bundle_parameterization import BundleParameterization
+    from caliscope.core.capture_volume import _SCIPY_STATUS_REASONS, CaptureVolume, OptimizationStatus
+    from caliscope.core.point_data import WorldPoints
+
+    if use_constraints and self.constraints is not None and self._build_constraint_arrays() is not None:
+        raise NotImplementedError(
+            "rigid-distance constraint rows are not implemented in the CUDA engine yet; call "
+            "optimize(use_constraints=False) or use seam S1 with install(fallback=...)"
+        )
+    camera_indices, image_coords, image_to_world_indices, _ = ba_arrays(self)
+    new_camera_array = deepcopy(self.camera_array)
+    parameterization = BundleParameterization.from_camera_array(
+        new_camera_array, n_points=len(self.world_points.points), refine_intrinsics=refine_intrinsics
+    )
+    x0 = parameterization.pack(new_camera_array, self.world_points.points)
+    flags, const = blocks_to_arrays(parameterization.blocks)
+    logger.info(f"Beginning bundle adjustment on {len(image_coords)} observations")
+    result = solver.solve_arrays(
+        flags, const, parameterization.n_points, camera_indices, image_to_world_indices, image_coords, x0,
+        use_bounds=True, ftol=ftol, max_nfev=max_nfev, loss=loss, f_scale=f_scale, verbose=verbose,
+    )  # fmt: skip
+    termination_reason = _SCIPY_STATUS_REASONS.get(result.status, f"unknown_{result.status}")
+    converged = result.status in (1, 2, 3, 4)
+    if strict and not converged:
+        from caliscope.exceptions import CalibrationError
+
+        raise CalibrationError(
+            f"Bundle adjustment did not converge: {termination_reason}\n"
+            f"Pass strict=False to suppress this error and inspect the result."
+        )
+    new_points_xyz = parameterization.unpack_into(new_camera_array, result.x)
+    status = OptimizationStatus(
+        converged=converged,
+        termination_reason=termination_reason,
+        iterations=int(result.nfev),
+        final_cost=float(result.cost),
+        bound_warnings=parameterization.bound_warnings(result.x),
+    )
+    new_world_df = self.world_points.df.copy()
+    new_world_df[["x_coord", "y_coord", "z_coord"]] = new_points_xyz
+    return CaptureVolume(
+        camera_array=new_camera_array,
+        image_points=self.image_points,
+        world_points=WorldPoints(new_world_df),
+        constraints=self.constraints,
+        _optimization_status=status,
+    )

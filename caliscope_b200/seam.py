@@ -18,11 +18,17 @@ from . import solver
 
 _TARGET = "caliscope.core.capture_volume"
 _original = None
+_original_methods: dict = {}
 
 
-def install(fallback=None) -> None:
-    """``fallback``: optional callable with scipy's ``least_squares`` signature for calls this engine does
-    not implement (distance-constraint rows).  Default ``None`` = raise ``NotImplementedError``."""
+def install(fallback=None, full: bool = False) -> None:
+    """Seam S1: replace the ``least_squares`` attribute ``CaptureVolume.optimize`` calls.
+
+    ``fallback``: optional callable with scipy's ``least_squares`` signature for calls this engine does
+    not implement (distance-constraint rows).  Default ``None`` = raise ``NotImplementedError``.
+    ``full=True`` additionally installs seam S2: ``CaptureVolume.optimize`` and
+    ``CaptureVolume._compute_img_to_obj_map`` are replaced by the vectorised versions in
+    ``caliscope_b200.capture_volume`` (same signatures and results, no per-row Python loops)."""
     global _original
     from . import _lib
 
@@ -32,19 +38,32 @@ def install(fallback=None) -> None:
         _original = mod.least_squares
     solver._fallback = fallback
     mod.least_squares = solver.least_squares
+    if full:
+        from . import capture_volume as cv2b
+
+        cls = mod.CaptureVolume
+        if not _original_methods:
+            _original_methods.update(optimize=cls.optimize, _compute_img_to_obj_map=cls._compute_img_to_obj_map)
+        cls.optimize = cv2b.optimize
+        cls._compute_img_to_obj_map = cv2b.fast_img_to_obj_map
 
 
 def uninstall() -> None:
     global _original
+    mod = importlib.import_module(_TARGET)
     if _original is not None:
-        importlib.import_module(_TARGET).least_squares = _original
+        mod.least_squares = _original
         _original = None
+    if _original_methods:
+        for name, fn in _original_methods.items():
+            setattr(mod.CaptureVolume, name, fn)
+        _original_methods.clear()
     solver._fallback = None
 
 
 @contextlib.contextmanager
-def installed(fallback=None):
-    install(fallback)
+def installed(fallback=None, full: bool = False):
+    install(fallback, full)
     try:
         yield
     finally:

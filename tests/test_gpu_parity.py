@@ -368,3 +368,49 @@ def test_solve_filter_resolve_loop_matches_scipy_stage_by_stage():
     s3 = O.solve_scipy(rig3, out.stages[1].x)
     assert abs(out.rmse_px[2] - O.overall_rmse_px(s3.x, rig3)) < 1e-6
     assert out.rmse_px[2] < out.rmse_px[0]
+
+
+# ---------------------------------------------------------------------------------------------
+# Schur tiling: every work-item shape (single diagonal tile, diagonal pairs, off-diagonal tiles,
+# odd / even block counts, k-slab splits) against the dense NumPy Schur complement
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize(
+    "n_cams,refine",
+    [(5, False), (17, False), (33, False), (40, True), (64, False)],  # 30, 102, 198, 360, 384 reduced parameters
+)
+def test_schur_system_all_tile_shapes(n_cams, refine):
+    from caliscope_b200 import synthetic
+
+    r = synthetic.make_rig(n_cams, 700, 9000, seed=n_cams, refine_intrinsics=refine)
+    rig = O.Rig(r.cam_flags, r.cam_const, r.n_pts, r.obs_cam, r.obs_pt, r.obs_xy)
+    lam = 1e-3
+    with make_problem(rig) as p:
+        ne = p.normal_equations(r.x0, lam)
+        P = p.cam_stride
+    lin = LS.linearize(r.x0, rig)
+    Dc2 = np.einsum("cii->ci", lin.U)
+    Dp2 = np.einsum("jii->ji", lin.V)
+    S, b, Einv, Wd = LS.schur_system(lin, rig, lam, np.where(Dc2 > 0, Dc2, 1.0), np.where(Dp2 > 0, Dp2, 1.0))
+    scale = np.abs(S).max()
+    assert np.abs(ne["S"] - S).max() < 1e-9 * scale
+    assert np.abs(ne["S"] - ne["S"].T).max() < 1e-12 * scale
+    assert np.abs(ne["b"] - b).max() < 1e-9 * np.abs(b).max()
+    dc = np.linalg.solve(S, -b).reshape(n_cams, P)
+    assert np.abs(ne["dc"] - dc).max() < 1e-3 * np.abs(dc).max()
+    dp = -np.einsum("jab,jb->ja", Einv, lin.gp + np.einsum("jcpa,cp->ja", Wd, ne["dc"]))
+    assert np.abs(ne["dp"] - dp).max() < 1e-9 * np.abs(dp).max()
+
+
+def test_solve_with_many_cameras_and_sparse_visibility():
+    """Each point seen by few of many cameras (sparse visibility), odd tile count."""
+    from caliscope_b200 import synthetic
+
+    r = synthetic.make_rig(33, 2000, 12000, seed=11)
+    rig = O.Rig(r.cam_flags, r.cam_const, r.n_pts, r.obs_cam, r.obs_pt, r.obs_xy)
+    ref = O.solve_scipy(rig, r.x0)
+    with make_problem(rig) as p:
+        res = p.solve(r.x0)
+        rm = p.overall_rmse_px(res.x)
+    assert res.status in (1, 2, 3, 4)
+    assert res.cost <= ref.cost * (1 + 1e-8)
+    assert abs(rm - O.overall_rmse_px(ref.x, rig)) < 1e-6

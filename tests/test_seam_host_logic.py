@@ -1,0 +1,140 @@
+"""Seam S1 / S2 host logic against the unmodified reference (build container only: needs
+/root/reference).  The CUDA solve is replaced by a recorder that returns the reference's own scipy
+result, so what is checked is everything AROUND the solve: the arrays handed to the engine, the
+vectorised observation->point map, and the CaptureVolume that comes back."""
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+REF = Path("/root/reference")
+pytestmark = pytest.mark.skipif(not (REF / "src").exists(), reason="reference checkout only exists in the build container")
+
+
+@pytest.fixture(scope="module")
+def session_volume():
+    for p in (str(ROOT / "tests" / "golden" / "_refshim"), str(REF / "src")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from caliscope.cameras.camera_array import CameraArray
+    from caliscope.core.capture_volume import CaptureVolume
+    from caliscope.core.point_data import ImagePoints, WorldPoints
+
+    d = REF / "tests/sessions/post_optimization"
+    ca = CameraArray.from_toml(d / "camera_array.toml")
+    ip = ImagePoints.from_csv(d / "calibration/extrinsic/CHARUCO/xy_CHARUCO.csv")
+    wp = WorldPoints.from_csv(d / "calibration/extrinsic/CHARUCO/xyz_CHARUCO.csv")
+    return CaptureVolume(ca, ip, wp)
+
+
+def _reference_run(cv, **kw):
+    """Run the unmodified optimize(), recording what it hands to scipy and what scipy returns."""
+    import caliscope.core.capture_volume as mod
+
+    rec = {}
+    real = mod.least_squares
+
+    def spy(fun, x0, **k):
+        res = real(fun, x0, **k)
+        rec.update(x0=np.array(x0), args=k["args"], result=res, kwargs=k)
+        return res
+
+    mod.least_squares = spy
+    try:
+        out = cv.optimize(**kw)
+    finally:
+        mod.least_squares = real
+    return out, rec
+
+
+def test_img_to_obj_map_vectorised_equals_reference(session_volume):
+    from caliscope.core.constraints import ConstraintSet
+    from caliscope.core.capture_volume import CaptureVolume
+    from caliscope_b200.capture_volume import fast_img_to_obj_map
+
+    cv = session_volume
+    assert np.array_equal(fast_img_to_obj_map(cv), cv.img_to_obj_map)
+    # static object: world rows moved to STATIC_SYNC_INDEX, observations keep their sync_index
+    from caliscope.core.point_data import STATIC_SYNC_INDEX, WorldPoints
+
+    wdf = cv.world_points.df.copy()
+    first = wdf.drop_duplicates(subset=["object_id", "keypoint_id"]).copy().reset_index(drop=True)
+    first["sync_index"] = STATIC_SYNC_INDEX
+    oid = int(wdf["object_id"].iloc[0])
+    cs = ConstraintSet(distances=(), static_object_ids=frozenset({oid}))
+    cv_static = CaptureVolume(cv.camera_array, cv.image_points, WorldPoints(first), constraints=cs)
+    assert np.array_equal(fast_img_to_obj_map(cv_static), cv_static.img_to_obj_map)
+    assert (cv_static.img_to_obj_map >= 0).sum() > len(first)  # many observations per static point
+
+
+@pytest.mark.parametrize("refine", [False, True])
+def test_s2_optimize_hands_the_engine_what_the_reference_hands_scipy(session_volume, monkeypatch, refine):
+    from caliscope_b200 import capture_volume as S2
+    from caliscope_b200 import solver
+    from caliscope_b200.problem import SolveResult, blocks_to_arrays
+
+    cv = session_volume
+    ref_out, rec = _reference_run(cv, refine_intrinsics=refine)
+    par, cam, xy, obj = rec["args"][:4]
+    seen = {}
+
+    def fake_solve_arrays(flags, const, n_pts, camera_indices, obj_indices, image_coords, x0, **kw):
+        seen.update(flags=flags, const=const, n_pts=n_pts, cam=camera_indices, obj=obj_indices, xy=image_coords, x0=x0, kw=kw)
+        r = rec["result"]
+        return SolveResult(x=r.x.copy(), status=int(r.status), nfev=int(r.nfev), njev=int(r.njev), nit=0, cost=float(r.cost),
+                           initial_cost=0.0, optimality=0.0, lambda_final=0.0, pcg_iterations=0, kernel_launches=0,
+                           solve_ms=0.0, rj_ms=0.0, rj_launches=0)  # fmt: skip
+
+    monkeypatch.setattr(solver, "solve_arrays", fake_solve_arrays)
+    out = S2.optimize(cv, refine_intrinsics=refine)
+    f, c = blocks_to_arrays(par.blocks)
+    assert np.array_equal(seen["flags"], f) and np.array_equal(seen["const"], c)
+    assert seen["n_pts"] == par.n_points
+    assert np.array_equal(seen["cam"], cam) and seen["cam"].dtype == cam.dtype
+    assert np.array_equal(seen["xy"], xy) and np.array_equal(seen["obj"], obj)
+    assert np.array_equal(seen["x0"], rec["x0"])
+    assert seen["kw"]["ftol"] == 1e-8 and seen["kw"]["loss"] == "linear" and seen["kw"]["max_nfev"] is None
+    # the returned volume is what the reference builds from the same result
+    assert out.optimization_status == ref_out.optimization_status
+    assert np.array_equal(out.world_points.points, ref_out.world_points.points)
+    for cid, camr in ref_out.camera_array.cameras.items():
+        camo = out.camera_array.cameras[cid]
+        assert np.array_equal(camo.rotation, camr.rotation) and np.array_equal(camo.translation, camr.translation)
+        assert np.array_equal(camo.matrix, camr.matrix) and np.array_equal(camo.distortions, camr.distortions)
+    assert abs(out.reprojection_report.overall_rmse - ref_out.reprojection_report.overall_rmse) == 0.0
+    assert cv.optimization_status is None  # input untouched
+
+
+def test_s2_strict_raises_calibration_error(session_volume, monkeypatch):
+    from caliscope.exceptions import CalibrationError
+    from caliscope_b200 import capture_volume as S2
+    from caliscope_b200 import solver
+    from caliscope_b200.problem import SolveResult
+
+    def fake(flags, const, n_pts, cam, obj, xy, x0, **kw):
+        return SolveResult(x=np.array(x0), status=0, nfev=3, njev=1, nit=0, cost=1.0, initial_cost=1.0, optimality=1.0,
+                           lambda_final=0.0, pcg_iterations=0, kernel_launches=0, solve_ms=0.0, rj_ms=0.0, rj_launches=0)  # fmt: skip
+
+    monkeypatch.setattr(solver, "solve_arrays", fake)
+    with pytest.raises(CalibrationError, match="max_evaluations"):
+        S2.optimize(session_volume, max_nfev=3)
+    out = S2.optimize(session_volume, max_nfev=3, strict=False)
+    assert out.optimization_status.converged is False and out.optimization_status.iterations == 3
+
+
+def test_seam_install_full_patches_and_restores(session_volume):
+    import caliscope.core.capture_volume as mod
+    import caliscope_b200.seam as seam
+    from caliscope_b200 import capture_volume as S2
+    from caliscope_b200 import solver
+
+    before = (mod.least_squares, mod.CaptureVolume.optimize, mod.CaptureVolume._compute_img_to_obj_map)
+    with seam.installed(full=True):
+        assert mod.least_squares is solver.least_squares
+        assert mod.CaptureVolume.optimize is S2.optimize
+        assert mod.CaptureVolume._compute_img_to_obj_map is S2.fast_img_to_obj_map
+    assert (mod.least_squares, mod.CaptureVolume.optimize, mod.CaptureVolume._compute_img_to_obj_map) == before
