@@ -555,7 +555,13 @@ int lm_solve(CbBaProblem* p, const CbBaOptions* opt, double* x_inout, CbBaResult
       cost = h.sc[cb::SC_COST];
       gnorm = h.sc[cb::SC_GNORM_C];
       for (int s = 0; s < p->red_slots; ++s) gnorm = std::max(gnorm, h.slots[s]);
-      if (njev == 1) res->initial_cost = cost;
+      if (njev == 1) {
+        res->initial_cost = cost;
+        if (!std::isfinite(cost)) {  // scipy: ValueError("Residuals are not finite in the initial point.")
+          g_last_error = "Residuals are not finite in the initial point.";
+          return CB_E_INVALID;
+        }
+      }
       if (gnorm < gtol) { status = 1; break; }
       ++nit;
     }

@@ -83,12 +83,18 @@ def make_allreduce_hook(group=None, device_buffers: bool = True):
     import torch
     import torch.distributed as dist
 
+    cache: dict = {}  # (ptr, n) -> tensor view, stream ptr -> ExternalStream: keep the per-call Python cost low
+
     def hook(_user, buf_ptr, n, stream_ptr):
         try:
             if device_buffers:
-                t = torch.as_tensor(_CudaBuffer(buf_ptr, n), device="cuda")
+                t = cache.get((buf_ptr, n))
+                if t is None:
+                    t = cache[(buf_ptr, n)] = torch.as_tensor(_CudaBuffer(buf_ptr, n), device="cuda")
                 if stream_ptr:
-                    ext = torch.cuda.ExternalStream(int(stream_ptr))
+                    ext = cache.get(stream_ptr)
+                    if ext is None:
+                        ext = cache[stream_ptr] = torch.cuda.ExternalStream(int(stream_ptr))
                     with torch.cuda.stream(ext):
                         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
                 else:

@@ -292,6 +292,10 @@ def test_invalid_inputs_are_rejected():
     with pytest.raises(cb.EngineError):  # fisheye blocks are always locked (bundle_parameterization.py:76-94)
         cb.BAProblem(np.array([3, 0], np.int32), rig.cam_const[:2], rig.n_pts, rig.obs_cam % 2, rig.obs_pt, rig.obs_xy)
     with make_problem(rig) as p:
+        x_bad = g["x0"].copy()
+        x_bad[rig.n_camera_params + 1] = np.nan
+        with pytest.raises(cb.EngineError, match="not finite in the initial point"):  # scipy raises ValueError here
+            p.solve(x_bad)
         with pytest.raises(ValueError):
             p.solve(g["x0"][:-1])
         with pytest.raises(ValueError):
