@@ -40,6 +40,8 @@ WORKLOADS = {
     "cfg3": (16, 10_000, 400_000, True),
     "cfg2": (8, 2_000, 40_000, False),
 }
+# BASELINE.json configs[4]: cfg4 rig + 2 % outliers, solve(linear) -> solve(soft_l1) -> 2.5 % per-camera cull -> solve(linear)
+PIPELINE_WORKLOADS = {"cfg5": (64, 50_000, 2_000_000, 0.02), "cfg5_small": (8, 2_000, 40_000, 0.02)}
 
 
 def make_workload(name: str):
@@ -86,7 +88,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "10", "-i", str(self.gpu)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
             )  # fmt: skip
         except Exception:
@@ -300,7 +302,6 @@ def run_ours(args) -> None:
     wall_ms = 1e3 * (time.perf_counter() - t0)
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
     launches = cb._lib.load().cb_ba_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     x_final = res.x
     if world > 1:
         x_final = D.gather_points(res.x, ncp, rig.n_pts, shard)
@@ -328,6 +329,7 @@ def run_ours(args) -> None:
     barrier()
     e2e_wall_ms = 1e3 * (time.perf_counter() - t1)
     e2e_ms = max_over_ranks(max(f0.elapsed_time(f1), e2e_wall_ms))
+    clocks = sampler.stop() if rank == 0 else None  # sampled across both timed regions
     h2d = int(l_cam.nbytes + l_pt.nbytes + l_xy.nbytes + x0.nbytes + rig.cam_flags.nbytes + rig.cam_const.nbytes)
     d2h = int(x0.nbytes + 8 * 32)
 
@@ -413,20 +415,59 @@ def run_ours(args) -> None:
         dist.destroy_process_group()
 
 
+def run_pipeline(args) -> None:
+    """Outlier-filter + re-solve loop (calibrate_extrinsics.py:206-250) on one GPU; one step = the whole loop."""
+    import torch
+
+    from caliscope_b200 import pipeline, synthetic
+
+    n_cams, n_pts, n_obs, frac = PIPELINE_WORKLOADS[args.workload]
+    rig = synthetic.make_rig(n_cams, n_pts, n_obs, seed=0, outlier_frac=frac, name=args.workload)
+    call = lambda: pipeline.solve_filter_resolve(rig.cam_flags, rig.cam_const, rig.n_pts, rig.obs_cam, rig.obs_pt,
+                                                 rig.obs_xy, rig.x0)  # noqa: E731
+    for _ in range(args.warmup):
+        out = call()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    nit = 0
+    for _ in range(args.steps):
+        out = call()
+        nit += sum(s.nit for s in out.stages)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    line = {
+        "metric": METRIC, "value": nit / wall, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {n_cams}-cam / {n_pts}-point / {n_obs}-observation rig with {frac:.0%} outliers, "
+                   "solve(linear) -> solve(soft_l1, ftol 1e-4) -> 2.5 % per-camera cull -> solve(linear); host buffers, "
+                   "problem upload + index build twice per step (BASELINE.json configs[4])"},
+        "stages": [{"loss": l, "nfev": s.nfev, "nit": s.nit, "status": s.status, "cost": s.cost, "solve_ms": s.solve_ms,
+                    "rms_px": r} for l, s, r in zip(("linear", "soft_l1", "linear after cull"), out.stages, out.rmse_px)],
+        "kept_fraction": float(out.keep.mean()),
+        "outliers_removed_fraction": float(1.0 - out.keep[rig.outlier_mask].mean()),
+    }  # fmt: skip
+    print(json.dumps(line), flush=True)
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg4")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS) + sorted(PIPELINE_WORKLOADS), default="cfg4")
     ap.add_argument("--ref-max-nfev", type=int, default=0, help="cap on scipy evaluations per reference step (0: run to convergence)")
     ap.add_argument("--ref-budget-s", type=float, default=240.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
-    if args.impl == "reference":
+    if args.workload in PIPELINE_WORKLOADS:
+        if args.impl != "ours" or args.gpus != 1:
+            raise SystemExit("pipeline workloads run on the CUDA arm, one GPU")
+        run_pipeline(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
