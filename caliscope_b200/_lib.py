@@ -103,6 +103,8 @@ SYMBOLS = {
         [_P, _P, C.c_double, C.c_int32, C.c_double, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     ),
     "cb_ba_error_order_stats": (C.c_int, [_P, _P, C.c_double, _P, _P, _P, _P, _P]),
+    "cb_ba_rmse_px": (C.c_int, [_P, _P, _P, _P, _P]),
+    "cb_ba_cull": (C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(_P), _P, _P, _P]),
     "cb_ba_debug_pcg_time": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "cb_ba_launch_count": (C.c_int64, []),
 }

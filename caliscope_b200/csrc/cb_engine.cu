@@ -173,6 +173,10 @@ struct CbBaProblem {
   int *d_cm_pt = nullptr, *d_cm_row = nullptr, *d_cm_orig = nullptr, *d_cam_start = nullptr;
   int *d_chunk_cam = nullptr, *d_chunk_begin = nullptr, *d_chunk_end = nullptr, *d_cam_chunk_start = nullptr;
   int *d_pt_start = nullptr, *d_pm_orig = nullptr, *d_pm_cam = nullptr, *d_pm_row = nullptr, *d_pm_pt = nullptr;
+  const int *d_obs_cam = nullptr, *d_obs_pt = nullptr;  // caller-order observation list (owned unless the caller's)
+  const double* d_obs_xy = nullptr;
+  std::vector<int> h_cam_flags;
+  std::vector<double> h_cam_const;
   int *d_tile_of = nullptr, *d_tile_slot_start = nullptr, *d_tile_slots = nullptr;
   cb::SyItem* d_items = nullptr;
   int n_items = 0, n_slots = 0;
@@ -827,9 +831,14 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
     CB_CUDA(cudaEventRecord(xy_ready, side_stream()));
     d_cam = t_cam; d_pt = t_pt; d_xy = t_xy;
   }
+  if (t_cam) {  // keep the uploaded list: the cull path compacts it on the device
+    p->allocs.push_back(t_cam); p->allocs.push_back(t_pt); p->allocs.push_back(t_xy);
+  }
+  p->d_obs_cam = d_cam; p->d_obs_pt = d_pt; p->d_obs_xy = d_xy;
+  p->h_cam_flags.assign(d->cam_flags, d->cam_flags + p->n_cams);
+  p->h_cam_const.assign(d->cam_const, d->cam_const + 9 * (size_t)p->n_cams);
   int rc = build_indices(p, d_cam, d_pt, d_xy, st, xy_ready);
   if (xy_ready) cudaEventDestroy(xy_ready);
-  if (t_cam) { cached_free(t_cam); cached_free(t_pt); cached_free(t_xy); }
   CB_TRY(rc);
 
   // Schur work items: off-diagonal tiles and pairs of diagonal tiles, each split over k so that the
@@ -1140,6 +1149,122 @@ int cb_ba_error_order_stats(CbBaProblem* p, const double* x, double q_percent, d
   CB_CUDA(e);
   for (int c = 0; c < p->n_cams; ++c) count[c] = hc[c];
   return CB_OK;
+}
+
+// Overall and per-camera RMS pixel error (reprojection_report's overall_rmse / by_camera,
+// capture_volume.py:197-202), reduced on the device.
+int cb_ba_rmse_px(CbBaProblem* p, const double* x, double* overall, double* per_camera, void* stream) {
+  if (!p || !x || !overall) { g_last_error = "cb_ba_rmse_px: null argument"; return CB_E_INVALID; }
+  CB_CUDA(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  CB_TRY(p->P == 6 ? (eval_mode<6, 4>(p, x, st)) : (eval_mode<9, 4>(p, x, st)));
+  double* d_ss;
+  CB_TRY(dalloc(&d_ss, p->n_cams));
+  CB_LAUNCH(cb::cam_err_stats_kernel, p->n_cams, 256, 0, st, p->d_out2, p->d_cam_start, (const double*)nullptr,
+            (long long*)nullptr, d_ss);
+  std::vector<double> ss(p->n_cams);
+  std::vector<int> cs(p->n_cams + 1);
+  cudaMemcpyAsync(ss.data(), d_ss, sizeof(double) * p->n_cams, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(cs.data(), p->d_cam_start, sizeof(int) * (p->n_cams + 1), cudaMemcpyDeviceToHost, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  cached_free(d_ss);
+  CB_CUDA(e);
+  double tot = 0.0;
+  for (int c = 0; c < p->n_cams; ++c) {
+    tot += ss[c];
+    const int nc = cs[c + 1] - cs[c];
+    if (per_camera) per_camera[c] = nc > 0 ? std::sqrt(ss[c] / nc) : 0.0;
+  }
+  *overall = p->n_obs > 0 ? std::sqrt(tot / p->n_obs) : 0.0;
+  return CB_OK;
+}
+
+// Observation cull on the device (capture_volume.py:607-646): keep error <= thresholds[camera], restore the
+// lowest-error observations of a camera that would fall below min_per_camera, compact the caller-order list
+// and build the filtered problem from it without a host round trip.  keep_mask (host, n_obs bytes, caller
+// order) may be NULL.
+int cb_ba_cull(CbBaProblem* p, const double* x, const double* thresholds, int32_t min_per_camera, CbBaProblem** out,
+               int64_t* n_kept, uint8_t* keep_mask, void* stream) {
+  if (!p || !x || !thresholds || !out || min_per_camera < 1) { g_last_error = "cb_ba_cull: bad argument"; return CB_E_INVALID; }
+  *out = nullptr;
+  CB_CUDA(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = p->n_obs, nc = p->n_cams;
+  CB_TRY(p->P == 6 ? (eval_mode<6, 4>(p, x, st)) : (eval_mode<9, 4>(p, x, st)));
+  double *d_thr, *d_ss;
+  long long* d_kept;
+  unsigned char* d_flag;
+  int *d_iota, *d_sel, *d_nsel;
+  CB_TRY(dalloc(&d_thr, nc)); CB_TRY(dalloc(&d_ss, nc)); CB_TRY(dalloc(&d_kept, nc)); CB_TRY(dalloc(&d_flag, n));
+  CB_TRY(dalloc(&d_iota, n)); CB_TRY(dalloc(&d_sel, n)); CB_TRY(dalloc(&d_nsel, 1));
+  std::vector<double> thr(thresholds, thresholds + nc);
+  std::vector<long long> kept(nc);
+  std::vector<int> cs(nc + 1);
+  CB_CUDA(cudaMemcpyAsync(d_thr, thr.data(), sizeof(double) * nc, cudaMemcpyHostToDevice, st));
+  CB_LAUNCH(cb::cam_err_stats_kernel, nc, 256, 0, st, p->d_out2, p->d_cam_start, (const double*)d_thr, d_kept, d_ss);
+  CB_CUDA(cudaMemcpyAsync(kept.data(), d_kept, sizeof(long long) * nc, cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaMemcpyAsync(cs.data(), p->d_cam_start, sizeof(int) * (nc + 1), cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  bool changed = false;
+  for (int c = 0; c < nc; ++c) {  // safety floor (rare): threshold := n_needed-th smallest of the dropped errors
+    const long long total = cs[c + 1] - cs[c];
+    if (kept[c] < min_per_camera && kept[c] < total) {
+      const long long need = std::min<long long>(min_per_camera, total) - kept[c];
+      std::vector<double> ec((size_t)total);
+      CB_CUDA(cudaMemcpy(ec.data(), p->d_out2 + cs[c], sizeof(double) * total, cudaMemcpyDeviceToHost));
+      std::vector<double> dropped;
+      for (double v : ec)
+        if (!(v <= thr[c])) dropped.push_back(v);
+      if ((long long)dropped.size() >= need) {
+        std::nth_element(dropped.begin(), dropped.begin() + (need - 1), dropped.end());
+        thr[c] = dropped[need - 1];
+        changed = true;
+      }
+    }
+  }
+  if (changed) CB_CUDA(cudaMemcpyAsync(d_thr, thr.data(), sizeof(double) * nc, cudaMemcpyHostToDevice, st));
+  CB_LAUNCH(cb::keep_flag_kernel, cdiv(n, 256), 256, 0, st, p->d_out2, p->d_cm_orig, p->d_cam_start, nc,
+            (const double*)d_thr, n, d_flag);
+  CB_LAUNCH(cb::iota_kernel, cdiv(n, 256), 256, 0, st, d_iota, n);
+  size_t tb = 0;
+  cub::DeviceSelect::Flagged(nullptr, tb, d_iota, d_flag, d_sel, d_nsel, n, st);
+  void* d_tmp;
+  CB_TRY(cached_malloc(&d_tmp, std::max<size_t>(tb, 16)));
+  CB_CUDA(cub::DeviceSelect::Flagged(d_tmp, tb, d_iota, d_flag, d_sel, d_nsel, n, st));
+  g_launches.fetch_add(2);
+  int nsel = 0;
+  CB_CUDA(cudaMemcpyAsync(&nsel, d_nsel, sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (keep_mask) CB_CUDA(cudaMemcpyAsync(keep_mask, d_flag, n, cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  int rc = CB_OK;
+  if (nsel <= 0) {
+    g_last_error = "No image observations provided";  // every observation was culled
+    rc = CB_E_INVALID;
+  } else {
+    int *c_cam, *c_pt;
+    double* c_xy;
+    CB_TRY(dalloc(&c_cam, nsel)); CB_TRY(dalloc(&c_pt, nsel)); CB_TRY(dalloc(&c_xy, 2 * (size_t)nsel));
+    CB_LAUNCH(cb::gather_obs_kernel, cdiv(nsel, 256), 256, 0, st, d_sel, nsel, p->d_obs_cam, p->d_obs_pt,
+              reinterpret_cast<const double2*>(p->d_obs_xy), c_cam, c_pt, reinterpret_cast<double2*>(c_xy));
+    CbBaProblemDesc d2;
+    d2.n_cams = nc; d2.n_pts = p->n_pts; d2.n_obs = nsel;
+    d2.cam_flags = p->h_cam_flags.data(); d2.cam_const = p->h_cam_const.data();
+    d2.obs_cam = c_cam; d2.obs_pt = c_pt; d2.obs_xy = c_xy; d2.obs_on_device = 1;
+    CbBaProblem* q = new CbBaProblem();
+    q->allocs.push_back(c_cam); q->allocs.push_back(c_pt); q->allocs.push_back(c_xy);  // owned by the new problem
+    rc = problem_create_impl(&d2, p->device, st, q);
+    if (rc != CB_OK) {
+      std::string keep = g_last_error;
+      cb_ba_problem_destroy(q);
+      g_last_error = keep;
+    } else {
+      *out = q;
+    }
+  }
+  if (n_kept) *n_kept = nsel;
+  cached_free(d_tmp); cached_free(d_thr); cached_free(d_ss); cached_free(d_kept); cached_free(d_flag);
+  cached_free(d_iota); cached_free(d_sel); cached_free(d_nsel);
+  return rc;
 }
 
 }  // extern "C"

@@ -1318,6 +1318,66 @@ order_stats_kernel(const double* __restrict__ err_cm, const int* __restrict__ ca
   }
 }
 
+// per camera: number of observations with error <= threshold, and sum of squared errors (block per camera)
+__global__ void __launch_bounds__(256)
+cam_err_stats_kernel(const double* __restrict__ err_cm, const int* __restrict__ cam_start,
+                     const double* __restrict__ thr, long long* __restrict__ kept, double* __restrict__ sumsq) {
+  __shared__ double sh[8];
+  __shared__ long long shk[8];
+  const int c = blockIdx.x;
+  const double t = thr ? thr[c] : 0.0;
+  long long k = 0;
+  double s = 0.0;
+  for (int i = cam_start[c] + threadIdx.x; i < cam_start[c + 1]; i += 256) {
+    const double e = err_cm[i];
+    k += (thr && e <= t) ? 1 : 0;
+    s = fma(e, e, s);
+  }
+  s = warp_sum(s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) k += __shfl_xor_sync(0xffffffffu, k, o);
+  if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5] = s; shk[threadIdx.x >> 5] = k; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0;
+    long long b = 0;
+    for (int w = 0; w < 8; ++w) { a += sh[w]; b += shk[w]; }
+    sumsq[c] = a;
+    if (kept) kept[c] = b;
+  }
+}
+
+// keep flag per observation in CALLER order: error <= threshold of its camera (camera found from cam_start)
+__global__ void keep_flag_kernel(const double* __restrict__ err_cm, const int* __restrict__ cm_orig,
+                                 const int* __restrict__ cam_start, int n_cams, const double* __restrict__ thr, int n,
+                                 unsigned char* __restrict__ flag) {
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  int lo = 0, hi = n_cams;  // largest c with cam_start[c] <= q
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (cam_start[mid] <= q) lo = mid; else hi = mid;
+  }
+  flag[cm_orig[q]] = err_cm[q] <= thr[lo] ? 1 : 0;
+}
+
+// gather the kept observations (indices `sel` into the caller-order arrays) into compact arrays
+__global__ void gather_obs_kernel(const int* __restrict__ sel, int n_sel, const int* __restrict__ cam,
+                                  const int* __restrict__ pt, const double2* __restrict__ xy, int* __restrict__ cam_o,
+                                  int* __restrict__ pt_o, double2* __restrict__ xy_o) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_sel) {
+    const int o = sel[i];
+    cam_o[i] = cam[o];
+    pt_o[i] = pt[o];
+    xy_o[i] = xy[o];
+  }
+}
+__global__ void iota_kernel(int* __restrict__ a, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = i;
+}
+
 __global__ void cm_to_orig_kernel(const double* __restrict__ in_cm, const int* __restrict__ cm_orig, int n,
                                   double* __restrict__ out) {
   int q = blockIdx.x * blockDim.x + threadIdx.x;

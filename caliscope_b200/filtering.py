@@ -23,13 +23,13 @@ def _numpy_linear_interp(a: np.ndarray, b: np.ndarray, t: np.ndarray) -> np.ndar
     return out
 
 
-def percentile_thresholds(prob: BAProblem, x, percentile: float, scope: str = "per_camera"):
-    """(euclidean error per observation, threshold per camera index).  ``percentile`` is the share of worst
-    observations to remove, as in ``filter_by_percentile_error``; cameras without observations get +inf."""
+def percentile_thresholds(prob: BAProblem, x, percentile: float, scope: str = "per_camera", want_err: bool = True):
+    """(euclidean error per observation or None, threshold per camera index).  ``percentile`` is the share of
+    worst observations to remove, as in ``filter_by_percentile_error``; cameras without observations get +inf."""
     if not (0 < percentile <= 100):
         raise ValueError(f"percentile must be between 0 and 100, got {percentile}")
     keep_q = 100 - percentile
-    err, lo, hi, cnt = prob.error_order_stats(x, keep_q)
+    err, lo, hi, cnt = prob.error_order_stats(x, keep_q, want_err=want_err or scope == "overall")
     if scope == "per_camera":
         v = (cnt - 1).astype(np.float64) * (keep_q / 100.0)
         t = v - np.floor(v)

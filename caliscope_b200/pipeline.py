@@ -8,7 +8,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .filtering import filter_by_percentile_error
+from .filtering import percentile_thresholds
 from .problem import BAProblem, SolveResult
 
 
@@ -21,7 +21,8 @@ class PipelineResult:
 
 
 def solve_filter_resolve(cam_flags, cam_const, n_pts, obs_cam, obs_pt, obs_xy, x0, *, filter_percentile: float = 2.5,
-                         min_per_camera: int = 10, device: int = 0, ftol: float = 1e-8, verbose: int = 0) -> PipelineResult:  # fmt: skip
+                         min_per_camera: int = 10, device: int = 0, ftol: float = 1e-8, verbose: int = 0,
+                         want_mask: bool = True) -> PipelineResult:  # fmt: skip
     obs_cam = np.ascontiguousarray(obs_cam, dtype=np.int32)
     obs_pt = np.ascontiguousarray(obs_pt, dtype=np.int32)
     obs_xy = np.ascontiguousarray(obs_xy, dtype=np.float64).reshape(-1, 2)
@@ -35,8 +36,11 @@ def solve_filter_resolve(cam_flags, cam_const, n_pts, obs_cam, obs_pt, obs_xy, x
         s2 = prob.solve(s1.x, loss="soft_l1", f_scale=1.0 / f_median, ftol=1e-4, max_nfev=2000, verbose=verbose)
         stages.append(s2)
         rmse.append(prob.overall_rmse_px(s2.x))
-        keep, _, _ = filter_by_percentile_error(prob, s2.x, obs_cam, filter_percentile, "per_camera", min_per_camera)
-    with BAProblem(cam_flags, cam_const, n_pts, obs_cam[keep], obs_pt[keep], obs_xy[keep], device=device) as prob2:
+        # thresholds from exact per-camera order statistics, cull + compaction on the device: the observation
+        # list does not come back to the host between the cull and the re-solve
+        _, thr = percentile_thresholds(prob, s2.x, filter_percentile, "per_camera", want_err=False)
+        prob2, keep = prob.cull(s2.x, thr, min_per_camera, want_mask=want_mask)
+    with prob2:
         s3 = prob2.solve(s2.x, ftol=ftol, verbose=verbose)
         stages.append(s3)
         rmse.append(prob2.overall_rmse_px(s3.x))

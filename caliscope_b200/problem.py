@@ -159,9 +159,43 @@ class BAProblem:
         L.check(self._lib.cb_ba_reproj_errors_px(self._h, _ptr(x), _ptr(out), C.c_void_p(stream)), "reproj_errors_px")
         return out
 
+    def rmse_px(self, x, stream: int = 0) -> tuple[float, np.ndarray]:
+        """(overall RMSE, per-camera RMSE) in pixels, reduced on the device
+        (ReprojectionReport.overall_rmse / by_camera, capture_volume.py:197-202)."""
+        x = self._x(x)
+        overall = C.c_double()
+        per_cam = np.empty(self.n_cams)
+        L.check(self._lib.cb_ba_rmse_px(self._h, _ptr(x), C.addressof(overall), _ptr(per_cam), C.c_void_p(stream)), "rmse_px")
+        return overall.value, per_cam
+
     def overall_rmse_px(self, x) -> float:
-        e = self.reproj_errors_px(x)
-        return float(np.sqrt(np.mean(np.sum(e * e, axis=1))))
+        return self.rmse_px(x)[0]
+
+    def cull(self, x, thresholds, min_per_camera: int = 10, want_mask: bool = True, stream: int = 0):
+        """Device-side ``_filter_by_reprojection_thresholds`` (capture_volume.py:607-646): returns
+        (filtered BAProblem on the same cameras / point numbering, keep mask in this problem's observation
+        order or None).  The observation list never leaves the device."""
+        x = self._x(x)
+        thr = np.ascontiguousarray(thresholds, dtype=np.float64)
+        if thr.shape != (self.n_cams,):
+            raise ValueError(f"thresholds must have shape ({self.n_cams},)")
+        if min_per_camera < 1:
+            raise ValueError(f"min_per_camera must be >= 1, got {min_per_camera}")
+        mask = np.empty(self.n_obs, np.uint8) if want_mask else None
+        h = C.c_void_p()
+        n_kept = C.c_int64()
+        L.check(
+            self._lib.cb_ba_cull(self._h, _ptr(x), _ptr(thr), int(min_per_camera), C.byref(h), C.addressof(n_kept),
+                                 _ptr(mask) if want_mask else None, C.c_void_p(stream)),
+            "cull",
+        )  # fmt: skip
+        new = BAProblem.__new__(BAProblem)
+        new._lib, new._h, new._keep = self._lib, h, ()
+        new.cam_flags, new.cam_const = self.cam_flags, self.cam_const
+        new.n_cams, new.n_pts, new.device, new.n_obs = self.n_cams, self.n_pts, self.device, int(n_kept.value)
+        new.cam_offsets, new.n_camera_params, new.n_params = self.cam_offsets, self.n_camera_params, self.n_params
+        new.cam_stride = self.cam_stride
+        return new, (mask.astype(bool) if want_mask else None)
 
     def normal_equations(self, x, lam: float, loss: str = "linear", f_scale: float = 1.0, stream: int = 0) -> dict:
         """One damped linearisation, every stage returned (test / diagnostic)."""
@@ -184,15 +218,16 @@ class BAProblem:
         out["cost"] = cost.value
         return out
 
-    def error_order_stats(self, x, q_percent: float, stream: int = 0):
+    def error_order_stats(self, x, q_percent: float, stream: int = 0, want_err: bool = True):
         x = self._x(x)
-        err = np.empty(self.n_obs)
+        err = np.empty(self.n_obs) if want_err else None
         lo = np.empty(self.n_cams)
         hi = np.empty(self.n_cams)
         cnt = np.empty(self.n_cams, np.int64)
         L.check(
             self._lib.cb_ba_error_order_stats(
-                self._h, _ptr(x), float(q_percent), _ptr(err), _ptr(lo), _ptr(hi), _ptr(cnt), C.c_void_p(stream)
+                self._h, _ptr(x), float(q_percent), _ptr(err) if want_err else None, _ptr(lo), _ptr(hi), _ptr(cnt),
+                C.c_void_p(stream)
             ),
             "error_order_stats",
         )

@@ -164,6 +164,17 @@ int cb_ba_normal_equations(CbBaProblem* p, const double* x, double lambda, int32
 int cb_ba_error_order_stats(CbBaProblem* p, const double* x, double q_percent, double* err, double* lo,
                             double* hi, int64_t* count, void* stream);
 
+/* Overall and per-camera (nullable, n_cams) RMS pixel error, reduced on the device
+ * (ReprojectionReport.overall_rmse / by_camera, capture_volume.py:197-202). */
+int cb_ba_rmse_px(CbBaProblem* p, const double* x, double* overall, double* per_camera, void* stream);
+
+/* Device-side observation cull == _filter_by_reprojection_thresholds (capture_volume.py:607-646) at array level:
+ * keep error <= thresholds[camera] (host, n_cams), restore lowest-error observations up to min_per_camera, compact
+ * the observation list on the device and build the filtered problem (same cameras and point numbering) from it.
+ * keep_mask: host, n_obs bytes in the caller's observation order, or NULL.  *out must be destroyed by the caller. */
+int cb_ba_cull(CbBaProblem* p, const double* x, const double* thresholds, int32_t min_per_camera, CbBaProblem** out,
+               int64_t* n_kept, uint8_t* keep_mask, void* stream);
+
 /* Diagnostic: mean milliseconds of one PCG-kernel launch forced to run exactly max_iter iterations on the
  * system left by the last cb_ba_normal_equations call. */
 int cb_ba_debug_pcg_time(CbBaProblem* p, int max_iter, int reps, double* ms_per_launch, void* stream);

@@ -418,3 +418,48 @@ def test_solve_with_many_cameras_and_sparse_visibility():
     assert res.status in (1, 2, 3, 4)
     assert res.cost <= ref.cost * (1 + 1e-8)
     assert abs(rm - O.overall_rmse_px(ref.x, rig)) < 1e-6
+
+
+def test_solve_is_bitwise_reproducible():
+    """All reductions are ordered (no floating-point atomics): two solves give identical bits."""
+    from caliscope_b200 import synthetic
+
+    r = synthetic.make_rig(12, 1500, 30000, seed=9, refine_intrinsics=True)
+    rig = O.Rig(r.cam_flags, r.cam_const, r.n_pts, r.obs_cam, r.obs_pt, r.obs_xy)
+    with make_problem(rig) as p:
+        a = p.solve(r.x0)
+        b = p.solve(r.x0)
+    with make_problem(rig) as p2:
+        c = p2.solve(r.x0)
+    assert a.nfev == b.nfev == c.nfev
+    assert np.array_equal(a.x, b.x) and np.array_equal(a.x, c.x)
+    assert a.cost == b.cost == c.cost
+
+
+def test_device_cull_matches_host_filter_and_reference_mask():
+    from caliscope_b200 import filtering
+
+    g, rig = load_golden("session4_refine0.npz")
+    x = g["x_default"]
+    with make_problem(rig) as p:
+        rm, per_cam = p.rmse_px(x)
+        _, thr = filtering.percentile_thresholds(p, x, float(g["filt_percentile"]), want_err=False)
+        p2, keep = p.cull(x, thr, int(g["filt_min_per_camera"]))
+        with p2:
+            assert p2.n_obs == int(keep.sum())
+            r_f = p2.residuals(x)
+            rm_f = p2.overall_rmse_px(x)
+        r_all = p.residuals(x).reshape(-1, 2)
+        # min_per_camera floor: impossible thresholds, 7 observations per camera must survive
+        p3, keep3 = p.cull(x, np.full(rig.n_cams, -1.0), 7)
+        p3.close()
+    assert np.array_equal(keep, g["filt_keep"])  # the reference's own keep mask
+    assert np.array_equal(r_f.reshape(-1, 2), r_all[keep])  # compacted list keeps the caller's order
+    assert abs(rm - float(g["rmse_default"])) < 1e-8
+    assert abs(rm_f - float(g["filt_rmse_after"])) < 1e-8
+    e = O.reproj_errors_px(x, rig)
+    for c in range(rig.n_cams):
+        ec = np.sqrt(np.sum(e[rig.obs_cam == c] ** 2, axis=1))
+        assert abs(per_cam[c] - np.sqrt(np.mean(ec**2))) < 1e-9
+        assert keep3[rig.obs_cam == c].sum() == 7
+        assert np.array_equal(np.sort(ec)[:7], np.sort(ec[keep3[rig.obs_cam == c]]))
