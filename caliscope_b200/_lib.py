@@ -93,6 +93,9 @@ SYMBOLS = {
     "cb_ba_problem_create": (C.c_int, [C.POINTER(ProblemDesc), C.c_int, _P, C.POINTER(_P)]),
     "cb_ba_problem_destroy": (C.c_int, [_P]),
     "cb_ba_problem_n_params": (C.c_int64, [_P]),
+    "cb_ba_problem_set_constraints": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P]),
+    "cb_ba_problem_n_constraints": (C.c_int64, [_P]),
+    "cb_ba_constraint_rows": (C.c_int, [_P, _P, _P, _P, _P]),
     "cb_ba_solve": (C.c_int, [_P, C.POINTER(Options), _P, C.POINTER(Result), _P]),
     "cb_ba_residuals": (C.c_int, [_P, _P, _P, _P]),
     "cb_ba_jacobian_blocks": (C.c_int, [_P, _P, _P, _P, _P]),

@@ -78,11 +78,15 @@ def optimize(self, ftol: float = 1e-8, max_nfev: int | None = None, verbose: int
     from caliscope.core.capture_volume import _SCIPY_STATUS_REASONS, CaptureVolume, OptimizationStatus
     from caliscope.core.point_data import WorldPoints
 
-    if use_constraints and self.constraints is not None and self._build_constraint_arrays() is not None:
-        raise NotImplementedError(
-            "rigid-distance constraint rows are not implemented in the CUDA engine yet; call "
-            "optimize(use_constraints=False) or use seam S1 with install(fallback=...)"
-        )
+    constraints = None
+    if use_constraints and self.constraints is not None:
+        arrays = self._build_constraint_arrays()
+        if arrays is not None:  # capture_volume.py:373-383
+            groups_a, groups_b, distances, sigmas = arrays
+            focal = [cam.matrix[0, 0] for cam in self.camera_array.posed_cameras.values() if cam.matrix is not None]
+            f_median = float(np.median(focal))
+            constraints = (groups_a, groups_b, distances, (pixel_sigma / f_median) / sigmas)
+            logger.info(f"Adding {len(groups_a)} constraint rows (f_median={f_median:.0f}, pixel_sigma={pixel_sigma})")
     camera_indices, image_coords, image_to_world_indices, _ = ba_arrays(self)
     new_camera_array = deepcopy(self.camera_array)
     parameterization = BundleParameterization.from_camera_array(
@@ -93,7 +97,8 @@ def optimize(self, ftol: float = 1e-8, max_nfev: int | None = None, verbose: int
     logger.info(f"Beginning bundle adjustment on {len(image_coords)} observations")
     result = solver.solve_arrays(
         flags, const, parameterization.n_points, camera_indices, image_to_world_indices, image_coords, x0,
-        use_bounds=True, ftol=ftol, max_nfev=max_nfev, loss=loss, f_scale=f_scale, verbose=verbose,
+        use_bounds=True, constraints=constraints, ftol=ftol, max_nfev=max_nfev, loss=loss, f_scale=f_scale,
+        verbose=verbose,
     )  # fmt: skip
     termination_reason = _SCIPY_STATUS_REASONS.get(result.status, f"unknown_{result.status}")
     converged = result.status in (1, 2, 3, 4)

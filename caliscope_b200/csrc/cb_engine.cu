@@ -22,6 +22,7 @@
 
 #include "../../include/caliscope_b200.h"
 #include "cb_kernels.cuh"
+#include "cb_constraints.cuh"
 
 namespace {
 
@@ -196,6 +197,14 @@ struct CbBaProblem {
   // pcg launch configuration
   int pcg_cs = 1, pcg_rows = 0, pcg_mode = 0, pcg_cl = 1, pcg_npa = 0;
   size_t pcg_smem = 0;
+  // rigid-distance constraints (optional)
+  int n_c = 0, n_comp = 0, n_dim_max = 0, n_cblk = 0;
+  cb::ConstraintTables ct = {};
+  double *d_c_rs = nullptr, *d_c_dirw = nullptr, *d_compL = nullptr, *d_gpt = nullptr;
+  int* d_pt_comp = nullptr;
+  size_t comp_build_smem = 0, comp_back_smem = 0;
+  std::vector<int> h_ga, h_gb;
+  std::vector<double> h_cdist, h_cw;
   int red_slots = 64;
   size_t red_len() const { return (size_t)nP * nP + 3 * (size_t)nP + 1 + red_slots; }
 };
@@ -357,7 +366,10 @@ int linearize(CbBaProblem* p, const double* xc, const double* xp4, int loss, dou
   CB_LAUNCH((cb::cam_reduce_kernel<P>), p->n_cams, 64, 0, st, p->d_cam_chunk_start, p->d_partial, p->d_Upk, p->d_gc,
             p->d_camcost);
   static_assert(RT::NACC <= 64, "cam_reduce block too small");
-  CB_LAUNCH(cb::sum_kernel, 1, 256, 0, st, p->d_camcost, p->n_cams, p->d_costsum);
+  if (p->n_c)
+    CB_LAUNCH((cb::constraint_eval_kernel<false>), p->n_cblk, cb::CC_THREADS, 0, st, p->ct, xp4, loss, fscale, p->d_c_rs,
+              p->d_c_dirw, (double*)nullptr, p->d_camcost + p->n_cams);
+  CB_LAUNCH(cb::sum_kernel, 1, 256, 0, st, p->d_camcost, p->n_cams + p->n_cblk, p->d_costsum);
   CB_CUDA(cudaMemsetAsync(p->d_gmax, 0, sizeof(unsigned long long), st));
   (void)rj_ms;
   return CB_OK;
@@ -367,7 +379,7 @@ template <int P>
 int build_system(CbBaProblem* p, double lam, bool new_lin, const CbBaOptions* opt, cudaStream_t st) {
 #define CB_PT_BUILD(FUSED, DUPS)                                                                                  \
   CB_LAUNCH((cb::pt_build_kernel<P, FUSED, DUPS>), p->pt_blocks, cb::PT_WARPS * 32, 0, st, p->d_pt_start, p->d_pm_cam, \
-            p->d_pm_row, p->n_pts, p->d_jrows, p->d_V6, p->d_gp, p->d_Dp2, lam, p->d_Linv6, p->d_tvec, p->d_Zt,      \
+            p->d_pm_row, p->d_pt_comp, p->n_pts, p->d_jrows, p->d_V6, p->d_gp, p->d_Dp2, lam, p->d_Linv6, p->d_tvec, p->d_Zt,      \
             (size_t)p->LD, p->d_gmax)
   if (new_lin) {
     if (p->n_dups) CB_PT_BUILD(true, true); else CB_PT_BUILD(true, false);
@@ -375,6 +387,10 @@ int build_system(CbBaProblem* p, double lam, bool new_lin, const CbBaOptions* op
     if (p->n_dups) CB_PT_BUILD(false, true); else CB_PT_BUILD(false, false);
   }
 #undef CB_PT_BUILD
+  if (p->n_c)
+    CB_LAUNCH((cb::comp_build_kernel<P>), p->n_comp, cb::CC_THREADS, p->comp_build_smem, st, p->ct, p->d_pt_start,
+              p->d_pm_cam, p->d_pm_row, p->d_jrows, p->d_V6, p->d_gp, p->d_Dp2, p->d_gpt, p->d_c_rs, p->d_c_dirw, lam,
+              new_lin ? 1 : 0, p->n_cams, p->d_compL, p->d_tvec, p->d_Zt, (size_t)p->LD, p->d_gmax);
   CB_LAUNCH(cb::schur_syrk_kernel, p->n_items, cb::SY_THREADS, sizeof(cb::SyrkSmem), st, p->d_Zt, (size_t)p->LD,
             p->d_tvec, p->d_items, p->d_part, p->d_tpart);
   const size_t nfin = (size_t)p->nP * p->nP + p->nP + 1;
@@ -439,10 +455,15 @@ int solve_step(CbBaProblem* p, double lam, int cur, const CbBaOptions* opt, doub
   CB_LAUNCH(cb::cam_update_kernel, 1, 256, 0, st, p->nP, lam, p->d_xc[cur], p->d_dc, p->d_lo, p->d_hi,
             p->d_red + nn + p->nP, p->d_Dc2, p->d_active, p->d_xc[cur ^ 1], p->d_sc);
   // (reading the 320 MB of Jacobian rows instead of the 461 MB dense factor was measured: no faster)
+  const int bstride = p->pt_blocks + p->n_comp;
   CB_LAUNCH(cb::pt_backsub_kernel, p->pt_blocks, cb::PT_WARPS * 32, sizeof(double) * p->nP, st, p->n_pts, p->nP, lam,
-            p->d_Zt, (size_t)p->LD, p->d_dc, p->d_Linv6, p->d_tvec, p->d_gp, p->d_Dp2, p->d_xp4[cur],
-            p->d_xp4[cur ^ 1], dp_out, p->d_bpart);
-  CB_LAUNCH(cb::sum3_kernel, 3, 256, 0, st, p->d_bpart, p->pt_blocks, p->d_red2 + 1);
+            p->d_pt_comp, bstride, p->d_Zt, (size_t)p->LD, p->d_dc, p->d_Linv6, p->d_tvec, p->d_gp, p->d_Dp2,
+            p->d_xp4[cur], p->d_xp4[cur ^ 1], dp_out, p->d_bpart);
+  if (p->n_c)
+    CB_LAUNCH(cb::comp_backsub_kernel, p->n_comp, cb::CC_THREADS, p->comp_back_smem, st, p->ct, p->nP, lam, p->d_Zt,
+              (size_t)p->LD, p->d_dc, p->d_compL, p->d_tvec, p->d_gpt, p->d_Dp2, p->d_xp4[cur], p->d_xp4[cur ^ 1],
+              dp_out, p->d_bpart, bstride, p->pt_blocks);
+  CB_LAUNCH(cb::sum3_kernel, 3, 256, 0, st, p->d_bpart, bstride, p->d_red2 + 1);
   return CB_OK;
 }
 
@@ -450,7 +471,10 @@ template <int P>
 int trial_cost(CbBaProblem* p, int nxt, int loss, double fscale, const CbBaOptions* opt, cudaStream_t st) {
   CB_TRY(run_cam_prep<P>(p, p->d_xc[nxt], st));
   launch_resjac<P, 1>(p, p->d_xp4[nxt], loss, fscale, nullptr, st);
-  CB_LAUNCH(cb::sum_kernel, 1, 256, 0, st, p->d_partial, p->n_chunks, p->d_red2);
+  if (p->n_c)
+    CB_LAUNCH((cb::constraint_eval_kernel<true>), p->n_cblk, cb::CC_THREADS, 0, st, p->ct, p->d_xp4[nxt], loss, fscale,
+              (double*)nullptr, (double*)nullptr, (double*)nullptr, p->d_partial + p->n_chunks);
+  CB_LAUNCH(cb::sum_kernel, 1, 256, 0, st, p->d_partial, p->n_chunks + p->n_cblk, p->d_red2);
   if (opt && opt->allreduce) {
     if (opt->allreduce(opt->allreduce_user, p->d_red2, 4, (void*)st) != 0) {
       g_last_error = "all-reduce callback failed";
@@ -922,6 +946,7 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
   CB_TRY(palloc(p, &p->d_partial, (size_t)std::max(p->n_chunks, 1) * NACC));
   CB_TRY(palloc(p, &p->d_Upk, (size_t)p->n_cams * NU)); CB_TRY(palloc(p, &p->d_gc, p->nP));
   CB_TRY(palloc(p, &p->d_camcost, p->n_cams)); CB_TRY(palloc(p, &p->d_costsum, 4));
+  CB_TRY(palloc(p, &p->d_gpt, 3 * npts));
   CB_TRY(palloc(p, &p->d_V6, 6 * npts)); CB_TRY(palloc(p, &p->d_gp, 3 * npts)); CB_TRY(palloc(p, &p->d_Dp2, 3 * npts));
   CB_TRY(palloc(p, &p->d_Dc2, p->nP)); CB_TRY(palloc(p, &p->d_Linv6, 6 * npts));
   CB_TRY(palloc(p, &p->d_tvec, (size_t)p->K_pad));
@@ -980,6 +1005,10 @@ int cb_ba_solve(CbBaProblem* p, const CbBaOptions* opt, double* x_inout, CbBaRes
   if (opt->loss < 0 || opt->loss > CB_LOSS_ARCTAN) { g_last_error = "unknown loss id"; return CB_E_INVALID; }
   CB_CUDA(cudaSetDevice(p->device));
   cudaStream_t st = (cudaStream_t)stream;
+  if (p->n_c && opt->allreduce) {
+    g_last_error = "rigid-distance constraints are not supported with observation sharding yet (components would span ranks)";
+    return CB_E_UNSUPPORTED;
+  }
   return p->P == 6 ? lm_solve<6>(p, opt, x_inout, result, st) : lm_solve<9>(p, opt, x_inout, result, st);
 }
 
@@ -1151,6 +1180,153 @@ int cb_ba_error_order_stats(CbBaProblem* p, const double* x, double q_percent, d
   return CB_OK;
 }
 
+// Rigid-distance constraint rows (reprojection.py:112-117, 207-226; arrays as built by
+// CaptureVolume._build_constraint_arrays, capture_volume.py:446-516, with
+// weights = (pixel_sigma / f_median) / sigma, :377-381).  Host arrays; call once after problem_create.
+int cb_ba_problem_set_constraints(CbBaProblem* p, int64_t n_c, const int32_t* groups_a, const int32_t* groups_b,
+                                  const double* distances, const double* weights, void* stream) {
+  if (!p || n_c < 0 || (n_c > 0 && (!groups_a || !groups_b || !distances || !weights))) {
+    g_last_error = "cb_ba_problem_set_constraints: bad argument";
+    return CB_E_INVALID;
+  }
+  if (p->n_c) { g_last_error = "constraints already set on this problem"; return CB_E_INVALID; }
+  if (n_c == 0) return CB_OK;
+  CB_CUDA(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nc = (int)n_c, npts = p->n_pts;
+  for (long long i = 0; i < 4ll * nc; ++i)
+    if (groups_a[i] < 0 || groups_a[i] >= npts || groups_b[i] < 0 || groups_b[i] >= npts) {
+      g_last_error = "constraint group index out of range";
+      return CB_E_INVALID;
+    }
+  // connected components of the constraint graph (union-find over points)
+  std::vector<int> parent(npts);
+  for (int i = 0; i < npts; ++i) parent[i] = i;
+  auto find = [&](int a) { while (parent[a] != a) { parent[a] = parent[parent[a]]; a = parent[a]; } return a; };
+  std::vector<char> used(npts, 0);
+  for (int k = 0; k < nc; ++k) {
+    const int r0 = find(groups_a[4 * k]);
+    used[groups_a[4 * k]] = 1;
+    for (int q = 0; q < 4; ++q) {
+      used[groups_a[4 * k + q]] = 1; used[groups_b[4 * k + q]] = 1;
+      parent[find(groups_a[4 * k + q])] = r0;
+      parent[find(groups_b[4 * k + q])] = r0;
+    }
+  }
+  std::vector<int> comp_of_root(npts, -1), pt_comp(npts, -1), pt_lidx(npts, -1);
+  std::vector<std::vector<int>> comp_pts;
+  for (int j = 0; j < npts; ++j) {
+    if (!used[j]) continue;
+    const int r = find(j);
+    if (comp_of_root[r] < 0) { comp_of_root[r] = (int)comp_pts.size(); comp_pts.emplace_back(); }
+    const int c = comp_of_root[r];
+    pt_comp[j] = c;
+    pt_lidx[j] = (int)comp_pts[c].size();
+    comp_pts[c].push_back(j);
+  }
+  const int ncomp = (int)comp_pts.size();
+  std::vector<int> cps(ncomp + 1, 0), cpts, ccs(ncomp + 1, 0), ccons(nc);
+  std::vector<long long> loff(ncomp);
+  long long ltot = 0;
+  int ndmax = 0;
+  for (int c = 0; c < ncomp; ++c) {
+    cps[c] = (int)cpts.size();
+    cpts.insert(cpts.end(), comp_pts[c].begin(), comp_pts[c].end());
+    const long long n = 3ll * comp_pts[c].size();
+    loff[c] = ltot;
+    ltot += n * n;
+    ndmax = std::max(ndmax, (int)n);
+  }
+  cps[ncomp] = (int)cpts.size();
+  if (ndmax > 1200) {
+    g_last_error = "a rigid component couples more than 400 points; not supported by this build";
+    return CB_E_UNSUPPORTED;
+  }
+  std::vector<int> cnu(nc), cg((size_t)nc * 8, -1), cl((size_t)nc * 8, 0), ccomp(nc);
+  std::vector<double> ccoef((size_t)nc * 8, 0.0);
+  for (int k = 0; k < nc; ++k) {
+    int nu = 0;
+    for (int side = 0; side < 2; ++side)
+      for (int q = 0; q < 4; ++q) {
+        const int pt = side == 0 ? groups_a[4 * k + q] : groups_b[4 * k + q];
+        int u = 0;
+        for (; u < nu; ++u)
+          if (cg[(size_t)k * 8 + u] == pt) break;
+        if (u == nu) { cg[(size_t)k * 8 + u] = pt; cl[(size_t)k * 8 + u] = pt_lidx[pt]; ++nu; }
+        ccoef[(size_t)k * 8 + u] += side == 0 ? 0.25 : -0.25;
+      }
+    cnu[k] = nu;
+    ccomp[k] = pt_comp[groups_a[4 * k]];
+    ccs[ccomp[k] + 1]++;
+  }
+  for (int c = 0; c < ncomp; ++c) ccs[c + 1] += ccs[c];
+  {
+    std::vector<int> cur(ccs.begin(), ccs.end() - 1);
+    for (int k = 0; k < nc; ++k) ccons[cur[ccomp[k]]++] = k;  // ascending constraint id within a component
+  }
+  // upload
+  int *d_nu, *d_g, *d_l, *d_cps, *d_cpts, *d_ccs, *d_ccons;
+  double *d_coef, *d_dist, *d_w;
+  long long* d_loff;
+  CB_TRY(palloc(p, &d_nu, nc)); CB_TRY(palloc(p, &d_g, (size_t)nc * 8)); CB_TRY(palloc(p, &d_l, (size_t)nc * 8));
+  CB_TRY(palloc(p, &d_coef, (size_t)nc * 8)); CB_TRY(palloc(p, &d_dist, nc)); CB_TRY(palloc(p, &d_w, nc));
+  CB_TRY(palloc(p, &d_cps, ncomp + 1)); CB_TRY(palloc(p, &d_cpts, cpts.size())); CB_TRY(palloc(p, &d_ccs, ncomp + 1));
+  CB_TRY(palloc(p, &d_ccons, nc)); CB_TRY(palloc(p, &d_loff, ncomp)); CB_TRY(palloc(p, &p->d_pt_comp, npts));
+  CB_TRY(palloc(p, &p->d_c_rs, nc)); CB_TRY(palloc(p, &p->d_c_dirw, 3 * (size_t)nc));
+  CB_TRY(palloc(p, &p->d_compL, (size_t)ltot));
+#define CB_UP(dst, vec) CB_CUDA(cudaMemcpyAsync(dst, (vec).data(), sizeof((vec)[0]) * (vec).size(), cudaMemcpyHostToDevice, st))
+  CB_UP(d_nu, cnu); CB_UP(d_g, cg); CB_UP(d_l, cl); CB_UP(d_coef, ccoef); CB_UP(d_cps, cps); CB_UP(d_cpts, cpts);
+  CB_UP(d_ccs, ccs); CB_UP(d_ccons, ccons); CB_UP(d_loff, loff); CB_UP(p->d_pt_comp, pt_comp);
+#undef CB_UP
+  CB_CUDA(cudaMemcpyAsync(d_dist, distances, sizeof(double) * nc, cudaMemcpyHostToDevice, st));
+  CB_CUDA(cudaMemcpyAsync(d_w, weights, sizeof(double) * nc, cudaMemcpyHostToDevice, st));
+  p->n_cblk = cdiv(nc, cb::CC_THREADS);
+  // the cost / step partial-sum arrays grow by the constraint blocks / components
+  const int NACC = (p->P == 6) ? 28 : 55;
+  CB_TRY(palloc(p, &p->d_camcost, (size_t)p->n_cams + p->n_cblk));
+  CB_TRY(palloc(p, &p->d_partial, (size_t)std::max(p->n_chunks, 1) * NACC + p->n_cblk));
+  CB_TRY(palloc(p, &p->d_bpart, 3 * ((size_t)p->pt_blocks + ncomp)));
+  CB_CUDA(cudaStreamSynchronize(st));
+  p->ct.n_c = nc; p->ct.n_comp = ncomp; p->ct.n_dim_max = ndmax;
+  p->ct.c_nu = d_nu; p->ct.c_gidx = d_g; p->ct.c_lidx = d_l; p->ct.c_coef = d_coef; p->ct.c_dist = d_dist; p->ct.c_w = d_w;
+  p->ct.comp_pt_start = d_cps; p->ct.comp_pts = d_cpts; p->ct.comp_c_start = d_ccs; p->ct.comp_cons = d_ccons;
+  p->ct.comp_L_off = d_loff; p->ct.pt_comp = p->d_pt_comp;
+  p->n_c = nc; p->n_comp = ncomp; p->n_dim_max = ndmax;
+  const int esm = std::min(ndmax, cb::CC_SMEM_DIM);
+  p->comp_build_smem = sizeof(double) * ((size_t)ndmax * (1 + p->P) + (size_t)esm * esm) + 4 * ((size_t)(p->n_cams + 31) / 32 + 4);
+  p->comp_back_smem = sizeof(double) * ((size_t)p->nP + ndmax);
+  if (p->P == 6)
+    CB_CUDA(cudaFuncSetAttribute(cb::comp_build_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->comp_build_smem));
+  else
+    CB_CUDA(cudaFuncSetAttribute(cb::comp_build_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->comp_build_smem));
+  CB_CUDA(cudaFuncSetAttribute(cb::comp_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->comp_back_smem));
+  p->h_ga.assign(groups_a, groups_a + 4 * (size_t)nc); p->h_gb.assign(groups_b, groups_b + 4 * (size_t)nc);
+  p->h_cdist.assign(distances, distances + nc); p->h_cw.assign(weights, weights + nc);
+  return CB_OK;
+}
+
+int64_t cb_ba_problem_n_constraints(const CbBaProblem* p) { return p ? p->n_c : -1; }
+
+// Constraint rows at x: r (n_c, == the tail of joint_residuals) and dir (n_c x 3) = w * unit(mean(P[ga]) - mean(P[gb]));
+// the Jacobian entry of member point q of group a (b) is +(-) dir / 4, summed over repeats (reprojection.py:207-226).
+int cb_ba_constraint_rows(CbBaProblem* p, const double* x, double* r_out, double* dir_out, void* stream) {
+  if (!p || !x || !r_out) { g_last_error = "cb_ba_constraint_rows: null argument"; return CB_E_INVALID; }
+  if (!p->n_c) return CB_OK;
+  CB_CUDA(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  CB_TRY(upload_x(p, x, st));
+  double *d_r, *d_rs, *d_dir;
+  CB_TRY(dalloc(&d_r, p->n_c)); CB_TRY(dalloc(&d_rs, p->n_c)); CB_TRY(dalloc(&d_dir, 3 * (size_t)p->n_c));
+  CB_LAUNCH((cb::constraint_eval_kernel<false>), p->n_cblk, cb::CC_THREADS, 0, st, p->ct, p->d_xp4[0], 0, 1.0, d_rs, d_dir,
+            d_r, (double*)nullptr);
+  cudaMemcpyAsync(r_out, d_r, sizeof(double) * p->n_c, cudaMemcpyDeviceToHost, st);
+  if (dir_out) cudaMemcpyAsync(dir_out, d_dir, sizeof(double) * 3 * (size_t)p->n_c, cudaMemcpyDeviceToHost, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  cached_free(d_r); cached_free(d_rs); cached_free(d_dir);
+  CB_CUDA(e);
+  return CB_OK;
+}
+
 // Overall and per-camera RMS pixel error (reprojection_report's overall_rmse / by_camera,
 // capture_volume.py:197-202), reduced on the device.
 int cb_ba_rmse_px(CbBaProblem* p, const double* x, double* overall, double* per_camera, void* stream) {
@@ -1258,7 +1434,16 @@ int cb_ba_cull(CbBaProblem* p, const double* x, const double* thresholds, int32_
       cb_ba_problem_destroy(q);
       g_last_error = keep;
     } else {
-      *out = q;
+      if (p->n_c)
+        rc = cb_ba_problem_set_constraints(q, p->n_c, p->h_ga.data(), p->h_gb.data(), p->h_cdist.data(), p->h_cw.data(),
+                                           stream);
+      if (rc != CB_OK) {
+        std::string keep = g_last_error;
+        cb_ba_problem_destroy(q);
+        g_last_error = keep;
+      } else {
+        *out = q;
+      }
     }
   }
   if (n_kept) *n_kept = nsel;

@@ -409,7 +409,7 @@ __device__ __forceinline__ void pt_build_run(const double* __restrict__ jrows, c
 template <int P, bool FUSED, bool DUPS>
 __global__ void __launch_bounds__(PT_WARPS * 32)
 pt_build_kernel(const int* __restrict__ pt_start, const int* __restrict__ pm_cam,
-                const int* __restrict__ pm_row, int n_pts,
+                const int* __restrict__ pm_row, const int* __restrict__ pt_comp, int n_pts,
                 const double* __restrict__ jrows, double* __restrict__ V6, double* __restrict__ gp,
                 double* __restrict__ Dp2, double lam, double* __restrict__ Linv6, double* __restrict__ tvec,
                 double* __restrict__ Zt, size_t LD, unsigned long long* __restrict__ gmax_bits) {
@@ -421,6 +421,9 @@ pt_build_kernel(const int* __restrict__ pt_start, const int* __restrict__ pm_cam
   if (j < n_pts) {
     const int s = pt_start[j], e = pt_start[j + 1];
     double v[9], D[3];
+    // points tied by rigid-distance constraints are eliminated per component (comp_build_kernel);
+    // here they only get their observation sums V, gp
+    const bool in_comp = pt_comp != nullptr && pt_comp[j] >= 0;
     // first batch of rows: indices loaded once, used by both phases
     const int pos0 = s + lane;
     int row0 = 0, cam0 = -1, prev0 = -2;
@@ -459,7 +462,7 @@ pt_build_kernel(const int* __restrict__ pt_start, const int* __restrict__ pm_cam
 #pragma unroll
         for (int k = 0; k < 3; ++k) gp[(size_t)j * 3 + k] = v[6 + k];
         Dp2[(size_t)j * 3] = D[0]; Dp2[(size_t)j * 3 + 1] = D[1]; Dp2[(size_t)j * 3 + 2] = D[2];
-        gm = fmax(fabs(v[6]), fmax(fabs(v[7]), fabs(v[8])));
+        if (!in_comp) gm = fmax(fabs(v[6]), fmax(fabs(v[7]), fabs(v[8])));
       }
     } else {
 #pragma unroll
@@ -469,14 +472,14 @@ pt_build_kernel(const int* __restrict__ pt_start, const int* __restrict__ pm_cam
     }
     double Li[6];
     chol3_inv(v, D, lam, Li);
-    if (lane == 0) {
+    if (lane == 0 && !in_comp) {
 #pragma unroll
       for (int k = 0; k < 6; ++k) Linv6[(size_t)j * 6 + k] = Li[k];
       tvec[3 * (size_t)j + 0] = Li[0] * v[6];
       tvec[3 * (size_t)j + 1] = Li[1] * v[6] + Li[2] * v[7];
       tvec[3 * (size_t)j + 2] = Li[3] * v[6] + Li[4] * v[7] + Li[5] * v[8];
     }
-    for (int pos = pos0; pos < e; pos += 32) {
+    for (int pos = pos0; pos < e && !in_comp; pos += 32) {
       const int cam = (pos == pos0) ? cam0 : pm_cam[pos];
       const int prev = (pos == pos0) ? prev0 : pm_cam[pos - 1];
       if (prev == cam) continue;  // not the first of its (point, camera) run
@@ -1109,7 +1112,8 @@ __global__ void cam_update_kernel(int nP, double lam, const double* __restrict__
 
 // point back-substitution: dp = -Linv^T (t + Zt_rows dc), one warp per point; block partial sums
 __global__ void __launch_bounds__(PT_WARPS * 32)
-pt_backsub_kernel(int n_pts, int nP, double lam, const double* __restrict__ Zt, size_t LD,
+pt_backsub_kernel(int n_pts, int nP, double lam, const int* __restrict__ pt_comp, int bpart_stride,
+                  const double* __restrict__ Zt, size_t LD,
                   const double* __restrict__ dc, const double* __restrict__ Linv6, const double* __restrict__ tvec,
                   const double* __restrict__ gp, const double* __restrict__ Dp2, const double* __restrict__ xp4,
                   double* __restrict__ xp4_new, double* __restrict__ dp_out, double* __restrict__ bpart) {
@@ -1120,7 +1124,7 @@ pt_backsub_kernel(int n_pts, int nP, double lam, const double* __restrict__ Zt, 
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int j = blockIdx.x * PT_WARPS + wid;
   double pred = 0.0, st2 = 0.0, x2 = 0.0;
-  if (j < n_pts) {
+  if (j < n_pts && !(pt_comp != nullptr && pt_comp[j] >= 0)) {
     const double* z = Zt + 3 * (size_t)j * LD;
     double u0 = 0.0, u1 = 0.0, u2 = 0.0;
     for (int k = lane; k < nP; k += 32) {
@@ -1154,8 +1158,8 @@ pt_backsub_kernel(int n_pts, int nP, double lam, const double* __restrict__ Zt, 
     double a = 0, b = 0, c = 0;
     for (int w = 0; w < PT_WARPS; ++w) { a += wsum[0][w]; b += wsum[1][w]; c += wsum[2][w]; }
     bpart[blockIdx.x] = a;
-    bpart[gridDim.x + blockIdx.x] = b;
-    bpart[2 * (size_t)gridDim.x + blockIdx.x] = c;
+    bpart[bpart_stride + blockIdx.x] = b;
+    bpart[2 * (size_t)bpart_stride + blockIdx.x] = c;
   }
 }
 

@@ -75,7 +75,10 @@ class BAProblem:
     objects exposing ``data_ptr()`` on ``device`` (used in place, no copy).
     """
 
-    def __init__(self, cam_flags, cam_const, n_pts, obs_cam, obs_pt, obs_xy, *, device: int = 0, stream: int = 0):
+    def __init__(self, cam_flags, cam_const, n_pts, obs_cam, obs_pt, obs_xy, *, constraints=None, device: int = 0,
+                 stream: int = 0):
+        """``constraints``: optional ``(groups_a (n_c,4), groups_b (n_c,4), distances (n_c,), weights (n_c,))`` --
+        the rigid-distance rows of capture_volume.py:373-383 / reprojection.py:112-117."""
         lib = L.load()
         self._lib = lib
         self._h = None
@@ -112,6 +115,23 @@ class BAProblem:
         L.check(lib.cb_ba_problem_create(C.byref(desc), self.device, C.c_void_p(stream), C.byref(h)), "problem_create")
         self._h = h
         self.cam_stride = int(lib.cb_ba_cam_stride(h))
+        self.n_constraints = 0
+        if constraints is not None and constraints[0] is not None and len(constraints[0]) > 0:
+            ga = np.ascontiguousarray(constraints[0], dtype=np.int32).reshape(-1, 4)
+            gb = np.ascontiguousarray(constraints[1], dtype=np.int32).reshape(-1, 4)
+            dist = np.ascontiguousarray(constraints[2], dtype=np.float64)
+            w = np.ascontiguousarray(constraints[3], dtype=np.float64)
+            if not (len(ga) == len(gb) == len(dist) == len(w)):
+                self.close()
+                raise ValueError("constraint arrays must have the same length")
+            try:
+                L.check(lib.cb_ba_problem_set_constraints(h, len(ga), _ptr(ga), _ptr(gb), _ptr(dist), _ptr(w),
+                                                          C.c_void_p(stream)), "set_constraints")  # fmt: skip
+            except Exception:
+                self.close()
+                raise
+            self.n_constraints = len(ga)
+            self.constraints = (ga, gb, dist, w)
 
     # -- lifetime -----------------------------------------------------------------------------
     def close(self) -> None:
@@ -139,10 +159,22 @@ class BAProblem:
 
     # -- evaluation ---------------------------------------------------------------------------
     def residuals(self, x, stream: int = 0) -> np.ndarray:
+        """== joint_residuals: 2*n_obs reprojection rows, then the n_c constraint rows."""
         x = self._x(x)
-        out = np.empty(2 * self.n_obs)
+        out = np.empty(2 * self.n_obs + self.n_constraints)
         L.check(self._lib.cb_ba_residuals(self._h, _ptr(x), _ptr(out), C.c_void_p(stream)), "residuals")
+        if self.n_constraints:
+            tail = out[2 * self.n_obs :]
+            L.check(self._lib.cb_ba_constraint_rows(self._h, _ptr(x), _ptr(tail), None, C.c_void_p(stream)), "constraint_rows")
         return out
+
+    def constraint_rows(self, x, stream: int = 0) -> tuple[np.ndarray, np.ndarray]:
+        """(r (n_c,), dir (n_c,3)): constraint residuals and weight * unit direction (Jacobian entries are +-dir/4)."""
+        x = self._x(x)
+        r = np.empty(self.n_constraints)
+        d = np.empty((self.n_constraints, 3))
+        L.check(self._lib.cb_ba_constraint_rows(self._h, _ptr(x), _ptr(r), _ptr(d), C.c_void_p(stream)), "constraint_rows")
+        return r, d
 
     def jacobian_blocks(self, x, stream: int = 0) -> tuple[np.ndarray, np.ndarray]:
         x = self._x(x)
@@ -195,6 +227,9 @@ class BAProblem:
         new.n_cams, new.n_pts, new.device, new.n_obs = self.n_cams, self.n_pts, self.device, int(n_kept.value)
         new.cam_offsets, new.n_camera_params, new.n_params = self.cam_offsets, self.n_camera_params, self.n_params
         new.cam_stride = self.cam_stride
+        new.n_constraints = self.n_constraints
+        if self.n_constraints:
+            new.constraints = self.constraints
         return new, (mask.astype(bool) if want_mask else None)
 
     def normal_equations(self, x, lam: float, loss: str = "linear", f_scale: float = 1.0, stream: int = 0) -> dict:

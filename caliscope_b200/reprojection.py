@@ -3,8 +3,8 @@
 Same function names and signatures (``project_points`` :18-32, ``reprojection_errors`` :35-72,
 ``joint_residuals`` :75-119, ``joint_jacobian`` :128-234); every number comes from the CUDA
 engine through the C ABI -- there is no NumPy/OpenCV computation path here.
-Distance-constraint rows (reprojection.py:112-117, 207-226) are not implemented on the GPU yet
-and raise ``NotImplementedError``.
+Distance-constraint rows (reprojection.py:112-117, 207-226) are evaluated on the GPU too
+(``cb_ba_constraint_rows``); only the +-1/4 sparse pattern is assembled on the host.
 """
 from __future__ import annotations
 
@@ -15,19 +15,20 @@ from .problem import BAProblem, blocks_to_arrays
 _CACHE: dict = {"key": None, "problem": None}
 
 
-def problem_for(parameterization, camera_indices, image_coords, obj_indices, *, device: int = 0) -> BAProblem:
+def problem_for(parameterization, camera_indices, image_coords, obj_indices, constraints=None, *, device: int = 0) -> BAProblem:
     """Device problem for one ``args`` tuple; cached on array identity so scipy-style repeated
     ``fun(x)`` / ``jac(x)`` calls (e.g. finite-difference tests) re-use the uploaded observation list."""
-    key = (id(parameterization), id(camera_indices), id(image_coords), id(obj_indices), len(camera_indices), device)
+    cid = id(constraints[0]) if constraints is not None and constraints[0] is not None else 0
+    key = (id(parameterization), id(camera_indices), id(image_coords), id(obj_indices), len(camera_indices), cid, device)
     if _CACHE["key"] == key and _CACHE["problem"] is not None:
         return _CACHE["problem"]
     if _CACHE["problem"] is not None:
         _CACHE["problem"].close()
     flags, const = blocks_to_arrays(parameterization.blocks)
     prob = BAProblem(flags, const, parameterization.n_points, np.asarray(camera_indices), np.asarray(obj_indices),
-                     np.asarray(image_coords, dtype=np.float64), device=device)  # fmt: skip
+                     np.asarray(image_coords, dtype=np.float64), constraints=constraints, device=device)  # fmt: skip
     # keep the key objects alive so their ids cannot be recycled while the entry is cached
-    _CACHE.update(key=key, problem=prob, refs=(parameterization, camera_indices, image_coords, obj_indices))
+    _CACHE.update(key=key, problem=prob, refs=(parameterization, camera_indices, image_coords, obj_indices, constraints))
     return prob
 
 
@@ -37,11 +38,10 @@ def clear_cache() -> None:
     _CACHE.update(key=None, problem=None, refs=None)
 
 
-def _no_constraints(groups_a) -> None:
-    if groups_a is not None and len(groups_a) > 0:
-        raise NotImplementedError(
-            "rigid-distance constraint rows (reprojection.py:112-117) are not implemented in the CUDA engine yet"
-        )
+def _pack_constraints(ga, gb, dist, w):
+    if ga is None or len(ga) == 0:
+        return None
+    return (ga, gb, dist, w)
 
 
 def project_points(world, rvec, tvec, K, dist, fisheye: bool) -> np.ndarray:
@@ -79,8 +79,8 @@ def reprojection_errors(camera_array, camera_indices, image_coords, world_coords
 
 def joint_residuals(params, parameterization, camera_indices, image_coords, obj_indices, constraint_groups_a=None,
                     constraint_groups_b=None, constraint_distances=None, constraint_weights=None) -> np.ndarray:  # fmt: skip
-    _no_constraints(constraint_groups_a)
-    return problem_for(parameterization, camera_indices, image_coords, obj_indices).residuals(params)
+    cons = _pack_constraints(constraint_groups_a, constraint_groups_b, constraint_distances, constraint_weights)
+    return problem_for(parameterization, camera_indices, image_coords, obj_indices, cons).residuals(params)
 
 
 def joint_jacobian(params, parameterization, camera_indices, image_coords, obj_indices, constraint_groups_a=None,
@@ -88,8 +88,8 @@ def joint_jacobian(params, parameterization, camera_indices, image_coords, obj_i
     """CSR matrix with the reference's row/column layout, assembled from the engine's dense blocks."""
     from scipy.sparse import csr_matrix
 
-    _no_constraints(constraint_groups_a)
-    prob = problem_for(parameterization, camera_indices, image_coords, obj_indices)
+    cons = _pack_constraints(constraint_groups_a, constraint_groups_b, constraint_distances, constraint_weights)
+    prob = problem_for(parameterization, camera_indices, image_coords, obj_indices, cons)
     Jc, Jp = prob.jacobian_blocks(params)
     cam = np.asarray(camera_indices, dtype=np.int64)
     pt = np.asarray(obj_indices, dtype=np.int64)
@@ -108,4 +108,21 @@ def joint_jacobian(params, parameterization, camera_indices, image_coords, obj_i
             pos = indptr[2 * sel + half][:, None] + np.arange(w + 3)[None]
             data[pos] = vals[:, half, :]
             indices[pos] = cols
-    return csr_matrix((data, indices, indptr), shape=(2 * len(cam), prob.n_params))
+    J = csr_matrix((data, indices, indptr), shape=(2 * len(cam), prob.n_params))
+    if cons is None:
+        return J
+    # constraint rows: +-1/4 of (weight * unit direction) per group column, repeats summed (reprojection.py:207-226)
+    from scipy.sparse import coo_matrix, vstack
+
+    _, d = prob.constraint_rows(params)
+    n_c = len(d)
+    rows, cols, vals = [], [], []
+    for groups, sign in ((np.asarray(cons[0]), 0.25), (np.asarray(cons[1]), -0.25)):
+        for q in range(4):
+            base = ncp + 3 * groups[:, q].astype(np.int64)
+            for k in range(3):
+                rows.append(np.arange(n_c))
+                cols.append(base + k)
+                vals.append(sign * d[:, k])
+    Cm = coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n_c, prob.n_params))
+    return vstack([J, Cm.tocsr()]).tocsr()

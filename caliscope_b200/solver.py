@@ -7,8 +7,9 @@
 
 ``least_squares`` below has that signature.  When ``fun`` is a ``joint_residuals`` (the reference's or
 this package's) it never calls ``fun``/``jac``: it hands ``args`` to the CUDA engine and returns an
-object with the fields the reference reads (``x``, ``status``, ``nfev``, ``cost``).  Anything else is
-not this path and raises (or is delegated to the callable given to ``install(fallback=...)``).
+object with the fields the reference reads (``x``, ``status``, ``nfev``, ``cost``), rigid-distance
+constraint rows included.  Anything else is not this path and raises (or is delegated to the callable
+given to ``install(fallback=...)``).
 """
 from __future__ import annotations
 
@@ -35,9 +36,10 @@ def is_bundle_adjustment_call(fun: Any, args: tuple) -> bool:
 
 
 def solve_arrays(cam_flags, cam_const, n_pts, camera_indices, obj_indices, image_coords, x0, *, use_bounds=True,
-                 device: int = 0, **kw) -> SolveResult:  # fmt: skip
-    """Array-level entry: build the device problem, solve, free it."""
-    with BAProblem(cam_flags, cam_const, n_pts, camera_indices, obj_indices, image_coords, device=device) as prob:
+                 constraints=None, device: int = 0, **kw) -> SolveResult:  # fmt: skip
+    """Array-level entry: build the device problem (optionally with rigid-distance rows), solve, free it."""
+    with BAProblem(cam_flags, cam_const, n_pts, camera_indices, obj_indices, image_coords, constraints=constraints,
+                   device=device) as prob:  # fmt: skip
         return prob.solve(x0, use_bounds=use_bounds, **kw)
 
 
@@ -52,15 +54,9 @@ def least_squares(fun, x0, jac="2-point", bounds=(-np.inf, np.inf), method="trf"
         raise NotImplementedError("caliscope_b200.least_squares only replaces the bundle-adjustment call "
                                   "(fun=joint_residuals, args=(parameterization, camera_indices, ...))")  # fmt: skip
     par, camera_indices, image_coords, obj_indices = args[:4]
-    groups_a = args[4] if len(args) > 4 else None
-    if groups_a is not None and len(groups_a) > 0:
-        if _fallback is not None:
-            logger.info("distance-constraint rows present: delegating this solve to the fallback solver")
-            return _fallback(fun, x0, jac=jac, bounds=bounds, method=method, ftol=ftol, xtol=xtol, gtol=gtol,
-                             x_scale=x_scale if x_scale is not None else 1.0, loss=loss, f_scale=f_scale,
-                             max_nfev=max_nfev, verbose=verbose, args=args, kwargs=kwargs or {})  # fmt: skip
-        raise NotImplementedError("rigid-distance constraint rows are not implemented in the CUDA engine yet; "
-                                  "call optimize(use_constraints=False) or install(fallback=scipy's least_squares)")  # fmt: skip
+    constraints = None
+    if len(args) >= 8 and args[4] is not None and len(args[4]) > 0:
+        constraints = (args[4], args[5], args[6], args[7])
     if method != "trf":
         raise ValueError("caliscope_b200.least_squares replaces method='trf' only")
     flags, const = blocks_to_arrays(par.blocks)
@@ -68,7 +64,7 @@ def least_squares(fun, x0, jac="2-point", bounds=(-np.inf, np.inf), method="trf"
     use_bounds = bool(np.any(np.isfinite(np.atleast_1d(lo))) or np.any(np.isfinite(np.atleast_1d(hi))))
     res = solve_arrays(flags, const, par.n_points, np.asarray(camera_indices), np.asarray(obj_indices),
                        np.asarray(image_coords, dtype=np.float64), np.asarray(x0, dtype=np.float64),
-                       use_bounds=use_bounds, ftol=ftol if ftol is not None else 0.0, xtol=xtol if xtol is not None else 0.0,
+                       use_bounds=use_bounds, constraints=constraints, ftol=ftol if ftol is not None else 0.0, xtol=xtol if xtol is not None else 0.0,
                        gtol=gtol if gtol is not None else 0.0, max_nfev=max_nfev, loss=loss, f_scale=f_scale,
                        verbose=2 if verbose >= 2 else int(verbose))  # fmt: skip
     return res

@@ -133,6 +133,18 @@ int cb_ba_problem_create(const CbBaProblemDesc* desc, int device, void* stream, 
 int cb_ba_problem_destroy(CbBaProblem* p);
 int64_t cb_ba_problem_n_params(const CbBaProblem* p);
 
+/* Rigid-distance constraint rows (reprojection.py:112-117 and :207-226): groups_a / groups_b are n_c x 4 world-point
+ * row indices, distances and weights n_c doubles -- the arrays CaptureVolume._build_constraint_arrays produces
+ * (capture_volume.py:446-516) with weights = (pixel_sigma / f_median) / sigma (:377-381).  Host pointers, copied.
+ * Call at most once, after cb_ba_problem_create; single-GPU solves only in this build. */
+int cb_ba_problem_set_constraints(CbBaProblem* p, int64_t n_c, const int32_t* groups_a, const int32_t* groups_b,
+                                  const double* distances, const double* weights, void* stream);
+int64_t cb_ba_problem_n_constraints(const CbBaProblem* p);
+
+/* Constraint rows at x: r_out (n_c) == the tail of joint_residuals; dir_out (n_c x 3, nullable) = weight * unit vector
+ * between the two endpoint means: the Jacobian entry of a group-a (group-b) member is +(-) dir / 4, repeats summed. */
+int cb_ba_constraint_rows(CbBaProblem* p, const double* x, double* r_out, double* dir_out, void* stream);
+
 /* Replaces least_squares(joint_residuals, x0, jac=joint_jacobian, method="trf", ...)
  * (capture_volume.py:387-411).  x_inout: host, n_params doubles, overwritten with result.x. */
 int cb_ba_solve(CbBaProblem* p, const CbBaOptions* opt, double* x_inout, CbBaResult* result, void* stream);

@@ -224,3 +224,86 @@ def lm_solve(
             status = term
             break
     return dict(x=x, cost=lin.cost, status=status, nfev=nfev, njev=njev, nit=nit, history=history)
+
+
+def lm_solve_dense(
+    rig: O.Rig,
+    x0: np.ndarray,
+    *,
+    ftol: float = 1e-8,
+    xtol: float = 1e-8,
+    gtol: float = 1e-8,
+    max_nfev: int | None = None,
+    loss: str = "linear",
+    f_scale: float = 1.0,
+    lam0: float = 1e-4,
+    verbose: int = 0,
+):
+    """The same damped Gauss-Newton iteration on the FULL dense normal equations, constraint rows included
+    (any point-point coupling is handled by brute force).  Small problems only; used to check the
+    component-wise elimination of the CUDA engine when rigid-distance rows are present."""
+    x = np.asarray(x0, dtype=np.float64).copy()
+    n = len(x)
+    lo, hi = rig.bounds()
+    if max_nfev is None:
+        max_nfev = 100 * n
+
+    def lin(xx):
+        f = O.residuals(xx, rig)
+        J = O.jacobian(xx, rig).toarray()
+        cost = O.robust_cost(f, loss, f_scale)
+        js, fs = O.robust_row_scales(f, loss, f_scale)
+        Js = J * js[:, None]
+        return cost, Js.T @ Js, Js.T @ fs
+
+    cost, H, g = lin(x)
+    nfev = njev = 1
+    lam, nu = lam0, 2.0
+    D = np.zeros(n)
+    status, nit = 0, 0
+    while True:
+        D = np.maximum(D, np.diag(H))
+        De = np.where(D > 0, D, 1.0)
+        gnorm = np.abs(g).max()
+        if gnorm < gtol:
+            status = 1
+            break
+        if nfev >= max_nfev:
+            break
+        nit += 1
+        while True:
+            d = np.linalg.solve(H + lam * np.diag(De), -g)
+            xn = np.clip(x + d, lo, hi)
+            de = xn - x
+            pred = 0.5 * np.sum(de * (lam * De * de - g))
+            fn = O.residuals(xn, rig)
+            nfev += 1
+            cn = O.robust_cost(fn, loss, f_scale) if np.all(np.isfinite(fn)) else np.inf
+            actual = cost - cn
+            ratio = actual / pred if pred > 0 else -1.0
+            sn = np.linalg.norm(de)
+            ft = actual < ftol * cost and ratio > 0.25
+            xt = sn < xtol * (xtol + np.linalg.norm(x))
+            term = 4 if (ft and xt) else 2 if ft else 3 if xt else 0
+            if verbose:
+                print(f"it {nit:3d} nfev {nfev:3d} cost {cost:.15e} -> {cn:.15e} ratio {ratio:+.3f} lam {lam:.2e} |dx| {sn:.2e}")
+            if actual > 0:
+                lam = max(lam * max(1.0 / 3.0, 1 - (2 * ratio - 1) ** 3), 1e-15)
+                nu = 2.0
+                break
+            lam = min(lam * nu, 1e12)
+            nu *= 2
+            if term or nfev >= max_nfev:
+                break
+        if actual > 0:
+            x = xn
+            if term:
+                cost = cn
+                status = term
+                break
+            cost, H, g = lin(x)
+            njev += 1
+        if term:
+            status = term
+            break
+    return dict(x=x, cost=cost, status=status, nfev=nfev, njev=njev, nit=nit)

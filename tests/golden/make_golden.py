@@ -133,6 +133,45 @@ def solve_case(cv: CaptureVolume, refine: bool, loss="linear", f_scale=1.0, tigh
     return out
 
 
+def constraint_groups(cv: CaptureVolume, pixel_sigma: float = 1.0):
+    """Exactly what optimize() builds (capture_volume.py:373-383)."""
+    arrays = cv._build_constraint_arrays()
+    assert arrays is not None
+    ga, gb, dist, sig = arrays
+    f_median = float(np.median([c.matrix[0, 0] for c in cv.camera_array.posed_cameras.values()]))
+    return ga, gb, dist, (pixel_sigma / f_median) / sig
+
+
+def aruco_constraint_volume():
+    """tests/synthetic/test_rigid_constraints.py:32-58 plus a second mobile marker linked by a centre distance."""
+    from caliscope.core.aruco_marker import ArucoMarker, ArucoMarkerSet, DistanceLink
+    from caliscope.synthetic.camera_synthesizer import CameraSynthesizer
+    from caliscope.synthetic.scene_factories import aruco_scene
+    from caliscope.synthetic.se3_pose import SE3Pose
+    from caliscope.synthetic.trajectory import Trajectory
+
+    camera_array = CameraSynthesizer().add_ring(n=4, radius=2.0, height=0.5).build()
+    markers = {0: ArucoMarker(0, 0.1), 1: ArucoMarker(1, 0.1, static=True)}
+    marker_set = ArucoMarkerSet(dictionary=cv2.aruco.DICT_4X4_50, markers=markers)
+    static_pose = SE3Pose.from_axis_angle(axis=np.array([0.0, 0.0, 1.0]), angle_rad=0.0, translation=np.array([0.3, -0.2, 0.0]))
+    trajectories = {0: Trajectory.orbital(n_frames=20, radius=0.5), 1: Trajectory.stationary(n_frames=20, pose=static_pose)}
+    scene, constraints = aruco_scene(marker_set=marker_set, trajectories=trajectories, camera_array=camera_array,
+                                     pixel_noise_sigma=0.5)  # fmt: skip
+    return CaptureVolume.bootstrap(scene.image_points_noisy, scene.intrinsics_only_cameras(), constraints=constraints)
+
+
+def board_truss_volume():
+    """A 5x7 planar grid (the synthetic charuco stand-in) with the reference's truss + brace constraints."""
+    from caliscope.core.constraints import ConstraintSet
+    from caliscope.synthetic.scene_factories import default_ring_scene
+
+    ring = default_ring_scene(pixel_noise_sigma=0.5, random_seed=42)
+    obj = ring.objects[0].calibration_object
+    truss = ConstraintSet._truss_distance_constraints(np.asarray(obj.points), 0.05, 0.002)
+    cs = ConstraintSet(distances=truss, static_object_ids=frozenset())
+    return CaptureVolume.bootstrap(ring.image_points_noisy, ring.intrinsics_only_cameras(), constraints=cs)
+
+
 def filter_case(cv_opt: CaptureVolume, percentile: float, min_per_camera: int = 10):
     """Keep-mask of filter_by_percentile_error (capture_volume.py:607-646,709-753) in
     matched-observation order, with the inputs it was computed from."""
@@ -286,6 +325,17 @@ def main() -> None:
     )
     g = solve_case(cvs, False, groups=groups, tight=False)
     np.savez_compressed(out_dir / "small_pinhole_constraints.npz", **g)
+
+    for name, vol in (("aruco_constraints", aruco_constraint_volume()), ("board_truss_constraints", board_truss_volume())):
+        for refine in (False, True):
+            g = solve_case(vol, refine, groups=constraint_groups(vol), tight=True)
+            opt = vol.optimize(refine_intrinsics=refine)
+            assert abs(opt.optimization_status.final_cost - g["cost_default"]) < 1e-12 * g["cost_default"]
+            g["rigidity_rmse_mm_before"] = vol.rigidity_report().rmse_mm
+            g["rigidity_rmse_mm_after"] = opt.rigidity_report().rmse_mm
+            np.savez_compressed(out_dir / f"{name}_refine{int(refine)}.npz", **g)
+            print(name, refine, "n_c", len(g["groups_a"]), "obs", len(g["obs_cam"]), "pts", int(g["n_pts"]), "rmse",
+                  g["rmse0"], g["rmse_default"], g["rmse_tight"], "nfev", g["nfev_default"], "cost", g["cost_default"], g["cost_tight"])  # fmt: skip
 
     np.savez_compressed(out_dir / "mixed_fisheye.npz", **mixed_fisheye_case())
     np.savez_compressed(out_dir / "projection.npz", **projection_case())

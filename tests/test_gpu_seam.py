@@ -59,17 +59,39 @@ def test_project_points_and_reprojection_errors_mirror(golden_dir):
         R.project_points(p["pts"], p["rvec"], p["tvec"], p["K"], p["d5"], True)
 
 
-def test_constraint_rows_are_refused_not_silently_dropped():
+@pytest.mark.parametrize("name", ["small_pinhole_constraints.npz", "aruco_constraints_refine1.npz"])
+def test_constraint_rows_in_the_mirror_functions(name):
+    """joint_residuals / joint_jacobian with the four constraint arrays (reprojection.py:112-117, 207-226)."""
     from caliscope_b200 import reprojection as R
-    from caliscope_b200 import solver
 
-    g, rig = load_golden("small_pinhole_constraints.npz")
+    g, rig = load_golden(name)
     par = mirror_parameterization(g, rig)
     args = (par, rig.obs_cam, rig.obs_xy, rig.obs_pt, g["groups_a"], g["groups_b"], g["distances"], g["weights"])
-    with pytest.raises(NotImplementedError):
-        R.joint_residuals(g["x0"], *args)
-    with pytest.raises(NotImplementedError):
-        solver.least_squares(R.joint_residuals, g["x0"], args=args, jac=R.joint_jacobian, method="trf")
+    r = R.joint_residuals(g["x0"], *args)
+    assert r.shape == g["r0"].shape
+    assert np.abs(r - g["r0"]).max() < 1e-12
+    J = R.joint_jacobian(g["x0"], *args)
+    Jref = golden_csr(g, rig)
+    assert J.shape == Jref.shape
+    assert rel_col_err(J.toarray(), Jref.toarray()) < 1e-10
+    n_rows = 2 * rig.n_obs
+    assert np.abs(J.toarray()[n_rows:] - Jref.toarray()[n_rows:]).max() < 1e-9
+    R.clear_cache()
+
+
+def test_constraints_with_sharding_are_refused_not_silently_dropped():
+    import caliscope_b200 as cb
+
+    g, rig = load_golden("small_pinhole_constraints.npz")
+    cons = (g["groups_a"], g["groups_b"], g["distances"], g["weights"])
+    with cb.BAProblem(rig.cam_flags, rig.cam_const, rig.n_pts, rig.obs_cam, rig.obs_pt, rig.obs_xy, constraints=cons) as p:
+        with pytest.raises(cb.EngineError):
+            p.solve(g["x0"], allreduce=lambda *a: 0, rank=0, world_size=2)
+    bad = g["groups_a"].copy()
+    bad[0, 0] = rig.n_pts
+    with pytest.raises(cb.EngineError):
+        cb.BAProblem(rig.cam_flags, rig.cam_const, rig.n_pts, rig.obs_cam, rig.obs_pt, rig.obs_xy,
+                     constraints=(bad, g["groups_b"], g["distances"], g["weights"]))
 
 
 @pytest.mark.parametrize("name,refine", [("session4_refine0.npz", False), ("session4_refine1.npz", True)])

@@ -14,6 +14,9 @@ CASES = [
     "small_pinhole_refine0.npz",
     "small_pinhole_refine1.npz",
     "small_pinhole_constraints.npz",
+    "aruco_constraints_refine0.npz",
+    "aruco_constraints_refine1.npz",
+    "board_truss_constraints_refine0.npz",
     "mixed_fisheye.npz",
     "ring_perfect.npz",
     "ring_noisy_refine1.npz",

@@ -138,3 +138,37 @@ def test_seam_install_full_patches_and_restores(session_volume):
         assert mod.CaptureVolume.optimize is S2.optimize
         assert mod.CaptureVolume._compute_img_to_obj_map is S2.fast_img_to_obj_map
     assert (mod.least_squares, mod.CaptureVolume.optimize, mod.CaptureVolume._compute_img_to_obj_map) == before
+
+
+def test_s2_optimize_passes_the_reference_constraint_arrays(monkeypatch):
+    """capture_volume.py:373-383: groups, distances and (pixel_sigma / f_median) / sigma weights."""
+    import importlib.util
+
+    from caliscope_b200 import capture_volume as S2
+    from caliscope_b200 import solver
+    from caliscope_b200.problem import SolveResult
+
+    spec = importlib.util.spec_from_file_location("make_golden", ROOT / "tests" / "golden" / "make_golden.py")
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    vol = mg.aruco_constraint_volume()
+    ref_out, rec = _reference_run(vol, pixel_sigma=0.7)
+    seen = {}
+
+    def fake(flags, const, n_pts, cam, obj, xy, x0, **kw):
+        seen.update(kw)
+        r = rec["result"]
+        return SolveResult(x=r.x.copy(), status=int(r.status), nfev=int(r.nfev), njev=int(r.njev), nit=0, cost=float(r.cost),
+                           initial_cost=0.0, optimality=0.0, lambda_final=0.0, pcg_iterations=0, kernel_launches=0,
+                           solve_ms=0.0, rj_ms=0.0, rj_launches=0)  # fmt: skip
+
+    monkeypatch.setattr(solver, "solve_arrays", fake)
+    out = S2.optimize(vol, pixel_sigma=0.7)
+    ga, gb, dist, w = rec["args"][4:8]
+    cons = seen["constraints"]
+    assert np.array_equal(cons[0], ga) and np.array_equal(cons[1], gb)
+    assert np.array_equal(cons[2], dist) and np.array_equal(cons[3], w)
+    assert out.optimization_status == ref_out.optimization_status
+    assert out.rigidity_report().rmse_mm == ref_out.rigidity_report().rmse_mm
+    S2.optimize(vol, use_constraints=False)
+    assert seen["constraints"] is None
