@@ -1005,10 +1005,8 @@ int cb_ba_solve(CbBaProblem* p, const CbBaOptions* opt, double* x_inout, CbBaRes
   if (opt->loss < 0 || opt->loss > CB_LOSS_ARCTAN) { g_last_error = "unknown loss id"; return CB_E_INVALID; }
   CB_CUDA(cudaSetDevice(p->device));
   cudaStream_t st = (cudaStream_t)stream;
-  if (p->n_c && opt->allreduce) {
-    g_last_error = "rigid-distance constraints are not supported with observation sharding yet (components would span ranks)";
-    return CB_E_UNSUPPORTED;
-  }
+  // with an all-reduce hook the caller shards by constraint component (distributed.shard_points), so every
+  // constraint row and every point it touches are local to this rank
   return p->P == 6 ? lm_solve<6>(p, opt, x_inout, result, st) : lm_solve<9>(p, opt, x_inout, result, st);
 }
 

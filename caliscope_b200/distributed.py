@@ -21,16 +21,26 @@ import numpy as np
 class PointShard:
     rank: int
     world_size: int
-    pt_lo: int  # this rank owns global points [pt_lo, pt_hi)
-    pt_hi: int
+    pt_index: np.ndarray  # global ids of the points this rank owns, ascending
     obs_index: np.ndarray  # indices into the global observation list, ascending
     obs_cam: np.ndarray
-    obs_pt: np.ndarray  # LOCAL point ids (global - pt_lo)
+    obs_pt: np.ndarray  # LOCAL point ids (position in pt_index)
     obs_xy: np.ndarray
+    constraints: tuple | None = None  # (groups_a, groups_b, distances, weights) in LOCAL point ids
+    constraint_index: np.ndarray | None = None  # indices into the global constraint list
 
     @property
     def n_pts(self) -> int:
-        return self.pt_hi - self.pt_lo
+        return len(self.pt_index)
+
+    # contiguous-range views kept for callers that shard without constraints
+    @property
+    def pt_lo(self) -> int:
+        return int(self.pt_index[0]) if len(self.pt_index) else 0
+
+    @property
+    def pt_hi(self) -> int:
+        return int(self.pt_index[-1]) + 1 if len(self.pt_index) else 0
 
 
 def point_ranges(obs_pt: np.ndarray, n_pts: int, world_size: int) -> np.ndarray:
@@ -48,25 +58,80 @@ def point_ranges(obs_pt: np.ndarray, n_pts: int, world_size: int) -> np.ndarray:
     return np.asarray(bounds, dtype=np.int64)
 
 
-def shard_points(obs_cam, obs_pt, obs_xy, n_pts: int, rank: int, world_size: int) -> PointShard:
+def _component_labels(n_pts: int, groups_a: np.ndarray, groups_b: np.ndarray) -> np.ndarray:
+    """Connected components of the constraint graph (union-find); every point gets the smallest point id of
+    its component as label, so unconstrained points label themselves."""
+    parent = np.arange(n_pts, dtype=np.int64)
+
+    def find(a: int) -> int:
+        while parent[a] != a:
+            parent[a] = parent[parent[a]]
+            a = parent[a]
+        return a
+
+    members = np.concatenate([groups_a, groups_b], axis=1).astype(np.int64)
+    for row in members:
+        r0 = find(int(row[0]))
+        for q in row[1:]:
+            rq = find(int(q))
+            if rq != r0:
+                lo, hi = (r0, rq) if r0 < rq else (rq, r0)
+                parent[hi] = lo
+                r0 = lo
+    return np.array([find(int(j)) for j in range(n_pts)], dtype=np.int64)
+
+
+def shard_points(obs_cam, obs_pt, obs_xy, n_pts: int, rank: int, world_size: int, constraints=None) -> PointShard:
+    """Partition the points (and with them the observations and constraint rows) over the ranks.
+
+    Without constraints: contiguous point ranges balanced by observation count.  With rigid-distance
+    constraints the unit of assignment is a connected component of the constraint graph, so no component is
+    split across ranks (each rank eliminates its components locally); units are dealt in order of their
+    first point to the rank whose cumulative observation count they fall into."""
     obs_pt = np.asarray(obs_pt)
-    bounds = point_ranges(obs_pt, n_pts, world_size)
-    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-    sel = np.nonzero((obs_pt >= lo) & (obs_pt < hi))[0]
-    return PointShard(
+    counts = np.bincount(obs_pt.astype(np.int64), minlength=n_pts)
+    if constraints is None or constraints[0] is None or len(constraints[0]) == 0:
+        bounds = point_ranges(obs_pt, n_pts, world_size)
+        owner = np.searchsorted(bounds[1:], np.arange(n_pts), side="right")
+    else:
+        ga, gb = np.asarray(constraints[0]).reshape(-1, 4), np.asarray(constraints[1]).reshape(-1, 4)
+        label = _component_labels(n_pts, ga, gb)
+        unit_counts = np.bincount(label, weights=counts.astype(np.float64), minlength=n_pts)
+        is_root = label == np.arange(n_pts)
+        csum = np.cumsum(np.where(is_root, unit_counts, 0.0))  # cumulative weight at each unit's first point
+        total = csum[-1] if n_pts else 0.0
+        start = csum - np.where(is_root, unit_counts, 0.0)
+        unit_owner = np.minimum((start * world_size / max(total, 1.0)).astype(np.int64), world_size - 1)
+        owner = unit_owner[label]
+    pts = np.nonzero(owner == rank)[0]
+    local_of = np.full(n_pts, -1, dtype=np.int64)
+    local_of[pts] = np.arange(len(pts))
+    sel = np.nonzero(owner[obs_pt] == rank)[0]
+    shard = PointShard(
         rank=rank,
         world_size=world_size,
-        pt_lo=lo,
-        pt_hi=hi,
+        pt_index=pts,
         obs_index=sel,
         obs_cam=np.ascontiguousarray(np.asarray(obs_cam)[sel], dtype=np.int32),
-        obs_pt=np.ascontiguousarray(obs_pt[sel] - lo, dtype=np.int32),
+        obs_pt=np.ascontiguousarray(local_of[obs_pt[sel]], dtype=np.int32),
         obs_xy=np.ascontiguousarray(np.asarray(obs_xy, dtype=np.float64).reshape(-1, 2)[sel]),
     )
+    if constraints is not None and constraints[0] is not None and len(constraints[0]) > 0:
+        ga, gb = np.asarray(constraints[0]).reshape(-1, 4), np.asarray(constraints[1]).reshape(-1, 4)
+        csel = np.nonzero(owner[ga[:, 0]] == rank)[0]
+        shard.constraint_index = csel
+        shard.constraints = (
+            np.ascontiguousarray(local_of[ga[csel]], dtype=np.int32),
+            np.ascontiguousarray(local_of[gb[csel]], dtype=np.int32),
+            np.ascontiguousarray(np.asarray(constraints[2], dtype=np.float64)[csel]),
+            np.ascontiguousarray(np.asarray(constraints[3], dtype=np.float64)[csel]),
+        )
+        assert shard.constraints[0].min(initial=0) >= 0 and shard.constraints[1].min(initial=0) >= 0
+    return shard
 
 
 def local_x(x_global: np.ndarray, n_camera_params: int, shard: PointShard) -> np.ndarray:
-    pts = x_global[n_camera_params:].reshape(-1, 3)[shard.pt_lo : shard.pt_hi]
+    pts = x_global[n_camera_params:].reshape(-1, 3)[shard.pt_index]
     return np.concatenate([x_global[:n_camera_params], pts.ravel()])
 
 
@@ -118,30 +183,35 @@ def gather_points(x_local: np.ndarray, n_camera_params: int, n_pts_global: int, 
 
     mine = np.ascontiguousarray(x_local[n_camera_params:])
     sizes = [None] * shard.world_size
-    dist.all_gather_object(sizes, (shard.pt_lo, shard.pt_hi), group=group)
+    dist.all_gather_object(sizes, int(shard.n_pts), group=group)
     backend = dist.get_backend(group)
     dev = "cuda" if backend == "nccl" else "cpu"
-    maxlen = max(3 * (hi - lo) for lo, hi in sizes)
-    send = torch.zeros(maxlen, dtype=torch.float64, device=dev)
-    send[: len(mine)] = torch.from_numpy(mine).to(dev)
-    recv = [torch.zeros(maxlen, dtype=torch.float64, device=dev) for _ in sizes]
+    maxn = max(sizes)
+    send = torch.zeros(4 * maxn, dtype=torch.float64, device=dev)  # [ids | xyz]
+    send[: len(shard.pt_index)] = torch.from_numpy(shard.pt_index.astype(np.float64)).to(dev)
+    send[maxn : maxn + len(mine)] = torch.from_numpy(mine).to(dev)
+    recv = [torch.zeros(4 * maxn, dtype=torch.float64, device=dev) for _ in sizes]
     dist.all_gather(recv, send, group=group)
-    pts = np.zeros(3 * n_pts_global)
-    for (lo, hi), t in zip(sizes, recv):
-        pts[3 * lo : 3 * hi] = t[: 3 * (hi - lo)].cpu().numpy()
-    return np.concatenate([x_local[:n_camera_params], pts])
+    pts = np.zeros((n_pts_global, 3))
+    for n, t in zip(sizes, recv):
+        t = t.cpu().numpy()
+        pts[t[:n].astype(np.int64)] = t[maxn : maxn + 3 * n].reshape(-1, 3)
+    return np.concatenate([x_local[:n_camera_params], pts.ravel()])
 
 
-def solve_sharded(cam_flags, cam_const, n_pts, obs_cam, obs_pt, obs_xy, x0, *, device: int, group=None, **solve_kw):
-    """Shard by point, solve with one all-reduce of the reduced camera system per LM trial, gather."""
+def solve_sharded(cam_flags, cam_const, n_pts, obs_cam, obs_pt, obs_xy, x0, *, device: int, group=None, constraints=None,
+                  **solve_kw):
+    """Shard by point (by constraint component when rigid-distance rows are present), solve with one
+    all-reduce of the reduced camera system per LM trial, gather."""
     import torch.distributed as dist
 
     from .problem import BAProblem
 
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    shard = shard_points(obs_cam, obs_pt, obs_xy, n_pts, rank, world)
+    shard = shard_points(obs_cam, obs_pt, obs_xy, n_pts, rank, world, constraints)
     ncp = int(np.where(np.asarray(cam_flags) & 1, 9, 6).sum())
-    with BAProblem(cam_flags, cam_const, shard.n_pts, shard.obs_cam, shard.obs_pt, shard.obs_xy, device=device) as prob:
+    with BAProblem(cam_flags, cam_const, shard.n_pts, shard.obs_cam, shard.obs_pt, shard.obs_xy,
+                   constraints=shard.constraints, device=device) as prob:
         res = prob.solve(
             local_x(np.asarray(x0, dtype=np.float64), ncp, shard),
             allreduce=make_allreduce_hook(group),

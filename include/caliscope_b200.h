@@ -136,7 +136,8 @@ int64_t cb_ba_problem_n_params(const CbBaProblem* p);
 /* Rigid-distance constraint rows (reprojection.py:112-117 and :207-226): groups_a / groups_b are n_c x 4 world-point
  * row indices, distances and weights n_c doubles -- the arrays CaptureVolume._build_constraint_arrays produces
  * (capture_volume.py:446-516) with weights = (pixel_sigma / f_median) / sigma (:377-381).  Host pointers, copied.
- * Call at most once, after cb_ba_problem_create; single-GPU solves only in this build. */
+ * Call at most once, after cb_ba_problem_create.  Under observation sharding every point a row touches must belong
+ * to the same rank (shard by connected component of the constraint graph). */
 int cb_ba_problem_set_constraints(CbBaProblem* p, int64_t n_c, const int32_t* groups_a, const int32_t* groups_b,
                                   const double* distances, const double* weights, void* stream);
 int64_t cb_ba_problem_n_constraints(const CbBaProblem* p);

@@ -89,3 +89,28 @@ def test_allreduce_hook_and_gather_world_size_2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(results) == [(0, "ok"), (1, "ok")], results
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_component_aware_sharding_keeps_rigid_bodies_on_one_rank(world):
+    """With rigid-distance rows the unit of assignment is a connected component of the constraint graph."""
+    from tests._util import load_golden
+
+    g, rig = load_golden("board_truss_constraints_refine0.npz")
+    cons = (g["groups_a"], g["groups_b"], g["distances"], g["weights"])
+    seen_obs = np.zeros(rig.n_obs, int)
+    seen_con = np.zeros(len(cons[0]), int)
+    seen_pts = np.zeros(rig.n_pts, int)
+    for k in range(world):
+        s = D.shard_points(rig.obs_cam, rig.obs_pt, rig.obs_xy, rig.n_pts, k, world, cons)
+        seen_obs[s.obs_index] += 1
+        seen_con[s.constraint_index] += 1
+        seen_pts[s.pt_index] += 1
+        assert np.array_equal(s.pt_index[s.obs_pt], rig.obs_pt[s.obs_index])
+        ga, gb, dist, w = s.constraints
+        assert ga.min() >= 0 and gb.min() >= 0 and ga.max() < s.n_pts and gb.max() < s.n_pts  # fully local
+        assert np.array_equal(s.pt_index[ga], g["groups_a"][s.constraint_index])
+        assert np.array_equal(s.pt_index[gb], g["groups_b"][s.constraint_index])
+        assert np.array_equal(dist, g["distances"][s.constraint_index])
+        assert len(s.constraint_index) > 0
+    assert np.all(seen_obs == 1) and np.all(seen_con == 1) and np.all(seen_pts == 1)

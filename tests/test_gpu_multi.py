@@ -77,3 +77,55 @@ def test_two_gpu_sharded_solve_matches_single_gpu(refine):
     assert results[0][5] in (1, 2, 3, 4)
     assert abs(results[0][3] - single.cost) < 1e-9 * single.cost
     assert abs(rm1 - rm2) < 1e-6
+
+
+def _worker_constraints(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from caliscope_b200 import distributed as D
+        from tests._util import load_golden
+
+        g, rig = load_golden("board_truss_constraints_refine0.npz")
+        cons = (g["groups_a"], g["groups_b"], g["distances"], g["weights"])
+        res, shard = D.solve_sharded(rig.cam_flags, rig.cam_const, rig.n_pts, rig.obs_cam, rig.obs_pt, rig.obs_xy, g["x0"],
+                                     device=rank, constraints=cons)  # fmt: skip
+        out.put((rank, "ok", res.x, res.cost, res.nfev, res.status))
+    except Exception as e:  # pragma: no cover
+        import traceback
+
+        out.put((rank, "err: " + repr(e) + traceback.format_exc(), None, None, None, None))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
+def test_two_gpu_sharded_solve_with_constraints_matches_single_gpu():
+    import torch.multiprocessing as mp
+
+    import caliscope_b200 as cb
+    from tests._util import load_golden
+
+    g, rig = load_golden("board_truss_constraints_refine0.npz")
+    cons = (g["groups_a"], g["groups_b"], g["distances"], g["weights"])
+    with cb.BAProblem(rig.cam_flags, rig.cam_const, rig.n_pts, rig.obs_cam, rig.obs_pt, rig.obs_xy, constraints=cons) as p:
+        single = p.solve(g["x0"])
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_constraints, args=(k, 2, port, out)) for k in range(2)]
+    for q in procs:
+        q.start()
+    results = sorted([out.get(timeout=600) for _ in procs], key=lambda t: t[0])
+    for q in procs:
+        q.join(timeout=60)
+    assert [t[1] for t in results] == ["ok", "ok"], results
+    assert np.array_equal(results[0][2], results[1][2])
+    assert abs(results[0][3] - single.cost) < 1e-9 * single.cost
+    assert results[0][3] <= float(g["cost_default"]) * (1 + 1e-8)
+    assert np.abs(results[0][2] - single.x).max() < 1e-6

@@ -79,19 +79,18 @@ def test_constraint_rows_in_the_mirror_functions(name):
     R.clear_cache()
 
 
-def test_constraints_with_sharding_are_refused_not_silently_dropped():
+def test_bad_constraint_indices_are_rejected():
     import caliscope_b200 as cb
 
     g, rig = load_golden("small_pinhole_constraints.npz")
-    cons = (g["groups_a"], g["groups_b"], g["distances"], g["weights"])
-    with cb.BAProblem(rig.cam_flags, rig.cam_const, rig.n_pts, rig.obs_cam, rig.obs_pt, rig.obs_xy, constraints=cons) as p:
-        with pytest.raises(cb.EngineError):
-            p.solve(g["x0"], allreduce=lambda *a: 0, rank=0, world_size=2)
     bad = g["groups_a"].copy()
     bad[0, 0] = rig.n_pts
     with pytest.raises(cb.EngineError):
         cb.BAProblem(rig.cam_flags, rig.cam_const, rig.n_pts, rig.obs_cam, rig.obs_pt, rig.obs_xy,
                      constraints=(bad, g["groups_b"], g["distances"], g["weights"]))
+    with pytest.raises(ValueError):
+        cb.BAProblem(rig.cam_flags, rig.cam_const, rig.n_pts, rig.obs_cam, rig.obs_pt, rig.obs_xy,
+                     constraints=(g["groups_a"], g["groups_b"][:1], g["distances"], g["weights"]))
 
 
 @pytest.mark.parametrize("name,refine", [("session4_refine0.npz", False), ("session4_refine1.npz", True)])
