@@ -39,6 +39,8 @@ WORKLOADS = {
     "cfg4_intrinsics": (64, 50_000, 2_000_000, True),
     "cfg3": (16, 10_000, 400_000, True),
     "cfg2": (8, 2_000, 40_000, False),
+    # what one rank holds of cfg4 at 8 GPUs: used on ONE GPU to profile the per-iteration fixed cost
+    "cfg4_shard8": (64, 6_250, 250_000, False),
 }
 # BASELINE.json configs[4]: cfg4 rig + 2 % outliers, solve(linear) -> solve(soft_l1) -> 2.5 % per-camera cull -> solve(linear)
 PIPELINE_WORKLOADS = {"cfg5": (64, 50_000, 2_000_000, 0.02), "cfg5_small": (8, 2_000, 40_000, 0.02)}
@@ -252,13 +254,13 @@ def run_ours(args) -> None:
         shard = D.shard_points(rig.obs_cam, rig.obs_pt, rig.obs_xy, rig.n_pts, rank, world)
         l_cam, l_pt, l_xy, l_npts = shard.obs_cam, shard.obs_pt, shard.obs_xy, shard.n_pts
         x0 = D.local_x(rig.x0, ncp, shard)
-        hook = D.make_allreduce_hook()
+        transport = D.transport_kwargs(local_rank)
     else:
         shard = None
         l_cam, l_pt, l_xy, l_npts = rig.obs_cam, rig.obs_pt, rig.obs_xy, rig.n_pts
         x0 = rig.x0
-        hook = None
-    solve_kw = dict(ftol=1e-8, allreduce=hook, rank=rank, world_size=world, stream=stream)
+        transport = {}
+    solve_kw = dict(ftol=1e-8, rank=rank, world_size=world, stream=stream, **transport)
 
     def barrier():
         if world > 1:
@@ -450,20 +452,92 @@ def run_pipeline(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+def run_triangulation(args) -> None:
+    """The step in front of bundle adjustment on the cfg4 rig: undistort 2 M pixel
+    observations and DLT-triangulate the 50 000 points, host buffers in and out; one step = both calls."""
+    import torch
+
+    from caliscope_b200 import synthetic
+    from caliscope_b200 import triangulation as T
+
+    rig = synthetic.cfg4()
+    proj, _ = synthetic.exact_normalized_observations(rig)
+    K = np.array([[rig.cam_const[0, 0], 0, rig.cam_const[0, 2]], [0, rig.cam_const[0, 1], rig.cam_const[0, 3]], [0, 0, 1.0]])
+    mats = np.tile(K, (rig.n_cams, 1, 1))
+    dists = [np.array([c[4], c[5], c[6], c[7], c[8]]) for c in rig.cam_const]
+    fish = np.zeros(rig.n_cams, np.int32)
+    key = rig.obs_pt.astype(np.int64)
+    st = T.TriangulationStats()
+
+    def step():
+        return T.triangulate_groups(proj, rig.obs_cam, key, rig.obs_xy, stats=st, undistort=(mats, dists, fish))
+
+    for _ in range(args.warmup):
+        xyz, count, _, _ = step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    dlt_ms = 0.0
+    launches0 = T.L.load().cb_ba_launch_count()
+    for _ in range(args.steps):
+        xyz, count, _, _ = step()
+        dlt_ms += st.dlt_ms
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    launches = T.L.load().cb_ba_launch_count() - launches0
+    truth = rig.x_true[-3 * rig.n_pts:].reshape(-1, 3)
+    peak, peak_src = load_peaks()
+    alg = 24 * rig.n_obs + 56 * rig.n_pts  # row index 4 + camera 4 + xy 16 per observation; start 4+4, xyz 24, count/rep 8, sig 16 per group
+    line = {
+        "metric": "triangulated_points_per_sec", "value": rig.n_pts * args.steps / wall, "unit": "points/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "triangulate_cfg4: undistort 2 000 000 pixel observations (64 pinhole cameras) + DLT of 50 000 "
+                   "points in one cb_undistort_triangulate call; host buffers in and out, uploads inside the timed "
+                   "region (inputs 56 MB + sort buffers > L2)"},
+        "e2e": {"value": rig.n_pts * args.steps / wall, "unit": "points/s", "ms_per_step": 1e3 * wall / args.steps,
+                "h2d_bytes_per_step": int(rig.n_obs * (16 + 4 + 8)),
+                "d2h_bytes_per_step": int(rig.n_pts * (24 + 4 + 4 + 16))},
+        "gpu_launches": int(launches),
+        "max_abs_error_vs_truth_m": float(np.abs(xyz - truth).max()),
+        "roofline": {"kernel": "tri_dlt_kernel (gather rows, 4x4 normal matrix, Jacobi eigenvector)", "bound": "hbm",
+                     "achieved": alg / (dlt_ms / args.steps * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": alg / (dlt_ms / args.steps * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": int(alg), "avg_launch_ms": dlt_ms / args.steps},
+    }  # fmt: skip
+    if not args.no_cpu_baseline:
+        from oracle import triangulation as OT
+
+        n_s = 2000
+        m = rig.obs_pt < n_s
+        pm = {i: proj[i] for i in range(rig.n_cams)}
+        und = OT.undistort_points(rig.obs_xy[m], K, dists[0], False)
+        z = np.zeros(int(m.sum()), np.int64)
+        t1 = time.perf_counter()
+        OT.triangulate_image_points(pm, z, rig.obs_cam[m].astype(np.int64), z, rig.obs_pt[m].astype(np.int64), und)
+        dt = time.perf_counter() - t1
+        line["cpu_baseline"] = {"value": n_s / dt, "unit": "points/s", "cores": 1, "kind": "port",
+                                "sample": f"first {n_s} points ({int(m.sum())} observations) of the same rig, one SVD per point"}
+    print(json.dumps(line), flush=True)
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=sorted(WORKLOADS) + sorted(PIPELINE_WORKLOADS), default="cfg4")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS) + sorted(PIPELINE_WORKLOADS) + ["triangulate_cfg4"], default="cfg4")
     ap.add_argument("--ref-max-nfev", type=int, default=0, help="cap on scipy evaluations per reference step (0: run to convergence)")
     ap.add_argument("--ref-budget-s", type=float, default=240.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
-    if args.workload in PIPELINE_WORKLOADS:
+    if args.workload == "triangulate_cfg4":
+        if args.impl != "ours" or args.gpus != 1:
+            raise SystemExit("triangulate_cfg4 runs on the CUDA arm, one GPU")
+        run_triangulation(args)
+    elif args.workload in PIPELINE_WORKLOADS:
         if args.impl != "ours" or args.gpus != 1:
             raise SystemExit("pipeline workloads run on the CUDA arm, one GPU")
         run_pipeline(args)

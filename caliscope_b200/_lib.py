@@ -59,6 +59,7 @@ class Options(C.Structure):
         ("pcg_max_iter", C.c_int32),
         ("allreduce", ALLREDUCE_FN),
         ("allreduce_user", C.c_void_p),
+        ("nccl_comm", C.c_void_p),
         ("rank", C.c_int32),
         ("world_size", C.c_int32),
     ]
@@ -79,6 +80,16 @@ class Result(C.Structure):
         ("solve_ms", C.c_double),
         ("rj_ms", C.c_double),
         ("rj_launches", C.c_int64),
+    ]
+
+
+class TriStats(C.Structure):
+    _fields_ = [
+        ("group_ms", C.c_double),
+        ("dlt_ms", C.c_double),
+        ("total_ms", C.c_double),
+        ("kernel_launches", C.c_int32),
+        ("pad_", C.c_int32),
     ]
 
 
@@ -109,6 +120,20 @@ SYMBOLS = {
     "cb_ba_rmse_px": (C.c_int, [_P, _P, _P, _P, _P]),
     "cb_ba_cull": (C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(_P), _P, _P, _P]),
     "cb_ba_debug_pcg_time": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
+    "cb_undistort_points": (C.c_int, [C.c_int32, _P, _P, _P, C.c_int64, _P, _P, C.c_int, C.c_int, _P, C.c_int, _P]),
+    "cb_triangulate_dlt": (
+        C.c_int,
+        [C.c_int32, _P, C.c_int64, _P, _P, _P, C.c_int, C.c_int32, C.POINTER(C.c_int32), _P, _P, _P, _P,
+         C.POINTER(TriStats), C.c_int, _P],
+    ),
+    "cb_undistort_triangulate": (
+        C.c_int,
+        [C.c_int32, _P, _P, _P, _P, C.c_int64, _P, _P, _P, C.c_int, C.c_int32, C.POINTER(C.c_int32), _P, _P, _P, _P,
+         C.POINTER(TriStats), C.c_int, _P],
+    ),
+    "cb_nccl_unique_id": (C.c_int, [_P]),
+    "cb_nccl_comm_create": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "cb_nccl_comm_destroy": (C.c_int, [_P]),
     "cb_ba_launch_count": (C.c_int64, []),
 }
 

@@ -7,6 +7,7 @@
 // codes follow scipy's (site-packages/scipy/optimize/_lsq/common.py:705-717, trf.py:466-475);
 // the step itself is a damped Gauss-Newton step from the Schur-complement reduced camera system.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <atomic>
@@ -23,6 +24,7 @@
 #include "../../include/caliscope_b200.h"
 #include "cb_kernels.cuh"
 #include "cb_constraints.cuh"
+#include "cb_triangulate.cuh"
 
 namespace {
 
@@ -51,6 +53,68 @@ std::atomic<long long> g_launches{0};
   } while (0)
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------
+// NCCL, resolved at run time from the libnccl the process already has loaded (torch's bundled copy):
+// no link-time dependency, no second NCCL in the address space.
+// ------------------------------------------------------------------------------------------
+struct NcclApi {
+  bool ok = false;
+  std::string err;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, /* ncclUniqueId by value */ struct UidBlob, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+struct UidBlob { char internal[128]; };
+
+NcclApi& nccl() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* h = nullptr;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+      h = dlopen(name, RTLD_NOW | RTLD_NOLOAD);  // only an already-loaded library
+      if (h) break;
+    }
+    if (!h)
+      for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+        h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+      }
+    if (!h) { api.err = "libnccl.so.2 not found in the process (import torch first)"; return; }
+    api.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+    api.CommInitRank = (int (*)(void**, int, UidBlob, int))dlsym(h, "ncclCommInitRank");
+    api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+    api.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+    api.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy;
+    if (!api.ok) api.err = "libnccl is missing ncclGetUniqueId / ncclCommInitRank / ncclAllReduce / ncclCommDestroy";
+  });
+  return api;
+}
+
+// sum-all-reduce of n doubles in place through whichever transport the options carry
+int do_allreduce(const CbBaOptions* opt, double* buf, long long n, cudaStream_t st) {
+  if (opt->nccl_comm) {
+    NcclApi& a = nccl();
+    if (!a.ok) { g_last_error = a.err; return CB_E_UNSUPPORTED; }
+    const int rc = a.AllReduce(buf, buf, (size_t)n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, opt->nccl_comm, st);
+    if (rc != 0) {
+      g_last_error = std::string("ncclAllReduce: ") + (a.GetErrorString ? a.GetErrorString(rc) : "error");
+      return CB_E_CALLBACK;
+    }
+    return CB_OK;
+  }
+  if (opt->allreduce(opt->allreduce_user, buf, n, (void*)st) != 0) {
+    g_last_error = "all-reduce callback failed";
+    return CB_E_CALLBACK;
+  }
+  return CB_OK;
+}
+
+inline bool sharded(const CbBaOptions* opt) { return opt && (opt->allreduce || opt->nccl_comm); }
 
 // Process-wide caching allocator: repeated problem_create / destroy cycles (one per
 // CaptureVolume.optimize call: linear -> soft_l1 -> filter -> linear) reuse device and pinned
@@ -399,14 +463,9 @@ int build_system(CbBaProblem* p, double lam, bool new_lin, const CbBaOptions* op
   // gradient inf-norm over points: one slot per rank so a SUM all-reduce carries the max
   const size_t slot0 = (size_t)p->nP * p->nP + 3 * (size_t)p->nP + 1;
   CB_CUDA(cudaMemsetAsync(p->d_red + slot0, 0, sizeof(double) * p->red_slots, st));
-  const int rank = (opt && opt->allreduce) ? std::min(std::max(opt->rank, 0), p->red_slots - 1) : 0;
+  const int rank = sharded(opt) ? std::min(std::max(opt->rank, 0), p->red_slots - 1) : 0;
   CB_CUDA(cudaMemcpyAsync(p->d_red + slot0 + rank, p->d_gmax, sizeof(double), cudaMemcpyDeviceToDevice, st));
-  if (opt && opt->allreduce) {
-    if (opt->allreduce(opt->allreduce_user, p->d_red, (long long)p->red_len(), (void*)st) != 0) {
-      g_last_error = "all-reduce callback failed";
-      return CB_E_CALLBACK;
-    }
-  }
+  if (sharded(opt)) CB_TRY(do_allreduce(opt, p->d_red, (long long)p->red_len(), st));
   CB_LAUNCH(cb::post_reduce_kernel, 1, 256, 0, st, p->nP, lam, new_lin ? 1 : 0, p->d_red, p->d_Dc2, p->d_active,
             p->d_sc);
   return CB_OK;
@@ -475,12 +534,7 @@ int trial_cost(CbBaProblem* p, int nxt, int loss, double fscale, const CbBaOptio
     CB_LAUNCH((cb::constraint_eval_kernel<true>), p->n_cblk, cb::CC_THREADS, 0, st, p->ct, p->d_xp4[nxt], loss, fscale,
               (double*)nullptr, (double*)nullptr, (double*)nullptr, p->d_partial + p->n_chunks);
   CB_LAUNCH(cb::sum_kernel, 1, 256, 0, st, p->d_partial, p->n_chunks + p->n_cblk, p->d_red2);
-  if (opt && opt->allreduce) {
-    if (opt->allreduce(opt->allreduce_user, p->d_red2, 4, (void*)st) != 0) {
-      g_last_error = "all-reduce callback failed";
-      return CB_E_CALLBACK;
-    }
-  }
+  if (sharded(opt)) CB_TRY(do_allreduce(opt, p->d_red2, 4, st));
   return CB_OK;
 }
 
@@ -765,11 +819,46 @@ void cb_ba_default_options(CbBaOptions* o) {
   o->pcg_max_iter = 0;
   o->allreduce = nullptr;
   o->allreduce_user = nullptr;
+  o->nccl_comm = nullptr;
   o->rank = 0;
   o->world_size = 1;
 }
 
 int64_t cb_ba_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int cb_nccl_unique_id(char id_out[128]) {
+  NcclApi& a = nccl();
+  if (!a.ok) { g_last_error = a.err; return CB_E_UNSUPPORTED; }
+  UidBlob u;
+  const int rc = a.GetUniqueId(&u);
+  if (rc != 0) { g_last_error = "ncclGetUniqueId failed"; return CB_E_CALLBACK; }
+  std::memcpy(id_out, u.internal, 128);
+  return CB_OK;
+}
+
+int cb_nccl_comm_create(const char id[128], int rank, int world_size, int device, void** comm_out) {
+  if (!id || !comm_out || rank < 0 || rank >= world_size) { g_last_error = "cb_nccl_comm_create: bad argument"; return CB_E_INVALID; }
+  NcclApi& a = nccl();
+  if (!a.ok) { g_last_error = a.err; return CB_E_UNSUPPORTED; }
+  CB_CUDA(cudaSetDevice(device));
+  UidBlob u;
+  std::memcpy(u.internal, id, 128);
+  void* comm = nullptr;
+  const int rc = a.CommInitRank(&comm, world_size, u, rank);
+  if (rc != 0) {
+    g_last_error = std::string("ncclCommInitRank: ") + (a.GetErrorString ? a.GetErrorString(rc) : "error");
+    return CB_E_CALLBACK;
+  }
+  *comm_out = comm;
+  return CB_OK;
+}
+
+int cb_nccl_comm_destroy(void* comm) {
+  if (!comm) return CB_OK;
+  NcclApi& a = nccl();
+  if (!a.ok) return CB_E_UNSUPPORTED;
+  return a.CommDestroy(comm) == 0 ? CB_OK : CB_E_CALLBACK;
+}
 
 int cb_ba_problem_destroy(CbBaProblem* p) {
   if (!p) return CB_OK;
@@ -1448,6 +1537,266 @@ int cb_ba_cull(CbBaProblem* p, const double* x, const double* thresholds, int32_
   cached_free(d_tmp); cached_free(d_thr); cached_free(d_ss); cached_free(d_kept); cached_free(d_flag);
   cached_free(d_iota); cached_free(d_sel); cached_free(d_nsel);
   return rc;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// the step in front of bundle adjustment: undistortion + DLT triangulation
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct ScopedFree {
+  std::vector<void*> dev, host;
+  ~ScopedFree() {
+    for (void* q : dev) cached_free(q);
+    for (void* q : host) cached_free_host(q);
+  }
+};
+
+int select_device(int device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    g_last_error = "no CUDA device";
+    return CB_E_NO_DEVICE;
+  }
+  if (device < 0 || device >= ndev) { g_last_error = "device index out of range"; return CB_E_INVALID; }
+  CB_CUDA(cudaSetDevice(device));
+  return CB_OK;
+}
+
+int build_undist_table(int32_t n_cams, const int32_t* cam_fisheye, const double* cam_k, const double* cam_dist,
+                       std::vector<cb::UndistCam>& tab) {
+  tab.resize(n_cams);
+  for (int c = 0; c < n_cams; ++c) {
+    cb::UndistCam& u = tab[c];
+    u.fx = cam_k[5 * c]; u.fy = cam_k[5 * c + 1]; u.cx = cam_k[5 * c + 2]; u.cy = cam_k[5 * c + 3]; u.skew = cam_k[5 * c + 4];
+    for (int k = 0; k < 12; ++k) u.d[k] = cam_dist[12 * c + k];
+    u.fisheye = cam_fisheye[c] ? 1 : 0;
+    u.pad = 0;
+    if (!(u.fx != 0.0) || !(u.fy != 0.0)) { g_last_error = "zero focal length in the camera table"; return CB_E_INVALID; }
+  }
+  return CB_OK;
+}
+
+// host array -> device through a pinned bounce buffer (or pass through when already on the device)
+template <typename T>
+int to_device(const T* src, size_t n, int on_device, const T** out, ScopedFree& sf, cudaStream_t st) {
+  if (on_device) { *out = src; return CB_OK; }
+  T* d = nullptr;
+  CB_TRY(dalloc(&d, n));
+  sf.dev.push_back(d);
+  T* h = nullptr;
+  CB_TRY(cached_malloc_host((void**)&h, sizeof(T) * std::max<size_t>(n, 1)));
+  sf.host.push_back(h);
+  std::memcpy(h, src, sizeof(T) * n);
+  CB_CUDA(cudaMemcpyAsync(d, h, sizeof(T) * n, cudaMemcpyHostToDevice, st));
+  *out = d;
+  return CB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cb_undistort_points(int32_t n_cams, const int32_t* cam_fisheye, const double* cam_k, const double* cam_dist,
+                        int64_t n, const int32_t* obs_cam, const double* xy_in, int on_device, int to_pixels,
+                        double* xy_out, int device, void* stream) {
+  if (n_cams <= 0 || !cam_fisheye || !cam_k || !cam_dist || n < 0 || (n > 0 && (!xy_in || !xy_out))) {
+    g_last_error = "cb_undistort_points: bad argument";
+    return CB_E_INVALID;
+  }
+  if (n_cams > 1 && !obs_cam) { g_last_error = "cb_undistort_points: obs_cam is required with more than one camera"; return CB_E_INVALID; }
+  CB_TRY(select_device(device));
+  if (n == 0) return CB_OK;
+  if (!on_device && obs_cam)
+    for (int64_t i = 0; i < n; ++i)
+      if (obs_cam[i] < 0 || obs_cam[i] >= n_cams) { g_last_error = "cb_undistort_points: camera index out of range"; return CB_E_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  ScopedFree sf;
+  std::vector<cb::UndistCam> tab;
+  CB_TRY(build_undist_table(n_cams, cam_fisheye, cam_k, cam_dist, tab));
+  cb::UndistCam* d_tab = nullptr;
+  CB_TRY(dalloc(&d_tab, (size_t)n_cams));
+  sf.dev.push_back(d_tab);
+  CB_CUDA(cudaMemcpyAsync(d_tab, tab.data(), sizeof(cb::UndistCam) * n_cams, cudaMemcpyHostToDevice, st));
+  const int* d_cam = nullptr;
+  const double* d_in = nullptr;
+  if (obs_cam) CB_TRY(to_device(obs_cam, (size_t)n, on_device, &d_cam, sf, st));
+  CB_TRY(to_device(xy_in, 2 * (size_t)n, on_device, &d_in, sf, st));
+  double* d_out = xy_out;
+  double* h_out = nullptr;
+  if (!on_device) {
+    CB_TRY(dalloc(&d_out, 2 * (size_t)n));
+    sf.dev.push_back(d_out);
+    CB_TRY(cached_malloc_host((void**)&h_out, sizeof(double) * 2 * (size_t)n));
+    sf.host.push_back(h_out);
+  }
+  CB_LAUNCH(cb::undistort_kernel, cdiv(n, 256), 256, 0, st, d_tab, d_cam, d_in, d_out, (long long)n, to_pixels ? 1 : 0);
+  CB_CUDA(cudaGetLastError());
+  if (!on_device) {
+    CB_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CB_CUDA(cudaStreamSynchronize(st));
+    std::memcpy(xy_out, h_out, sizeof(double) * 2 * (size_t)n);
+  } else {
+    CB_CUDA(cudaStreamSynchronize(st));  // the camera table is a stack-lifetime upload
+  }
+  return CB_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+// shared body of cb_triangulate_dlt / cb_undistort_triangulate: `undist` non-null = obs_xy are raw pixels,
+// undistorted on the device (normalised output) before the DLT, never leaving HBM in between.
+int triangulate_impl(int32_t n_cams, const std::vector<cb::UndistCam>* undist, const double* proj, int64_t n_obs,
+                     const int32_t* obs_cam, const int64_t* obs_key, const double* obs_xy, int obs_on_device,
+                     int32_t max_groups, int32_t* n_groups_out, double* xyz_out, int32_t* count_out,
+                     int32_t* rep_row_out, uint64_t* camset_sig_out, CbTriStats* stats, int device, void* stream) {
+  if (n_cams <= 0 || !proj || n_obs < 0 || n_obs > 0x7fffffffLL || !n_groups_out || max_groups < 0 ||
+      (n_obs > 0 && (!obs_cam || !obs_key || !obs_xy)) ||
+      (max_groups > 0 && (!xyz_out || !count_out || !rep_row_out || !camset_sig_out))) {
+    g_last_error = "cb_triangulate_dlt: bad argument";
+    return CB_E_INVALID;
+  }
+  CB_TRY(select_device(device));
+  *n_groups_out = 0;
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+  if (n_obs == 0) return CB_OK;
+  const long long launches0 = g_launches.load();
+  cudaStream_t st = (cudaStream_t)stream;
+  ScopedFree sf;
+  const int n = (int)n_obs;
+  const int TB = 256, G = cdiv(n, TB);
+  if (!obs_on_device)
+    for (int64_t i = 0; i < n_obs; ++i) {
+      if (obs_cam[i] < 0 || obs_cam[i] >= n_cams) { g_last_error = "cb_triangulate_dlt: camera index out of range"; return CB_E_INVALID; }
+      if (obs_key[i] < 0) { g_last_error = "cb_triangulate_dlt: negative group key"; return CB_E_INVALID; }
+    }
+  cudaEvent_t ev[4];
+  for (auto& e : ev) CB_CUDA(cudaEventCreate(&e));
+  struct EvGuard { cudaEvent_t* e; ~EvGuard() { for (int i = 0; i < 4; ++i) cudaEventDestroy(e[i]); } } evg{ev};
+  CB_CUDA(cudaEventRecord(ev[0], st));
+
+  const int* d_cam = nullptr;
+  const long long* d_key = nullptr;
+  const double* d_xy = nullptr;
+  CB_TRY(to_device(obs_cam, (size_t)n, obs_on_device, &d_cam, sf, st));
+  CB_TRY(to_device((const long long*)obs_key, (size_t)n, obs_on_device, &d_key, sf, st));
+  CB_TRY(to_device(obs_xy, 2 * (size_t)n, obs_on_device, &d_xy, sf, st));
+  if (undist) {
+    cb::UndistCam* d_tab = nullptr;
+    CB_TRY(dalloc(&d_tab, (size_t)n_cams));
+    sf.dev.push_back(d_tab);
+    CB_CUDA(cudaMemcpyAsync(d_tab, undist->data(), sizeof(cb::UndistCam) * n_cams, cudaMemcpyHostToDevice, st));
+    double* d_und = nullptr;
+    CB_TRY(dalloc(&d_und, 2 * (size_t)n));
+    sf.dev.push_back(d_und);
+    CB_LAUNCH(cb::undistort_kernel, G, TB, 0, st, d_tab, d_cam, d_xy, d_und, (long long)n, 0);
+    d_xy = d_und;
+  }
+  double* d_proj = nullptr;
+  CB_TRY(dalloc(&d_proj, 12 * (size_t)n_cams));
+  sf.dev.push_back(d_proj);
+  CB_CUDA(cudaMemcpyAsync(d_proj, proj, sizeof(double) * 12 * (size_t)n_cams, cudaMemcpyHostToDevice, st));
+
+  // (1) stable radix sort of (key, row) -> rows of one group adjacent, in caller order inside the group
+  unsigned long long* k_out = nullptr;
+  int *v_in = nullptr, *v_out = nullptr, *d_head = nullptr, *d_gid = nullptr, *d_start = nullptr;
+  CB_TRY(dalloc(&k_out, (size_t)n)); sf.dev.push_back(k_out);
+  CB_TRY(dalloc(&v_in, (size_t)n)); sf.dev.push_back(v_in);
+  CB_TRY(dalloc(&v_out, (size_t)n)); sf.dev.push_back(v_out);
+  CB_TRY(dalloc(&d_head, (size_t)n)); sf.dev.push_back(d_head);
+  CB_TRY(dalloc(&d_gid, (size_t)n)); sf.dev.push_back(d_gid);
+  CB_TRY(dalloc(&d_start, (size_t)n + 1)); sf.dev.push_back(d_start);
+  size_t tb_sort = 0, tb_scan = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb_sort, (const unsigned long long*)d_key, k_out, v_in, v_out, n, 0, 64, st);
+  cub::DeviceScan::InclusiveSum(nullptr, tb_scan, d_head, d_gid, n, st);
+  void* d_tmp = nullptr;
+  CB_TRY(cached_malloc(&d_tmp, std::max<size_t>(std::max(tb_sort, tb_scan), 16)));
+  sf.dev.push_back(d_tmp);
+  size_t tb = std::max(tb_sort, tb_scan);
+  CB_LAUNCH(cb::tri_iota_kernel, G, TB, 0, st, v_in, (long long)n);
+  CB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb, (const unsigned long long*)d_key, k_out, v_in, v_out, n, 0, 63, st));
+  g_launches.fetch_add(8);
+  // (2) group boundaries
+  CB_LAUNCH(cb::tri_heads_kernel, G, TB, 0, st, k_out, (long long)n, d_head);
+  CB_CUDA(cub::DeviceScan::InclusiveSum(d_tmp, tb, d_head, d_gid, n, st));
+  g_launches.fetch_add(2);
+  CB_LAUNCH(cb::tri_starts_kernel, G, TB, 0, st, d_head, d_gid, (long long)n, d_start);
+  int n_groups = 0;
+  CB_CUDA(cudaMemcpyAsync(&n_groups, d_gid + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaEventRecord(ev[1], st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  *n_groups_out = n_groups;
+  if (n_groups > max_groups) {
+    g_last_error = "cb_triangulate_dlt: " + std::to_string(n_groups) + " groups but room for " + std::to_string(max_groups);
+    return CB_E_INVALID;
+  }
+  // (3) DLT per group
+  double* d_xyz = nullptr;
+  int *d_count = nullptr, *d_rep = nullptr;
+  unsigned long long* d_sig = nullptr;
+  CB_TRY(dalloc(&d_xyz, 3 * (size_t)n_groups)); sf.dev.push_back(d_xyz);
+  CB_TRY(dalloc(&d_count, (size_t)n_groups)); sf.dev.push_back(d_count);
+  CB_TRY(dalloc(&d_rep, (size_t)n_groups)); sf.dev.push_back(d_rep);
+  CB_TRY(dalloc(&d_sig, 2 * (size_t)n_groups)); sf.dev.push_back(d_sig);
+  const size_t proj_bytes = sizeof(double) * 12 * (size_t)n_cams;
+  const int in_smem = proj_bytes <= 40 * 1024 ? 1 : 0;
+  const int lanes = (n / std::max(n_groups, 1) > 16) ? 32 : 8;
+  const long long threads = (long long)n_groups * lanes;
+  CB_CUDA(cudaEventRecord(ev[2], st));
+  if (lanes == 32)
+    CB_LAUNCH(cb::tri_dlt_kernel<32>, cdiv(threads, cb::TRI_THREADS), cb::TRI_THREADS, in_smem ? proj_bytes : 0, st,
+              d_proj, n_cams, in_smem, d_start, v_out, d_cam, d_xy, n_groups, d_xyz, d_count, d_rep, d_sig);
+  else
+    CB_LAUNCH(cb::tri_dlt_kernel<8>, cdiv(threads, cb::TRI_THREADS), cb::TRI_THREADS, in_smem ? proj_bytes : 0, st,
+              d_proj, n_cams, in_smem, d_start, v_out, d_cam, d_xy, n_groups, d_xyz, d_count, d_rep, d_sig);
+  CB_CUDA(cudaGetLastError());
+  CB_CUDA(cudaEventRecord(ev[3], st));
+  CB_CUDA(cudaMemcpyAsync(xyz_out, d_xyz, sizeof(double) * 3 * (size_t)n_groups, cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaMemcpyAsync(count_out, d_count, sizeof(int) * (size_t)n_groups, cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaMemcpyAsync(rep_row_out, d_rep, sizeof(int) * (size_t)n_groups, cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaMemcpyAsync(camset_sig_out, d_sig, sizeof(unsigned long long) * 2 * (size_t)n_groups,
+                          cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  if (stats) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev[0], ev[1]); stats->group_ms = ms;
+    cudaEventElapsedTime(&ms, ev[2], ev[3]); stats->dlt_ms = ms;
+    cudaEventElapsedTime(&ms, ev[0], ev[3]); stats->total_ms = ms;
+    stats->kernel_launches = (int)(g_launches.load() - launches0);
+  }
+  return CB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cb_triangulate_dlt(int32_t n_cams, const double* proj, int64_t n_obs, const int32_t* obs_cam,
+                       const int64_t* obs_key, const double* obs_xy, int obs_on_device, int32_t max_groups,
+                       int32_t* n_groups_out, double* xyz_out, int32_t* count_out, int32_t* rep_row_out,
+                       uint64_t* camset_sig_out, CbTriStats* stats, int device, void* stream) {
+  return triangulate_impl(n_cams, nullptr, proj, n_obs, obs_cam, obs_key, obs_xy, obs_on_device, max_groups,
+                          n_groups_out, xyz_out, count_out, rep_row_out, camset_sig_out, stats, device, stream);
+}
+
+int cb_undistort_triangulate(int32_t n_cams, const int32_t* cam_fisheye, const double* cam_k, const double* cam_dist,
+                             const double* proj, int64_t n_obs, const int32_t* obs_cam, const int64_t* obs_key,
+                             const double* obs_px, int obs_on_device, int32_t max_groups, int32_t* n_groups_out,
+                             double* xyz_out, int32_t* count_out, int32_t* rep_row_out, uint64_t* camset_sig_out,
+                             CbTriStats* stats, int device, void* stream) {
+  if (n_cams <= 0 || !cam_fisheye || !cam_k || !cam_dist) {
+    g_last_error = "cb_undistort_triangulate: bad argument";
+    return CB_E_INVALID;
+  }
+  std::vector<cb::UndistCam> tab;
+  CB_TRY(build_undist_table(n_cams, cam_fisheye, cam_k, cam_dist, tab));
+  return triangulate_impl(n_cams, &tab, proj, n_obs, obs_cam, obs_key, obs_px, obs_on_device, max_groups, n_groups_out,
+                          xyz_out, count_out, rep_row_out, camset_sig_out, stats, device, stream);
 }
 
 }  // extern "C"

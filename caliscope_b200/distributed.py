@@ -176,6 +176,75 @@ def make_allreduce_hook(group=None, device_buffers: bool = True):
     return hook
 
 
+class EngineNcclComm:
+    """An NCCL communicator owned by the engine: ``cb_ba_solve`` issues ``ncclAllReduce`` on its own
+    stream, with no Python in the loop.  torch.distributed only carries the 128-byte unique id
+    (``cb_nccl_unique_id`` on rank 0 -> broadcast -> ``cb_nccl_comm_create`` on every rank)."""
+
+    def __init__(self, device: int, group=None):
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib as L
+
+        self._lib = L.load()
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        uid = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{device}")
+        if rank == 0:
+            buf = (C.c_char * 128)()
+            L.check(self._lib.cb_nccl_unique_id(buf), "nccl_unique_id")
+            uid.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
+        dist.broadcast(uid, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        raw = bytes(uid.cpu().numpy().tobytes())
+        h = C.c_void_p()
+        L.check(self._lib.cb_nccl_comm_create(raw, rank, world, int(device), C.byref(h)), "nccl_comm_create")
+        self.handle = h.value
+        self.rank, self.world_size = rank, world
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.cb_nccl_comm_destroy(C.c_void_p(self.handle))
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_COMMS: dict = {}
+
+
+def engine_comm(device: int, group=None) -> EngineNcclComm:
+    """Per-(device, group) cached communicator (creation is a collective: all ranks call it together)."""
+    key = (int(device), id(group))
+    c = _COMMS.get(key)
+    if c is None or c.handle is None:
+        c = _COMMS[key] = EngineNcclComm(device, group)
+    return c
+
+
+def close_comms() -> None:
+    """Destroy every cached engine communicator (call before ``dist.destroy_process_group``)."""
+    for c in list(_COMMS.values()):
+        c.close()
+    _COMMS.clear()
+
+
+def transport_kwargs(device: int, group=None) -> dict:
+    """``solve(...)`` keyword arguments selecting the all-reduce transport: the engine's own NCCL
+    communicator on an NCCL process group (``CB_ALLREDUCE=torch`` forces the callback), the
+    torch.distributed callback otherwise (gloo CPU tests use ``make_allreduce_hook`` directly)."""
+    import os
+
+    import torch.distributed as dist
+
+    if dist.get_backend(group) == "nccl" and os.environ.get("CB_ALLREDUCE", "nccl") != "torch":
+        return {"nccl_comm": engine_comm(device, group)}
+    return {"allreduce": make_allreduce_hook(group)}
+
+
 def gather_points(x_local: np.ndarray, n_camera_params: int, n_pts_global: int, shard: PointShard, group=None) -> np.ndarray:
     """Every rank returns the full parameter vector (cameras are already identical on all ranks)."""
     import torch
@@ -214,9 +283,9 @@ def solve_sharded(cam_flags, cam_const, n_pts, obs_cam, obs_pt, obs_xy, x0, *, d
                    constraints=shard.constraints, device=device) as prob:
         res = prob.solve(
             local_x(np.asarray(x0, dtype=np.float64), ncp, shard),
-            allreduce=make_allreduce_hook(group),
             rank=rank,
             world_size=world,
+            **transport_kwargs(device, group),
             **solve_kw,
         )
     res.x = gather_points(res.x, ncp, n_pts, shard, group)

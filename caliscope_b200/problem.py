@@ -284,6 +284,7 @@ class BAProblem:
         lambda0: float = 1e-4,
         pcg_tol: float = 1e-6,
         allreduce=None,
+        nccl_comm=None,
         rank: int = 0,
         world_size: int = 1,
         stream: int = 0,
@@ -305,6 +306,8 @@ class BAProblem:
         if allreduce is not None:
             cb = L.ALLREDUCE_FN(allreduce)
             opt.allreduce = cb
+        if nccl_comm is not None:
+            opt.nccl_comm = C.c_void_p(getattr(nccl_comm, "handle", nccl_comm))
         opt.rank, opt.world_size = int(rank), int(world_size)
         res = L.Result()
         L.check(self._lib.cb_ba_solve(self._h, C.byref(opt), _ptr(x), C.byref(res), C.c_void_p(stream)), "solve")

@@ -19,6 +19,7 @@ from . import solver
 _TARGET = "caliscope.core.capture_volume"
 _original = None
 _original_methods: dict = {}
+_original_functions: dict = {}
 
 
 def install(fallback=None, full: bool = False) -> None:
@@ -28,7 +29,9 @@ def install(fallback=None, full: bool = False) -> None:
     not implement (distance-constraint rows).  Default ``None`` = raise ``NotImplementedError``.
     ``full=True`` additionally installs seam S2: ``CaptureVolume.optimize`` and
     ``CaptureVolume._compute_img_to_obj_map`` are replaced by the vectorised versions in
-    ``caliscope_b200.capture_volume`` (same signatures and results, no per-row Python loops)."""
+    ``caliscope_b200.capture_volume`` (same signatures and results, no per-row Python loops), and seam
+    S3: ``caliscope.core.point_data.triangulate_image_points`` (the DLT triangulation
+    ``ImagePoints.triangulate`` calls, point_data.py:474,509) becomes the GPU version."""
     global _original
     from . import _lib
 
@@ -46,6 +49,12 @@ def install(fallback=None, full: bool = False) -> None:
             _original_methods.update(optimize=cls.optimize, _compute_img_to_obj_map=cls._compute_img_to_obj_map)
         cls.optimize = cv2b.optimize
         cls._compute_img_to_obj_map = cv2b.fast_img_to_obj_map
+        from . import triangulation
+
+        pd_mod = importlib.import_module("caliscope.core.point_data")
+        if "triangulate_image_points" not in _original_functions:
+            _original_functions["triangulate_image_points"] = pd_mod.triangulate_image_points
+        pd_mod.triangulate_image_points = triangulation.triangulate_image_points
 
 
 def uninstall() -> None:
@@ -58,6 +67,11 @@ def uninstall() -> None:
         for name, fn in _original_methods.items():
             setattr(mod.CaptureVolume, name, fn)
         _original_methods.clear()
+    if _original_functions:
+        pd_mod = importlib.import_module("caliscope.core.point_data")
+        for name, fn in _original_functions.items():
+            setattr(pd_mod, name, fn)
+        _original_functions.clear()
     solver._fallback = None
 
 

@@ -187,3 +187,19 @@ def cfg4(seed: int = 0, refine_intrinsics: bool = False) -> SyntheticRig:
 def cfg5(seed: int = 0) -> SyntheticRig:
     return make_rig(64, 50_000, 2_000_000, seed=seed, outlier_frac=0.02,
                     name="cfg5 64-cam/50k-pt/2M-obs + 2% outliers (filter + re-solve loop)")  # fmt: skip
+
+
+def exact_normalized_observations(rig: SyntheticRig):
+    """Inputs of the triangulation step for a rig: normalised projection matrices ``[R|t]`` of the TRUE
+    poses, (n_cams,3,4), and the exact normalised image coordinates ``(Xc.x/Xc.z, Xc.y/Xc.z)`` of every
+    observation row (what undistortion of noise-free pixels would give)."""
+    P = np.where(rig.cam_flags & 1, 9, 6)
+    off = np.concatenate([[0], np.cumsum(P)])
+    proj = np.empty((rig.n_cams, 3, 4))
+    for c in range(rig.n_cams):
+        blk = rig.x_true[off[c] : off[c] + 6]
+        proj[c, :, :3] = _rot(blk[:3])
+        proj[c, :, 3] = blk[3:6]
+    X = rig.x_true[off[-1] :].reshape(-1, 3)
+    Xc = np.einsum("nij,nj->ni", proj[rig.obs_cam, :, :3], X[rig.obs_pt]) + proj[rig.obs_cam, :, 3]
+    return proj, np.ascontiguousarray(Xc[:, :2] / Xc[:, 2:3])

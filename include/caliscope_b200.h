@@ -99,8 +99,9 @@ typedef struct {
   double lambda0;      /* initial LM damping; <= 0: 1e-4 */
   double pcg_tol;      /* relative PCG tolerance for the reduced camera system; <= 0: 1e-6 */
   int32_t pcg_max_iter; /* <= 0: 4 * n_camera_params */
-  CbAllReduceSum allreduce; /* NULL: single GPU */
+  CbAllReduceSum allreduce; /* NULL: single GPU (unless nccl_comm is set) */
   void* allreduce_user;
+  void* nccl_comm;          /* ncclComm_t from cb_nccl_comm_create: the engine calls ncclAllReduce itself on the solve stream */
   int32_t rank;       /* informational (verbose output only on rank 0) */
   int32_t world_size; /* 1 if allreduce is NULL */
 } CbBaOptions;
@@ -191,6 +192,54 @@ int cb_ba_cull(CbBaProblem* p, const double* x, const double* thresholds, int32_
 /* Diagnostic: mean milliseconds of one PCG-kernel launch forced to run exactly max_iter iterations on the
  * system left by the last cb_ba_normal_equations call. */
 int cb_ba_debug_pcg_time(CbBaProblem* p, int max_iter, int reps, double* ms_per_launch, void* stream);
+
+/* ---- the step in front of bundle adjustment ------------------------------------------- */
+
+/* == CameraData.undistort_points (reference cameras/camera_array.py:135-174): cv2.undistortPoints (5 fixed-point
+ * iterations) / cv2.fisheye.undistortPoints (Newton on theta) on float32 copies of the points, float32 results,
+ * here for the observations of all cameras in one launch.
+ *   cam_fisheye[n_cams]; cam_k[n_cams][5] = fx,fy,cx,cy,skew; cam_dist[n_cams][12] = k1 k2 p1 p2 k3 k4 k5 k6 s1..s4
+ *   (zero-padded; fisheye: k1..k4); obs_cam[n] camera row per point (NULL with a single camera);
+ *   to_pixels: 0 = normalised image plane (P = I), 1 = pixels (P = K).
+ *   on_device: xy_in / obs_cam / xy_out are device pointers. */
+int cb_undistort_points(int32_t n_cams, const int32_t* cam_fisheye, const double* cam_k, const double* cam_dist,
+                        int64_t n, const int32_t* obs_cam, const double* xy_in, int on_device, int to_pixels,
+                        double* xy_out, int device, void* stream);
+
+typedef struct CbTriStats {
+  double group_ms;  /* upload + radix sort + group boundaries */
+  double dlt_ms;    /* the DLT kernel alone (CUDA events on the launch stream) */
+  double total_ms;
+  int32_t kernel_launches;
+  int32_t pad_;
+} CbTriStats;
+
+/* == triangulate_image_points (reference core/point_data.py:122-229).  Observations with equal obs_key (a
+ * non-negative 63-bit packing of (sync_index, object_id, keypoint_id) made by the caller) form one group; every
+ * group gets the DLT point of its rows  [x*P2 - P0 ; y*P2 - P1]  (smallest right singular vector, via the 4x4 normal
+ * matrix), groups in ascending key order.  proj = host [n_cams][3][4] normalised projection matrices.
+ * Outputs (host, room for max_groups): xyz[g][3] (NaN when the group has < 2 rows), count[g], rep_row[g] = caller
+ * row of the group's first observation, camset_sig[g][2] = order-independent 128-bit signature of the group's
+ * camera multiset (lets the host mirror reproduce the reference's by-camera-set output order). */
+int cb_triangulate_dlt(int32_t n_cams, const double* proj, int64_t n_obs, const int32_t* obs_cam,
+                       const int64_t* obs_key, const double* obs_xy, int obs_on_device, int32_t max_groups,
+                       int32_t* n_groups_out, double* xyz_out, int32_t* count_out, int32_t* rep_row_out,
+                       uint64_t* camset_sig_out, CbTriStats* stats, int device, void* stream);
+
+/* cb_undistort_points (normalised output) + cb_triangulate_dlt in one call: obs_px are raw pixels, the undistorted
+ * coordinates stay in HBM between the two kernels (what ImagePoints.triangulate does, point_data.py:416-559). */
+int cb_undistort_triangulate(int32_t n_cams, const int32_t* cam_fisheye, const double* cam_k, const double* cam_dist,
+                             const double* proj, int64_t n_obs, const int32_t* obs_cam, const int64_t* obs_key,
+                             const double* obs_px, int obs_on_device, int32_t max_groups, int32_t* n_groups_out,
+                             double* xyz_out, int32_t* count_out, int32_t* rep_row_out, uint64_t* camset_sig_out,
+                             CbTriStats* stats, int device, void* stream);
+
+/* Optional NCCL transport owned by the engine (no host callback per all-reduce).  NCCL is resolved at run time from
+ * the libnccl the process already has loaded (PyTorch's).  Rank 0 calls cb_nccl_unique_id and distributes the 128
+ * bytes (e.g. torch.distributed.broadcast); every rank then calls cb_nccl_comm_create (collective). */
+int cb_nccl_unique_id(char id_out[128]);
+int cb_nccl_comm_create(const char id[128], int rank, int world_size, int device, void** comm_out);
+int cb_nccl_comm_destroy(void* comm);
 
 /* Number of kernel launches issued by this library in the calling process so far. */
 int64_t cb_ba_launch_count(void);

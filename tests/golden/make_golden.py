@@ -289,9 +289,107 @@ def projection_case():
     }  # fmt: skip
 
 
+def triangulation_case():
+    """The step in front of bundle adjustment: ``triangulate_image_points`` (point_data.py:122-229) and
+    ``CameraData.undistort_points`` (camera_array.py:135-174), called as the reference calls them.
+
+    (1) session4: ``ImagePoints.triangulate(camera_array)`` end to end with the array-level call
+        recorded (arguments and return value);
+    (2) a seeded synthetic case with singleton groups, repeated cameras inside a group (static
+        objects), unsorted rows, sparse camera ids and negative sync indices;
+    (3) undistortion of a pixel grid + random points for a pinhole and a fisheye camera, both outputs.
+    """
+    import caliscope.core.point_data as pd_mod
+
+    out: dict = {}
+    # (1)
+    p = REF / "tests/sessions/post_optimization"
+    ca = CameraArray.from_toml(p / "camera_array.toml")
+    ip = ImagePoints.from_csv(p / "calibration/extrinsic/CHARUCO/xy_CHARUCO.csv")
+    rec: dict = {}
+    orig = pd_mod.triangulate_image_points
+
+    def recording(pm, sync, cam, obj, kp, xy):
+        res = orig(pm, sync, cam, obj, kp, xy)
+        rec.update(pm=pm, sync=sync, cam=cam, obj=obj, kp=kp, xy=xy, res=res)
+        return res
+
+    pd_mod.triangulate_image_points = recording
+    try:
+        wp = ip.triangulate(ca)
+    finally:
+        pd_mod.triangulate_image_points = orig
+    ids = np.array(sorted(rec["pm"]), dtype=np.int64)
+    out.update(
+        s4_cam_ids=ids, s4_proj=np.stack([rec["pm"][int(c)] for c in ids]), s4_sync=rec["sync"], s4_cam=rec["cam"],
+        s4_obj=rec["obj"], s4_kp=rec["kp"], s4_xy=rec["xy"], s4_out_sync=rec["res"][0], s4_out_obj=rec["res"][1],
+        s4_out_kp=rec["res"][2], s4_out_xyz=rec["res"][3], s4_world_xyz=wp.points,
+    )  # fmt: skip
+    # raw pixels of the same rows and what the reference's per-camera undistortion made of them
+    df = ip.df
+    posed = list(ca.posed_cam_id_to_index.keys())
+    df = df[df["cam_id"].isin(posed)]
+    und = pd_mod._undistort_batch(df, ca)
+    out.update(
+        s4_px=und[["img_loc_x", "img_loc_y"]].to_numpy(np.float64), s4_px_cam=und["cam_id"].to_numpy(np.int64),
+        s4_px_undist=und[["img_loc_undistort_x", "img_loc_undistort_y"]].to_numpy(np.float64),
+        s4_K=np.stack([ca.cameras[int(c)].matrix for c in ids]),
+        s4_dist=np.stack([np.asarray(ca.cameras[int(c)].distortions, np.float64).ravel() for c in ids]),
+    )  # fmt: skip
+    # (2)
+    rng = np.random.default_rng(11)
+    cam_ids = np.array([1, 3, 4, 8, 15, 16, 23], dtype=np.int64)
+    pm = {}
+    for c in cam_ids:
+        R = cv2.Rodrigues(rng.normal(0, 0.4, 3))[0]
+        t = np.array([0.0, 0.0, 3.0]) + rng.normal(0, 0.3, 3)
+        pm[int(c)] = np.hstack([R, t[:, None]])
+    rows = []
+    for j in range(400):
+        X = rng.uniform(-0.5, 0.5, 3)
+        sync = int(j // 20) - 3
+        k = int(rng.integers(1, 8))
+        cams = rng.choice(cam_ids, size=k, replace=(j % 9 == 0))
+        for c in cams:
+            h = pm[int(c)] @ np.append(X, 1.0)
+            rows.append((sync, int(c), j % 4, j % 20, *(h[:2] / h[2] + rng.normal(0, 2e-3, 2))))
+    rows = np.array(rows)
+    rng.shuffle(rows)
+    a = (rows[:, 0].astype(np.int64), rows[:, 1].astype(np.int64), rows[:, 2].astype(np.int64), rows[:, 3].astype(np.int64),
+         np.ascontiguousarray(rows[:, 4:6]))  # fmt: skip
+    res = orig(pm, *a)
+    out.update(
+        syn_cam_ids=cam_ids, syn_proj=np.stack([pm[int(c)] for c in cam_ids]), syn_sync=a[0], syn_cam=a[1], syn_obj=a[2],
+        syn_kp=a[3], syn_xy=a[4], syn_out_sync=res[0], syn_out_obj=res[1], syn_out_kp=res[2], syn_out_xyz=res[3],
+    )  # fmt: skip
+    # (3)
+    gx, gy = np.meshgrid(np.linspace(0, 1920, 33), np.linspace(0, 1080, 19))
+    pts = np.vstack([np.stack([gx.ravel(), gy.ravel()], 1), rng.uniform([0, 0], [1920, 1080], (3000, 2))])
+    Kp = np.array([[1394.6, 0, 960.0], [0, 1380.1, 540.0], [0, 0, 1]])
+    d5 = np.array([0.115, -0.219, 0.0012, 0.0086, 0.113])
+    Kf = np.array([[600.0, 0, 955.0], [0, 605.0, 545.0], [0, 0, 1]])
+    d4 = np.array([0.05, -0.01, 0.003, -0.0005])
+    cp = CameraData(cam_id=0, size=(1920, 1080), matrix=Kp, distortions=d5)
+    cf = CameraData(cam_id=1, size=(1920, 1080), fisheye=True, matrix=Kf, distortions=d4)
+    out.update(
+        und_pts=pts, und_Kp=Kp, und_d5=d5, und_Kf=Kf, und_d4=d4,
+        und_pinhole_norm=cp.undistort_points(pts, output="normalized").astype(np.float64),
+        und_pinhole_px=cp.undistort_points(pts, output="pixels").astype(np.float64),
+        und_fisheye_norm=cf.undistort_points(pts, output="normalized").astype(np.float64),
+        und_fisheye_px=cf.undistort_points(pts, output="pixels").astype(np.float64),
+    )  # fmt: skip
+    return out
+
+
 def main() -> None:
     np.set_printoptions(precision=12)
     out_dir = HERE
+
+    tri = triangulation_case()
+    np.savez_compressed(out_dir / "triangulation.npz", **tri)
+    print("triangulation", len(tri["s4_out_xyz"]), "session points,", len(tri["syn_out_xyz"]), "synthetic points")
+    if "--only-triangulation" in sys.argv:
+        return
 
     cv = session4()
     for refine in (False, True):

@@ -26,12 +26,13 @@ def _free_port() -> int:
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out, refine):
+def _worker(rank, world, port, out, refine, transport="nccl"):
     import torch
     import torch.distributed as dist
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ["CB_ALLREDUCE"] = transport
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
@@ -46,12 +47,19 @@ def _worker(rank, world, port, out, refine):
 
         out.put((rank, "err: " + repr(e) + traceback.format_exc(), None, None, None, None))
     finally:
-        dist.destroy_process_group()
+        try:
+            from caliscope_b200 import distributed as D
+
+            D.close_comms()
+        finally:
+            dist.destroy_process_group()
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("refine", [False, True])
-def test_two_gpu_sharded_solve_matches_single_gpu(refine):
+@pytest.mark.parametrize("refine,transport", [(False, "nccl"), (True, "nccl"), (False, "torch")])
+def test_two_gpu_sharded_solve_matches_single_gpu(refine, transport):
+    """transport "nccl": the engine's own communicator (ncclAllReduce issued from cb_ba_solve);
+    "torch": the CbAllReduceSum callback over torch.distributed."""
     import torch.multiprocessing as mp
 
     import caliscope_b200 as cb
@@ -64,7 +72,7 @@ def test_two_gpu_sharded_solve_matches_single_gpu(refine):
         ctx = mp.get_context("spawn")
         out = ctx.Queue()
         port = _free_port()
-        procs = [ctx.Process(target=_worker, args=(k, 2, port, out, refine)) for k in range(2)]
+        procs = [ctx.Process(target=_worker, args=(k, 2, port, out, refine, transport)) for k in range(2)]
         for q in procs:
             q.start()
         results = sorted([out.get(timeout=600) for _ in procs], key=lambda t: t[0])
@@ -101,7 +109,12 @@ def _worker_constraints(rank, world, port, out):
 
         out.put((rank, "err: " + repr(e) + traceback.format_exc(), None, None, None, None))
     finally:
-        dist.destroy_process_group()
+        try:
+            from caliscope_b200 import distributed as D
+
+            D.close_comms()
+        finally:
+            dist.destroy_process_group()
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")

@@ -127,7 +127,7 @@ def test_shared_library_exports_every_declared_symbol():
     from caliscope_b200 import _lib
 
     header = (ROOT / "include" / "caliscope_b200.h").read_text()
-    declared = set(re.findall(r"\b(cb_ba_[a-z_0-9]+)\s*\(", header))
+    declared = set(re.findall(r"\b(cb_[a-z_0-9]+)\s*\(", header))
     assert declared, "header parse failed"
     assert declared == set(_lib.SYMBOLS), f"binding table out of sync: {declared ^ set(_lib.SYMBOLS)}"
     lib = _lib.load()

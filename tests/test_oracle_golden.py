@@ -144,3 +144,41 @@ def test_rotation_derivative_identity():
             d[k] = 1e-6
             fd[:, k] = (O.rodrigues(r + d)[0] @ X - O.rodrigues(r - d)[0] @ X) / 2e-6
         assert np.abs(A - fd).max() < 1e-8
+
+
+# ---- the step in front of bundle adjustment: undistortion + DLT triangulation ----
+def _tri_golden(golden_dir):
+    return np.load(golden_dir / "triangulation.npz")
+
+
+@pytest.mark.parametrize("case", ["s4", "syn"])
+def test_triangulation_oracle_matches_reference(golden_dir, case):
+    """oracle.triangulation.triangulate_image_points == the reference function (point_data.py:122-229):
+    same keys in the same order, xyz to rounding."""
+    from oracle import triangulation as T
+
+    g = _tri_golden(golden_dir)
+    pm = {int(c): g[f"{case}_proj"][i] for i, c in enumerate(g[f"{case}_cam_ids"])}
+    s, o, k, xyz = T.triangulate_image_points(pm, g[f"{case}_sync"], g[f"{case}_cam"], g[f"{case}_obj"], g[f"{case}_kp"],
+                                              g[f"{case}_xy"])  # fmt: skip
+    assert np.array_equal(s, g[f"{case}_out_sync"])
+    assert np.array_equal(o, g[f"{case}_out_obj"])
+    assert np.array_equal(k, g[f"{case}_out_kp"])
+    assert np.abs(xyz - g[f"{case}_out_xyz"]).max() < 1e-10
+
+
+def test_undistort_oracle_is_bit_exact_against_cv2(golden_dir):
+    """oracle.triangulation.undistort_points == CameraData.undistort_points (camera_array.py:135-174)."""
+    from oracle import triangulation as T
+
+    g = _tri_golden(golden_dir)
+    pts = g["und_pts"]
+    assert np.array_equal(T.undistort_points(pts, g["und_Kp"], g["und_d5"], False, "normalized"), g["und_pinhole_norm"])
+    assert np.array_equal(T.undistort_points(pts, g["und_Kp"], g["und_d5"], False, "pixels"), g["und_pinhole_px"])
+    assert np.array_equal(T.undistort_points(pts, g["und_Kf"], g["und_d4"], True, "normalized"), g["und_fisheye_norm"])
+    assert np.array_equal(T.undistort_points(pts, g["und_Kf"], g["und_d4"], True, "pixels"), g["und_fisheye_px"])
+    # session rows, camera by camera, as _undistort_batch does (point_data.py:236-252)
+    for i, c in enumerate(g["s4_cam_ids"]):
+        m = g["s4_px_cam"] == c
+        got = T.undistort_points(g["s4_px"][m], g["s4_K"][i], g["s4_dist"][i], False, "normalized")
+        assert np.array_equal(got, g["s4_px_undist"][m])
