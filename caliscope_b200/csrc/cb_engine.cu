@@ -1590,9 +1590,48 @@ int to_device(const T* src, size_t n, int on_device, const T** out, ScopedFree& 
   T* h = nullptr;
   CB_TRY(cached_malloc_host((void**)&h, sizeof(T) * std::max<size_t>(n, 1)));
   sf.host.push_back(h);
-  std::memcpy(h, src, sizeof(T) * n);
-  CB_CUDA(cudaMemcpyAsync(d, h, sizeof(T) * n, cudaMemcpyHostToDevice, st));
+  // chunked so the DMA of one chunk overlaps the host memcpy of the next
+  const size_t bytes = sizeof(T) * n, chunk = (size_t)4 << 20;
+  for (size_t off = 0; off < bytes; off += chunk) {
+    const size_t sz = std::min(chunk, bytes - off);
+    std::memcpy((char*)h + off, (const char*)src + off, sz);
+    CB_CUDA(cudaMemcpyAsync((char*)d + off, (char*)h + off, sz, cudaMemcpyHostToDevice, st));
+  }
   *out = d;
+  return CB_OK;
+}
+
+// host doubles -> device floats, converted while staging into the pinned bounce buffer
+int to_device_f32(const double* src, size_t n, const float** out, ScopedFree& sf, cudaStream_t st) {
+  float* d = nullptr;
+  CB_TRY(dalloc(&d, n));
+  sf.dev.push_back(d);
+  float* h = nullptr;
+  CB_TRY(cached_malloc_host((void**)&h, sizeof(float) * std::max<size_t>(n, 1)));
+  sf.host.push_back(h);
+  const size_t chunk = (size_t)1 << 20;  // elements
+  for (size_t off = 0; off < n; off += chunk) {
+    const size_t m = std::min(chunk, n - off);
+    for (size_t i = 0; i < m; ++i) h[off + i] = (float)src[off + i];
+    CB_CUDA(cudaMemcpyAsync(d + off, h + off, sizeof(float) * m, cudaMemcpyHostToDevice, st));
+  }
+  *out = d;
+  return CB_OK;
+}
+
+int validate_rows(const int* d_cam, const long long* d_key, long long n, int n_cams, cudaStream_t st, const char* who) {
+  int* d_bad = nullptr;
+  CB_TRY(dalloc(&d_bad, 1));
+  CB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+  CB_LAUNCH(cb::tri_validate_kernel, cdiv(n, 256), 256, 0, st, d_cam, d_key, n, n_cams, d_bad);
+  int bad = 0;
+  CB_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  cached_free(d_bad);
+  if (bad) {
+    g_last_error = std::string(who) + ": camera index out of range or negative group key in " + std::to_string(bad) + " rows";
+    return CB_E_INVALID;
+  }
   return CB_OK;
 }
 
@@ -1610,9 +1649,6 @@ int cb_undistort_points(int32_t n_cams, const int32_t* cam_fisheye, const double
   if (n_cams > 1 && !obs_cam) { g_last_error = "cb_undistort_points: obs_cam is required with more than one camera"; return CB_E_INVALID; }
   CB_TRY(select_device(device));
   if (n == 0) return CB_OK;
-  if (!on_device && obs_cam)
-    for (int64_t i = 0; i < n; ++i)
-      if (obs_cam[i] < 0 || obs_cam[i] >= n_cams) { g_last_error = "cb_undistort_points: camera index out of range"; return CB_E_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
   ScopedFree sf;
   std::vector<cb::UndistCam> tab;
@@ -1633,7 +1669,9 @@ int cb_undistort_points(int32_t n_cams, const int32_t* cam_fisheye, const double
     CB_TRY(cached_malloc_host((void**)&h_out, sizeof(double) * 2 * (size_t)n));
     sf.host.push_back(h_out);
   }
-  CB_LAUNCH(cb::undistort_kernel, cdiv(n, 256), 256, 0, st, d_tab, d_cam, d_in, d_out, (long long)n, to_pixels ? 1 : 0);
+  if (d_cam) CB_TRY(validate_rows(d_cam, nullptr, n, n_cams, st, "cb_undistort_points"));
+  CB_LAUNCH(cb::undistort_kernel<double>, cdiv(n, 256), 256, 0, st, d_tab, d_cam, d_in, d_out, (long long)n,
+            to_pixels ? 1 : 0);
   CB_CUDA(cudaGetLastError());
   if (!on_device) {
     CB_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost, st));
@@ -1670,11 +1708,6 @@ int triangulate_impl(int32_t n_cams, const std::vector<cb::UndistCam>* undist, c
   ScopedFree sf;
   const int n = (int)n_obs;
   const int TB = 256, G = cdiv(n, TB);
-  if (!obs_on_device)
-    for (int64_t i = 0; i < n_obs; ++i) {
-      if (obs_cam[i] < 0 || obs_cam[i] >= n_cams) { g_last_error = "cb_triangulate_dlt: camera index out of range"; return CB_E_INVALID; }
-      if (obs_key[i] < 0) { g_last_error = "cb_triangulate_dlt: negative group key"; return CB_E_INVALID; }
-    }
   cudaEvent_t ev[4];
   for (auto& e : ev) CB_CUDA(cudaEventCreate(&e));
   struct EvGuard { cudaEvent_t* e; ~EvGuard() { for (int i = 0; i < 4; ++i) cudaEventDestroy(e[i]); } } evg{ev};
@@ -1685,7 +1718,7 @@ int triangulate_impl(int32_t n_cams, const std::vector<cb::UndistCam>* undist, c
   const double* d_xy = nullptr;
   CB_TRY(to_device(obs_cam, (size_t)n, obs_on_device, &d_cam, sf, st));
   CB_TRY(to_device((const long long*)obs_key, (size_t)n, obs_on_device, &d_key, sf, st));
-  CB_TRY(to_device(obs_xy, 2 * (size_t)n, obs_on_device, &d_xy, sf, st));
+  CB_TRY(validate_rows(d_cam, d_key, n, n_cams, st, "cb_triangulate_dlt"));
   if (undist) {
     cb::UndistCam* d_tab = nullptr;
     CB_TRY(dalloc(&d_tab, (size_t)n_cams));
@@ -1694,8 +1727,18 @@ int triangulate_impl(int32_t n_cams, const std::vector<cb::UndistCam>* undist, c
     double* d_und = nullptr;
     CB_TRY(dalloc(&d_und, 2 * (size_t)n));
     sf.dev.push_back(d_und);
-    CB_LAUNCH(cb::undistort_kernel, G, TB, 0, st, d_tab, d_cam, d_xy, d_und, (long long)n, 0);
+    if (obs_on_device) {
+      CB_LAUNCH(cb::undistort_kernel<double>, G, TB, 0, st, d_tab, d_cam, obs_xy, d_und, (long long)n, 0);
+    } else {
+      // host pixels: round to float32 while staging (the reference does the same cast, camera_array.py:156),
+      // which halves the upload
+      const float* d_px = nullptr;
+      CB_TRY(to_device_f32(obs_xy, 2 * (size_t)n, &d_px, sf, st));
+      CB_LAUNCH(cb::undistort_kernel<float>, G, TB, 0, st, d_tab, d_cam, d_px, d_und, (long long)n, 0);
+    }
     d_xy = d_und;
+  } else {
+    CB_TRY(to_device(obs_xy, 2 * (size_t)n, obs_on_device, &d_xy, sf, st));
   }
   double* d_proj = nullptr;
   CB_TRY(dalloc(&d_proj, 12 * (size_t)n_cams));
@@ -1745,7 +1788,9 @@ int triangulate_impl(int32_t n_cams, const std::vector<cb::UndistCam>* undist, c
   CB_TRY(dalloc(&d_sig, 2 * (size_t)n_groups)); sf.dev.push_back(d_sig);
   const size_t proj_bytes = sizeof(double) * 12 * (size_t)n_cams;
   const int in_smem = proj_bytes <= 40 * 1024 ? 1 : 0;
-  const int lanes = (n / std::max(n_groups, 1) > 16) ? 32 : 8;
+  // 8 lanes per group: the serial 4x4 eigen-solve of one lane per group, not the gather, bounds this kernel, so
+  // more groups per warp wins until groups get very long
+  const int lanes = (n / std::max(n_groups, 1) > 96) ? 32 : 8;
   const long long threads = (long long)n_groups * lanes;
   CB_CUDA(cudaEventRecord(ev[2], st));
   if (lanes == 32)

@@ -18,15 +18,23 @@ struct UndistCam {
   int pad;
 };
 
+__device__ __forceinline__ float2 load_px(const double* p, long long i) {
+  const double2 v = reinterpret_cast<const double2*>(p)[i];
+  return make_float2((float)v.x, (float)v.y);
+}
+__device__ __forceinline__ float2 load_px(const float* p, long long i) { return reinterpret_cast<const float2*>(p)[i]; }
+
 // float32 in -> double arithmetic -> float32 out, exactly the precision contract of the reference call.
+// TIN = double (caller's array, rounded to float32 here) or float (already rounded on the host while staging).
+template <typename TIN>
 __global__ void undistort_kernel(const UndistCam* __restrict__ cams, const int* __restrict__ obs_cam,
-                                 const double* __restrict__ xy_in, double* __restrict__ xy_out, long long n,
+                                 const TIN* __restrict__ xy_in, double* __restrict__ xy_out, long long n,
                                  int to_pixels) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const UndistCam& c = cams[obs_cam ? obs_cam[i] : 0];
-  const double2 in = reinterpret_cast<const double2*>(xy_in)[i];
-  const double u = (double)(float)in.x, v = (double)(float)in.y;
+  const float2 in = load_px(xy_in, i);
+  const double u = (double)in.x, v = (double)in.y;
   double x, y;
   if (c.fisheye) {
     const double pwx = (u - c.cx) / c.fx, pwy = (v - c.cy) / c.fy;
@@ -90,6 +98,15 @@ __global__ void undistort_kernel(const UndistCam* __restrict__ cams, const int* 
 __global__ void tri_iota_kernel(int* __restrict__ v, long long n) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i < n) v[i] = (int)i;
+}
+
+// counts rows whose camera index is outside [0, n_cams) or whose key is negative
+__global__ void tri_validate_kernel(const int* __restrict__ cam, const long long* __restrict__ key, long long n,
+                                    int n_cams, int* __restrict__ bad) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const bool b = cam[i] < 0 || cam[i] >= n_cams || (key && key[i] < 0);
+  if (b) atomicAdd(bad, 1);
 }
 
 __global__ void tri_heads_kernel(const unsigned long long* __restrict__ k, long long n, int* __restrict__ head) {
