@@ -7,6 +7,8 @@ Mirrors /root/reference/src/caliscope/core/capture_volume.py:
   * ``fast_img_to_obj_map``  == ``_compute_img_to_obj_map`` (:119-139)
   * ``optimize``             == ``CaptureVolume.optimize``   (:322-444), same signature, same result type,
                                 same errors (``CalibrationError`` iff ``strict`` and not converged).
+  * ``reprojection_report``  == ``CaptureVolume.reprojection_report`` (:150-235): pixel errors from the engine,
+                                per-camera / per-point RMSE by ``np.bincount`` instead of one boolean mask per key.
 
 Everything except the solve itself is the reference's own classes (imported from ``caliscope`` at call
 time); the solve goes to the CUDA engine through ``caliscope_b200.solver.solve_arrays``.
@@ -125,4 +127,77 @@ def optimize(self, ftol: float = 1e-8, max_nfev: int | None = None, verbose: int
         world_points=WorldPoints(new_world_df),
         constraints=self.constraints,
         _optimization_status=status,
+    )
+
+
+def _errors_px(camera_array, camera_indices, image_coords, world_coords) -> np.ndarray:
+    """reprojection.py:35-72 on the engine (module-level so the host-logic tests can substitute it)."""
+    from . import reprojection
+
+    return reprojection.reprojection_errors(camera_array, camera_indices, image_coords, world_coords)
+
+
+def reprojection_report(self):
+    """Same ``ReprojectionReport`` as capture_volume.py:150-235 (pixel units, stored intrinsics)."""
+    from caliscope.core.reprojection_report import ReprojectionReport
+
+    camera_indices, image_coords, obj_indices, mask = ba_arrays(self)
+    n_total = len(self.img_to_obj_map)
+    n_matched = int(mask.sum())
+    if n_matched == 0:
+        raise ValueError("No matched observations for reprojection error calculation")
+    df = self.image_points.df
+    matched = df[mask]
+    world_coords = self.world_points.points[obj_indices]
+    errors_xy = _errors_px(self.camera_array, camera_indices, image_coords, world_coords)
+    euclid = np.sqrt(np.sum(errors_xy**2, axis=1))
+    raw_errors = pd.DataFrame(
+        {
+            "sync_index": matched["sync_index"].values,
+            "cam_id": matched["cam_id"].values,
+            "object_id": matched["object_id"].values,
+            "keypoint_id": matched["keypoint_id"].values,
+            "error_x": errors_xy[:, 0],
+            "error_y": errors_xy[:, 1],
+            "euclidean_error": euclid,
+        }
+    )
+    sq = euclid**2
+    overall_rmse = float(np.sqrt(np.mean(sq)))
+    # per camera: camera_indices are positions in posed_cam_id_to_index
+    cam_index = self.camera_array.posed_cam_id_to_index
+    n_idx = (max(cam_index.values()) + 1) if cam_index else 0
+    cnt = np.bincount(camera_indices.astype(np.int64), minlength=n_idx)
+    tot = np.bincount(camera_indices.astype(np.int64), weights=sq, minlength=n_idx)
+    by_camera = {}
+    for cam_id in self.camera_array.posed_cameras.keys():
+        i = cam_index[cam_id]
+        by_camera[cam_id] = float(np.sqrt(tot[i] / cnt[i])) if cnt[i] > 0 else 0.0
+    # per (object_id, keypoint_id)
+    obj = matched["object_id"].to_numpy()
+    kp = matched["keypoint_id"].to_numpy()
+    pairs, inv = np.unique(np.stack([obj, kp], axis=1), axis=0, return_inverse=True)
+    inv = np.asarray(inv).reshape(-1)
+    pc = np.bincount(inv, minlength=len(pairs))
+    pt = np.bincount(inv, weights=sq, minlength=len(pairs))
+    by_point = {(o.item(), k.item()): float(np.sqrt(t / c)) for (o, k), t, c in zip(pairs, pt, pc)}
+    # unmatched observations per camera (all cameras, capture_volume.py:213-218)
+    all_cam = df["cam_id"].to_numpy()
+    unmatched_by_camera = {}
+    for cam_id in self.camera_array.cameras.keys():
+        sel = all_cam == cam_id
+        unmatched_by_camera[cam_id] = int(sel.sum() - (sel & mask).sum())
+    n_unmatched = n_total - n_matched
+    return ReprojectionReport(
+        overall_rmse=overall_rmse,
+        by_camera=by_camera,
+        by_point=by_point,
+        n_unmatched_observations=int(n_unmatched),
+        unmatched_rate=n_unmatched / n_total if n_total > 0 else 0.0,
+        unmatched_by_camera=unmatched_by_camera,
+        raw_errors=raw_errors,
+        n_observations_matched=int(n_matched),
+        n_observations_total=int(n_total),
+        n_cameras=len(self.camera_array.posed_cameras),
+        n_points=len(self.world_points.points),
     )

@@ -12,6 +12,7 @@ CameraArray, BundleParameterization, aniposelib export -- untouched.
 from __future__ import annotations
 
 import contextlib
+import functools
 import importlib
 
 from . import solver
@@ -29,7 +30,8 @@ def install(fallback=None, full: bool = False) -> None:
     not implement (distance-constraint rows).  Default ``None`` = raise ``NotImplementedError``.
     ``full=True`` additionally installs seam S2: ``CaptureVolume.optimize`` and
     ``CaptureVolume._compute_img_to_obj_map`` are replaced by the vectorised versions in
-    ``caliscope_b200.capture_volume`` (same signatures and results, no per-row Python loops), and seam
+    ``caliscope_b200.capture_volume`` (same signatures and results, no per-row Python loops),
+    ``CaptureVolume.reprojection_report`` by the engine-backed, bincount-aggregated version, and seam
     S3: ``caliscope.core.point_data.triangulate_image_points`` (the DLT triangulation
     ``ImagePoints.triangulate`` calls, point_data.py:474,509) becomes the GPU version."""
     global _original
@@ -46,9 +48,13 @@ def install(fallback=None, full: bool = False) -> None:
 
         cls = mod.CaptureVolume
         if not _original_methods:
-            _original_methods.update(optimize=cls.optimize, _compute_img_to_obj_map=cls._compute_img_to_obj_map)
+            _original_methods.update(optimize=cls.optimize, _compute_img_to_obj_map=cls._compute_img_to_obj_map,
+                                     reprojection_report=cls.__dict__["reprojection_report"])
         cls.optimize = cv2b.optimize
         cls._compute_img_to_obj_map = cv2b.fast_img_to_obj_map
+        report = functools.cached_property(cv2b.reprojection_report)
+        report.__set_name__(cls, "reprojection_report")
+        cls.reprojection_report = report
         from . import triangulation
 
         pd_mod = importlib.import_module("caliscope.core.point_data")

@@ -132,12 +132,56 @@ def test_seam_install_full_patches_and_restores(session_volume):
     from caliscope_b200 import capture_volume as S2
     from caliscope_b200 import solver
 
-    before = (mod.least_squares, mod.CaptureVolume.optimize, mod.CaptureVolume._compute_img_to_obj_map)
+    import caliscope.core.point_data as pd_mod
+    from caliscope_b200 import triangulation
+
+    def state():
+        return (mod.least_squares, mod.CaptureVolume.optimize, mod.CaptureVolume._compute_img_to_obj_map,
+                mod.CaptureVolume.__dict__["reprojection_report"], pd_mod.triangulate_image_points)  # fmt: skip
+
+    before = state()
     with seam.installed(full=True):
         assert mod.least_squares is solver.least_squares
         assert mod.CaptureVolume.optimize is S2.optimize
         assert mod.CaptureVolume._compute_img_to_obj_map is S2.fast_img_to_obj_map
-    assert (mod.least_squares, mod.CaptureVolume.optimize, mod.CaptureVolume._compute_img_to_obj_map) == before
+        assert mod.CaptureVolume.__dict__["reprojection_report"].func is S2.reprojection_report
+        assert pd_mod.triangulate_image_points is triangulation.triangulate_image_points
+    assert state() == before
+
+
+def test_s2_reprojection_report_equals_reference(session_volume, monkeypatch):
+    """capture_volume.py:150-235: every field of the report, with the engine's pixel errors replaced by
+    the reference's own ``reprojection_errors`` (this container has no GPU; the engine function is
+    parity-tested on the GPU in tests/test_gpu_seam.py)."""
+    from caliscope.core.capture_volume import CaptureVolume
+    from caliscope.core.reprojection import reprojection_errors
+    from caliscope_b200 import capture_volume as S2
+
+    monkeypatch.setattr(S2, "_errors_px", reprojection_errors)
+    cv = session_volume
+    # drop one camera's world matches so the unmatched counters are exercised
+    wdf = cv.world_points.df
+    from caliscope.core.point_data import WorldPoints
+
+    cv2 = CaptureVolume(cv.camera_array, cv.image_points, WorldPoints(wdf.iloc[: len(wdf) // 2].copy()))
+    for vol in (cv, cv2):
+        ref = vol.reprojection_report
+        got = S2.reprojection_report(vol)
+        assert got.overall_rmse == pytest.approx(ref.overall_rmse, rel=1e-13)
+        assert list(got.by_camera) == list(ref.by_camera)
+        for k in ref.by_camera:
+            assert got.by_camera[k] == pytest.approx(ref.by_camera[k], rel=1e-12)
+        assert set(got.by_point) == set(ref.by_point)
+        for k in ref.by_point:
+            assert got.by_point[k] == pytest.approx(ref.by_point[k], rel=1e-12)
+        assert got.unmatched_by_camera == ref.unmatched_by_camera
+        assert (got.n_unmatched_observations, got.n_observations_matched, got.n_observations_total, got.n_cameras,
+                got.n_points) == (ref.n_unmatched_observations, ref.n_observations_matched, ref.n_observations_total,
+                                  ref.n_cameras, ref.n_points)  # fmt: skip
+        assert got.unmatched_rate == ref.unmatched_rate
+        import pandas as pd
+
+        pd.testing.assert_frame_equal(got.raw_errors, ref.raw_errors)
 
 
 def test_s2_optimize_passes_the_reference_constraint_arrays(monkeypatch):
