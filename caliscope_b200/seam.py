@@ -23,11 +23,10 @@ _original_methods: dict = {}
 _original_functions: dict = {}
 
 
-def install(fallback=None, full: bool = False) -> None:
+def install(full: bool = False) -> None:
     """Seam S1: replace the ``least_squares`` attribute ``CaptureVolume.optimize`` calls.
 
-    ``fallback``: optional callable with scipy's ``least_squares`` signature for calls this engine does
-    not implement (distance-constraint rows).  Default ``None`` = raise ``NotImplementedError``.
+    A call that is not the bundle-adjustment call raises ``NotImplementedError``; there is no CPU route.
     ``full=True`` additionally installs seam S2: ``CaptureVolume.optimize`` and
     ``CaptureVolume._compute_img_to_obj_map`` are replaced by the vectorised versions in
     ``caliscope_b200.capture_volume`` (same signatures and results, no per-row Python loops),
@@ -41,7 +40,6 @@ def install(fallback=None, full: bool = False) -> None:
     mod = importlib.import_module(_TARGET)
     if _original is None:
         _original = mod.least_squares
-    solver._fallback = fallback
     mod.least_squares = solver.least_squares
     if full:
         from . import capture_volume as cv2b
@@ -78,12 +76,11 @@ def uninstall() -> None:
         for name, fn in _original_functions.items():
             setattr(pd_mod, name, fn)
         _original_functions.clear()
-    solver._fallback = None
 
 
 @contextlib.contextmanager
-def installed(fallback=None, full: bool = False):
-    install(fallback, full)
+def installed(full: bool = False):
+    install(full)
     try:
         yield
     finally:

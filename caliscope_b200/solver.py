@@ -8,22 +8,19 @@
 ``least_squares`` below has that signature.  When ``fun`` is a ``joint_residuals`` (the reference's or
 this package's) it never calls ``fun``/``jac``: it hands ``args`` to the CUDA engine and returns an
 object with the fields the reference reads (``x``, ``status``, ``nfev``, ``cost``), rigid-distance
-constraint rows included.  Anything else is not this path and raises (or is delegated to the callable
-given to ``install(fallback=...)``).
+constraint rows included.  Anything else is not this path and raises ``NotImplementedError``: the
+package has no CPU route of any kind.
 """
 from __future__ import annotations
 
 import logging
-from typing import Any, Callable
+from typing import Any
 
 import numpy as np
 
 from .problem import BAProblem, SolveResult, blocks_to_arrays
 
 logger = logging.getLogger(__name__)
-
-_fallback: Callable | None = None  # set by seam.install(fallback=...)
-
 
 def is_bundle_adjustment_call(fun: Any, args: tuple) -> bool:
     return (
@@ -47,10 +44,6 @@ def least_squares(fun, x0, jac="2-point", bounds=(-np.inf, np.inf), method="trf"
                   x_scale=None, loss="linear", f_scale=1.0, diff_step=None, tr_solver=None, tr_options=None,
                   jac_sparsity=None, max_nfev=None, verbose=0, args=(), kwargs=None, callback=None, **extra):  # fmt: skip
     if not is_bundle_adjustment_call(fun, tuple(args)):
-        if _fallback is not None:
-            return _fallback(fun, x0, jac=jac, bounds=bounds, method=method, ftol=ftol, xtol=xtol, gtol=gtol,
-                             x_scale=x_scale if x_scale is not None else 1.0, loss=loss, f_scale=f_scale,
-                             max_nfev=max_nfev, verbose=verbose, args=args, kwargs=kwargs or {})  # fmt: skip
         raise NotImplementedError("caliscope_b200.least_squares only replaces the bundle-adjustment call "
                                   "(fun=joint_residuals, args=(parameterization, camera_indices, ...))")  # fmt: skip
     par, camera_indices, image_coords, obj_indices = args[:4]
