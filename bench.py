@@ -66,7 +66,7 @@ def workload_config(name: str, rig, n_gpus: int) -> dict:
         "loss": "linear",
         "ftol": 1e-8,
         "sharding": "single GPU" if n_gpus == 1 else f"observations sharded by point over {n_gpus} GPUs, "
-        "one NCCL all-reduce of the reduced camera system per LM trial",
+        "one sum-all-reduce of the reduced camera system per LM trial (transport: see allreduce_transport)",
         "l2": "per-iteration working set (Jacobian rows + Schur factor, >500 MB) exceeds the 126 MB L2; no explicit flush",
     }
 
@@ -254,13 +254,15 @@ def run_ours(args) -> None:
         shard = D.shard_points(rig.obs_cam, rig.obs_pt, rig.obs_xy, rig.n_pts, rank, world)
         l_cam, l_pt, l_xy, l_npts = shard.obs_cam, shard.obs_pt, shard.obs_xy, shard.n_pts
         x0 = D.local_x(rig.x0, ncp, shard)
-        transport = D.transport_kwargs(local_rank)
+        transport = D.transport_kwargs(local_rank, n_camera_dims=rig.n_cams * (9 if np.any(rig.cam_flags & 1) else 6))
     else:
         shard = None
         l_cam, l_pt, l_xy, l_npts = rig.obs_cam, rig.obs_pt, rig.obs_xy, rig.n_pts
         x0 = rig.x0
         transport = {}
     solve_kw = dict(ftol=1e-8, rank=rank, world_size=world, stream=stream, **transport)
+    transport_name = {"peer_group": "peer memory (fused finalize + NVLink reduce kernel)", "nccl_comm": "engine-owned NCCL",
+                      "allreduce": "torch.distributed callback"}.get(next(iter(transport), ""), "none (single GPU)")
 
     def barrier():
         if world > 1:
@@ -280,6 +282,7 @@ def run_ours(args) -> None:
     d_xy = torch.from_numpy(np.ascontiguousarray(l_xy)).cuda()
     prob = cb.BAProblem(rig.cam_flags, rig.cam_const, l_npts, d_cam, d_pt, d_xy, device=dev, stream=stream)
     res = None
+    barrier()
     for _ in range(args.warmup):
         res = prob.solve(x0, **solve_kw)
     sampler = ClockSampler(dev)
@@ -372,6 +375,7 @@ def run_ours(args) -> None:
             "d2h_bytes_per_step": d2h,
         },
         "gpu_launches": int(launches),
+        "allreduce_transport": transport_name,
         "obs_residuals_per_sec": rig.n_obs * nfev / (dev_ms * 1e-3),
         "lm_iterations_per_step": nit / args.steps,
         "nfev_per_step": nfev / args.steps,
@@ -387,7 +391,7 @@ def run_ours(args) -> None:
             "peak": peak,
             "unit": "GB/s",
             "frac": achieved / peak,
-            "traffic": load_ncu_traffic(args.workload),
+            "traffic": load_ncu_traffic(args.workload) if world == 1 else None,  # the ncu capture is of the 1-GPU launch
             "peak_source": peak_src,
             "algorithmic_bytes_per_launch": rj_bytes,
             "avg_launch_ms": rj_avg_ms,

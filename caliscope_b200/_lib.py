@@ -60,6 +60,7 @@ class Options(C.Structure):
         ("allreduce", ALLREDUCE_FN),
         ("allreduce_user", C.c_void_p),
         ("nccl_comm", C.c_void_p),
+        ("peer_group", C.c_void_p),
         ("rank", C.c_int32),
         ("world_size", C.c_int32),
     ]
@@ -131,6 +132,9 @@ SYMBOLS = {
         [C.c_int32, _P, _P, _P, _P, C.c_int64, _P, _P, _P, C.c_int, C.c_int32, C.POINTER(C.c_int32), _P, _P, _P, _P,
          C.POINTER(TriStats), C.c_int, _P],
     ),
+    "cb_peer_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.POINTER(_P), _P]),
+    "cb_peer_connect": (C.c_int, [_P, _P]),
+    "cb_peer_destroy": (C.c_int, [_P]),
     "cb_nccl_unique_id": (C.c_int, [_P]),
     "cb_nccl_comm_create": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "cb_nccl_comm_destroy": (C.c_int, [_P]),

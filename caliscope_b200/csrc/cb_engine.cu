@@ -25,6 +25,7 @@
 #include "cb_kernels.cuh"
 #include "cb_constraints.cuh"
 #include "cb_triangulate.cuh"
+#include "cb_peer.cuh"
 
 namespace {
 
@@ -58,6 +59,22 @@ inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 // NCCL, resolved at run time from the libnccl the process already has loaded (torch's bundled copy):
 // no link-time dependency, no second NCCL in the address space.
 // ------------------------------------------------------------------------------------------
+}  // namespace
+
+// symmetric IPC buffer of one rank + the mapped views of its peers (cb_peer.cuh)
+struct CbPeerGroup {
+  int rank = 0, world = 1, device = 0;
+  size_t cap = 0;  // doubles per data buffer
+  size_t bytes = 0;
+  void* base = nullptr;
+  void* peer_base[cb::PEER_MAXW] = {};
+  cb::PeerTable tab = {};
+  unsigned long long epoch_big = 0, epoch_small = 0;
+  bool connected = false;
+};
+
+namespace {
+
 struct NcclApi {
   bool ok = false;
   std::string err;
@@ -97,6 +114,12 @@ NcclApi& nccl() {
 
 // sum-all-reduce of n doubles in place through whichever transport the options carry
 int do_allreduce(const CbBaOptions* opt, double* buf, long long n, cudaStream_t st) {
+  if (opt->peer_group) {
+    CbPeerGroup* g = (CbPeerGroup*)opt->peer_group;
+    if (n > cb::PEER_SMALL_N) { g_last_error = "peer transport: unexpected all-reduce length"; return CB_E_INVALID; }
+    CB_LAUNCH(cb::peer_small_allreduce_kernel, 1, 32, 0, st, buf, (int)n, g->tab, ++g->epoch_small);
+    return CB_OK;
+  }
   if (opt->nccl_comm) {
     NcclApi& a = nccl();
     if (!a.ok) { g_last_error = a.err; return CB_E_UNSUPPORTED; }
@@ -114,7 +137,7 @@ int do_allreduce(const CbBaOptions* opt, double* buf, long long n, cudaStream_t 
   return CB_OK;
 }
 
-inline bool sharded(const CbBaOptions* opt) { return opt && (opt->allreduce || opt->nccl_comm); }
+inline bool sharded(const CbBaOptions* opt) { return opt && (opt->allreduce || opt->nccl_comm || opt->peer_group); }
 
 // Process-wide caching allocator: repeated problem_create / destroy cycles (one per
 // CaptureVolume.optimize call: linear -> soft_l1 -> filter -> linear) reuse device and pinned
@@ -270,6 +293,7 @@ struct CbBaProblem {
   std::vector<int> h_ga, h_gb;
   std::vector<double> h_cdist, h_cw;
   int red_slots = 64;
+  CbPeerGroup* peer = nullptr;  // set for the duration of a solve that uses the peer transport
   size_t red_len() const { return (size_t)nP * nP + 3 * (size_t)nP + 1 + red_slots; }
 };
 
@@ -458,14 +482,29 @@ int build_system(CbBaProblem* p, double lam, bool new_lin, const CbBaOptions* op
   CB_LAUNCH(cb::schur_syrk_kernel, p->n_items, cb::SY_THREADS, sizeof(cb::SyrkSmem), st, p->d_Zt, (size_t)p->LD,
             p->d_tvec, p->d_items, p->d_part, p->d_tpart);
   const size_t nfin = (size_t)p->nP * p->nP + p->nP + 1;
-  CB_LAUNCH((cb::schur_finalize_kernel<P>), cdiv((long long)nfin, 256), 256, 0, st, p->nP, p->n_blk, p->d_tile_of,
-            p->d_tile_slot_start, p->d_tile_slots, p->d_part, p->d_tpart, p->d_Upk, p->d_gc, p->d_costsum, p->d_red);
   // gradient inf-norm over points: one slot per rank so a SUM all-reduce carries the max
   const size_t slot0 = (size_t)p->nP * p->nP + 3 * (size_t)p->nP + 1;
-  CB_CUDA(cudaMemsetAsync(p->d_red + slot0, 0, sizeof(double) * p->red_slots, st));
   const int rank = sharded(opt) ? std::min(std::max(opt->rank, 0), p->red_slots - 1) : 0;
-  CB_CUDA(cudaMemcpyAsync(p->d_red + slot0 + rank, p->d_gmax, sizeof(double), cudaMemcpyDeviceToDevice, st));
-  if (sharded(opt)) CB_TRY(do_allreduce(opt, p->d_red, (long long)p->red_len(), st));
+  if (opt && opt->peer_group) {
+    // finalize + all-reduce over NVLink peer memory in one kernel (cb_peer.cuh)
+    CbPeerGroup* g = (CbPeerGroup*)opt->peer_group;
+    // every block spins on the peers' flags, so the whole grid must be co-resident: size it from the occupancy API
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+      int nb = 0;
+      CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cb::schur_finalize_peer_kernel<P>, cb::PEER_THREADS, 0));
+      blocks_per_sm = std::max(1, std::min(nb, 2));
+    }
+    CB_LAUNCH((cb::schur_finalize_peer_kernel<P>), blocks_per_sm * p->num_sms, cb::PEER_THREADS, 0, st, p->nP, p->n_blk, p->d_tile_of,
+              p->d_tile_slot_start, p->d_tile_slots, p->d_part, p->d_tpart, p->d_Upk, p->d_gc, p->d_costsum,
+              (const double*)p->d_gmax, p->red_slots, rank, g->tab, ++g->epoch_big, p->d_red);
+  } else {
+    CB_LAUNCH((cb::schur_finalize_kernel<P>), cdiv((long long)nfin, 256), 256, 0, st, p->nP, p->n_blk, p->d_tile_of,
+              p->d_tile_slot_start, p->d_tile_slots, p->d_part, p->d_tpart, p->d_Upk, p->d_gc, p->d_costsum, p->d_red);
+    CB_CUDA(cudaMemsetAsync(p->d_red + slot0, 0, sizeof(double) * p->red_slots, st));
+    CB_CUDA(cudaMemcpyAsync(p->d_red + slot0 + rank, p->d_gmax, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (sharded(opt)) CB_TRY(do_allreduce(opt, p->d_red, (long long)p->red_len(), st));
+  }
   CB_LAUNCH(cb::post_reduce_kernel, 1, 256, 0, st, p->nP, lam, new_lin ? 1 : 0, p->d_red, p->d_Dc2, p->d_active,
             p->d_sc);
   return CB_OK;
@@ -550,7 +589,13 @@ int readback(CbBaProblem* p, HostScalars* h, cudaStream_t st) {
   CB_CUDA(cudaMemcpyAsync(p->h_sc + cb::SC_COUNT, p->d_red2, sizeof(double) * 4, cudaMemcpyDeviceToHost, st));
   CB_CUDA(cudaMemcpyAsync(p->h_sc + cb::SC_COUNT + 4, p->d_red + slot0, sizeof(double) * p->red_slots,
                           cudaMemcpyDeviceToHost, st));
+  int peer_err = 0;
+  if (p->peer) CB_CUDA(cudaMemcpyAsync(&peer_err, p->peer->tab.err, sizeof(int), cudaMemcpyDeviceToHost, st));
   CB_CUDA(cudaStreamSynchronize(st));
+  if (peer_err) {
+    g_last_error = "peer all-reduce timed out waiting for another rank";
+    return CB_E_CALLBACK;
+  }
   std::memcpy(h->sc, p->h_sc, sizeof(double) * cb::SC_COUNT);
   std::memcpy(h->red2, p->h_sc + cb::SC_COUNT, sizeof(double) * 4);
   std::memcpy(h->slots, p->h_sc + cb::SC_COUNT + 4, sizeof(double) * p->red_slots);
@@ -820,11 +865,95 @@ void cb_ba_default_options(CbBaOptions* o) {
   o->allreduce = nullptr;
   o->allreduce_user = nullptr;
   o->nccl_comm = nullptr;
+  o->peer_group = nullptr;
   o->rank = 0;
   o->world_size = 1;
 }
 
 int64_t cb_ba_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int cb_peer_create(int rank, int world_size, int device, int64_t capacity_doubles, CbPeerGroup** out,
+                   char handle_out[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (!out || !handle_out || rank < 0 || rank >= world_size || world_size > cb::PEER_MAXW || capacity_doubles <= 0) {
+    g_last_error = "cb_peer_create: bad argument (world_size <= 16)";
+    return CB_E_INVALID;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); g_last_error = "no CUDA device"; return CB_E_NO_DEVICE; }
+  CB_CUDA(cudaSetDevice(device));
+  auto* g = new CbPeerGroup();
+  g->rank = rank; g->world = world_size; g->device = device;
+  g->cap = ((size_t)capacity_doubles + 31) / 32 * 32;
+  g->bytes = cb::PEER_OFF_DATA + 2 * g->cap * sizeof(double);
+  cudaError_t e = cudaMalloc(&g->base, g->bytes);  // a whole allocation of its own: IPC handles name allocations
+  if (e != cudaSuccess) { g_last_error = std::string("cudaMalloc: ") + cudaGetErrorString(e); delete g; return CB_E_NOMEM; }
+  e = cudaMemset(g->base, 0, g->bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, g->base);
+  if (e != cudaSuccess) {
+    g_last_error = std::string("cb_peer_create: ") + cudaGetErrorString(e);
+    cudaFree(g->base);
+    delete g;
+    return CB_E_CUDA;
+  }
+  std::memcpy(handle_out, &h, 64);
+  *out = g;
+  return CB_OK;
+}
+
+int cb_peer_connect(CbPeerGroup* g, const char* handles) {
+  if (!g || !handles) { g_last_error = "cb_peer_connect: null argument"; return CB_E_INVALID; }
+  if (g->connected) return CB_OK;
+  CB_CUDA(cudaSetDevice(g->device));
+  for (int r = 0; r < g->world; ++r) {
+    if (r == g->rank) { g->peer_base[r] = g->base; continue; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handles + 64 * (size_t)r, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(&g->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      g_last_error = "cudaIpcOpenMemHandle(rank " + std::to_string(r) + "): " + cudaGetErrorString(e);
+      cudaGetLastError();
+      for (int q = 0; q < r; ++q)
+        if (q != g->rank && g->peer_base[q]) { cudaIpcCloseMemHandle(g->peer_base[q]); g->peer_base[q] = nullptr; }
+      return CB_E_UNSUPPORTED;
+    }
+  }
+  cb::PeerTable& t = g->tab;
+  t.rank = g->rank; t.world = g->world;
+  for (int r = 0; r < g->world; ++r) {
+    char* b = (char*)g->peer_base[r];
+    t.data[r][0] = (const double*)(b + cb::PEER_OFF_DATA);
+    t.data[r][1] = (const double*)(b + cb::PEER_OFF_DATA) + g->cap;
+    t.flags_big_of[r] = (unsigned long long*)(b + cb::PEER_OFF_FLAGS_BIG);
+    t.flags_small_of[r] = (unsigned long long*)(b + cb::PEER_OFF_FLAGS_SMALL);
+    t.small_of[r] = (double*)(b + cb::PEER_OFF_SMALL);
+  }
+  char* mine = (char*)g->base;
+  t.my_data[0] = (double*)(mine + cb::PEER_OFF_DATA);
+  t.my_data[1] = (double*)(mine + cb::PEER_OFF_DATA) + g->cap;
+  t.my_flags_big = (unsigned long long*)(mine + cb::PEER_OFF_FLAGS_BIG);
+  t.my_flags_small = (unsigned long long*)(mine + cb::PEER_OFF_FLAGS_SMALL);
+  t.my_small = (double*)(mine + cb::PEER_OFF_SMALL);
+  t.done = (unsigned int*)(mine + cb::PEER_OFF_DONE);
+  t.err = (int*)(mine + cb::PEER_OFF_ERR);
+  g->connected = true;
+  return CB_OK;
+}
+
+int cb_peer_destroy(CbPeerGroup* g) {
+  if (!g) return CB_OK;
+  cudaSetDevice(g->device);
+  cudaDeviceSynchronize();
+  if (g->connected)
+    for (int r = 0; r < g->world; ++r)
+      if (r != g->rank && g->peer_base[r]) cudaIpcCloseMemHandle(g->peer_base[r]);
+  if (g->base) cudaFree(g->base);
+  cudaGetLastError();
+  delete g;
+  return CB_OK;
+}
 
 int cb_nccl_unique_id(char id_out[128]) {
   NcclApi& a = nccl();
@@ -1096,7 +1225,20 @@ int cb_ba_solve(CbBaProblem* p, const CbBaOptions* opt, double* x_inout, CbBaRes
   cudaStream_t st = (cudaStream_t)stream;
   // with an all-reduce hook the caller shards by constraint component (distributed.shard_points), so every
   // constraint row and every point it touches are local to this rank
-  return p->P == 6 ? lm_solve<6>(p, opt, x_inout, result, st) : lm_solve<9>(p, opt, x_inout, result, st);
+  p->peer = nullptr;
+  if (opt->peer_group) {
+    CbPeerGroup* g = (CbPeerGroup*)opt->peer_group;
+    if (!g->connected || g->device != p->device) { g_last_error = "peer group is not connected on this device"; return CB_E_INVALID; }
+    if (g->cap < p->red_len()) {
+      g_last_error = "peer group capacity " + std::to_string(g->cap) + " doubles < " + std::to_string(p->red_len());
+      return CB_E_INVALID;
+    }
+    if (opt->rank != g->rank || opt->world_size != g->world) { g_last_error = "rank / world_size differ from the peer group's"; return CB_E_INVALID; }
+    p->peer = g;
+  }
+  const int rc = p->P == 6 ? lm_solve<6>(p, opt, x_inout, result, st) : lm_solve<9>(p, opt, x_inout, result, st);
+  p->peer = nullptr;
+  return rc;
 }
 
 }  // extern "C"

@@ -723,20 +723,21 @@ schur_syrk_kernel(const double* __restrict__ Zt, size_t LD, const double* __rest
 }
 
 // red = [ S (nP*nP) | b (nP) | gc (nP) | diagU (nP) | cost | gpmax slots ... ]   (local partials)
+// one output element of S = U - Z Z^T, b = g_c - Z t (+ g_c, diag U, cost) from the split-K partial tiles;
+// diagonal tiles hold only their upper-triangular 24x24 blocks
 template <int P>
-__global__ void schur_finalize_kernel(int nP, int n_blk, const int* __restrict__ tile_of,
-                                      const int* __restrict__ tile_slot_start, const int* __restrict__ tile_slots,
-                                      const double* __restrict__ part, const double* __restrict__ tpart,
-                                      const double* __restrict__ Upk, const double* __restrict__ gc,
-                                      const double* __restrict__ cam_cost_sum, double* __restrict__ red) {
+__device__ __forceinline__ void finalize_elem(size_t idx, int nP, int n_blk, const int* __restrict__ tile_of,
+                                              const int* __restrict__ tile_slot_start,
+                                              const int* __restrict__ tile_slots, const double* __restrict__ part,
+                                              const double* __restrict__ tpart, const double* __restrict__ Upk,
+                                              const double* __restrict__ gc, const double* __restrict__ cam_cost_sum,
+                                              double* __restrict__ red) {
   using RT = RowT<P>;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t nn = (size_t)nP * nP;
   if (idx < nn) {
     const int i = (int)(idx / nP), j = (int)(idx % nP);
     int I = i / SY_TILE, J = j / SY_TILE, li = i % SY_TILE, lj = j % SY_TILE;
     if (I > J) { int t = I; I = J; J = t; t = li; li = lj; lj = t; }
-    // diagonal tiles hold only their upper-triangular 24x24 blocks
     if (I == J && li / 24 > lj / 24) { int t = li; li = lj; lj = t; }
     const int tile = tile_of[I * n_blk + J];
     double s = 0.0;
@@ -764,6 +765,16 @@ __global__ void schur_finalize_kernel(int nP, int n_blk, const int* __restrict__
   } else if (idx == nn + (size_t)nP) {
     red[nn + 3 * (size_t)nP] = cam_cost_sum[0];
   }
+}
+
+template <int P>
+__global__ void schur_finalize_kernel(int nP, int n_blk, const int* __restrict__ tile_of,
+                                      const int* __restrict__ tile_slot_start, const int* __restrict__ tile_slots,
+                                      const double* __restrict__ part, const double* __restrict__ tpart,
+                                      const double* __restrict__ Upk, const double* __restrict__ gc,
+                                      const double* __restrict__ cam_cost_sum, double* __restrict__ red) {
+  finalize_elem<P>((size_t)blockIdx.x * blockDim.x + threadIdx.x, nP, n_blk, tile_of, tile_slot_start, tile_slots, part,
+                   tpart, Upk, gc, cam_cost_sum, red);
 }
 
 // after the all-reduce: Marquardt scaling (running max of diag U), damping, camera gradient norm

@@ -213,7 +213,66 @@ class EngineNcclComm:
             pass
 
 
+class EnginePeerGroup:
+    """Symmetric CUDA-IPC buffers for the peer-memory all-reduce (``cb_peer_*``, csrc/cb_peer.cuh):
+    the Schur finalize kernel sums the reduced camera system straight out of the peers' HBM over
+    NVLink.  torch.distributed only carries the 64-byte IPC handles at set-up.  ``n_camera_dims`` is
+    the largest ``n_cams * P`` (P = 9 with free intrinsics else 6) this group will be used for."""
+
+    def __init__(self, device: int, n_camera_dims: int, group=None):
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib as L
+
+        self._lib = L.load()
+        self._group = group
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        cap = int(n_camera_dims) ** 2 + 3 * int(n_camera_dims) + 65
+        h = C.c_void_p()
+        mine = (C.c_char * 64)()
+        L.check(self._lib.cb_peer_create(rank, world, int(device), cap, C.byref(h), mine), "peer_create")
+        self.handle = h.value
+        self.capacity = cap
+        self.rank, self.world_size = rank, world
+        send = torch.frombuffer(bytearray(mine.raw), dtype=torch.uint8).to(f"cuda:{device}")
+        recv = [torch.empty(64, dtype=torch.uint8, device=f"cuda:{device}") for _ in range(world)]
+        dist.all_gather(recv, send, group=group)
+        blob = b"".join(bytes(t.cpu().numpy().tobytes()) for t in recv)
+        try:
+            L.check(self._lib.cb_peer_connect(C.c_void_p(self.handle), blob), "peer_connect")
+            ok = 1
+        except Exception:
+            ok = 0
+            self._connect_error = True
+        flag = torch.tensor([ok], dtype=torch.int32, device=f"cuda:{device}")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        self.usable = bool(flag.item())
+
+    def close(self):
+        if getattr(self, "handle", None):
+            import torch.distributed as dist
+
+            if dist.is_initialized():
+                dist.barrier(group=self._group)  # nobody may still be reading this rank's buffer
+            self._lib.cb_peer_destroy(C.c_void_p(self.handle))
+            self.handle = None
+
+
 _COMMS: dict = {}
+_PEERS: dict = {}
+
+
+def engine_peer_group(device: int, n_camera_dims: int, group=None) -> EnginePeerGroup:
+    """Cached per (device, group); re-created (collectively) when a larger reduced system comes along."""
+    key = (int(device), id(group))
+    g = _PEERS.get(key)
+    need = int(n_camera_dims) ** 2 + 3 * int(n_camera_dims) + 65
+    if g is None or g.handle is None or g.capacity < need:
+        if g is not None:
+            g.close()
+        g = _PEERS[key] = EnginePeerGroup(device, n_camera_dims, group)
+    return g
 
 
 def engine_comm(device: int, group=None) -> EngineNcclComm:
@@ -227,22 +286,38 @@ def engine_comm(device: int, group=None) -> EngineNcclComm:
 
 def close_comms() -> None:
     """Destroy every cached engine communicator (call before ``dist.destroy_process_group``)."""
+    for g in list(_PEERS.values()):
+        g.close()
+    _PEERS.clear()
     for c in list(_COMMS.values()):
         c.close()
     _COMMS.clear()
 
 
-def transport_kwargs(device: int, group=None) -> dict:
-    """``solve(...)`` keyword arguments selecting the all-reduce transport: the engine's own NCCL
-    communicator on an NCCL process group (``CB_ALLREDUCE=torch`` forces the callback), the
-    torch.distributed callback otherwise (gloo CPU tests use ``make_allreduce_hook`` directly)."""
+def transport_kwargs(device: int, group=None, n_camera_dims: int | None = None) -> dict:
+    """``solve(...)`` keyword arguments selecting the all-reduce transport on an NCCL process group
+    (``CB_ALLREDUCE`` = ``peer`` | ``nccl`` | ``torch``):
+
+    * ``peer``  — all-reduce over NVLink peer memory fused into the Schur finalize kernel (default when
+      ``n_camera_dims`` is given; ``nccl`` is used instead when CUDA IPC cannot map the peers);
+    * ``nccl``  — the engine's own NCCL communicator;
+    * ``torch`` — the ``CbAllReduceSum`` callback over ``torch.distributed`` (also what the gloo CPU
+      tests use, through ``make_allreduce_hook`` directly)."""
     import os
 
     import torch.distributed as dist
 
-    if dist.get_backend(group) == "nccl" and os.environ.get("CB_ALLREDUCE", "nccl") != "torch":
-        return {"nccl_comm": engine_comm(device, group)}
-    return {"allreduce": make_allreduce_hook(group)}
+    if dist.get_backend(group) != "nccl":
+        return {"allreduce": make_allreduce_hook(group)}
+    mode = os.environ.get("CB_ALLREDUCE", "peer")
+    if mode == "peer" and n_camera_dims is not None and dist.get_world_size(group) <= 16:
+        g = engine_peer_group(device, n_camera_dims, group)
+        if g.usable:
+            return {"peer_group": g}
+        mode = "nccl"
+    if mode == "torch":
+        return {"allreduce": make_allreduce_hook(group)}
+    return {"nccl_comm": engine_comm(device, group)}
 
 
 def gather_points(x_local: np.ndarray, n_camera_params: int, n_pts_global: int, shard: PointShard, group=None) -> np.ndarray:
@@ -281,11 +356,12 @@ def solve_sharded(cam_flags, cam_const, n_pts, obs_cam, obs_pt, obs_xy, x0, *, d
     ncp = int(np.where(np.asarray(cam_flags) & 1, 9, 6).sum())
     with BAProblem(cam_flags, cam_const, shard.n_pts, shard.obs_cam, shard.obs_pt, shard.obs_xy,
                    constraints=shard.constraints, device=device) as prob:
+        dist.barrier(group=group)  # ranks enter the first fused reduce together (the peer spin times out after 20 s)
         res = prob.solve(
             local_x(np.asarray(x0, dtype=np.float64), ncp, shard),
             rank=rank,
             world_size=world,
-            **transport_kwargs(device, group),
+            **transport_kwargs(device, group, n_camera_dims=len(np.asarray(cam_flags)) * (9 if np.any(np.asarray(cam_flags) & 1) else 6)),
             **solve_kw,
         )
     res.x = gather_points(res.x, ncp, n_pts, shard, group)

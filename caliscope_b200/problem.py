@@ -285,6 +285,7 @@ class BAProblem:
         pcg_tol: float = 1e-6,
         allreduce=None,
         nccl_comm=None,
+        peer_group=None,
         rank: int = 0,
         world_size: int = 1,
         stream: int = 0,
@@ -308,6 +309,8 @@ class BAProblem:
             opt.allreduce = cb
         if nccl_comm is not None:
             opt.nccl_comm = C.c_void_p(getattr(nccl_comm, "handle", nccl_comm))
+        if peer_group is not None:
+            opt.peer_group = C.c_void_p(getattr(peer_group, "handle", peer_group))
         opt.rank, opt.world_size = int(rank), int(world_size)
         res = L.Result()
         L.check(self._lib.cb_ba_solve(self._h, C.byref(opt), _ptr(x), C.byref(res), C.c_void_p(stream)), "solve")

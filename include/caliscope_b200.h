@@ -102,6 +102,8 @@ typedef struct {
   CbAllReduceSum allreduce; /* NULL: single GPU (unless nccl_comm is set) */
   void* allreduce_user;
   void* nccl_comm;          /* ncclComm_t from cb_nccl_comm_create: the engine calls ncclAllReduce itself on the solve stream */
+  void* peer_group;         /* CbPeerGroup* from cb_peer_create/_connect: all-reduce over NVLink peer memory, fused into
+                               the Schur finalize kernel (takes precedence over nccl_comm / allreduce) */
   int32_t rank;       /* informational (verbose output only on rank 0) */
   int32_t world_size; /* 1 if allreduce is NULL */
 } CbBaOptions;
@@ -240,6 +242,17 @@ int cb_undistort_triangulate(int32_t n_cams, const int32_t* cam_fisheye, const d
 int cb_nccl_unique_id(char id_out[128]);
 int cb_nccl_comm_create(const char id[128], int rank, int world_size, int device, void** comm_out);
 int cb_nccl_comm_destroy(void* comm);
+
+/* Peer-memory transport (one node, NVLink/NVSwitch, one process per GPU).  Every rank creates its symmetric buffer
+ * (capacity_doubles >= (n_cams*P)^2 + 3*n_cams*P + 65 for the problems it will solve, P = 9 with free intrinsics
+ * else 6), the 64-byte CUDA IPC handles are exchanged by any means, then every rank connects with all handles in
+ * rank order.  During cb_ba_solve the reduced camera system is then summed by schur_finalize_peer_kernel reading
+ * the peers' buffers directly; no NCCL call is made.  world_size <= 16.  Destroy only after every rank is done. */
+typedef struct CbPeerGroup CbPeerGroup;
+int cb_peer_create(int rank, int world_size, int device, int64_t capacity_doubles, CbPeerGroup** out,
+                   char handle_out[64]);
+int cb_peer_connect(CbPeerGroup* group, const char* handles /* world_size x 64 bytes */);
+int cb_peer_destroy(CbPeerGroup* group);
 
 /* Number of kernel launches issued by this library in the calling process so far. */
 int64_t cb_ba_launch_count(void);

@@ -41,6 +41,8 @@ def _worker(rank, world, port, out, refine, transport="nccl"):
 
         r = synthetic.make_rig(12, 3000, 60000, seed=2, refine_intrinsics=refine)
         res, shard = D.solve_sharded(r.cam_flags, r.cam_const, r.n_pts, r.obs_cam, r.obs_pt, r.obs_xy, r.x0, device=rank)
+        if transport == "peer":  # no silent downgrade to NCCL
+            assert D._PEERS and all(g.usable for g in D._PEERS.values()), "CUDA IPC peer mapping unavailable"
         out.put((rank, "ok", res.x, res.cost, res.nfev, res.status))
     except Exception as e:  # pragma: no cover
         import traceback
@@ -56,10 +58,11 @@ def _worker(rank, world, port, out, refine, transport="nccl"):
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("refine,transport", [(False, "nccl"), (True, "nccl"), (False, "torch")])
+@pytest.mark.parametrize("refine,transport", [(False, "nccl"), (True, "nccl"), (False, "torch"), (False, "peer"), (True, "peer")])
 def test_two_gpu_sharded_solve_matches_single_gpu(refine, transport):
     """transport "nccl": the engine's own communicator (ncclAllReduce issued from cb_ba_solve);
-    "torch": the CbAllReduceSum callback over torch.distributed."""
+    "torch": the CbAllReduceSum callback over torch.distributed; "peer": all-reduce over NVLink peer
+    memory fused into the Schur finalize kernel (csrc/cb_peer.cuh)."""
     import torch.multiprocessing as mp
 
     import caliscope_b200 as cb
