@@ -179,3 +179,29 @@ def test_filter_keep_mask_and_percentile_rule_on_reference_errors():
             lo, hi = e[int(np.floor(v))], e[min(int(np.floor(v)) + 1, n - 1)]
             t = filtering._numpy_linear_interp(np.array([lo]), np.array([hi]), np.array([v - np.floor(v)]))[0]
             assert t == np.percentile(e, q)
+
+
+def test_every_device_entry_point_refuses_to_run_without_a_gpu():
+    """The triangulation / undistortion mirrors and the peer-memory transport go through the same C ABI: on a
+    box without a device they raise EngineUnavailable (CB_E_NO_DEVICE), they do not compute on the CPU."""
+    import caliscope_b200 as cb
+    from caliscope_b200 import _lib
+    from caliscope_b200 import triangulation as T
+
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            pytest.skip("CUDA device present")
+    except ImportError:
+        pass
+    proj = np.tile(np.hstack([np.eye(3), np.zeros((3, 1))]), (2, 1, 1))
+    with pytest.raises(cb.EngineUnavailable):
+        T.triangulate_groups(proj, np.array([0, 1], np.int32), np.array([0, 0], np.int64), np.zeros((2, 2)))
+    with pytest.raises(cb.EngineUnavailable):
+        T.undistort_points(np.zeros((3, 2)), None, np.eye(3)[None], [np.zeros(5)], [False])
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    buf = (ctypes.c_char * 64)()
+    assert lib.cb_peer_create(0, 2, 0, 1024, ctypes.byref(h), buf) == -3  # CB_E_NO_DEVICE
+    assert lib.cb_peer_create(5, 2, 0, 1024, ctypes.byref(h), buf) == -1  # CB_E_INVALID: rank >= world_size
