@@ -3,7 +3,8 @@
 //                             cv2.undistortPoints / cv2.fisheye.undistortPoints on float32 copies of the points)
 //   * tri_* kernels        == triangulate_image_points     (reference core/point_data.py:122-229): group observations
 //                             by a 64-bit composite key, DLT system per group, smallest right singular vector.
-// Both are HBM-bound streaming kernels: 32 B (undistort) / ~36 B (DLT, gathered) per observation.
+// Algorithmic traffic is 36 B (undistort) / 24 B (DLT, gathered) per observation, but on B200 both are bound by the fp64
+// pipe (iterative inverse distortion; 4x4 eigen-solve), not by HBM: profiles/r01/ncu_summary_triangulate.jsonl.
 #pragma once
 #include <cstdint>
 
