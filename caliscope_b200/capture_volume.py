@@ -201,3 +201,125 @@ def reprojection_report(self):
         n_cameras=len(self.camera_array.posed_cameras),
         n_points=len(self.world_points.points),
     )
+
+
+# ---- filtering (capture_volume.py:607-753) -------------------------------------------------------------------
+def _pack_columns(frames, cols):
+    """One non-negative int64 per row of each frame, equal iff the ``cols`` tuples are equal (shared
+    offsets/spans over all frames); ``None`` when the ranges do not fit 62 bits."""
+    arrs = [[f[c].to_numpy().astype(np.int64) for c in cols] for f in frames]
+    lo, span = [], []
+    for j in range(len(cols)):
+        vals = [a[j] for a in arrs if len(a[j])]
+        if not vals:
+            lo.append(0)
+            span.append(1)
+            continue
+        mn = min(int(v.min()) for v in vals)
+        mx = max(int(v.max()) for v in vals)
+        lo.append(mn)
+        span.append(mx - mn + 1)
+    total = 1
+    for s in span:
+        total *= s
+    if total >= 2**62:
+        return None
+    out = []
+    for a in arrs:
+        key = np.zeros(len(a[0]), dtype=np.int64)
+        for j in range(len(cols)):
+            key = key * span[j] + (a[j] - lo[j])
+        out.append(key)
+    return out
+
+
+def filter_by_reprojection_thresholds(self, thresholds: dict, min_per_camera: int):
+    """``CaptureVolume._filter_by_reprojection_thresholds`` (capture_volume.py:607-683) without the row-wise
+    pandas work: keep mask by ``filtering.keep_mask`` (index-exact, tests/golden), kept image rows selected by
+    position instead of a 4-key merge, orphaned world points pruned by packed-key membership.  Falls back to the
+    reference implementation when image keys repeat (the merge would then multiply rows)."""
+    from caliscope.core.capture_volume import CaptureVolume
+    from caliscope.core.point_data import STATIC_SYNC_INDEX, ImagePoints, WorldPoints
+
+    from .filtering import keep_mask
+
+    img_df = self.image_points.df
+    obs_keys = ["sync_index", "cam_id", "object_id", "keypoint_id"]
+    if img_df.duplicated(subset=obs_keys).any():
+        return _reference_filter(self, thresholds, min_per_camera)
+    raw = self.reprojection_report.raw_errors
+    _, _, _, mask = ba_arrays(self)  # raw_errors rows are image rows [mask], in order (capture_volume.py:157-170)
+    cam_ids = raw["cam_id"].to_numpy()
+    err = raw["euclidean_error"].to_numpy()
+    uniq, inv = np.unique(cam_ids, return_inverse=True)
+    thr = np.array([float(thresholds[int(c)]) if int(c) in thresholds else np.nan for c in uniq])
+    inv = np.asarray(inv).reshape(-1)
+    if len(err) == 0:
+        keep = np.zeros(0, dtype=bool)
+    elif min_per_camera >= 1:
+        keep = keep_mask(err, inv, thr, int(min_per_camera))
+    else:  # the private method does not validate; a floor below 1 never restores anything (:626-631)
+        keep = err <= thr[inv]
+    rows = np.flatnonzero(mask)[keep]
+    filtered_img_df = img_df.iloc[rows].reset_index(drop=True)
+
+    wdf = self.world_points.df
+    pt_keys = ["sync_index", "object_id", "keypoint_id"]
+    packed = _pack_columns([wdf, filtered_img_df], pt_keys)
+    if packed is None:
+        return _reference_filter(self, thresholds, min_per_camera)
+    filtered_world_df = wdf[np.isin(packed[0], packed[1])].reset_index(drop=True)
+    static_world_df = wdf[wdf["sync_index"] == STATIC_SYNC_INDEX]
+    if not static_world_df.empty:
+        ok = _pack_columns([static_world_df, filtered_img_df], ["object_id", "keypoint_id"])
+        if ok is None:
+            return _reference_filter(self, thresholds, min_per_camera)
+        static_to_keep = static_world_df[np.isin(ok[0], ok[1])]
+        if not static_to_keep.empty:
+            filtered_world_df = pd.concat([filtered_world_df, static_to_keep], ignore_index=True)
+    return CaptureVolume(
+        camera_array=self.camera_array,
+        image_points=ImagePoints(filtered_img_df),
+        world_points=WorldPoints(filtered_world_df),
+        constraints=self.constraints,
+    )
+
+
+def _reference_filter(self, thresholds, min_per_camera):
+    from . import seam
+
+    fn = seam._original_methods.get("_filter_by_reprojection_thresholds")
+    if fn is None:
+        from caliscope.core.capture_volume import CaptureVolume
+
+        fn = CaptureVolume._filter_by_reprojection_thresholds
+        if fn is filter_by_reprojection_thresholds:  # pragma: no cover - patched without the seam's bookkeeping
+            raise RuntimeError("reference filter implementation is not reachable")
+    return fn(self, thresholds, min_per_camera)
+
+
+def filter_by_percentile_error(self, percentile: float, scope="per_camera", min_per_camera: int = 10):
+    """``CaptureVolume.filter_by_percentile_error`` (capture_volume.py:709-753): the per-camera thresholds are
+    ``np.percentile`` of each camera's errors, taken from one grouping pass instead of one boolean mask per camera."""
+    if not (0 < percentile <= 100):
+        raise ValueError(f"percentile must be between 0 and 100, got {percentile}")
+    if min_per_camera < 1:
+        raise ValueError(f"min_per_camera must be >= 1, got {min_per_camera}")
+    raw = self.reprojection_report.raw_errors
+    err = raw["euclidean_error"].to_numpy()
+    keep_percentile = 100 - percentile
+    posed = list(self.camera_array.posed_cameras.keys())
+    if scope == "per_camera":
+        cam_ids = raw["cam_id"].to_numpy()
+        order = np.argsort(cam_ids, kind="stable")
+        sorted_ids = cam_ids[order]
+        thresholds = {}
+        for cam_id in posed:
+            b, e = np.searchsorted(sorted_ids, cam_id, "left"), np.searchsorted(sorted_ids, cam_id, "right")
+            thresholds[cam_id] = float(np.percentile(err[order[b:e]], keep_percentile)) if e > b else float(np.inf)
+    elif scope == "overall":
+        g = float(np.percentile(err, keep_percentile))
+        thresholds = {cam_id: g for cam_id in posed}
+    else:
+        raise ValueError(f"scope must be 'per_camera' or 'overall', got {scope}")
+    return self._filter_by_reprojection_thresholds(thresholds, min_per_camera)

@@ -30,7 +30,8 @@ def install(full: bool = False) -> None:
     ``full=True`` additionally installs seam S2: ``CaptureVolume.optimize`` and
     ``CaptureVolume._compute_img_to_obj_map`` are replaced by the vectorised versions in
     ``caliscope_b200.capture_volume`` (same signatures and results, no per-row Python loops),
-    ``CaptureVolume.reprojection_report`` by the engine-backed, bincount-aggregated version, and seam
+    ``CaptureVolume.reprojection_report`` by the engine-backed, bincount-aggregated version, the percentile /
+    threshold filters by merge-free versions (``filter_by_absolute_error`` reaches them unchanged), and seam
     S3: ``caliscope.core.point_data.triangulate_image_points`` (the DLT triangulation
     ``ImagePoints.triangulate`` calls, point_data.py:474,509) becomes the GPU version."""
     global _original
@@ -47,12 +48,16 @@ def install(full: bool = False) -> None:
         cls = mod.CaptureVolume
         if not _original_methods:
             _original_methods.update(optimize=cls.optimize, _compute_img_to_obj_map=cls._compute_img_to_obj_map,
-                                     reprojection_report=cls.__dict__["reprojection_report"])
+                                     reprojection_report=cls.__dict__["reprojection_report"],
+                                     _filter_by_reprojection_thresholds=cls._filter_by_reprojection_thresholds,
+                                     filter_by_percentile_error=cls.filter_by_percentile_error)
         cls.optimize = cv2b.optimize
         cls._compute_img_to_obj_map = cv2b.fast_img_to_obj_map
         report = functools.cached_property(cv2b.reprojection_report)
         report.__set_name__(cls, "reprojection_report")
         cls.reprojection_report = report
+        cls._filter_by_reprojection_thresholds = cv2b.filter_by_reprojection_thresholds
+        cls.filter_by_percentile_error = cv2b.filter_by_percentile_error
         from . import triangulation
 
         pd_mod = importlib.import_module("caliscope.core.point_data")

@@ -137,7 +137,8 @@ def test_seam_install_full_patches_and_restores(session_volume):
 
     def state():
         return (mod.least_squares, mod.CaptureVolume.optimize, mod.CaptureVolume._compute_img_to_obj_map,
-                mod.CaptureVolume.__dict__["reprojection_report"], pd_mod.triangulate_image_points)  # fmt: skip
+                mod.CaptureVolume.__dict__["reprojection_report"], mod.CaptureVolume._filter_by_reprojection_thresholds,
+                mod.CaptureVolume.filter_by_percentile_error, pd_mod.triangulate_image_points)  # fmt: skip
 
     before = state()
     with seam.installed(full=True):
@@ -146,6 +147,8 @@ def test_seam_install_full_patches_and_restores(session_volume):
         assert mod.CaptureVolume._compute_img_to_obj_map is S2.fast_img_to_obj_map
         assert mod.CaptureVolume.__dict__["reprojection_report"].func is S2.reprojection_report
         assert pd_mod.triangulate_image_points is triangulation.triangulate_image_points
+        assert mod.CaptureVolume._filter_by_reprojection_thresholds is S2.filter_by_reprojection_thresholds
+        assert mod.CaptureVolume.filter_by_percentile_error is S2.filter_by_percentile_error
     assert state() == before
 
 
@@ -182,6 +185,80 @@ def test_s2_reprojection_report_equals_reference(session_volume, monkeypatch):
         import pandas as pd
 
         pd.testing.assert_frame_equal(got.raw_errors, ref.raw_errors)
+
+
+def _static_volume(cv):
+    """The session with its first object declared static: world rows at STATIC_SYNC_INDEX, observations keep
+    their sync_index (point_data.py:506-527)."""
+    from caliscope.core.capture_volume import CaptureVolume
+    from caliscope.core.constraints import ConstraintSet
+    from caliscope.core.point_data import STATIC_SYNC_INDEX, WorldPoints
+
+    wdf = cv.world_points.df.copy()
+    first = wdf.drop_duplicates(subset=["object_id", "keypoint_id"]).copy().reset_index(drop=True)
+    first["sync_index"] = STATIC_SYNC_INDEX
+    oid = int(wdf["object_id"].iloc[0])
+    cs = ConstraintSet(distances=(), static_object_ids=frozenset({oid}))
+    return CaptureVolume(cv.camera_array, cv.image_points, WorldPoints(first), constraints=cs)
+
+
+@pytest.mark.parametrize("kind", ["session", "static", "half_world"])
+def test_s2_filters_equal_the_reference(session_volume, kind):
+    """capture_volume.py:607-753: same filtered image rows, same pruned world rows (order, index, dtypes), for
+    per-camera and overall percentiles, an absolute threshold, and a min_per_camera floor that has to restore rows."""
+    import pandas as pd
+    from caliscope.core.capture_volume import CaptureVolume
+    from caliscope.core.point_data import WorldPoints
+    from caliscope_b200 import capture_volume as S2
+
+    cv = session_volume
+    if kind == "static":
+        cv = _static_volume(cv)
+    elif kind == "half_world":
+        wdf = cv.world_points.df
+        cv = CaptureVolume(cv.camera_array, cv.image_points, WorldPoints(wdf.iloc[: len(wdf) // 2].copy()))
+
+    def same(a, b):
+        pd.testing.assert_frame_equal(a.image_points.df, b.image_points.df)
+        pd.testing.assert_frame_equal(a.world_points.df, b.world_points.df)
+        assert a.constraints == b.constraints
+        assert np.array_equal(a.img_to_obj_map, b.img_to_obj_map)
+
+    for pct, scope, floor in ((5.0, "per_camera", 10), (2.5, "overall", 10), (60.0, "per_camera", 400), (100.0, "per_camera", 7)):
+        ref = cv.filter_by_percentile_error(pct, scope, floor)
+        got = S2.filter_by_percentile_error(_with_s2_filter(cv), pct, scope, floor)
+        same(got, ref)
+    thr = {cid: 0.8 for cid in cv.camera_array.posed_cameras}
+    same(S2.filter_by_reprojection_thresholds(cv, thr, 25), cv._filter_by_reprojection_thresholds(thr, 25))
+    # a camera missing from the thresholds dict keeps nothing but its floor
+    thr.pop(next(iter(thr)))
+    same(S2.filter_by_reprojection_thresholds(cv, thr, 3), cv._filter_by_reprojection_thresholds(thr, 3))
+    with pytest.raises(ValueError):
+        S2.filter_by_percentile_error(cv, 0.0)
+    with pytest.raises(ValueError):
+        S2.filter_by_percentile_error(cv, 5.0, "per_frame")
+    with pytest.raises(ValueError):
+        S2.filter_by_percentile_error(cv, 5.0, "per_camera", 0)
+
+
+class _S2FilterProxy:
+    """``filter_by_percentile_error`` calls ``self._filter_by_reprojection_thresholds``: route that to the S2 version
+    without installing the seam (which needs the CUDA library)."""
+
+    def __init__(self, cv):
+        self._cv = cv
+
+    def __getattr__(self, name):
+        return getattr(self._cv, name)
+
+    def _filter_by_reprojection_thresholds(self, thresholds, min_per_camera):
+        from caliscope_b200 import capture_volume as S2
+
+        return S2.filter_by_reprojection_thresholds(self._cv, thresholds, min_per_camera)
+
+
+def _with_s2_filter(cv):
+    return _S2FilterProxy(cv)
 
 
 def test_s2_optimize_passes_the_reference_constraint_arrays(monkeypatch):
