@@ -1590,7 +1590,7 @@ int cb_ba_rmse_px(CbBaProblem* p, const double* x, double* overall, double* per_
 // order) may be NULL.
 int cb_ba_cull(CbBaProblem* p, const double* x, const double* thresholds, int32_t min_per_camera, CbBaProblem** out,
                int64_t* n_kept, uint8_t* keep_mask, void* stream) {
-  if (!p || !x || !thresholds || !out || min_per_camera < 1) { g_last_error = "cb_ba_cull: bad argument"; return CB_E_INVALID; }
+  if (!p || !x || !thresholds || !out || min_per_camera < 0) { g_last_error = "cb_ba_cull: bad argument"; return CB_E_INVALID; }
   *out = nullptr;
   CB_CUDA(cudaSetDevice(p->device));
   cudaStream_t st = (cudaStream_t)stream;

@@ -343,6 +343,80 @@ def gather_points(x_local: np.ndarray, n_camera_params: int, n_pts_global: int, 
     return np.concatenate([x_local[:n_camera_params], pts.ravel()])
 
 
+def global_cull_thresholds(err_local, cam_local, n_cams: int, percentile: float, min_per_camera: int = 10, group=None,
+                           scope: str = "per_camera") -> np.ndarray:
+    """Per-camera pixel thresholds of ``filter_by_percentile_error`` + the ``min_per_camera`` floor of
+    ``_filter_by_reprojection_thresholds`` (capture_volume.py:607-646, 709-753) when the observations are
+    sharded: every rank contributes its local euclidean errors, every rank returns the identical final
+    thresholds ``t`` such that the reference's keep mask is exactly ``err <= t[camera]`` (apply locally with
+    ``BAProblem.cull(x, t, min_per_camera=0)``).
+
+    One all-gather of (error, camera) — 12 B per observation over NVLink — then a two-key stable sort on the
+    group's device; the two order statistics ``np.percentile`` interpolates between are read at their exact
+    global positions, so the thresholds are bit-identical to the single-process ones."""
+    import torch
+    import torch.distributed as dist
+
+    from .filtering import _numpy_linear_interp
+
+    if not (0 < percentile <= 100):
+        raise ValueError(f"percentile must be between 0 and 100, got {percentile}")
+    if min_per_camera < 1:
+        raise ValueError(f"min_per_camera must be >= 1, got {min_per_camera}")
+    world = dist.get_world_size(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    e = torch.as_tensor(np.ascontiguousarray(err_local, dtype=np.float64)).to(dev)
+    c = torch.as_tensor(np.ascontiguousarray(cam_local, dtype=np.int64)).to(dev)
+    n_loc = torch.tensor([e.numel()], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, n_loc, group=group)
+    sizes = [int(t.item()) for t in sizes]
+    cap = max(max(sizes), 1)
+    pad_e = torch.zeros(cap, dtype=torch.float64, device=dev)
+    pad_c = torch.zeros(cap, dtype=torch.int64, device=dev)
+    pad_e[: e.numel()] = e
+    pad_c[: c.numel()] = c
+    ge = [torch.empty(cap, dtype=torch.float64, device=dev) for _ in range(world)]
+    gc = [torch.empty(cap, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(ge, pad_e, group=group)
+    dist.all_gather(gc, pad_c, group=group)
+    E = torch.cat([t[:n] for t, n in zip(ge, sizes)])
+    Cm = torch.cat([t[:n] for t, n in zip(gc, sizes)])
+    # sort by (camera, error): stable sort on the minor key first
+    i1 = torch.sort(E, stable=True).indices
+    i2 = torch.sort(Cm[i1], stable=True).indices
+    Es = E[i1][i2]
+    cnt = torch.bincount(Cm, minlength=n_cams).cpu().numpy().astype(np.int64)
+    start = np.concatenate([[0], np.cumsum(cnt)[:-1]])
+    keep_q = 100 - percentile
+    if scope == "per_camera":
+        v = (cnt - 1).astype(np.float64) * (keep_q / 100.0)
+        lo_i = np.floor(np.maximum(v, 0)).astype(np.int64)
+        hi_i = np.minimum(lo_i + 1, np.maximum(cnt - 1, 0))
+        has = cnt > 0
+        pos = np.concatenate([(start + lo_i)[has], (start + hi_i)[has]])
+        vals = Es[torch.as_tensor(pos, device=dev)].cpu().numpy() if has.any() else np.zeros(0)
+        lo = np.zeros(n_cams)
+        hi = np.zeros(n_cams)
+        lo[has], hi[has] = vals[: has.sum()], vals[has.sum() :]
+        thr = _numpy_linear_interp(lo, hi, v - np.floor(v))
+        thr[~has] = np.inf
+    elif scope == "overall":
+        thr = np.full(n_cams, float(np.percentile(E.cpu().numpy(), keep_q)))
+    else:
+        raise ValueError(f"scope must be 'per_camera' or 'overall', got {scope}")
+    # safety floor on the GLOBAL counts: a camera's sorted segment is kept up to a prefix, so restoring the
+    # lowest-error dropped rows is moving the threshold to the (need)-th dropped value (capture_volume.py:626-646)
+    Cs = Cm[i1][i2]
+    kept = torch.bincount(Cs[Es <= torch.as_tensor(thr, device=dev)[Cs]], minlength=n_cams).cpu().numpy().astype(np.int64)
+    short = np.flatnonzero((kept < min_per_camera) & (kept < cnt))
+    if len(short):
+        need = np.minimum(min_per_camera, cnt[short]) - kept[short]
+        pos = start[short] + kept[short] + need - 1
+        thr[short] = Es[torch.as_tensor(pos, device=dev)].cpu().numpy()
+    return thr
+
+
 def solve_sharded(cam_flags, cam_const, n_pts, obs_cam, obs_pt, obs_xy, x0, *, device: int, group=None, constraints=None,
                   **solve_kw):
     """Shard by point (by constraint component when rigid-distance rows are present), solve with one

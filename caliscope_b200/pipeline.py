@@ -45,3 +45,61 @@ def solve_filter_resolve(cam_flags, cam_const, n_pts, obs_cam, obs_pt, obs_xy, x
         stages.append(s3)
         rmse.append(prob2.overall_rmse_px(s3.x))
     return PipelineResult(x=s3.x, keep=keep, stages=stages, rmse_px=rmse)
+
+
+def solve_filter_resolve_sharded(cam_flags, cam_const, n_pts, obs_cam, obs_pt, obs_xy, x0, *, device: int, group=None,
+                                 filter_percentile: float = 2.5, min_per_camera: int = 10, ftol: float = 1e-8,
+                                 verbose: int = 0) -> PipelineResult:  # fmt: skip
+    """The same loop with the observations sharded by point over the ranks of ``group`` (BASELINE.json config 5 on
+    several GPUs): every solve is the sharded solve of ``distributed.solve_sharded``; the cull thresholds are the
+    GLOBAL per-camera percentiles (``distributed.global_cull_thresholds``: one all-gather of the pixel errors), the
+    keep mask and the compaction stay local to each rank.  Every rank returns the full parameter vector and the full
+    keep mask (in the caller's observation order)."""
+    import torch
+    import torch.distributed as dist
+
+    from . import distributed as D
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    obs_cam = np.ascontiguousarray(obs_cam, dtype=np.int32)
+    obs_pt = np.ascontiguousarray(obs_pt, dtype=np.int32)
+    obs_xy = np.ascontiguousarray(obs_xy, dtype=np.float64).reshape(-1, 2)
+    cam_flags = np.asarray(cam_flags)
+    f_median = float(np.median(np.asarray(cam_const, dtype=np.float64).reshape(-1, 9)[:, 0]))
+    ncp = int(np.where(cam_flags & 1, 9, 6).sum())
+    shard = D.shard_points(obs_cam, obs_pt, obs_xy, n_pts, rank, world)
+    kw = dict(rank=rank, world_size=world, verbose=verbose,
+              **D.transport_kwargs(device, group, n_camera_dims=len(cam_flags) * (9 if np.any(cam_flags & 1) else 6)))  # fmt: skip
+    stages: list[SolveResult] = []
+    rmse: list[float] = []
+
+    def global_rmse(prob, x) -> float:
+        e = prob.reproj_errors_px(x)
+        acc = torch.tensor([float(np.sum(e * e)), float(len(e))], dtype=torch.float64,
+                           device="cuda" if dist.get_backend(group) == "nccl" else "cpu")  # fmt: skip
+        dist.all_reduce(acc, group=group)
+        return float(np.sqrt(acc[0].item() / max(acc[1].item(), 1.0)))
+
+    with BAProblem(cam_flags, cam_const, shard.n_pts, shard.obs_cam, shard.obs_pt, shard.obs_xy, device=device) as prob:
+        dist.barrier(group=group)
+        s1 = prob.solve(D.local_x(np.asarray(x0, dtype=np.float64), ncp, shard), ftol=ftol, **kw)
+        stages.append(s1)
+        rmse.append(global_rmse(prob, s1.x))
+        s2 = prob.solve(s1.x, loss="soft_l1", f_scale=1.0 / f_median, ftol=1e-4, max_nfev=2000, **kw)
+        stages.append(s2)
+        e = prob.reproj_errors_px(s2.x)
+        err = np.sqrt(np.sum(e * e, axis=1))
+        rmse.append(global_rmse(prob, s2.x))
+        thr = D.global_cull_thresholds(err, shard.obs_cam, len(cam_flags), filter_percentile, min_per_camera, group)
+        prob2, keep_local = prob.cull(s2.x, thr, 0, want_mask=True)
+    with prob2:
+        s3 = prob2.solve(s2.x, ftol=ftol, **kw)
+        stages.append(s3)
+        rmse.append(global_rmse(prob2, s3.x))
+    x = D.gather_points(s3.x, ncp, n_pts, shard, group)
+    # full keep mask: every rank contributes its observations' flags at their global positions
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    full = torch.zeros(len(obs_cam), dtype=torch.int32, device=dev)
+    full[torch.as_tensor(shard.obs_index, device=dev)] = torch.as_tensor(keep_local.astype(np.int32), device=dev)
+    dist.all_reduce(full, group=group)
+    return PipelineResult(x=x, keep=full.cpu().numpy().astype(bool), stages=stages, rmse_px=rmse)

@@ -211,8 +211,8 @@ class BAProblem:
         thr = np.ascontiguousarray(thresholds, dtype=np.float64)
         if thr.shape != (self.n_cams,):
             raise ValueError(f"thresholds must have shape ({self.n_cams},)")
-        if min_per_camera < 1:
-            raise ValueError(f"min_per_camera must be >= 1, got {min_per_camera}")
+        if min_per_camera < 0:
+            raise ValueError(f"min_per_camera must be >= 0 (0: thresholds only), got {min_per_camera}")
         mask = np.empty(self.n_obs, np.uint8) if want_mask else None
         h = C.c_void_p()
         n_kept = C.c_int64()

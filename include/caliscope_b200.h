@@ -187,7 +187,9 @@ int cb_ba_rmse_px(CbBaProblem* p, const double* x, double* overall, double* per_
 /* Device-side observation cull == _filter_by_reprojection_thresholds (capture_volume.py:607-646) at array level:
  * keep error <= thresholds[camera] (host, n_cams), restore lowest-error observations up to min_per_camera, compact
  * the observation list on the device and build the filtered problem (same cameras and point numbering) from it.
- * keep_mask: host, n_obs bytes in the caller's observation order, or NULL.  *out must be destroyed by the caller. */
+ * keep_mask: host, n_obs bytes in the caller's observation order, or NULL.  *out must be destroyed by the caller.
+ * min_per_camera = 0 applies the thresholds only (sharded solves: the floor is a global property and is folded into the
+ * thresholds by the caller, caliscope_b200/distributed.global_cull_thresholds). */
 int cb_ba_cull(CbBaProblem* p, const double* x, const double* thresholds, int32_t min_per_camera, CbBaProblem** out,
                int64_t* n_kept, uint8_t* keep_mask, void* stream);
 

@@ -114,3 +114,70 @@ def test_component_aware_sharding_keeps_rigid_bodies_on_one_rank(world):
         assert np.array_equal(dist, g["distances"][s.constraint_index])
         assert len(s.constraint_index) > 0
     assert np.all(seen_obs == 1) and np.all(seen_con == 1) and np.all(seen_pts == 1)
+
+
+def _cull_worker(rank, world, port, out):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from caliscope_b200 import distributed as D
+
+        rng = np.random.default_rng(3)
+        n, n_cams = 6000, 7
+        err = rng.gamma(2.0, 0.4, n)
+        cam = rng.integers(0, n_cams - 1, n)  # the last camera has no observations
+        cam[:3] = 5
+        err[cam == 4] += 10.0  # one camera far above an absolute threshold
+        owner = rng.integers(0, world, n)
+        sel = owner == rank
+        res = {}
+        for pct, floor in ((2.5, 10), (50.0, 10), (100.0, 25), (99.9, 400)):
+            res[(pct, floor, "per_camera")] = D.global_cull_thresholds(err[sel], cam[sel], n_cams, pct, floor)
+        res[(5.0, 10, "overall")] = D.global_cull_thresholds(err[sel], cam[sel], n_cams, 5.0, 10, scope="overall")
+        out.put((rank, "ok", res))
+    except Exception as e:  # pragma: no cover
+        import traceback
+
+        out.put((rank, "err: " + repr(e) + traceback.format_exc(), None))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_cull_thresholds_equal_the_single_process_filter():
+    """filter_by_percentile_error + the min_per_camera floor over observations split across 2 ranks (gloo):
+    the keep mask ``err <= t[camera]`` from the gathered thresholds equals filtering.keep_mask on the whole list."""
+    import torch.multiprocessing as mp
+
+    from caliscope_b200 import filtering
+
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_cull_worker, args=(k, 2, port, out)) for k in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted([out.get(timeout=300) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    assert [r[1] for r in results] == ["ok", "ok"], results
+    rng = np.random.default_rng(3)
+    n, n_cams = 6000, 7
+    err = rng.gamma(2.0, 0.4, n)
+    cam = rng.integers(0, n_cams - 1, n)
+    cam[:3] = 5
+    err[cam == 4] += 10.0
+    for key, thr0 in results[0][2].items():
+        pct, floor, scope = key
+        assert np.array_equal(thr0, results[1][2][key])  # identical on both ranks
+        keep_q = 100 - pct
+        if scope == "per_camera":
+            base = np.array([np.percentile(err[cam == c], keep_q) if np.any(cam == c) else np.inf for c in range(n_cams)])
+        else:
+            base = np.full(n_cams, np.percentile(err, keep_q))
+        ref = filtering.keep_mask(err, cam, base, floor)
+        assert np.array_equal(err <= thr0[cam], ref), key
+        untouched = np.array([np.sum((cam == c) & (err <= base[c])) >= min(floor, np.sum(cam == c)) for c in range(n_cams)])
+        assert np.array_equal(thr0[untouched], base[untouched])  # bit-identical to np.percentile where no floor applies
