@@ -2,7 +2,6 @@
 torch.distributed (gloo, world_size 2)."""
 from __future__ import annotations
 
-import ctypes
 import os
 import socket
 
