@@ -52,12 +52,39 @@ def make_workload(name: str):
     return synthetic.make_rig(n_cams, n_pts, n_obs, refine_intrinsics=refine, seed=0, name=name)
 
 
+L2_MB = 126.0
+FLUSH_BYTES = 256 << 20
+
+
+def working_set_mb(n_cams: int, n_pts: int, n_obs: int, P: int, n_gpus: int) -> float:
+    """Per-GPU working set of one LM iteration: Jacobian rows (20 / 28 doubles per observation) + the dense k-major Schur
+    factor (3 n_pts x ceil(n_cams P / 96) 96 doubles)."""
+    rows = n_obs * (160 if P == 6 else 224) / n_gpus
+    zt = 3 * n_pts * (-(-n_cams * P // 96) * 96) * 8 / n_gpus
+    return (rows + zt) / 1e6
+
+
+def needs_l2_flush(n_cams: int, n_pts: int, n_obs: int, P: int, n_gpus: int) -> bool:
+    return working_set_mb(n_cams, n_pts, n_obs, P, n_gpus) <= 1.5 * L2_MB
+
+
+def _l2_note(n_cams: int, n_pts: int, n_obs: int, P: int, n_gpus: int) -> str:
+    mb = working_set_mb(n_cams, n_pts, n_obs, P, n_gpus)
+    if not needs_l2_flush(n_cams, n_pts, n_obs, P, n_gpus):
+        return f"per-iteration working set (Jacobian rows + Schur factor, {mb:.0f} MB per GPU) exceeds the 126 MB L2; no explicit flush"
+    return (f"per-iteration working set is {mb:.0f} MB per GPU, so the 126 MB L2 is flushed before every timed step by writing a "
+            f"{FLUSH_BYTES >> 20} MB buffer (inside the timed region)")
+
+
 def workload_config(name: str, rig, n_gpus: int) -> dict:
     n_cams, n_pts, n_obs, refine = WORKLOADS[name]
     return {
         "workload": f"{name}: synthetic {n_cams}-cam / {n_pts}-point / {n_obs}-observation ring rig, "
         + ("extrinsics + focal scale + k1 + k2" if refine else "extrinsics only")
-        + ", seed 0, 0.5 px noise (BASELINE.json configs[3])",
+        + ", seed 0, 0.5 px noise ("
+        + {"cfg2": "BASELINE.json configs[1]", "cfg3": "BASELINE.json configs[2]", "cfg4": "BASELINE.json configs[3]",
+           "cfg4_intrinsics": "BASELINE.json configs[3] with Pc = 9"}.get(name, "profiling workload, not a BASELINE config")
+        + ")",
         "n_cams": n_cams,
         "n_pts": n_pts,
         "n_obs": n_obs,
@@ -66,7 +93,7 @@ def workload_config(name: str, rig, n_gpus: int) -> dict:
         "ftol": 1e-8,
         "sharding": "single GPU" if n_gpus == 1 else f"observations sharded by point over {n_gpus} GPUs, "
         "one sum-all-reduce of the reduced camera system per LM trial (transport: see allreduce_transport)",
-        "l2": "per-iteration working set (Jacobian rows + Schur factor, >500 MB) exceeds the 126 MB L2; no explicit flush",
+        "l2": _l2_note(n_cams, n_pts, n_obs, 9 if refine else 6, n_gpus),
     }
 
 
@@ -281,8 +308,14 @@ def run_ours(args) -> None:
     d_xy = torch.from_numpy(np.ascontiguousarray(l_xy)).cuda()
     prob = cb.BAProblem(rig.cam_flags, rig.cam_const, l_npts, d_cam, d_pt, d_xy, device=dev, stream=stream)
     res = None
+    n_c, n_p, n_o, refine = WORKLOADS[args.workload]
+    flush = None
+    if needs_l2_flush(n_c, n_p, n_o, 9 if refine else 6, world):
+        flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device="cuda")
     barrier()
-    for _ in range(args.warmup):
+    for i in range(args.warmup):
+        if flush is not None:
+            flush.fill_(i & 0x7F)
         res = prob.solve(x0, **solve_kw)
     sampler = ClockSampler(dev)
     if rank == 0:
@@ -295,7 +328,9 @@ def run_ours(args) -> None:
     nit = nfev = 0
     rj_ms = 0.0
     rj_n = 0
-    for _ in range(args.steps):
+    for i in range(args.steps):
+        if flush is not None:
+            flush.fill_(i & 0x7F)  # evict the previous step's data from L2 (same stream as the solve)
         res = prob.solve(x0, **solve_kw)
         nit += res.nit
         nfev += res.nfev
