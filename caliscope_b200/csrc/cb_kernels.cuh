@@ -657,11 +657,7 @@ schur_syrk_kernel(const double* __restrict__ Zt, size_t LD, const double* __rest
 
   // ---------------- diagonal pair ----------------
   int bsel[3], brow[3], bcol[3];
-#ifdef CB_SY_MAP_B
-  const int wmap = (wid & 1) * 4 + (wid >> 1);  // 3-block lists on even warps
-#else
   const int wmap = wid;
-#endif
 #pragma unroll
   for (int b = 0; b < 3; ++b) {
     bsel[b] = SY_DIAG_BLOCKS[wmap][b][0];
