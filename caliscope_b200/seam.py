@@ -32,8 +32,9 @@ def install(full: bool = False) -> None:
     ``caliscope_b200.capture_volume`` (same signatures and results, no per-row Python loops),
     ``CaptureVolume.reprojection_report`` by the engine-backed, bincount-aggregated version, the percentile /
     threshold filters by merge-free versions (``filter_by_absolute_error`` reaches them unchanged), and seam
-    S3: ``caliscope.core.point_data.triangulate_image_points`` (the DLT triangulation
-    ``ImagePoints.triangulate`` calls, point_data.py:474,509) becomes the GPU version."""
+    S3: ``caliscope.core.point_data.triangulate_image_points`` (point_data.py:122-229) and
+    ``ImagePoints.triangulate`` (:416-559; pixels -> undistortion -> DLT in one device call) become the GPU
+    versions."""
     global _original
     from . import _lib
 
@@ -64,6 +65,9 @@ def install(full: bool = False) -> None:
         if "triangulate_image_points" not in _original_functions:
             _original_functions["triangulate_image_points"] = pd_mod.triangulate_image_points
         pd_mod.triangulate_image_points = triangulation.triangulate_image_points
+        if "ImagePoints.triangulate" not in _original_functions:
+            _original_functions["ImagePoints.triangulate"] = pd_mod.ImagePoints.triangulate
+        pd_mod.ImagePoints.triangulate = triangulation.triangulate
 
 
 def uninstall() -> None:
@@ -79,7 +83,10 @@ def uninstall() -> None:
     if _original_functions:
         pd_mod = importlib.import_module("caliscope.core.point_data")
         for name, fn in _original_functions.items():
-            setattr(pd_mod, name, fn)
+            if name == "ImagePoints.triangulate":
+                pd_mod.ImagePoints.triangulate = fn
+            else:
+                setattr(pd_mod, name, fn)
         _original_functions.clear()
 
 

@@ -127,31 +127,122 @@ def triangulate_image_points(
     n_obs = len(keypoint_ids)
     if n_obs < 2:
         return _empty()
+    _, proj, row = _camera_rows(projection_matrices, camera_ids)
+    key = pack_keys(sync_indices, object_ids, keypoint_ids)
+    xyz, count, rep, sig = triangulate_groups(proj, row, key, img_xy, device=device, stats=stats)
+    return _reference_order(sync_indices, object_ids, keypoint_ids, xyz, count, rep, sig)
+
+
+def _camera_rows(projection_matrices: dict, camera_ids: np.ndarray):
+    """Sorted camera ids, their stacked [R|t] and the row of every observation's camera (KeyError like the
+    reference's dict lookup when a camera has no projection matrix)."""
     cam_ids = np.array(sorted(projection_matrices), dtype=np.int64)
     proj = np.stack([np.asarray(projection_matrices[int(c)], dtype=np.float64)[:3, :4] for c in cam_ids])
     row = np.searchsorted(cam_ids, camera_ids)
     if np.any(row >= len(cam_ids)) or np.any(cam_ids[np.minimum(row, len(cam_ids) - 1)] != camera_ids):
         missing = np.setdiff1d(camera_ids, cam_ids)
-        raise KeyError(int(missing[0]))  # the reference indexes the dict: KeyError on an unknown camera
-    key = pack_keys(sync_indices, object_ids, keypoint_ids)
-    xyz, count, rep, sig = triangulate_groups(proj, row, key, img_xy, device=device, stats=stats)
+        raise KeyError(int(missing[0]))
+    return cam_ids, proj, row
+
+
+def _reference_order(sync_indices, object_ids, keypoint_ids, xyz, count, rep, sig):
+    """Groups seen by >= 2 rows, camera sets in order of first appearance over the key-sorted groups (the
+    reference's dict insertion order, point_data.py:164-172), keys ascending inside a set; the group size is
+    part of a set's identity next to its 128-bit camera-multiset signature."""
     keep = np.flatnonzero(count >= 2)
     if len(keep) == 0:
         return _empty()
-    # camera sets in order of first appearance over the key-sorted groups (dict insertion order,
-    # point_data.py:164-172); the group size is part of the identity next to the 128-bit signature
     ident = np.empty(len(keep), dtype=[("a", np.uint64), ("b", np.uint64), ("n", np.int64)])
     ident["a"], ident["b"], ident["n"] = sig[keep, 0], sig[keep, 1], count[keep]
     _, first, inverse = np.unique(ident, return_index=True, return_inverse=True)
-    order = np.argsort(first[inverse], kind="stable")
+    order = np.argsort(first[np.asarray(inverse).reshape(-1)], kind="stable")
     sel = keep[order]
     r = rep[sel]
     return (
-        sync_indices[r].astype(np.int64),
-        object_ids[r].astype(np.int64),
-        keypoint_ids[r].astype(np.int64),
+        np.asarray(sync_indices)[r].astype(np.int64),
+        np.asarray(object_ids)[r].astype(np.int64),
+        np.asarray(keypoint_ids)[r].astype(np.int64),
         xyz[sel].copy(),
     )
+
+
+def triangulate_pixels(projection_matrices: dict, camera_models: dict, sync_indices, camera_ids, object_ids, keypoint_ids,
+                       img_px, *, device: int = 0, stats: TriangulationStats | None = None):
+    """``_undistort_batch`` + ``triangulate_image_points`` (point_data.py:236-252, 122-229) in one device call:
+    ``img_px`` are raw pixels, ``camera_models[cam_id] = (matrix 3x3, distortions, fisheye)``; the undistorted
+    coordinates never come back to the host (``cb_undistort_triangulate``)."""
+    sync_indices = np.asarray(sync_indices)
+    camera_ids = np.asarray(camera_ids)
+    object_ids = np.asarray(object_ids)
+    keypoint_ids = np.asarray(keypoint_ids)
+    if len(keypoint_ids) < 2:
+        return _empty()
+    cam_ids, proj, row = _camera_rows(projection_matrices, camera_ids)
+    mats = np.stack([np.asarray(camera_models[int(c)][0], dtype=np.float64) for c in cam_ids])
+    dists = [np.asarray(camera_models[int(c)][1], dtype=np.float64).ravel() for c in cam_ids]
+    fish = np.array([1 if camera_models[int(c)][2] else 0 for c in cam_ids], dtype=np.int32)
+    key = pack_keys(sync_indices, object_ids, keypoint_ids)
+    xyz, count, rep, sig = triangulate_groups(proj, row, key, img_px, device=device, stats=stats, undistort=(mats, dists, fish))
+    return _reference_order(sync_indices, object_ids, keypoint_ids, xyz, count, rep, sig)
+
+
+def triangulate(self, camera_array, static_object_ids: frozenset = frozenset()):
+    """Drop-in for ``ImagePoints.triangulate`` (point_data.py:416-559): same ``WorldPoints`` (rows, order, columns,
+    frame times, static objects at ``STATIC_SYNC_INDEX``), with undistortion and DLT in one device call per part
+    instead of a per-camera OpenCV loop followed by per-camera-set SVD batches."""
+    import pandas as pd
+    from caliscope.core.point_data import STATIC_SYNC_INDEX, WORLD_POINT_COLUMNS, WorldPoints
+
+    def empty():
+        return WorldPoints(pd.DataFrame(columns=list(WORLD_POINT_COLUMNS.keys())))
+
+    xy_df = self.df
+    if xy_df.empty:
+        return empty()
+    cam_ids_in_data = xy_df["cam_id"].unique()
+    posed_cam_ids = list(camera_array.posed_cam_id_to_index.keys())
+    valid_cam_ids = [c for c in cam_ids_in_data if c in posed_cam_ids]
+    if not valid_cam_ids:
+        return empty()
+    pm = camera_array.normalized_projection_matrices
+    # the reference undistorts every camera that has rows, posed or not, and fails on a missing calibration
+    # (camera_array.py:152-153) before it filters to posed cameras
+    for cam_id, camera in camera_array.cameras.items():
+        if (camera.matrix is None or camera.distortions is None) and bool((xy_df["cam_id"] == cam_id).any()):
+            raise ValueError(f"Camera {cam_id} lacks intrinsic calibration; cannot undistort points.")
+    known = xy_df["cam_id"].isin(list(camera_array.cameras.keys()))
+    valid_data = xy_df[known & xy_df["cam_id"].isin(valid_cam_ids)]
+    if valid_data.empty:
+        return empty()
+    models = {int(c): (camera_array.cameras[c].matrix, camera_array.cameras[c].distortions, camera_array.cameras[c].fisheye)
+              for c in pm}  # fmt: skip
+    frame_times = xy_df.groupby("sync_index")["frame_time"].mean()
+    if static_object_ids:
+        static_mask = valid_data["object_id"].isin(static_object_ids)
+        mobile_data, static_data = valid_data[~static_mask], valid_data[static_mask]
+    else:
+        mobile_data, static_data = valid_data, valid_data.iloc[0:0]
+
+    def part(data, sync_arr):
+        return triangulate_pixels(pm, models, sync_arr, data["cam_id"].to_numpy(), data["object_id"].to_numpy(),
+                                  data["keypoint_id"].to_numpy(), data[["img_loc_x", "img_loc_y"]].to_numpy(np.float64))  # fmt: skip
+
+    parts = []
+    if not mobile_data.empty:
+        s, o, k, xyz = part(mobile_data, mobile_data["sync_index"].to_numpy())
+        if len(k) > 0:
+            parts.append(pd.DataFrame({"sync_index": s, "object_id": o, "keypoint_id": k, "x_coord": xyz[:, 0],
+                                       "y_coord": xyz[:, 1], "z_coord": xyz[:, 2],
+                                       "frame_time": frame_times.reindex(s).to_numpy()}))  # fmt: skip
+    if not static_data.empty:
+        s, o, k, xyz = part(static_data, np.full(len(static_data), STATIC_SYNC_INDEX, dtype=np.int64))
+        if len(k) > 0:
+            parts.append(pd.DataFrame({"sync_index": s, "object_id": o, "keypoint_id": k, "x_coord": xyz[:, 0],
+                                       "y_coord": xyz[:, 1], "z_coord": xyz[:, 2],
+                                       "frame_time": np.full(len(k), np.nan)}))  # fmt: skip
+    if not parts:
+        return empty()
+    return WorldPoints(pd.concat(parts, ignore_index=True))
 
 
 def undistort_points(points, cam_rows, matrices, distortions, fisheye, *, output: str = "normalized", device: int = 0,

@@ -138,7 +138,8 @@ def test_seam_install_full_patches_and_restores(session_volume):
     def state():
         return (mod.least_squares, mod.CaptureVolume.optimize, mod.CaptureVolume._compute_img_to_obj_map,
                 mod.CaptureVolume.__dict__["reprojection_report"], mod.CaptureVolume._filter_by_reprojection_thresholds,
-                mod.CaptureVolume.filter_by_percentile_error, pd_mod.triangulate_image_points)  # fmt: skip
+                mod.CaptureVolume.filter_by_percentile_error, pd_mod.triangulate_image_points,
+                pd_mod.ImagePoints.triangulate)  # fmt: skip
 
     before = state()
     with seam.installed(full=True):
@@ -147,6 +148,7 @@ def test_seam_install_full_patches_and_restores(session_volume):
         assert mod.CaptureVolume._compute_img_to_obj_map is S2.fast_img_to_obj_map
         assert mod.CaptureVolume.__dict__["reprojection_report"].func is S2.reprojection_report
         assert pd_mod.triangulate_image_points is triangulation.triangulate_image_points
+        assert pd_mod.ImagePoints.triangulate is triangulation.triangulate
         assert mod.CaptureVolume._filter_by_reprojection_thresholds is S2.filter_by_reprojection_thresholds
         assert mod.CaptureVolume.filter_by_percentile_error is S2.filter_by_percentile_error
     assert state() == before
@@ -259,6 +261,29 @@ class _S2FilterProxy:
 
 def _with_s2_filter(cv):
     return _S2FilterProxy(cv)
+
+
+@pytest.mark.parametrize("static", [False, True])
+def test_s3_triangulate_equals_the_reference_world_points(session_volume, monkeypatch, static):
+    """ImagePoints.triangulate (point_data.py:416-559) through the fused pixels -> undistort -> DLT call, the device
+    call replaced by its oracle-backed stand-in: same rows, order, columns and frame times as the reference."""
+    import pandas as pd
+    from caliscope_b200 import triangulation as T
+    from tests._util import fake_triangulate_groups
+
+    monkeypatch.setattr(T, "triangulate_groups", fake_triangulate_groups)
+    cv = session_volume
+    ip, ca = cv.image_points, cv.camera_array
+    ids = frozenset({int(ip.df["object_id"].iloc[0])}) if static else frozenset()
+    ref = ip.triangulate(ca, static_object_ids=ids)
+    got = T.triangulate(ip, ca, static_object_ids=ids)
+    assert list(got.df.columns) == list(ref.df.columns) and len(got.df) == len(ref.df) > 0
+    pd.testing.assert_frame_equal(got.df, ref.df, rtol=0, atol=1e-9)
+    assert (got.min_index, got.max_index) == (ref.min_index, ref.max_index)
+    if static:
+        from caliscope.core.point_data import STATIC_SYNC_INDEX
+
+        assert (got.df["sync_index"] == STATIC_SYNC_INDEX).sum() > 0
 
 
 def test_s2_optimize_passes_the_reference_constraint_arrays(monkeypatch):

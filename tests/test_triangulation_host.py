@@ -4,41 +4,17 @@ results and errors.  The device call ``triangulate_groups`` is replaced by an or
 returns exactly what the kernel returns per group (xyz, count, representative row, camera-multiset signature)."""
 from __future__ import annotations
 
-import hashlib
-
 import numpy as np
 import pytest
 
 from caliscope_b200 import triangulation as T
 from oracle import triangulation as OT
-
-
-def _fake_groups(proj, obs_cam, obs_key, obs_xy, **_):
-    """Same contract as cb_triangulate_dlt: groups in ascending key order, stable inside a group."""
-    order = np.argsort(obs_key, kind="stable")
-    keys = obs_key[order]
-    starts = np.flatnonzero(np.concatenate([[True], keys[1:] != keys[:-1]]))
-    ends = np.concatenate([starts[1:], [len(order)]])
-    xyz, count, rep, sig = [], [], [], []
-    for b, e in zip(starts, ends):
-        rows = order[b:e]
-        count.append(e - b)
-        rep.append(rows[0])
-        h = hashlib.sha256(np.sort(obs_cam[rows]).astype(np.int64).tobytes()).digest()
-        sig.append(np.frombuffer(h[:16], dtype=np.uint64))
-        if e - b < 2:
-            xyz.append([np.nan] * 3)
-            continue
-        A = np.concatenate([np.stack([obs_xy[r, 0] * proj[obs_cam[r], 2] - proj[obs_cam[r], 0],
-                                      obs_xy[r, 1] * proj[obs_cam[r], 2] - proj[obs_cam[r], 1]]) for r in rows])  # fmt: skip
-        w = np.linalg.svd(A, full_matrices=False)[2][-1]
-        xyz.append(w[:3] / w[3])
-    return np.array(xyz).reshape(-1, 3), np.array(count, np.int32), np.array(rep, np.int32), np.array(sig).reshape(-1, 2)
+from tests._util import fake_triangulate_groups
 
 
 @pytest.fixture()
 def fake_device(monkeypatch):
-    monkeypatch.setattr(T, "triangulate_groups", _fake_groups)
+    monkeypatch.setattr(T, "triangulate_groups", fake_triangulate_groups)
 
 
 @pytest.mark.parametrize("case", ["s4", "syn"])
