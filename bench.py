@@ -40,6 +40,8 @@ WORKLOADS = {
     "cfg2": (8, 2_000, 40_000, False),
     # what one rank holds of cfg4 at 8 GPUs: used on ONE GPU to profile the per-iteration fixed cost
     "cfg4_shard8": (64, 6_250, 250_000, False),
+    # the realistic Caliscope shape: local visibility, 8 cameras per point (synthetic.sparse64)
+    "sparse64": (64, 250_000, 2_000_000, False),
 }
 # BASELINE.json configs[4]: cfg4 rig + 2 % outliers, solve(linear) -> solve(soft_l1) -> 2.5 % per-camera cull -> solve(linear)
 PIPELINE_WORKLOADS = {"cfg5": (64, 50_000, 2_000_000, 0.02), "cfg5_small": (8, 2_000, 40_000, 0.02)}
@@ -49,7 +51,42 @@ def make_workload(name: str):
     from caliscope_b200 import synthetic
 
     n_cams, n_pts, n_obs, refine = WORKLOADS[name]
+    if name == "sparse64":
+        return synthetic.sparse64()
     return synthetic.make_rig(n_cams, n_pts, n_obs, refine_intrinsics=refine, seed=0, name=name)
+
+
+def golden_scipy(name: str):
+    """scipy's answer for this workload, committed by tests/golden/make_bench_golden.py (same oracle call as the live
+    cpu_baseline leg): lets every GPU count print a parity block without 40-200 s of CPU per line."""
+    p = ROOT / "tests" / "golden" / "bench_scipy.json"
+    try:
+        return json.loads(p.read_text()).get(name)
+    except Exception:
+        return None
+
+
+def pin_to_gpu_numa(dev: int) -> str:
+    """Bind this process to the CPUs local to GPU `dev` (the end-to-end arm is host-memcpy / PCIe sensitive; round 1 saw
+    5.5 vs 7.1 ms per solve on the same code depending on where the process landed)."""
+    try:
+        import torch
+
+        bus = torch.cuda.get_device_properties(dev).pci_bus_id
+        dom = torch.cuda.get_device_properties(dev).pci_domain_id
+        devid = torch.cuda.get_device_properties(dev).pci_device_id
+        path = Path(f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{devid:02x}.0/local_cpulist")
+        cpus: set[int] = set()
+        for part in path.read_text().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"pinned to {len(cpus)} CPUs local to GPU {dev} ({path.read_text().strip()})"
+    except Exception as e:  # best effort
+        return f"not pinned ({type(e).__name__})"
+    return "not pinned"
 
 
 L2_MB = 126.0
@@ -57,11 +94,11 @@ FLUSH_BYTES = 256 << 20
 
 
 def working_set_mb(n_cams: int, n_pts: int, n_obs: int, P: int, n_gpus: int) -> float:
-    """Per-GPU working set of one LM iteration: Jacobian rows (20 / 28 doubles per observation) + the dense k-major Schur
-    factor (3 n_pts x ceil(n_cams P / 96) 96 doubles)."""
-    rows = n_obs * (160 if P == 6 else 224) / n_gpus
+    """Per-GPU working set of one LM iteration: the two observation lists (camera-major 24 B + point-major 20 B per
+    observation) + the dense k-major Schur factor (3 n_pts x ceil(n_cams P / 96) 96 doubles)."""
+    obs = n_obs * 44 / n_gpus
     zt = 3 * n_pts * (-(-n_cams * P // 96) * 96) * 8 / n_gpus
-    return (rows + zt) / 1e6
+    return (obs + zt) / 1e6
 
 
 def needs_l2_flush(n_cams: int, n_pts: int, n_obs: int, P: int, n_gpus: int) -> bool:
@@ -71,7 +108,7 @@ def needs_l2_flush(n_cams: int, n_pts: int, n_obs: int, P: int, n_gpus: int) -> 
 def _l2_note(n_cams: int, n_pts: int, n_obs: int, P: int, n_gpus: int) -> str:
     mb = working_set_mb(n_cams, n_pts, n_obs, P, n_gpus)
     if not needs_l2_flush(n_cams, n_pts, n_obs, P, n_gpus):
-        return f"per-iteration working set (Jacobian rows + Schur factor, {mb:.0f} MB per GPU) exceeds the 126 MB L2; no explicit flush"
+        return f"per-iteration working set (observation lists + Schur factor, {mb:.0f} MB per GPU) exceeds the 126 MB L2; no explicit flush"
     return (f"per-iteration working set is {mb:.0f} MB per GPU, so the 126 MB L2 is flushed before every timed step by writing a "
             f"{FLUSH_BYTES >> 20} MB buffer (inside the timed region)")
 
@@ -227,11 +264,32 @@ def run_reference(args) -> None:
 # ------------------------------------------------------------------------------------------------
 # the CUDA arm
 # ------------------------------------------------------------------------------------------------
-def algorithmic_bytes_rj(rig) -> int:
-    """n_obs*(24 + 16 + 16*Pc + 48) + 24*n_pts + 8*sum_c(Pc + 9)."""
+def algorithmic_bytes(rig) -> dict:
+    """SURVEY.md 8(d).  `materialised`: the residual+Jacobian kernel that writes J (184 / 232 B per observation) -- kept for
+    comparability with round 1; `fused`: the formulation that never writes J,
+    n_obs (24 + 8*3*Pc) + 8 n_pts (6+3) + 8 n_cams (Pc (Pc+1)/2 + Pc) -- what pt_pass_kernel actually has to move
+    (observation in, Z block out) and what `roofline.achieved` is computed from."""
     pc = np.where(rig.cam_flags & 1, 9, 6)
     P = int(pc.max())
-    return int(rig.n_obs * (24 + 16 + 16 * P + 48) + 24 * rig.n_pts + 8 * int((pc + 9).sum()))
+    return {
+        "materialised": int(rig.n_obs * (24 + 16 + 16 * P + 48) + 24 * rig.n_pts + 8 * int((pc + 9).sum())),
+        "fused": int(rig.n_obs * (24 + 24 * P) + 72 * rig.n_pts + 8 * rig.n_cams * (P * (P + 1) // 2 + P)),
+        "P": P,
+    }
+
+
+def syrk_flops(rig) -> dict:
+    """Schur product S = Z Z^T.  dense: every point against every camera pair, upper triangle by 96-wide tiles with
+    24-blocks on the diagonal tiles (what the kernel issues when the visibility is dense); algorithmic:
+    sum_j 3 (P n_j)^2 / 2 multiply-adds over the cameras n_j that actually see point j."""
+    P = int(np.where(rig.cam_flags & 1, 9, 6).max())
+    nP = rig.n_cams * P
+    nb = -(-nP // 96)
+    dense_cols2 = (nb * (nb - 1) // 2) * 96 * 96 + nb * 10 * 24 * 24
+    # distinct cameras per point
+    key = np.unique(rig.obs_pt.astype(np.int64) * rig.n_cams + rig.obs_cam)
+    nj = np.bincount((key // rig.n_cams).astype(np.int64), minlength=rig.n_pts).astype(np.float64)
+    return {"dense_flop": 2.0 * 3 * rig.n_pts * dense_cols2, "algorithmic_flop": float(2.0 * np.sum(3 * (P * nj) ** 2 / 2))}
 
 
 def load_peaks() -> tuple[float, str]:
@@ -244,16 +302,84 @@ def load_peaks() -> tuple[float, str]:
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def load_ncu_traffic(workload: str):
-    p = ROOT / "profiles" / "resjac_ncu_summary.json"
-    if p.exists():
-        try:
-            d = json.loads(p.read_text())
-            if d.get("workload") == workload:
-                return d.get("dram_bytes_per_launch")
-        except Exception:
-            pass
+def kernel_source_hash() -> str:
+    import hashlib
+
+    h = hashlib.sha256()
+    for f in sorted((ROOT / "caliscope_b200" / "csrc").glob("*.cu*")):
+        h.update(f.read_bytes())
+    return h.hexdigest()[:16]
+
+
+def load_ncu_traffic(workload: str, kernel: str):
+    """DRAM bytes per launch from the committed ncu digest, only if it was taken from THIS kernel source (the digest
+    carries the hash of csrc/ at capture time); a stale digest yields None instead of a wrong number."""
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    try:
+        d = json.loads(p.read_text())
+        e = d.get(workload, {}).get(kernel)
+        if e and e.get("csrc_sha16") == kernel_source_hash():
+            return e.get("dram_bytes_per_launch")
+    except Exception:
+        pass
     return None
+
+
+def make_parameterization(rig):
+    """The reference-shaped ``BundleParameterization`` of a synthetic rig (host mirror class; the reference's own
+    class has the same fields) -- what ``CaptureVolume.optimize`` passes as ``args[0]``."""
+    from caliscope_b200.bundle_parameterization import BundleParameterization, CameraBlock
+
+    blocks = []
+    for c in range(rig.n_cams):
+        k = rig.cam_const[c]
+        blocks.append(CameraBlock(cam_id=c, free_intrinsics=bool(rig.cam_flags[c] & 1), fx_initial=float(k[0]), fy_initial=float(k[1]),
+                                  cx=float(k[2]), cy=float(k[3]), fisheye=bool(rig.cam_flags[c] & 2),
+                                  dist_fixed=tuple(float(v) for v in k[6:9]), k1_initial=float(k[4]), k2_initial=float(k[5])))  # fmt: skip
+    return BundleParameterization(blocks=tuple(blocks), n_points=rig.n_pts)
+
+
+def selfcheck_sharded(dev: int, rank: int, world: int) -> dict:
+    """N > 1 only: the sharded solve against the SAME rig solved whole on this rank's own GPU, on a small rig with
+    duplicate (camera, point) rows, once plain and once with rigid-distance constraint rows; every rank checks its own
+    copy and the worst case over ranks is reported.  This is the multi-GPU correctness evidence the 1-GPU test box cannot
+    produce (tests/test_gpu_multi.py needs >= 2 GPUs)."""
+    import torch
+    import torch.distributed as dist
+
+    import caliscope_b200 as cb
+    from caliscope_b200 import distributed as D
+    from caliscope_b200 import synthetic
+
+    out = {}
+    rig = synthetic.make_rig(8, 1500, 24_000, seed=5, name="selfcheck")
+    rng = np.random.default_rng(11)
+    # rigid pairs: 60 disjoint groups of 8 points, 3 distance rows each (noisy truth => the rows are active)
+    Xt = rig.x_true[-3 * rig.n_pts:].reshape(-1, 3)
+    ga, gb, dist_, w = [], [], [], []
+    for g in range(60):
+        pts = np.arange(8 * g, 8 * g + 8)
+        for a, b in ((0, 4), (1, 5), (2, 7)):
+            A, B = np.repeat(pts[a], 4), np.repeat(pts[b], 4)
+            ga.append(A); gb.append(B)
+            dist_.append(np.linalg.norm(Xt[pts[a]] - Xt[pts[b]]) * (1 + 1e-3 * rng.normal()))
+            w.append(1.0 / (1394.6 * 0.002))
+    cons = (np.array(ga, np.int32), np.array(gb, np.int32), np.array(dist_), np.array(w))
+    for label, c in (("plain", None), ("constraints", cons)):
+        with cb.BAProblem(rig.cam_flags, rig.cam_const, rig.n_pts, rig.obs_cam, rig.obs_pt, rig.obs_xy, constraints=c,
+                          device=dev) as p1:
+            r1 = p1.solve(rig.x0)
+        rs, _ = D.solve_sharded(rig.cam_flags, rig.cam_const, rig.n_pts, rig.obs_cam, rig.obs_pt, rig.obs_xy, rig.x0,
+                                device=dev, constraints=c)
+        dx = float(np.abs(rs.x - r1.x).max())
+        t = torch.tensor([dx, abs(rs.cost - r1.cost) / max(r1.cost, 1e-300), float(rs.nfev != r1.nfev)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[label] = {"max_abs_dx": float(t[0]), "rel_dcost": float(t[1]), "nfev_equal": bool(t[2] == 0),
+                      "nfev": int(r1.nfev), "status": int(rs.status)}
+    out["ok"] = all(v["max_abs_dx"] < 1e-9 and v["rel_dcost"] < 1e-9 for v in out.values() if isinstance(v, dict))
+    out["what"] = ("sharded solve vs the same 8-cam / 1500-point / 24k-observation rig solved whole on each rank's own GPU; "
+                   "max over ranks of max|x_sharded - x_single| (bar 1e-9) and relative cost difference")
+    return out
 
 
 def run_ours(args) -> None:
@@ -262,6 +388,8 @@ def run_ours(args) -> None:
 
     import caliscope_b200 as cb
     from caliscope_b200 import distributed as D
+    from caliscope_b200 import reprojection as R
+    from caliscope_b200 import solver
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -272,7 +400,9 @@ def run_ours(args) -> None:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = local_rank if world > 1 else 0
     torch.cuda.set_device(dev)
+    numa = pin_to_gpu_numa(dev)
     stream = torch.cuda.current_stream().cuda_stream
+    lib = cb._lib.load()
 
     rig = make_workload(args.workload)
     ncp = int(np.where(rig.cam_flags & 1, 9, 6).sum())
@@ -287,7 +417,7 @@ def run_ours(args) -> None:
         x0 = rig.x0
         transport = {}
     solve_kw = dict(ftol=1e-8, rank=rank, world_size=world, stream=stream, **transport)
-    transport_name = {"peer_group": "peer memory (fused finalize + NVLink reduce kernel)", "nccl_comm": "engine-owned NCCL",
+    transport_name = {"peer_group": "peer memory (fused finalize + NVLink reduce kernel, cooperative launch)", "nccl_comm": "engine-owned NCCL",
                       "allreduce": "torch.distributed callback"}.get(next(iter(transport), ""), "none (single GPU)")
 
     def barrier():
@@ -321,38 +451,53 @@ def run_ours(args) -> None:
     if rank == 0:
         sampler.start()
     barrier()
-    launches0 = cb._lib.load().cb_ba_launch_count()
+    launches0 = lib.cb_ba_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
-    nit = nfev = 0
-    rj_ms = 0.0
-    rj_n = 0
+    nit = nfev = trials = 0
+    pp_ms = sy_ms = 0.0
+    pp_n = sy_n = 0
     for i in range(args.steps):
         if flush is not None:
             flush.fill_(i & 0x7F)  # evict the previous step's data from L2 (same stream as the solve)
         res = prob.solve(x0, **solve_kw)
         nit += res.nit
         nfev += res.nfev
-        rj_ms += res.rj_ms
-        rj_n += res.rj_launches
+        trials += res.trials_queued
+        pp_ms += res.rj_ms
+        pp_n += res.rj_launches
+        sy_ms += res.syrk_ms
+        sy_n += res.syrk_launches
     e1.record()
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = cb._lib.load().cb_ba_launch_count() - launches0
+    launches = lib.cb_ba_launch_count() - launches0
+    used_graph = res.used_graph
     x_final = res.x
     if world > 1:
         x_final = D.gather_points(res.x, ncp, rig.n_pts, shard)
     prob.close()
 
-    # ---- end-to-end arm: pinned host buffers, upload + index build + solve + download ---------
-    h_cam = torch.from_numpy(l_cam).pin_memory().numpy()
-    h_pt = torch.from_numpy(l_pt).pin_memory().numpy()
-    h_xy = torch.from_numpy(np.ascontiguousarray(l_xy)).pin_memory().numpy()
+    # ---- end-to-end arm: the reference-facing call on pageable NumPy arrays -----------------------
+    # N = 1: caliscope_b200.solver.least_squares(joint_residuals, x0, args=(parameterization, camera_indices int16,
+    #        image_coords, image_to_world_indices, None x4), jac=..., x_scale="jac", method="trf", bounds=par.bounds(), ...)
+    #        exactly as /root/reference/src/caliscope/core/capture_volume.py:387-411 calls scipy: blocks -> arrays,
+    #        pageable upload, index build, solve, result download all inside the timed region.
+    # N > 1: the same per rank on its shard (pageable host arrays -> BAProblem -> sharded solve).
+    par = make_parameterization(rig)
+    cam16 = rig.obs_cam.astype(np.int16)  # capture_volume.py:353-355 builds int16 camera indices
+    xy_h = np.array(rig.obs_xy)  # pageable copies
+    obj_h = np.array(rig.obs_pt, dtype=np.int32)
+    lc, lp, lx = np.array(l_cam), np.array(l_pt), np.array(l_xy)
 
     def e2e_step():
-        with cb.BAProblem(rig.cam_flags, rig.cam_const, l_npts, h_cam, h_pt, h_xy, device=dev, stream=stream) as p2:
+        if world == 1:
+            return solver.least_squares(R.joint_residuals, rig.x0, args=(par, cam16, xy_h, obj_h, None, None, None, None),
+                                        jac=R.joint_jacobian, x_scale="jac", method="trf", bounds=par.bounds(), ftol=1e-8,
+                                        loss="linear", f_scale=1.0, max_nfev=None, verbose=0)
+        with cb.BAProblem(rig.cam_flags, rig.cam_const, l_npts, lc, lp, lx, device=dev, stream=stream) as p2:
             return p2.solve(x0, **solve_kw)
 
     for _ in range(min(args.warmup, 3)):
@@ -369,11 +514,17 @@ def run_ours(args) -> None:
     e2e_wall_ms = 1e3 * (time.perf_counter() - t1)
     e2e_ms = max_over_ranks(max(f0.elapsed_time(f1), e2e_wall_ms))
     clocks = sampler.stop() if rank == 0 else None  # sampled across both timed regions
-    h2d = int(l_cam.nbytes + l_pt.nbytes + l_xy.nbytes + x0.nbytes + rig.cam_flags.nbytes + rig.cam_const.nbytes)
-    d2h = int(x0.nbytes + 8 * 32)
+    if world == 1:
+        h2d = int(cam16.nbytes * 2 + obj_h.nbytes + xy_h.nbytes + rig.x0.nbytes + rig.cam_flags.nbytes + rig.cam_const.nbytes)
+    else:
+        h2d = int(lc.nbytes + lp.nbytes + lx.nbytes + x0.nbytes + rig.cam_flags.nbytes + rig.cam_const.nbytes)
+    d2h = int(x0.nbytes + 4 * 160)
+
+    selfcheck = selfcheck_sharded(dev, rank, world) if (world > 1 and not args.no_selfcheck) else None
 
     if rank != 0:
         if world > 1:
+            D.close_comms()
             dist.destroy_process_group()
         return
 
@@ -383,9 +534,16 @@ def run_ours(args) -> None:
     orc = O.Rig(rig.cam_flags, rig.cam_const, rig.n_pts, rig.obs_cam, rig.obs_pt, rig.obs_xy)
     rms_px = O.overall_rmse_px(x_final, orc)
     peak, peak_src = load_peaks()
-    rj_bytes = algorithmic_bytes_rj(rig) / world  # each rank's launch covers its shard
-    rj_avg_ms = rj_ms / max(rj_n, 1)
-    achieved = rj_bytes / (rj_avg_ms * 1e-3) / 1e9 if rj_avg_ms > 0 else 0.0
+    ab = algorithmic_bytes(rig)
+    pp_bytes = ab["fused"] / world  # each rank's launch covers its shard
+    pp_avg_ms = pp_ms / max(pp_n, 1)
+    achieved = pp_bytes / (pp_avg_ms * 1e-3) / 1e9 if pp_avg_ms > 0 else 0.0
+    sf = syrk_flops(rig)
+    sy_avg_ms = sy_ms / max(sy_n, 1)
+    dmma, dfma = __import__("ctypes").c_double(), __import__("ctypes").c_double()
+    if lib.cb_debug_fp64_peak(dev, __import__("ctypes").byref(dmma), __import__("ctypes").byref(dfma)) != 0:
+        dmma.value = 37.1
+    P = ab["P"]
     line = {
         "metric": METRIC,
         "value": nit / (dev_ms * 1e-3),
@@ -407,8 +565,15 @@ def run_ours(args) -> None:
             "ms_per_step": e2e_ms / args.steps,
             "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": d2h,
+            "call": ("caliscope_b200.solver.least_squares(joint_residuals, x0, args=(parameterization, camera_indices[int16], "
+                     "image_coords, image_to_world_indices, None, None, None, None), jac=joint_jacobian, x_scale='jac', method='trf', "
+                     "bounds=parameterization.bounds(), ftol=1e-8) on pageable NumPy arrays -- the call capture_volume.py:387-411 makes")
+            if world == 1 else "per rank: BAProblem(pageable shard arrays) + sharded solve + close",
+            "host": numa,
         },
         "gpu_launches": int(launches),
+        "lm_loop": {"decision": "on the device (LmState)", "trial_replay": "cuda graph" if used_graph else "direct launches",
+                    "trials_queued_per_step": trials / args.steps, "host_syncs_per_trial": 0},
         "allreduce_transport": transport_name,
         "obs_residuals_per_sec": rig.n_obs * nfev / (dev_ms * 1e-3),
         "lm_iterations_per_step": nit / args.steps,
@@ -419,19 +584,50 @@ def run_ours(args) -> None:
         "final_cost": res.cost,
         "status": res.status,
         "roofline": {
-            "kernel": "resjac_kernel<P,0> (residual + analytic Jacobian rows + per-camera J^T J)",
+            "kernel": f"pt_pass_kernel<{P},...> (per observation: residual + analytic Jacobian blocks recomputed in registers, "
+                      "V/g reduction, 3x3 Cholesky, Z = Jc^T Jp L^-T streamed to the Schur factor; no Jacobian is written)",
             "bound": "hbm",
             "achieved": achieved,
             "peak": peak,
             "unit": "GB/s",
             "frac": achieved / peak,
-            "traffic": load_ncu_traffic(args.workload) if world == 1 else None,  # the ncu capture is of the 1-GPU launch
+            "traffic": load_ncu_traffic(args.workload, "pt_pass_kernel") if world == 1 else None,
             "peak_source": peak_src,
-            "algorithmic_bytes_per_launch": rj_bytes,
-            "avg_launch_ms": rj_avg_ms,
-            "launches_timed": int(rj_n),
+            "algorithmic_bytes_per_launch": pp_bytes,
+            "algorithmic_bytes_per_obs": {"fused (this kernel, SURVEY 8d minimum)": 24 + 24 * P,
+                                          "materialised J (round-1 kernel, SURVEY 8d comparability figure)": 24 + 16 + 16 * P + 48},
+            "avg_launch_ms": pp_avg_ms,
+            "launches_timed": int(pp_n),
+            "share_of_step": (pp_ms / max(dev_ms, 1e-9)),
+        },
+        "roofline_tensor": {
+            "kernel": "schur_syrk_kernel (S = Z Z^T on mma.sync.m8n8k4.f64, TMA-staged tiles)",
+            "bound": "tensor",
+            "achieved": sf["dense_flop"] / world / (sy_avg_ms * 1e-3) / 1e12 if sy_avg_ms > 0 else 0.0,
+            "peak": dmma.value,
+            "unit": "TFLOP/s",
+            "frac": (sf["dense_flop"] / world / (sy_avg_ms * 1e-3) / 1e12 / dmma.value) if sy_avg_ms > 0 else 0.0,
+            "frac_algorithmic": (sf["algorithmic_flop"] / world / (sy_avg_ms * 1e-3) / 1e12 / dmma.value) if sy_avg_ms > 0 else 0.0,
+            "peak_source": "measured live: cb_debug_fp64_peak (mma.sync.m8n8k4.f64, 8 warps/SM); DFMA %.1f TFLOP/s" % dfma.value,
+            "flop_per_launch": {"issued (dense tiles)": sf["dense_flop"] / world, "algorithmic sum_j 3 (P n_j)^2": sf["algorithmic_flop"] / world},
+            "avg_launch_ms": sy_avg_ms,
+            "launches_timed": int(sy_n),
+            "share_of_step": (sy_ms / max(dev_ms, 1e-9)),
         },
     }
+    gold = golden_scipy(args.workload)
+    if gold is not None:
+        bar = 1e-6
+        line["parity"] = {
+            "rms_px_gpu": rms_px, "rms_px_scipy": gold["scipy_rms_px"], "abs_diff_px": abs(rms_px - gold["scipy_rms_px"]),
+            "bar_px": bar, "green": bool(abs(rms_px - gold["scipy_rms_px"]) < bar),
+            "cost_gpu": res.cost, "cost_scipy": gold["scipy_cost"],
+            "scipy": f"committed: tests/golden/bench_scipy.json[{args.workload}] (nfev {gold['scipy_nfev']}, nit {gold['scipy_nit']}, {gold['wall_s']} s), "
+                     "generated by tests/golden/make_bench_golden.py = oracle.ba_oracle.solve_scipy",
+            "note": "P = 9 (free intrinsics): scipy's own default-vs-tight runs differ by up to 3e-6 px on small rigs (DESIGN.md 2)" if P == 9 else "",
+        }  # fmt: skip
+    if selfcheck is not None:
+        line["selfcheck"] = selfcheck
     if world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_step(rig, args.ref_max_nfev)
         line["cpu_baseline"] = {
@@ -448,46 +644,105 @@ def run_ours(args) -> None:
             "obs_residuals_per_sec": rig.n_obs * cpu["nfev"] / cpu["wall_s"],
         }
         if args.ref_max_nfev <= 0:
-            line["parity"] = {"rms_px_gpu": rms_px, "rms_px_scipy": cpu["rmse_px"],
-                              "abs_diff_px": abs(rms_px - cpu["rmse_px"]), "bar_px": 1e-6}  # fmt: skip
+            line.setdefault("parity", {})
+            line["parity"].update({"rms_px_scipy_live": cpu["rmse_px"], "abs_diff_px_live": abs(rms_px - cpu["rmse_px"]),
+                                   "bar_px": 1e-6, "green_live": bool(abs(rms_px - cpu["rmse_px"]) < 1e-6)})  # fmt: skip
     print(json.dumps(line), flush=True)
     if world > 1:
+        D.close_comms()
         dist.destroy_process_group()
 
 
 def run_pipeline(args) -> None:
-    """Outlier-filter + re-solve loop (calibrate_extrinsics.py:206-250) on one GPU; one step = the whole loop."""
+    """Outlier-filter + re-solve loop (calibrate_extrinsics.py:206-250); one step = the whole loop from host buffers
+    (problem upload + index build twice per step).  N > 1: observations sharded by point, global per-camera
+    percentile thresholds from one all-gather of the pixel errors (pipeline.solve_filter_resolve_sharded)."""
     import torch
+    import torch.distributed as dist
 
+    from caliscope_b200 import distributed as D
     from caliscope_b200 import pipeline, synthetic
 
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = local_rank if world > 1 else 0
+    torch.cuda.set_device(dev)
+    numa = pin_to_gpu_numa(dev)
     n_cams, n_pts, n_obs, frac = PIPELINE_WORKLOADS[args.workload]
     rig = synthetic.make_rig(n_cams, n_pts, n_obs, seed=0, outlier_frac=frac, name=args.workload)
-    call = lambda: pipeline.solve_filter_resolve(rig.cam_flags, rig.cam_const, rig.n_pts, rig.obs_cam, rig.obs_pt,
-                                                 rig.obs_xy, rig.x0)  # noqa: E731
+    if world == 1:
+        call = lambda: pipeline.solve_filter_resolve(rig.cam_flags, rig.cam_const, rig.n_pts, rig.obs_cam, rig.obs_pt,
+                                                     rig.obs_xy, rig.x0)  # noqa: E731
+    else:
+        call = lambda: pipeline.solve_filter_resolve_sharded(rig.cam_flags, rig.cam_const, rig.n_pts, rig.obs_cam,
+                                                             rig.obs_pt, rig.obs_xy, rig.x0, device=dev)  # noqa: E731
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     for _ in range(args.warmup):
         out = call()
-    torch.cuda.synchronize()
+    sampler = ClockSampler(dev)
+    if rank == 0:
+        sampler.start()
+    barrier()
     t0 = time.perf_counter()
     nit = 0
     for _ in range(args.steps):
         out = call()
         nit += sum(s.nit for s in out.stages)
-    torch.cuda.synchronize()
+    barrier()
     wall = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        D.close_comms()
+        dist.destroy_process_group()
+        return
+    from oracle import ba_oracle as O
+    from oracle import filtering as OF
+
+    gold = golden_scipy("cfg5_stage1") if args.workload == "cfg5" else None
+    orc3 = O.Rig(rig.cam_flags, rig.cam_const, rig.n_pts, rig.obs_cam[out.keep], rig.obs_pt[out.keep], rig.obs_xy[out.keep])
     line = {
-        "metric": METRIC, "value": nit / wall, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC, "value": nit / wall, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {n_cams}-cam / {n_pts}-point / {n_obs}-observation rig with {frac:.0%} outliers, "
                    "solve(linear) -> solve(soft_l1, ftol 1e-4) -> 2.5 % per-camera cull -> solve(linear); host buffers, "
-                   "problem upload + index build twice per step (BASELINE.json configs[4])"},
+                   "problem upload + index build twice per step (BASELINE.json configs[4])",
+                   "sharding": "single GPU" if world == 1 else f"observations sharded by point over {world} GPUs; global per-camera "
+                   "percentile thresholds from one all-gather of the pixel errors; keep mask and compaction local to each rank",
+                   "host": numa},
+        "clocks": clocks,
+        "e2e": {"value": nit / wall, "unit": UNIT, "ms_per_step": 1e3 * wall / args.steps,
+                "h2d_bytes_per_step": int((rig.obs_cam.nbytes + rig.obs_pt.nbytes + rig.obs_xy.nbytes) / world + 3 * rig.x0.nbytes),
+                "d2h_bytes_per_step": int(3 * rig.x0.nbytes + rig.n_obs / world)},
         "stages": [{"loss": l, "nfev": s.nfev, "nit": s.nit, "status": s.status, "cost": s.cost, "solve_ms": s.solve_ms,
                     "rms_px": r} for l, s, r in zip(("linear", "soft_l1", "linear after cull"), out.stages, out.rmse_px)],
         "kept_fraction": float(out.keep.mean()),
         "outliers_removed_fraction": float(1.0 - out.keep[rig.outlier_mask].mean()),
+        "final_rms_px": float(O.overall_rmse_px(out.x, orc3)),
     }  # fmt: skip
+    if gold is not None:
+        line["parity"] = {"stage": "1 (linear, all observations)", "rms_px_gpu": out.rmse_px[0], "rms_px_scipy": gold["scipy_rms_px"],
+                          "abs_diff_px": abs(out.rmse_px[0] - gold["scipy_rms_px"]), "bar_px": 1e-6,
+                          "green": bool(abs(out.rmse_px[0] - gold["scipy_rms_px"]) < 1e-6),
+                          "scipy": "committed: tests/golden/bench_scipy.json[cfg5_stage1]"}  # fmt: skip
     print(json.dumps(line), flush=True)
+    if world > 1:
+        D.close_comms()
+        dist.destroy_process_group()
 
 
 def run_triangulation(args) -> None:
@@ -568,6 +823,7 @@ def main() -> None:
     ap.add_argument("--ref-max-nfev", type=int, default=0, help="cap on scipy evaluations per reference step (0: run to convergence)")
     ap.add_argument("--ref-budget-s", type=float, default=240.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-selfcheck", action="store_true", help="N > 1: skip the sharded-vs-single-GPU equality check on the small rig")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -576,8 +832,8 @@ def main() -> None:
             raise SystemExit("triangulate_cfg4 runs on the CUDA arm, one GPU")
         run_triangulation(args)
     elif args.workload in PIPELINE_WORKLOADS:
-        if args.impl != "ours" or args.gpus != 1:
-            raise SystemExit("pipeline workloads run on the CUDA arm, one GPU")
+        if args.impl != "ours":
+            raise SystemExit("pipeline workloads run on the CUDA arm")
         run_pipeline(args)
     elif args.impl == "reference":
         run_reference(args)

@@ -81,6 +81,11 @@ class Result(C.Structure):
         ("solve_ms", C.c_double),
         ("rj_ms", C.c_double),
         ("rj_launches", C.c_int64),
+        ("syrk_ms", C.c_double),
+        ("syrk_launches", C.c_int64),
+        ("trials_queued", C.c_int64),
+        ("used_graph", C.c_int32),
+        ("pad_", C.c_int32),
     ]
 
 
@@ -121,6 +126,7 @@ SYMBOLS = {
     "cb_ba_rmse_px": (C.c_int, [_P, _P, _P, _P, _P]),
     "cb_ba_cull": (C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(_P), _P, _P, _P]),
     "cb_ba_debug_pcg_time": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
+    "cb_debug_fp64_peak": (C.c_int, [C.c_int, _P, _P]),
     "cb_undistort_points": (C.c_int, [C.c_int32, _P, _P, _P, C.c_int64, _P, _P, C.c_int, C.c_int, _P, C.c_int, _P]),
     "cb_triangulate_dlt": (
         C.c_int,

@@ -9,7 +9,7 @@
 // (an L-transformed basis of the component's coordinates), so the SYRK, the reduced solve and the dense
 // Zt^T dc product are unchanged; only the per-point build / back-substitution differ for these points.
 #pragma once
-#include "cb_device.cuh"
+#include "cb_kernels.cuh"
 
 namespace cb {
 
@@ -36,13 +36,25 @@ struct ConstraintTables {
 // residual, robust rescale and scaled direction per constraint; block partial sums of the cost.
 //   diff = sum_u coef_u X_u ; r = (|diff| - d) w ; row of the Jacobian for point u: coef_u * dirw^T
 //   with dirw = jscale * w * diff/|diff| (zero sub-gradient at coincident endpoints).
-// COST_ONLY: only the partial sums (trial point).
+// COST_ONLY: only the partial sums.
+// With `st` it is one step of the LM trial: evaluates at point buffer (st->cur ^ flip) and writes the scaled residual
+// and direction into slot (st->cur ^ flip) of c_rs2 / c_dirw2 (the trial point's rows become the next linearisation's
+// if the step is accepted).
 template <bool COST_ONLY>
 __global__ void __launch_bounds__(CC_THREADS)
-constraint_eval_kernel(ConstraintTables T, const double* __restrict__ xp4, int loss, double fscale,
-                       double* __restrict__ c_rs, double* __restrict__ c_dirw, double* __restrict__ raw_r,
-                       double* __restrict__ cost_part) {
+constraint_eval_kernel(const LmState* __restrict__ st, int flip, ConstraintTables T, CPtr2 xp2, int loss, double fscale,
+                       Ptr2 c_rs2, Ptr2 c_dirw2, double* __restrict__ raw_r, double* __restrict__ cost_part) {
   __shared__ double sh[CC_THREADS / 32];
+  int sel = 0;
+  if (st != nullptr) {
+    if (st->done) return;
+    sel = st->cur ^ flip;
+    loss = st->loss;
+    fscale = st->fscale;
+  }
+  const double* __restrict__ xp4 = xp2.p[sel];
+  double* __restrict__ c_rs = c_rs2.p[sel];
+  double* __restrict__ c_dirw = c_dirw2.p[sel];
   const int k = blockIdx.x * CC_THREADS + threadIdx.x;
   double cost = 0.0;
   if (k < T.n_c) {
@@ -101,14 +113,16 @@ __device__ __forceinline__ void forward_solve_cols(const double* L, int n, doubl
 // One CTA per component: assemble E and g, Marquardt scale, Cholesky, t = L^-1 g, Z = W L^-T per camera.
 template <int P>
 __global__ void __launch_bounds__(CC_THREADS)
-comp_build_kernel(ConstraintTables T, const int* __restrict__ pt_start, const int* __restrict__ pm_cam,
-                  const int* __restrict__ pm_row, const double* __restrict__ jrows, const double* __restrict__ V6,
-                  const double* __restrict__ gp, double* __restrict__ Dp2, double* __restrict__ gpt,
-                  const double* __restrict__ c_rs, const double* __restrict__ c_dirw, double lam, int new_lin,
-                  int n_cams, double* __restrict__ compL, double* __restrict__ tvec, double* __restrict__ Zt, size_t LD,
+comp_build_kernel(const LmState* __restrict__ st, ConstraintTables T, const int* __restrict__ pt_start,
+                  const int* __restrict__ pm_cam, const double* __restrict__ V6, const double* __restrict__ gp,
+                  double* __restrict__ Dp2, double* __restrict__ gpt, CPtr2 c_rs2, CPtr2 c_dirw2, int n_cams,
+                  double* __restrict__ compL, double* __restrict__ tvec, double* __restrict__ Zt, size_t LD,
                   unsigned long long* __restrict__ gmax_bits) {
-  using RT = RowT<P>;
   extern __shared__ __align__(16) double csm[];
+  if (st->done) return;
+  const double lam = st->lam;
+  const double* __restrict__ c_rs = c_rs2.p[st->cur];
+  const double* __restrict__ c_dirw = c_dirw2.p[st->cur];
   const int comp = blockIdx.x;
   const int p0 = T.comp_pt_start[comp], m = T.comp_pt_start[comp + 1] - p0, n = 3 * m;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -163,8 +177,8 @@ comp_build_kernel(ConstraintTables T, const int* __restrict__ pt_start, const in
   for (int i = tid; i < n; i += CC_THREADS) {
     const int q = T.comp_pts[p0 + i / 3];
     double* dq = Dp2 + 3 * (size_t)q + (i % 3);
-    double D = *dq;
-    if (new_lin) { D = fmax(D, E[(size_t)i * n + i]); *dq = D; }
+    double D = fmax(*dq, E[(size_t)i * n + i]);  // running max; idempotent while the point is unchanged
+    *dq = D;
     E[(size_t)i * n + i] += lam * (D > 0.0 ? D : 1.0);
     gpt[3 * (size_t)q + (i % 3)] = g[i];
     gm = fmax(gm, fabs(g[i]));
@@ -172,7 +186,7 @@ comp_build_kernel(ConstraintTables T, const int* __restrict__ pt_start, const in
   gm = warp_max(gm);
   if (lane == 0) s_gmax[wid] = gm;
   __syncthreads();
-  if (tid == 0 && new_lin) {
+  if (tid == 0) {
     double mx = 0.0;
     for (int w = 0; w < NW; ++w) mx = fmax(mx, s_gmax[w]);
     if (mx > 0.0) atomicMax(gmax_bits, (unsigned long long)__double_as_longlong(mx));
@@ -210,13 +224,17 @@ comp_build_kernel(ConstraintTables T, const int* __restrict__ pt_start, const in
     __syncthreads();
     for (int i = tid; i < m; i += CC_THREADS) {
       const int q = T.comp_pts[p0 + i];
+      // W = sum_rows Jc^T Jp of the (camera, point) pair was left in the point's Zt rows by pt_pass_kernel (identity
+      // factor for component points); entries of cameras that do not see the point hold last trial's transformed
+      // values and count as zero
       for (int pos = pt_start[q]; pos < pt_start[q + 1]; ++pos) {
         if (pm_cam[pos] != c) continue;
-        const double* v = jrows + (size_t)pm_row[pos] * RT::ROWD;
+        const double* w = Zt + (3 * (size_t)q) * LD + (size_t)c * P;
 #pragma unroll
         for (int p = 0; p < P; ++p)
 #pragma unroll
-          for (int a = 0; a < 3; ++a) Wt[(size_t)p * n + 3 * i + a] += v[8 + p] * v[2 + a] + v[8 + P + p] * v[5 + a];
+          for (int a = 0; a < 3; ++a) Wt[(size_t)p * n + 3 * i + a] = w[(size_t)a * LD + p];
+        break;
       }
     }
     __syncthreads();
@@ -237,12 +255,15 @@ comp_build_kernel(ConstraintTables T, const int* __restrict__ pt_start, const in
 
 // One CTA per component: dp = -L^-T (t + Zt_rows dc), new points, predicted-reduction partial sums
 __global__ void __launch_bounds__(CC_THREADS)
-comp_backsub_kernel(ConstraintTables T, int nP, double lam, const double* __restrict__ Zt, size_t LD,
+comp_backsub_kernel(const LmState* __restrict__ st, ConstraintTables T, int nP, const double* __restrict__ Zt, size_t LD,
                     const double* __restrict__ dc, const double* __restrict__ compL, const double* __restrict__ tvec,
-                    const double* __restrict__ gpt, const double* __restrict__ Dp2, const double* __restrict__ xp4,
-                    double* __restrict__ xp4_new, double* __restrict__ dp_out, double* __restrict__ bpart,
-                    int bpart_stride, int bpart_off) {
+                    const double* __restrict__ gpt, const double* __restrict__ Dp2, Ptr2 xp2,
+                    double* __restrict__ dp_out, double* __restrict__ bpart, int bpart_stride, int bpart_off) {
   extern __shared__ __align__(16) double bsm[];
+  if (st->done) return;
+  const double lam = st->lam;
+  const double* __restrict__ xp4 = xp2.p[st->cur];
+  double* __restrict__ xp4_new = xp2.p[st->cur ^ 1];
   const int comp = blockIdx.x;
   const int p0 = T.comp_pt_start[comp], m = T.comp_pt_start[comp + 1] - p0, n = 3 * m;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;

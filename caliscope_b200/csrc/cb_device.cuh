@@ -201,4 +201,61 @@ __device__ __forceinline__ void project_obs(const double* __restrict__ cam, bool
   o.v = fma(cam[CT_FY], o.yd, cam[CT_CY]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// One observation's scaled residual and analytic Jacobian blocks, recomputed from (camera table entry,
+// point, pixel) wherever they are needed (camera pass, point pass, back-substitution): no Jacobian row
+// is ever written to HBM.  Reference: src/caliscope/core/reprojection.py:96-110 (residual / fx0),
+// :171-205 (camera block [J_r, J_t (, J_s, J_k1, J_k2)] / fx0, point block J_t R / fx0); robust rescaling
+// as scipy common.py:720-731.
+//   f[2]      residuals (after robust rescale)
+//   JX[6]     d f / d X      (2 x 3, row-major)
+//   Jc[2*P]   d f / d camera (2 x P, row-major); P = 9 slots are zero for a locked camera
+// returns the cost contribution 0.5 * fs^2 * (rho(z0) + rho(z1)).
+// ---------------------------------------------------------------------------------------------
+template <int P>
+__device__ __forceinline__ double obs_jac(const double* __restrict__ cam, double X0, double X1, double X2,
+                                          double ox, double oy, int loss, double fscale, double* __restrict__ f,
+                                          double* __restrict__ JX, double* __restrict__ Jc) {
+  const int flags = (int)cam[CT_FLAGS];
+  const bool fish = (flags & 2) != 0;
+  const bool free_i = (P == 9) && (flags & 1) != 0;
+  ProjOut o;
+  project_obs<true>(cam, fish, X0, X1, X2, o);
+  double f0 = (o.u - ox) * cam[CT_IFX0], f1 = (o.v - oy) * cam[CT_IFX0];
+  double w0, w1;
+  const double cost = robust_row(loss, fscale, f0, w0) + robust_row(loss, fscale, f1, w1);
+  f[0] = f0; f[1] = f1;
+  const double sx = cam[CT_SX] * o.iz * w0, sy = cam[CT_SY] * o.iz * w1;
+  double Jt[6];
+  Jt[0] = sx * o.xa; Jt[1] = sx * o.xb; Jt[2] = -(Jt[0] * o.a + Jt[1] * o.b);
+  Jt[3] = sy * o.ya; Jt[4] = sy * o.yb; Jt[5] = -(Jt[3] * o.a + Jt[4] * o.b);
+  const double* R = cam + CT_R;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) JX[3 * i + k] = Jt[3 * i] * R[k] + Jt[3 * i + 1] * R[3 + k] + Jt[3 * i + 2] * R[6 + k];
+  const double* Jr = cam + CT_JR;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    // (J_X,i x X) Jr, negated
+    const double a0 = JX[3 * i], a1 = JX[3 * i + 1], a2 = JX[3 * i + 2];
+    const double c0 = a1 * X2 - a2 * X1, c1 = a2 * X0 - a0 * X2, c2 = a0 * X1 - a1 * X0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) Jc[P * i + k] = -(c0 * Jr[k] + c1 * Jr[3 + k] + c2 * Jr[6 + k]);
+    Jc[P * i + 3] = Jt[3 * i]; Jc[P * i + 4] = Jt[3 * i + 1]; Jc[P * i + 5] = Jt[3 * i + 2];
+  }
+  if constexpr (P == 9) {
+    if (free_i) {
+      const double ar2 = cam[CT_SX] * o.a * o.r2 * w0, br2 = cam[CT_SY] * o.b * o.r2 * w1;
+      Jc[6] = o.xd * w0;  Jc[P + 6] = cam[CT_FYR] * o.yd * w1;
+      Jc[7] = ar2;        Jc[P + 7] = br2;
+      Jc[8] = ar2 * o.r2; Jc[P + 8] = br2 * o.r2;
+    } else {
+      Jc[6] = Jc[7] = Jc[8] = 0.0;
+      Jc[P + 6] = Jc[P + 7] = Jc[P + 8] = 0.0;
+    }
+  }
+  return cost;
+}
+
 }  // namespace cb

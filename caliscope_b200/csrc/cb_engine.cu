@@ -71,6 +71,7 @@ struct CbPeerGroup {
   cb::PeerTable tab = {};
   unsigned long long epoch_big = 0, epoch_small = 0;
   bool connected = false;
+  bool poisoned = false;  // a solve failed part-way: the ranks' epochs may be out of step, the group must be re-created
 };
 
 namespace {
@@ -240,6 +241,26 @@ void cached_free_host(void* p) {
   g_cache.live_host.erase(it);
 }
 
+struct ScopedFree {
+  std::vector<void*> dev, host;
+  ~ScopedFree() {
+    for (void* q : dev) cached_free(q);
+    for (void* q : host) cached_free_host(q);
+  }
+};
+
+int select_device(int device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    g_last_error = "no CUDA device";
+    return CB_E_NO_DEVICE;
+  }
+  if (device < 0 || device >= ndev) { g_last_error = "device index out of range"; return CB_E_INVALID; }
+  CB_CUDA(cudaSetDevice(device));
+  return CB_OK;
+}
+
 template <typename T>
 int dalloc(T** p, size_t n) {
   return cached_malloc((void**)p, std::max<size_t>(n, 1) * sizeof(T));
@@ -247,20 +268,30 @@ int dalloc(T** p, size_t n) {
 
 }  // namespace
 
+struct TrialGraph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;  // bracket the point pass inside the graph
+  cudaEvent_t ev_c = nullptr, ev_d = nullptr;  // bracket the Schur product
+  int n_kernels = 0;
+};
+
 struct CbBaProblem {
   int device = 0, num_sms = 148;
   int n_cams = 0, n_pts = 0, P = 6, nP = 0, n_obs = 0, n_params = 0;
   int LD = 0, n_blk = 0, n_tiles = 0, n_split = 1, k_chunks = 0, K_pad = 0;
-  int n_chunks = 0, pt_blocks = 0, n_dups = 0;
+  int n_chunks = 0, pt_grid = 0, pt_lanes = 32, n_dups = 0;
+  int cam_in_smem = 0;
+  size_t pt_smem = 0, bs_smem = 0;
   std::vector<int> h_cam_off;
   std::vector<void*> allocs;
   // problem tables
   int *d_cam_off = nullptr, *d_cam_flags = nullptr;
   double* d_cam_const = nullptr;
-  double2* d_cm_xy = nullptr;
-  int *d_cm_pt = nullptr, *d_cm_row = nullptr, *d_cm_orig = nullptr, *d_cam_start = nullptr;
+  double2 *d_cm_xy = nullptr, *d_pm_xy = nullptr;
+  int *d_cm_pt = nullptr, *d_cm_orig = nullptr, *d_cam_start = nullptr;
   int *d_chunk_cam = nullptr, *d_chunk_begin = nullptr, *d_chunk_end = nullptr, *d_cam_chunk_start = nullptr;
-  int *d_pt_start = nullptr, *d_pm_orig = nullptr, *d_pm_cam = nullptr, *d_pm_row = nullptr, *d_pm_pt = nullptr;
+  int *d_pt_start = nullptr, *d_pm_orig = nullptr, *d_pm_cam = nullptr, *d_pm_pt = nullptr;
   const int *d_obs_cam = nullptr, *d_obs_pt = nullptr;  // caller-order observation list (owned unless the caller's)
   const double* d_obs_xy = nullptr;
   std::vector<int> h_cam_flags;
@@ -270,24 +301,40 @@ struct CbBaProblem {
   int n_items = 0, n_slots = 0;
   unsigned char* d_active = nullptr;
   double *d_lo = nullptr, *d_hi = nullptr;
-  // work buffers
+  // work buffers (index [2]: current / trial point, selected on the device by LmState::cur)
   double *d_x = nullptr, *d_xc[2] = {nullptr, nullptr}, *d_xp4[2] = {nullptr, nullptr};
-  double *d_camtab = nullptr, *d_jrows = nullptr, *d_partial = nullptr, *d_Upk = nullptr, *d_gc = nullptr,
-         *d_camcost = nullptr, *d_costsum = nullptr, *d_V6 = nullptr, *d_gp = nullptr, *d_Dp2 = nullptr,
+  double *d_camtab[2] = {nullptr, nullptr}, *d_Upk[2] = {nullptr, nullptr}, *d_gc[2] = {nullptr, nullptr},
+         *d_costsum[2] = {nullptr, nullptr};
+  double *d_partial = nullptr, *d_camcost = nullptr, *d_V6 = nullptr, *d_gp = nullptr, *d_Dp2 = nullptr,
          *d_Dc2 = nullptr, *d_Linv6 = nullptr, *d_tvec = nullptr, *d_Zt = nullptr, *d_part = nullptr,
          *d_tpart = nullptr, *d_red = nullptr, *d_Minv = nullptr, *d_dc = nullptr, *d_dp = nullptr,
          *d_bpart = nullptr, *d_sc = nullptr, *d_red2 = nullptr, *d_out2 = nullptr;
   unsigned long long* d_gmax = nullptr;
-  double* h_sc = nullptr;  // pinned
+  unsigned int* d_counter = nullptr;
+  cb::LmState* d_state = nullptr;
+  cb::LmState* h_state = nullptr;  // pinned, 4 slots
+  cb::LmLogRow* d_log = nullptr;
+  int log_cap = 4096;
   double* h_x = nullptr;   // pinned staging for x
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev_state[2] = {nullptr, nullptr};
+  cudaEvent_t ev_pp[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};  // point-pass / Schur brackets (direct mode)
+  cudaStream_t cap_stream = nullptr;
+  // trial graphs, keyed by everything that is baked into the captured launches
+  struct GraphKey {
+    void *nccl, *peer; int rank, world;
+    bool operator==(const GraphKey& o) const { return nccl == o.nccl && peer == o.peer && rank == o.rank && world == o.world; }
+  };
+  long long n_solves = 0;
+  bool graph_valid = false;
+  GraphKey graph_key = {};
+  TrialGraph tg[2];
   // pcg launch configuration
   int pcg_cs = 1, pcg_rows = 0, pcg_mode = 0, pcg_cl = 1, pcg_npa = 0;
   size_t pcg_smem = 0;
   // rigid-distance constraints (optional)
   int n_c = 0, n_comp = 0, n_dim_max = 0, n_cblk = 0;
   cb::ConstraintTables ct = {};
-  double *d_c_rs = nullptr, *d_c_dirw = nullptr, *d_compL = nullptr, *d_gpt = nullptr;
+  double *d_c_rs[2] = {nullptr, nullptr}, *d_c_dirw[2] = {nullptr, nullptr}, *d_compL = nullptr, *d_gpt = nullptr;
   int* d_pt_comp = nullptr;
   size_t comp_build_smem = 0, comp_back_smem = 0;
   std::vector<int> h_ga, h_gb;
@@ -295,6 +342,21 @@ struct CbBaProblem {
   int red_slots = 64;
   CbPeerGroup* peer = nullptr;  // set for the duration of a solve that uses the peer transport
   size_t red_len() const { return (size_t)nP * nP + 3 * (size_t)nP + 1 + red_slots; }
+  cb::CPtr2 c_camtab() const { return {{d_camtab[0], d_camtab[1]}}; }
+  cb::Ptr2 m_camtab() const { return {{d_camtab[0], d_camtab[1]}}; }
+  cb::CPtr2 c_xp() const { return {{d_xp4[0], d_xp4[1]}}; }
+  cb::Ptr2 m_xp() const { return {{d_xp4[0], d_xp4[1]}}; }
+  cb::Ptr2 m_xc() const { return {{d_xc[0], d_xc[1]}}; }
+  cb::CPtr2 c_Upk() const { return {{d_Upk[0], d_Upk[1]}}; }
+  cb::Ptr2 m_Upk() const { return {{d_Upk[0], d_Upk[1]}}; }
+  cb::CPtr2 c_gc() const { return {{d_gc[0], d_gc[1]}}; }
+  cb::Ptr2 m_gc() const { return {{d_gc[0], d_gc[1]}}; }
+  cb::CPtr2 c_costsum() const { return {{d_costsum[0], d_costsum[1]}}; }
+  cb::Ptr2 m_costsum() const { return {{d_costsum[0], d_costsum[1]}}; }
+  cb::CPtr2 c_crs() const { return {{d_c_rs[0], d_c_rs[1]}}; }
+  cb::Ptr2 m_crs() const { return {{d_c_rs[0], d_c_rs[1]}}; }
+  cb::CPtr2 c_cdirw() const { return {{d_c_dirw[0], d_c_dirw[1]}}; }
+  cb::Ptr2 m_cdirw() const { return {{d_c_dirw[0], d_c_dirw[1]}}; }
 };
 
 namespace {
@@ -310,6 +372,15 @@ int bits_for(unsigned long long v) {
   int b = 1;
   while (b < 64 && (v >> b) != 0ull) ++b;
   return b;
+}
+
+void destroy_graphs(CbBaProblem* p) {
+  for (auto& g : p->tg) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (g.graph) cudaGraphDestroy(g.graph);
+    g.exec = nullptr; g.graph = nullptr; g.n_kernels = 0;
+  }
+  p->graph_valid = false;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -332,32 +403,26 @@ int build_indices(CbBaProblem* p, const int* d_obs_cam, const int* d_obs_pt, con
                   cudaStream_t st, cudaEvent_t xy_ready) {
   const int n = p->n_obs;
   const int TB = 256, G = cdiv(std::max(n, 1), TB);
+  ScopedFree sf;
   int* d_bad;
-  CB_TRY(dalloc(&d_bad, 1));
-  CB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+  CB_TRY(dalloc(&d_bad, 2)); sf.dev.push_back(d_bad);
+  CB_CUDA(cudaMemsetAsync(d_bad, 0, 2 * sizeof(int), st));
   CB_LAUNCH(cb::validate_kernel, G, TB, 0, st, d_obs_cam, d_obs_pt, n, p->n_cams, p->n_pts, d_bad);
-  int bad = 0;
-  CB_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
-  CB_CUDA(cudaStreamSynchronize(st));
-  cached_free(d_bad);
-  if (bad) {
-    g_last_error = "obs_cam / obs_pt index out of range in " + std::to_string(bad) + " observations";
-    return CB_E_INVALID;
-  }
 
-  int* d_bad2;
-  CB_TRY(dalloc(&d_bad2, 1));
   unsigned long long *k_in, *k_out;
   int *v_in, *v_out, *pm_pt, *pm_cam, *cm_cam;
-  CB_TRY(dalloc(&k_in, n)); CB_TRY(dalloc(&k_out, n));
-  CB_TRY(dalloc(&v_in, n)); CB_TRY(dalloc(&v_out, n));
-  CB_TRY(dalloc(&pm_pt, n)); CB_TRY(dalloc(&pm_cam, n)); CB_TRY(dalloc(&cm_cam, n));
+  CB_TRY(dalloc(&k_in, n)); sf.dev.push_back(k_in);
+  CB_TRY(dalloc(&k_out, n)); sf.dev.push_back(k_out);
+  CB_TRY(dalloc(&v_in, n)); sf.dev.push_back(v_in);
+  CB_TRY(dalloc(&v_out, n)); sf.dev.push_back(v_out);
+  CB_TRY(dalloc(&cm_cam, n)); sf.dev.push_back(cm_cam);
+  pm_pt = p->d_pm_pt; pm_cam = p->d_pm_cam;
 
-  // temp storage for cub (max of sort and scan requirements)
+  // temp storage for cub
   size_t tb = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in, k_out, v_in, v_out, n, 0, 64, st);
   void* d_tmp;
-  CB_TRY(cached_malloc(&d_tmp, std::max<size_t>(tb, 16)));
+  CB_TRY(cached_malloc(&d_tmp, std::max<size_t>(tb, 16))); sf.dev.push_back(d_tmp);
 
   // (1) point-major order: key = pt * n_cams + cam, stable -> ties keep caller order
   CB_LAUNCH(cb::make_keys_kernel, G, TB, 0, st, d_obs_pt, d_obs_cam, (long long)p->n_cams, n, k_in, v_in);
@@ -366,34 +431,28 @@ int build_indices(CbBaProblem* p, const int* d_obs_cam, const int* d_obs_pt, con
   g_launches.fetch_add(4);
   CB_LAUNCH(cb::split_keys_kernel, G, TB, 0, st, k_out, (long long)p->n_cams, n, pm_pt, pm_cam);
   CB_LAUNCH(cb::lower_bound_kernel, cdiv(p->n_pts + 1, TB), TB, 0, st, pm_pt, n, p->n_pts, p->d_pt_start);
-  CB_CUDA(cudaMemcpyAsync(p->d_pm_cam, pm_cam, sizeof(int) * n, cudaMemcpyDeviceToDevice, st));
-  CB_CUDA(cudaMemcpyAsync(p->d_pm_pt, pm_pt, sizeof(int) * n, cudaMemcpyDeviceToDevice, st));
-  CB_CUDA(cudaMemsetAsync(d_bad2, 0, sizeof(int), st));
-  CB_LAUNCH(cb::count_dups_kernel, G, TB, 0, st, pm_pt, pm_cam, n, d_bad2);
-  CB_CUDA(cudaMemcpyAsync(&p->n_dups, d_bad2, sizeof(int), cudaMemcpyDeviceToHost, st));
-  // (2) row layout of the Jacobian buffer: (point block of PT_BLOCK points, camera, point).  Within a
-  //     block all rows of one camera are adjacent, so a camera-major warp of resjac_kernel writes runs of
-  //     consecutive 160-byte rows (DRAM page locality; scattered single rows cap at ~2.4 TB/s on B200,
-  //     runs of >= 8 rows reach ~4.5 TB/s -- profiles/microbench/row_scatter.cu), while every point's rows
-  //     stay inside one contiguous block for the point-centric kernels.
-  CB_LAUNCH(cb::make_block_keys_kernel, G, TB, 0, st, pm_pt, pm_cam, p->n_cams, cb::PT_BLOCK, n, k_in, v_in);
-  const int kb2 = bits_for(((unsigned long long)(p->n_pts / cb::PT_BLOCK + 1) * p->n_cams + p->n_cams) * cb::PT_BLOCK);
-  CB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb, k_in, k_out, v_in, v_out, n, 0, kb2, st));
-  g_launches.fetch_add(4);
-  CB_LAUNCH(cb::invert_perm_kernel, G, TB, 0, st, v_out, n, p->d_pm_row);  // pm position -> row
-  // (3) camera-major order: key = cam * n_pts + pt over the point-major positions (stable)
+  CB_LAUNCH(cb::count_dups_kernel, G, TB, 0, st, pm_pt, pm_cam, n, d_bad + 1);
+  // (2) camera-major order: key = cam * n_pts + pt over the point-major positions (stable)
   CB_LAUNCH(cb::make_keys_kernel, G, TB, 0, st, pm_cam, pm_pt, (long long)p->n_pts, n, k_in, v_in);
   CB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb, k_in, k_out, v_in, v_out, n, 0, kb, st));
   g_launches.fetch_add(4);
   CB_LAUNCH(cb::split_keys_kernel, G, TB, 0, st, k_out, (long long)p->n_pts, n, cm_cam, v_in);
   CB_LAUNCH(cb::lower_bound_kernel, cdiv(p->n_cams + 1, TB), TB, 0, st, cm_cam, n, p->n_cams, p->d_cam_start);
   if (xy_ready) CB_CUDA(cudaStreamWaitEvent(st, xy_ready, 0));
-  CB_LAUNCH(cb::cm_gather_kernel, G, TB, 0, st, v_out, p->d_pm_row, p->d_pm_orig, pm_pt,
-            reinterpret_cast<const double2*>(d_obs_xy), n, p->d_cm_row, p->d_cm_pt, p->d_cm_orig, p->d_cm_xy);
-  // (4) chunk table (host, n_cams + 1 integers)
+  CB_LAUNCH(cb::cm_gather_kernel, G, TB, 0, st, v_out, p->d_pm_orig, pm_pt,
+            reinterpret_cast<const double2*>(d_obs_xy), n, p->d_cm_pt, p->d_cm_orig, p->d_cm_xy);
+  CB_LAUNCH(cb::pm_gather_kernel, G, TB, 0, st, p->d_pm_orig, reinterpret_cast<const double2*>(d_obs_xy), n, p->d_pm_xy);
+  // (3) chunk table (host, n_cams + 1 integers)
   std::vector<int> cam_start(p->n_cams + 1);
+  int bad[2] = {0, 0};
   CB_CUDA(cudaMemcpyAsync(cam_start.data(), p->d_cam_start, sizeof(int) * (p->n_cams + 1), cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaMemcpyAsync(bad, d_bad, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
   CB_CUDA(cudaStreamSynchronize(st));
+  if (bad[0]) {
+    g_last_error = "obs_cam / obs_pt index out of range in " + std::to_string(bad[0]) + " observations";
+    return CB_E_INVALID;
+  }
+  p->n_dups = bad[1];
   std::vector<int> cc, cbeg, cend, ccs(p->n_cams + 1);
   int chunk = cb::RJ_CHUNK;
   if (const char* e = std::getenv("CB_RJ_CHUNK")) chunk = std::max(cb::RJ_THREADS, std::atoi(e));
@@ -417,100 +476,52 @@ int build_indices(CbBaProblem* p, const int* d_obs_cam, const int* d_obs_pt, con
   }
   CB_CUDA(cudaMemcpyAsync(p->d_cam_chunk_start, ccs.data(), sizeof(int) * ccs.size(), cudaMemcpyHostToDevice, st));
   CB_CUDA(cudaStreamSynchronize(st));
-  cached_free(d_tmp); cached_free(k_in); cached_free(k_out); cached_free(v_in); cached_free(v_out);
-  cached_free(pm_pt); cached_free(pm_cam); cached_free(cm_cam); cached_free(d_bad2);
   return CB_OK;
 }
 
 // ------------------------------------------------------------------------------------------
-// one evaluation / linearisation / damped system / step
+// the kernels of one evaluation / one LM trial
 // ------------------------------------------------------------------------------------------
 template <int P>
-int run_cam_prep(CbBaProblem* p, const double* xc, cudaStream_t st) {
-  CB_LAUNCH(cb::cam_prep_kernel, cdiv(p->n_cams, 64), 64, 0, st, xc, p->d_cam_flags, p->d_cam_const, p->n_cams, P,
-            p->d_camtab);
+int run_cam_prep(CbBaProblem* p, const double* xc, double* camtab, cudaStream_t st) {
+  CB_LAUNCH(cb::cam_prep_kernel, cdiv(p->n_cams, 64), 64, 0, st, xc, p->d_cam_flags, p->d_cam_const, p->n_cams, P, camtab);
   return CB_OK;
 }
 
+// camera-major pass; st_dev == nullptr: stand-alone evaluation at buffer 0
 template <int P, int MODE>
-void launch_resjac(CbBaProblem* p, const double* xp4, int loss, double fscale, double* out2, cudaStream_t st) {
+void launch_resjac(CbBaProblem* p, const cb::LmState* st_dev, int flip, int loss, double fscale, double* out2,
+                   cudaStream_t st) {
   if (p->n_chunks == 0) return;
-  CB_LAUNCH((cb::resjac_kernel<P, MODE>), p->n_chunks, cb::RJ_THREADS, 0, st, p->d_chunk_cam, p->d_chunk_begin,
-            p->d_chunk_end, p->d_cm_xy, p->d_cm_pt, p->d_cm_row, p->d_cm_orig, p->d_camtab, xp4, loss, fscale,
-            p->d_jrows, p->d_partial, out2);
-}
-
-// residual + Jacobian rows + per-camera / per-point normal-equation blocks at (xc, xp4)
-template <int P>
-int linearize(CbBaProblem* p, const double* xc, const double* xp4, int loss, double fscale, cudaStream_t st,
-              bool time_rj, float* rj_ms) {
-  using RT = cb::RowT<P>;
-  CB_TRY(run_cam_prep<P>(p, xc, st));
-  if (time_rj) CB_CUDA(cudaEventRecord(p->ev2, st));
-  launch_resjac<P, 0>(p, xp4, loss, fscale, nullptr, st);
-  if (time_rj) {
-    CB_CUDA(cudaEventRecord(p->ev3, st));
-  }
-  CB_LAUNCH((cb::cam_reduce_kernel<P>), p->n_cams, 64, 0, st, p->d_cam_chunk_start, p->d_partial, p->d_Upk, p->d_gc,
-            p->d_camcost);
-  static_assert(RT::NACC <= 64, "cam_reduce block too small");
-  if (p->n_c)
-    CB_LAUNCH((cb::constraint_eval_kernel<false>), p->n_cblk, cb::CC_THREADS, 0, st, p->ct, xp4, loss, fscale, p->d_c_rs,
-              p->d_c_dirw, (double*)nullptr, p->d_camcost + p->n_cams);
-  CB_LAUNCH(cb::sum_kernel, 1, 256, 0, st, p->d_camcost, p->n_cams + p->n_cblk, p->d_costsum);
-  CB_CUDA(cudaMemsetAsync(p->d_gmax, 0, sizeof(unsigned long long), st));
-  (void)rj_ms;
-  return CB_OK;
+  CB_LAUNCH((cb::resjac_kernel<P, MODE>), p->n_chunks, cb::RJ_THREADS, 0, st, st_dev, flip, p->d_chunk_cam,
+            p->d_chunk_begin, p->d_chunk_end, p->d_cm_xy, p->d_cm_pt, p->d_cm_orig, p->c_camtab(), p->c_xp(), loss,
+            fscale, p->d_partial, out2);
 }
 
 template <int P>
-int build_system(CbBaProblem* p, double lam, bool new_lin, const CbBaOptions* opt, cudaStream_t st) {
-#define CB_PT_BUILD(FUSED, DUPS)                                                                                  \
-  CB_LAUNCH((cb::pt_build_kernel<P, FUSED, DUPS>), p->pt_blocks, cb::PT_WARPS * 32, 0, st, p->d_pt_start, p->d_pm_cam, \
-            p->d_pm_row, p->d_pt_comp, p->n_pts, p->d_jrows, p->d_V6, p->d_gp, p->d_Dp2, lam, p->d_Linv6, p->d_tvec, p->d_Zt,      \
-            (size_t)p->LD, p->d_gmax)
-  if (new_lin) {
-    if (p->n_dups) CB_PT_BUILD(true, true); else CB_PT_BUILD(true, false);
-  } else {
-    if (p->n_dups) CB_PT_BUILD(false, true); else CB_PT_BUILD(false, false);
-  }
-#undef CB_PT_BUILD
-  if (p->n_c)
-    CB_LAUNCH((cb::comp_build_kernel<P>), p->n_comp, cb::CC_THREADS, p->comp_build_smem, st, p->ct, p->d_pt_start,
-              p->d_pm_cam, p->d_pm_row, p->d_jrows, p->d_V6, p->d_gp, p->d_Dp2, p->d_gpt, p->d_c_rs, p->d_c_dirw, lam,
-              new_lin ? 1 : 0, p->n_cams, p->d_compL, p->d_tvec, p->d_Zt, (size_t)p->LD, p->d_gmax);
-  CB_LAUNCH(cb::schur_syrk_kernel, p->n_items, cb::SY_THREADS, sizeof(cb::SyrkSmem), st, p->d_Zt, (size_t)p->LD,
-            p->d_tvec, p->d_items, p->d_part, p->d_tpart);
-  const size_t nfin = (size_t)p->nP * p->nP + p->nP + 1;
-  // gradient inf-norm over points: one slot per rank so a SUM all-reduce carries the max
-  const size_t slot0 = (size_t)p->nP * p->nP + 3 * (size_t)p->nP + 1;
-  const int rank = sharded(opt) ? std::min(std::max(opt->rank, 0), p->red_slots - 1) : 0;
-  if (opt && opt->peer_group) {
-    // finalize + all-reduce over NVLink peer memory in one kernel (cb_peer.cuh)
-    CbPeerGroup* g = (CbPeerGroup*)opt->peer_group;
-    // every block spins on the peers' flags, so the whole grid must be co-resident: size it from the occupancy API
-    static int blocks_per_sm = 0;
-    if (blocks_per_sm == 0) {
-      int nb = 0;
-      CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cb::schur_finalize_peer_kernel<P>, cb::PEER_THREADS, 0));
-      blocks_per_sm = std::max(1, std::min(nb, 2));
-    }
-    CB_LAUNCH((cb::schur_finalize_peer_kernel<P>), blocks_per_sm * p->num_sms, cb::PEER_THREADS, 0, st, p->nP, p->n_blk, p->d_tile_of,
-              p->d_tile_slot_start, p->d_tile_slots, p->d_part, p->d_tpart, p->d_Upk, p->d_gc, p->d_costsum,
-              (const double*)p->d_gmax, p->red_slots, rank, g->tab, ++g->epoch_big, p->d_red);
-  } else {
-    CB_LAUNCH((cb::schur_finalize_kernel<P>), cdiv((long long)nfin, 256), 256, 0, st, p->nP, p->n_blk, p->d_tile_of,
-              p->d_tile_slot_start, p->d_tile_slots, p->d_part, p->d_tpart, p->d_Upk, p->d_gc, p->d_costsum, p->d_red);
-    CB_CUDA(cudaMemsetAsync(p->d_red + slot0, 0, sizeof(double) * p->red_slots, st));
-    CB_CUDA(cudaMemcpyAsync(p->d_red + slot0 + rank, p->d_gmax, sizeof(double), cudaMemcpyDeviceToDevice, st));
-    if (sharded(opt)) CB_TRY(do_allreduce(opt, p->d_red, (long long)p->red_len(), st));
-  }
-  CB_LAUNCH(cb::post_reduce_kernel, 1, 256, 0, st, p->nP, lam, new_lin ? 1 : 0, p->d_red, p->d_Dc2, p->d_active,
-            p->d_sc);
-  return CB_OK;
+void launch_pt_pass(CbBaProblem* p, cudaStream_t st) {
+#define CB_PT_PASS(LANES, DUPS)                                                                                       \
+  CB_LAUNCH((cb::pt_pass_kernel<P, LANES, DUPS>), p->pt_grid, cb::PT_WARPS * 32, p->pt_smem, st, p->d_state,          \
+            p->d_pt_start, p->d_pm_cam, p->d_pm_xy, p->d_pt_comp, p->n_pts, p->n_cams, p->c_camtab(), p->c_xp(),       \
+            p->d_V6, p->d_gp, p->d_Dp2, p->d_Linv6, p->d_tvec, p->d_Zt, (size_t)p->LD, p->d_gmax, p->cam_in_smem)
+  if (p->pt_lanes == 8) { if (p->n_dups) CB_PT_PASS(8, true); else CB_PT_PASS(8, false); }
+  else { if (p->n_dups) CB_PT_PASS(32, true); else CB_PT_PASS(32, false); }
+#undef CB_PT_PASS
 }
 
-using PcgFn = void (*)(const double*, const double*, const double*, int, int, int, double, int, double*, double*);
+template <int P>
+void launch_pt_backsub(CbBaProblem* p, double* dp_out, cudaStream_t st) {
+  const int bstride = p->pt_grid + p->n_comp;
+#define CB_PT_BACK(LANES)                                                                                             \
+  CB_LAUNCH((cb::pt_backsub_kernel<P, LANES>), p->pt_grid, cb::PT_WARPS * 32, p->bs_smem, st, p->d_state,             \
+            p->d_pt_start, p->d_pm_cam, p->d_pm_xy, p->d_pt_comp, p->n_pts, p->n_cams, p->nP, p->c_camtab(),           \
+            p->m_xp(), p->d_dc, p->d_Linv6, p->d_tvec, p->d_gp, p->d_Dp2, dp_out, p->d_bpart, bstride, p->cam_in_smem)
+  if (p->pt_lanes == 8) CB_PT_BACK(8); else CB_PT_BACK(32);
+#undef CB_PT_BACK
+}
+
+using PcgFn = void (*)(const cb::LmState*, const double*, const double*, const double*, int, int, int, double, int,
+                       double*, double*);
 // mode 0: slab in shared memory, 1: slab from global, 2: slab in registers with cl columns per lane
 PcgFn pcg_fn(int mode, int P, int cl) {
   if (mode == 2) {
@@ -521,7 +532,7 @@ PcgFn pcg_fn(int mode, int P, int cl) {
   return mode == 0 ? cb::pcg_cluster_kernel<0, 9, 1> : cb::pcg_cluster_kernel<1, 9, 1>;
 }
 
-int launch_pcg(CbBaProblem* p, double tol2, int max_iter, cudaStream_t st) {
+int launch_pcg(CbBaProblem* p, const cb::LmState* st_dev, double tol2, int max_iter, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(p->pcg_cs);
   cfg.blockDim = dim3(cb::PCG_THREADS);
@@ -537,68 +548,104 @@ int launch_pcg(CbBaProblem* p, double tol2, int max_iter, cudaStream_t st) {
   const double* S = p->d_red;
   const double* b = p->d_red + (size_t)p->nP * p->nP;
   auto fn = pcg_fn(p->pcg_mode, p->P, p->pcg_cl);
-  CB_CUDA(cudaLaunchKernelEx(&cfg, fn, S, b, (const double*)p->d_Minv, p->nP, p->pcg_npa, p->pcg_rows, tol2, max_iter,
-                             p->d_dc, p->d_sc));
+  CB_CUDA(cudaLaunchKernelEx(&cfg, fn, st_dev, S, b, (const double*)p->d_Minv, p->nP, p->pcg_npa, p->pcg_rows, tol2,
+                             max_iter, p->d_dc, p->d_sc));
   g_launches.fetch_add(1);
   return CB_OK;
 }
 
+// camera-major pass at buffer (cur ^ flip) + reduction of its partials; mode as trial_reduce_kernel
 template <int P>
-int solve_step(CbBaProblem* p, double lam, int cur, const CbBaOptions* opt, double* dp_out, cudaStream_t st) {
-  CB_LAUNCH((cb::block_inverse_kernel<P>), cdiv(p->n_cams, 64), 64, 0, st, p->d_red, p->nP, p->n_cams, p->d_Minv);
-  const double tol = (opt && opt->pcg_tol > 0) ? opt->pcg_tol : 1e-6;
-  const int mit = (opt && opt->pcg_max_iter > 0) ? opt->pcg_max_iter : 4 * p->nP;
-  CB_TRY(launch_pcg(p, tol * tol, mit, st));
-  const size_t nn = (size_t)p->nP * p->nP;
-  CB_LAUNCH(cb::cam_update_kernel, 1, 256, 0, st, p->nP, lam, p->d_xc[cur], p->d_dc, p->d_lo, p->d_hi,
-            p->d_red + nn + p->nP, p->d_Dc2, p->d_active, p->d_xc[cur ^ 1], p->d_sc);
-  // (reading the 320 MB of Jacobian rows instead of the 461 MB dense factor was measured: no faster)
-  const int bstride = p->pt_blocks + p->n_comp;
-  CB_LAUNCH(cb::pt_backsub_kernel, p->pt_blocks, cb::PT_WARPS * 32, sizeof(double) * p->nP, st, p->n_pts, p->nP, lam,
-            p->d_pt_comp, bstride, p->d_Zt, (size_t)p->LD, p->d_dc, p->d_Linv6, p->d_tvec, p->d_gp, p->d_Dp2,
-            p->d_xp4[cur], p->d_xp4[cur ^ 1], dp_out, p->d_bpart);
+int camera_pass(CbBaProblem* p, int flip, int mode, cudaStream_t st) {
+  const int loss = 0;
+  const double fscale = 1.0;  // the kernels take both from the device state
+  launch_resjac<P, 0>(p, p->d_state, flip, loss, fscale, nullptr, st);
   if (p->n_c)
-    CB_LAUNCH(cb::comp_backsub_kernel, p->n_comp, cb::CC_THREADS, p->comp_back_smem, st, p->ct, p->nP, lam, p->d_Zt,
-              (size_t)p->LD, p->d_dc, p->d_compL, p->d_tvec, p->d_gpt, p->d_Dp2, p->d_xp4[cur], p->d_xp4[cur ^ 1],
-              dp_out, p->d_bpart, bstride, p->pt_blocks);
-  CB_LAUNCH(cb::sum3_kernel, 3, 256, 0, st, p->d_bpart, bstride, p->d_red2 + 1);
+    CB_LAUNCH((cb::constraint_eval_kernel<false>), p->n_cblk, cb::CC_THREADS, 0, st, (const cb::LmState*)p->d_state, flip,
+              p->ct, p->c_xp(), loss, fscale, p->m_crs(), p->m_cdirw(), (double*)nullptr, p->d_camcost + p->n_cams);
+  CB_LAUNCH((cb::trial_reduce_kernel<P>), p->n_cams + 1, 64, 0, st, p->d_state, mode, p->n_cams, p->d_cam_chunk_start,
+            p->d_partial, p->m_Upk(), p->m_gc(), p->m_costsum(), p->d_camcost, p->n_cblk, p->d_bpart,
+            p->pt_grid + p->n_comp, p->pt_grid + p->n_comp, p->d_red2, p->d_counter, p->d_sc, p->d_log);
   return CB_OK;
 }
 
+// damped system at the current point: point pass, Schur product, reduced system (+ all-reduce), head-of-iteration tests
 template <int P>
-int trial_cost(CbBaProblem* p, int nxt, int loss, double fscale, const CbBaOptions* opt, cudaStream_t st) {
-  CB_TRY(run_cam_prep<P>(p, p->d_xc[nxt], st));
-  launch_resjac<P, 1>(p, p->d_xp4[nxt], loss, fscale, nullptr, st);
+int build_system(CbBaProblem* p, const CbBaOptions* opt, cudaStream_t st, cudaEvent_t ev_a, cudaEvent_t ev_b,
+                 cudaEvent_t ev_c = nullptr, cudaEvent_t ev_d = nullptr) {
+  if (ev_a) CB_CUDA(cudaEventRecord(ev_a, st));
+  launch_pt_pass<P>(p, st);
+  if (ev_b) CB_CUDA(cudaEventRecord(ev_b, st));
   if (p->n_c)
-    CB_LAUNCH((cb::constraint_eval_kernel<true>), p->n_cblk, cb::CC_THREADS, 0, st, p->ct, p->d_xp4[nxt], loss, fscale,
-              (double*)nullptr, (double*)nullptr, (double*)nullptr, p->d_partial + p->n_chunks);
-  CB_LAUNCH(cb::sum_kernel, 1, 256, 0, st, p->d_partial, p->n_chunks + p->n_cblk, p->d_red2);
-  if (sharded(opt)) CB_TRY(do_allreduce(opt, p->d_red2, 4, st));
-  return CB_OK;
-}
-
-struct HostScalars {
-  double sc[cb::SC_COUNT];
-  double red2[4];
-  double slots[64];
-};
-
-int readback(CbBaProblem* p, HostScalars* h, cudaStream_t st) {
-  const size_t slot0 = (size_t)p->nP * p->nP + 3 * (size_t)p->nP + 1;
-  CB_CUDA(cudaMemcpyAsync(p->h_sc, p->d_sc, sizeof(double) * cb::SC_COUNT, cudaMemcpyDeviceToHost, st));
-  CB_CUDA(cudaMemcpyAsync(p->h_sc + cb::SC_COUNT, p->d_red2, sizeof(double) * 4, cudaMemcpyDeviceToHost, st));
-  CB_CUDA(cudaMemcpyAsync(p->h_sc + cb::SC_COUNT + 4, p->d_red + slot0, sizeof(double) * p->red_slots,
-                          cudaMemcpyDeviceToHost, st));
-  int peer_err = 0;
-  if (p->peer) CB_CUDA(cudaMemcpyAsync(&peer_err, p->peer->tab.err, sizeof(int), cudaMemcpyDeviceToHost, st));
-  CB_CUDA(cudaStreamSynchronize(st));
-  if (peer_err) {
-    g_last_error = "peer all-reduce timed out waiting for another rank";
-    return CB_E_CALLBACK;
+    CB_LAUNCH((cb::comp_build_kernel<P>), p->n_comp, cb::CC_THREADS, p->comp_build_smem, st, (const cb::LmState*)p->d_state,
+              p->ct, p->d_pt_start, p->d_pm_cam, p->d_V6, p->d_gp, p->d_Dp2, p->d_gpt, p->c_crs(), p->c_cdirw(), p->n_cams,
+              p->d_compL, p->d_tvec, p->d_Zt, (size_t)p->LD, p->d_gmax);
+  if (ev_c) CB_CUDA(cudaEventRecord(ev_c, st));
+  CB_LAUNCH(cb::schur_syrk_kernel, p->n_items, cb::SY_THREADS, sizeof(cb::SyrkSmem), st, (const cb::LmState*)p->d_state,
+            p->d_Zt, (size_t)p->LD, p->d_tvec, p->d_items, p->d_part, p->d_tpart);
+  if (ev_d) CB_CUDA(cudaEventRecord(ev_d, st));
+  const size_t nfin = (size_t)p->nP * p->nP + p->nP + 1;
+  // gradient inf-norm over points: one slot per rank so a SUM all-reduce carries the max
+  const int rank = sharded(opt) ? std::min(std::max(opt->rank, 0), p->red_slots - 1) : 0;
+  if (opt && opt->peer_group) {
+    // finalize + all-reduce over NVLink peer memory in one COOPERATIVE launch (cb_peer.cuh)
+    CbPeerGroup* g = (CbPeerGroup*)opt->peer_group;
+    int nb = 0;
+    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cb::schur_finalize_peer_kernel<P>, cb::PEER_THREADS, 0));
+    const int grid = std::max(1, std::min(nb, 2)) * p->num_sms;
+    const cb::LmState* sd = p->d_state;
+    int nP = p->nP, n_blk = p->n_blk, red_slots = p->red_slots, rk = rank;
+    cb::CPtr2 upk = p->c_Upk(), gc = p->c_gc(), cs = p->c_costsum();
+    const double* gmax = (const double*)p->d_gmax;
+    void* args[] = {&sd, &nP, &n_blk, &p->d_tile_of, &p->d_tile_slot_start, &p->d_tile_slots, &p->d_part, &p->d_tpart,
+                    &upk, &gc, &cs, &gmax, &red_slots, &rk, &g->tab, &p->d_red};
+    CB_CUDA(cudaLaunchCooperativeKernel((const void*)cb::schur_finalize_peer_kernel<P>, dim3(grid), dim3(cb::PEER_THREADS),
+                                        args, 0, st));
+    g_launches.fetch_add(1);
+  } else {
+    CB_LAUNCH((cb::schur_finalize_kernel<P>), cdiv((long long)std::max<size_t>(nfin, p->red_slots), 256), 256, 0, st,
+              (const cb::LmState*)p->d_state, p->nP, p->n_blk, p->d_tile_of, p->d_tile_slot_start, p->d_tile_slots,
+              p->d_part, p->d_tpart, p->c_Upk(), p->c_gc(), p->c_costsum(), (const double*)p->d_gmax, p->red_slots, rank,
+              p->d_red);
+    if (sharded(opt)) CB_TRY(do_allreduce(opt, p->d_red, (long long)p->red_len(), st));
   }
-  std::memcpy(h->sc, p->h_sc, sizeof(double) * cb::SC_COUNT);
-  std::memcpy(h->red2, p->h_sc + cb::SC_COUNT, sizeof(double) * 4);
-  std::memcpy(h->slots, p->h_sc + cb::SC_COUNT + 4, sizeof(double) * p->red_slots);
+  CB_LAUNCH((cb::reduced_prep_kernel<P>), 1, 256, 0, st, p->d_state, p->nP, p->n_cams, p->red_slots, p->d_red, p->d_Dc2,
+            p->d_active, p->d_Minv, p->d_gmax, p->d_sc);
+  return CB_OK;
+}
+
+template <int P>
+int solve_step(CbBaProblem* p, double* dp_out, cudaStream_t st) {
+  CB_TRY(launch_pcg(p, p->d_state, 0.0, 0, st));  // tolerance and iteration cap come from the device state
+  const size_t nn = (size_t)p->nP * p->nP;
+  CB_LAUNCH(cb::cam_step_kernel, 1, 256, 0, st, (const cb::LmState*)p->d_state, p->nP, p->n_cams, p->P, p->m_xc(), p->d_dc,
+            p->d_lo, p->d_hi, p->d_red + nn + p->nP, p->d_Dc2, p->d_active, p->d_cam_flags, p->d_cam_const, p->m_camtab(),
+            p->d_sc);
+  launch_pt_backsub<P>(p, dp_out, st);
+  if (p->n_c)
+    CB_LAUNCH(cb::comp_backsub_kernel, p->n_comp, cb::CC_THREADS, p->comp_back_smem, st, (const cb::LmState*)p->d_state,
+              p->ct, p->nP, p->d_Zt, (size_t)p->LD, p->d_dc, p->d_compL, p->d_tvec, p->d_gpt, p->d_Dp2, p->m_xp(), dp_out,
+              p->d_bpart, p->pt_grid + p->n_comp, p->pt_grid);
+  return CB_OK;
+}
+
+// one whole LM trial: the same launches every time, all decisions on the device
+template <int P>
+int enqueue_trial(CbBaProblem* p, const CbBaOptions* opt, cudaStream_t st, cudaEvent_t* ev) {
+  CB_TRY(build_system<P>(p, opt, st, ev[0], ev[1], ev[2], ev[3]));
+  CB_TRY(solve_step<P>(p, nullptr, st));
+  const bool multi = sharded(opt);
+  CB_TRY(camera_pass<P>(p, 1, multi ? 2 : 1, st));
+  if (multi) {
+    cb::PeerTable none = {};
+    if (opt->peer_group) {
+      CB_LAUNCH(cb::lm_decide_kernel, 1, 32, 0, st, p->d_state, (const double*)p->d_sc, p->d_red2, p->d_log,
+                ((CbPeerGroup*)opt->peer_group)->tab, 1);
+    } else {
+      CB_TRY(do_allreduce(opt, p->d_red2, 4, st));
+      CB_LAUNCH(cb::lm_decide_kernel, 1, 32, 0, st, p->d_state, (const double*)p->d_sc, p->d_red2, p->d_log, none, 0);
+    }
+  }
   return CB_OK;
 }
 
@@ -637,138 +684,198 @@ int set_bounds(CbBaProblem* p, bool use_bounds, cudaStream_t st) {
   return CB_OK;
 }
 
+// fresh device state for a solve (or a diagnostic evaluation) starting at buffer 0
+int init_state(CbBaProblem* p, const CbBaOptions* opt, double lam, long long max_nfev, cudaStream_t st) {
+  cb::LmState& h = p->h_state[3];
+  std::memset(&h, 0, sizeof(h));
+  h.lam = lam; h.nu = 2.0;
+  h.ftol = opt->ftol; h.xtol = opt->xtol; h.gtol = opt->gtol;
+  h.nfev = 1; h.njev = 1; h.nit = 0; h.max_nfev = max_nfev;
+  h.new_lin = 1;
+  h.log_cap = p->log_cap;
+  h.loss = opt->loss;
+  h.fscale = opt->f_scale > 0 ? opt->f_scale : 1.0;
+  const double tol = opt->pcg_tol > 0 ? opt->pcg_tol : 1e-6;
+  h.pcg_tol2 = tol * tol;
+  h.pcg_max_iter = opt->pcg_max_iter > 0 ? opt->pcg_max_iter : 4 * p->nP;
+  if (opt->peer_group) {
+    CbPeerGroup* g = (CbPeerGroup*)opt->peer_group;
+    h.epoch_big = g->epoch_big; h.epoch_small = g->epoch_small;
+  }
+  CB_CUDA(cudaMemcpyAsync(p->d_state, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+  CB_CUDA(cudaMemsetAsync(p->d_gmax, 0, 2 * sizeof(unsigned long long), st));
+  CB_CUDA(cudaMemsetAsync(p->d_counter, 0, 4 * sizeof(unsigned int), st));
+  CB_CUDA(cudaMemsetAsync(p->d_sc, 0, sizeof(double) * cb::SC_COUNT, st));
+  CB_CUDA(cudaMemsetAsync(p->d_Dc2, 0, sizeof(double) * p->nP, st));
+  CB_CUDA(cudaMemsetAsync(p->d_Dp2, 0, sizeof(double) * 3 * (size_t)std::max(p->n_pts, 1), st));
+  return CB_OK;
+}
+
+// capture one LM trial into a graph (two instances, so that the event pair of trial t can be read while trial t+1 runs)
+template <int P>
+int ensure_graphs(CbBaProblem* p, const CbBaOptions* opt) {
+  CbBaProblem::GraphKey key{opt->nccl_comm, opt->peer_group, opt->rank, opt->world_size};
+  if (p->graph_valid && p->graph_key == key) return CB_OK;
+  destroy_graphs(p);
+  if (!p->cap_stream) CB_CUDA(cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking));
+  for (int k = 0; k < 2; ++k) {
+    TrialGraph& g = p->tg[k];
+    if (!g.ev_a) {
+      CB_CUDA(cudaEventCreate(&g.ev_a)); CB_CUDA(cudaEventCreate(&g.ev_b));
+      CB_CUDA(cudaEventCreate(&g.ev_c)); CB_CUDA(cudaEventCreate(&g.ev_d));
+    }
+    cudaEvent_t evs[4] = {g.ev_a, g.ev_b, g.ev_c, g.ev_d};
+    const long long l0 = g_launches.load();
+    CB_CUDA(cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_trial<P>(p, opt, p->cap_stream, evs);
+    cudaError_t e = cudaStreamEndCapture(p->cap_stream, &g.graph);
+    g_launches.store(l0);  // capture launches nothing
+    if (rc != CB_OK) { if (g.graph) { cudaGraphDestroy(g.graph); g.graph = nullptr; } return rc; }
+    if (e != cudaSuccess) {
+      g_last_error = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e);
+      cudaGetLastError();
+      return CB_E_CUDA;
+    }
+    size_t nn = 0;
+    cudaGraphGetNodes(g.graph, nullptr, &nn);
+    g.n_kernels = (int)nn - 4;  // minus the four event-record nodes
+    CB_CUDA(cudaGraphInstantiate(&g.exec, g.graph, 0));
+  }
+  p->graph_key = key;
+  p->graph_valid = true;
+  return CB_OK;
+}
+
 // ------------------------------------------------------------------------------------------
-// Levenberg-Marquardt driver
+// Levenberg-Marquardt driver: the loop itself runs on the device (cb_lm.cuh); the host only keeps the GPU fed one
+// trial ahead and looks at the state of trial t-1 while trial t executes.
 // ------------------------------------------------------------------------------------------
 template <int P>
 int lm_solve(CbBaProblem* p, const CbBaOptions* opt, double* x_inout, CbBaResult* res, cudaStream_t st) {
-  const int loss = opt->loss;
-  const double fscale = opt->f_scale > 0 ? opt->f_scale : 1.0;
-  const double ftol = opt->ftol, xtol = opt->xtol, gtol = opt->gtol;
   const long long max_nfev = opt->max_nfev > 0 ? opt->max_nfev : 100ll * p->n_params;
   const bool verbose = opt->verbose >= 2 && opt->rank == 0;
   const long long launches0 = g_launches.load();
   std::memset(res, 0, sizeof(*res));
 
+  // One CUDA graph per trial from the second solve on a problem (capture + instantiation cost about as much as the
+  // launches of one short solve save), never when a host callback carries the all-reduce (it cannot be captured).
+  // CB_LM_GRAPH = 0: never, 1: from the second solve (default), 2: always.
+  int graph_mode = 1;
+  if (const char* e = std::getenv("CB_LM_GRAPH")) graph_mode = std::atoi(e);
+  ++p->n_solves;
+  bool use_graph = opt->allreduce == nullptr && (graph_mode >= 2 || (graph_mode == 1 && (p->n_solves >= 2 || p->graph_valid)));
+  if (use_graph) {
+    int rc = ensure_graphs<P>(p, opt);
+    if (rc != CB_OK) {
+      if (std::getenv("CB_LM_GRAPH_STRICT")) return rc;
+      cudaGetLastError();
+      use_graph = false;  // capture unsupported for this configuration: direct launches
+    }
+  }
+
   CB_TRY(set_bounds(p, opt->use_bounds != 0, st));
-  CB_CUDA(cudaMemsetAsync(p->d_Dc2, 0, sizeof(double) * p->nP, st));
-  CB_CUDA(cudaMemsetAsync(p->d_Dp2, 0, sizeof(double) * 3 * (size_t)std::max(p->n_pts, 1), st));
-  CB_CUDA(cudaMemsetAsync(p->d_sc, 0, sizeof(double) * cb::SC_COUNT, st));
+  CB_TRY(init_state(p, opt, opt->lambda0 > 0 ? opt->lambda0 : 1e-4, max_nfev, st));
   CB_TRY(upload_x(p, x_inout, st));
   CB_CUDA(cudaEventRecord(p->ev0, st));
+  CB_TRY(run_cam_prep<P>(p, p->d_xc[0], p->d_camtab[0], st));
+  CB_TRY(camera_pass<P>(p, 0, 0, st));
 
-  int cur = 0;
-  double lam = opt->lambda0 > 0 ? opt->lambda0 : 1e-4, nu = 2.0;
-  long long nfev = 1, njev = 1, nit = 0, pcg_total = 0;
-  double rj_ms_total = 0.0;
-  long long rj_launches = 0;
-  float ms = 0.f;
-  CB_TRY(linearize<P>(p, p->d_xc[cur], p->d_xp4[cur], loss, fscale, st, true, nullptr));
-  bool rj_pending = true;  // ev2/ev3 bracket the last residual+Jacobian launch; read after the next sync
-
-  bool new_lin = true;
-  int status = 0;
-  double cost = 0.0, gnorm = 0.0;
-  HostScalars h;
-  if (verbose)
-    std::fprintf(stderr, "%5s %5s %22s %22s %9s %10s %10s %10s %5s\n", "nit", "nfev", "cost", "cost_new", "ratio",
-                 "lambda", "|step|", "|g|inf", "pcg");
-  while (true) {
-    if (nfev >= max_nfev && !new_lin) { status = 0; break; }
-    CB_TRY(build_system<P>(p, lam, new_lin, opt, st));
-    if (nfev >= max_nfev) {
-      // out of evaluations: only refresh cost / gradient norm for the report
-      CB_TRY(readback(p, &h, st));
-      cost = h.sc[cb::SC_COST];
-      gnorm = h.sc[cb::SC_GNORM_C];
-      for (int s = 0; s < p->red_slots; ++s) gnorm = std::max(gnorm, h.slots[s]);
-      if (res->initial_cost == 0.0 && njev == 1) res->initial_cost = cost;
-      status = (gnorm < gtol) ? 1 : 0;
-      break;
-    }
-    CB_TRY(solve_step<P>(p, lam, cur, opt, nullptr, st));
-    CB_TRY(trial_cost<P>(p, cur ^ 1, loss, fscale, opt, st));
-    CB_TRY(readback(p, &h, st));
-    if (rj_pending) {
-      CB_CUDA(cudaEventElapsedTime(&ms, p->ev2, p->ev3));
-      rj_ms_total += ms; ++rj_launches; rj_pending = false;
-    }
-    if (new_lin) {
-      cost = h.sc[cb::SC_COST];
-      gnorm = h.sc[cb::SC_GNORM_C];
-      for (int s = 0; s < p->red_slots; ++s) gnorm = std::max(gnorm, h.slots[s]);
-      if (njev == 1) {
-        res->initial_cost = cost;
-        if (!std::isfinite(cost)) {  // scipy: ValueError("Residuals are not finite in the initial point.")
-          g_last_error = "Residuals are not finite in the initial point.";
-          return CB_E_INVALID;
-        }
-      }
-      if (gnorm < gtol) { status = 1; break; }
-      ++nit;
-    }
-    ++nfev;
-    pcg_total += (long long)h.sc[cb::SC_PCG_ITS];
-    const double cost_new = h.red2[0];
-    const double pred = h.sc[cb::SC_PRED_C] + h.red2[1];
-    const double step2 = h.sc[cb::SC_STEP2_C] + h.red2[2];
-    const double x2 = h.sc[cb::SC_X2_C] + h.red2[3];
-    const bool pcg_bad = h.sc[cb::SC_PCG_FLAG] != 0.0;
-    const bool finite = std::isfinite(cost_new) && std::isfinite(pred) && !pcg_bad;
-    const double actual = finite ? cost - cost_new : -1.0;
-    const double ratio = (finite && pred > 0) ? actual / pred : -1.0;
-    const double step_norm = std::sqrt(step2), x_norm = std::sqrt(x2);
-    const bool ft = finite && actual < ftol * cost && ratio > 0.25;
-    const bool xt = finite && step_norm < xtol * (xtol + x_norm);
-    const int term = (ft && xt) ? 4 : ft ? 2 : xt ? 3 : 0;
-    if (verbose)
-      std::fprintf(stderr, "%5lld %5lld %22.15e %22.15e %+9.3f %10.2e %10.2e %10.2e %5d\n", nit, nfev, cost, cost_new,
-                   ratio, lam, step_norm, gnorm, (int)h.sc[cb::SC_PCG_ITS]);
-    if (finite && actual > 0) {
-      cur ^= 1;
-      const double t = 2.0 * ratio - 1.0;
-      lam = lam * std::max(1.0 / 3.0, 1.0 - t * t * t);
-      lam = std::max(lam, 1e-15);
-      nu = 2.0;
-      cost = cost_new;
-      new_lin = true;
-      if (term) {  // converged on this step: the Jacobian at the final point is not needed
-        status = term;
-        break;
-      }
-      CB_TRY(linearize<P>(p, p->d_xc[cur], p->d_xp4[cur], loss, fscale, st, true, nullptr));
-      rj_pending = true;
-      ++njev;
+  double pp_ms_total = 0.0;
+  long long pp_launches = 0, trials = 0;
+  double sy_ms_total = 0.0;
+  long long sy_launches = 0;
+  auto read_pp = [&](long long t) {
+    float ms = 0.f;
+    const TrialGraph& g = p->tg[t & 1];
+    cudaEvent_t a = use_graph ? g.ev_a : p->ev_pp[t & 1][0], b = use_graph ? g.ev_b : p->ev_pp[t & 1][1];
+    cudaEvent_t c = use_graph ? g.ev_c : p->ev_pp[t & 1][2], d = use_graph ? g.ev_d : p->ev_pp[t & 1][3];
+    if (cudaEventElapsedTime(&ms, a, b) == cudaSuccess) { pp_ms_total += ms; ++pp_launches; }
+    else cudaGetLastError();
+    if (cudaEventElapsedTime(&ms, c, d) == cudaSuccess) { sy_ms_total += ms; ++sy_launches; }
+    else cudaGetLastError();
+  };
+  bool done = false;
+  long long t = 0;
+  int rc = CB_OK;
+  while (!done) {
+    if (use_graph) {
+      cudaError_t e = cudaGraphLaunch(p->tg[t & 1].exec, st);
+      if (e != cudaSuccess) { g_last_error = std::string("cudaGraphLaunch: ") + cudaGetErrorString(e); rc = CB_E_CUDA; break; }
+      g_launches.fetch_add(p->tg[t & 1].n_kernels);
     } else {
-      lam = std::min(lam * nu, 1e12);
-      nu *= 2.0;
-      new_lin = false;
+      rc = enqueue_trial<P>(p, opt, st, p->ev_pp[t & 1]);
+      if (rc != CB_OK) break;
     }
-    if (term) { status = term; break; }
+    cudaMemcpyAsync(&p->h_state[t & 1], p->d_state, sizeof(cb::LmState), cudaMemcpyDeviceToHost, st);
+    cudaEventRecord(p->ev_state[t & 1], st);
+    ++trials;
+    if (t >= 1) {
+      // trial t is queued; now look at the outcome of trial t-1
+      cudaError_t e = cudaEventSynchronize(p->ev_state[(t - 1) & 1]);
+      if (e != cudaSuccess) { g_last_error = std::string("LM trial: ") + cudaGetErrorString(e); rc = CB_E_CUDA; break; }
+      read_pp(t - 1);
+      if (p->h_state[(t - 1) & 1].done) done = true;
+    }
+    ++t;
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (rc == CB_OK && e != cudaSuccess) { g_last_error = std::string("LM solve: ") + cudaGetErrorString(e); rc = CB_E_CUDA; }
+  if (rc != CB_OK) { if (p->peer) p->peer->poisoned = true; return rc; }
+  const cb::LmState fin = p->h_state[(t - 1) & 1];   // trial t-1 ran predicated-off or finished: final either way
+  if (p->peer) {
+    int peer_err = 0;
+    CB_CUDA(cudaMemcpy(&peer_err, p->peer->tab.err, sizeof(int), cudaMemcpyDeviceToHost));
+    p->peer->epoch_big = fin.epoch_big;
+    p->peer->epoch_small = fin.epoch_small;
+    if (peer_err) {
+      p->peer->poisoned = true;
+      g_last_error = "peer all-reduce timed out waiting for another rank";
+      return CB_E_CALLBACK;
+    }
+  }
+  if (fin.err == cb::LM_ERR_NONFINITE_X0) {  // scipy: ValueError("Residuals are not finite in the initial point.")
+    g_last_error = "Residuals are not finite in the initial point.";
+    return CB_E_INVALID;
+  }
+  if (verbose) {
+    const int nl = std::min(fin.n_log, p->log_cap);
+    std::vector<cb::LmLogRow> rows((size_t)std::max(nl, 1));
+    if (nl) CB_CUDA(cudaMemcpy(rows.data(), p->d_log, sizeof(cb::LmLogRow) * nl, cudaMemcpyDeviceToHost));
+    std::fprintf(stderr, "%5s %5s %22s %22s %9s %10s %10s %10s %5s\n", "nit", "nfev", "cost", "cost_new", "ratio", "lambda",
+                 "|step|", "|g|inf", "pcg");
+    for (int i = 0; i < nl; ++i)
+      std::fprintf(stderr, "%5lld %5lld %22.15e %22.15e %+9.3f %10.2e %10.2e %10.2e %5d\n", (long long)rows[i].nit,
+                   (long long)rows[i].nfev, rows[i].cost, rows[i].cost_new, rows[i].ratio, rows[i].lam, rows[i].step,
+                   rows[i].gnorm, (int)rows[i].pcg);
   }
   CB_CUDA(cudaEventRecord(p->ev1, st));
-  CB_TRY(download_x(p, cur, x_inout, st));
-  if (rj_pending) {
-    CB_CUDA(cudaEventElapsedTime(&ms, p->ev2, p->ev3));
-    rj_ms_total += ms; ++rj_launches;
-  }
+  CB_TRY(download_x(p, fin.cur, x_inout, st));
+  float ms = 0.f;
   CB_CUDA(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
-  res->status = status;
-  res->nfev = nfev;
-  res->njev = njev;
-  res->nit = nit;
-  res->cost = cost;
-  res->optimality = gnorm;
-  res->lambda_final = lam;
-  res->pcg_iterations = pcg_total;
+  res->status = fin.status;
+  res->nfev = fin.nfev;
+  res->njev = fin.njev;
+  res->nit = fin.nit;
+  res->cost = fin.cost;
+  res->initial_cost = fin.initial_cost;
+  res->optimality = fin.gnorm;
+  res->lambda_final = fin.lam;
+  res->pcg_iterations = fin.pcg_total;
   res->kernel_launches = g_launches.load() - launches0;
   res->solve_ms = ms;
-  res->rj_ms = rj_ms_total;
-  res->rj_launches = rj_launches;
+  res->rj_ms = pp_ms_total;
+  res->rj_launches = pp_launches;
+  res->syrk_ms = sy_ms_total;
+  res->syrk_launches = sy_launches;
+  res->trials_queued = trials;
+  res->used_graph = use_graph ? 1 : 0;
+  if (fin.err == cb::LM_ERR_STUCK_NONFINITE)
+    g_last_error = "every trial step is non-finite with the damping at its cap; stopped with status 0";
   if (opt->verbose >= 1 && opt->rank == 0)
     std::fprintf(stderr,
-                 "[caliscope_b200] status %d nfev %lld njev %lld nit %lld cost %.15e -> %.15e |g| %.2e  %.3f ms\n", status,
-                 nfev, njev, nit, res->initial_cost, cost, gnorm, ms);
+                 "[caliscope_b200] status %d nfev %lld njev %lld nit %lld cost %.15e -> %.15e |g| %.2e  %.3f ms (%lld trials queued, %s)\n",
+                 fin.status, (long long)fin.nfev, (long long)fin.njev, (long long)fin.nit, fin.initial_cost, fin.cost,
+                 fin.gnorm, ms, trials, use_graph ? "graph" : "direct");
   return CB_OK;
 }
 
@@ -992,13 +1099,18 @@ int cb_nccl_comm_destroy(void* comm) {
 int cb_ba_problem_destroy(CbBaProblem* p) {
   if (!p) return CB_OK;
   cudaSetDevice(p->device);
+  destroy_graphs(p);
+  for (auto& g : p->tg) {
+    for (cudaEvent_t e : {g.ev_a, g.ev_b, g.ev_c, g.ev_d})
+      if (e) cudaEventDestroy(e);
+  }
+  if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
   for (void* a : p->allocs) cached_free(a);
-  cached_free_host(p->h_sc);
+  cached_free_host(p->h_state);
   cached_free_host(p->h_x);
-  if (p->ev0) cudaEventDestroy(p->ev0);
-  if (p->ev1) cudaEventDestroy(p->ev1);
-  if (p->ev2) cudaEventDestroy(p->ev2);
-  if (p->ev3) cudaEventDestroy(p->ev3);
+  for (cudaEvent_t e : {p->ev0, p->ev1, p->ev2, p->ev3, p->ev_state[0], p->ev_state[1], p->ev_pp[0][0], p->ev_pp[0][1],
+                        p->ev_pp[0][2], p->ev_pp[0][3], p->ev_pp[1][0], p->ev_pp[1][1], p->ev_pp[1][2], p->ev_pp[1][3]})
+    if (e) cudaEventDestroy(e);
   delete p;
   return CB_OK;
 }
@@ -1039,7 +1151,18 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
   p->K_pad = cdiv(3ll * std::max(p->n_pts, 1), cb::SY_KC) * cb::SY_KC;
   p->k_chunks = p->K_pad / cb::SY_KC;
   p->n_split = std::max(1, std::min(p->k_chunks, p->num_sms / std::max(p->n_tiles, 1)));
-  p->pt_blocks = cdiv(std::max(p->n_pts, 1), cb::PT_WARPS);
+  // point kernels: 8 lanes per point when points have few observations (typical rigs: 2-6 cameras per point), a whole
+  // warp otherwise; persistent grid (2 CTAs per SM) so the camera table is staged into shared memory once per CTA
+  p->pt_lanes = ((double)p->n_obs / std::max(p->n_pts, 1) <= 10.0) ? 8 : 32;
+  if (const char* ev = std::getenv("CB_PT_LANES")) p->pt_lanes = std::atoi(ev) == 8 ? 8 : 32;
+  {
+    const int per_block = cb::PT_WARPS * (32 / p->pt_lanes);
+    p->pt_grid = std::max(1, std::min(cdiv(std::max(p->n_pts, 1), per_block), 2 * p->num_sms));
+    const size_t tab_bytes = sizeof(double) * cb::CT_SIZE * (size_t)p->n_cams;
+    p->cam_in_smem = tab_bytes <= 64 * 1024 ? 1 : 0;
+    p->pt_smem = p->cam_in_smem ? tab_bytes : 0;
+    p->bs_smem = sizeof(double) * (((size_t)p->nP + 3) & ~(size_t)3) + (p->cam_in_smem ? tab_bytes : 0);
+  }
 
   const int n = p->n_obs;
   // tables
@@ -1049,12 +1172,11 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
   CB_CUDA(cudaMemcpyAsync(p->d_cam_off, p->h_cam_off.data(), sizeof(int) * (p->n_cams + 1), cudaMemcpyHostToDevice, st));
   CB_CUDA(cudaMemcpyAsync(p->d_cam_flags, d->cam_flags, sizeof(int) * p->n_cams, cudaMemcpyHostToDevice, st));
   CB_CUDA(cudaMemcpyAsync(p->d_cam_const, d->cam_const, sizeof(double) * 9 * p->n_cams, cudaMemcpyHostToDevice, st));
-  CB_TRY(palloc(p, &p->d_cm_xy, n)); CB_TRY(palloc(p, &p->d_cm_pt, n)); CB_TRY(palloc(p, &p->d_cm_row, n));
+  CB_TRY(palloc(p, &p->d_cm_xy, n)); CB_TRY(palloc(p, &p->d_cm_pt, n)); CB_TRY(palloc(p, &p->d_pm_xy, n));
   CB_TRY(palloc(p, &p->d_cm_orig, n)); CB_TRY(palloc(p, &p->d_cam_start, p->n_cams + 1));
   CB_TRY(palloc(p, &p->d_cam_chunk_start, p->n_cams + 1));
   CB_TRY(palloc(p, &p->d_pt_start, p->n_pts + 1)); CB_TRY(palloc(p, &p->d_pm_orig, n));
   CB_TRY(palloc(p, &p->d_pm_cam, n));
-  CB_TRY(palloc(p, &p->d_pm_row, n));
   CB_TRY(palloc(p, &p->d_pm_pt, n));
   // observation list: host -> device if needed
   const int *d_cam = d->obs_cam, *d_pt = d->obs_pt;
@@ -1155,15 +1277,17 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
   CB_TRY(palloc(p, &p->d_lo, p->nP)); CB_TRY(palloc(p, &p->d_hi, p->nP));
 
   // work buffers
-  const int ROWD = (p->P == 6) ? 20 : 28, NACC = (p->P == 6) ? 28 : 55, NU = (p->P == 6) ? 21 : 45;
+  const int NACC = (p->P == 6) ? 28 : 55, NU = (p->P == 6) ? 21 : 45;
   const size_t npts = (size_t)std::max(p->n_pts, 1);
   CB_TRY(palloc(p, &p->d_x, (size_t)p->n_params + 1));
-  for (int k = 0; k < 2; ++k) { CB_TRY(palloc(p, &p->d_xc[k], p->nP)); CB_TRY(palloc(p, &p->d_xp4[k], 4 * npts)); }
-  CB_TRY(palloc(p, &p->d_camtab, (size_t)p->n_cams * cb::CT_SIZE));
-  CB_TRY(palloc(p, &p->d_jrows, (size_t)std::max(n, 1) * ROWD));
+  for (int k = 0; k < 2; ++k) {
+    CB_TRY(palloc(p, &p->d_xc[k], p->nP)); CB_TRY(palloc(p, &p->d_xp4[k], 4 * npts));
+    CB_TRY(palloc(p, &p->d_camtab[k], (size_t)p->n_cams * cb::CT_SIZE));
+    CB_TRY(palloc(p, &p->d_Upk[k], (size_t)p->n_cams * NU)); CB_TRY(palloc(p, &p->d_gc[k], p->nP));
+    CB_TRY(palloc(p, &p->d_costsum[k], 4));
+  }
   CB_TRY(palloc(p, &p->d_partial, (size_t)std::max(p->n_chunks, 1) * NACC));
-  CB_TRY(palloc(p, &p->d_Upk, (size_t)p->n_cams * NU)); CB_TRY(palloc(p, &p->d_gc, p->nP));
-  CB_TRY(palloc(p, &p->d_camcost, p->n_cams)); CB_TRY(palloc(p, &p->d_costsum, 4));
+  CB_TRY(palloc(p, &p->d_camcost, p->n_cams));
   CB_TRY(palloc(p, &p->d_gpt, 3 * npts));
   CB_TRY(palloc(p, &p->d_V6, 6 * npts)); CB_TRY(palloc(p, &p->d_gp, 3 * npts)); CB_TRY(palloc(p, &p->d_Dp2, 3 * npts));
   CB_TRY(palloc(p, &p->d_Dc2, p->nP)); CB_TRY(palloc(p, &p->d_Linv6, 6 * npts));
@@ -1174,21 +1298,42 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
   CB_TRY(palloc(p, &p->d_red, p->red_len()));
   CB_TRY(palloc(p, &p->d_Minv, (size_t)p->n_cams * p->P * p->P));
   CB_TRY(palloc(p, &p->d_dc, p->nP)); CB_TRY(palloc(p, &p->d_dp, 3 * npts));
-  CB_TRY(palloc(p, &p->d_bpart, 3 * (size_t)p->pt_blocks));
+  CB_TRY(palloc(p, &p->d_bpart, 3 * (size_t)p->pt_grid));
   CB_TRY(palloc(p, &p->d_sc, cb::SC_COUNT)); CB_TRY(palloc(p, &p->d_red2, 8));
   CB_TRY(palloc(p, &p->d_gmax, 2));
+  CB_TRY(palloc(p, &p->d_counter, 4));
+  CB_TRY(palloc(p, &p->d_state, 1));
+  CB_TRY(palloc(p, &p->d_log, (size_t)p->log_cap));
   CB_TRY(palloc(p, &p->d_out2, 2 * (size_t)std::max(n, 1)));
   CB_CUDA(cudaMemsetAsync(p->d_Zt, 0, sizeof(double) * (size_t)p->K_pad * p->LD, st));
   CB_CUDA(cudaMemsetAsync(p->d_tvec, 0, sizeof(double) * p->K_pad, st));
   CB_CUDA(cudaMemsetAsync(p->d_tpart, 0, sizeof(double) * (size_t)p->n_slots * cb::SY_TILE, st));
   CB_CUDA(cudaMemsetAsync(p->d_part, 0, sizeof(double) * (size_t)p->n_slots * cb::SY_TILE * cb::SY_TILE, st));
   CB_CUDA(cudaMemsetAsync(p->d_red2, 0, sizeof(double) * 8, st));
-  CB_TRY(cached_malloc_host((void**)&p->h_sc, sizeof(double) * (cb::SC_COUNT + 4 + p->red_slots)));
+  CB_CUDA(cudaMemsetAsync(p->d_Linv6, 0, sizeof(double) * 6 * npts, st));
+  CB_TRY(cached_malloc_host((void**)&p->h_state, sizeof(cb::LmState) * 4));
   CB_TRY(cached_malloc_host((void**)&p->h_x, sizeof(double) * ((size_t)p->n_params + 1)));
-  CB_CUDA(cudaEventCreate(&p->ev0)); CB_CUDA(cudaEventCreate(&p->ev1));
-  CB_CUDA(cudaEventCreate(&p->ev2)); CB_CUDA(cudaEventCreate(&p->ev3));
+  for (cudaEvent_t* e : {&p->ev0, &p->ev1, &p->ev2, &p->ev3, &p->ev_pp[0][0], &p->ev_pp[0][1], &p->ev_pp[0][2], &p->ev_pp[0][3],
+                         &p->ev_pp[1][0], &p->ev_pp[1][1], &p->ev_pp[1][2], &p->ev_pp[1][3]})
+    CB_CUDA(cudaEventCreate(e));
+  for (cudaEvent_t* e : {&p->ev_state[0], &p->ev_state[1]}) CB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   CB_CUDA(cudaFuncSetAttribute(cb::schur_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)sizeof(cb::SyrkSmem)));
+  if (p->pt_smem > 48 * 1024 || p->bs_smem > 48 * 1024) {
+    const int a = (int)p->pt_smem, b2 = (int)p->bs_smem;
+#define CB_SMEM_ATTR(PP)                                                                                           \
+    do {                                                                                                             \
+      cudaFuncSetAttribute(cb::pt_pass_kernel<PP, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);       \
+      cudaFuncSetAttribute(cb::pt_pass_kernel<PP, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);        \
+      cudaFuncSetAttribute(cb::pt_pass_kernel<PP, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);      \
+      cudaFuncSetAttribute(cb::pt_pass_kernel<PP, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);       \
+      cudaFuncSetAttribute(cb::pt_backsub_kernel<PP, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, b2);          \
+      cudaFuncSetAttribute(cb::pt_backsub_kernel<PP, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, b2);         \
+    } while (0)
+    if (p->P == 6) CB_SMEM_ATTR(6); else CB_SMEM_ATTR(9);
+#undef CB_SMEM_ATTR
+    CB_CUDA(cudaGetLastError());
+  }
   CB_TRY(choose_pcg_config(p));
   CB_CUDA(cudaStreamSynchronize(st));
   return CB_OK;
@@ -1234,6 +1379,10 @@ int cb_ba_solve(CbBaProblem* p, const CbBaOptions* opt, double* x_inout, CbBaRes
       return CB_E_INVALID;
     }
     if (opt->rank != g->rank || opt->world_size != g->world) { g_last_error = "rank / world_size differ from the peer group's"; return CB_E_INVALID; }
+    if (g->poisoned) {
+      g_last_error = "peer group is unusable after a failed solve (the ranks' sequence numbers may differ): re-create it";
+      return CB_E_INVALID;
+    }
     p->peer = g;
   }
   const int rc = p->P == 6 ? lm_solve<6>(p, opt, x_inout, result, st) : lm_solve<9>(p, opt, x_inout, result, st);
@@ -1246,8 +1395,8 @@ namespace {
 template <int P, int MODE>
 int eval_mode(CbBaProblem* p, const double* x, cudaStream_t st) {
   CB_TRY(upload_x(p, x, st));
-  CB_TRY(run_cam_prep<P>(p, p->d_xc[0], st));
-  launch_resjac<P, MODE>(p, p->d_xp4[0], 0, 1.0, p->d_out2, st);
+  CB_TRY(run_cam_prep<P>(p, p->d_xc[0], p->d_camtab[0], st));
+  launch_resjac<P, MODE>(p, nullptr, 0, 0, 1.0, p->d_out2, st);
   return CB_OK;
 }
 }  // namespace
@@ -1283,13 +1432,13 @@ int cb_ba_jacobian_blocks(CbBaProblem* p, const double* x, double* Jc, double* J
   CB_TRY(dalloc(&dJc, 18 * (size_t)std::max(n, 1)));
   CB_TRY(dalloc(&dJp, 6 * (size_t)std::max(n, 1)));
   if (p->P == 6) {
-    CB_TRY(run_cam_prep<6>(p, p->d_xc[0], st));
-    launch_resjac<6, 0>(p, p->d_xp4[0], 0, 1.0, nullptr, st);
-    if (n) CB_LAUNCH((cb::rows_to_blocks_kernel<6>), cdiv(n, 256), 256, 0, st, p->d_jrows, p->d_pm_row, p->d_pm_orig, n, dJc, dJp);
+    CB_TRY(run_cam_prep<6>(p, p->d_xc[0], p->d_camtab[0], st));
+    if (n) CB_LAUNCH((cb::jac_blocks_kernel<6>), cdiv(n, 128), 128, 0, st, p->d_obs_cam, p->d_obs_pt,
+                     reinterpret_cast<const double2*>(p->d_obs_xy), n, (const double*)p->d_camtab[0], (const double*)p->d_xp4[0], dJc, dJp);
   } else {
-    CB_TRY(run_cam_prep<9>(p, p->d_xc[0], st));
-    launch_resjac<9, 0>(p, p->d_xp4[0], 0, 1.0, nullptr, st);
-    if (n) CB_LAUNCH((cb::rows_to_blocks_kernel<9>), cdiv(n, 256), 256, 0, st, p->d_jrows, p->d_pm_row, p->d_pm_orig, n, dJc, dJp);
+    CB_TRY(run_cam_prep<9>(p, p->d_xc[0], p->d_camtab[0], st));
+    if (n) CB_LAUNCH((cb::jac_blocks_kernel<9>), cdiv(n, 128), 128, 0, st, p->d_obs_cam, p->d_obs_pt,
+                     reinterpret_cast<const double2*>(p->d_obs_xy), n, (const double*)p->d_camtab[0], (const double*)p->d_xp4[0], dJc, dJp);
   }
   cudaError_t e1 = cudaMemcpyAsync(Jc, dJc, sizeof(double) * 18 * (size_t)n, cudaMemcpyDeviceToHost, st);
   cudaError_t e2 = cudaMemcpyAsync(Jp, dJp, sizeof(double) * 6 * (size_t)n, cudaMemcpyDeviceToHost, st);
@@ -1308,20 +1457,22 @@ int normal_eq_impl(CbBaProblem* p, const double* x, double lam, int loss, double
   using RT = cb::RowT<P>;
   CbBaOptions opt;
   cb_ba_default_options(&opt);
+  opt.loss = loss; opt.f_scale = fs;
+  opt.ftol = opt.xtol = opt.gtol = 0.0;
   CB_TRY(set_bounds(p, false, st));
-  CB_CUDA(cudaMemsetAsync(p->d_Dc2, 0, sizeof(double) * p->nP, st));
-  CB_CUDA(cudaMemsetAsync(p->d_Dp2, 0, sizeof(double) * 3 * (size_t)std::max(p->n_pts, 1), st));
+  CB_TRY(init_state(p, &opt, lam, 1ll << 40, st));
   CB_TRY(upload_x(p, x, st));
-  CB_TRY(linearize<P>(p, p->d_xc[0], p->d_xp4[0], loss, fs, st, false, nullptr));
-  CB_TRY(build_system<P>(p, lam, true, &opt, st));
+  CB_TRY(run_cam_prep<P>(p, p->d_xc[0], p->d_camtab[0], st));
+  CB_TRY(camera_pass<P>(p, 0, 0, st));
+  CB_TRY(build_system<P>(p, &opt, st, nullptr, nullptr));
   const size_t nn = (size_t)p->nP * p->nP;
   std::vector<double> hS(nn + 3 * (size_t)p->nP + 1);
   CB_CUDA(cudaMemcpyAsync(hS.data(), p->d_red, sizeof(double) * hS.size(), cudaMemcpyDeviceToHost, st));
-  CB_TRY(solve_step<P>(p, lam, 0, &opt, p->d_dp, st));
+  CB_TRY(solve_step<P>(p, p->d_dp, st));
   std::vector<double> hU((size_t)p->n_cams * RT::NU), hV(6 * (size_t)std::max(p->n_pts, 1));
-  CB_CUDA(cudaMemcpyAsync(hU.data(), p->d_Upk, sizeof(double) * hU.size(), cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaMemcpyAsync(hU.data(), p->d_Upk[0], sizeof(double) * hU.size(), cudaMemcpyDeviceToHost, st));
   CB_CUDA(cudaMemcpyAsync(hV.data(), p->d_V6, sizeof(double) * hV.size(), cudaMemcpyDeviceToHost, st));
-  if (gc) CB_CUDA(cudaMemcpyAsync(gc, p->d_gc, sizeof(double) * p->nP, cudaMemcpyDeviceToHost, st));
+  if (gc) CB_CUDA(cudaMemcpyAsync(gc, p->d_gc[0], sizeof(double) * p->nP, cudaMemcpyDeviceToHost, st));
   if (gp) CB_CUDA(cudaMemcpyAsync(gp, p->d_gp, sizeof(double) * 3 * (size_t)p->n_pts, cudaMemcpyDeviceToHost, st));
   if (dc) CB_CUDA(cudaMemcpyAsync(dc, p->d_dc, sizeof(double) * p->nP, cudaMemcpyDeviceToHost, st));
   if (dp) CB_CUDA(cudaMemcpyAsync(dp, p->d_dp, sizeof(double) * 3 * (size_t)p->n_pts, cudaMemcpyDeviceToHost, st));
@@ -1365,9 +1516,9 @@ int cb_ba_debug_pcg_time(CbBaProblem* p, int max_iter, int reps, double* ms_per_
   if (!p || !ms_per_launch || reps <= 0) { g_last_error = "cb_ba_debug_pcg_time: bad argument"; return CB_E_INVALID; }
   CB_CUDA(cudaSetDevice(p->device));
   cudaStream_t st = (cudaStream_t)stream;
-  CB_TRY(launch_pcg(p, 0.0, max_iter, st));
+  CB_TRY(launch_pcg(p, nullptr, 0.0, max_iter, st));
   CB_CUDA(cudaEventRecord(p->ev2, st));
-  for (int r = 0; r < reps; ++r) CB_TRY(launch_pcg(p, 0.0, max_iter, st));
+  for (int r = 0; r < reps; ++r) CB_TRY(launch_pcg(p, nullptr, 0.0, max_iter, st));
   CB_CUDA(cudaEventRecord(p->ev3, st));
   CB_CUDA(cudaEventSynchronize(p->ev3));
   float ms = 0.f;
@@ -1378,6 +1529,76 @@ int cb_ba_debug_pcg_time(CbBaProblem* p, int max_iter, int reps, double* ms_per_
   std::fprintf(stderr, "[pcg profile] cycles/iteration on CTA 0 thread 0: A(update+precond) %.0f block-barrier %.0f B(matvec) %.0f cluster-barrier %.0f C(dots) %.0f\n",
                t[cb::SC_PCG_T0] / max_iter, t[cb::SC_PCG_T0 + 1] / max_iter, t[cb::SC_PCG_T0 + 2] / max_iter,
                t[cb::SC_PCG_T0 + 3] / max_iter, t[cb::SC_PCG_T0 + 4] / max_iter);
+  return CB_OK;
+}
+
+}  // extern "C"
+namespace {
+template <int NT>
+__global__ void fp64_dmma_peak_kernel(double* out, int iters, double a0, double b0) {
+  double c[NT][2];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) { c[i][0] = threadIdx.x; c[i][1] = i; }
+  double a = a0 + threadIdx.x * 1e-9, b = b0;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < NT; ++i) cb::dmma884(c[i][0], c[i][1], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < NT; ++i) s += c[i][0] + c[i][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+template <int NACC>
+__global__ void fp64_dfma_peak_kernel(double* out, int iters, double a, double b) {
+  double acc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) acc[i] = threadIdx.x * 1e-3 + i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = fma(acc[i], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) s += acc[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace
+extern "C" {
+
+int cb_debug_fp64_peak(int device, double* dmma_tflops, double* dfma_tflops) {
+  if (!dmma_tflops || !dfma_tflops) { g_last_error = "cb_debug_fp64_peak: null argument"; return CB_E_INVALID; }
+  CB_TRY(select_device(device));
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int warps = 8, threads = warps * 32, iters = 20000;
+  double* out = nullptr;
+  CB_TRY(dalloc(&out, (size_t)sms * threads));
+  ScopedFree sf; sf.dev.push_back(out);
+  cudaEvent_t e0, e1;
+  CB_CUDA(cudaEventCreate(&e0)); CB_CUDA(cudaEventCreate(&e1));
+  float ms = 0.f;
+  double best_mma = 0.0, best_fma = 0.0;
+  for (int rep = 0; rep < 3; ++rep) {
+    fp64_dmma_peak_kernel<16><<<sms, threads>>>(out, rep == 0 ? 200 : iters, 1.0000001, 1e-9);
+    if (rep == 0) { cudaDeviceSynchronize(); continue; }
+    cudaEventRecord(e0);
+    fp64_dmma_peak_kernel<16><<<sms, threads>>>(out, iters, 1.0000001, 1e-9);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms, e0, e1);
+    best_mma = std::max(best_mma, 2.0 * 256 * 16 * iters * (double)warps * sms / ms * 1e-9);
+    cudaEventRecord(e0);
+    fp64_dfma_peak_kernel<16><<<sms, threads>>>(out, iters, 1.0000001, 1e-9);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms, e0, e1);
+    best_fma = std::max(best_fma, 2.0 * 16 * iters * (double)threads * sms / ms * 1e-9);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  CB_CUDA(cudaGetLastError());
+  *dmma_tflops = best_mma;
+  *dfma_tflops = best_fma;
   return CB_OK;
 }
 
@@ -1501,7 +1722,7 @@ int cb_ba_problem_set_constraints(CbBaProblem* p, int64_t n_c, const int32_t* gr
   CB_TRY(palloc(p, &d_coef, (size_t)nc * 8)); CB_TRY(palloc(p, &d_dist, nc)); CB_TRY(palloc(p, &d_w, nc));
   CB_TRY(palloc(p, &d_cps, ncomp + 1)); CB_TRY(palloc(p, &d_cpts, cpts.size())); CB_TRY(palloc(p, &d_ccs, ncomp + 1));
   CB_TRY(palloc(p, &d_ccons, nc)); CB_TRY(palloc(p, &d_loff, ncomp)); CB_TRY(palloc(p, &p->d_pt_comp, npts));
-  CB_TRY(palloc(p, &p->d_c_rs, nc)); CB_TRY(palloc(p, &p->d_c_dirw, 3 * (size_t)nc));
+  for (int k = 0; k < 2; ++k) { CB_TRY(palloc(p, &p->d_c_rs[k], nc)); CB_TRY(palloc(p, &p->d_c_dirw[k], 3 * (size_t)nc)); }
   CB_TRY(palloc(p, &p->d_compL, (size_t)ltot));
 #define CB_UP(dst, vec) CB_CUDA(cudaMemcpyAsync(dst, (vec).data(), sizeof((vec)[0]) * (vec).size(), cudaMemcpyHostToDevice, st))
   CB_UP(d_nu, cnu); CB_UP(d_g, cg); CB_UP(d_l, cl); CB_UP(d_coef, ccoef); CB_UP(d_cps, cps); CB_UP(d_cpts, cpts);
@@ -1514,7 +1735,8 @@ int cb_ba_problem_set_constraints(CbBaProblem* p, int64_t n_c, const int32_t* gr
   const int NACC = (p->P == 6) ? 28 : 55;
   CB_TRY(palloc(p, &p->d_camcost, (size_t)p->n_cams + p->n_cblk));
   CB_TRY(palloc(p, &p->d_partial, (size_t)std::max(p->n_chunks, 1) * NACC + p->n_cblk));
-  CB_TRY(palloc(p, &p->d_bpart, 3 * ((size_t)p->pt_blocks + ncomp)));
+  CB_TRY(palloc(p, &p->d_bpart, 3 * ((size_t)p->pt_grid + ncomp)));
+  destroy_graphs(p);  // captured launches hold the old buffer addresses
   CB_CUDA(cudaStreamSynchronize(st));
   p->ct.n_c = nc; p->ct.n_comp = ncomp; p->ct.n_dim_max = ndmax;
   p->ct.c_nu = d_nu; p->ct.c_gidx = d_g; p->ct.c_lidx = d_l; p->ct.c_coef = d_coef; p->ct.c_dist = d_dist; p->ct.c_w = d_w;
@@ -1546,8 +1768,8 @@ int cb_ba_constraint_rows(CbBaProblem* p, const double* x, double* r_out, double
   CB_TRY(upload_x(p, x, st));
   double *d_r, *d_rs, *d_dir;
   CB_TRY(dalloc(&d_r, p->n_c)); CB_TRY(dalloc(&d_rs, p->n_c)); CB_TRY(dalloc(&d_dir, 3 * (size_t)p->n_c));
-  CB_LAUNCH((cb::constraint_eval_kernel<false>), p->n_cblk, cb::CC_THREADS, 0, st, p->ct, p->d_xp4[0], 0, 1.0, d_rs, d_dir,
-            d_r, (double*)nullptr);
+  CB_LAUNCH((cb::constraint_eval_kernel<false>), p->n_cblk, cb::CC_THREADS, 0, st, (const cb::LmState*)nullptr, 0, p->ct,
+            p->c_xp(), 0, 1.0, (cb::Ptr2{{d_rs, d_rs}}), (cb::Ptr2{{d_dir, d_dir}}), d_r, (double*)nullptr);
   cudaMemcpyAsync(r_out, d_r, sizeof(double) * p->n_c, cudaMemcpyDeviceToHost, st);
   if (dir_out) cudaMemcpyAsync(dir_out, d_dir, sizeof(double) * 3 * (size_t)p->n_c, cudaMemcpyDeviceToHost, st);
   cudaError_t e = cudaStreamSynchronize(st);
@@ -1600,8 +1822,14 @@ int cb_ba_cull(CbBaProblem* p, const double* x, const double* thresholds, int32_
   long long* d_kept;
   unsigned char* d_flag;
   int *d_iota, *d_sel, *d_nsel;
-  CB_TRY(dalloc(&d_thr, nc)); CB_TRY(dalloc(&d_ss, nc)); CB_TRY(dalloc(&d_kept, nc)); CB_TRY(dalloc(&d_flag, n));
-  CB_TRY(dalloc(&d_iota, n)); CB_TRY(dalloc(&d_sel, n)); CB_TRY(dalloc(&d_nsel, 1));
+  ScopedFree sf;  // every early return below releases the temporaries
+  CB_TRY(dalloc(&d_thr, nc)); sf.dev.push_back(d_thr);
+  CB_TRY(dalloc(&d_ss, nc)); sf.dev.push_back(d_ss);
+  CB_TRY(dalloc(&d_kept, nc)); sf.dev.push_back(d_kept);
+  CB_TRY(dalloc(&d_flag, n)); sf.dev.push_back(d_flag);
+  CB_TRY(dalloc(&d_iota, n)); sf.dev.push_back(d_iota);
+  CB_TRY(dalloc(&d_sel, n)); sf.dev.push_back(d_sel);
+  CB_TRY(dalloc(&d_nsel, 1)); sf.dev.push_back(d_nsel);
   std::vector<double> thr(thresholds, thresholds + nc);
   std::vector<long long> kept(nc);
   std::vector<int> cs(nc + 1);
@@ -1635,6 +1863,7 @@ int cb_ba_cull(CbBaProblem* p, const double* x, const double* thresholds, int32_
   cub::DeviceSelect::Flagged(nullptr, tb, d_iota, d_flag, d_sel, d_nsel, n, st);
   void* d_tmp;
   CB_TRY(cached_malloc(&d_tmp, std::max<size_t>(tb, 16)));
+  sf.dev.push_back(d_tmp);
   CB_CUDA(cub::DeviceSelect::Flagged(d_tmp, tb, d_iota, d_flag, d_sel, d_nsel, n, st));
   g_launches.fetch_add(2);
   int nsel = 0;
@@ -1646,9 +1875,12 @@ int cb_ba_cull(CbBaProblem* p, const double* x, const double* thresholds, int32_
     g_last_error = "No image observations provided";  // every observation was culled
     rc = CB_E_INVALID;
   } else {
-    int *c_cam, *c_pt;
-    double* c_xy;
-    CB_TRY(dalloc(&c_cam, nsel)); CB_TRY(dalloc(&c_pt, nsel)); CB_TRY(dalloc(&c_xy, 2 * (size_t)nsel));
+    int *c_cam = nullptr, *c_pt = nullptr;
+    double* c_xy = nullptr;
+    if (dalloc(&c_cam, nsel) != CB_OK || dalloc(&c_pt, nsel) != CB_OK || dalloc(&c_xy, 2 * (size_t)nsel) != CB_OK) {
+      cached_free(c_cam); cached_free(c_pt); cached_free(c_xy);
+      return CB_E_NOMEM;
+    }
     CB_LAUNCH(cb::gather_obs_kernel, cdiv(nsel, 256), 256, 0, st, d_sel, nsel, p->d_obs_cam, p->d_obs_pt,
               reinterpret_cast<const double2*>(p->d_obs_xy), c_cam, c_pt, reinterpret_cast<double2*>(c_xy));
     CbBaProblemDesc d2;
@@ -1676,8 +1908,6 @@ int cb_ba_cull(CbBaProblem* p, const double* x, const double* thresholds, int32_
     }
   }
   if (n_kept) *n_kept = nsel;
-  cached_free(d_tmp); cached_free(d_thr); cached_free(d_ss); cached_free(d_kept); cached_free(d_flag);
-  cached_free(d_iota); cached_free(d_sel); cached_free(d_nsel);
   return rc;
 }
 
@@ -1688,25 +1918,7 @@ int cb_ba_cull(CbBaProblem* p, const double* x, const double* thresholds, int32_
 // ------------------------------------------------------------------------------------------
 namespace {
 
-struct ScopedFree {
-  std::vector<void*> dev, host;
-  ~ScopedFree() {
-    for (void* q : dev) cached_free(q);
-    for (void* q : host) cached_free_host(q);
-  }
-};
 
-int select_device(int device) {
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-    cudaGetLastError();
-    g_last_error = "no CUDA device";
-    return CB_E_NO_DEVICE;
-  }
-  if (device < 0 || device >= ndev) { g_last_error = "device index out of range"; return CB_E_INVALID; }
-  CB_CUDA(cudaSetDevice(device));
-  return CB_OK;
-}
 
 int build_undist_table(int32_t n_cams, const int32_t* cam_fisheye, const double* cam_k, const double* cam_dist,
                        std::vector<cb::UndistCam>& tab) {

@@ -3,19 +3,16 @@
 // Per LM linearisation (reference analogues in brackets, paths relative to /root/reference):
 //   cam_prep_kernel     Rodrigues + SO(3) right Jacobian + intrinsics per camera
 //                       [bundle_parameterization.py:166-186 trial_projection_inputs]
-//   resjac_kernel       residual + analytic 2x(P+3) Jacobian row per observation, camera-major,
-//                       fused per-camera U = Jc^T Jc, g = Jc^T r and cost accumulation
+//   resjac_kernel       camera-major pass: residual + analytic 2x(P+3) Jacobian block per observation kept in
+//                       registers, fused per-camera U = Jc^T Jc, g = Jc^T r and cost accumulation
 //                       [src/caliscope/core/reprojection.py:75-119 and :128-234]
-//   cam_reduce_kernel   chunk partials -> U_c, g_c, cost_c
-//   pt_reduce_kernel    per point V = Jp^T Jp, g = Jp^T r from the point-major Jacobian rows
-//   pt_zbuild_kernel    3x3 damped Cholesky per point, Z = (Jc^T Jp) L^-T scattered to the k-major Zt
+//   pt_pass_kernel      (cb_lm.cuh) point-major pass: V, g, 3x3 damped Cholesky, Z = (Jc^T Jp) L^-T -> k-major Zt
 //   schur_syrk_kernel   Z Z^T (+ Z t) with bulk-async (TMA) staged shared-memory tiles, split-K
 //   schur_finalize_kernel  S = U - Z Z^T, b = g_c - Z t into the all-reduce buffer
-//   post_reduce_kernel  Marquardt scaling (running max of diag U, scipy x_scale='jac' analogue,
-//                       site-packages/scipy/optimize/_lsq/common.py:598-610) and damping
-//   block_inverse_kernel / pcg_cluster_kernel   block-Jacobi PCG on the dense reduced system
-//   cam_update_kernel / pt_backsub_kernel       step, bounds clamp, predicted reduction
-//   cost_kernel         trial-point cost only                      [reprojection.py:75-119]
+//   reduced_prep_kernel (cb_lm.cuh) Marquardt scaling (running max of diag U, scipy x_scale='jac' analogue,
+//                       site-packages/scipy/optimize/_lsq/common.py:598-610), damping, block-Jacobi inverses
+//   pcg_cluster_kernel  block-Jacobi PCG on the dense reduced system
+//   cam_step_kernel / pt_backsub_kernel (cb_lm.cuh)   step, bounds clamp, predicted reduction
 #pragma once
 #include <cooperative_groups.h>
 
@@ -27,7 +24,6 @@ namespace cg = cooperative_groups;
 constexpr int RJ_THREADS = 128;   // resjac / cost block size
 constexpr int RJ_CHUNK = 2048;    // observations per block (all of one camera)
 constexpr int PT_WARPS = 8;       // warps (points) per block in the point-centric kernels
-constexpr int PT_BLOCK = 16;      // points per block of the Jacobian row layout (block, camera, point)
 constexpr int SY_TILE = 96;       // Schur tile edge
 constexpr int SY_KC = 32;         // k rows per pipeline stage
 constexpr int SY_STAGES = 4;
@@ -39,7 +35,6 @@ template <int P>
 struct RowT {
   static constexpr int NU = P * (P + 1) / 2;
   static constexpr int NACC = NU + P + 1;                 // U packed, g, cost
-  static constexpr int ROWD = (P == 6) ? 20 : 28;         // doubles per Jacobian row (32 B multiple)
 };
 
 // scalar slots (device double array `sc`)
@@ -86,25 +81,39 @@ __global__ void pack_x_kernel(double* __restrict__ x, const int* __restrict__ ca
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void cam_prep_kernel(const double* __restrict__ xc, const int* __restrict__ cam_flags,
-                                const double* __restrict__ cam_const, int n_cams, int P,
-                                double* __restrict__ camtab) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_cams) return;
-  const double* q = xc + (size_t)c * P;
-  const double* k = cam_const + (size_t)c * 9;
-  double* o = camtab + (size_t)c * CT_SIZE;
-  int flags = cam_flags[c];
-  bool free_i = (flags & 1) != 0, fish = (flags & 2) != 0;
-  double r0 = q[0], r1 = q[1], r2 = q[2];
-  double th2 = r0 * r0 + r1 * r1 + r2 * r2, th = sqrt(th2);
+// Levenberg-Marquardt state, resident in device memory for the whole solve (cb_lm.cuh holds the kernels that
+// advance it).  Every per-trial kernel returns at once when `done` is set, picks its input buffers by `cur`
+// and reads the damping from `lam`, so a trial is the same launch sequence every time (one CUDA graph).
+// ---------------------------------------------------------------------------------------------
+struct LmState {
+  double lam, nu, cost, gnorm, initial_cost;
+  double ftol, xtol, gtol;
+  long long nfev, njev, nit, max_nfev, pcg_total;
+  unsigned long long epoch_big, epoch_small;
+  double fscale, pcg_tol2;  // robust-loss scale, squared PCG tolerance (read by the kernels, not baked into the launches)
+  int cur, done, status, new_lin, err, bad_streak, n_log, log_cap;
+  int loss, pcg_max_iter;
+};
+struct Ptr2 {
+  double* p[2];
+};
+struct CPtr2 {
+  const double* p[2];
+};
+
+// camera table entry: Rodrigues, SO(3) right Jacobian, intrinsics  [bundle_parameterization.py:166-186]
+__device__ __forceinline__ void cam_prep_one(const double* __restrict__ q, const double* __restrict__ k, int flags,
+                                             double* __restrict__ o) {
+  const bool free_i = (flags & 1) != 0;
+  const double r0 = q[0], r1 = q[1], r2 = q[2];
+  const double th2 = r0 * r0 + r1 * r1 + r2 * r2, th = sqrt(th2);
   double R[9];
+  double s = 0.0, co = 1.0;
+  if (th >= 1e-12) sincos(th, &s, &co);
   if (th < 1e-12) {
     R[0] = 1; R[1] = -r2; R[2] = r1; R[3] = r2; R[4] = 1; R[5] = -r0; R[6] = -r1; R[7] = r0; R[8] = 1;
   } else {
-    double s, co;
-    sincos(th, &s, &co);
-    double it = 1.0 / th, kx = r0 * it, ky = r1 * it, kz = r2 * it, c1 = 1.0 - co;
+    const double it = 1.0 / th, kx = r0 * it, ky = r1 * it, kz = r2 * it, c1 = 1.0 - co;
     R[0] = co + c1 * kx * kx;      R[1] = c1 * kx * ky - s * kz; R[2] = c1 * kx * kz + s * ky;
     R[3] = c1 * ky * kx + s * kz;  R[4] = co + c1 * ky * ky;     R[5] = c1 * ky * kz - s * kx;
     R[6] = c1 * kz * kx - s * ky;  R[7] = c1 * kz * ky + s * kx; R[8] = co + c1 * kz * kz;
@@ -114,26 +123,23 @@ __global__ void cam_prep_kernel(const double* __restrict__ xc, const int* __rest
     B = 0.5 - th2 / 24.0 + th2 * th2 / 720.0;
     C = 1.0 / 6.0 - th2 / 120.0 + th2 * th2 / 5040.0;
   } else {
-    double s, co;
-    sincos(th, &s, &co);
     B = (1.0 - co) / th2;
     C = (th - s) / (th2 * th);
   }
   // K = [r]x ; K^2 = r r^T - |r|^2 I ; Jr = I - B K + C K^2
-  double K2[9] = {r0 * r0 - th2, r0 * r1, r0 * r2, r1 * r0, r1 * r1 - th2, r1 * r2, r2 * r0, r2 * r1, r2 * r2 - th2};
-  double Km[9] = {0, -r2, r1, r2, 0, -r0, -r1, r0, 0};
+  const double K2[9] = {r0 * r0 - th2, r0 * r1, r0 * r2, r1 * r0, r1 * r1 - th2, r1 * r2, r2 * r0, r2 * r1, r2 * r2 - th2};
+  const double Km[9] = {0, -r2, r1, r2, 0, -r0, -r1, r0, 0};
 #pragma unroll
   for (int i = 0; i < 9; ++i) {
     o[CT_R + i] = R[i];
     o[CT_JR + i] = ((i % 4 == 0) ? 1.0 : 0.0) - B * Km[i] + C * K2[i];
   }
   o[CT_T + 0] = q[3]; o[CT_T + 1] = q[4]; o[CT_T + 2] = q[5];
-  double s = 1.0, k1 = k[4], k2 = k[5];
-  if (free_i) { s = q[6]; k1 = q[7]; k2 = q[8]; }
-  double fx = s * k[0], fy = s * k[1];
+  double sc = 1.0, k1 = k[4], k2 = k[5];
+  if (free_i) { sc = q[6]; k1 = q[7]; k2 = q[8]; }
+  const double fx = sc * k[0], fy = sc * k[1];
   o[CT_FX] = fx; o[CT_FY] = fy; o[CT_CX] = k[2]; o[CT_CY] = k[3];
   o[CT_D + 0] = k1; o[CT_D + 1] = k2; o[CT_D + 2] = k[6]; o[CT_D + 3] = k[7]; o[CT_D + 4] = k[8];
-  (void)fish;
   o[CT_IFX0] = 1.0 / k[0];
   o[CT_SX] = fx / k[0];
   o[CT_SY] = fy / k[0];
@@ -142,28 +148,47 @@ __global__ void cam_prep_kernel(const double* __restrict__ xc, const int* __rest
   o[35] = k[0];
 }
 
+__global__ void cam_prep_kernel(const double* __restrict__ xc, const int* __restrict__ cam_flags,
+                                const double* __restrict__ cam_const, int n_cams, int P,
+                                double* __restrict__ camtab) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cams) return;
+  cam_prep_one(xc + (size_t)c * P, cam_const + (size_t)c * 9, cam_flags[c], camtab + (size_t)c * CT_SIZE);
+}
+
 // ---------------------------------------------------------------------------------------------
-// Residual + Jacobian, camera-major.  One block = one chunk of <= RJ_CHUNK observations of ONE
-// camera: the camera table entry is block-uniform (shared memory broadcast) and the per-camera
-// normal-equation blocks reduce in registers -> warp shuffles -> one partial per chunk.
+// Camera-major pass.  One block = one chunk of <= RJ_CHUNK observations of ONE camera: the camera table
+// entry is block-uniform (shared memory broadcast) and the per-camera normal-equation blocks reduce in
+// registers -> warp shuffles -> one partial per chunk.  No Jacobian row is written: the point-major pass
+// (cb_lm.cuh pt_pass_kernel) recomputes the blocks it needs from the same 24 B / observation.
 //
-// MODE 0: write the scaled Jacobian row [r(2) | Jp(2x3) | Jc(2xP)] at the observation's point-major
-//         slot (full 32-byte sectors, STG.256) and accumulate U_c, g_c, cost.
-// MODE 1: cost only (trial point).
+// MODE 0: linearisation: residual + Jacobian blocks in registers, accumulate U_c, g_c, cost.
+// MODE 1: cost only.
 // MODE 2: raw residuals to out2[orig*2]      (== joint_residuals order)
 // MODE 3: pixel errors to out2[orig*2]       (== reprojection_errors)
 // MODE 4: euclidean pixel error to out2[q]   (camera-major, for the percentile filter)
+// With `st` the kernel is one step of the LM trial: it returns when st->done and evaluates at buffer
+// (st->cur ^ flip) of camtab2 / xp2 (flip = 1: the trial point).
 // ---------------------------------------------------------------------------------------------
 template <int P, int MODE>
 __global__ void __launch_bounds__(RJ_THREADS, (MODE == 0 && P == 6) ? 3 : 1)
-resjac_kernel(const int* __restrict__ chunk_cam, const int* __restrict__ chunk_begin,
-              const int* __restrict__ chunk_end, const double2* __restrict__ cm_xy,
-              const int* __restrict__ cm_pt, const int* __restrict__ cm_row, const int* __restrict__ cm_orig,
-              const double* __restrict__ camtab, const double* __restrict__ xp4, int loss, double fscale,
-              double* __restrict__ jrows, double* __restrict__ partial, double* __restrict__ out2) {
+resjac_kernel(const LmState* __restrict__ st, int flip, const int* __restrict__ chunk_cam,
+              const int* __restrict__ chunk_begin, const int* __restrict__ chunk_end,
+              const double2* __restrict__ cm_xy, const int* __restrict__ cm_pt, const int* __restrict__ cm_orig,
+              CPtr2 camtab2, CPtr2 xp2, int loss, double fscale, double* __restrict__ partial,
+              double* __restrict__ out2) {
   using RT = RowT<P>;
   __shared__ double cam[CT_SIZE];
   __shared__ double red[(MODE == 0 ? RT::NACC : 1) * (RJ_THREADS / 32)];
+  int sel = 0;
+  if (st != nullptr) {
+    if (st->done) return;
+    sel = st->cur ^ flip;
+    loss = st->loss;
+    fscale = st->fscale;
+  }
+  const double* __restrict__ camtab = camtab2.p[sel];
+  const double* __restrict__ xp4 = xp2.p[sel];
   const int chunk = blockIdx.x;
   const int c = chunk_cam[chunk];
   const int begin = chunk_begin[chunk], end = chunk_end[chunk];
@@ -171,99 +196,40 @@ resjac_kernel(const int* __restrict__ chunk_cam, const int* __restrict__ chunk_b
   __syncthreads();
   const int flags = (int)cam[CT_FLAGS];
   const bool fish = (flags & 2) != 0;
-  const bool free_i = (P == 9) && (flags & 1) != 0;
 
   double acc[(MODE == 0) ? RT::NACC : 1];
 #pragma unroll
   for (int k = 0; k < ((MODE == 0) ? RT::NACC : 1); ++k) acc[k] = 0.0;
 
-  // Two-deep software pipeline over this thread's observations: the index triple of iteration
-  // i+2 and the point gather of iteration i+1 are in flight while iteration i computes (the
-  // loads are a dependent chain cm_pt -> xp4[pt], ~2 DRAM/L2 latencies, and only 12-16 warps
-  // fit per SM, so the latency has to be hidden inside the thread).
+  // Two-deep software pipeline over this thread's observations: the index pair of iteration i+2 and the
+  // point gather of iteration i+1 are in flight while iteration i computes (the loads are a dependent
+  // chain cm_pt -> xp4[pt], ~2 DRAM/L2 latencies, so the latency has to be hidden inside the thread).
   int q = begin + threadIdx.x;
   double2 xy_a = make_double2(0.0, 0.0), xy_b = xy_a;
-  int pt_a = 0, row_a = 0, org_a = 0, pt_b = 0, row_b = 0, org_b = 0;
+  int pt_a = 0, org_a = 0, pt_b = 0, org_b = 0;
   double Xn0 = 0.0, Xn1 = 0.0, Xn2 = 0.0, Xn3 = 0.0;
-  auto load_idx = [&](int qq, double2& xy, int& pt, int& row, int& org) {
+  auto load_idx = [&](int qq, double2& xy, int& pt, int& org) {
     if (qq < end) {
       xy = cm_xy[qq];
       pt = cm_pt[qq];
-      if constexpr (MODE == 0) row = cm_row[qq];
       if constexpr (MODE == 2 || MODE == 3) org = cm_orig[qq];
     }
   };
-  load_idx(q, xy_a, pt_a, row_a, org_a);
-  load_idx(q + RJ_THREADS, xy_b, pt_b, row_b, org_b);
+  load_idx(q, xy_a, pt_a, org_a);
+  load_idx(q + RJ_THREADS, xy_b, pt_b, org_b);
   if (q < end) ld256nc(xp4 + 4 * (size_t)pt_a, Xn0, Xn1, Xn2, Xn3);
   for (; q < end; q += RJ_THREADS) {
     const double2 xy = xy_a;
-    const int row = row_a, org = org_a;
+    const int org = org_a;
     const double X0 = Xn0, X1 = Xn1, X2 = Xn2;
-    (void)row; (void)org;
+    (void)org;
     // rotate the pipeline
-    xy_a = xy_b; pt_a = pt_b; row_a = row_b; org_a = org_b;
+    xy_a = xy_b; pt_a = pt_b; org_a = org_b;
     if (q + RJ_THREADS < end) ld256nc(xp4 + 4 * (size_t)pt_a, Xn0, Xn1, Xn2, Xn3);
-    load_idx(q + 2 * RJ_THREADS, xy_b, pt_b, row_b, org_b);
-    ProjOut o;
-    project_obs<MODE == 0>(cam, fish, X0, X1, X2, o);
-    const double ex = o.u - xy.x, ey = o.v - xy.y;
-    if constexpr (MODE == 3) {
-      const size_t i = (size_t)org;
-      out2[2 * i] = ex; out2[2 * i + 1] = ey;
-      continue;
-    }
-    if constexpr (MODE == 4) {
-      out2[q] = sqrt(ex * ex + ey * ey);
-      continue;
-    }
-    double f0 = ex * cam[CT_IFX0], f1 = ey * cam[CT_IFX0];
-    if constexpr (MODE == 2) {
-      const size_t i = (size_t)org;
-      out2[2 * i] = f0; out2[2 * i + 1] = f1;
-      continue;
-    }
-    if constexpr (MODE == 1) {
-      acc[0] += robust_cost_only(loss, fscale, f0) + robust_cost_only(loss, fscale, f1);
-      continue;
-    }
+    load_idx(q + 2 * RJ_THREADS, xy_b, pt_b, org_b);
     if constexpr (MODE == 0) {
-      double w0, w1;
-      acc[RT::NACC - 1] += robust_row(loss, fscale, f0, w0) + robust_row(loss, fscale, f1, w1);
-      // d(u,v)/dXc / fx0, rows scaled by the robust weights
-      const double sx = cam[CT_SX] * o.iz * w0, sy = cam[CT_SY] * o.iz * w1;
-      double Jt[6];
-      Jt[0] = sx * o.xa; Jt[1] = sx * o.xb; Jt[2] = -(Jt[0] * o.a + Jt[1] * o.b);
-      Jt[3] = sy * o.ya; Jt[4] = sy * o.yb; Jt[5] = -(Jt[3] * o.a + Jt[4] * o.b);
-      const double* R = cam + CT_R;
-      double JX[6];
-#pragma unroll
-      for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-          JX[3 * i + k] = Jt[3 * i] * R[k] + Jt[3 * i + 1] * R[3 + k] + Jt[3 * i + 2] * R[6 + k];
-      double Jc[2 * P];
-      const double* Jr = cam + CT_JR;
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        // (J_X,i x X) Jr, negated
-        const double a0 = JX[3 * i], a1 = JX[3 * i + 1], a2 = JX[3 * i + 2];
-        const double c0 = a1 * X2 - a2 * X1, c1 = a2 * X0 - a0 * X2, c2 = a0 * X1 - a1 * X0;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) Jc[P * i + k] = -(c0 * Jr[k] + c1 * Jr[3 + k] + c2 * Jr[6 + k]);
-        Jc[P * i + 3] = Jt[3 * i]; Jc[P * i + 4] = Jt[3 * i + 1]; Jc[P * i + 5] = Jt[3 * i + 2];
-      }
-      if constexpr (P == 9) {
-        if (free_i) {
-          const double ar2 = cam[CT_SX] * o.a * o.r2 * w0, br2 = cam[CT_SY] * o.b * o.r2 * w1;
-          Jc[6] = o.xd * w0;                 Jc[P + 6] = cam[CT_FYR] * o.yd * w1;
-          Jc[7] = ar2;                       Jc[P + 7] = br2;
-          Jc[8] = ar2 * o.r2;                Jc[P + 8] = br2 * o.r2;
-        } else {
-          Jc[6] = Jc[7] = Jc[8] = 0.0;
-          Jc[P + 6] = Jc[P + 7] = Jc[P + 8] = 0.0;
-        }
-      }
+      double f[2], JX[6], Jc[2 * P];
+      acc[RT::NACC - 1] += obs_jac<P>(cam, X0, X1, X2, xy.x, xy.y, loss, fscale, f, JX, Jc);
       // U (packed upper), g
       int u = 0;
 #pragma unroll
@@ -274,21 +240,26 @@ resjac_kernel(const int* __restrict__ chunk_cam, const int* __restrict__ chunk_b
           ++u;
         }
 #pragma unroll
-      for (int a = 0; a < P; ++a) acc[RT::NU + a] = fma(Jc[a], f0, fma(Jc[P + a], f1, acc[RT::NU + a]));
-      // row store
-      double* dst = jrows + (size_t)row * RT::ROWD;
-      st256(dst, f0, f1, JX[0], JX[1]);
-      st256(dst + 4, JX[2], JX[3], JX[4], JX[5]);
-      if constexpr (P == 6) {
-        st256(dst + 8, Jc[0], Jc[1], Jc[2], Jc[3]);
-        st256(dst + 12, Jc[4], Jc[5], Jc[6], Jc[7]);
-        st256(dst + 16, Jc[8], Jc[9], Jc[10], Jc[11]);
+      for (int a = 0; a < P; ++a) acc[RT::NU + a] = fma(Jc[a], f[0], fma(Jc[P + a], f[1], acc[RT::NU + a]));
+    } else {
+      ProjOut o;
+      project_obs<false>(cam, fish, X0, X1, X2, o);
+      const double ex = o.u - xy.x, ey = o.v - xy.y;
+      if constexpr (MODE == 3) {
+        const size_t i = (size_t)org;
+        out2[2 * i] = ex; out2[2 * i + 1] = ey;
+      } else if constexpr (MODE == 4) {
+        // explicit round-to-nearest products and sums (no FMA contraction): the value is compared with thresholds
+        // computed on the host with NumPy from the MODE 3 errors and must agree to the last bit
+        out2[q] = sqrt(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)));
       } else {
-        st256(dst + 8, Jc[0], Jc[1], Jc[2], Jc[3]);
-        st256(dst + 12, Jc[4], Jc[5], Jc[6], Jc[7]);
-        st256(dst + 16, Jc[8], Jc[9], Jc[10], Jc[11]);
-        st256(dst + 20, Jc[12], Jc[13], Jc[14], Jc[15]);
-        st256(dst + 24, Jc[16], Jc[17], 0.0, 0.0);
+        const double f0 = ex * cam[CT_IFX0], f1 = ey * cam[CT_IFX0];
+        if constexpr (MODE == 2) {
+          const size_t i = (size_t)org;
+          out2[2 * i] = f0; out2[2 * i + 1] = f1;
+        } else {
+          acc[0] += robust_cost_only(loss, fscale, f0) + robust_cost_only(loss, fscale, f1);
+        }
       }
     }
   }
@@ -310,20 +281,6 @@ resjac_kernel(const int* __restrict__ chunk_cam, const int* __restrict__ chunk_b
   }
 }
 
-// chunk partials -> per-camera packed U, g, cost
-template <int P>
-__global__ void cam_reduce_kernel(const int* __restrict__ cam_chunk_start, const double* __restrict__ partial,
-                                  double* __restrict__ Upk, double* __restrict__ gc, double* __restrict__ cam_cost) {
-  using RT = RowT<P>;
-  const int c = blockIdx.x, k = threadIdx.x;
-  if (k >= RT::NACC) return;
-  double v = 0.0;
-  for (int ch = cam_chunk_start[c]; ch < cam_chunk_start[c + 1]; ++ch) v += partial[(size_t)ch * RT::NACC + k];
-  if (k < RT::NU) Upk[(size_t)c * RT::NU + k] = v;
-  else if (k < RT::NU + P) gc[(size_t)c * P + (k - RT::NU)] = v;
-  else cam_cost[c] = v;
-}
-
 // deterministic single-block sum of n doubles -> out[0]
 __global__ void sum_kernel(const double* __restrict__ in, int n, double* __restrict__ out) {
   __shared__ double sh[32];
@@ -337,6 +294,24 @@ __global__ void sum_kernel(const double* __restrict__ in, int n, double* __restr
     v = warp_sum(v);
     if (threadIdx.x == 0) out[0] = v;
   }
+}
+
+// Jacobian blocks in caller order for the test / diagnostic entry point cb_ba_jacobian_blocks:
+// Jc (n_obs, 2, 9) with zeros beyond the camera's width, Jp (n_obs, 2, 3)   [== joint_jacobian's non-zeros]
+template <int P>
+__global__ void jac_blocks_kernel(const int* __restrict__ obs_cam, const int* __restrict__ obs_pt,
+                                  const double2* __restrict__ obs_xy, int n, const double* __restrict__ camtab,
+                                  const double* __restrict__ xp4, double* __restrict__ Jc_out,
+                                  double* __restrict__ Jp_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* X = xp4 + 4 * (size_t)obs_pt[i];
+  const double2 xy = obs_xy[i];
+  double f[2], JX[6], Jc[2 * P];
+  obs_jac<P>(camtab + (size_t)obs_cam[i] * CT_SIZE, X[0], X[1], X[2], xy.x, xy.y, 0, 1.0, f, JX, Jc);
+  for (int k = 0; k < 6; ++k) Jp_out[(size_t)i * 6 + k] = JX[k];
+  for (int r = 0; r < 2; ++r)
+    for (int p = 0; p < 9; ++p) Jc_out[(size_t)i * 18 + r * 9 + p] = (p < P) ? Jc[r * P + p] : 0.0;
 }
 
 // 3x3 SPD: E = V + lam * D ; L = chol(E) ; returns Linv (lower, packed 00,10,11,20,21,22); zero if not PD
@@ -362,172 +337,6 @@ __device__ __forceinline__ void chol3_inv(const double* V6, const double* D2, do
     Li[0] = i00; Li[1] = i10; Li[2] = i11; Li[3] = i20; Li[4] = i21; Li[5] = i22;
   } else {
     Li[0] = Li[1] = Li[2] = Li[3] = Li[4] = Li[5] = 0.0;
-  }
-}
-
-// DUPS path of pt_build_kernel: a (point, camera) pair observed more than once (static objects seen in
-// many frames).  Z = (sum_rows Jc^T Jp) Linv^T = sum_rows Jc^T (Jp Linv^T).  Only instantiated for problems
-// that contain such pairs, so its accumulators do not set the register budget of the common single-row path.
-template <int P>
-__device__ __forceinline__ void pt_build_run(const double* __restrict__ jrows, const int* __restrict__ pm_cam,
-                                          const int* __restrict__ pm_row, int pos, int e, int cam,
-                                          const double* __restrict__ Li, double* __restrict__ z0, size_t LD) {
-  using RT = RowT<P>;
-  double z[3][P];
-#pragma unroll
-  for (int a = 0; a < 3; ++a)
-#pragma unroll
-    for (int p = 0; p < P; ++p) z[a][p] = 0.0;
-  int r = pos;
-  do {
-    const double* src = jrows + (size_t)pm_row[r] * RT::ROWD;
-    double w[RT::ROWD];
-#pragma unroll
-    for (int k = 0; k < RT::ROWD; k += 4) ld256(src + k, w[k], w[k + 1], w[k + 2], w[k + 3]);
-    const double q00 = w[2] * Li[0], q01 = w[2] * Li[1] + w[3] * Li[2], q02 = w[2] * Li[3] + w[3] * Li[4] + w[4] * Li[5];
-    const double q10 = w[5] * Li[0], q11 = w[5] * Li[1] + w[6] * Li[2], q12 = w[5] * Li[3] + w[6] * Li[4] + w[7] * Li[5];
-#pragma unroll
-    for (int p = 0; p < P; ++p) {
-      z[0][p] = fma(w[8 + p], q00, fma(w[8 + P + p], q10, z[0][p]));
-      z[1][p] = fma(w[8 + p], q01, fma(w[8 + P + p], q11, z[1][p]));
-      z[2][p] = fma(w[8 + p], q02, fma(w[8 + P + p], q12, z[2][p]));
-    }
-    ++r;
-  } while (r < e && pm_cam[r] == cam);
-#pragma unroll
-  for (int a = 0; a < 3; ++a)
-#pragma unroll
-    for (int p = 0; p < P; ++p) z0[a * LD + p] = z[a][p];
-}
-
-// Point-centric build of the Schur factor, one warp per point over its contiguous point-major rows:
-//   FUSED: V = sum Jp^T Jp, gp = sum Jp^T r over the rows (new linearisation), Marquardt scale update
-//   then  : Linv = chol(V + lam D)^-1, t = Linv gp, and per observed camera Z = (Jc^T Jp) Linv^T
-//           written to the k-major Zt (rows 3j..3j+2, columns cam*P..cam*P+P-1).
-// Repeated (camera, point) rows are adjacent (rows are sorted by point, then camera): the first
-// row of a run sums the run, so Z stays one block per (camera, point) pair without atomics.
-template <int P, bool FUSED, bool DUPS>
-__global__ void __launch_bounds__(PT_WARPS * 32)
-pt_build_kernel(const int* __restrict__ pt_start, const int* __restrict__ pm_cam,
-                const int* __restrict__ pm_row, const int* __restrict__ pt_comp, int n_pts,
-                const double* __restrict__ jrows, double* __restrict__ V6, double* __restrict__ gp,
-                double* __restrict__ Dp2, double lam, double* __restrict__ Linv6, double* __restrict__ tvec,
-                double* __restrict__ Zt, size_t LD, unsigned long long* __restrict__ gmax_bits) {
-  using RT = RowT<P>;
-  __shared__ double wmax[PT_WARPS];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int j = blockIdx.x * PT_WARPS + wid;
-  double gm = 0.0;
-  if (j < n_pts) {
-    const int s = pt_start[j], e = pt_start[j + 1];
-    double v[9], D[3];
-    // points tied by rigid-distance constraints are eliminated per component (comp_build_kernel);
-    // here they only get their observation sums V, gp
-    const bool in_comp = pt_comp != nullptr && pt_comp[j] >= 0;
-    // first batch of rows: indices loaded once, used by both phases
-    const int pos0 = s + lane;
-    int row0 = 0, cam0 = -1, prev0 = -2;
-    if (pos0 < e) {
-      row0 = pm_row[pos0];
-      cam0 = pm_cam[pos0];
-      prev0 = (pos0 > s) ? pm_cam[pos0 - 1] : -2;
-    }
-    if constexpr (FUSED) {
-#pragma unroll
-      for (int k = 0; k < 9; ++k) v[k] = 0.0;
-      for (int pos = pos0; pos < e; pos += 32) {
-        const double* src = jrows + (size_t)(pos == pos0 ? row0 : pm_row[pos]) * RT::ROWD;
-        double f0, f1, a0, a1, a2, b0, b1, b2;
-        ld256(src, f0, f1, a0, a1);
-        ld256(src + 4, a2, b0, b1, b2);
-        // the Jc part of the row is needed in phase 2: start pulling it towards L2 now
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 8));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 12));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 16));
-        if (P == 9) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 20));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 24));
-        }
-        v[0] += a0 * a0 + b0 * b0; v[1] += a0 * a1 + b0 * b1; v[2] += a0 * a2 + b0 * b2;
-        v[3] += a1 * a1 + b1 * b1; v[4] += a1 * a2 + b1 * b2; v[5] += a2 * a2 + b2 * b2;
-        v[6] += a0 * f0 + b0 * f1; v[7] += a1 * f0 + b1 * f1; v[8] += a2 * f0 + b2 * f1;
-      }
-#pragma unroll
-      for (int k = 0; k < 9; ++k) v[k] = warp_sum(v[k]);
-      const double* d = Dp2 + (size_t)j * 3;
-      D[0] = fmax(d[0], v[0]); D[1] = fmax(d[1], v[3]); D[2] = fmax(d[2], v[5]);
-      if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < 6; ++k) V6[(size_t)j * 6 + k] = v[k];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) gp[(size_t)j * 3 + k] = v[6 + k];
-        Dp2[(size_t)j * 3] = D[0]; Dp2[(size_t)j * 3 + 1] = D[1]; Dp2[(size_t)j * 3 + 2] = D[2];
-        if (!in_comp) gm = fmax(fabs(v[6]), fmax(fabs(v[7]), fabs(v[8])));
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < 6; ++k) v[k] = V6[(size_t)j * 6 + k];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) { v[6 + k] = gp[(size_t)j * 3 + k]; D[k] = Dp2[(size_t)j * 3 + k]; }
-    }
-    double Li[6];
-    chol3_inv(v, D, lam, Li);
-    if (lane == 0 && !in_comp) {
-#pragma unroll
-      for (int k = 0; k < 6; ++k) Linv6[(size_t)j * 6 + k] = Li[k];
-      tvec[3 * (size_t)j + 0] = Li[0] * v[6];
-      tvec[3 * (size_t)j + 1] = Li[1] * v[6] + Li[2] * v[7];
-      tvec[3 * (size_t)j + 2] = Li[3] * v[6] + Li[4] * v[7] + Li[5] * v[8];
-    }
-    for (int pos = pos0; pos < e && !in_comp; pos += 32) {
-      const int cam = (pos == pos0) ? cam0 : pm_cam[pos];
-      const int prev = (pos == pos0) ? prev0 : pm_cam[pos - 1];
-      if (prev == cam) continue;  // not the first of its (point, camera) run
-      double* z0 = Zt + (3 * (size_t)j) * LD + (size_t)cam * P;
-      if constexpr (DUPS) {
-        if (pos + 1 < e && pm_cam[pos + 1] == cam) {
-          pt_build_run<P>(jrows, pm_cam, pm_row, pos, e, cam, Li, z0, LD);
-          continue;
-        }
-      }
-      // single row: Z = Jc^T (Jp Linv^T), streamed straight to the stores
-      const double* src = jrows + (size_t)((pos == pos0) ? row0 : pm_row[pos]) * RT::ROWD;
-      double f0, f1, a0, a1, a2, b0, b1, b2;
-      ld256(src, f0, f1, a0, a1);
-      ld256(src + 4, a2, b0, b1, b2);
-      const double q00 = a0 * Li[0], q01 = a0 * Li[1] + a1 * Li[2], q02 = a0 * Li[3] + a1 * Li[4] + a2 * Li[5];
-      const double q10 = b0 * Li[0], q11 = b0 * Li[1] + b1 * Li[2], q12 = b0 * Li[3] + b1 * Li[4] + b2 * Li[5];
-      double jc[2 * P + (P == 9 ? 2 : 0)];
-#pragma unroll
-      for (int k = 0; k < RT::ROWD - 8; k += 4) ld256(src + 8 + k, jc[k], jc[k + 1], jc[k + 2], jc[k + 3]);
-      if constexpr (P == 6) {
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          const double qa = a == 0 ? q00 : a == 1 ? q01 : q02, qb = a == 0 ? q10 : a == 1 ? q11 : q12;
-          double2* dst = reinterpret_cast<double2*>(z0 + a * LD);  // cam*48 B and LD*8 B are 16-byte multiples
-#pragma unroll
-          for (int h = 0; h < 3; ++h)
-            dst[h] = make_double2(fma(jc[2 * h], qa, jc[P + 2 * h] * qb), fma(jc[2 * h + 1], qa, jc[P + 2 * h + 1] * qb));
-        }
-      } else {
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          const double qa = a == 0 ? q00 : a == 1 ? q01 : q02, qb = a == 0 ? q10 : a == 1 ? q11 : q12;
-#pragma unroll
-          for (int pp = 0; pp < P; ++pp) z0[a * LD + pp] = fma(jc[pp], qa, jc[P + pp] * qb);
-        }
-      }
-      (void)f0; (void)f1;
-    }
-  }
-  if constexpr (FUSED) {
-    if (lane == 0) wmax[wid] = gm;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double m = 0.0;
-      for (int w = 0; w < PT_WARPS; ++w) m = fmax(m, wmax[w]);
-      if (m > 0.0) atomicMax(gmax_bits, (unsigned long long)__double_as_longlong(m));
-    }
   }
 }
 
@@ -576,10 +385,12 @@ __constant__ signed char SY_DIAG_BLOCKS[8][3][3] = {
     {{1, 1, 1}, {1, 1, 2}, {-1, 0, 0}}, {{1, 1, 3}, {1, 2, 3}, {-1, 0, 0}}};
 
 __global__ void __launch_bounds__(SY_THREADS, 1)
-schur_syrk_kernel(const double* __restrict__ Zt, size_t LD, const double* __restrict__ tvec,
-                  const SyItem* __restrict__ items, double* __restrict__ part, double* __restrict__ tpart) {
+schur_syrk_kernel(const LmState* __restrict__ st, const double* __restrict__ Zt, size_t LD,
+                  const double* __restrict__ tvec, const SyItem* __restrict__ items, double* __restrict__ part,
+                  double* __restrict__ tpart) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SyrkSmem& sm = *reinterpret_cast<SyrkSmem*>(smem_raw);
+  if (st->done) return;
   const SyItem item = items[blockIdx.x];
   const bool diag = item.kind == 1;
   const bool two = diag ? (item.J >= 0) : true;  // second smem tile in use
@@ -763,85 +574,22 @@ __device__ __forceinline__ void finalize_elem(size_t idx, int nP, int n_blk, con
   }
 }
 
+// single-rank / NCCL / callback transports: this rank's partial reduced system into `red`, the point-gradient
+// inf-norm into this rank's slot (so that a SUM all-reduce carries the max)
 template <int P>
-__global__ void schur_finalize_kernel(int nP, int n_blk, const int* __restrict__ tile_of,
-                                      const int* __restrict__ tile_slot_start, const int* __restrict__ tile_slots,
-                                      const double* __restrict__ part, const double* __restrict__ tpart,
-                                      const double* __restrict__ Upk, const double* __restrict__ gc,
-                                      const double* __restrict__ cam_cost_sum, double* __restrict__ red) {
-  finalize_elem<P>((size_t)blockIdx.x * blockDim.x + threadIdx.x, nP, n_blk, tile_of, tile_slot_start, tile_slots, part,
-                   tpart, Upk, gc, cam_cost_sum, red);
-}
-
-// after the all-reduce: Marquardt scaling (running max of diag U), damping, camera gradient norm
-__global__ void post_reduce_kernel(int nP, double lam, int update_scale, double* __restrict__ red,
-                                   double* __restrict__ Dc2, const unsigned char* __restrict__ active,
-                                   double* __restrict__ sc) {
-  __shared__ double sh[32];
-  const size_t nn = (size_t)nP * nP;
-  double gm = 0.0;
-  for (int i = threadIdx.x; i < nP; i += blockDim.x) {
-    double d = Dc2[i];
-    if (update_scale) { d = fmax(d, red[nn + 2 * (size_t)nP + i]); Dc2[i] = d; }
-    red[(size_t)i * nP + i] += lam * (d > 0.0 ? d : 1.0);
-    if (active[i]) gm = fmax(gm, fabs(red[nn + nP + i]));
-  }
-  gm = warp_max(gm);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = gm;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double m = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, sh[w]);
-    sc[SC_GNORM_C] = m;
-    sc[SC_COST] = red[nn + 3 * (size_t)nP];
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// block-Jacobi preconditioner: inverse of each camera's P x P diagonal block of S (packed symmetric)
-// ---------------------------------------------------------------------------------------------
-template <int P>
-__global__ void block_inverse_kernel(const double* __restrict__ S, int nP, int n_cams, double* __restrict__ Minv) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_cams) return;
-  double A[P][P], Li[P][P];
-  for (int i = 0; i < P; ++i)
-    for (int j = 0; j < P; ++j) A[i][j] = S[(size_t)(c * P + i) * nP + c * P + j];
-  bool ok = true;
-  // in-place Cholesky (lower)
-  for (int j = 0; j < P; ++j) {
-    double d = A[j][j];
-    for (int k = 0; k < j; ++k) d -= A[j][k] * A[j][k];
-    if (!(d > 0.0)) { ok = false; d = 1.0; }
-    d = sqrt(d);
-    A[j][j] = d;
-    for (int i = j + 1; i < P; ++i) {
-      double s = A[i][j];
-      for (int k = 0; k < j; ++k) s -= A[i][k] * A[j][k];
-      A[i][j] = s / d;
-    }
-  }
-  // Li = L^-1 (lower)
-  for (int j = 0; j < P; ++j) {
-    Li[j][j] = 1.0 / A[j][j];
-    for (int i = j + 1; i < P; ++i) {
-      double s = 0.0;
-      for (int k = j; k < i; ++k) s -= A[i][k] * Li[k][j];
-      Li[i][j] = s / A[i][i];
-    }
-  }
-  double* out = Minv + (size_t)c * P * P;
-  for (int i = 0; i < P; ++i)
-    for (int j = 0; j < P; ++j) {
-      double s = 0.0;
-      if (ok) {
-        for (int k = (i > j ? i : j); k < P; ++k) s += Li[k][i] * Li[k][j];
-      } else {
-        const double d = S[(size_t)(c * P + i) * nP + c * P + i];
-        s = (i == j) ? (d > 0.0 ? 1.0 / d : 1.0) : 0.0;
-      }
-      out[i * P + j] = s;
-    }
+__global__ void schur_finalize_kernel(const LmState* __restrict__ st, int nP, int n_blk,
+                                      const int* __restrict__ tile_of, const int* __restrict__ tile_slot_start,
+                                      const int* __restrict__ tile_slots, const double* __restrict__ part,
+                                      const double* __restrict__ tpart, CPtr2 Upk2, CPtr2 gc2, CPtr2 costsum2,
+                                      const double* __restrict__ gmax, int red_slots, int rank_slot,
+                                      double* __restrict__ red) {
+  if (st->done) return;
+  const int cur = st->cur;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  finalize_elem<P>(idx, nP, n_blk, tile_of, tile_slot_start, tile_slots, part, tpart, Upk2.p[cur], gc2.p[cur],
+                   costsum2.p[cur], red);
+  const size_t slot0 = (size_t)nP * nP + 3 * (size_t)nP + 1;
+  if (idx < (size_t)red_slots) red[slot0 + idx] = ((int)idx == rank_slot) ? gmax[0] : 0.0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -865,10 +613,15 @@ __global__ void block_inverse_kernel(const double* __restrict__ S, int nP, int n
 // barrier per iteration, all loop buffers double-buffered by iteration parity.
 template <int MODE, int P, int CL>
 __global__ void __launch_bounds__(PCG_THREADS, 1)
-pcg_cluster_kernel(const double* __restrict__ S, const double* __restrict__ bvec, const double* __restrict__ Minv,
-                   int nP, int nPa, int rows_per, double tol2, int max_iter, double* __restrict__ xout,
-                   double* __restrict__ sc) {
+pcg_cluster_kernel(const LmState* __restrict__ st, const double* __restrict__ S, const double* __restrict__ bvec,
+                   const double* __restrict__ Minv, int nP, int nPa, int rows_per, double tol2, int max_iter,
+                   double* __restrict__ xout, double* __restrict__ sc) {
   constexpr bool SLAB_SMEM = (MODE == 0);
+  if (st != nullptr) {
+    if (st->done) return;  // uniform over the cluster, before any cluster operation
+    tol2 = st->pcg_tol2;
+    max_iter = st->pcg_max_iter;
+  }
   constexpr int NW = PCG_THREADS / 32;
   constexpr int MAXC = 16;  // largest cluster
   extern __shared__ __align__(16) double psm[];
@@ -1082,111 +835,6 @@ pcg_cluster_kernel(const double* __restrict__ S, const double* __restrict__ bvec
 }
 
 // ---------------------------------------------------------------------------------------------
-// camera step: bounds clamp, effective step written back to dc, predicted reduction (camera part)
-// ---------------------------------------------------------------------------------------------
-__global__ void cam_update_kernel(int nP, double lam, const double* __restrict__ xc, double* __restrict__ dc,
-                                  const double* __restrict__ lo, const double* __restrict__ hi,
-                                  const double* __restrict__ gc_total, const double* __restrict__ Dc2,
-                                  const unsigned char* __restrict__ active, double* __restrict__ xc_new,
-                                  double* __restrict__ sc) {
-  __shared__ double sh[3][32];
-  double pred = 0.0, st2 = 0.0, x2 = 0.0;
-  for (int i = threadIdx.x; i < nP; i += blockDim.x) {
-    const double x = xc[i];
-    double xn = x + dc[i];
-    xn = fmin(fmax(xn, lo[i]), hi[i]);
-    if (!active[i]) xn = x;
-    const double de = xn - x;
-    dc[i] = de;
-    xc_new[i] = xn;
-    if (active[i]) {
-      const double d = Dc2[i] > 0.0 ? Dc2[i] : 1.0;
-      pred += 0.5 * de * (lam * d * de - gc_total[i]);
-      st2 += de * de;
-      x2 += x * x;
-    }
-  }
-  pred = warp_sum(pred); st2 = warp_sum(st2); x2 = warp_sum(x2);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane == 0) { sh[0][wid] = pred; sh[1][wid] = st2; sh[2][wid] = x2; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double a = 0, b = 0, c = 0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += sh[0][w]; b += sh[1][w]; c += sh[2][w]; }
-    sc[SC_PRED_C] = a; sc[SC_STEP2_C] = b; sc[SC_X2_C] = c;
-  }
-}
-
-// point back-substitution: dp = -Linv^T (t + Zt_rows dc), one warp per point; block partial sums
-__global__ void __launch_bounds__(PT_WARPS * 32)
-pt_backsub_kernel(int n_pts, int nP, double lam, const int* __restrict__ pt_comp, int bpart_stride,
-                  const double* __restrict__ Zt, size_t LD,
-                  const double* __restrict__ dc, const double* __restrict__ Linv6, const double* __restrict__ tvec,
-                  const double* __restrict__ gp, const double* __restrict__ Dp2, const double* __restrict__ xp4,
-                  double* __restrict__ xp4_new, double* __restrict__ dp_out, double* __restrict__ bpart) {
-  extern __shared__ double dcs[];
-  __shared__ double wsum[3][PT_WARPS];
-  for (int i = threadIdx.x; i < nP; i += blockDim.x) dcs[i] = dc[i];
-  __syncthreads();
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int j = blockIdx.x * PT_WARPS + wid;
-  double pred = 0.0, st2 = 0.0, x2 = 0.0;
-  if (j < n_pts && !(pt_comp != nullptr && pt_comp[j] >= 0)) {
-    const double* z = Zt + 3 * (size_t)j * LD;
-    double u0 = 0.0, u1 = 0.0, u2 = 0.0;
-    for (int k = lane; k < nP; k += 32) {
-      const double d = dcs[k];
-      u0 = fma(z[k], d, u0);
-      u1 = fma(z[LD + k], d, u1);
-      u2 = fma(z[2 * LD + k], d, u2);
-    }
-    u0 = warp_sum(u0); u1 = warp_sum(u1); u2 = warp_sum(u2);
-    if (lane == 0) {
-      const double* Li = Linv6 + (size_t)j * 6;
-      const double v0 = tvec[3 * (size_t)j] + u0, v1 = tvec[3 * (size_t)j + 1] + u1, v2 = tvec[3 * (size_t)j + 2] + u2;
-      const double d0 = -(Li[0] * v0 + Li[1] * v1 + Li[3] * v2);
-      const double d1 = -(Li[2] * v1 + Li[4] * v2);
-      const double d2 = -(Li[5] * v2);
-      const double* xo = xp4 + 4 * (size_t)j;
-      double* xn = xp4_new + 4 * (size_t)j;
-      xn[0] = xo[0] + d0; xn[1] = xo[1] + d1; xn[2] = xo[2] + d2; xn[3] = 0.0;
-      if (dp_out) { dp_out[3 * (size_t)j] = d0; dp_out[3 * (size_t)j + 1] = d1; dp_out[3 * (size_t)j + 2] = d2; }
-      const double* D = Dp2 + 3 * (size_t)j;
-      const double* g = gp + 3 * (size_t)j;
-      const double e0 = D[0] > 0.0 ? D[0] : 1.0, e1 = D[1] > 0.0 ? D[1] : 1.0, e2 = D[2] > 0.0 ? D[2] : 1.0;
-      pred = 0.5 * (d0 * (lam * e0 * d0 - g[0]) + d1 * (lam * e1 * d1 - g[1]) + d2 * (lam * e2 * d2 - g[2]));
-      st2 = d0 * d0 + d1 * d1 + d2 * d2;
-      x2 = xo[0] * xo[0] + xo[1] * xo[1] + xo[2] * xo[2];
-    }
-  }
-  if (lane == 0) { wsum[0][wid] = pred; wsum[1][wid] = st2; wsum[2][wid] = x2; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double a = 0, b = 0, c = 0;
-    for (int w = 0; w < PT_WARPS; ++w) { a += wsum[0][w]; b += wsum[1][w]; c += wsum[2][w]; }
-    bpart[blockIdx.x] = a;
-    bpart[bpart_stride + blockIdx.x] = b;
-    bpart[2 * (size_t)bpart_stride + blockIdx.x] = c;
-  }
-}
-
-// three deterministic sums of n values each (laid out back to back) -> out[0..2]
-__global__ void sum3_kernel(const double* __restrict__ in, int n, double* __restrict__ out) {
-  __shared__ double sh[32];
-  const double* src = in + (size_t)blockIdx.x * n;
-  double v = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) v += src[i];
-  v = warp_sum(v);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    v = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
-    v = warp_sum(v);
-    if (threadIdx.x == 0) out[blockIdx.x] = v;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // index building helpers (setup)
 // ---------------------------------------------------------------------------------------------
 __global__ void make_keys_kernel(const int* __restrict__ a, const int* __restrict__ b, long long nb, int n,
@@ -1196,20 +844,6 @@ __global__ void make_keys_kernel(const int* __restrict__ a, const int* __restric
     keys[i] = (unsigned long long)a[i] * (unsigned long long)nb + (unsigned long long)b[i];
     vals[i] = i;
   }
-}
-// key = ((pt / blk) * n_cams + cam) * blk + pt % blk over the point-major positions
-__global__ void make_block_keys_kernel(const int* __restrict__ pm_pt, const int* __restrict__ pm_cam, int n_cams,
-                                       int blk, int n, unsigned long long* __restrict__ keys, int* __restrict__ vals) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    const unsigned long long pt = (unsigned long long)pm_pt[i];
-    keys[i] = ((pt / blk) * (unsigned long long)n_cams + (unsigned long long)pm_cam[i]) * blk + pt % blk;
-    vals[i] = i;
-  }
-}
-__global__ void invert_perm_kernel(const int* __restrict__ perm, int n, int* __restrict__ inv) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) inv[perm[i]] = i;
 }
 // sorted keys = major*nb + minor -> major/minor arrays
 __global__ void split_keys_kernel(const unsigned long long* __restrict__ keys, long long nb, int n,
@@ -1231,20 +865,24 @@ __global__ void lower_bound_kernel(const int* __restrict__ sorted_major, int n, 
   }
   start[j] = lo;
 }
-// camera-major gather: q -> point-major position -> (Jacobian row, point, original observation, xy)
-__global__ void cm_gather_kernel(const int* __restrict__ cm_pos, const int* __restrict__ pm_row,
-                                 const int* __restrict__ pm_orig, const int* __restrict__ pm_pt,
-                                 const double2* __restrict__ obs_xy, int n, int* __restrict__ cm_row,
+// camera-major gather: q -> point-major position -> (point, original observation, xy)
+__global__ void cm_gather_kernel(const int* __restrict__ cm_pos, const int* __restrict__ pm_orig,
+                                 const int* __restrict__ pm_pt, const double2* __restrict__ obs_xy, int n,
                                  int* __restrict__ cm_pt, int* __restrict__ cm_orig, double2* __restrict__ cm_xy) {
   int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q < n) {
     const int pos = cm_pos[q];
     const int o = pm_orig[pos];
-    cm_row[q] = pm_row[pos];
     cm_pt[q] = pm_pt[pos];
     cm_orig[q] = o;
     cm_xy[q] = obs_xy[o];
   }
+}
+// point-major pixel list
+__global__ void pm_gather_kernel(const int* __restrict__ pm_orig, const double2* __restrict__ obs_xy, int n,
+                                 double2* __restrict__ pm_xy) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) pm_xy[i] = obs_xy[pm_orig[i]];
 }
 __global__ void count_dups_kernel(const int* __restrict__ pm_pt, const int* __restrict__ pm_cam, int n,
                                   int* __restrict__ count) {
@@ -1255,21 +893,6 @@ __global__ void validate_kernel(const int* __restrict__ cam, const int* __restri
                                 int* __restrict__ bad) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n && (cam[i] < 0 || cam[i] >= n_cams || pt[i] < 0 || pt[i] >= n_pts)) atomicAdd(bad, 1);
-}
-
-// Jacobian rows (point-major) -> caller-order dense blocks Jc (n_obs,2,9), Jp (n_obs,2,3)
-template <int P>
-__global__ void rows_to_blocks_kernel(const double* __restrict__ jrows, const int* __restrict__ pm_row,
-                                      const int* __restrict__ pm_orig, int n, double* __restrict__ Jc,
-                                      double* __restrict__ Jp) {
-  using RT = RowT<P>;
-  int pos = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pos >= n) return;
-  const double* v = jrows + (size_t)pm_row[pos] * RT::ROWD;
-  const size_t o = (size_t)pm_orig[pos];
-  for (int k = 0; k < 6; ++k) Jp[o * 6 + k] = v[2 + k];
-  for (int i = 0; i < 2; ++i)
-    for (int p = 0; p < 9; ++p) Jc[o * 18 + i * 9 + p] = (p < P) ? v[8 + i * P + p] : 0.0;
 }
 
 // ---------------------------------------------------------------------------------------------

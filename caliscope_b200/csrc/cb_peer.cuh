@@ -16,7 +16,7 @@
 // after it passed the barrier of k+1, which every peer signals after it finished reading reduction k.
 // A spin that sees no signal for 20 s sets `err` and falls through; the host turns that into CB_E_CALLBACK.
 #pragma once
-#include "cb_kernels.cuh"
+#include "cb_lm.cuh"
 
 namespace cb {
 
@@ -73,21 +73,28 @@ __device__ __forceinline__ void peer_wait(const unsigned long long* flag, unsign
 
 constexpr int PEER_THREADS = 512;
 
+// Launched COOPERATIVELY (cudaLaunchCooperativeKernel): every block spins on the peers' flags, so the whole grid must
+// be co-resident; the cooperative launch makes the runtime guarantee it (or fail the launch) instead of trusting an
+// occupancy estimate.  The reduction's sequence number is read from the device-resident LM state (st->epoch_big + 1;
+// reduced_prep_kernel advances it), so the launch is identical every trial and replays from a CUDA graph.
 template <int P>
 __global__ void __launch_bounds__(PEER_THREADS, 2)
-schur_finalize_peer_kernel(int nP, int n_blk, const int* __restrict__ tile_of, const int* __restrict__ tile_slot_start,
-                           const int* __restrict__ tile_slots, const double* __restrict__ part,
-                           const double* __restrict__ tpart, const double* __restrict__ Upk,
-                           const double* __restrict__ gc, const double* __restrict__ cam_cost_sum,
-                           const double* __restrict__ gmax, int red_slots, int rank_slot, PeerTable tab,
-                           unsigned long long epoch, double* __restrict__ red) {
+schur_finalize_peer_kernel(const LmState* __restrict__ st, int nP, int n_blk, const int* __restrict__ tile_of,
+                           const int* __restrict__ tile_slot_start, const int* __restrict__ tile_slots,
+                           const double* __restrict__ part, const double* __restrict__ tpart, CPtr2 Upk2, CPtr2 gc2,
+                           CPtr2 costsum2, const double* __restrict__ gmax, int red_slots, int rank_slot, PeerTable tab,
+                           double* __restrict__ red) {
+  if (st->done) return;  // identical on every rank: the decision is taken on all-reduced numbers
+  const int cur = st->cur;
+  const unsigned long long epoch = st->epoch_big + 1ull;
   const int parity = (int)(epoch & 1ull);
   double* mine = tab.my_data[parity];
   const size_t nn = (size_t)nP * nP, nfin = nn + nP + 1, slot0 = nn + 3 * (size_t)nP + 1, total = slot0 + red_slots;
   const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   // (1) this rank's partial reduced system
   for (size_t idx = t0; idx < nfin; idx += stride)
-    finalize_elem<P>(idx, nP, n_blk, tile_of, tile_slot_start, tile_slots, part, tpart, Upk, gc, cam_cost_sum, mine);
+    finalize_elem<P>(idx, nP, n_blk, tile_of, tile_slot_start, tile_slots, part, tpart, Upk2.p[cur], gc2.p[cur],
+                     costsum2.p[cur], mine);
   for (size_t s = t0; s < (size_t)red_slots; s += stride) mine[slot0 + s] = ((int)s == rank_slot) ? gmax[0] : 0.0;
   // (2) last block to finish publishes the epoch to every peer
   __shared__ int s_last;
@@ -106,7 +113,8 @@ schur_finalize_peer_kernel(int nP, int n_blk, const int* __restrict__ tile_of, c
   // (3) wait for every rank's epoch
   if ((int)threadIdx.x < tab.world) peer_wait(&tab.my_flags_big[threadIdx.x], epoch, tab.err);
   __syncthreads();
-  // (4) sum over ranks in rank order, read over NVLink (cache-volatile: the buffers are rewritten every other epoch)
+  // (4) each block sums its slice over the ranks in rank order, read over NVLink (cache-volatile: the buffers are
+  //     rewritten every other epoch); all ranks therefore hold the bitwise identical reduced system
   for (size_t k = t0; k < total; k += stride) {
     double s = 0.0;
 #pragma unroll 4
@@ -115,7 +123,7 @@ schur_finalize_peer_kernel(int nP, int n_blk, const int* __restrict__ tile_of, c
   }
 }
 
-// n <= PEER_SMALL_N doubles, in place; one warp
+// n <= PEER_SMALL_N doubles, in place; one warp (stand-alone form, used outside the LM loop)
 __global__ void peer_small_allreduce_kernel(double* buf, int n, PeerTable tab, unsigned long long epoch) {
   const int t = threadIdx.x;
   const int parity = (int)(epoch & 1ull);
@@ -136,6 +144,39 @@ __global__ void peer_small_allreduce_kernel(double* buf, int n, PeerTable tab, u
     double s = 0.0;
     for (int r = 0; r < tab.world; ++r) s += __ldcv(tab.my_small + ((size_t)parity * PEER_MAXW + r) * PEER_SMALL_N + t);
     buf[t] = s;
+  }
+}
+
+// The accept / reject decision on several GPUs.  use_peer = 1: the 4 trial sums (cost, predicted reduction, step and
+// x norms of this rank's points) are summed over the ranks right here (push model over peer memory, rank order =>
+// identical on every rank); use_peer = 0: red2 was all-reduced by NCCL / the callback before this launch.  One warp.
+__global__ void lm_decide_kernel(LmState* __restrict__ st, const double* __restrict__ sc, double* __restrict__ red2,
+                                 LmLogRow* __restrict__ log, PeerTable tab, int use_peer) {
+  if (st->done) return;
+  const int t = threadIdx.x;
+  if (use_peer) {
+    const unsigned long long epoch = st->epoch_small + 1ull;
+    const int parity = (int)(epoch & 1ull);
+    if (t < tab.world) {
+      double* dst = tab.small_of[t] + ((size_t)parity * PEER_MAXW + tab.rank) * PEER_SMALL_N;
+#pragma unroll
+      for (int k = 0; k < PEER_SMALL_N; ++k) __stcg(dst + k, red2[k]);
+      __threadfence_system();
+      st_release_sys(&tab.flags_small_of[t][tab.rank], epoch);
+      peer_wait(&tab.my_flags_small[t], epoch, tab.err);
+    }
+    __syncwarp();
+    if (t < PEER_SMALL_N) {
+      double s = 0.0;
+      for (int r = 0; r < tab.world; ++r) s += __ldcv(tab.my_small + ((size_t)parity * PEER_MAXW + r) * PEER_SMALL_N + t);
+      red2[t] = s;
+    }
+    __syncwarp();
+  }
+  if (t == 0) {
+    if (use_peer) st->epoch_small += 1ull;
+    const double r2[4] = {red2[0], red2[1], red2[2], red2[3]};
+    lm_decide(st, sc, r2, log);
   }
 }
 

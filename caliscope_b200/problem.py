@@ -51,6 +51,10 @@ class SolveResult:
     solve_ms: float
     rj_ms: float
     rj_launches: int
+    syrk_ms: float = 0.0
+    syrk_launches: int = 0
+    trials_queued: int = 0
+    used_graph: bool = False
     success: bool = True
     message: str = ""
 
@@ -319,5 +323,6 @@ class BAProblem:
             x=x, status=res.status, nfev=res.nfev, njev=res.njev, nit=res.nit, cost=res.cost,
             initial_cost=res.initial_cost, optimality=res.optimality, lambda_final=res.lambda_final,
             pcg_iterations=res.pcg_iterations, kernel_launches=res.kernel_launches, solve_ms=res.solve_ms,
-            rj_ms=res.rj_ms, rj_launches=res.rj_launches,
+            rj_ms=res.rj_ms, rj_launches=res.rj_launches, syrk_ms=res.syrk_ms, syrk_launches=res.syrk_launches,
+            trials_queued=res.trials_queued, used_graph=bool(res.used_graph),
         )  # fmt: skip

@@ -32,6 +32,37 @@ def is_bundle_adjustment_call(fun: Any, args: tuple) -> bool:
     )
 
 
+def _expected_bounds(par) -> tuple[np.ndarray, np.ndarray]:
+    """The only bounds the engine implements: ``BundleParameterization.bounds()``
+    (/root/reference/src/caliscope/core/bundle_parameterization.py:151-164): s in [0.5, 2], k1 in [-1, 1],
+    k2 in [-2, 2] on cameras with free intrinsics, everything else unbounded."""
+    widths = [9 if (b.free_intrinsics and not b.fisheye) else 6 for b in par.blocks]
+    n = int(sum(widths)) + 3 * int(par.n_points)
+    lo, hi = np.full(n, -np.inf), np.full(n, np.inf)
+    o = 0
+    for w in widths:
+        if w == 9:
+            lo[o + 6 : o + 9] = (0.5, -1.0, -2.0)
+            hi[o + 6 : o + 9] = (2.0, 1.0, 2.0)
+        o += w
+    return lo, hi
+
+
+def _check_supported(par, lo, hi, use_bounds: bool, x_scale, tr_solver, n: int) -> None:
+    """Fail loudly on a call the engine would otherwise answer with different semantics."""
+    if use_bounds:
+        elo, ehi = _expected_bounds(par)
+        lo_b, hi_b = np.broadcast_to(lo, (n,)), np.broadcast_to(hi, (n,))
+        if len(elo) != n or not (np.array_equal(lo_b, elo) and np.array_equal(hi_b, ehi)):
+            raise NotImplementedError(
+                "caliscope_b200.least_squares implements exactly BundleParameterization.bounds() "
+                "(s in [0.5, 2], k1 in [-1, 1], k2 in [-2, 2] on free-intrinsics cameras); other bounds are not supported")
+    if x_scale is not None and not (isinstance(x_scale, str) and x_scale == "jac"):
+        raise NotImplementedError("caliscope_b200.least_squares implements x_scale='jac' only (Marquardt scaling)")
+    if tr_solver not in (None, "lsmr"):
+        raise NotImplementedError("caliscope_b200.least_squares replaces tr_solver='lsmr' (the sparse path) only")
+
+
 def solve_arrays(cam_flags, cam_const, n_pts, camera_indices, obj_indices, image_coords, x0, *, use_bounds=True,
                  constraints=None, device: int = 0, **kw) -> SolveResult:  # fmt: skip
     """Array-level entry: build the device problem (optionally with rigid-distance rows), solve, free it."""
@@ -55,6 +86,7 @@ def least_squares(fun, x0, jac="2-point", bounds=(-np.inf, np.inf), method="trf"
     flags, const = blocks_to_arrays(par.blocks)
     lo, hi = (np.asarray(b, dtype=np.float64) for b in bounds) if isinstance(bounds, (tuple, list)) else (bounds.lb, bounds.ub)
     use_bounds = bool(np.any(np.isfinite(np.atleast_1d(lo))) or np.any(np.isfinite(np.atleast_1d(hi))))
+    _check_supported(par, lo, hi, use_bounds, x_scale, tr_solver, np.asarray(x0).shape[0])
     res = solve_arrays(flags, const, par.n_points, np.asarray(camera_indices), np.asarray(obj_indices),
                        np.asarray(image_coords, dtype=np.float64), np.asarray(x0, dtype=np.float64),
                        use_bounds=use_bounds, constraints=constraints, ftol=ftol if ftol is not None else 0.0, xtol=xtol if xtol is not None else 0.0,

@@ -107,7 +107,11 @@ def make_rig(
     outlier_frac: float = 0.0,
     outlier_px: float = 50.0,
     name: str = "",
+    cams_per_point: int | None = None,
 ) -> SyntheticRig:
+    """``cams_per_point``: local visibility -- every point faces a random azimuth and is seen only by the
+    ``cams_per_point`` in-frame cameras nearest to that direction (a marker on a subject inside a ring rig: the
+    realistic Caliscope shape, 2-8 cameras per point), instead of by a uniform random subset of all cameras."""
     rng = np.random.default_rng(seed)
     rvec, tvec = _ring_cameras(n_cams)
     w, h = WEBCAM_SIZE
@@ -129,6 +133,17 @@ def make_rig(
     pair_cam = np.concatenate(pair_cam)
     pair_pt = np.concatenate(pair_pt)
     pair_uv = np.concatenate(pair_uv)
+    if cams_per_point is not None:
+        cam_pos = np.array([-_rot(rvec[c]).T @ tvec[c] for c in range(n_cams)])
+        cam_az = np.arctan2(cam_pos[:, 1], cam_pos[:, 0])
+        facing = rng.uniform(-np.pi, np.pi, n_pts)
+        d = np.abs(np.angle(np.exp(1j * (cam_az[pair_cam] - facing[pair_pt]))))
+        order = np.lexsort((d, pair_pt))  # by point, nearest camera first
+        pt_sorted = pair_pt[order]
+        first = np.searchsorted(pt_sorted, np.arange(n_pts))
+        rank_in_pt = np.arange(len(order)) - first[pt_sorted]
+        keep = np.sort(order[rank_in_pt < cams_per_point])  # back to camera-major order
+        pair_cam, pair_pt, pair_uv = pair_cam[keep], pair_pt[keep], pair_uv[keep]
     n_pairs = len(pair_cam)
     if n_obs <= n_pairs:
         sel = np.sort(rng.permutation(n_pairs)[:n_obs])
@@ -187,6 +202,13 @@ def cfg4(seed: int = 0, refine_intrinsics: bool = False) -> SyntheticRig:
 def cfg5(seed: int = 0) -> SyntheticRig:
     return make_rig(64, 50_000, 2_000_000, seed=seed, outlier_frac=0.02,
                     name="cfg5 64-cam/50k-pt/2M-obs + 2% outliers (filter + re-solve loop)")  # fmt: skip
+
+
+def sparse64(seed: int = 0) -> SyntheticRig:
+    """64 cameras / 250 000 points / 2 000 000 observations with 8 cameras per point (local visibility): the same
+    observation count as cfg4 at the camera-per-point density of real Caliscope sessions."""
+    return make_rig(64, 250_000, 2_000_000, seed=seed, cams_per_point=8,
+                    name="sparse64 64-cam/250k-pt/2M-obs, 8 cameras per point (local visibility)")  # fmt: skip
 
 
 def exact_normalized_observations(rig: SyntheticRig):

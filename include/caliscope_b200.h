@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CB_BA_ABI_VERSION 1
+#define CB_BA_ABI_VERSION 2
 
 /* cam_flags bits (CameraBlock.free_intrinsics / .fisheye, bundle_parameterization.py:36-51) */
 #define CB_CAM_FREE_INTRINSICS 1
@@ -122,8 +122,13 @@ typedef struct {
   int64_t pcg_iterations; /* total PCG iterations over the solve */
   int64_t kernel_launches;
   double solve_ms; /* device time of the LM loop (CUDA events on the solve stream) */
-  double rj_ms;    /* total device time spent in the residual+Jacobian kernel */
+  double rj_ms;    /* total device time spent in the residual+Jacobian (point pass) kernel, CUDA events around each launch */
   int64_t rj_launches;
+  double syrk_ms;  /* total device time spent in the Schur product kernel */
+  int64_t syrk_launches;
+  int64_t trials_queued; /* LM trials handed to the device (the last one runs predicated-off) */
+  int32_t used_graph;    /* 1: trials were replayed from a CUDA graph, 0: launched directly */
+  int32_t pad_;
 } CbBaResult;
 
 int cb_ba_abi_version(void);
@@ -196,6 +201,11 @@ int cb_ba_cull(CbBaProblem* p, const double* x, const double* thresholds, int32_
 /* Diagnostic: mean milliseconds of one PCG-kernel launch forced to run exactly max_iter iterations on the
  * system left by the last cb_ba_normal_equations call. */
 int cb_ba_debug_pcg_time(CbBaProblem* p, int max_iter, int reps, double* ms_per_launch, void* stream);
+
+/* Measured fp64 throughput of the device (TFLOP/s): `mma.sync.m8n8k4.f64` (DMMA, the tensor path the Schur product
+ * runs on) and plain DFMA register chains, 8 warps per SM, a few milliseconds each.  The roofline denominator for the
+ * Schur product; there is no driver-measured fp64 figure in MEASURED_PEAKS.json. */
+int cb_debug_fp64_peak(int device, double* dmma_tflops, double* dfma_tflops);
 
 /* ---- the step in front of bundle adjustment ------------------------------------------- */
 

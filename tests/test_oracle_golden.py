@@ -86,6 +86,26 @@ def test_filter_error_inputs_match_reference():
     assert np.abs(e - g["filt_err_xy"]).max() < 1e-9
 
 
+def test_oracle_filter_rule_matches_reference_keep_mask():
+    """oracle/filtering.py (thresholds + keep mask + min_per_camera floor) against the unmodified reference's
+    filter_by_percentile_error on the session fixture: thresholds to the last bit, mask index for index."""
+    from oracle import filtering as OF
+
+    g, rig = load_golden("session4_refine0.npz")
+    err = OF.euclidean_error(g["filt_err_xy"])
+    assert np.array_equal(err, g["filt_err"])
+    thr = OF.percentile_thresholds(err, g["filt_cam"], rig.n_cams, float(g["filt_percentile"]), "per_camera")
+    assert np.array_equal(thr, g["filt_thresholds"])
+    keep = OF.keep_mask(err, g["filt_cam"], thr, int(g["filt_min_per_camera"]))
+    assert np.array_equal(keep, g["filt_keep"])
+    # the floor: a threshold below every error keeps exactly min_per_camera lowest-error rows per camera
+    keep0 = OF.keep_mask(err, g["filt_cam"], np.zeros(rig.n_cams), 7)
+    for c in range(rig.n_cams):
+        sel = g["filt_cam"] == c
+        assert keep0[sel].sum() == min(7, sel.sum())
+        assert err[sel][keep0[sel]].max() <= np.sort(err[sel])[min(7, sel.sum()) - 1]
+
+
 @pytest.mark.parametrize("name,refine", [("session4_refine0.npz", False), ("small_pinhole_refine1.npz", True)])
 def test_scipy_solve_reproduces_reference_run(name, refine):
     """Same scipy, restated fun/jac -> same trajectory as the reference's optimize()."""
