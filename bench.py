@@ -411,8 +411,10 @@ def run_ours(args) -> None:
         l_cam, l_pt, l_xy, l_npts = shard.obs_cam, shard.obs_pt, shard.obs_xy, shard.n_pts
         x0 = D.local_x(rig.x0, ncp, shard)
         transport = D.transport_kwargs(local_rank, n_camera_dims=rig.n_cams * (9 if np.any(rig.cam_flags & 1) else 6))
+        cam_order = D.camera_order(rig.obs_cam, rig.obs_pt, rig.n_cams, rig.n_pts, 9 if np.any(rig.cam_flags & 1) else 6)
     else:
         shard = None
+        cam_order = None
         l_cam, l_pt, l_xy, l_npts = rig.obs_cam, rig.obs_pt, rig.obs_xy, rig.n_pts
         x0 = rig.x0
         transport = {}
@@ -436,7 +438,7 @@ def run_ours(args) -> None:
     d_cam = torch.from_numpy(l_cam).cuda()
     d_pt = torch.from_numpy(l_pt).cuda()
     d_xy = torch.from_numpy(np.ascontiguousarray(l_xy)).cuda()
-    prob = cb.BAProblem(rig.cam_flags, rig.cam_const, l_npts, d_cam, d_pt, d_xy, device=dev, stream=stream)
+    prob = cb.BAProblem(rig.cam_flags, rig.cam_const, l_npts, d_cam, d_pt, d_xy, device=dev, stream=stream, cam_order=cam_order)
     res = None
     n_c, n_p, n_o, refine = WORKLOADS[args.workload]
     flush = None
@@ -497,7 +499,7 @@ def run_ours(args) -> None:
             return solver.least_squares(R.joint_residuals, rig.x0, args=(par, cam16, xy_h, obj_h, None, None, None, None),
                                         jac=R.joint_jacobian, x_scale="jac", method="trf", bounds=par.bounds(), ftol=1e-8,
                                         loss="linear", f_scale=1.0, max_nfev=None, verbose=0)
-        with cb.BAProblem(rig.cam_flags, rig.cam_const, l_npts, lc, lp, lx, device=dev, stream=stream) as p2:
+        with cb.BAProblem(rig.cam_flags, rig.cam_const, l_npts, lc, lp, lx, device=dev, stream=stream, cam_order=cam_order) as p2:
             return p2.solve(x0, **solve_kw)
 
     for _ in range(min(args.warmup, 3)):

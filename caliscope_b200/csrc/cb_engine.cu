@@ -283,10 +283,17 @@ struct CbBaProblem {
   int n_chunks = 0, pt_grid = 0, pt_lanes = 32, n_dups = 0;
   int cam_in_smem = 0;
   size_t pt_smem = 0, bs_smem = 0;
-  std::vector<int> h_cam_off;
+  std::vector<int> h_cam_off;   // caller's layout: x offset of caller camera c
+  std::vector<int> h_perm, h_slot;  // internal slot i holds caller camera h_perm[i]; h_slot[c] = slot of caller camera c
+  std::vector<int> h_iflags;    // flags by internal slot
+  bool order_auto = false, order_identity = true;
+  int ncp = 0;                  // total camera parameters in x
+  int *d_cam_xoff = nullptr, *d_cam_slot = nullptr, *d_klist = nullptr;
+  bool schur_sparse = false;
+  double schur_rows_dense = 0.0, schur_rows_listed = 0.0;  // weighted k rows the Schur product streams: all vs listed
   std::vector<void*> allocs;
   // problem tables
-  int *d_cam_off = nullptr, *d_cam_flags = nullptr;
+  int* d_cam_flags = nullptr;
   double* d_cam_const = nullptr;
   double2 *d_cm_xy = nullptr, *d_pm_xy = nullptr;
   int *d_cm_pt = nullptr, *d_cm_orig = nullptr, *d_cam_start = nullptr;
@@ -399,8 +406,92 @@ cudaStream_t side_stream() {
   return s;
 }
 
+// Internal camera order.  The reduced system and the Schur factor are laid out by camera slot; the Schur product only
+// has to visit, per pair of 96-column tiles, the points seen from BOTH tiles.  When visibility is local (ring rigs:
+// a point is seen by a few neighbouring cameras) but the caller's numbering is not (e.g. ring by ring), putting cameras
+// that share points next to each other empties most tile pairs.  Order = the caller's (`cam_order` = slot -> camera,
+// REQUIRED to be the same on every rank of a sharded solve), or chosen here from a sampled co-visibility matrix
+// (greedy chain: next = the unplaced camera sharing most points with the last 16 placed), kept only if it lowers the
+// number of (point, tile pair) incidences.
+int choose_camera_order(CbBaProblem* p, const int* cam_order, cudaStream_t st) {
+  const int nc = p->n_cams;
+  p->h_perm.resize(nc); p->h_slot.resize(nc);
+  for (int i = 0; i < nc; ++i) p->h_perm[i] = i;
+  p->order_auto = false;
+  if (cam_order) {
+    std::vector<char> seen(nc, 0);
+    for (int i = 0; i < nc; ++i) {
+      const int c = cam_order[i];
+      if (c < 0 || c >= nc || seen[c]) { g_last_error = "cam_order is not a permutation of 0..n_cams-1"; return CB_E_INVALID; }
+      seen[c] = 1;
+      p->h_perm[i] = c;
+    }
+  } else {
+    const int cams_per_tile = std::max(1, cb::SY_TILE / p->P);
+    const double avg = (double)p->n_obs / std::max(p->n_pts, 1);
+    int want = (p->n_blk >= 3 && avg <= nc / 3.0) ? 1 : 0;
+    if (const char* e = std::getenv("CB_CAM_ORDER")) want = std::atoi(e);
+    if (want) {
+      p->order_auto = true;
+      const int stride = std::max(1, p->n_pts / 8192), ns = cdiv(p->n_pts, stride);
+      unsigned int* d_W;
+      CB_TRY(dalloc(&d_W, (size_t)nc * nc));
+      ScopedFree sf; sf.dev.push_back(d_W);
+      CB_CUDA(cudaMemsetAsync(d_W, 0, sizeof(unsigned int) * nc * nc, st));
+      CB_LAUNCH(cb::covis_kernel, cdiv((long long)ns * 32, 256), 256, 0, st, p->d_pt_start, p->d_pm_cam, p->n_pts, stride, nc, d_W);
+      std::vector<unsigned int> W((size_t)nc * nc);
+      CB_CUDA(cudaMemcpyAsync(W.data(), d_W, sizeof(unsigned int) * nc * nc, cudaMemcpyDeviceToHost, st));
+      CB_CUDA(cudaStreamSynchronize(st));
+      // greedy chain
+      std::vector<char> placed(nc, 0);
+      std::vector<int> order;
+      int start = 0;
+      unsigned long long best = ~0ull;
+      for (int c = 0; c < nc; ++c) {
+        unsigned long long tot = 0;
+        for (int q = 0; q < nc; ++q) if (q != c) tot += W[(size_t)c * nc + q];
+        if (tot < best) { best = tot; start = c; }
+      }
+      order.push_back(start); placed[start] = 1;
+      while ((int)order.size() < nc) {
+        int pick = -1;
+        unsigned long long bw = 0;
+        const int lo = std::max(0, (int)order.size() - cams_per_tile);
+        for (int c = 0; c < nc; ++c) {
+          if (placed[c]) continue;
+          unsigned long long w = 0;
+          for (int k = lo; k < (int)order.size(); ++k) w += W[(size_t)c * nc + order[k]];
+          if (pick < 0 || w > bw) { pick = c; bw = w; }
+        }
+        order.push_back(pick); placed[pick] = 1;
+      }
+      // keep it only if it lowers the co-visibility mass that falls OUTSIDE the diagonal tiles (pairs of cameras in
+      // different tiles that share points are what forces off-diagonal tile pairs to be visited)
+      auto off_mass = [&](const std::vector<int>& ord) {
+        std::vector<int> tile(nc);
+        for (int i = 0; i < nc; ++i) tile[ord[i]] = (i * p->P) / cb::SY_TILE;
+        unsigned long long m = 0;
+        for (int a = 0; a < nc; ++a)
+          for (int b = 0; b < nc; ++b)
+            if (tile[a] != tile[b]) m += W[(size_t)a * nc + b];
+        return m;
+      };
+      std::vector<int> ident(nc);
+      for (int i = 0; i < nc; ++i) ident[i] = i;
+      if (off_mass(order) < 0.8 * off_mass(ident)) p->h_perm = order;
+    }
+  }
+  p->order_identity = true;
+  for (int i = 0; i < nc; ++i) {
+    p->h_slot[p->h_perm[i]] = i;
+    if (p->h_perm[i] != i) p->order_identity = false;
+  }
+  CB_CUDA(cudaMemcpyAsync(p->d_cam_slot, p->h_slot.data(), sizeof(int) * nc, cudaMemcpyHostToDevice, st));
+  return CB_OK;
+}
+
 int build_indices(CbBaProblem* p, const int* d_obs_cam, const int* d_obs_pt, const double* d_obs_xy,
-                  cudaStream_t st, cudaEvent_t xy_ready) {
+                  const int* cam_order, cudaStream_t st, cudaEvent_t xy_ready) {
   const int n = p->n_obs;
   const int TB = 256, G = cdiv(std::max(n, 1), TB);
   ScopedFree sf;
@@ -432,6 +523,9 @@ int build_indices(CbBaProblem* p, const int* d_obs_cam, const int* d_obs_pt, con
   CB_LAUNCH(cb::split_keys_kernel, G, TB, 0, st, k_out, (long long)p->n_cams, n, pm_pt, pm_cam);
   CB_LAUNCH(cb::lower_bound_kernel, cdiv(p->n_pts + 1, TB), TB, 0, st, pm_pt, n, p->n_pts, p->d_pt_start);
   CB_LAUNCH(cb::count_dups_kernel, G, TB, 0, st, pm_pt, pm_cam, n, d_bad + 1);
+  // (1b) internal camera order (see choose_camera_order), then pm_cam := internal slots
+  CB_TRY(choose_camera_order(p, cam_order, st));
+  if (!p->order_identity) CB_LAUNCH(cb::remap_kernel, G, TB, 0, st, pm_cam, (const int*)p->d_cam_slot, n);
   // (2) camera-major order: key = cam * n_pts + pt over the point-major positions (stable)
   CB_LAUNCH(cb::make_keys_kernel, G, TB, 0, st, pm_cam, pm_pt, (long long)p->n_pts, n, k_in, v_in);
   CB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb, k_in, k_out, v_in, v_out, n, 0, kb, st));
@@ -582,7 +676,7 @@ int build_system(CbBaProblem* p, const CbBaOptions* opt, cudaStream_t st, cudaEv
               p->d_compL, p->d_tvec, p->d_Zt, (size_t)p->LD, p->d_gmax);
   if (ev_c) CB_CUDA(cudaEventRecord(ev_c, st));
   CB_LAUNCH(cb::schur_syrk_kernel, p->n_items, cb::SY_THREADS, sizeof(cb::SyrkSmem), st, (const cb::LmState*)p->d_state,
-            p->d_Zt, (size_t)p->LD, p->d_tvec, p->d_items, p->d_part, p->d_tpart);
+            p->d_Zt, (size_t)p->LD, p->d_tvec, p->d_items, (const int*)p->d_klist, p->d_part, p->d_tpart);
   if (ev_d) CB_CUDA(cudaEventRecord(ev_d, st));
   const size_t nfin = (size_t)p->nP * p->nP + p->nP + 1;
   // gradient inf-norm over points: one slot per rank so a SUM all-reduce carries the max
@@ -653,15 +747,15 @@ int upload_x(CbBaProblem* p, const double* x, cudaStream_t st) {
   std::memcpy(p->h_x, x, sizeof(double) * p->n_params);
   CB_CUDA(cudaMemcpyAsync(p->d_x, p->h_x, sizeof(double) * p->n_params, cudaMemcpyHostToDevice, st));
   const int n = std::max(p->n_cams * p->P, p->n_pts);
-  CB_LAUNCH(cb::unpack_x_kernel, cdiv(std::max(n, 1), 256), 256, 0, st, p->d_x, p->d_cam_off, p->d_cam_flags,
-            p->d_cam_const, p->n_cams, p->P, p->n_pts, p->d_xc[0], p->d_xp4[0]);
+  CB_LAUNCH(cb::unpack_x_kernel, cdiv(std::max(n, 1), 256), 256, 0, st, p->d_x, p->d_cam_xoff, p->d_cam_flags,
+            p->d_cam_const, p->n_cams, p->P, p->n_pts, p->ncp, p->d_xc[0], p->d_xp4[0]);
   return CB_OK;
 }
 
 int download_x(CbBaProblem* p, int cur, double* x, cudaStream_t st) {
   const int n = std::max(p->n_cams * p->P, p->n_pts);
-  CB_LAUNCH(cb::pack_x_kernel, cdiv(std::max(n, 1), 256), 256, 0, st, p->d_x, p->d_cam_off, p->n_cams, p->P, p->n_pts,
-            p->d_xc[cur], p->d_xp4[cur]);
+  CB_LAUNCH(cb::pack_x_kernel, cdiv(std::max(n, 1), 256), 256, 0, st, p->d_x, p->d_cam_xoff, p->d_cam_flags, p->n_cams,
+            p->P, p->n_pts, p->ncp, p->d_xc[cur], p->d_xp4[cur]);
   CB_CUDA(cudaMemcpyAsync(p->h_x, p->d_x, sizeof(double) * p->n_params, cudaMemcpyDeviceToHost, st));
   CB_CUDA(cudaStreamSynchronize(st));
   std::memcpy(x, p->h_x, sizeof(double) * p->n_params);
@@ -672,7 +766,7 @@ int set_bounds(CbBaProblem* p, bool use_bounds, cudaStream_t st) {
   std::vector<double> lo((size_t)p->nP, -1e300), hi((size_t)p->nP, 1e300);
   if (use_bounds && p->P == 9) {
     for (int c = 0; c < p->n_cams; ++c)
-      if (p->h_cam_off[c + 1] - p->h_cam_off[c] == 9) {
+      if (p->h_iflags[c] & CB_CAM_FREE_INTRINSICS) {
         lo[c * 9 + 6] = 0.5; hi[c * 9 + 6] = 2.0;
         lo[c * 9 + 7] = -1.0; hi[c * 9 + 7] = 1.0;
         lo[c * 9 + 8] = -2.0; hi[c * 9 + 8] = 2.0;
@@ -1118,6 +1212,141 @@ int cb_ba_problem_destroy(CbBaProblem* p) {
 int64_t cb_ba_problem_n_params(const CbBaProblem* p) { return p ? p->n_params : -1; }
 int cb_ba_cam_stride(const CbBaProblem* p) { return p ? p->P : -1; }
 
+// Schur work items.  Dense visibility: off-diagonal tiles and pairs of diagonal tiles, each split over k so that the
+// grid is one CTA per SM with equal DMMA work (a diagonal pair costs 45/36 of a full tile per chunk).  Sparse
+// visibility (fewer than 70 % of the (point, tile pair) incidences exist): every tile pair gets the compacted list of
+// the k rows of the points BOTH its column tiles see, and CTAs are dealt in proportion to list length.
+static int build_schur_items(CbBaProblem* p, cudaStream_t st) {
+  const int nb = p->n_blk;
+  std::vector<int> tof((size_t)nb * nb, -1);
+  int nt = 0;
+  for (int I = 0; I < nb; ++I)
+    for (int J = I; J < nb; ++J) tof[(size_t)I * nb + J] = nt++;
+  double w_pair = 1.55;  // measured cost of a diagonal-pair CTA per k chunk relative to an off-diagonal one
+  if (const char* ev = std::getenv("CB_SY_PAIR_W")) w_pair = std::atof(ev);
+  const double w_single = 0.75;
+
+  // per-pair point lists, if sparse
+  std::vector<std::vector<int>> plist;  // indexed by tile id (tof)
+  bool sparse = false;
+  int want_sparse = -1;
+  if (const char* ev = std::getenv("CB_SY_SPARSE")) want_sparse = std::atoi(ev);
+  if (nb >= 2 && nb <= 64 && p->n_pts > 0 && want_sparse != 0) {
+    unsigned long long* d_mask;
+    CB_TRY(dalloc(&d_mask, (size_t)p->n_pts));
+    ScopedFree sf; sf.dev.push_back(d_mask);
+    CB_LAUNCH(cb::pt_tile_mask_kernel, cdiv(p->n_pts, 256), 256, 0, st, p->d_pt_start, p->d_pm_cam, p->n_pts, p->P, d_mask);
+    std::vector<unsigned long long> mask((size_t)p->n_pts);
+    CB_CUDA(cudaMemcpyAsync(mask.data(), d_mask, sizeof(unsigned long long) * p->n_pts, cudaMemcpyDeviceToHost, st));
+    CB_CUDA(cudaStreamSynchronize(st));
+    std::vector<long long> cnt(nt, 0);
+    for (int j = 0; j < p->n_pts; ++j) {
+      unsigned long long m = mask[j];
+      for (unsigned long long a = m; a; a &= a - 1) {
+        const int I = __builtin_ctzll(a);
+        for (unsigned long long b2 = a; b2; b2 &= b2 - 1) cnt[tof[(size_t)I * nb + __builtin_ctzll(b2)]]++;
+      }
+    }
+    double listed = 0.0, dense = 0.0;
+    for (int I = 0; I < nb; ++I)
+      for (int J = I; J < nb; ++J) {
+        const double w = (I == J) ? w_single : 1.0;
+        listed += w * (double)cnt[tof[(size_t)I * nb + J]];
+        dense += w * (double)p->n_pts;
+      }
+    p->schur_rows_dense = 3.0 * dense; p->schur_rows_listed = 3.0 * listed;
+    sparse = want_sparse == 1 || listed < 0.7 * dense;
+    if (sparse) {
+      plist.resize(nt);
+      for (int t = 0; t < nt; ++t) plist[t].reserve((size_t)cnt[t]);
+      for (int j = 0; j < p->n_pts; ++j) {
+        unsigned long long m = mask[j];
+        for (unsigned long long a = m; a; a &= a - 1) {
+          const int I = __builtin_ctzll(a);
+          for (unsigned long long b2 = a; b2; b2 &= b2 - 1) plist[tof[(size_t)I * nb + __builtin_ctzll(b2)]].push_back(j);
+        }
+      }
+    }
+  }
+  p->schur_sparse = sparse;
+
+  struct Group { int kind, I, J; double w; int chunks; int koff; };
+  std::vector<Group> groups;
+  std::vector<int> klist;
+  if (!sparse) {
+    for (int I = 0; I < nb; ++I)
+      for (int J = I + 1; J < nb; ++J) groups.push_back({0, I, J, 1.0, p->k_chunks, -1});
+    for (int I = 0; I < nb; I += 2) {
+      if (I + 1 < nb) groups.push_back({1, I, I + 1, w_pair, p->k_chunks, -1});
+      else groups.push_back({1, I, -1, w_single, p->k_chunks, -1});
+    }
+  } else {
+    const int zero_row = p->K_pad;  // rows K_pad .. K_pad + SY_KC - 1 of Zt / tvec are never written
+    for (int I = 0; I < nb; ++I)
+      for (int J = I; J < nb; ++J) {
+        const std::vector<int>& pl = plist[tof[(size_t)I * nb + J]];
+        if (pl.empty()) continue;
+        const int koff = (int)klist.size();
+        for (int j : pl) { klist.push_back(3 * j); klist.push_back(3 * j + 1); klist.push_back(3 * j + 2); }
+        while (klist.size() % cb::SY_KC) klist.push_back(zero_row);
+        const int chunks = (int)((klist.size() - koff) / cb::SY_KC);
+        if (I == J) groups.push_back({1, I, -1, w_single, chunks, koff});
+        else groups.push_back({0, I, J, 1.0, chunks, koff});
+      }
+  }
+  double W = 0.0;
+  for (auto& g : groups) W += g.w * g.chunks;
+  std::vector<cb::SyItem> items;
+  std::vector<std::vector<int>> slots_of(nt);
+  int slot = 0;
+  for (auto& g : groups) {
+    int n = (int)std::floor(p->num_sms * (g.w * g.chunks) / std::max(W, 1.0));
+    n = std::max(1, std::min(n, g.chunks));
+    for (int s2 = 0; s2 < n; ++s2) {
+      cb::SyItem it;
+      it.kind = g.kind; it.I = g.I; it.J = g.J; it.koff = g.koff;
+      it.c0 = (int)(((long long)g.chunks * s2) / n);
+      it.c1 = (int)(((long long)g.chunks * (s2 + 1)) / n);
+      it.slotA = slot++;
+      it.slotB = -1;
+      if (g.kind == 0) {
+        slots_of[tof[(size_t)g.I * nb + g.J]].push_back(it.slotA);
+      } else {
+        slots_of[tof[(size_t)g.I * nb + g.I]].push_back(it.slotA);
+        if (g.J >= 0) {
+          it.slotB = slot++;
+          slots_of[tof[(size_t)g.J * nb + g.J]].push_back(it.slotB);
+        }
+      }
+      items.push_back(it);
+    }
+  }
+  p->n_items = (int)items.size();
+  p->n_slots = std::max(slot, 1);
+  std::vector<int> sstart(nt + 1, 0), sflat;
+  for (int t = 0; t < nt; ++t) {
+    sstart[t] = (int)sflat.size();
+    sflat.insert(sflat.end(), slots_of[t].begin(), slots_of[t].end());
+  }
+  sstart[nt] = (int)sflat.size();
+  CB_TRY(palloc(p, &p->d_items, std::max<size_t>(items.size(), 1)));
+  CB_TRY(palloc(p, &p->d_tile_of, tof.size()));
+  CB_TRY(palloc(p, &p->d_tile_slot_start, sstart.size()));
+  CB_TRY(palloc(p, &p->d_tile_slots, std::max<size_t>(sflat.size(), 1)));
+  if (!klist.empty()) {
+    CB_TRY(palloc(p, &p->d_klist, klist.size()));
+    CB_CUDA(cudaMemcpyAsync(p->d_klist, klist.data(), sizeof(int) * klist.size(), cudaMemcpyHostToDevice, st));
+  }
+  if (!items.empty())
+    CB_CUDA(cudaMemcpyAsync(p->d_items, items.data(), sizeof(cb::SyItem) * items.size(), cudaMemcpyHostToDevice, st));
+  CB_CUDA(cudaMemcpyAsync(p->d_tile_of, tof.data(), sizeof(int) * tof.size(), cudaMemcpyHostToDevice, st));
+  CB_CUDA(cudaMemcpyAsync(p->d_tile_slot_start, sstart.data(), sizeof(int) * sstart.size(), cudaMemcpyHostToDevice, st));
+  if (!sflat.empty())
+    CB_CUDA(cudaMemcpyAsync(p->d_tile_slots, sflat.data(), sizeof(int) * sflat.size(), cudaMemcpyHostToDevice, st));
+  CB_CUDA(cudaStreamSynchronize(st));  // the host vectors above go out of scope
+  return CB_OK;
+}
+
 static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_t st, CbBaProblem* p) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -1144,7 +1373,8 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
   }
   p->P = any_free ? 9 : 6;
   p->nP = p->n_cams * p->P;
-  p->n_params = p->h_cam_off[p->n_cams] + 3 * p->n_pts;
+  p->ncp = p->h_cam_off[p->n_cams];
+  p->n_params = p->ncp + 3 * p->n_pts;
   p->n_blk = cdiv(p->nP, cb::SY_TILE);
   p->LD = p->n_blk * cb::SY_TILE;
   p->n_tiles = p->n_blk * (p->n_blk + 1) / 2;
@@ -1166,12 +1396,9 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
 
   const int n = p->n_obs;
   // tables
-  CB_TRY(palloc(p, &p->d_cam_off, p->n_cams + 1));
+  CB_TRY(palloc(p, &p->d_cam_xoff, p->n_cams)); CB_TRY(palloc(p, &p->d_cam_slot, p->n_cams));
   CB_TRY(palloc(p, &p->d_cam_flags, p->n_cams));
   CB_TRY(palloc(p, &p->d_cam_const, (size_t)p->n_cams * 9));
-  CB_CUDA(cudaMemcpyAsync(p->d_cam_off, p->h_cam_off.data(), sizeof(int) * (p->n_cams + 1), cudaMemcpyHostToDevice, st));
-  CB_CUDA(cudaMemcpyAsync(p->d_cam_flags, d->cam_flags, sizeof(int) * p->n_cams, cudaMemcpyHostToDevice, st));
-  CB_CUDA(cudaMemcpyAsync(p->d_cam_const, d->cam_const, sizeof(double) * 9 * p->n_cams, cudaMemcpyHostToDevice, st));
   CB_TRY(palloc(p, &p->d_cm_xy, n)); CB_TRY(palloc(p, &p->d_cm_pt, n)); CB_TRY(palloc(p, &p->d_pm_xy, n));
   CB_TRY(palloc(p, &p->d_cm_orig, n)); CB_TRY(palloc(p, &p->d_cam_start, p->n_cams + 1));
   CB_TRY(palloc(p, &p->d_cam_chunk_start, p->n_cams + 1));
@@ -1201,76 +1428,30 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
   p->d_obs_cam = d_cam; p->d_obs_pt = d_pt; p->d_obs_xy = d_xy;
   p->h_cam_flags.assign(d->cam_flags, d->cam_flags + p->n_cams);
   p->h_cam_const.assign(d->cam_const, d->cam_const + 9 * (size_t)p->n_cams);
-  int rc = build_indices(p, d_cam, d_pt, d_xy, st, xy_ready);
+  int rc = build_indices(p, d_cam, d_pt, d_xy, d->cam_order, st, xy_ready);
   if (xy_ready) cudaEventDestroy(xy_ready);
   CB_TRY(rc);
-
-  // Schur work items: off-diagonal tiles and pairs of diagonal tiles, each split over k so that the
-  // grid is one CTA per SM with equal DMMA work (a diagonal pair costs 45/36 of a full tile per chunk).
+  // camera tables by internal slot
   {
-    const int nb = p->n_blk;
-    std::vector<int> tof((size_t)nb * nb, -1);
-    int nt = 0;
-    for (int I = 0; I < nb; ++I)
-      for (int J = I; J < nb; ++J) tof[(size_t)I * nb + J] = nt++;
-    struct Group { int kind, I, J; double w; };
-    std::vector<Group> groups;
-    for (int I = 0; I < nb; ++I)
-      for (int J = I + 1; J < nb; ++J) groups.push_back({0, I, J, 1.0});
-    double w_pair = 1.55;  // measured cost of a diagonal-pair CTA per k chunk relative to an off-diagonal one
-    if (const char* ev = std::getenv("CB_SY_PAIR_W")) w_pair = std::atof(ev);
-    for (int I = 0; I < nb; I += 2) {
-      if (I + 1 < nb) groups.push_back({1, I, I + 1, w_pair});
-      else groups.push_back({1, I, -1, 0.75});
+    std::vector<int> xoff(p->n_cams);
+    std::vector<double> iconst((size_t)p->n_cams * 9);
+    p->h_iflags.resize(p->n_cams);
+    for (int i = 0; i < p->n_cams; ++i) {
+      const int c = p->h_perm[i];
+      xoff[i] = p->h_cam_off[c];
+      p->h_iflags[i] = d->cam_flags[c];
+      std::memcpy(&iconst[(size_t)i * 9], d->cam_const + (size_t)c * 9, 9 * sizeof(double));
     }
-    double W = 0.0;
-    for (auto& g : groups) W += g.w;
-    std::vector<cb::SyItem> items;
-    std::vector<std::vector<int>> slots_of(nt);
-    int slot = 0;
-    for (auto& g : groups) {
-      int n = (int)std::floor(p->num_sms * g.w / W);
-      n = std::max(1, std::min(n, p->k_chunks));
-      for (int s = 0; s < n; ++s) {
-        cb::SyItem it;
-        it.kind = g.kind; it.I = g.I; it.J = g.J;
-        it.c0 = (int)(((long long)p->k_chunks * s) / n);
-        it.c1 = (int)(((long long)p->k_chunks * (s + 1)) / n);
-        it.slotA = slot++;
-        it.slotB = -1;
-        if (g.kind == 0) {
-          slots_of[tof[(size_t)g.I * nb + g.J]].push_back(it.slotA);
-        } else {
-          slots_of[tof[(size_t)g.I * nb + g.I]].push_back(it.slotA);
-          if (g.J >= 0) {
-            it.slotB = slot++;
-            slots_of[tof[(size_t)g.J * nb + g.J]].push_back(it.slotB);
-          }
-        }
-        items.push_back(it);
-      }
-    }
-    p->n_items = (int)items.size();
-    p->n_slots = slot;
-    std::vector<int> sstart(nt + 1, 0), sflat;
-    for (int t = 0; t < nt; ++t) {
-      sstart[t] = (int)sflat.size();
-      sflat.insert(sflat.end(), slots_of[t].begin(), slots_of[t].end());
-    }
-    sstart[nt] = (int)sflat.size();
-    CB_TRY(palloc(p, &p->d_items, items.size()));
-    CB_TRY(palloc(p, &p->d_tile_of, tof.size()));
-    CB_TRY(palloc(p, &p->d_tile_slot_start, sstart.size()));
-    CB_TRY(palloc(p, &p->d_tile_slots, sflat.size()));
-    CB_CUDA(cudaMemcpyAsync(p->d_items, items.data(), sizeof(cb::SyItem) * items.size(), cudaMemcpyHostToDevice, st));
-    CB_CUDA(cudaMemcpyAsync(p->d_tile_of, tof.data(), sizeof(int) * tof.size(), cudaMemcpyHostToDevice, st));
-    CB_CUDA(cudaMemcpyAsync(p->d_tile_slot_start, sstart.data(), sizeof(int) * sstart.size(), cudaMemcpyHostToDevice, st));
-    CB_CUDA(cudaMemcpyAsync(p->d_tile_slots, sflat.data(), sizeof(int) * sflat.size(), cudaMemcpyHostToDevice, st));
-    CB_CUDA(cudaStreamSynchronize(st));  // the host vectors above go out of scope
+    CB_CUDA(cudaMemcpyAsync(p->d_cam_xoff, xoff.data(), sizeof(int) * p->n_cams, cudaMemcpyHostToDevice, st));
+    CB_CUDA(cudaMemcpyAsync(p->d_cam_flags, p->h_iflags.data(), sizeof(int) * p->n_cams, cudaMemcpyHostToDevice, st));
+    CB_CUDA(cudaMemcpyAsync(p->d_cam_const, iconst.data(), sizeof(double) * 9 * p->n_cams, cudaMemcpyHostToDevice, st));
+    CB_CUDA(cudaStreamSynchronize(st));
   }
+
+  CB_TRY(build_schur_items(p, st));
   std::vector<unsigned char> act((size_t)p->nP, 0);
   for (int c = 0; c < p->n_cams; ++c)
-    for (int a = 0; a < p->h_cam_off[c + 1] - p->h_cam_off[c]; ++a) act[(size_t)c * p->P + a] = 1;
+    for (int a = 0; a < ((p->h_iflags[c] & CB_CAM_FREE_INTRINSICS) ? 9 : 6); ++a) act[(size_t)c * p->P + a] = 1;
   CB_TRY(palloc(p, &p->d_active, p->nP));
   CB_CUDA(cudaMemcpyAsync(p->d_active, act.data(), p->nP, cudaMemcpyHostToDevice, st));
   CB_CUDA(cudaStreamSynchronize(st));
@@ -1291,8 +1472,9 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
   CB_TRY(palloc(p, &p->d_gpt, 3 * npts));
   CB_TRY(palloc(p, &p->d_V6, 6 * npts)); CB_TRY(palloc(p, &p->d_gp, 3 * npts)); CB_TRY(palloc(p, &p->d_Dp2, 3 * npts));
   CB_TRY(palloc(p, &p->d_Dc2, p->nP)); CB_TRY(palloc(p, &p->d_Linv6, 6 * npts));
-  CB_TRY(palloc(p, &p->d_tvec, (size_t)p->K_pad));
-  CB_TRY(palloc(p, &p->d_Zt, (size_t)p->K_pad * p->LD));
+  // + one chunk of rows that stay zero for good: the padding target of the compacted k-lists
+  CB_TRY(palloc(p, &p->d_tvec, (size_t)p->K_pad + cb::SY_KC));
+  CB_TRY(palloc(p, &p->d_Zt, ((size_t)p->K_pad + cb::SY_KC) * p->LD));
   CB_TRY(palloc(p, &p->d_part, (size_t)p->n_slots * cb::SY_TILE * cb::SY_TILE));
   CB_TRY(palloc(p, &p->d_tpart, (size_t)p->n_slots * cb::SY_TILE));
   CB_TRY(palloc(p, &p->d_red, p->red_len()));
@@ -1305,8 +1487,8 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
   CB_TRY(palloc(p, &p->d_state, 1));
   CB_TRY(palloc(p, &p->d_log, (size_t)p->log_cap));
   CB_TRY(palloc(p, &p->d_out2, 2 * (size_t)std::max(n, 1)));
-  CB_CUDA(cudaMemsetAsync(p->d_Zt, 0, sizeof(double) * (size_t)p->K_pad * p->LD, st));
-  CB_CUDA(cudaMemsetAsync(p->d_tvec, 0, sizeof(double) * p->K_pad, st));
+  CB_CUDA(cudaMemsetAsync(p->d_Zt, 0, sizeof(double) * ((size_t)p->K_pad + cb::SY_KC) * p->LD, st));
+  CB_CUDA(cudaMemsetAsync(p->d_tvec, 0, sizeof(double) * ((size_t)p->K_pad + cb::SY_KC), st));
   CB_CUDA(cudaMemsetAsync(p->d_tpart, 0, sizeof(double) * (size_t)p->n_slots * cb::SY_TILE, st));
   CB_CUDA(cudaMemsetAsync(p->d_part, 0, sizeof(double) * (size_t)p->n_slots * cb::SY_TILE * cb::SY_TILE, st));
   CB_CUDA(cudaMemsetAsync(p->d_red2, 0, sizeof(double) * 8, st));
@@ -1385,6 +1567,11 @@ int cb_ba_solve(CbBaProblem* p, const CbBaOptions* opt, double* x_inout, CbBaRes
     }
     p->peer = g;
   }
+  if (sharded(opt) && p->order_auto && !p->order_identity) {
+    g_last_error = "sharded solve on a problem whose camera order was chosen from this rank's observations only: pass "
+                   "CbBaProblemDesc.cam_order (the same on every rank)";
+    return CB_E_INVALID;
+  }
   const int rc = p->P == 6 ? lm_solve<6>(p, opt, x_inout, result, st) : lm_solve<9>(p, opt, x_inout, result, st);
   p->peer = nullptr;
   return rc;
@@ -1433,11 +1620,11 @@ int cb_ba_jacobian_blocks(CbBaProblem* p, const double* x, double* Jc, double* J
   CB_TRY(dalloc(&dJp, 6 * (size_t)std::max(n, 1)));
   if (p->P == 6) {
     CB_TRY(run_cam_prep<6>(p, p->d_xc[0], p->d_camtab[0], st));
-    if (n) CB_LAUNCH((cb::jac_blocks_kernel<6>), cdiv(n, 128), 128, 0, st, p->d_obs_cam, p->d_obs_pt,
+    if (n) CB_LAUNCH((cb::jac_blocks_kernel<6>), cdiv(n, 128), 128, 0, st, p->d_obs_cam, (const int*)p->d_cam_slot, p->d_obs_pt,
                      reinterpret_cast<const double2*>(p->d_obs_xy), n, (const double*)p->d_camtab[0], (const double*)p->d_xp4[0], dJc, dJp);
   } else {
     CB_TRY(run_cam_prep<9>(p, p->d_xc[0], p->d_camtab[0], st));
-    if (n) CB_LAUNCH((cb::jac_blocks_kernel<9>), cdiv(n, 128), 128, 0, st, p->d_obs_cam, p->d_obs_pt,
+    if (n) CB_LAUNCH((cb::jac_blocks_kernel<9>), cdiv(n, 128), 128, 0, st, p->d_obs_cam, (const int*)p->d_cam_slot, p->d_obs_pt,
                      reinterpret_cast<const double2*>(p->d_obs_xy), n, (const double*)p->d_camtab[0], (const double*)p->d_xp4[0], dJc, dJp);
   }
   cudaError_t e1 = cudaMemcpyAsync(Jc, dJc, sizeof(double) * 18 * (size_t)n, cudaMemcpyDeviceToHost, st);
@@ -1478,15 +1665,30 @@ int normal_eq_impl(CbBaProblem* p, const double* x, double lam, int loss, double
   if (dp) CB_CUDA(cudaMemcpyAsync(dp, p->d_dp, sizeof(double) * 3 * (size_t)p->n_pts, cudaMemcpyDeviceToHost, st));
   CB_CUDA(cudaStreamSynchronize(st));
   if (cost) *cost = hS[nn + 3 * (size_t)p->nP];
-  if (S) std::memcpy(S, hS.data(), sizeof(double) * nn);
-  if (b) std::memcpy(b, hS.data() + nn, sizeof(double) * p->nP);
+  // reduced system back in the caller's camera order
+  const int nP = p->nP;
+  if (S)
+    for (int i = 0; i < nP; ++i)
+      for (int j = 0; j < nP; ++j)
+        S[((size_t)p->h_perm[i / P] * P + i % P) * nP + (size_t)p->h_perm[j / P] * P + j % P] = hS[(size_t)i * nP + j];
+  if (b)
+    for (int i = 0; i < nP; ++i) b[(size_t)p->h_perm[i / P] * P + i % P] = hS[nn + i];
+  if (!p->order_identity) {
+    std::vector<double> tmp(nP);
+    for (double* v : {gc, dc})
+      if (v) {
+        std::memcpy(tmp.data(), v, sizeof(double) * nP);
+        for (int i = 0; i < nP; ++i) v[(size_t)p->h_perm[i / P] * P + i % P] = tmp[i];
+      }
+  }
   if (U)
-    for (int c = 0; c < p->n_cams; ++c) {
+    for (int i = 0; i < p->n_cams; ++i) {
+      const int c = p->h_perm[i];
       int u = 0;
       for (int a = 0; a < P; ++a)
         for (int bb = a; bb < P; ++bb, ++u) {
-          U[((size_t)c * P + a) * P + bb] = hU[(size_t)c * RT::NU + u];
-          U[((size_t)c * P + bb) * P + a] = hU[(size_t)c * RT::NU + u];
+          U[((size_t)c * P + a) * P + bb] = hU[(size_t)i * RT::NU + u];
+          U[((size_t)c * P + bb) * P + a] = hU[(size_t)i * RT::NU + u];
         }
     }
   if (V)
@@ -1620,13 +1822,17 @@ int cb_ba_error_order_stats(CbBaProblem* p, const double* x, double q_percent, d
     cudaMemcpyAsync(err, p->d_out2 + n, sizeof(double) * n, cudaMemcpyDeviceToHost, st);
   }
   std::vector<long long> hc(p->n_cams);
-  cudaMemcpyAsync(lo, d_lo, sizeof(double) * p->n_cams, cudaMemcpyDeviceToHost, st);
-  cudaMemcpyAsync(hi, d_hi, sizeof(double) * p->n_cams, cudaMemcpyDeviceToHost, st);
+  std::vector<double> hlo(p->n_cams), hhi(p->n_cams);
+  cudaMemcpyAsync(hlo.data(), d_lo, sizeof(double) * p->n_cams, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(hhi.data(), d_hi, sizeof(double) * p->n_cams, cudaMemcpyDeviceToHost, st);
   cudaMemcpyAsync(hc.data(), d_cnt, sizeof(long long) * p->n_cams, cudaMemcpyDeviceToHost, st);
   cudaError_t e = cudaStreamSynchronize(st);
   cached_free(d_lo); cached_free(d_hi); cached_free(d_cnt);
   CB_CUDA(e);
-  for (int c = 0; c < p->n_cams; ++c) count[c] = hc[c];
+  for (int i = 0; i < p->n_cams; ++i) {  // internal slot -> caller's camera index
+    const int c = p->h_perm[i];
+    count[c] = hc[i]; lo[c] = hlo[i]; hi[c] = hhi[i];
+  }
   return CB_OK;
 }
 
@@ -1800,7 +2006,7 @@ int cb_ba_rmse_px(CbBaProblem* p, const double* x, double* overall, double* per_
   for (int c = 0; c < p->n_cams; ++c) {
     tot += ss[c];
     const int nc = cs[c + 1] - cs[c];
-    if (per_camera) per_camera[c] = nc > 0 ? std::sqrt(ss[c] / nc) : 0.0;
+    if (per_camera) per_camera[p->h_perm[c]] = nc > 0 ? std::sqrt(ss[c] / nc) : 0.0;
   }
   *overall = p->n_obs > 0 ? std::sqrt(tot / p->n_obs) : 0.0;
   return CB_OK;
@@ -1830,7 +2036,8 @@ int cb_ba_cull(CbBaProblem* p, const double* x, const double* thresholds, int32_
   CB_TRY(dalloc(&d_iota, n)); sf.dev.push_back(d_iota);
   CB_TRY(dalloc(&d_sel, n)); sf.dev.push_back(d_sel);
   CB_TRY(dalloc(&d_nsel, 1)); sf.dev.push_back(d_nsel);
-  std::vector<double> thr(thresholds, thresholds + nc);
+  std::vector<double> thr(nc);
+  for (int i = 0; i < nc; ++i) thr[i] = thresholds[p->h_perm[i]];  // by internal camera slot
   std::vector<long long> kept(nc);
   std::vector<int> cs(nc + 1);
   CB_CUDA(cudaMemcpyAsync(d_thr, thr.data(), sizeof(double) * nc, cudaMemcpyHostToDevice, st));
@@ -1887,6 +2094,8 @@ int cb_ba_cull(CbBaProblem* p, const double* x, const double* thresholds, int32_
     d2.n_cams = nc; d2.n_pts = p->n_pts; d2.n_obs = nsel;
     d2.cam_flags = p->h_cam_flags.data(); d2.cam_const = p->h_cam_const.data();
     d2.obs_cam = c_cam; d2.obs_pt = c_pt; d2.obs_xy = c_xy; d2.obs_on_device = 1;
+    d2.pad_ = 0;
+    d2.cam_order = p->h_perm.data();  // the filtered problem keeps this problem's camera order
     CbBaProblem* q = new CbBaProblem();
     q->allocs.push_back(c_cam); q->allocs.push_back(c_pt); q->allocs.push_back(c_xy);  // owned by the new problem
     rc = problem_create_impl(&d2, p->device, st, q);
@@ -1903,6 +2112,7 @@ int cb_ba_cull(CbBaProblem* p, const double* x, const double* thresholds, int32_
         cb_ba_problem_destroy(q);
         g_last_error = keep;
       } else {
+        q->order_auto = p->order_auto;
         *out = q;
       }
     }

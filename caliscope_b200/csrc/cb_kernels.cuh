@@ -44,16 +44,18 @@ enum {
 };
 
 // ---------------------------------------------------------------------------------------------
-__global__ void unpack_x_kernel(const double* __restrict__ x, const int* __restrict__ cam_off,
+// x (BundleParameterization.pack layout, caller's camera order) <-> engine buffers.  Internal camera slot i holds the
+// caller's camera whose block starts at cam_xoff[i] (the engine may reorder cameras so that cameras that see the same
+// points share Schur tiles); its width is 9 with free intrinsics, else 6.
+__global__ void unpack_x_kernel(const double* __restrict__ x, const int* __restrict__ cam_xoff,
                                 const int* __restrict__ cam_flags, const double* __restrict__ cam_const,
-                                int n_cams, int P, int n_pts, double* __restrict__ xc, double* __restrict__ xp4) {
+                                int n_cams, int P, int n_pts, int ncp, double* __restrict__ xc, double* __restrict__ xp4) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int ncp = cam_off[n_cams];
   if (i < n_cams * P) {
     int c = i / P, p = i % P;
-    int w = cam_off[c + 1] - cam_off[c];
+    int w = (cam_flags[c] & 1) ? 9 : 6;
     double v;
-    if (p < w) v = x[cam_off[c] + p];
+    if (p < w) v = x[cam_xoff[c] + p];
     else v = (p == 6) ? 1.0 : cam_const[c * 9 + 4 + (p - 7)];  // s = 1, k1_initial, k2_initial
     xc[i] = v;
   }
@@ -65,13 +67,13 @@ __global__ void unpack_x_kernel(const double* __restrict__ x, const int* __restr
   }
 }
 
-__global__ void pack_x_kernel(double* __restrict__ x, const int* __restrict__ cam_off, int n_cams, int P, int n_pts,
-                              const double* __restrict__ xc, const double* __restrict__ xp4) {
+__global__ void pack_x_kernel(double* __restrict__ x, const int* __restrict__ cam_xoff, const int* __restrict__ cam_flags,
+                              int n_cams, int P, int n_pts, int ncp, const double* __restrict__ xc,
+                              const double* __restrict__ xp4) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int ncp = cam_off[n_cams];
   if (i < n_cams * P) {
     int c = i / P, p = i % P;
-    if (p < cam_off[c + 1] - cam_off[c]) x[cam_off[c] + p] = xc[i];
+    if (p < ((cam_flags[c] & 1) ? 9 : 6)) x[cam_xoff[c] + p] = xc[i];
   }
   if (i < n_pts) {
     x[ncp + 3 * (size_t)i + 0] = xp4[4 * (size_t)i + 0];
@@ -299,7 +301,8 @@ __global__ void sum_kernel(const double* __restrict__ in, int n, double* __restr
 // Jacobian blocks in caller order for the test / diagnostic entry point cb_ba_jacobian_blocks:
 // Jc (n_obs, 2, 9) with zeros beyond the camera's width, Jp (n_obs, 2, 3)   [== joint_jacobian's non-zeros]
 template <int P>
-__global__ void jac_blocks_kernel(const int* __restrict__ obs_cam, const int* __restrict__ obs_pt,
+__global__ void jac_blocks_kernel(const int* __restrict__ obs_cam, const int* __restrict__ cam_slot,
+                                  const int* __restrict__ obs_pt,
                                   const double2* __restrict__ obs_xy, int n, const double* __restrict__ camtab,
                                   const double* __restrict__ xp4, double* __restrict__ Jc_out,
                                   double* __restrict__ Jp_out) {
@@ -308,7 +311,7 @@ __global__ void jac_blocks_kernel(const int* __restrict__ obs_cam, const int* __
   const double* X = xp4 + 4 * (size_t)obs_pt[i];
   const double2 xy = obs_xy[i];
   double f[2], JX[6], Jc[2 * P];
-  obs_jac<P>(camtab + (size_t)obs_cam[i] * CT_SIZE, X[0], X[1], X[2], xy.x, xy.y, 0, 1.0, f, JX, Jc);
+  obs_jac<P>(camtab + (size_t)cam_slot[obs_cam[i]] * CT_SIZE, X[0], X[1], X[2], xy.x, xy.y, 0, 1.0, f, JX, Jc);
   for (int k = 0; k < 6; ++k) Jp_out[(size_t)i * 6 + k] = JX[k];
   for (int r = 0; r < 2; ++r)
     for (int p = 0; p < 9; ++p) Jc_out[(size_t)i * 18 + r * 9 + p] = (p < P) ? Jc[r * P + p] : 0.0;
@@ -368,8 +371,10 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 struct SyItem {
   int kind;    // 0: off-diagonal tile, 1: diagonal pair (I2 < 0: single diagonal tile)
   int I, J;    // kind 0: tile (I, J); kind 1: tiles (I, I) and (J, J) with J = I2
-  int c0, c1;  // k-chunk range
+  int c0, c1;  // k-chunk range (chunks of SY_KC rows; of the item's k-list when koff >= 0, of 0..K_pad otherwise)
   int slotA, slotB;  // partial-output slots (kind 0 uses slotA only)
+  int koff;    // >= 0: offset of this item's compacted row list in `klist` (only the rows k = 3*point + axis of points
+               // seen by cameras of BOTH column tiles; padded with the index of an all-zero row); -1: all rows
 };
 
 // Fragment ownership (PTX m8n8k4.f64): A[row = lane>>2][k = lane&3], B[k = lane&3][col = lane>>2],
@@ -386,8 +391,8 @@ __constant__ signed char SY_DIAG_BLOCKS[8][3][3] = {
 
 __global__ void __launch_bounds__(SY_THREADS, 1)
 schur_syrk_kernel(const LmState* __restrict__ st, const double* __restrict__ Zt, size_t LD,
-                  const double* __restrict__ tvec, const SyItem* __restrict__ items, double* __restrict__ part,
-                  double* __restrict__ tpart) {
+                  const double* __restrict__ tvec, const SyItem* __restrict__ items, const int* __restrict__ klist,
+                  double* __restrict__ part, double* __restrict__ tpart) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SyrkSmem& sm = *reinterpret_cast<SyrkSmem*>(smem_raw);
   if (st->done) return;
@@ -407,7 +412,7 @@ schur_syrk_kernel(const LmState* __restrict__ st, const double* __restrict__ Zt,
   __syncthreads();
 
   const uint32_t row_bytes = SY_TILE * 8;
-  const uint32_t stage_bytes = SY_KC * row_bytes * (two ? 2u : 1u) + (diag ? SY_KC * 8u : 0u);
+  const uint32_t stage_bytes = SY_KC * row_bytes * (two ? 2u : 1u);
   const int n_it = item.c1 - item.c0;
 
   if (wid == SY_CONSUMER_WARPS) {
@@ -415,14 +420,19 @@ schur_syrk_kernel(const LmState* __restrict__ st, const double* __restrict__ Zt,
     for (int it = 0; it < n_it; ++it) {
       const int stage = it % SY_STAGES, round = it / SY_STAGES;
       if (round > 0) mbar_wait(&sm.empty[stage], (uint32_t)((round - 1) & 1));
+      // row of this lane: straight through k, or through the item's compacted list (rows of points that both
+      // column tiles see; everything else would multiply structural zeros)
+      const size_t k = item.koff >= 0 ? (size_t)klist[(size_t)item.koff + (size_t)(item.c0 + it) * SY_KC + lane]
+                                      : (size_t)(item.c0 + it) * SY_KC + lane;
+      // t rides along as a plain shared-memory store: ordered before lane 0's arrive (release) by the warp barrier,
+      // visible to the consumers after their acquire on `full`
+      if (diag) sm.t[stage][lane] = tvec[k];
+      __syncwarp();
       if (lane == 0) mbar_expect_tx(&sm.full[stage], stage_bytes);
       __syncwarp();
-      const size_t k = (size_t)(item.c0 + it) * SY_KC + lane;
       bulk_g2s(&sm.A[stage][lane * SY_LDS], Zt + k * LD + (size_t)item.I * SY_TILE, row_bytes, &sm.full[stage]);
       if (two)
         bulk_g2s(&sm.B[stage][lane * SY_LDS], Zt + k * LD + (size_t)item.J * SY_TILE, row_bytes, &sm.full[stage]);
-      if (diag && lane == 0)
-        bulk_g2s(&sm.t[stage][0], tvec + (size_t)(item.c0 + it) * SY_KC, SY_KC * 8, &sm.full[stage]);
     }
     return;
   }
@@ -877,6 +887,42 @@ __global__ void cm_gather_kernel(const int* __restrict__ cm_pos, const int* __re
     cm_orig[q] = o;
     cm_xy[q] = obs_xy[o];
   }
+}
+// caller's camera id -> internal slot, in place
+__global__ void remap_kernel(int* __restrict__ a, const int* __restrict__ map, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = map[a[i]];
+}
+// co-visibility counts over a sample of points (one warp per sampled point): W[a][b] += 1 for every pair of cameras
+// that see it.  Only used to choose the internal camera order of sparse rigs.
+__global__ void covis_kernel(const int* __restrict__ pt_start, const int* __restrict__ pm_cam, int n_pts, int stride,
+                             int n_cams, unsigned int* __restrict__ W) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const long long j = (long long)w * stride;
+  if (j >= n_pts) return;
+  const int s = pt_start[j], e = min(pt_start[j + 1], s + 256);
+  for (int a = s + lane; a < e; a += 32) {
+    const int ca = pm_cam[a];
+    if (a > s && pm_cam[a - 1] == ca) continue;
+    for (int b = s; b < e; ++b) {
+      const int cb = pm_cam[b];
+      if (b > s && pm_cam[b - 1] == cb) continue;
+      atomicAdd(&W[(size_t)ca * n_cams + cb], 1u);
+    }
+  }
+}
+// per point: bit I set iff some camera that sees the point owns a column of Schur tile I (pm_cam holds internal slots)
+__global__ void pt_tile_mask_kernel(const int* __restrict__ pt_start, const int* __restrict__ pm_cam, int n_pts, int P,
+                                    unsigned long long* __restrict__ mask) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_pts) return;
+  unsigned long long m = 0ull;
+  for (int pos = pt_start[j]; pos < pt_start[j + 1]; ++pos) {
+    const int c0 = pm_cam[pos] * P;
+    m |= 1ull << (c0 / SY_TILE);
+    m |= 1ull << ((c0 + P - 1) / SY_TILE);
+  }
+  mask[j] = m;
 }
 // point-major pixel list
 __global__ void pm_gather_kernel(const int* __restrict__ pm_orig, const double2* __restrict__ obs_xy, int n,

@@ -130,6 +130,44 @@ def shard_points(obs_cam, obs_pt, obs_xy, n_pts: int, rank: int, world_size: int
     return shard
 
 
+def camera_order(obs_cam, obs_pt, n_cams: int, n_pts: int, cam_stride: int = 6, tile: int = 96) -> np.ndarray:
+    """Internal camera order for a SHARDED solve (``CbBaProblemDesc.cam_order``: slot -> camera), computed from the
+    whole observation list so that every rank lays the reduced camera system out identically.  Same rule as the
+    engine's own choice (``choose_camera_order`` in csrc/cb_engine.cu): co-visibility counts over a sample of points,
+    greedy chain (next = the unplaced camera sharing most points with the cameras of the last tile), kept only if it
+    removes at least 20 % of the co-visibility mass that falls between different 96-column Schur tiles.  Dense
+    rigs get the identity."""
+    obs_cam = np.asarray(obs_cam, dtype=np.int64)
+    obs_pt = np.asarray(obs_pt, dtype=np.int64)
+    ident = np.arange(n_cams, dtype=np.int32)
+    per_tile = max(1, tile // cam_stride)
+    if n_cams * cam_stride <= 2 * tile or len(obs_cam) > n_pts * n_cams / 3.0:
+        return ident
+    stride = max(1, n_pts // 8192)
+    sel = (obs_pt % stride) == 0
+    M = np.zeros((n_pts // stride + 1, n_cams), dtype=np.float64)
+    M[obs_pt[sel] // stride, obs_cam[sel]] = 1.0
+    W = M.T @ M
+    np.fill_diagonal(W, 0.0)
+    order = [int(np.argmin(W.sum(axis=1)))]
+    placed = np.zeros(n_cams, bool)
+    placed[order[0]] = True
+    while len(order) < n_cams:
+        w = W[:, order[-per_tile:]].sum(axis=1)
+        w[placed] = -1.0
+        c = int(np.argmax(w))
+        order.append(c)
+        placed[c] = True
+    order = np.asarray(order, dtype=np.int32)
+
+    def off_mass(o):
+        t = np.empty(n_cams, np.int64)
+        t[o] = (np.arange(n_cams) * cam_stride) // tile
+        return W[t[:, None] != t[None, :]].sum()
+
+    return order if off_mass(order) < 0.8 * off_mass(ident) else ident
+
+
 def local_x(x_global: np.ndarray, n_camera_params: int, shard: PointShard) -> np.ndarray:
     pts = x_global[n_camera_params:].reshape(-1, 3)[shard.pt_index]
     return np.concatenate([x_global[:n_camera_params], pts.ravel()])
@@ -428,8 +466,9 @@ def solve_sharded(cam_flags, cam_const, n_pts, obs_cam, obs_pt, obs_xy, x0, *, d
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     shard = shard_points(obs_cam, obs_pt, obs_xy, n_pts, rank, world, constraints)
     ncp = int(np.where(np.asarray(cam_flags) & 1, 9, 6).sum())
+    order = camera_order(obs_cam, obs_pt, len(np.asarray(cam_flags)), n_pts, 9 if np.any(np.asarray(cam_flags) & 1) else 6)
     with BAProblem(cam_flags, cam_const, shard.n_pts, shard.obs_cam, shard.obs_pt, shard.obs_xy,
-                   constraints=shard.constraints, device=device) as prob:
+                   constraints=shard.constraints, device=device, cam_order=order) as prob:
         dist.barrier(group=group)  # ranks enter the first fused reduce together (the peer spin times out after 20 s)
         res = prob.solve(
             local_x(np.asarray(x0, dtype=np.float64), ncp, shard),

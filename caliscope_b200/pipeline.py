@@ -82,7 +82,9 @@ def solve_filter_resolve_sharded(cam_flags, cam_const, n_pts, obs_cam, obs_pt, o
         dist.all_reduce(acc, group=group)
         return float(np.sqrt(acc[0].item() / max(acc[1].item(), 1.0)))
 
-    with BAProblem(cam_flags, cam_const, shard.n_pts, shard.obs_cam, shard.obs_pt, shard.obs_xy, device=device) as prob:
+    order = D.camera_order(obs_cam, obs_pt, len(cam_flags), n_pts, 9 if np.any(cam_flags & 1) else 6)
+    with BAProblem(cam_flags, cam_const, shard.n_pts, shard.obs_cam, shard.obs_pt, shard.obs_xy, device=device,
+                   cam_order=order) as prob:
         dist.barrier(group=group)
         s1 = prob.solve(D.local_x(np.asarray(x0, dtype=np.float64), ncp, shard), ftol=ftol, **kw)
         stages.append(s1)

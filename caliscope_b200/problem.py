@@ -80,7 +80,7 @@ class BAProblem:
     """
 
     def __init__(self, cam_flags, cam_const, n_pts, obs_cam, obs_pt, obs_xy, *, constraints=None, device: int = 0,
-                 stream: int = 0):
+                 stream: int = 0, cam_order=None):
         """``constraints``: optional ``(groups_a (n_c,4), groups_b (n_c,4), distances (n_c,), weights (n_c,))`` --
         the rigid-distance rows of capture_volume.py:373-383 / reprojection.py:112-117."""
         lib = L.load()
@@ -111,9 +111,12 @@ class BAProblem:
         self.cam_offsets = np.concatenate([[0], np.cumsum(widths)]).astype(np.int64)
         self.n_camera_params = int(self.cam_offsets[-1])
         self.n_params = self.n_camera_params + 3 * self.n_pts
+        order = None if cam_order is None else np.ascontiguousarray(cam_order, dtype=np.int32)
+        if order is not None and order.shape != (self.n_cams,):
+            raise ValueError(f"cam_order must have shape ({self.n_cams},)")
         desc = L.ProblemDesc(
             self.n_cams, self.n_pts, n_obs, _ptr(self.cam_flags), _ptr(self.cam_const), ptrs[0], ptrs[1], ptrs[2],
-            1 if on_dev else 0,
+            1 if on_dev else 0, 0, _ptr(order) if order is not None else None,
         )  # fmt: skip
         h = C.c_void_p()
         L.check(lib.cb_ba_problem_create(C.byref(desc), self.device, C.c_void_p(stream), C.byref(h)), "problem_create")

@@ -74,6 +74,12 @@ typedef struct {
   const int32_t* obs_pt;
   const double* obs_xy;
   int32_t obs_on_device;
+  int32_t pad_;
+  /* Optional (NULL: the engine decides).  Internal camera order, host, n_cams entries: cam_order[slot] = camera index.
+   * Only the layout of the reduced camera system depends on it (cameras that see the same points should be neighbours,
+   * so that whole 96-column tile pairs of the Schur product are empty); no input or output of the ABI is reordered.
+   * Every rank of a sharded solve MUST pass the same order (caliscope_b200.distributed does). */
+  const int32_t* cam_order;
 } CbBaProblemDesc;
 
 /*
