@@ -1,0 +1,385 @@
+// Kernels of the extrinsic bootstrap: what produces the start vector of bundle adjustment.
+//
+//   pnp_ippe_kernel     == compute_camera_to_object_poses_pnp
+//                          (reference core/bootstrap_pose/pose_network_builder.py:211-330): one planar PnP per
+//                          (camera, sync_index, object) group with cv2.solvePnP(..., SOLVEPNP_IPPE) on undistorted
+//                          normalised points (:301-306), reprojection RMSE in the normalised plane (:314-318).
+//                          OpenCV is an un-vendored dependency; the published algorithms are restated: IPPE (Collins &
+//                          Bartoli, IJCV 2014) on the Harker-O'Leary homography (BMVC 2005), see oracle/ippe.py which is
+//                          pinned against cv2 to 1e-13.
+//   stereo_pairs_kernel == calculate_stereo_rmse_for_pair (:638-685) for ALL camera pairs at once: every pair of
+//                          observations of the same (sync, object, keypoint) from two cameras that have an aggregated
+//                          relative pose is triangulated from the two views (cv2.triangulatePoints: DLT, :668),
+//                          projected back into both (:672-676) and its squared residuals are emitted under the pair's id;
+//                          a stable sort + segmented sum gives sqrt(mean) per pair (:678-679).
+//
+// Both are latency / fp64-pipe bound (a few dependent 3x3 / 4x4 eigen-solves per group), not HBM bound: 28-36 algorithmic
+// bytes per observation against hundreds of dependent flops.
+#pragma once
+#include "cb_triangulate.cuh"
+
+namespace cb {
+
+constexpr int BS_THREADS = 256;
+
+// Eigenvector of the smallest eigenvalue of a symmetric 3x3 (cyclic Jacobi).
+__device__ __forceinline__ void sym3_min_eigvec(double a[3][3], double out[3]) {
+  double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+#pragma unroll 1
+  for (int sweep = 0; sweep < 16; ++sweep) {
+    const double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
+    const double dg = a[0][0] * a[0][0] + a[1][1] * a[1][1] + a[2][2] * a[2][2];
+    if (off <= 1e-36 * dg) break;
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int q = p + 1; q < 3; ++q) {
+        const double apq = a[p][q];
+        if (apq != 0.0) {
+          const double theta = (a[q][q] - a[p][p]) / (2.0 * apq);
+          const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+          const double c = rsqrt(t * t + 1.0), s = t * c;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const double akp = a[k][p], akq = a[k][q];
+            a[k][p] = c * akp - s * akq;
+            a[k][q] = s * akp + c * akq;
+          }
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const double apk = a[p][k], aqk = a[q][k];
+            a[p][k] = c * apk - s * aqk;
+            a[q][k] = s * apk + c * aqk;
+          }
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const double vkp = V[k][p], vkq = V[k][q];
+            V[k][p] = c * vkp - s * vkq;
+            V[k][q] = s * vkp + c * vkq;
+          }
+        }
+      }
+  }
+  int m = 0;
+  if (a[1][1] < a[m][m]) m = 1;
+  if (a[2][2] < a[m][m]) m = 2;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) out[k] = (m == 0) ? V[k][0] : (m == 1) ? V[k][1] : V[k][2];
+}
+
+__device__ __forceinline__ void mat3_mul(const double* A, const double* B, double* C) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+
+// status codes of a PnP group
+constexpr int PNP_OK = 0, PNP_TOO_FEW = 1, PNP_NON_PLANAR = 2, PNP_DEGENERATE = 3;
+
+// One warp per (camera, sync, object) group; rows[start[g] .. start[g+1]) index the caller's observation arrays.
+// obj: (n_obs, 3) object-frame coordinates (NaN z counts as 0, as the reference's nan_to_num), img: (n_obs, 2) undistorted
+// normalised coordinates already rounded to float32 (the undistortion kernel does that).  Outputs per group:
+// R (9, row-major), t (3), rmse, status, count, representative row.
+__global__ void __launch_bounds__(BS_THREADS)
+pnp_ippe_kernel(const int* __restrict__ start, const int* __restrict__ rows, const double* __restrict__ obj,
+                const double* __restrict__ img, int n_groups, int min_points, double* __restrict__ R_out,
+                double* __restrict__ t_out, double* __restrict__ rmse_out, int* __restrict__ status_out,
+                int* __restrict__ count_out, int* __restrict__ rep_out) {
+  const int lane = threadIdx.x & 31;
+  const long long g = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (g >= n_groups) return;
+  const int b = start[g], e = start[g + 1], n = e - b;
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  auto fail = [&](int code) {
+    if (lane == 0) {
+      for (int k = 0; k < 9; ++k) R_out[9 * g + k] = nan;
+      for (int k = 0; k < 3; ++k) t_out[3 * g + k] = nan;
+      rmse_out[g] = nan;
+      status_out[g] = code;
+      count_out[g] = n;
+      rep_out[g] = rows[b];
+    }
+  };
+  // float32 object coordinates (the reference casts obj_points to float32 before the call, :296)
+  auto ox = [&](int r, int k) {
+    double v = obj[3 * (size_t)r + k];
+    if (k == 2 && v != v) v = 0.0;
+    return (double)(float)v;
+  };
+  // ---- pass 0: means, z spread
+  double sx = 0, sy = 0, sz = 0, su = 0, sv = 0, zmin = 1e300, zmax = -1e300;
+  for (int i = b + lane; i < e; i += 32) {
+    const int r = rows[i];
+    double zraw = obj[3 * (size_t)r + 2];
+    if (zraw != zraw) zraw = 0.0;
+    sx += ox(r, 0); sy += ox(r, 1); sz += ox(r, 2);
+    su += img[2 * (size_t)r]; sv += img[2 * (size_t)r + 1];
+    zmin = fmin(zmin, zraw); zmax = fmax(zmax, zraw);
+  }
+  sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz); su = warp_sum(su); sv = warp_sum(sv);
+  zmax = warp_max(zmax); zmin = -warp_max(-zmin);
+  if (!(zmax - zmin < 1e-6)) { fail(PNP_NON_PLANAR); return; }  // np.ptp(z) < 1e-6 (:279)
+  if (n < min_points) { fail(PNP_TOO_FEW); return; }
+  const double mx = sx / n, my = sy / n, mz = sz / n, mu = su / n, mv = sv / n;
+  // ---- pass 1: isotropic scales
+  double ka = 0, kb = 0;
+  for (int i = b + lane; i < e; i += 32) {
+    const int r = rows[i];
+    const double ax = ox(r, 0) - mx, ay = ox(r, 1) - my, bu = img[2 * (size_t)r] - mu, bv = img[2 * (size_t)r + 1] - mv;
+    ka += ax * ax + ay * ay;
+    kb += bu * bu + bv * bv;
+  }
+  ka = warp_sum(ka); kb = warp_sum(kb);
+  if (!(ka > 0.0) || !(kb > 0.0)) { fail(PNP_DEGENERATE); return; }
+  const double betaA = sqrt(2.0 * n / ka), betaB = sqrt(2.0 * n / kb);
+  // normalised source A = betaA (obj - mean), target B = betaB (img - mean)
+#define BS_LOAD(r)                                                                                     \
+  const double A0 = betaA * (ox(r, 0) - mx), A1 = betaA * (ox(r, 1) - my);                            \
+  const double B0 = betaB * (img[2 * (size_t)(r)] - mu), B1 = betaB * (img[2 * (size_t)(r) + 1] - mv)
+  // ---- pass 2: means of C1..C4, A A^T
+  double c1 = 0, c2 = 0, c3 = 0, c4 = 0, a00 = 0, a01 = 0, a11 = 0;
+  for (int i = b + lane; i < e; i += 32) {
+    const int r = rows[i];
+    BS_LOAD(r);
+    c1 += -B0 * A0; c2 += -B0 * A1; c3 += -B1 * A0; c4 += -B1 * A1;
+    a00 += A0 * A0; a01 += A0 * A1; a11 += A1 * A1;
+  }
+  c1 = warp_sum(c1) / n; c2 = warp_sum(c2) / n; c3 = warp_sum(c3) / n; c4 = warp_sum(c4) / n;
+  a00 = warp_sum(a00); a01 = warp_sum(a01); a11 = warp_sum(a11);
+  const double det = a00 * a11 - a01 * a01;
+  if (!(fabs(det) > 0.0)) { fail(PNP_DEGENERATE); return; }
+  const double i00 = a11 / det, i01 = -a01 / det, i11 = a00 / det;
+  // ---- pass 3: A Mx, A My (2x3 each)
+  double amx[6] = {0, 0, 0, 0, 0, 0}, amy[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = b + lane; i < e; i += 32) {
+    const int r = rows[i];
+    BS_LOAD(r);
+    const double mxr[3] = {-B0 * A0 - c1, -B0 * A1 - c2, -B0}, myr[3] = {-B1 * A0 - c3, -B1 * A1 - c4, -B1};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      amx[k] += A0 * mxr[k]; amx[3 + k] += A1 * mxr[k];
+      amy[k] += A0 * myr[k]; amy[3 + k] += A1 * myr[k];
+    }
+  }
+  double Bx[6], By[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { amx[k] = warp_sum(amx[k]); amy[k] = warp_sum(amy[k]); }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    Bx[k] = i00 * amx[k] + i01 * amx[3 + k]; Bx[3 + k] = i01 * amx[k] + i11 * amx[3 + k];
+    By[k] = i00 * amy[k] + i01 * amy[3 + k]; By[3 + k] = i01 * amy[k] + i11 * amy[3 + k];
+  }
+  // ---- pass 4: D^T D with D rows = Mx_i - A_i^T Bx ; My_i - A_i^T By
+  double dd[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = b + lane; i < e; i += 32) {
+    const int r = rows[i];
+    BS_LOAD(r);
+    double d1[3], d2[3];
+    const double mxr[3] = {-B0 * A0 - c1, -B0 * A1 - c2, -B0}, myr[3] = {-B1 * A0 - c3, -B1 * A1 - c4, -B1};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      d1[k] = mxr[k] - (A0 * Bx[k] + A1 * Bx[3 + k]);
+      d2[k] = myr[k] - (A0 * By[k] + A1 * By[3 + k]);
+    }
+    dd[0] += d1[0] * d1[0] + d2[0] * d2[0]; dd[1] += d1[0] * d1[1] + d2[0] * d2[1]; dd[2] += d1[0] * d1[2] + d2[0] * d2[2];
+    dd[3] += d1[1] * d1[1] + d2[1] * d2[1]; dd[4] += d1[1] * d1[2] + d2[1] * d2[2]; dd[5] += d1[2] * d1[2] + d2[2] * d2[2];
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) dd[k] = warp_sum(dd[k]);
+  double M[3][3] = {{dd[0], dd[1], dd[2]}, {dd[1], dd[3], dd[4]}, {dd[2], dd[4], dd[5]}};
+  double h789[3];
+  sym3_min_eigvec(M, h789);
+  // normalised-frame homography, then H = TB^-1 Hn TA
+  double Hn[9];
+  Hn[0] = -(Bx[0] * h789[0] + Bx[1] * h789[1] + Bx[2] * h789[2]);
+  Hn[1] = -(Bx[3] * h789[0] + Bx[4] * h789[1] + Bx[5] * h789[2]);
+  Hn[2] = -(c1 * h789[0] + c2 * h789[1]);
+  Hn[3] = -(By[0] * h789[0] + By[1] * h789[1] + By[2] * h789[2]);
+  Hn[4] = -(By[3] * h789[0] + By[4] * h789[1] + By[5] * h789[2]);
+  Hn[5] = -(c3 * h789[0] + c4 * h789[1]);
+  Hn[6] = h789[0]; Hn[7] = h789[1]; Hn[8] = h789[2];
+  // canonical source frame = centred object points (mean removed), so TA = diag(betaA, betaA, 1) there
+  const double TA[9] = {betaA, 0, 0, 0, betaA, 0, 0, 0, 1};
+  const double TBi[9] = {1.0 / betaB, 0, mu, 0, 1.0 / betaB, mv, 0, 0, 1};
+  double T1[9], H[9];
+  mat3_mul(Hn, TA, T1);
+  mat3_mul(TBi, T1, H);
+  if (!(fabs(H[8]) > 0.0)) { fail(PNP_DEGENERATE); return; }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) H[k] /= H[8];
+  H[8] = 1.0;
+  // ---- the two IPPE rotations from the first-order behaviour of H at the origin
+  const double p = H[2], q = H[5];
+  const double j00 = H[0] - H[6] * p, j01 = H[1] - H[7] * p, j10 = H[3] - H[6] * q, j11 = H[4] - H[7] * q;
+  double Rv[9];
+  {
+    const double nrm = sqrt(p * p + q * q + 1.0), ax = p / nrm, ay = q / nrm, az = 1.0 / nrm;
+    const double d = 1.0 / (1.0 + az);  // az > 0
+    // rotation taking (p, q, 1) onto +z, transposed
+    Rv[0] = 1.0 - ax * ax * d; Rv[1] = -ax * ay * d;      Rv[2] = ax;
+    Rv[3] = -ax * ay * d;      Rv[4] = 1.0 - ay * ay * d; Rv[5] = ay;
+    Rv[6] = -ax;               Rv[7] = -ay;               Rv[8] = 1.0 - (ax * ax + ay * ay) * d;
+  }
+  const double b00 = Rv[0] - p * Rv[6], b01 = Rv[1] - p * Rv[7], b10 = Rv[3] - q * Rv[6], b11 = Rv[4] - q * Rv[7];
+  const double dti = 1.0 / (b00 * b11 - b01 * b10);
+  const double bi00 = dti * b11, bi01 = -dti * b01, bi10 = -dti * b10, bi11 = dti * b00;
+  const double A00 = bi00 * j00 + bi01 * j10, A01 = bi00 * j01 + bi01 * j11, A10 = bi10 * j00 + bi11 * j10,
+               A11 = bi10 * j01 + bi11 * j11;
+  const double ata00 = A00 * A00 + A01 * A01, ata01 = A00 * A10 + A01 * A11, ata11 = A10 * A10 + A11 * A11;
+  const double gamma = sqrt(0.5 * (ata00 + ata11 + sqrt((ata00 - ata11) * (ata00 - ata11) + 4.0 * ata01 * ata01)));
+  if (!(gamma > 0.0) || !(gamma == gamma)) { fail(PNP_DEGENERATE); return; }
+  const double r00 = A00 / gamma, r01 = A01 / gamma, r10 = A10 / gamma, r11 = A11 / gamma;
+  const double bb0 = sqrt(fmax(0.0, 1.0 - r00 * r00 - r10 * r10));
+  double bb1 = sqrt(fmax(0.0, 1.0 - r01 * r01 - r11 * r11));
+  if (-r00 * r01 - r10 * r11 < 0) bb1 = -bb1;
+  double Rs[2][9], ts[2][3], err[2];
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const double sg = s == 0 ? 1.0 : -1.0;
+    const double c0[3] = {r00, r10, sg * bb0}, c1v[3] = {r01, r11, sg * bb1};
+    const double c2v[3] = {c0[1] * c1v[2] - c0[2] * c1v[1], c0[2] * c1v[0] - c0[0] * c1v[2], c0[0] * c1v[1] - c0[1] * c1v[0]};
+    const double Rt[9] = {c0[0], c1v[0], c2v[0], c0[1], c1v[1], c2v[1], c0[2], c1v[2], c2v[2]};
+    mat3_mul(Rv, Rt, Rs[s]);
+  }
+  // ---- pass 5: translations (least squares), both candidates
+  {
+    double acc[2][3] = {{0, 0, 0}, {0, 0, 0}}, suu = 0, su1 = 0, sv1 = 0;
+    for (int i = b + lane; i < e; i += 32) {
+      const int r = rows[i];
+      const double X = ox(r, 0) - mx, Y = ox(r, 1) - my, u = img[2 * (size_t)r], v = img[2 * (size_t)r + 1];
+      su1 += u; sv1 += v; suu += u * u + v * v;
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const double* R = Rs[s];
+        const double rx = R[0] * X + R[1] * Y, ry = R[3] * X + R[4] * Y, rz = R[6] * X + R[7] * Y;
+        const double bx = u * rz - rx, by = v * rz - ry;
+        acc[s][0] += bx; acc[s][1] += by; acc[s][2] -= u * bx + v * by;
+      }
+    }
+    su1 = warp_sum(su1); sv1 = warp_sum(sv1); suu = warp_sum(suu);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) acc[s][k] = warp_sum(acc[s][k]);
+      // A^T A = [n 0 -su; 0 n -sv; -su -sv suu]: eliminate tx, ty
+      const double nn = (double)n;
+      const double den = suu - (su1 * su1 + sv1 * sv1) / nn;
+      const double tz = (acc[s][2] + (su1 * acc[s][0] + sv1 * acc[s][1]) / nn) / den;
+      ts[s][0] = (acc[s][0] + su1 * tz) / nn;
+      ts[s][1] = (acc[s][1] + sv1 * tz) / nn;
+      ts[s][2] = tz;
+    }
+  }
+  // ---- pass 6: reprojection error of both, best first
+  {
+    double e0 = 0, e1 = 0;
+    for (int i = b + lane; i < e; i += 32) {
+      const int r = rows[i];
+      const double X = ox(r, 0) - mx, Y = ox(r, 1) - my, u = img[2 * (size_t)r], v = img[2 * (size_t)r + 1];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const double* R = Rs[s];
+        const double xc = R[0] * X + R[1] * Y + ts[s][0], yc = R[3] * X + R[4] * Y + ts[s][1], zc = R[6] * X + R[7] * Y + ts[s][2];
+        const double du = u - xc / zc, dv = v - yc / zc;
+        if (s == 0) e0 += du * du + dv * dv; else e1 += du * du + dv * dv;
+      }
+    }
+    err[0] = warp_sum(e0); err[1] = warp_sum(e1);
+  }
+#undef BS_LOAD
+  const int best = (err[1] < err[0]) ? 1 : 0;
+  if (lane == 0) {
+    const double* R = Rs[best];
+    // canonical (centred, z = mean z) frame -> the caller's object frame: t - R mean
+    const double tx = ts[best][0] - (R[0] * mx + R[1] * my + R[2] * mz);
+    const double ty = ts[best][1] - (R[3] * mx + R[4] * my + R[5] * mz);
+    const double tz = ts[best][2] - (R[6] * mx + R[7] * my + R[8] * mz);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R_out[9 * g + k] = R[k];
+    t_out[3 * g] = tx; t_out[3 * g + 1] = ty; t_out[3 * g + 2] = tz;
+    rmse_out[g] = sqrt(err[best] / n);
+    status_out[g] = (R[0] == R[0] && tz == tz) ? PNP_OK : PNP_DEGENERATE;
+    count_out[g] = n;
+    rep_out[g] = rows[b];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Stereo RMSE of every camera pair.  Groups = rows sharing (sync, object, keypoint); pair_of[a * n_cams + b] (a < b) =
+// index of the pair's pose [R | t] (camera a at the origin, camera b = R X + t) or -1.  Each group emits one slot per
+// unordered pair of its rows (slot_start from an exclusive scan of n (n - 1) / 2): key = pair index (n_pairs = none),
+// value = squared residuals of the two views.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void stereo_slots_kernel(const int* __restrict__ start, int n_groups, long long* __restrict__ nslots) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  const long long n = start[g + 1] - start[g];
+  nslots[g] = n * (n - 1) / 2;
+}
+
+__device__ __forceinline__ double sq_res_f32(double nx, double ny, double px, double py) {
+  // the reference subtracts float32 projections from float32 points and squares in float32 (:678-679)
+  const float ex = (float)nx - (float)px, ey = (float)ny - (float)py;
+  return (double)(ex * ex) + (double)(ey * ey);
+}
+
+template <int LANES>
+__global__ void __launch_bounds__(BS_THREADS)
+stereo_pairs_kernel(const int* __restrict__ start, const int* __restrict__ rows, const int* __restrict__ obs_cam,
+                    const double* __restrict__ xy, int n_groups, const long long* __restrict__ slot_start, int n_cams,
+                    const int* __restrict__ pair_of, const double* __restrict__ pair_Rt, int n_pairs,
+                    int* __restrict__ key_out, double* __restrict__ val_out) {
+  const int lane = threadIdx.x & (LANES - 1);
+  const long long g = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / LANES;
+  if (g >= n_groups) return;
+  const int b = start[g], n = start[g + 1] - b;
+  const long long s0 = slot_start[g], np = (long long)n * (n - 1) / 2;
+  for (long long k = lane; k < np; k += LANES) {
+    // k -> (i, j), i < j, row-major over the strict upper triangle
+    int i = (int)((2.0 * n - 1.0 - sqrt((2.0 * n - 1.0) * (2.0 * n - 1.0) - 8.0 * (double)k)) * 0.5);
+    while ((long long)i * (2 * n - i - 1) / 2 > k) --i;
+    while ((long long)(i + 1) * (2 * n - i - 2) / 2 <= k) ++i;
+    const int j = (int)(k - (long long)i * (2 * n - i - 1) / 2) + i + 1;
+    int ra = rows[b + i], rb = rows[b + j];
+    int ca = obs_cam[ra], cb = obs_cam[rb];
+    if (ca > cb) { int t = ca; ca = cb; cb = t; t = ra; ra = rb; rb = t; }
+    int pid = (ca != cb) ? pair_of[(size_t)ca * n_cams + cb] : -1;
+    double val = 0.0;
+    if (pid >= 0) {
+      const double* Rt = pair_Rt + 12 * (size_t)pid;  // [R (9) | t (3)]
+      const double ax = xy[2 * (size_t)ra], ay = xy[2 * (size_t)ra + 1], bx = xy[2 * (size_t)rb], by = xy[2 * (size_t)rb + 1];
+      // DLT rows: x P[2] - P[0], y P[2] - P[1] for P1 = [I | 0], P2 = [R | t]
+      double r[4][4];
+      r[0][0] = -1; r[0][1] = 0; r[0][2] = ax; r[0][3] = 0;
+      r[1][0] = 0; r[1][1] = -1; r[1][2] = ay; r[1][3] = 0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        r[2][c] = bx * Rt[6 + c] - Rt[c];
+        r[3][c] = by * Rt[6 + c] - Rt[3 + c];
+      }
+      r[2][3] = bx * Rt[11] - Rt[9];
+      r[3][3] = by * Rt[11] - Rt[10];
+      double M[4][4];
+#pragma unroll
+      for (int p2 = 0; p2 < 4; ++p2)
+#pragma unroll
+        for (int q2 = 0; q2 < 4; ++q2) M[p2][q2] = r[0][p2] * r[0][q2] + r[1][p2] * r[1][q2] + r[2][p2] * r[2][q2] + r[3][p2] * r[3][q2];
+      double w[4];
+      sym4_min_eigvec(M, w);
+      // cv2.triangulatePoints returns float32 for float32 inputs; the reference divides in float32 (:669)
+      const float w3 = (float)w[3];
+      const double X = (double)((float)w[0] / w3), Y = (double)((float)w[1] / w3), Z = (double)((float)w[2] / w3);
+      const double pax = X / Z, pay = Y / Z;
+      const double xb = Rt[0] * X + Rt[1] * Y + Rt[2] * Z + Rt[9], yb = Rt[3] * X + Rt[4] * Y + Rt[5] * Z + Rt[10],
+                   zb = Rt[6] * X + Rt[7] * Y + Rt[8] * Z + Rt[11];
+      val = sq_res_f32(ax, ay, pax, pay) + sq_res_f32(bx, by, xb / zb, yb / zb);
+    } else {
+      pid = n_pairs;
+    }
+    key_out[s0 + k] = pid;
+    val_out[s0 + k] = val;
+  }
+}
+
+}  // namespace cb

@@ -25,6 +25,7 @@
 #include "cb_kernels.cuh"
 #include "cb_constraints.cuh"
 #include "cb_triangulate.cuh"
+#include "cb_bootstrap.cuh"
 #include "cb_peer.cuh"
 
 namespace {
@@ -2406,6 +2407,269 @@ int cb_undistort_triangulate(int32_t n_cams, const int32_t* cam_fisheye, const d
   CB_TRY(build_undist_table(n_cams, cam_fisheye, cam_k, cam_dist, tab));
   return triangulate_impl(n_cams, &tab, proj, n_obs, obs_cam, obs_key, obs_px, obs_on_device, max_groups, n_groups_out,
                           xyz_out, count_out, rep_row_out, camset_sig_out, stats, device, stream);
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// extrinsic bootstrap: batched planar PnP and stereo RMSE
+// ------------------------------------------------------------------------------------------
+namespace {
+
+// stable sort of the rows by key, group boundaries: d_rows (n), d_start (n_groups + 1)
+int group_by_key(const long long* d_key, int n, cudaStream_t st, ScopedFree& sf, int** d_rows, int** d_start, int* n_groups) {
+  const int TB = 256, G = cdiv(n, TB);
+  unsigned long long* k_out = nullptr;
+  int *v_in = nullptr, *v_out = nullptr, *d_head = nullptr, *d_gid = nullptr, *dstart = nullptr;
+  CB_TRY(dalloc(&k_out, (size_t)n)); sf.dev.push_back(k_out);
+  CB_TRY(dalloc(&v_in, (size_t)n)); sf.dev.push_back(v_in);
+  CB_TRY(dalloc(&v_out, (size_t)n)); sf.dev.push_back(v_out);
+  CB_TRY(dalloc(&d_head, (size_t)n)); sf.dev.push_back(d_head);
+  CB_TRY(dalloc(&d_gid, (size_t)n)); sf.dev.push_back(d_gid);
+  CB_TRY(dalloc(&dstart, (size_t)n + 1)); sf.dev.push_back(dstart);
+  size_t tb_sort = 0, tb_scan = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb_sort, (const unsigned long long*)d_key, k_out, v_in, v_out, n, 0, 64, st);
+  cub::DeviceScan::InclusiveSum(nullptr, tb_scan, d_head, d_gid, n, st);
+  void* d_tmp = nullptr;
+  size_t tb = std::max(tb_sort, tb_scan);
+  CB_TRY(cached_malloc(&d_tmp, std::max<size_t>(tb, 16)));
+  sf.dev.push_back(d_tmp);
+  CB_LAUNCH(cb::tri_iota_kernel, G, TB, 0, st, v_in, (long long)n);
+  CB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb, (const unsigned long long*)d_key, k_out, v_in, v_out, n, 0, 63, st));
+  g_launches.fetch_add(8);
+  CB_LAUNCH(cb::tri_heads_kernel, G, TB, 0, st, k_out, (long long)n, d_head);
+  CB_CUDA(cub::DeviceScan::InclusiveSum(d_tmp, tb, d_head, d_gid, n, st));
+  g_launches.fetch_add(2);
+  CB_LAUNCH(cb::tri_starts_kernel, G, TB, 0, st, d_head, d_gid, (long long)n, dstart);
+  CB_CUDA(cudaMemcpyAsync(n_groups, d_gid + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  *d_rows = v_out;
+  *d_start = dstart;
+  return CB_OK;
+}
+
+// pixels (host, double) -> device, undistorted to the normalised plane with the reference's float32 rounding
+int upload_undistorted(int32_t n_cams, const int32_t* cam_fisheye, const double* cam_k, const double* cam_dist, int n,
+                       const int* d_cam, const double* obs_px, ScopedFree& sf, cudaStream_t st, double** d_norm) {
+  std::vector<cb::UndistCam> tab;
+  CB_TRY(build_undist_table(n_cams, cam_fisheye, cam_k, cam_dist, tab));
+  cb::UndistCam* d_tab = nullptr;
+  CB_TRY(dalloc(&d_tab, (size_t)n_cams));
+  sf.dev.push_back(d_tab);
+  CB_CUDA(cudaMemcpy(d_tab, tab.data(), sizeof(cb::UndistCam) * n_cams, cudaMemcpyHostToDevice));
+  double* d_und = nullptr;
+  CB_TRY(dalloc(&d_und, 2 * (size_t)n));
+  sf.dev.push_back(d_und);
+  const float* d_px = nullptr;
+  CB_TRY(to_device_f32(obs_px, 2 * (size_t)n, &d_px, sf, st));
+  CB_LAUNCH(cb::undistort_kernel<float>, cdiv(n, 256), 256, 0, st, d_tab, d_cam, d_px, d_und, (long long)n, 0);
+  *d_norm = d_und;
+  return CB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cb_pnp_ippe(int32_t n_cams, const int32_t* cam_fisheye, const double* cam_k, const double* cam_dist, int64_t n_obs,
+                const int32_t* obs_cam, const int64_t* obs_key, const double* obs_px, const double* obs_obj,
+                int32_t min_points, int32_t max_groups, int32_t* n_groups_out, double* R_out, double* t_out,
+                double* rmse_out, int32_t* status_out, int32_t* count_out, int32_t* rep_row_out, CbTriStats* stats,
+                int device, void* stream) {
+  if (n_cams <= 0 || !cam_fisheye || !cam_k || !cam_dist || n_obs < 0 || n_obs > 0x7fffffffLL || !n_groups_out ||
+      max_groups < 0 || (n_obs > 0 && (!obs_cam || !obs_key || !obs_px || !obs_obj)) ||
+      (max_groups > 0 && (!R_out || !t_out || !rmse_out || !status_out || !count_out || !rep_row_out))) {
+    g_last_error = "cb_pnp_ippe: bad argument";
+    return CB_E_INVALID;
+  }
+  CB_TRY(select_device(device));
+  *n_groups_out = 0;
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+  if (n_obs == 0) return CB_OK;
+  const long long launches0 = g_launches.load();
+  cudaStream_t st = (cudaStream_t)stream;
+  ScopedFree sf;
+  const int n = (int)n_obs;
+  cudaEvent_t ev[4];
+  for (auto& e : ev) CB_CUDA(cudaEventCreate(&e));
+  struct EvGuard { cudaEvent_t* e; ~EvGuard() { for (int i = 0; i < 4; ++i) cudaEventDestroy(e[i]); } } evg{ev};
+  CB_CUDA(cudaEventRecord(ev[0], st));
+  const int* d_cam = nullptr;
+  const long long* d_key = nullptr;
+  const double* d_obj = nullptr;
+  CB_TRY(to_device(obs_cam, (size_t)n, 0, &d_cam, sf, st));
+  CB_TRY(to_device((const long long*)obs_key, (size_t)n, 0, &d_key, sf, st));
+  CB_TRY(to_device(obs_obj, 3 * (size_t)n, 0, &d_obj, sf, st));
+  CB_TRY(validate_rows(d_cam, d_key, n, n_cams, st, "cb_pnp_ippe"));
+  double* d_norm = nullptr;
+  CB_TRY(upload_undistorted(n_cams, cam_fisheye, cam_k, cam_dist, n, d_cam, obs_px, sf, st, &d_norm));
+  int *d_rows = nullptr, *d_start = nullptr, n_groups = 0;
+  CB_TRY(group_by_key(d_key, n, st, sf, &d_rows, &d_start, &n_groups));
+  CB_CUDA(cudaEventRecord(ev[1], st));
+  *n_groups_out = n_groups;
+  if (n_groups > max_groups) {
+    g_last_error = "cb_pnp_ippe: " + std::to_string(n_groups) + " groups but room for " + std::to_string(max_groups);
+    return CB_E_INVALID;
+  }
+  double *d_R, *d_t, *d_rmse;
+  int *d_status, *d_count, *d_rep;
+  CB_TRY(dalloc(&d_R, 9 * (size_t)n_groups)); sf.dev.push_back(d_R);
+  CB_TRY(dalloc(&d_t, 3 * (size_t)n_groups)); sf.dev.push_back(d_t);
+  CB_TRY(dalloc(&d_rmse, (size_t)n_groups)); sf.dev.push_back(d_rmse);
+  CB_TRY(dalloc(&d_status, (size_t)n_groups)); sf.dev.push_back(d_status);
+  CB_TRY(dalloc(&d_count, (size_t)n_groups)); sf.dev.push_back(d_count);
+  CB_TRY(dalloc(&d_rep, (size_t)n_groups)); sf.dev.push_back(d_rep);
+  CB_CUDA(cudaEventRecord(ev[2], st));
+  CB_LAUNCH(cb::pnp_ippe_kernel, cdiv((long long)n_groups * 32, cb::BS_THREADS), cb::BS_THREADS, 0, st, d_start, d_rows, d_obj,
+            (const double*)d_norm, n_groups, (int)min_points, d_R, d_t, d_rmse, d_status, d_count, d_rep);
+  CB_CUDA(cudaGetLastError());
+  CB_CUDA(cudaEventRecord(ev[3], st));
+  CB_CUDA(cudaMemcpyAsync(R_out, d_R, sizeof(double) * 9 * (size_t)n_groups, cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaMemcpyAsync(t_out, d_t, sizeof(double) * 3 * (size_t)n_groups, cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaMemcpyAsync(rmse_out, d_rmse, sizeof(double) * (size_t)n_groups, cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaMemcpyAsync(status_out, d_status, sizeof(int) * (size_t)n_groups, cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaMemcpyAsync(count_out, d_count, sizeof(int) * (size_t)n_groups, cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaMemcpyAsync(rep_row_out, d_rep, sizeof(int) * (size_t)n_groups, cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  if (stats) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev[0], ev[1]); stats->group_ms = ms;
+    cudaEventElapsedTime(&ms, ev[2], ev[3]); stats->dlt_ms = ms;
+    cudaEventElapsedTime(&ms, ev[0], ev[3]); stats->total_ms = ms;
+    stats->kernel_launches = (int)(g_launches.load() - launches0);
+  }
+  return CB_OK;
+}
+
+int cb_stereo_rmse(int32_t n_cams, const int32_t* cam_fisheye, const double* cam_k, const double* cam_dist,
+                   int32_t n_pairs, const int32_t* pair_a, const int32_t* pair_b, const double* pair_Rt, int64_t n_obs,
+                   const int32_t* obs_cam, const int64_t* obs_key, const double* obs_px, int32_t min_common,
+                   double* rmse_out, int64_t* count_out, CbTriStats* stats, int device, void* stream) {
+  if (n_cams <= 0 || !cam_fisheye || !cam_k || !cam_dist || n_pairs < 0 || n_obs < 0 || n_obs > 0x7fffffffLL ||
+      (n_pairs > 0 && (!pair_a || !pair_b || !pair_Rt || !rmse_out || !count_out)) ||
+      (n_obs > 0 && (!obs_cam || !obs_key || !obs_px))) {
+    g_last_error = "cb_stereo_rmse: bad argument";
+    return CB_E_INVALID;
+  }
+  CB_TRY(select_device(device));
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+  const double nan = std::nan("");
+  for (int p = 0; p < n_pairs; ++p) { rmse_out[p] = nan; count_out[p] = 0; }
+  if (n_pairs == 0 || n_obs == 0) return CB_OK;
+  const long long launches0 = g_launches.load();
+  cudaStream_t st = (cudaStream_t)stream;
+  ScopedFree sf;
+  const int n = (int)n_obs;
+  std::vector<int> pair_of((size_t)n_cams * n_cams, -1);
+  for (int p = 0; p < n_pairs; ++p) {
+    const int a = pair_a[p], b = pair_b[p];
+    if (a < 0 || b < 0 || a >= n_cams || b >= n_cams || a >= b) {
+      g_last_error = "cb_stereo_rmse: pairs must satisfy 0 <= a < b < n_cams";
+      return CB_E_INVALID;
+    }
+    pair_of[(size_t)a * n_cams + b] = p;
+  }
+  cudaEvent_t ev[4];
+  for (auto& e : ev) CB_CUDA(cudaEventCreate(&e));
+  struct EvGuard { cudaEvent_t* e; ~EvGuard() { for (int i = 0; i < 4; ++i) cudaEventDestroy(e[i]); } } evg{ev};
+  CB_CUDA(cudaEventRecord(ev[0], st));
+  const int* d_cam = nullptr;
+  const long long* d_key = nullptr;
+  const int* d_pair_of = nullptr;
+  const double* d_Rt = nullptr;
+  CB_TRY(to_device(obs_cam, (size_t)n, 0, &d_cam, sf, st));
+  CB_TRY(to_device((const long long*)obs_key, (size_t)n, 0, &d_key, sf, st));
+  CB_TRY(to_device(pair_of.data(), pair_of.size(), 0, &d_pair_of, sf, st));
+  CB_TRY(to_device(pair_Rt, 12 * (size_t)n_pairs, 0, &d_Rt, sf, st));
+  CB_TRY(validate_rows(d_cam, d_key, n, n_cams, st, "cb_stereo_rmse"));
+  double* d_norm = nullptr;
+  CB_TRY(upload_undistorted(n_cams, cam_fisheye, cam_k, cam_dist, n, d_cam, obs_px, sf, st, &d_norm));
+  int *d_rows = nullptr, *d_start = nullptr, n_groups = 0;
+  CB_TRY(group_by_key(d_key, n, st, sf, &d_rows, &d_start, &n_groups));
+  CB_CUDA(cudaEventRecord(ev[1], st));
+  // slots per group, exclusive scan
+  long long *d_nslots = nullptr, *d_slot_start = nullptr;
+  CB_TRY(dalloc(&d_nslots, (size_t)n_groups + 1)); sf.dev.push_back(d_nslots);
+  CB_TRY(dalloc(&d_slot_start, (size_t)n_groups + 1)); sf.dev.push_back(d_slot_start);
+  CB_CUDA(cudaMemsetAsync(d_nslots, 0, sizeof(long long) * ((size_t)n_groups + 1), st));
+  CB_LAUNCH(cb::stereo_slots_kernel, cdiv(n_groups, 256), 256, 0, st, d_start, n_groups, d_nslots);
+  size_t tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, d_nslots, d_slot_start, n_groups + 1, st);
+  void* d_tmp = nullptr;
+  CB_TRY(cached_malloc(&d_tmp, std::max<size_t>(tb, 16))); sf.dev.push_back(d_tmp);
+  CB_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_nslots, d_slot_start, n_groups + 1, st));
+  g_launches.fetch_add(2);
+  long long total = 0;
+  CB_CUDA(cudaMemcpyAsync(&total, d_slot_start + n_groups, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  if (total > 0x7fffffffLL) { g_last_error = "cb_stereo_rmse: more than 2^31 observation pairs"; return CB_E_UNSUPPORTED; }
+  if (total == 0) return CB_OK;
+  const int m = (int)total;
+  int *d_k = nullptr, *d_ks = nullptr;
+  double *d_v = nullptr, *d_vs = nullptr;
+  CB_TRY(dalloc(&d_k, (size_t)m)); sf.dev.push_back(d_k);
+  CB_TRY(dalloc(&d_ks, (size_t)m)); sf.dev.push_back(d_ks);
+  CB_TRY(dalloc(&d_v, (size_t)m)); sf.dev.push_back(d_v);
+  CB_TRY(dalloc(&d_vs, (size_t)m)); sf.dev.push_back(d_vs);
+  CB_CUDA(cudaEventRecord(ev[2], st));
+  const int lanes = (n / std::max(n_groups, 1) > 12) ? 32 : 8;
+  if (lanes == 32)
+    CB_LAUNCH(cb::stereo_pairs_kernel<32>, cdiv((long long)n_groups * 32, cb::BS_THREADS), cb::BS_THREADS, 0, st, d_start, d_rows,
+              d_cam, (const double*)d_norm, n_groups, (const long long*)d_slot_start, (int)n_cams, d_pair_of, d_Rt, (int)n_pairs, d_k, d_v);
+  else
+    CB_LAUNCH(cb::stereo_pairs_kernel<8>, cdiv((long long)n_groups * 8, cb::BS_THREADS), cb::BS_THREADS, 0, st, d_start, d_rows,
+              d_cam, (const double*)d_norm, n_groups, (const long long*)d_slot_start, (int)n_cams, d_pair_of, d_Rt, (int)n_pairs, d_k, d_v);
+  CB_CUDA(cudaGetLastError());
+  CB_CUDA(cudaEventRecord(ev[3], st));
+  // stable sort by pair id, then one segmented sum per pair (fixed order => reproducible sums)
+  size_t tb2 = 0, tb3 = 0;
+  const int kbits = bits_for((unsigned long long)n_pairs);
+  cub::DeviceRadixSort::SortPairs(nullptr, tb2, d_k, d_ks, d_v, d_vs, m, 0, kbits, st);
+  int *d_uk = nullptr, *d_nruns = nullptr;
+  double* d_sum = nullptr;
+  CB_TRY(dalloc(&d_uk, (size_t)n_pairs + 2)); sf.dev.push_back(d_uk);
+  CB_TRY(dalloc(&d_sum, (size_t)n_pairs + 2)); sf.dev.push_back(d_sum);
+  CB_TRY(dalloc(&d_nruns, 1)); sf.dev.push_back(d_nruns);
+  cub::DeviceReduce::ReduceByKey(nullptr, tb3, d_ks, d_uk, d_vs, d_sum, d_nruns, cub::Sum(), m, st);
+  void* d_tmp2 = nullptr;
+  CB_TRY(cached_malloc(&d_tmp2, std::max<size_t>(std::max(tb2, tb3), 16))); sf.dev.push_back(d_tmp2);
+  size_t tbs = std::max(tb2, tb3);
+  CB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp2, tbs, d_k, d_ks, d_v, d_vs, m, 0, kbits, st));
+  CB_CUDA(cub::DeviceReduce::ReduceByKey(d_tmp2, tbs, d_ks, d_uk, d_vs, d_sum, d_nruns, cub::Sum(), m, st));
+  g_launches.fetch_add(6);
+  // counts per pair: run lengths of the sorted keys (same run order as the segmented sums)
+  int *d_uk2 = nullptr, *d_len = nullptr;
+  CB_TRY(dalloc(&d_uk2, (size_t)n_pairs + 2)); sf.dev.push_back(d_uk2);
+  CB_TRY(dalloc(&d_len, (size_t)n_pairs + 2)); sf.dev.push_back(d_len);
+  size_t tb4 = 0;
+  cub::DeviceRunLengthEncode::Encode(nullptr, tb4, d_ks, d_uk2, d_len, d_nruns, m, st);
+  void* d_tmp3 = nullptr;
+  CB_TRY(cached_malloc(&d_tmp3, std::max<size_t>(tb4, 16))); sf.dev.push_back(d_tmp3);
+  std::vector<int> uk((size_t)n_pairs + 2), len((size_t)n_pairs + 2);
+  std::vector<double> sums((size_t)n_pairs + 2);
+  int nruns = 0;
+  CB_CUDA(cudaMemcpyAsync(&nruns, d_nruns, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaMemcpyAsync(uk.data(), d_uk, sizeof(int) * ((size_t)n_pairs + 1), cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaMemcpyAsync(sums.data(), d_sum, sizeof(double) * ((size_t)n_pairs + 1), cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cub::DeviceRunLengthEncode::Encode(d_tmp3, tb4, d_ks, d_uk2, d_len, d_nruns, m, st));
+  g_launches.fetch_add(2);
+  CB_CUDA(cudaMemcpyAsync(len.data(), d_len, sizeof(int) * ((size_t)n_pairs + 1), cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  for (int r = 0; r < nruns; ++r) {
+    const int pid = uk[r];
+    if (pid < 0 || pid >= n_pairs) continue;
+    const long long cnt = len[r];
+    count_out[pid] = cnt;
+    if (cnt >= min_common) rmse_out[pid] = std::sqrt(sums[r] / (2.0 * (double)cnt));  // mean over the 2N stacked rows
+  }
+  if (stats) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev[0], ev[1]); stats->group_ms = ms;
+    cudaEventElapsedTime(&ms, ev[2], ev[3]); stats->dlt_ms = ms;
+    cudaEventElapsedTime(&ms, ev[0], ev[3]); stats->total_ms = ms;
+    stats->kernel_launches = (int)(g_launches.load() - launches0);
+  }
+  return CB_OK;
 }
 
 }  // extern "C"

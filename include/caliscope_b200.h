@@ -275,6 +275,37 @@ int cb_peer_destroy(CbPeerGroup* group);
 /* Number of kernel launches issued by this library in the calling process so far. */
 int64_t cb_ba_launch_count(void);
 
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Extrinsic bootstrap (what produces bundle adjustment's start vector).
+ *
+ * cb_pnp_ippe == compute_camera_to_object_poses_pnp (reference core/bootstrap_pose/pose_network_builder.py:211-330):
+ *   obs_px are raw pixels of camera obs_cam (undistorted on the device with float32 rounding exactly as
+ *   CameraData.undistort_points does, cameras/camera_array.py:135-174), obs_obj the object-frame coordinates (n_obs x 3,
+ *   NaN z = 0), obs_key >= 0 packs (camera, sync_index, object) -- rows with equal key form one PnP group, groups come
+ *   back in ascending key order (== the reference's groupby order when the key is packed camera-major).  Per group:
+ *   R (3x3 row-major) and t of the object in the camera frame (cv2.solvePnP(SOLVEPNP_IPPE) + cv2.Rodrigues), the
+ *   reprojection RMSE in the normalised plane (:317-318), status (0 ok, 1 fewer than min_points rows, 2 non-planar
+ *   target -- the reference switches to SQPNP there, which this build does not implement --, 3 degenerate), row count and
+ *   one representative caller row.  All pointers host.
+ *
+ * cb_stereo_rmse == calculate_stereo_rmse_for_pair for every pair at once (:638-685, with the common observations of
+ *   _precompute_common_observations :576-603): pair p = cameras (pair_a[p] < pair_b[p]) with pose pair_Rt[p] = [R (9) | t (3)]
+ *   (camera a at the origin).  obs_key >= 0 packs (sync_index, object, keypoint).  Outputs per pair: rmse (NaN when the
+ *   pair has fewer than min_common common observations, the reference returns None there) and the number of common
+ *   observations.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int cb_pnp_ippe(int32_t n_cams, const int32_t* cam_fisheye, const double* cam_k, const double* cam_dist, int64_t n_obs,
+                const int32_t* obs_cam, const int64_t* obs_key, const double* obs_px, const double* obs_obj,
+                int32_t min_points, int32_t max_groups, int32_t* n_groups_out, double* R_out, double* t_out,
+                double* rmse_out, int32_t* status_out, int32_t* count_out, int32_t* rep_row_out, CbTriStats* stats,
+                int device, void* stream);
+
+int cb_stereo_rmse(int32_t n_cams, const int32_t* cam_fisheye, const double* cam_k, const double* cam_dist,
+                   int32_t n_pairs, const int32_t* pair_a, const int32_t* pair_b, const double* pair_Rt, int64_t n_obs,
+                   const int32_t* obs_cam, const int64_t* obs_key, const double* obs_px, int32_t min_common,
+                   double* rmse_out, int64_t* count_out, CbTriStats* stats, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
