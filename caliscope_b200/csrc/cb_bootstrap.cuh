@@ -74,8 +74,92 @@ __device__ __forceinline__ void mat3_mul(const double* A, const double* B, doubl
     for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
 }
 
+// The two IPPE rotations from the 2x2 Jacobian J of the model-to-image map at the model centroid and the image (p, q) of
+// the centroid; returns gamma, the first-order scale (<= 0 / NaN: degenerate).
+__device__ __forceinline__ double ippe_rotations(double j00, double j01, double j10, double j11, double p, double q,
+                                                 double Rs[2][9]) {
+  double Rv[9];
+  {
+    const double nrm = sqrt(p * p + q * q + 1.0), ax = p / nrm, ay = q / nrm, az = 1.0 / nrm;
+    const double d = 1.0 / (1.0 + az);  // az > 0
+    // rotation taking (p, q, 1) onto +z, transposed
+    Rv[0] = 1.0 - ax * ax * d; Rv[1] = -ax * ay * d;      Rv[2] = ax;
+    Rv[3] = -ax * ay * d;      Rv[4] = 1.0 - ay * ay * d; Rv[5] = ay;
+    Rv[6] = -ax;               Rv[7] = -ay;               Rv[8] = 1.0 - (ax * ax + ay * ay) * d;
+  }
+  const double b00 = Rv[0] - p * Rv[6], b01 = Rv[1] - p * Rv[7], b10 = Rv[3] - q * Rv[6], b11 = Rv[4] - q * Rv[7];
+  const double dti = 1.0 / (b00 * b11 - b01 * b10);
+  const double bi00 = dti * b11, bi01 = -dti * b01, bi10 = -dti * b10, bi11 = dti * b00;
+  const double A00 = bi00 * j00 + bi01 * j10, A01 = bi00 * j01 + bi01 * j11, A10 = bi10 * j00 + bi11 * j10,
+               A11 = bi10 * j01 + bi11 * j11;
+  const double ata00 = A00 * A00 + A01 * A01, ata01 = A00 * A10 + A01 * A11, ata11 = A10 * A10 + A11 * A11;
+  const double gamma = sqrt(0.5 * (ata00 + ata11 + sqrt((ata00 - ata11) * (ata00 - ata11) + 4.0 * ata01 * ata01)));
+  const double r00 = A00 / gamma, r01 = A01 / gamma, r10 = A10 / gamma, r11 = A11 / gamma;
+  const double bb0 = sqrt(fmax(0.0, 1.0 - r00 * r00 - r10 * r10));
+  double bb1 = sqrt(fmax(0.0, 1.0 - r01 * r01 - r11 * r11));
+  if (-r00 * r01 - r10 * r11 < 0) bb1 = -bb1;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const double sg = s == 0 ? 1.0 : -1.0;
+    const double c0[3] = {r00, r10, sg * bb0}, c1v[3] = {r01, r11, sg * bb1};
+    const double c2v[3] = {c0[1] * c1v[2] - c0[2] * c1v[1], c0[2] * c1v[0] - c0[0] * c1v[2], c0[0] * c1v[1] - c0[1] * c1v[0]};
+    const double Rt[9] = {c0[0], c1v[0], c2v[0], c0[1], c1v[1], c2v[1], c0[2], c1v[2], c2v[2]};
+    mat3_mul(Rv, Rt, Rs[s]);
+  }
+  return gamma;
+}
+
+// exp([w]x) (Rodrigues)
+__device__ __forceinline__ void rot_exp(const double* w, double* R) {
+  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], th = sqrt(th2);
+  double a, b;  // R = I + a K + b K^2, K = [w]x
+  if (th < 1e-8) { a = 1.0; b = 0.5; }
+  else { a = sin(th) / th; b = (1.0 - cos(th)) / th2; }
+  const double K[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+  double K2[9];
+  mat3_mul(K, K, K2);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = ((i % 4 == 0) ? 1.0 : 0.0) + a * K[i] + b * K2[i];
+}
+
+// solve the SPD 6x6 system H d = -g in place (Cholesky); H packed upper (21), returns false if not positive definite
+__device__ __forceinline__ bool solve6(const double* Hp, const double* g, double* d) {
+  double L[6][6];
+  int t = 0;
+  for (int i = 0; i < 6; ++i)
+    for (int j = i; j < 6; ++j) { L[j][i] = Hp[t]; ++t; }
+  double tr = 0.0;
+  for (int i = 0; i < 6; ++i) tr += L[i][i];
+  for (int i = 0; i < 6; ++i) L[i][i] += 1e-12 * tr;
+  for (int j = 0; j < 6; ++j) {
+    double v = L[j][j];
+    for (int k = 0; k < j; ++k) v -= L[j][k] * L[j][k];
+    if (!(v > 0.0)) return false;
+    v = sqrt(v);
+    L[j][j] = v;
+    for (int i = j + 1; i < 6; ++i) {
+      double s = L[i][j];
+      for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
+      L[i][j] = s / v;
+    }
+  }
+  double y[6];
+  for (int i = 0; i < 6; ++i) {
+    double s = -g[i];
+    for (int k = 0; k < i; ++k) s -= L[i][k] * y[k];
+    y[i] = s / L[i][i];
+  }
+  for (int i = 5; i >= 0; --i) {
+    double s = y[i];
+    for (int k = i + 1; k < 6; ++k) s -= L[k][i] * d[k];
+    d[i] = s / L[i][i];
+  }
+  return true;
+}
+
 // status codes of a PnP group
-constexpr int PNP_OK = 0, PNP_TOO_FEW = 1, PNP_NON_PLANAR = 2, PNP_DEGENERATE = 3;
+constexpr int PNP_OK = 0, PNP_TOO_FEW = 1, PNP_NON_PLANAR = 2, PNP_DEGENERATE = 3, PNP_OK_FALLBACK = 4;
+constexpr double IPPE_GAMMA_MIN = 1e-7;
 
 // One warp per (camera, sync, object) group; rows[start[g] .. start[g+1]) index the caller's observation arrays.
 // obj: (n_obs, 3) object-frame coordinates (NaN z counts as 0, as the reference's nan_to_num), img: (n_obs, 2) undistorted
@@ -205,42 +289,30 @@ pnp_ippe_kernel(const int* __restrict__ start, const int* __restrict__ rows, con
   double T1[9], H[9];
   mat3_mul(Hn, TA, T1);
   mat3_mul(TBi, T1, H);
-  if (!(fabs(H[8]) > 0.0)) { fail(PNP_DEGENERATE); return; }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) H[k] /= H[8];
-  H[8] = 1.0;
-  // ---- the two IPPE rotations from the first-order behaviour of H at the origin
-  const double p = H[2], q = H[5];
-  const double j00 = H[0] - H[6] * p, j01 = H[1] - H[7] * p, j10 = H[3] - H[6] * q, j11 = H[4] - H[7] * q;
-  double Rv[9];
-  {
-    const double nrm = sqrt(p * p + q * q + 1.0), ax = p / nrm, ay = q / nrm, az = 1.0 / nrm;
-    const double d = 1.0 / (1.0 + az);  // az > 0
-    // rotation taking (p, q, 1) onto +z, transposed
-    Rv[0] = 1.0 - ax * ax * d; Rv[1] = -ax * ay * d;      Rv[2] = ax;
-    Rv[3] = -ax * ay * d;      Rv[4] = 1.0 - ay * ay * d; Rv[5] = ay;
-    Rv[6] = -ax;               Rv[7] = -ay;               Rv[8] = 1.0 - (ax * ax + ay * ay) * d;
-  }
-  const double b00 = Rv[0] - p * Rv[6], b01 = Rv[1] - p * Rv[7], b10 = Rv[3] - q * Rv[6], b11 = Rv[4] - q * Rv[7];
-  const double dti = 1.0 / (b00 * b11 - b01 * b10);
-  const double bi00 = dti * b11, bi01 = -dti * b01, bi10 = -dti * b10, bi11 = dti * b00;
-  const double A00 = bi00 * j00 + bi01 * j10, A01 = bi00 * j01 + bi01 * j11, A10 = bi10 * j00 + bi11 * j10,
-               A11 = bi10 * j01 + bi11 * j11;
-  const double ata00 = A00 * A00 + A01 * A01, ata01 = A00 * A10 + A01 * A11, ata11 = A10 * A10 + A11 * A11;
-  const double gamma = sqrt(0.5 * (ata00 + ata11 + sqrt((ata00 - ata11) * (ata00 - ata11) + 4.0 * ata01 * ata01)));
-  if (!(gamma > 0.0) || !(gamma == gamma)) { fail(PNP_DEGENERATE); return; }
-  const double r00 = A00 / gamma, r01 = A01 / gamma, r10 = A10 / gamma, r11 = A11 / gamma;
-  const double bb0 = sqrt(fmax(0.0, 1.0 - r00 * r00 - r10 * r10));
-  double bb1 = sqrt(fmax(0.0, 1.0 - r01 * r01 - r11 * r11));
-  if (-r00 * r01 - r10 * r11 < 0) bb1 = -bb1;
+  // all model points on one line: no pose (cv2 reports success with a NaN pose; the reference keeps the group and its
+  // NaN filter drops it later, pose_network_builder.py:364-367)
+  if (!(fabs(det) > 1e-12 * (a00 + a11) * (a00 + a11))) { fail(PNP_DEGENERATE); return; }
   double Rs[2][9], ts[2][3], err[2];
+  double gamma = -1.0;
+  if (fabs(H[8]) > 0.0) {
 #pragma unroll
-  for (int s = 0; s < 2; ++s) {
-    const double sg = s == 0 ? 1.0 : -1.0;
-    const double c0[3] = {r00, r10, sg * bb0}, c1v[3] = {r01, r11, sg * bb1};
-    const double c2v[3] = {c0[1] * c1v[2] - c0[2] * c1v[1], c0[2] * c1v[0] - c0[0] * c1v[2], c0[0] * c1v[1] - c0[1] * c1v[0]};
-    const double Rt[9] = {c0[0], c1v[0], c2v[0], c0[1], c1v[1], c2v[1], c0[2], c1v[2], c2v[2]};
-    mat3_mul(Rv, Rt, Rs[s]);
+    for (int k = 0; k < 8; ++k) H[k] /= H[8];
+    H[8] = 1.0;
+    // ---- the two IPPE rotations from the first-order behaviour of H at the origin
+    const double p = H[2], q = H[5];
+    gamma = ippe_rotations(H[0] - H[6] * p, H[1] - H[7] * p, H[3] - H[6] * q, H[4] - H[7] * q, p, q, Rs);
+  }
+  // OpenCV's IPPE gives up when the homography is degenerate (three of four points collinear, ...): gamma collapses to
+  // ~1e-10 and the reference falls back to SOLVEPNP_ITERATIVE (:308-311).  Restated (oracle/ippe.py): the two IPPE poses of
+  // the AFFINE fit, each refined by Gauss-Newton on the reprojection error, the better one kept.
+  const bool fallback = !(gamma >= IPPE_GAMMA_MIN);
+  if (fallback) {
+    // affine fit in normalised coordinates: B ~ Mn A, Mn = (sum B A^T)(sum A A^T)^-1, sum B A^T = -n [c1 c2; c3 c4]
+    const double s00 = -n * c1, s01 = -n * c2, s10 = -n * c3, s11 = -n * c4, sc = betaA / betaB;
+    const double m00 = sc * (s00 * i00 + s01 * i01), m01 = sc * (s00 * i01 + s01 * i11);
+    const double m10 = sc * (s10 * i00 + s11 * i01), m11 = sc * (s10 * i01 + s11 * i11);
+    gamma = ippe_rotations(m00, m01, m10, m11, mu, mv, Rs);
+    if (!(gamma > 0.0)) { fail(PNP_DEGENERATE); return; }
   }
   // ---- pass 5: translations (least squares), both candidates
   {
@@ -271,6 +343,56 @@ pnp_ippe_kernel(const int* __restrict__ start, const int* __restrict__ rows, con
       ts[s][2] = tz;
     }
   }
+  // ---- fallback only: Gauss-Newton on the reprojection error, both candidates (rotation increment on the left)
+  if (fallback) {
+#pragma unroll 1
+    for (int s2 = 0; s2 < 2; ++s2) {
+#pragma unroll 1
+      for (int it = 0; it < 30; ++it) {
+        double Hp[21], gv[6];
+#pragma unroll
+        for (int k = 0; k < 21; ++k) Hp[k] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) gv[k] = 0.0;
+        const double* R = Rs[s2];
+        for (int i = b + lane; i < e; i += 32) {
+          const int r = rows[i];
+          const double X = ox(r, 0) - mx, Y = ox(r, 1) - my, u0 = img[2 * (size_t)r], v0 = img[2 * (size_t)r + 1];
+          const double xr = R[0] * X + R[1] * Y, yr = R[3] * X + R[4] * Y, zr = R[6] * X + R[7] * Y;
+          const double zc = zr + ts[s2][2], iz = 1.0 / zc, u = (xr + ts[s2][0]) * iz, v = (yr + ts[s2][1]) * iz;
+          // d(u, v)/d(Xc) rows, then Xc = exp(w) (R X) + t: dXc/dw = -[R X]x, dXc/dt = I
+          const double du[3] = {iz, 0.0, -u * iz}, dv[3] = {0.0, iz, -v * iz};
+          double Ju[6], Jv[6];
+          Ju[0] = du[1] * (-zr) + du[2] * yr;  Ju[1] = du[0] * zr + du[2] * (-xr);  Ju[2] = du[0] * (-yr) + du[1] * xr;
+          Jv[0] = dv[1] * (-zr) + dv[2] * yr;  Jv[1] = dv[0] * zr + dv[2] * (-xr);  Jv[2] = dv[0] * (-yr) + dv[1] * xr;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { Ju[3 + k] = du[k]; Jv[3 + k] = dv[k]; }
+          const double ru = u - u0, rv = v - v0;
+          int t2 = 0;
+#pragma unroll
+          for (int a2 = 0; a2 < 6; ++a2) {
+            gv[a2] += Ju[a2] * ru + Jv[a2] * rv;
+#pragma unroll
+            for (int b2 = a2; b2 < 6; ++b2) { Hp[t2] += Ju[a2] * Ju[b2] + Jv[a2] * Jv[b2]; ++t2; }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 21; ++k) Hp[k] = warp_sum(Hp[k]);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) gv[k] = warp_sum(gv[k]);
+        double d6[6];
+        if (!solve6(Hp, gv, d6)) break;
+        double dR[9], Rn[9];
+        rot_exp(d6, dR);
+        mat3_mul(dR, Rs[s2], Rn);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Rs[s2][k] = Rn[k];
+        ts[s2][0] += d6[0 + 3]; ts[s2][1] += d6[1 + 3]; ts[s2][2] += d6[2 + 3];
+        const double dn = d6[0] * d6[0] + d6[1] * d6[1] + d6[2] * d6[2] + d6[3] * d6[3] + d6[4] * d6[4] + d6[5] * d6[5];
+        if (dn < 1e-28) break;
+      }
+    }
+  }
   // ---- pass 6: reprojection error of both, best first
   {
     double e0 = 0, e1 = 0;
@@ -299,7 +421,7 @@ pnp_ippe_kernel(const int* __restrict__ start, const int* __restrict__ rows, con
     for (int k = 0; k < 9; ++k) R_out[9 * g + k] = R[k];
     t_out[3 * g] = tx; t_out[3 * g + 1] = ty; t_out[3 * g + 2] = tz;
     rmse_out[g] = sqrt(err[best] / n);
-    status_out[g] = (R[0] == R[0] && tz == tz) ? PNP_OK : PNP_DEGENERATE;
+    status_out[g] = (R[0] == R[0] && tz == tz) ? (fallback ? PNP_OK_FALLBACK : PNP_OK) : PNP_DEGENERATE;
     count_out[g] = n;
     rep_out[g] = rows[b];
   }

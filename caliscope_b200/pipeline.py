@@ -22,7 +22,7 @@ class PipelineResult:
 
 def solve_filter_resolve(cam_flags, cam_const, n_pts, obs_cam, obs_pt, obs_xy, x0, *, filter_percentile: float = 2.5,
                          min_per_camera: int = 10, device: int = 0, ftol: float = 1e-8, verbose: int = 0,
-                         want_mask: bool = True, keep_stage_x: bool = False) -> PipelineResult:  # fmt: skip
+                         want_mask: bool = True) -> PipelineResult:  # fmt: skip
     obs_cam = np.ascontiguousarray(obs_cam, dtype=np.int32)
     obs_pt = np.ascontiguousarray(obs_pt, dtype=np.int32)
     obs_xy = np.ascontiguousarray(obs_xy, dtype=np.float64).reshape(-1, 2)
@@ -44,8 +44,6 @@ def solve_filter_resolve(cam_flags, cam_const, n_pts, obs_cam, obs_pt, obs_xy, x
         s3 = prob2.solve(s2.x, ftol=ftol, verbose=verbose)
         stages.append(s3)
         rmse.append(prob2.overall_rmse_px(s3.x))
-    if not keep_stage_x:  # the per-stage vectors are n_params doubles each; drop them unless asked for
-        s1.x = s2.x = None
     return PipelineResult(x=s3.x, keep=keep, stages=stages, rmse_px=rmse)
 
 

@@ -34,7 +34,9 @@ def install(full: bool = False) -> None:
     threshold filters by merge-free versions (``filter_by_absolute_error`` reaches them unchanged), and seam
     S3: ``caliscope.core.point_data.triangulate_image_points`` (point_data.py:122-229) and
     ``ImagePoints.triangulate`` (:416-559; pixels -> undistortion -> DLT in one device call) become the GPU
-    versions."""
+    versions; and seam S4: the stage functions of the extrinsic bootstrap
+    (``caliscope.core.bootstrap_pose.pose_network_builder``: PnP per group, relative poses, outlier rejection, aggregation,
+    stereo RMSE) become ``caliscope_b200.bootstrap``'s."""
     global _original
     from . import _lib
 
@@ -68,6 +70,20 @@ def install(full: bool = False) -> None:
         if "ImagePoints.triangulate" not in _original_functions:
             _original_functions["ImagePoints.triangulate"] = pd_mod.ImagePoints.triangulate
         pd_mod.ImagePoints.triangulate = triangulation.triangulate
+        # seam S4: the extrinsic bootstrap (pose_network_builder.py): the five stage functions PoseNetworkBuilder calls are
+        # module attributes, so build_paired_pose_network / PoseNetworkBuilder run unchanged on top of the GPU stages
+        from . import bootstrap
+
+        pnb = importlib.import_module("caliscope.core.bootstrap_pose.pose_network_builder")
+        for name in _BOOTSTRAP_FUNCTIONS:
+            if name not in _original_bootstrap:
+                _original_bootstrap[name] = getattr(pnb, name)
+            setattr(pnb, name, getattr(bootstrap, name))
+
+
+_BOOTSTRAP_FUNCTIONS = ("compute_camera_to_object_poses_pnp", "compute_relative_poses", "reject_outliers", "aggregate_poses",
+                        "estimate_pnp_paired_pose_network")
+_original_bootstrap: dict = {}
 
 
 def uninstall() -> None:
@@ -88,6 +104,11 @@ def uninstall() -> None:
             else:
                 setattr(pd_mod, name, fn)
         _original_functions.clear()
+    if _original_bootstrap:
+        pnb = importlib.import_module("caliscope.core.bootstrap_pose.pose_network_builder")
+        for name, fn in _original_bootstrap.items():
+            setattr(pnb, name, fn)
+        _original_bootstrap.clear()
 
 
 @contextlib.contextmanager

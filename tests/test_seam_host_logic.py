@@ -318,3 +318,48 @@ def test_s2_optimize_passes_the_reference_constraint_arrays(monkeypatch):
     assert out.rigidity_report().rmse_mm == ref_out.rigidity_report().rmse_mm
     S2.optimize(vol, use_constraints=False)
     assert seen["constraints"] is None
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# seam S4: the bootstrap stage functions with the reference's container types (dict of StereoPair), fed with the
+# reference's own PnP poses (the device stages are in tests/test_gpu_bootstrap.py)
+# ---------------------------------------------------------------------------------------------------------------------
+def test_s4_bootstrap_dict_stages_equal_reference(session_volume):
+    from caliscope.core.bootstrap_pose import pose_network_builder as PNB
+    from caliscope_b200 import bootstrap as B
+
+    cv = session_volume
+    poses = PNB.compute_camera_to_object_poses_pnp(cv.image_points, cv.camera_array)
+    rel_ref = PNB.compute_relative_poses(poses, cv.camera_array)
+    rel = B.compute_relative_poses(poses, cv.camera_array)
+    assert set(rel) == set(rel_ref)
+    for k, sp in rel.items():
+        r = rel_ref[k]
+        if np.isnan(r.rotation).any():
+            assert np.isnan(sp.rotation).any()
+            continue
+        assert np.abs(sp.rotation - r.rotation).max() < 1e-12 and np.abs(sp.translation - r.translation).max() < 1e-12
+        assert sp.pair == r.pair and type(sp) is type(r)
+    filt_ref = PNB.reject_outliers(rel_ref, threshold=1.5)
+    filt = B.reject_outliers(rel_ref, threshold=1.5)
+    assert {k: len(v) for k, v in filt.items()} == {k: len(v) for k, v in filt_ref.items()}
+    for k in filt:
+        assert [id(sp) for sp in filt[k]] == [id(sp) for sp in filt_ref[k]]  # the very same samples survive, same order
+    agg_ref = PNB.aggregate_poses(filt_ref)
+    agg = B.aggregate_poses(filt_ref)
+    assert list(agg) == list(agg_ref)
+    for k in agg:
+        assert np.abs(agg[k].rotation - agg_ref[k].rotation).max() < 1e-9
+        assert np.abs(agg[k].translation - agg_ref[k].translation).max() < 1e-9
+
+
+def test_seam_install_full_patches_bootstrap_and_restores():
+    import caliscope.core.bootstrap_pose.pose_network_builder as pnb
+    import caliscope_b200.seam as seam
+    from caliscope_b200 import bootstrap as B
+
+    before = [getattr(pnb, n) for n in seam._BOOTSTRAP_FUNCTIONS]
+    with seam.installed(full=True):
+        for n in seam._BOOTSTRAP_FUNCTIONS:
+            assert getattr(pnb, n) is getattr(B, n)
+    assert [getattr(pnb, n) for n in seam._BOOTSTRAP_FUNCTIONS] == before
