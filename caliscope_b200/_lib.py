@@ -38,7 +38,7 @@ class ProblemDesc(C.Structure):
         ("obs_pt", C.c_void_p),
         ("obs_xy", C.c_void_p),
         ("obs_on_device", C.c_int32),
-        ("pad_", C.c_int32),
+        ("obs_cam_bits", C.c_int32),
         ("cam_order", C.c_void_p),
     ]
 

@@ -19,6 +19,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/caliscope_b200.h"
@@ -249,6 +250,45 @@ struct ScopedFree {
     for (void* q : host) cached_free_host(q);
   }
 };
+
+// Pageable host memory -> device at PCIe speed: cudaMemcpyAsync from pageable memory goes through one driver staging
+// buffer at ~6-10 GB/s, so the caller's arrays (NumPy, pageable) are copied by several threads into a pinned block in
+// chunks, each chunk's DMA queued the moment it is staged.  Returns once the source has been read completely (the caller
+// may free it); the pinned block must stay alive until `st` has drained (sf.host frees it at scope exit of the caller,
+// which synchronises first).
+int staged_h2d(void* d_dst, const void* h_src, size_t bytes, cudaStream_t st, ScopedFree& sf, int n_threads = 6) {
+  if (bytes == 0) return CB_OK;
+  void* pin = nullptr;
+  CB_TRY(cached_malloc_host(&pin, bytes));
+  sf.host.push_back(pin);
+  const size_t chunk = (size_t)2 << 20;
+  const size_t n_chunks = (bytes + chunk - 1) / chunk;
+  n_threads = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_threads, n_chunks));
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::atomic<size_t> next{0};
+  std::atomic<int> err{0};
+  auto work = [&]() {
+    cudaSetDevice(dev);
+    for (;;) {
+      const size_t c = next.fetch_add(1);
+      if (c >= n_chunks) break;
+      const size_t off = c * chunk, sz = std::min(chunk, bytes - off);
+      std::memcpy((char*)pin + off, (const char*)h_src + off, sz);
+      if (cudaMemcpyAsync((char*)d_dst + off, (char*)pin + off, sz, cudaMemcpyHostToDevice, st) != cudaSuccess) err.store(1);
+    }
+  };
+  if (n_threads == 1) {
+    work();
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads - 1; ++t) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+  }
+  if (err.load()) { g_last_error = std::string("staged host-to-device copy: ") + cudaGetErrorString(cudaGetLastError()); return CB_E_CUDA; }
+  return CB_OK;
+}
 
 int select_device(int device) {
   int ndev = 0;
@@ -1412,19 +1452,32 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
   int *t_cam = nullptr, *t_pt = nullptr;
   double* t_xy = nullptr;
   cudaEvent_t xy_ready = nullptr;
+  ScopedFree stage;  // pinned staging blocks: released when this function returns (it synchronises before)
   if (!d->obs_on_device) {
     CB_TRY(dalloc(&t_cam, n)); CB_TRY(dalloc(&t_pt, n)); CB_TRY(dalloc(&t_xy, 2 * (size_t)n));
-    CB_CUDA(cudaMemcpyAsync(t_cam, d->obs_cam, sizeof(int) * n, cudaMemcpyHostToDevice, st));
-    CB_CUDA(cudaMemcpyAsync(t_pt, d->obs_pt, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    p->allocs.push_back(t_cam); p->allocs.push_back(t_pt); p->allocs.push_back(t_xy);  // kept: the cull path compacts them
+    if (d->obs_cam_bits == 16) {
+      short* t16 = nullptr;
+      CB_TRY(dalloc(&t16, n));
+      stage.dev.push_back(t16);
+      CB_TRY(staged_h2d(t16, d->obs_cam, sizeof(short) * (size_t)n, st, stage));
+      CB_LAUNCH(cb::widen_i16_kernel, cdiv(n, 256), 256, 0, st, (const short*)t16, n, t_cam);
+    } else {
+      CB_TRY(staged_h2d(t_cam, d->obs_cam, sizeof(int) * (size_t)n, st, stage));
+    }
+    CB_TRY(staged_h2d(t_pt, d->obs_pt, sizeof(int) * (size_t)n, st, stage));
     // the image coordinates (two thirds of the upload) are only needed by the last index-build kernel:
     // copy them on a side stream while the sorts run
     CB_CUDA(cudaEventCreateWithFlags(&xy_ready, cudaEventDisableTiming));
-    CB_CUDA(cudaMemcpyAsync(t_xy, d->obs_xy, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, side_stream()));
+    int rc_xy = staged_h2d(t_xy, d->obs_xy, sizeof(double) * 2 * (size_t)n, side_stream(), stage);
+    if (rc_xy != CB_OK) { cudaEventDestroy(xy_ready); return rc_xy; }
     CB_CUDA(cudaEventRecord(xy_ready, side_stream()));
     d_cam = t_cam; d_pt = t_pt; d_xy = t_xy;
-  }
-  if (t_cam) {  // keep the uploaded list: the cull path compacts it on the device
-    p->allocs.push_back(t_cam); p->allocs.push_back(t_pt); p->allocs.push_back(t_xy);
+  } else if (d->obs_cam_bits == 16) {
+    CB_TRY(dalloc(&t_cam, n));
+    p->allocs.push_back(t_cam);
+    CB_LAUNCH(cb::widen_i16_kernel, cdiv(n, 256), 256, 0, st, (const short*)d->obs_cam, n, t_cam);
+    d_cam = t_cam;
   }
   p->d_obs_cam = d_cam; p->d_obs_pt = d_pt; p->d_obs_xy = d_xy;
   p->h_cam_flags.assign(d->cam_flags, d->cam_flags + p->n_cams);
@@ -1526,6 +1579,10 @@ int cb_ba_problem_create(const CbBaProblemDesc* d, int device, void* stream, CbB
   if (d && d->n_obs == 0) {
     // CaptureVolume._validate_geometry (capture_volume.py:97-98) rejects this before optimize() can run
     g_last_error = "No image observations provided";
+    return CB_E_INVALID;
+  }
+  if (d && d->obs_cam_bits != 0 && d->obs_cam_bits != 16 && d->obs_cam_bits != 32) {
+    g_last_error = "obs_cam_bits must be 0, 16 or 32";
     return CB_E_INVALID;
   }
   if (!d || !out || d->n_cams <= 0 || d->n_pts <= 0 || d->n_obs < 0 || d->n_obs > (1ll << 30) || !d->cam_flags ||
@@ -2095,7 +2152,7 @@ int cb_ba_cull(CbBaProblem* p, const double* x, const double* thresholds, int32_
     d2.n_cams = nc; d2.n_pts = p->n_pts; d2.n_obs = nsel;
     d2.cam_flags = p->h_cam_flags.data(); d2.cam_const = p->h_cam_const.data();
     d2.obs_cam = c_cam; d2.obs_pt = c_pt; d2.obs_xy = c_xy; d2.obs_on_device = 1;
-    d2.pad_ = 0;
+    d2.obs_cam_bits = 32;
     d2.cam_order = p->h_perm.data();  // the filtered problem keeps this problem's camera order
     CbBaProblem* q = new CbBaProblem();
     q->allocs.push_back(c_cam); q->allocs.push_back(c_pt); q->allocs.push_back(c_xy);  // owned by the new problem

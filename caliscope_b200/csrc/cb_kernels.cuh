@@ -888,6 +888,10 @@ __global__ void cm_gather_kernel(const int* __restrict__ cm_pos, const int* __re
     cm_xy[q] = obs_xy[o];
   }
 }
+__global__ void widen_i16_kernel(const short* __restrict__ in, int n, int* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (int)in[i];
+}
 // caller's camera id -> internal slot, in place
 __global__ void remap_kernel(int* __restrict__ a, const int* __restrict__ map, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;

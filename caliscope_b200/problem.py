@@ -92,12 +92,17 @@ class BAProblem:
         self.n_pts = int(n_pts)
         self.device = int(device)
         on_dev = hasattr(obs_cam, "data_ptr")
+        cam_bits = 32
         if on_dev:
             keep = (obs_cam, obs_pt, obs_xy)
             n_obs = int(obs_cam.shape[0])
             ptrs = (obs_cam.data_ptr(), obs_pt.data_ptr(), obs_xy.data_ptr())
         else:
-            oc = np.ascontiguousarray(obs_cam, dtype=np.int32)
+            if isinstance(obs_cam, np.ndarray) and obs_cam.dtype == np.int16:
+                oc = np.ascontiguousarray(obs_cam)  # the reference's camera_indices dtype: widened on the device
+                cam_bits = 16
+            else:
+                oc = np.ascontiguousarray(obs_cam, dtype=np.int32)
             op = np.ascontiguousarray(obs_pt, dtype=np.int32)
             ox = np.ascontiguousarray(obs_xy, dtype=np.float64).reshape(-1, 2)
             if not (len(oc) == len(op) == len(ox)):
@@ -116,7 +121,7 @@ class BAProblem:
             raise ValueError(f"cam_order must have shape ({self.n_cams},)")
         desc = L.ProblemDesc(
             self.n_cams, self.n_pts, n_obs, _ptr(self.cam_flags), _ptr(self.cam_const), ptrs[0], ptrs[1], ptrs[2],
-            1 if on_dev else 0, 0, _ptr(order) if order is not None else None,
+            1 if on_dev else 0, cam_bits, _ptr(order) if order is not None else None,
         )  # fmt: skip
         h = C.c_void_p()
         L.check(lib.cb_ba_problem_create(C.byref(desc), self.device, C.c_void_p(stream), C.byref(h)), "problem_create")

@@ -32,28 +32,33 @@ def is_bundle_adjustment_call(fun: Any, args: tuple) -> bool:
     )
 
 
-def _expected_bounds(par) -> tuple[np.ndarray, np.ndarray]:
+def _expected_bounds(par) -> tuple[np.ndarray, np.ndarray, int]:
     """The only bounds the engine implements: ``BundleParameterization.bounds()``
     (/root/reference/src/caliscope/core/bundle_parameterization.py:151-164): s in [0.5, 2], k1 in [-1, 1],
-    k2 in [-2, 2] on cameras with free intrinsics, everything else unbounded."""
+    k2 in [-2, 2] on cameras with free intrinsics, everything else unbounded.  Returns the camera part (the point part is
+    all -inf / +inf) and the total parameter count."""
     widths = [9 if (b.free_intrinsics and not b.fisheye) else 6 for b in par.blocks]
-    n = int(sum(widths)) + 3 * int(par.n_points)
-    lo, hi = np.full(n, -np.inf), np.full(n, np.inf)
+    ncp = int(sum(widths))
+    lo, hi = np.full(ncp, -np.inf), np.full(ncp, np.inf)
     o = 0
     for w in widths:
         if w == 9:
             lo[o + 6 : o + 9] = (0.5, -1.0, -2.0)
             hi[o + 6 : o + 9] = (2.0, 1.0, 2.0)
         o += w
-    return lo, hi
+    return lo, hi, ncp + 3 * int(par.n_points)
 
 
 def _check_supported(par, lo, hi, use_bounds: bool, x_scale, tr_solver, n: int) -> None:
     """Fail loudly on a call the engine would otherwise answer with different semantics."""
     if use_bounds:
-        elo, ehi = _expected_bounds(par)
+        elo, ehi, n_exp = _expected_bounds(par)
+        ncp = len(elo)
         lo_b, hi_b = np.broadcast_to(lo, (n,)), np.broadcast_to(hi, (n,))
-        if len(elo) != n or not (np.array_equal(lo_b, elo) and np.array_equal(hi_b, ehi)):
+        same = n_exp == n and np.array_equal(lo_b[:ncp], elo) and np.array_equal(hi_b[:ncp], ehi)
+        # the point part must be unbounded: two reductions instead of materialising +-inf vectors to compare with
+        same = same and (n == ncp or (lo_b[ncp:].max() == -np.inf and hi_b[ncp:].min() == np.inf))
+        if not same:
             raise NotImplementedError(
                 "caliscope_b200.least_squares implements exactly BundleParameterization.bounds() "
                 "(s in [0.5, 2], k1 in [-1, 1], k2 in [-2, 2] on free-intrinsics cameras); other bounds are not supported")
@@ -87,7 +92,7 @@ def least_squares(fun, x0, jac="2-point", bounds=(-np.inf, np.inf), method="trf"
     lo, hi = (np.asarray(b, dtype=np.float64) for b in bounds) if isinstance(bounds, (tuple, list)) else (bounds.lb, bounds.ub)
     use_bounds = bool(np.any(np.isfinite(np.atleast_1d(lo))) or np.any(np.isfinite(np.atleast_1d(hi))))
     _check_supported(par, lo, hi, use_bounds, x_scale, tr_solver, np.asarray(x0).shape[0])
-    res = solve_arrays(flags, const, par.n_points, np.asarray(camera_indices), np.asarray(obj_indices),
+    res = solve_arrays(flags, const, par.n_points, np.asarray(camera_indices), np.asarray(obj_indices),  # int16 indices pass as is
                        np.asarray(image_coords, dtype=np.float64), np.asarray(x0, dtype=np.float64),
                        use_bounds=use_bounds, constraints=constraints, ftol=ftol if ftol is not None else 0.0, xtol=xtol if xtol is not None else 0.0,
                        gtol=gtol if gtol is not None else 0.0, max_nfev=max_nfev, loss=loss, f_scale=f_scale,

@@ -74,7 +74,8 @@ typedef struct {
   const int32_t* obs_pt;
   const double* obs_xy;
   int32_t obs_on_device;
-  int32_t pad_;
+  int32_t obs_cam_bits; /* 0 or 32: obs_cam is int32; 16: obs_cam is int16 (what capture_volume.py:353-355 builds) and is
+                           widened on the device -- halves that upload and saves the caller a conversion pass */
   /* Optional (NULL: the engine decides).  Internal camera order, host, n_cams entries: cam_order[slot] = camera index.
    * Only the layout of the reduced camera system depends on it (cameras that see the same points should be neighbours,
    * so that whole 96-column tile pairs of the Schur product are empty); no input or output of the ABI is reordered.

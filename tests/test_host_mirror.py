@@ -205,3 +205,30 @@ def test_every_device_entry_point_refuses_to_run_without_a_gpu():
     buf = (ctypes.c_char * 64)()
     assert lib.cb_peer_create(0, 2, 0, 1024, ctypes.byref(h), buf) == -3  # CB_E_NO_DEVICE
     assert lib.cb_peer_create(5, 2, 0, 1024, ctypes.byref(h), buf) == -1  # CB_E_INVALID: rank >= world_size
+
+
+def test_least_squares_rejects_bounds_it_does_not_implement():
+    """The engine implements exactly BundleParameterization.bounds(); anything else must fail loudly instead of being
+    silently replaced."""
+    from caliscope_b200 import solver
+    from caliscope_b200.bundle_parameterization import BundleParameterization, CameraBlock
+
+    blocks = tuple(CameraBlock(cam_id=c, free_intrinsics=(c != 1), fx_initial=1000.0, fy_initial=1000.0, cx=640.0, cy=360.0,
+                               fisheye=False, dist_fixed=(0.0, 0.0, 0.0)) for c in range(3))  # fmt: skip
+    par = BundleParameterization(blocks=blocks, n_points=5)
+    lo, hi = par.bounds()
+    n = len(lo)
+    solver._check_supported(par, lo, hi, True, "jac", None, n)  # the reference's own bounds pass
+    solver._check_supported(par, -np.inf, np.inf, False, "jac", "lsmr", n)
+    bad_hi = hi.copy()
+    bad_hi[6] = 3.0
+    with pytest.raises(NotImplementedError, match="bounds"):
+        solver._check_supported(par, lo, bad_hi, True, "jac", None, n)
+    bad_lo = lo.copy()
+    bad_lo[-1] = 0.0  # a bound on a world point
+    with pytest.raises(NotImplementedError, match="bounds"):
+        solver._check_supported(par, bad_lo, hi, True, "jac", None, n)
+    with pytest.raises(NotImplementedError, match="x_scale"):
+        solver._check_supported(par, lo, hi, True, 1.0, None, n)
+    with pytest.raises(NotImplementedError, match="tr_solver"):
+        solver._check_supported(par, lo, hi, True, "jac", "exact", n)
