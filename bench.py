@@ -476,7 +476,7 @@ def run_ours(args) -> None:
     wall_ms = 1e3 * (time.perf_counter() - t0)
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
     launches = lib.cb_ba_launch_count() - launches0
-    used_graph = res.used_graph
+    used_graph = res.used_graph_mode
     x_final = res.x
     if world > 1:
         x_final = D.gather_points(res.x, ncp, rig.n_pts, shard)
@@ -509,8 +509,12 @@ def run_ours(args) -> None:
     t1 = time.perf_counter()
     f0.record()
     e2e_nit = 0
+    e_pp_ms = e_sy_ms = 0.0
+    e_pp_n = e_sy_n = 0
     for _ in range(args.steps):
-        e2e_nit += e2e_step().nit
+        r2 = e2e_step()
+        e2e_nit += r2.nit
+        e_pp_ms += r2.rj_ms; e_pp_n += r2.rj_launches; e_sy_ms += r2.syrk_ms; e_sy_n += r2.syrk_launches
     f1.record()
     barrier()
     e2e_wall_ms = 1e3 * (time.perf_counter() - t1)
@@ -538,6 +542,13 @@ def run_ours(args) -> None:
     peak, peak_src = load_peaks()
     ab = algorithmic_bytes(rig)
     pp_bytes = ab["fused"] / world  # each rank's launch covers its shard
+    # Per-kernel durations come from CUDA events recorded around the launches on the solve stream.  The resident arm replays
+    # the whole LM loop as one device-side WHILE graph (no host round trip, and no place for events), so there they come
+    # from the end-to-end arm's timed region, whose first-solve-on-a-fresh-problem runs the same kernels as direct launches.
+    timing_arm = "resident arm (direct launches / per-trial graphs)"
+    if pp_n == 0 and e_pp_n > 0:
+        pp_ms, pp_n, sy_ms, sy_n = e_pp_ms, e_pp_n, e_sy_ms, e_sy_n
+        timing_arm = "end-to-end arm's timed region (direct launches; the resident arm runs the loop as one WHILE graph)"
     pp_avg_ms = pp_ms / max(pp_n, 1)
     achieved = pp_bytes / (pp_avg_ms * 1e-3) / 1e9 if pp_avg_ms > 0 else 0.0
     sf = syrk_flops(rig)
@@ -574,7 +585,8 @@ def run_ours(args) -> None:
             "host": numa,
         },
         "gpu_launches": int(launches),
-        "lm_loop": {"decision": "on the device (LmState)", "trial_replay": "cuda graph" if used_graph else "direct launches",
+        "lm_loop": {"decision": "on the device (LmState)",
+                    "trial_replay": {0: "direct launches", 1: "one CUDA graph per trial", 2: "device loop: one WHILE-conditional graph per solve"}[int(used_graph)],
                     "trials_queued_per_step": trials / args.steps, "host_syncs_per_trial": 0},
         "allreduce_transport": transport_name,
         "obs_residuals_per_sec": rig.n_obs * nfev / (dev_ms * 1e-3),
@@ -600,7 +612,8 @@ def run_ours(args) -> None:
                                           "materialised J (round-1 kernel, SURVEY 8d comparability figure)": 24 + 16 + 16 * P + 48},
             "avg_launch_ms": pp_avg_ms,
             "launches_timed": int(pp_n),
-            "share_of_step": (pp_ms / max(dev_ms, 1e-9)),
+            "share_of_lm_iteration": pp_avg_ms / max(dev_ms / max(nit, 1), 1e-9),
+            "timed_in": timing_arm,
         },
         "roofline_tensor": {
             "kernel": "schur_syrk_kernel (S = Z Z^T on mma.sync.m8n8k4.f64, TMA-staged tiles)",
@@ -614,7 +627,8 @@ def run_ours(args) -> None:
             "flop_per_launch": {"issued (dense tiles)": sf["dense_flop"] / world, "algorithmic sum_j 3 (P n_j)^2": sf["algorithmic_flop"] / world},
             "avg_launch_ms": sy_avg_ms,
             "launches_timed": int(sy_n),
-            "share_of_step": (sy_ms / max(dev_ms, 1e-9)),
+            "share_of_lm_iteration": sy_avg_ms / max(dev_ms / max(nit, 1), 1e-9),
+            "timed_in": timing_arm,
         },
     }
     gold = golden_scipy(args.workload)

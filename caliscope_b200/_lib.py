@@ -129,6 +129,9 @@ SYMBOLS = {
     "cb_ba_cull": (C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(_P), _P, _P, _P]),
     "cb_ba_debug_pcg_time": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "cb_debug_fp64_peak": (C.c_int, [C.c_int, _P, _P]),
+    "cb_csv_write_numeric": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int64, C.c_int32, _P, _P, C.c_int32]),
+    "cb_csv_scan": (C.c_int, [C.c_char_p, _P, _P]),
+    "cb_csv_parse_numeric": (C.c_int, [C.c_char_p, C.c_int64, C.c_int32, _P, _P, _P, C.c_int32]),
     "cb_pnp_ippe": (C.c_int, [C.c_int32, _P, _P, _P, C.c_int64, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P,
                               _P, C.c_int, _P]),
     "cb_stereo_rmse": (C.c_int, [C.c_int32, _P, _P, _P, C.c_int32, _P, _P, _P, C.c_int64, _P, _P, _P, C.c_int32, _P, _P, _P,

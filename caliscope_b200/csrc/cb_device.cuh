@@ -22,6 +22,10 @@ constexpr int CT_SY = 32;    // fy / fx0
 constexpr int CT_FYR = 33;   // fy0 / fx0
 constexpr int CT_FLAGS = 34; // flags as double
 constexpr int CT_SIZE = 36;
+// stride of a camera-table entry in SHARED memory when lanes of a warp read DIFFERENT cameras (point-major kernels): an odd
+// number of doubles, so that the same field of 16 consecutive cameras falls into 16 different 8-byte banks (stride 36 puts
+// them into 4: an 8-way conflict on every one of the ~36 table reads per observation)
+constexpr int CT_SMEM = 37;
 
 constexpr double CB_EPS = 2.220446049250313e-16;
 
@@ -212,6 +216,29 @@ __device__ __forceinline__ void project_obs(const double* __restrict__ cam, bool
 //   Jc[2*P]   d f / d camera (2 x P, row-major); P = 9 slots are zero for a locked camera
 // returns the cost contribution 0.5 * fs^2 * (rho(z0) + rho(z1)).
 // ---------------------------------------------------------------------------------------------
+// light form for the V / g reduction of the point pass: residuals and d f / d X only (no camera block)
+__device__ __forceinline__ void obs_res_jx(const double* __restrict__ cam, double X0, double X1, double X2, double ox,
+                                           double oy, int loss, double fscale, double* __restrict__ f,
+                                           double* __restrict__ JX) {
+  const int flags = (int)cam[CT_FLAGS];
+  ProjOut o;
+  project_obs<true>(cam, (flags & 2) != 0, X0, X1, X2, o);
+  double f0 = (o.u - ox) * cam[CT_IFX0], f1 = (o.v - oy) * cam[CT_IFX0];
+  double w0, w1;
+  robust_row(loss, fscale, f0, w0);
+  robust_row(loss, fscale, f1, w1);
+  f[0] = f0; f[1] = f1;
+  const double sx = cam[CT_SX] * o.iz * w0, sy = cam[CT_SY] * o.iz * w1;
+  const double t0 = sx * o.xa, t1 = sx * o.xb, t2 = -(t0 * o.a + t1 * o.b);
+  const double t3 = sy * o.ya, t4 = sy * o.yb, t5 = -(t3 * o.a + t4 * o.b);
+  const double* R = cam + CT_R;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    JX[k] = t0 * R[k] + t1 * R[3 + k] + t2 * R[6 + k];
+    JX[3 + k] = t3 * R[k] + t4 * R[3 + k] + t5 * R[6 + k];
+  }
+}
+
 template <int P>
 __device__ __forceinline__ double obs_jac(const double* __restrict__ cam, double X0, double X1, double X2,
                                           double ox, double oy, int loss, double fscale, double* __restrict__ f,

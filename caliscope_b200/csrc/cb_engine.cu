@@ -376,6 +376,12 @@ struct CbBaProblem {
   bool graph_valid = false;
   GraphKey graph_key = {};
   TrialGraph tg[2];
+  // device-loop mode: ONE graph whose body (a WHILE conditional node) is the LM trial; the loop ends on the device
+  cudaGraph_t loop_graph = nullptr;
+  cudaGraphExec_t loop_exec = nullptr;
+  bool loop_valid = false, loop_failed = false;
+  GraphKey loop_key = {};
+  int loop_kernels = 0;
   // pcg launch configuration
   int pcg_cs = 1, pcg_rows = 0, pcg_mode = 0, pcg_cl = 1, pcg_npa = 0;
   size_t pcg_smem = 0;
@@ -429,6 +435,9 @@ void destroy_graphs(CbBaProblem* p) {
     g.exec = nullptr; g.graph = nullptr; g.n_kernels = 0;
   }
   p->graph_valid = false;
+  if (p->loop_exec) cudaGraphExecDestroy(p->loop_exec);
+  if (p->loop_graph) cudaGraphDestroy(p->loop_graph);
+  p->loop_exec = nullptr; p->loop_graph = nullptr; p->loop_valid = false;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -881,6 +890,51 @@ int ensure_graphs(CbBaProblem* p, const CbBaOptions* opt) {
   return CB_OK;
 }
 
+// Device-loop mode: a graph with one WHILE conditional node (CUDA 12.4+) whose body is the trial; the last body node sets
+// the loop condition from LmState::done, so the whole solve is ONE graph launch and ONE host synchronisation, and no
+// predicated-off trial is ever queued.  Any failure to build it is remembered and the per-trial graphs are used instead.
+template <int P>
+int ensure_loop_graph(CbBaProblem* p, const CbBaOptions* opt) {
+  CbBaProblem::GraphKey key{opt->nccl_comm, opt->peer_group, opt->rank, opt->world_size};
+  if (p->loop_valid && p->loop_key == key) return CB_OK;
+  if (p->loop_failed) return CB_E_UNSUPPORTED;
+  if (p->loop_exec) { cudaGraphExecDestroy(p->loop_exec); p->loop_exec = nullptr; }
+  if (p->loop_graph) { cudaGraphDestroy(p->loop_graph); p->loop_graph = nullptr; }
+  p->loop_valid = false;
+  if (!p->cap_stream && cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); p->loop_failed = true; return CB_E_UNSUPPORTED; }
+  auto fail = [&](const char* what) {
+    g_last_error = std::string("device-loop graph: ") + what + ": " + cudaGetErrorString(cudaGetLastError());
+    if (p->loop_graph) { cudaGraphDestroy(p->loop_graph); p->loop_graph = nullptr; }
+    p->loop_failed = true;
+    return CB_E_UNSUPPORTED;
+  };
+  if (cudaGraphCreate(&p->loop_graph, 0) != cudaSuccess) return fail("cudaGraphCreate");
+  cudaGraphConditionalHandle h;
+  if (cudaGraphConditionalHandleCreate(&h, p->loop_graph, 1, cudaGraphCondAssignDefault) != cudaSuccess) return fail("cudaGraphConditionalHandleCreate");
+  cudaGraphNodeParams np = {};
+  np.type = cudaGraphNodeTypeConditional;
+  np.conditional.handle = h;
+  np.conditional.type = cudaGraphCondTypeWhile;
+  np.conditional.size = 1;
+  cudaGraphNode_t node;
+  if (cudaGraphAddNode(&node, p->loop_graph, nullptr, 0, &np) != cudaSuccess) return fail("cudaGraphAddNode(conditional)");
+  cudaGraph_t body = np.conditional.phGraph_out[0];
+  if (cudaStreamBeginCaptureToGraph(p->cap_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+    return fail("cudaStreamBeginCaptureToGraph");
+  const long long l0 = g_launches.load();
+  cudaEvent_t none[4] = {nullptr, nullptr, nullptr, nullptr};
+  int rc = enqueue_trial<P>(p, opt, p->cap_stream, none);
+  if (rc == CB_OK) CB_LAUNCH(cb::lm_loop_cond_kernel, 1, 1, 0, p->cap_stream, (const cb::LmState*)p->d_state, h);
+  p->loop_kernels = (int)(g_launches.load() - l0);
+  g_launches.store(l0);
+  cudaError_t e = cudaStreamEndCapture(p->cap_stream, nullptr);
+  if (rc != CB_OK || e != cudaSuccess) return fail("capture of the trial");
+  if (cudaGraphInstantiate(&p->loop_exec, p->loop_graph, 0) != cudaSuccess) return fail("cudaGraphInstantiate");
+  p->loop_key = key;
+  p->loop_valid = true;
+  return CB_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // Levenberg-Marquardt driver: the loop itself runs on the device (cb_lm.cuh); the host only keeps the GPU fed one
 // trial ahead and looks at the state of trial t-1 while trial t executes.
@@ -892,13 +946,17 @@ int lm_solve(CbBaProblem* p, const CbBaOptions* opt, double* x_inout, CbBaResult
   const long long launches0 = g_launches.load();
   std::memset(res, 0, sizeof(*res));
 
-  // One CUDA graph per trial from the second solve on a problem (capture + instantiation cost about as much as the
+  // Replay from CUDA graphs from the second solve on a problem (capture + instantiation cost about as much as the
   // launches of one short solve save), never when a host callback carries the all-reduce (it cannot be captured).
-  // CB_LM_GRAPH = 0: never, 1: from the second solve (default), 2: always.
+  // CB_LM_GRAPH = 0: direct launches, 1 (default): from the second solve: device loop (WHILE graph) on one GPU, per-trial
+  // graphs when sharded, 2: per-trial graphs always, 3: device loop always.
   int graph_mode = 1;
   if (const char* e = std::getenv("CB_LM_GRAPH")) graph_mode = std::atoi(e);
   ++p->n_solves;
-  bool use_graph = opt->allreduce == nullptr && (graph_mode >= 2 || (graph_mode == 1 && (p->n_solves >= 2 || p->graph_valid)));
+  const bool later = p->n_solves >= 2 || p->graph_valid || p->loop_valid;
+  bool use_loop = opt->allreduce == nullptr && (graph_mode == 3 || (graph_mode == 1 && later && !sharded(opt))) && opt->verbose < 2;
+  if (use_loop && ensure_loop_graph<P>(p, opt) != CB_OK) { cudaGetLastError(); use_loop = false; }
+  bool use_graph = !use_loop && opt->allreduce == nullptr && (graph_mode >= 2 || (graph_mode == 1 && later));
   if (use_graph) {
     int rc = ensure_graphs<P>(p, opt);
     if (rc != CB_OK) {
@@ -932,6 +990,14 @@ int lm_solve(CbBaProblem* p, const CbBaOptions* opt, double* x_inout, CbBaResult
   bool done = false;
   long long t = 0;
   int rc = CB_OK;
+  if (use_loop) {
+    // the whole LM loop is one graph launch; the state comes back once
+    cudaError_t e = cudaGraphLaunch(p->loop_exec, st);
+    if (e != cudaSuccess) { g_last_error = std::string("cudaGraphLaunch(loop): ") + cudaGetErrorString(e); rc = CB_E_CUDA; }
+    cudaMemcpyAsync(&p->h_state[1], p->d_state, sizeof(cb::LmState), cudaMemcpyDeviceToHost, st);
+    t = 2;  // final state in slot (t - 1) & 1
+    done = true;
+  }
   while (!done) {
     if (use_graph) {
       cudaError_t e = cudaGraphLaunch(p->tg[t & 1].exec, st);
@@ -1002,15 +1068,20 @@ int lm_solve(CbBaProblem* p, const CbBaOptions* opt, double* x_inout, CbBaResult
   res->rj_launches = pp_launches;
   res->syrk_ms = sy_ms_total;
   res->syrk_launches = sy_launches;
+  if (use_loop) {
+    trials = fin.nfev - 1 + ((fin.status == 1 || fin.err) ? 1 : 0);
+    g_launches.fetch_add((long long)p->loop_kernels * trials);
+    res->kernel_launches = g_launches.load() - launches0;
+  }
   res->trials_queued = trials;
-  res->used_graph = use_graph ? 1 : 0;
+  res->used_graph = use_loop ? 2 : use_graph ? 1 : 0;
   if (fin.err == cb::LM_ERR_STUCK_NONFINITE)
     g_last_error = "every trial step is non-finite with the damping at its cap; stopped with status 0";
   if (opt->verbose >= 1 && opt->rank == 0)
     std::fprintf(stderr,
                  "[caliscope_b200] status %d nfev %lld njev %lld nit %lld cost %.15e -> %.15e |g| %.2e  %.3f ms (%lld trials queued, %s)\n",
                  fin.status, (long long)fin.nfev, (long long)fin.njev, (long long)fin.nit, fin.initial_cost, fin.cost,
-                 fin.gnorm, ms, trials, use_graph ? "graph" : "direct");
+                 fin.gnorm, ms, trials, use_loop ? "device loop" : use_graph ? "graph" : "direct");
   return CB_OK;
 }
 
@@ -1280,13 +1351,23 @@ static int build_schur_items(CbBaProblem* p, cudaStream_t st) {
     std::vector<unsigned long long> mask((size_t)p->n_pts);
     CB_CUDA(cudaMemcpyAsync(mask.data(), d_mask, sizeof(unsigned long long) * p->n_pts, cudaMemcpyDeviceToHost, st));
     CB_CUDA(cudaStreamSynchronize(st));
+    // incidence counts per tile pair, through the histogram of distinct masks (dense rigs: one mask, all tiles)
     std::vector<long long> cnt(nt, 0);
-    for (int j = 0; j < p->n_pts; ++j) {
-      unsigned long long m = mask[j];
-      for (unsigned long long a = m; a; a &= a - 1) {
-        const int I = __builtin_ctzll(a);
-        for (unsigned long long b2 = a; b2; b2 &= b2 - 1) cnt[tof[(size_t)I * nb + __builtin_ctzll(b2)]]++;
+    {
+      std::map<unsigned long long, long long> hist;
+      unsigned long long last = ~0ull;
+      long long run = 0;
+      for (int j = 0; j < p->n_pts; ++j) {  // run-length first: neighbouring points usually share their mask
+        if (mask[j] == last) { ++run; continue; }
+        if (run) hist[last] += run;
+        last = mask[j]; run = 1;
       }
+      if (run) hist[last] += run;
+      for (auto& kv : hist)
+        for (unsigned long long a = kv.first; a; a &= a - 1) {
+          const int I = __builtin_ctzll(a);
+          for (unsigned long long b2 = a; b2; b2 &= b2 - 1) cnt[tof[(size_t)I * nb + __builtin_ctzll(b2)]] += kv.second;
+        }
     }
     double listed = 0.0, dense = 0.0;
     for (int I = 0; I < nb; ++I)
@@ -1424,12 +1505,14 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
   p->n_split = std::max(1, std::min(p->k_chunks, p->num_sms / std::max(p->n_tiles, 1)));
   // point kernels: 8 lanes per point when points have few observations (typical rigs: 2-6 cameras per point), a whole
   // warp otherwise; persistent grid (2 CTAs per SM) so the camera table is staged into shared memory once per CTA
-  p->pt_lanes = ((double)p->n_obs / std::max(p->n_pts, 1) <= 10.0) ? 8 : 32;
+  // (8 lanes keep every lane busy for any group size that is not tiny against 8; a whole warp per point only pays when
+  // points carry hundreds of rows -- static objects seen in every frame)
+  p->pt_lanes = ((double)p->n_obs / std::max(p->n_pts, 1) <= 96.0) ? 8 : 32;
   if (const char* ev = std::getenv("CB_PT_LANES")) p->pt_lanes = std::atoi(ev) == 8 ? 8 : 32;
   {
     const int per_block = cb::PT_WARPS * (32 / p->pt_lanes);
     p->pt_grid = std::max(1, std::min(cdiv(std::max(p->n_pts, 1), per_block), 2 * p->num_sms));
-    const size_t tab_bytes = sizeof(double) * cb::CT_SIZE * (size_t)p->n_cams;
+    const size_t tab_bytes = sizeof(double) * cb::CT_SMEM * (size_t)p->n_cams;
     p->cam_in_smem = tab_bytes <= 64 * 1024 ? 1 : 0;
     p->pt_smem = p->cam_in_smem ? tab_bytes : 0;
     p->bs_smem = sizeof(double) * (((size_t)p->nP + 3) & ~(size_t)3) + (p->cam_in_smem ? tab_bytes : 0);
@@ -2725,6 +2808,222 @@ int cb_stereo_rmse(int32_t n_cams, const int32_t* cam_fisheye, const double* cam
     cudaEventElapsedTime(&ms, ev[2], ev[3]); stats->dlt_ms = ms;
     cudaEventElapsedTime(&ms, ev[0], ev[3]); stats->total_ms = ms;
     stats->kernel_launches = (int)(g_launches.load() - launches0);
+  }
+  return CB_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// numeric CSV tables at the boundary; see cb_io.h
+// ------------------------------------------------------------------------------------------
+#include "cb_io.h"
+
+namespace {
+struct MappedFile {
+  const char* data = nullptr;
+  size_t size = 0;
+  int fd = -1;
+  ~MappedFile() {
+    if (data && size) munmap((void*)data, size);
+    if (fd >= 0) close(fd);
+  }
+  int open_ro(const char* path) {
+    fd = ::open(path, O_RDONLY);
+    if (fd < 0) { g_last_error = std::string("cannot open ") + path + ": " + std::strerror(errno); return CB_E_INVALID; }
+    struct stat sb;
+    if (fstat(fd, &sb) != 0) { g_last_error = std::string("fstat ") + path; return CB_E_INVALID; }
+    size = (size_t)sb.st_size;
+    if (size == 0) return CB_OK;
+    void* m = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (m == MAP_FAILED) { g_last_error = std::string("mmap ") + path + ": " + std::strerror(errno); data = nullptr; return CB_E_INVALID; }
+    data = (const char*)m;
+    return CB_OK;
+  }
+};
+
+// start of the body (after the header line) or size
+size_t csv_body_start(const MappedFile& f) {
+  const char* nl = (const char*)memchr(f.data, '\n', f.size);
+  return nl ? (size_t)(nl - f.data) + 1 : f.size;
+}
+
+// line-aligned chunk boundaries of [b0, size)
+std::vector<size_t> csv_chunks(const MappedFile& f, size_t b0, int n) {
+  std::vector<size_t> cut{b0};
+  for (int t = 1; t < n; ++t) {
+    size_t pos = b0 + (f.size - b0) * (size_t)t / (size_t)n;
+    if (pos <= cut.back()) continue;
+    const char* nl = (const char*)memchr(f.data + pos, '\n', f.size - pos);
+    if (!nl) break;
+    pos = (size_t)(nl - f.data) + 1;
+    if (pos > cut.back() && pos < f.size) cut.push_back(pos);
+  }
+  cut.push_back(f.size);
+  return cut;
+}
+
+inline bool blank_line(const char* b, const char* e) {
+  for (const char* q = b; q < e; ++q)
+    if (*q != '\r' && *q != ' ') return false;
+  return true;
+}
+}  // namespace
+
+extern "C" {
+
+int cb_csv_write_numeric(const char* path, const char* header, int64_t n_rows, int32_t n_cols, const int32_t* col_kind,
+                         const void* const* col_data, int32_t n_threads) {
+  if (!path || !header || n_rows < 0 || n_cols <= 0 || !col_kind || !col_data) { g_last_error = "cb_csv_write_numeric: bad argument"; return CB_E_INVALID; }
+  const int nt = cbio::n_workers(n_threads, (size_t)n_rows, 20000);
+  std::vector<std::string> parts((size_t)nt);
+  cbio::parallel_for(nt, [&](int t) {
+    const int64_t r0 = n_rows * t / nt, r1 = n_rows * (t + 1) / nt;
+    std::string& out = parts[(size_t)t];
+    out.reserve((size_t)(r1 - r0) * (size_t)n_cols * 12);
+    for (int64_t r = r0; r < r1; ++r) {
+      for (int c = 0; c < n_cols; ++c) {
+        if (c) out.push_back(',');
+        if (col_kind[c] == 0) cbio::append_i64(out, ((const long long*)col_data[c])[r]);
+        else cbio::append_f6(out, ((const double*)col_data[c])[r]);
+      }
+      out.push_back('\n');
+    }
+  });
+  // temp file + fsync + atomic rename, as persistence._safe_write_csv (persistence.py:27-41)
+  const std::string tmp = std::string(path) + ".tmp";
+  const int fd = ::open(tmp.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+  if (fd < 0) { g_last_error = "cannot create " + tmp + ": " + std::strerror(errno); return CB_E_INVALID; }
+  auto write_all = [&](const char* p, size_t n) {
+    while (n) {
+      const ssize_t w = ::write(fd, p, n);
+      if (w < 0) { if (errno == EINTR) continue; return false; }
+      p += w; n -= (size_t)w;
+    }
+    return true;
+  };
+  bool ok = write_all(header, std::strlen(header)) && write_all("\n", 1);
+  for (auto& s : parts) ok = ok && write_all(s.data(), s.size());
+  ok = ok && fsync(fd) == 0;
+  ::close(fd);
+  if (!ok || std::rename(tmp.c_str(), path) != 0) {
+    g_last_error = std::string("writing ") + path + ": " + std::strerror(errno);
+    std::remove(tmp.c_str());
+    return CB_E_INVALID;
+  }
+  return CB_OK;
+}
+
+int cb_csv_scan(const char* path, int64_t* n_rows, int32_t* n_cols) {
+  if (!path || !n_rows || !n_cols) { g_last_error = "cb_csv_scan: bad argument"; return CB_E_INVALID; }
+  MappedFile f;
+  CB_TRY(f.open_ro(path));
+  *n_rows = 0; *n_cols = 0;
+  if (f.size == 0) return CB_OK;
+  const size_t b0 = csv_body_start(f);
+  int cols = 1;
+  for (size_t i = 0; i + 1 < b0 || (i < b0 && f.data[i] != '\n'); ++i)
+    if (f.data[i] == ',') ++cols;
+  *n_cols = cols;
+  const int nt = cbio::n_workers(0, f.size - b0, 1 << 20);
+  const std::vector<size_t> cut = csv_chunks(f, b0, nt);
+  std::vector<long long> cnt(cut.size(), 0);
+  cbio::parallel_for((int)cut.size() - 1, [&](int t) {
+    const char *p = f.data + cut[t], *e = f.data + cut[t + 1];
+    long long c = 0;
+    while (p < e) {
+      const char* nl = (const char*)memchr(p, '\n', (size_t)(e - p));
+      const char* le = nl ? nl : e;
+      if (!blank_line(p, le)) ++c;
+      p = nl ? nl + 1 : e;
+    }
+    cnt[(size_t)t] = c;
+  });
+  for (long long c : cnt) *n_rows += c;
+  return CB_OK;
+}
+
+int cb_csv_parse_numeric(const char* path, int64_t n_rows, int32_t n_cols, double* out, int32_t* col_all_int,
+                         int32_t* col_has_empty, int32_t n_threads) {
+  if (!path || n_rows < 0 || n_cols <= 0 || !out || !col_all_int || !col_has_empty) { g_last_error = "cb_csv_parse_numeric: bad argument"; return CB_E_INVALID; }
+  MappedFile f;
+  CB_TRY(f.open_ro(path));
+  for (int c = 0; c < n_cols; ++c) { col_all_int[c] = 1; col_has_empty[c] = 0; }
+  if (f.size == 0 || n_rows == 0) return CB_OK;
+  const size_t b0 = csv_body_start(f);
+  const int nt = cbio::n_workers(n_threads, f.size - b0, 1 << 20);
+  const std::vector<size_t> cut = csv_chunks(f, b0, nt);
+  const int nc = (int)cut.size() - 1;
+  // rows per chunk -> row offsets
+  std::vector<long long> cnt((size_t)nc + 1, 0);
+  cbio::parallel_for(nc, [&](int t) {
+    const char *p = f.data + cut[t], *e = f.data + cut[t + 1];
+    long long c = 0;
+    while (p < e) {
+      const char* nl = (const char*)memchr(p, '\n', (size_t)(e - p));
+      const char* le = nl ? nl : e;
+      if (!blank_line(p, le)) ++c;
+      p = nl ? nl + 1 : e;
+    }
+    cnt[(size_t)t + 1] = c;
+  });
+  for (int t = 0; t < nc; ++t) cnt[(size_t)t + 1] += cnt[(size_t)t];
+  if (cnt[(size_t)nc] != n_rows) { g_last_error = "cb_csv_parse_numeric: row count changed since cb_csv_scan"; return CB_E_INVALID; }
+  std::vector<std::vector<int>> all_int((size_t)nc, std::vector<int>((size_t)n_cols, 1)), has_empty((size_t)nc, std::vector<int>((size_t)n_cols, 0));
+  std::vector<long long> bad((size_t)nc, -1);
+  const double nan = std::nan("");
+  cbio::parallel_for(nc, [&](int t) {
+    const char *p = f.data + cut[t], *e = f.data + cut[t + 1];
+    long long row = cnt[(size_t)t];
+    while (p < e) {
+      const char* nl = (const char*)memchr(p, '\n', (size_t)(e - p));
+      const char* le = nl ? nl : e;
+      const char* next = nl ? nl + 1 : e;
+      if (le > p && le[-1] == '\r') --le;
+      if (blank_line(p, le)) { p = next; continue; }
+      const char* q = p;
+      for (int c = 0; c < n_cols; ++c) {
+        const char* fe = (const char*)memchr(q, ',', (size_t)(le - q));
+        if (!fe || c == n_cols - 1) fe = (c == n_cols - 1) ? le : (fe ? fe : le);
+        double v = nan;
+        if (fe == q) {
+          has_empty[(size_t)t][(size_t)c] = 1;
+          all_int[(size_t)t][(size_t)c] = 0;
+        } else {
+          const char* endp = cbio::precise_xstrtod(q, fe, &v);
+          if (endp != fe) {
+            // nan / inf spellings pandas accepts
+            std::string tok(q, fe);
+            if (tok == "nan" || tok == "NaN" || tok == "NA" || tok == "null" || tok == "NULL" || tok == "N/A" || tok == "n/a") { v = nan; has_empty[(size_t)t][(size_t)c] = 1; }
+            else if (tok == "inf" || tok == "Inf" || tok == "+inf") v = INFINITY;
+            else if (tok == "-inf" || tok == "-Inf") v = -INFINITY;
+            else { bad[(size_t)t] = row; return; }
+            all_int[(size_t)t][(size_t)c] = 0;
+          } else {
+            for (const char* z = q; z < fe; ++z)
+              if (!((*z >= '0' && *z <= '9') || ((*z == '-' || *z == '+') && z == q))) { all_int[(size_t)t][(size_t)c] = 0; break; }
+          }
+        }
+        out[(size_t)c * (size_t)n_rows + (size_t)row] = v;
+        q = (fe < le) ? fe + 1 : le;
+        if (fe >= le && c < n_cols - 1) {  // short row: remaining fields empty
+          for (int c2 = c + 1; c2 < n_cols; ++c2) {
+            out[(size_t)c2 * (size_t)n_rows + (size_t)row] = nan;
+            has_empty[(size_t)t][(size_t)c2] = 1; all_int[(size_t)t][(size_t)c2] = 0;
+          }
+          break;
+        }
+      }
+      ++row;
+      p = next;
+    }
+  });
+  for (int t = 0; t < nc; ++t) {
+    if (bad[(size_t)t] >= 0) { g_last_error = "cb_csv_parse_numeric: non-numeric field in data row " + std::to_string(bad[(size_t)t]); return CB_E_INVALID; }
+    for (int c = 0; c < n_cols; ++c) {
+      if (!all_int[(size_t)t][(size_t)c]) col_all_int[c] = 0;
+      if (has_empty[(size_t)t][(size_t)c]) col_has_empty[c] = 1;
+    }
   }
   return CB_OK;
 }

@@ -63,10 +63,12 @@ pt_pass_kernel(const LmState* __restrict__ st, const int* __restrict__ pt_start,
   const double fscale = st->fscale;
   const double* ctab = camtab2.p[cur];
   const double* xp4 = xp2.p[cur];
+  int cstride = CT_SIZE;
   if (cam_in_smem) {
-    for (int i = threadIdx.x; i < n_cams * CT_SIZE; i += blockDim.x) pt_sm[i] = ctab[i];
+    for (int i = threadIdx.x; i < n_cams * CT_SIZE; i += blockDim.x) pt_sm[(i / CT_SIZE) * CT_SMEM + i % CT_SIZE] = ctab[i];
     __syncthreads();
     ctab = pt_sm;
+    cstride = CT_SMEM;
   }
   constexpr int GPW = 32 / LANES;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -83,28 +85,18 @@ pt_pass_kernel(const LmState* __restrict__ st, const int* __restrict__ pt_start,
     }
     (void)X3;
     const bool in_comp = valid && pt_comp != nullptr && pt_comp[j] >= 0;
-    // ---- phase 1: V, g over the point's observations; the first batch stays in registers for phase 2
+    // ---- phase 1: V, g over the point's observations (residual and d f / d X only)
     double v[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) v[k] = 0.0;
-    double kf[2], kJX[6], kJc[2 * P];
-    int kcam = -1;
     for (int pos = s + gl; pos < e; pos += LANES) {
       const int cam = pm_cam[pos];
       const double2 xy = pm_xy[pos];
-      double f[2], JX[6], Jc[2 * P];
-      obs_jac<P>(ctab + (size_t)cam * CT_SIZE, X0, X1, X2, xy.x, xy.y, loss, fscale, f, JX, Jc);
+      double f[2], JX[6];
+      obs_res_jx(ctab + (size_t)cam * cstride, X0, X1, X2, xy.x, xy.y, loss, fscale, f, JX);
       v[0] += JX[0] * JX[0] + JX[3] * JX[3]; v[1] += JX[0] * JX[1] + JX[3] * JX[4]; v[2] += JX[0] * JX[2] + JX[3] * JX[5];
       v[3] += JX[1] * JX[1] + JX[4] * JX[4]; v[4] += JX[1] * JX[2] + JX[4] * JX[5]; v[5] += JX[2] * JX[2] + JX[5] * JX[5];
       v[6] += JX[0] * f[0] + JX[3] * f[1]; v[7] += JX[1] * f[0] + JX[4] * f[1]; v[8] += JX[2] * f[0] + JX[5] * f[1];
-      if (!DUPS && pos == s + gl) {
-        kcam = cam;
-        kf[0] = f[0]; kf[1] = f[1];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) kJX[k] = JX[k];
-#pragma unroll
-        for (int k = 0; k < 2 * P; ++k) kJc[k] = Jc[k];
-      }
     }
 #pragma unroll
     for (int k = 0; k < 9; ++k) v[k] = group_sum<LANES>(v[k]);
@@ -136,17 +128,9 @@ pt_pass_kernel(const LmState* __restrict__ st, const int* __restrict__ pt_start,
       double f[2], JX[6], Jc[2 * P];
       double z[3][P];
       if constexpr (!DUPS) {
-        if (pos == s + gl) {
-          cam = kcam;
-#pragma unroll
-          for (int k = 0; k < 6; ++k) JX[k] = kJX[k];
-#pragma unroll
-          for (int k = 0; k < 2 * P; ++k) Jc[k] = kJc[k];
-        } else {
-          cam = pm_cam[pos];
-          const double2 xy = pm_xy[pos];
-          obs_jac<P>(ctab + (size_t)cam * CT_SIZE, X0, X1, X2, xy.x, xy.y, loss, fscale, f, JX, Jc);
-        }
+        cam = pm_cam[pos];
+        const double2 xy = pm_xy[pos];
+        obs_jac<P>(ctab + (size_t)cam * cstride, X0, X1, X2, xy.x, xy.y, loss, fscale, f, JX, Jc);
         const double q00 = JX[0] * Li[0], q01 = JX[0] * Li[1] + JX[1] * Li[2], q02 = JX[0] * Li[3] + JX[1] * Li[4] + JX[2] * Li[5];
         const double q10 = JX[3] * Li[0], q11 = JX[3] * Li[1] + JX[4] * Li[2], q12 = JX[3] * Li[3] + JX[4] * Li[4] + JX[5] * Li[5];
 #pragma unroll
@@ -165,7 +149,7 @@ pt_pass_kernel(const LmState* __restrict__ st, const int* __restrict__ pt_start,
         int r = pos;
         do {
           const double2 xy = pm_xy[r];
-          obs_jac<P>(ctab + (size_t)cam * CT_SIZE, X0, X1, X2, xy.x, xy.y, loss, fscale, f, JX, Jc);
+          obs_jac<P>(ctab + (size_t)cam * cstride, X0, X1, X2, xy.x, xy.y, loss, fscale, f, JX, Jc);
           const double q00 = JX[0] * Li[0], q01 = JX[0] * Li[1] + JX[1] * Li[2], q02 = JX[0] * Li[3] + JX[1] * Li[4] + JX[2] * Li[5];
           const double q10 = JX[3] * Li[0], q11 = JX[3] * Li[1] + JX[4] * Li[2], q12 = JX[3] * Li[3] + JX[4] * Li[4] + JX[5] * Li[5];
 #pragma unroll
@@ -231,10 +215,12 @@ pt_backsub_kernel(const LmState* __restrict__ st, const int* __restrict__ pt_sta
   const double* xp4 = xp2.p[cur];
   double* xp4_new = xp2.p[cur ^ 1];
   for (int i = threadIdx.x; i < nP; i += blockDim.x) dcs[i] = dc[i];
+  int cstride = CT_SIZE;
   if (cam_in_smem) {
     double* cs = bs_sm + ((nP + 3) & ~3);
-    for (int i = threadIdx.x; i < n_cams * CT_SIZE; i += blockDim.x) cs[i] = ctab[i];
+    for (int i = threadIdx.x; i < n_cams * CT_SIZE; i += blockDim.x) cs[(i / CT_SIZE) * CT_SMEM + i % CT_SIZE] = ctab[i];
     ctab = cs;
+    cstride = CT_SMEM;
   }
   __syncthreads();
   constexpr int GPW = 32 / LANES;
@@ -256,7 +242,7 @@ pt_backsub_kernel(const LmState* __restrict__ st, const int* __restrict__ pt_sta
       const int cam = pm_cam[pos];
       const double2 xy = pm_xy[pos];
       double f[2], JX[6], Jc[2 * P];
-      obs_jac<P>(ctab + (size_t)cam * CT_SIZE, X0, X1, X2, xy.x, xy.y, loss, fscale, f, JX, Jc);
+      obs_jac<P>(ctab + (size_t)cam * cstride, X0, X1, X2, xy.x, xy.y, loss, fscale, f, JX, Jc);
       const double* d = dcs + cam * P;
       double s0 = 0.0, s1 = 0.0;
 #pragma unroll
@@ -553,6 +539,11 @@ trial_reduce_kernel(LmState* __restrict__ st, int mode, int n_cams, const int* _
       }
     }
   }
+}
+
+// Last node of the WHILE-loop body (device-loop mode): keep looping until the state machine says done.
+__global__ void lm_loop_cond_kernel(const LmState* __restrict__ st, cudaGraphConditionalHandle h) {
+  cudaGraphSetConditional(h, st->done ? 0u : 1u);
 }
 
 }  // namespace cb

@@ -55,6 +55,7 @@ class SolveResult:
     syrk_launches: int = 0
     trials_queued: int = 0
     used_graph: bool = False
+    used_graph_mode: int = 0  # 0 direct launches, 1 one graph per trial, 2 device loop (WHILE graph)
     success: bool = True
     message: str = ""
 
@@ -332,5 +333,5 @@ class BAProblem:
             initial_cost=res.initial_cost, optimality=res.optimality, lambda_final=res.lambda_final,
             pcg_iterations=res.pcg_iterations, kernel_launches=res.kernel_launches, solve_ms=res.solve_ms,
             rj_ms=res.rj_ms, rj_launches=res.rj_launches, syrk_ms=res.syrk_ms, syrk_launches=res.syrk_launches,
-            trials_queued=res.trials_queued, used_graph=bool(res.used_graph),
+            trials_queued=res.trials_queued, used_graph=bool(res.used_graph), used_graph_mode=int(res.used_graph),
         )  # fmt: skip

@@ -36,7 +36,8 @@ def install(full: bool = False) -> None:
     ``ImagePoints.triangulate`` (:416-559; pixels -> undistortion -> DLT in one device call) become the GPU
     versions; and seam S4: the stage functions of the extrinsic bootstrap
     (``caliscope.core.bootstrap_pose.pose_network_builder``: PnP per group, relative poses, outlier rejection, aggregation,
-    stereo RMSE) become ``caliscope_b200.bootstrap``'s."""
+    stereo RMSE) become ``caliscope_b200.bootstrap``'s; and seam S5: ``ImagePoints`` / ``WorldPoints`` ``.to_csv`` /
+    ``.from_csv`` go through the native numeric-CSV writer / parser (``caliscope_b200.tables``; byte-identical files)."""
     global _original
     from . import _lib
 
@@ -81,6 +82,45 @@ def install(full: bool = False) -> None:
             setattr(pnb, name, getattr(bootstrap, name))
 
 
+        # seam S5: the numeric CSV tables (ImagePoints / WorldPoints .to_csv / .from_csv) through the native writer / parser
+        from . import tables
+
+        pd_mod = importlib.import_module("caliscope.core.point_data")
+        for cls_name in ("ImagePoints", "WorldPoints"):
+            cls_t = getattr(pd_mod, cls_name)
+            if (cls_name, "to_csv") not in _original_tables:
+                _original_tables[(cls_name, "to_csv")] = cls_t.__dict__["to_csv"]
+                _original_tables[(cls_name, "from_csv")] = cls_t.__dict__["from_csv"]
+            cls_t.to_csv = _make_to_csv(cls_name, tables)
+            cls_t.from_csv = classmethod(_make_from_csv(tables))
+
+
+def _make_to_csv(cls_name: str, tables):
+    def to_csv(self, path) -> None:
+        """Same file, byte for byte, as the reference's to_csv (point_data.py:358-373 / :662-677)."""
+        from pathlib import Path
+
+        from caliscope.persistence import PersistenceError
+
+        try:
+            tables.write_table_csv(self._df, Path(path))
+        except NotImplementedError:
+            raise
+        except Exception as e:
+            what = "image points" if cls_name == "ImagePoints" else "world points"
+            raise PersistenceError(f"Failed to save {what} to {path}: {e}") from e
+
+    return to_csv
+
+
+def _make_from_csv(tables):
+    def from_csv(cls, path):
+        return cls(tables.read_table_csv(path))
+
+    return from_csv
+
+
+_original_tables: dict = {}
 _BOOTSTRAP_FUNCTIONS = ("compute_camera_to_object_poses_pnp", "compute_relative_poses", "reject_outliers", "aggregate_poses",
                         "estimate_pnp_paired_pose_network")
 _original_bootstrap: dict = {}
@@ -104,6 +144,11 @@ def uninstall() -> None:
             else:
                 setattr(pd_mod, name, fn)
         _original_functions.clear()
+    if _original_tables:
+        pd_mod = importlib.import_module("caliscope.core.point_data")
+        for (cls_name, attr), fn in _original_tables.items():
+            setattr(getattr(pd_mod, cls_name), attr, fn)
+        _original_tables.clear()
     if _original_bootstrap:
         pnb = importlib.import_module("caliscope.core.bootstrap_pose.pose_network_builder")
         for name, fn in _original_bootstrap.items():

@@ -134,7 +134,7 @@ typedef struct {
   double syrk_ms;  /* total device time spent in the Schur product kernel */
   int64_t syrk_launches;
   int64_t trials_queued; /* LM trials handed to the device (the last one runs predicated-off) */
-  int32_t used_graph;    /* 1: trials were replayed from a CUDA graph, 0: launched directly */
+  int32_t used_graph;    /* 0: trials launched directly, 1: one CUDA graph per trial, 2: device loop (one WHILE-conditional graph per solve) */
   int32_t pad_;
 } CbBaResult;
 
@@ -306,6 +306,22 @@ int cb_stereo_rmse(int32_t n_cams, const int32_t* cam_fisheye, const double* cam
                    int32_t n_pairs, const int32_t* pair_a, const int32_t* pair_b, const double* pair_Rt, int64_t n_obs,
                    const int32_t* obs_cam, const int64_t* obs_key, const double* obs_px, int32_t min_common,
                    double* rmse_out, int64_t* count_out, CbTriStats* stats, int device, void* stream);
+
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Numeric CSV tables at the boundary of the path: xy_<TRACKER>.csv / xyz_<TRACKER>.csv as written
+ * by ImagePoints.to_csv / WorldPoints.to_csv (reference core/point_data.py:358-373, 662-677 through
+ * persistence._safe_write_csv, persistence.py:27-41: `to_csv(index=False, float_format="%.6f")`, temp file + fsync +
+ * rename) and read by pd.read_csv.  Byte-identical files, all host cores; no device work.
+ *   col_kind[c]: 0 = int64 column, 1 = float64 column (NaN -> empty field).  header: the column names joined by ','.
+ *   cb_csv_parse_numeric: out is column-major float64 [n_cols][n_rows] (sizes from cb_csv_scan); col_all_int / col_has_empty
+ *   let the caller rebuild pandas' dtypes (int64 iff every field is an integer literal).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int cb_csv_write_numeric(const char* path, const char* header, int64_t n_rows, int32_t n_cols, const int32_t* col_kind,
+                         const void* const* col_data, int32_t n_threads);
+int cb_csv_scan(const char* path, int64_t* n_rows, int32_t* n_cols);
+int cb_csv_parse_numeric(const char* path, int64_t n_rows, int32_t n_cols, double* out, int32_t* col_all_int,
+                         int32_t* col_has_empty, int32_t n_threads);
 
 #ifdef __cplusplus
 }

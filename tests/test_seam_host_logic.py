@@ -363,3 +363,27 @@ def test_seam_install_full_patches_bootstrap_and_restores():
         for n in seam._BOOTSTRAP_FUNCTIONS:
             assert getattr(pnb, n) is getattr(B, n)
     assert [getattr(pnb, n) for n in seam._BOOTSTRAP_FUNCTIONS] == before
+
+
+def test_s5_point_tables_round_trip_through_the_seam(session_volume, tmp_path):
+    """ImagePoints / WorldPoints .to_csv / .from_csv behind seam S5: same bytes as the reference writes, same frames back."""
+    import caliscope.core.point_data as pd_mod
+    import caliscope_b200.seam as seam
+
+    cv = session_volume
+    ref_xy, ref_xyz = tmp_path / "ref_xy.csv", tmp_path / "ref_xyz.csv"
+    cv.image_points.to_csv(ref_xy)
+    cv.world_points.to_csv(ref_xyz)
+    before = (pd_mod.ImagePoints.__dict__["to_csv"], pd_mod.ImagePoints.__dict__["from_csv"])
+    with seam.installed(full=True):
+        out_xy, out_xyz = tmp_path / "xy.csv", tmp_path / "xyz.csv"
+        cv.image_points.to_csv(out_xy)
+        cv.world_points.to_csv(out_xyz)
+        assert out_xy.read_bytes() == ref_xy.read_bytes() and out_xyz.read_bytes() == ref_xyz.read_bytes()
+        ip = pd_mod.ImagePoints.from_csv(out_xy)
+        wp = pd_mod.WorldPoints.from_csv(out_xyz)
+    assert (pd_mod.ImagePoints.__dict__["to_csv"], pd_mod.ImagePoints.__dict__["from_csv"]) == before
+    import pandas as pd
+
+    pd.testing.assert_frame_equal(ip.df, pd_mod.ImagePoints.from_csv(ref_xy).df, check_exact=True)
+    pd.testing.assert_frame_equal(wp.df, pd_mod.WorldPoints.from_csv(ref_xyz).df, check_exact=True)
