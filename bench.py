@@ -761,6 +761,93 @@ def run_pipeline(args) -> None:
         dist.destroy_process_group()
 
 
+def run_bootstrap(args) -> None:
+    """The extrinsic bootstrap (what produces bundle adjustment's start vector) on a synthetic
+    64-camera board session: one step = PnP of every (camera, frame, board) group + relative poses + IQR outlier rule +
+    quaternion average + stereo RMSE of every camera pair, from host arrays."""
+    import torch
+
+    from caliscope_b200 import bootstrap as B
+    from caliscope_b200 import synthetic
+
+    n_frames = 1000
+    ses = synthetic.make_board_session(64, n_frames, seed=0)
+    tab = B.CameraTables(ses.cam_ids, {int(c): i for i, c in enumerate(ses.cam_ids)}, ses.cam_k, ses.cam_dist, ses.cam_fisheye,
+                         np.zeros(len(ses.cam_ids), bool), np.ones(len(ses.cam_ids), bool))  # fmt: skip
+    numa = pin_to_gpu_numa(0)
+    stats = {}
+
+    def step():
+        t0 = time.perf_counter()
+        res = B.pnp_arrays(tab, ses.cam_id, ses.sync_index, ses.object_id, ses.img_xy, ses.obj_xyz)
+        t1 = time.perf_counter()
+        live = res.status != B.PNP_TOO_FEW
+        rel = B.relative_pose_arrays(res.keys[live], res.R[live], res.t[live], tab)
+        pairs, _, R, t, cnt = B.filter_and_aggregate(rel, 1.5)
+        t2 = time.perf_counter()
+        rmse, ncom = B.stereo_rmse_arrays(tab, pairs, R, t, ses.cam_id, ses.sync_index, ses.object_id, ses.keypoint_id, ses.img_xy)
+        t3 = time.perf_counter()
+        stats.update(pnp_s=t1 - t0, host_s=t2 - t1, stereo_s=t3 - t2, groups=len(res.keys), rel=len(rel.pair_a), pairs=len(pairs),
+                     pnp_kernel_ms=res.kernel_ms, launches=res.launches, fallback=int((res.status == B.PNP_OK_FALLBACK).sum()))
+        return res, pairs, R, t, rmse
+
+    for _ in range(args.warmup):
+        out = step()
+    torch.cuda.synchronize()
+    launches0 = B.L.load().cb_ba_launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = step()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    launches = B.L.load().cb_ba_launch_count() - launches0
+    res, pairs, R, t, rmse = out
+    # truth: aggregated relative poses against the generator's cameras
+    err_R = err_t = 0.0
+    for k, (a, b) in enumerate(pairs):
+        Ra, Rb = synthetic._rot(ses.rvec[a]), synthetic._rot(ses.rvec[b])
+        err_R = max(err_R, float(np.abs(R[k] - Rb @ Ra.T).max()))
+        err_t = max(err_t, float(np.abs(t[k] - (ses.tvec[b] - Rb @ Ra.T @ ses.tvec[a])).max()))
+    line = {
+        "metric": "bootstrap_observations_per_sec", "value": ses.n_obs * args.steps / wall, "unit": "observations/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"bootstrap64: 64-camera ring, 7x5-corner board, {n_frames} frames, {ses.n_obs} observations, "
+                   f"{stats['groups']} PnP groups, {stats['rel']} relative poses, {stats['pairs']} camera pairs; host arrays in, "
+                   "poses out (uploads and sorts inside the timed region)", "host": numa},
+        "e2e": {"value": ses.n_obs * args.steps / wall, "unit": "observations/s", "ms_per_step": 1e3 * wall / args.steps,
+                "h2d_bytes_per_step": int(ses.n_obs * (4 + 8 + 8 + 24) + ses.n_obs * (4 + 8 + 8)),
+                "d2h_bytes_per_step": int(stats["groups"] * (72 + 24 + 8 + 12) + stats["pairs"] * 16)},
+        "gpu_launches": int(launches),
+        "stage_ms": {"pnp (device call)": 1e3 * stats["pnp_s"], "relative + IQR + average (host bookkeeping)": 1e3 * stats["host_s"],
+                     "stereo rmse (device call)": 1e3 * stats["stereo_s"], "pnp kernel alone": stats["pnp_kernel_ms"]},
+        "fallback_groups": stats["fallback"],
+        "truth": {"max_abs_dR": err_R, "max_abs_dt_m": err_t, "median_stereo_rmse": float(np.nanmedian(rmse))},
+    }  # fmt: skip
+    if not args.no_cpu_baseline:
+        from oracle import bootstrap as OB
+
+        nf = 40  # bounded sample: the first 40 frames through the reference's own OpenCV calls
+        m = ses.sync_index < nf
+        t1 = time.perf_counter()
+        poses_cv, pairs_cv = OB.reference_calls_cv2(ses.cam_ids, ses.cam_k, ses.cam_dist, ses.cam_fisheye, ses.sync_index[m], ses.cam_id[m],
+                                                    ses.object_id[m], ses.keypoint_id[m], ses.img_xy[m], ses.obj_xyz[m])
+        dt = time.perf_counter() - t1
+        # parity on the sample: device PnP against cv2's on the same groups
+        rs = B.pnp_arrays(tab, ses.cam_id[m], ses.sync_index[m], ses.object_id[m], ses.img_xy[m], ses.obj_xyz[m])
+        worst = 0.0
+        for i, k in enumerate(rs.keys):
+            kk = tuple(int(v) for v in k)
+            if kk in poses_cv and rs.status[i] == B.PNP_OK and np.isfinite(poses_cv[kk][0]).all():
+                worst = max(worst, float(np.abs(rs.R[i] - poses_cv[kk][0]).max()), float(np.abs(rs.t[i] - poses_cv[kk][1]).max()))
+        line["cpu_baseline"] = {"value": int(m.sum()) / dt, "unit": "observations/s", "cores": 1, "kind": "reference",
+                                "sample": f"first {nf} frames ({int(m.sum())} observations, {len(poses_cv)} PnP groups, {len(pairs_cv)} pairs): "
+                                "the reference's own OpenCV calls (cv2.undistortPoints, solvePnP(IPPE), Rodrigues, projectPoints, "
+                                "triangulatePoints) in its per-group / per-pair Python loops, on arrays instead of DataFrames"}
+        line["parity"] = {"pnp_pose_max_abs_diff_vs_cv2": worst, "bar": 1e-6, "green": bool(worst < 1e-6)}
+    print(json.dumps(line), flush=True)
+
+
 def run_triangulation(args) -> None:
     """The step in front of bundle adjustment on the cfg4 rig: undistort 2 M pixel
     observations and DLT-triangulate the 50 000 points, host buffers in and out; one step = both calls."""
@@ -835,7 +922,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=sorted(WORKLOADS) + sorted(PIPELINE_WORKLOADS) + ["triangulate_cfg4"], default="cfg4")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS) + sorted(PIPELINE_WORKLOADS) + ["triangulate_cfg4", "bootstrap64"], default="cfg4")
     ap.add_argument("--ref-max-nfev", type=int, default=0, help="cap on scipy evaluations per reference step (0: run to convergence)")
     ap.add_argument("--ref-budget-s", type=float, default=240.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -843,7 +930,11 @@ def main() -> None:
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
-    if args.workload == "triangulate_cfg4":
+    if args.workload == "bootstrap64":
+        if args.impl != "ours" or args.gpus != 1:
+            raise SystemExit("bootstrap64 runs on the CUDA arm, one GPU")
+        run_bootstrap(args)
+    elif args.workload == "triangulate_cfg4":
         if args.impl != "ours" or args.gpus != 1:
             raise SystemExit("triangulate_cfg4 runs on the CUDA arm, one GPU")
         run_triangulation(args)

@@ -669,8 +669,11 @@ using PcgFn = void (*)(const cb::LmState*, const double*, const double*, const d
 // mode 0: slab in shared memory, 1: slab from global, 2: slab in registers with cl columns per lane
 PcgFn pcg_fn(int mode, int P, int cl) {
   if (mode == 2) {
-    if (P == 6) return cl == 2 ? cb::pcg_cluster_kernel<2, 6, 2> : cl == 6 ? cb::pcg_cluster_kernel<2, 6, 6> : cb::pcg_cluster_kernel<2, 6, 12>;
-    return cl == 2 ? cb::pcg_cluster_kernel<2, 9, 2> : cl == 6 ? cb::pcg_cluster_kernel<2, 9, 6> : cb::pcg_cluster_kernel<2, 9, 12>;
+    if (P == 6)
+      return cl == 2 ? cb::pcg_cluster_kernel<2, 6, 2> : cl == 6 ? cb::pcg_cluster_kernel<2, 6, 6>
+           : cl == 12 ? cb::pcg_cluster_kernel<2, 6, 12> : cb::pcg_cluster_kernel<2, 6, 18>;
+    return cl == 2 ? cb::pcg_cluster_kernel<2, 9, 2> : cl == 6 ? cb::pcg_cluster_kernel<2, 9, 6>
+         : cl == 12 ? cb::pcg_cluster_kernel<2, 9, 12> : cb::pcg_cluster_kernel<2, 9, 18>;
   }
   if (P == 6) return mode == 0 ? cb::pcg_cluster_kernel<0, 6, 1> : cb::pcg_cluster_kernel<1, 6, 1>;
   return mode == 0 ? cb::pcg_cluster_kernel<0, 9, 1> : cb::pcg_cluster_kernel<1, 9, 1>;
@@ -1123,11 +1126,12 @@ int choose_pcg_config(CbBaProblem* p) {
   };
   int force_mode = -1;
   if (const char* ev = std::getenv("CB_PCG_MODE")) force_mode = std::atoi(ev);
-  // (1) slab in registers: up to 384 reduced parameters in one portable cluster
-  if (nP <= 384 && (force_mode < 0 || force_mode == 2)) {
-    const int cl = nP <= 64 ? 2 : nP <= 192 ? 6 : 12;
+  // (1) slab in registers: 3 rows x (32 cl) columns per warp; up to 384 reduced parameters in one portable cluster (<= 8
+  //     CTAs), up to 576 (64 cameras with free intrinsics) in a 12-CTA cluster (non-portable size, allowed up to 16)
+  if (nP <= 576 && (force_mode < 0 || force_mode == 2)) {
+    const int cl = nP <= 64 ? 2 : nP <= 192 ? 6 : nP <= 384 ? 12 : 18;
     const int cs = (nP + 3 * nw - 1) / (3 * nw);
-    if (cs <= 8 && try_config(2, cs, cl)) return CB_OK;
+    if (cs <= 16 && try_config(2, cs, cl)) return CB_OK;
   }
   // (2) slab in shared memory, smallest cluster that fits
   if (force_mode < 0 || force_mode == 0)
@@ -2392,6 +2396,8 @@ int cb_undistort_points(int32_t n_cams, const int32_t* cam_fisheye, const double
 
 namespace {
 
+int group_by_key(const long long* d_key, int n, cudaStream_t st, ScopedFree& sf, int** d_rows, int** d_start, int* n_groups);
+
 // shared body of cb_triangulate_dlt / cb_undistort_triangulate: `undist` non-null = obs_xy are raw pixels,
 // undistorted on the device (normalised output) before the DLT, never leaving HBM in between.
 int triangulate_impl(int32_t n_cams, const std::vector<cb::UndistCam>* undist, const double* proj, int64_t n_obs,
@@ -2450,34 +2456,10 @@ int triangulate_impl(int32_t n_cams, const std::vector<cb::UndistCam>* undist, c
   sf.dev.push_back(d_proj);
   CB_CUDA(cudaMemcpyAsync(d_proj, proj, sizeof(double) * 12 * (size_t)n_cams, cudaMemcpyHostToDevice, st));
 
-  // (1) stable radix sort of (key, row) -> rows of one group adjacent, in caller order inside the group
-  unsigned long long* k_out = nullptr;
-  int *v_in = nullptr, *v_out = nullptr, *d_head = nullptr, *d_gid = nullptr, *d_start = nullptr;
-  CB_TRY(dalloc(&k_out, (size_t)n)); sf.dev.push_back(k_out);
-  CB_TRY(dalloc(&v_in, (size_t)n)); sf.dev.push_back(v_in);
-  CB_TRY(dalloc(&v_out, (size_t)n)); sf.dev.push_back(v_out);
-  CB_TRY(dalloc(&d_head, (size_t)n)); sf.dev.push_back(d_head);
-  CB_TRY(dalloc(&d_gid, (size_t)n)); sf.dev.push_back(d_gid);
-  CB_TRY(dalloc(&d_start, (size_t)n + 1)); sf.dev.push_back(d_start);
-  size_t tb_sort = 0, tb_scan = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tb_sort, (const unsigned long long*)d_key, k_out, v_in, v_out, n, 0, 64, st);
-  cub::DeviceScan::InclusiveSum(nullptr, tb_scan, d_head, d_gid, n, st);
-  void* d_tmp = nullptr;
-  CB_TRY(cached_malloc(&d_tmp, std::max<size_t>(std::max(tb_sort, tb_scan), 16)));
-  sf.dev.push_back(d_tmp);
-  size_t tb = std::max(tb_sort, tb_scan);
-  CB_LAUNCH(cb::tri_iota_kernel, G, TB, 0, st, v_in, (long long)n);
-  CB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb, (const unsigned long long*)d_key, k_out, v_in, v_out, n, 0, 63, st));
-  g_launches.fetch_add(8);
-  // (2) group boundaries
-  CB_LAUNCH(cb::tri_heads_kernel, G, TB, 0, st, k_out, (long long)n, d_head);
-  CB_CUDA(cub::DeviceScan::InclusiveSum(d_tmp, tb, d_head, d_gid, n, st));
-  g_launches.fetch_add(2);
-  CB_LAUNCH(cb::tri_starts_kernel, G, TB, 0, st, d_head, d_gid, (long long)n, d_start);
-  int n_groups = 0;
-  CB_CUDA(cudaMemcpyAsync(&n_groups, d_gid + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+  // (1) stable radix sort of (key, row) -> rows of one group adjacent, in caller order inside the group; (2) boundaries
+  int *v_out = nullptr, *d_start = nullptr, n_groups = 0;
+  CB_TRY(group_by_key(d_key, n, st, sf, &v_out, &d_start, &n_groups));
   CB_CUDA(cudaEventRecord(ev[1], st));
-  CB_CUDA(cudaStreamSynchronize(st));
   *n_groups_out = n_groups;
   if (n_groups > max_groups) {
     g_last_error = "cb_triangulate_dlt: " + std::to_string(n_groups) + " groups but room for " + std::to_string(max_groups);
@@ -2491,7 +2473,7 @@ int triangulate_impl(int32_t n_cams, const std::vector<cb::UndistCam>* undist, c
   CB_TRY(dalloc(&d_count, (size_t)n_groups)); sf.dev.push_back(d_count);
   CB_TRY(dalloc(&d_rep, (size_t)n_groups)); sf.dev.push_back(d_rep);
   CB_TRY(dalloc(&d_sig, 2 * (size_t)n_groups)); sf.dev.push_back(d_sig);
-  const size_t proj_bytes = sizeof(double) * 12 * (size_t)n_cams;
+  const size_t proj_bytes = sizeof(double) * 13 * (size_t)n_cams;  // padded stride, see tri_dlt_kernel
   const int in_smem = proj_bytes <= 40 * 1024 ? 1 : 0;
   // 8 lanes per group: the serial 4x4 eigen-solve of one lane per group, not the gather, bounds this kernel, so
   // more groups per warp wins until groups get very long
@@ -2575,8 +2557,19 @@ int group_by_key(const long long* d_key, int n, cudaStream_t st, ScopedFree& sf,
   CB_TRY(cached_malloc(&d_tmp, std::max<size_t>(tb, 16)));
   sf.dev.push_back(d_tmp);
   CB_LAUNCH(cb::tri_iota_kernel, G, TB, 0, st, v_in, (long long)n);
-  CB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb, (const unsigned long long*)d_key, k_out, v_in, v_out, n, 0, 63, st));
-  g_launches.fetch_add(8);
+  // radix passes only over the key's significant bits (a packed (sync, object, keypoint) key of a 50k-point rig has 16)
+  unsigned long long* d_max = nullptr;
+  CB_TRY(dalloc(&d_max, 1)); sf.dev.push_back(d_max);
+  size_t tb_max = 0;
+  cub::DeviceReduce::Max(nullptr, tb_max, (const unsigned long long*)d_key, d_max, n, st);
+  if (tb_max > tb) { g_last_error = "group_by_key: scratch too small"; return CB_E_CUDA; }
+  CB_CUDA(cub::DeviceReduce::Max(d_tmp, tb_max, (const unsigned long long*)d_key, d_max, n, st));
+  unsigned long long h_max = 0;
+  CB_CUDA(cudaMemcpyAsync(&h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  const int key_bits = std::min(63, bits_for(h_max));
+  CB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb, (const unsigned long long*)d_key, k_out, v_in, v_out, n, 0, key_bits, st));
+  g_launches.fetch_add(2 + 2 * ((key_bits + 7) / 8));
   CB_LAUNCH(cb::tri_heads_kernel, G, TB, 0, st, k_out, (long long)n, d_head);
   CB_CUDA(cub::DeviceScan::InclusiveSum(d_tmp, tb, d_head, d_gid, n, st));
   g_launches.fetch_add(2);

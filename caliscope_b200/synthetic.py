@@ -225,3 +225,72 @@ def exact_normalized_observations(rig: SyntheticRig):
     X = rig.x_true[off[-1] :].reshape(-1, 3)
     Xc = np.einsum("nij,nj->ni", proj[rig.obs_cam, :, :3], X[rig.obs_pt]) + proj[rig.obs_cam, :, 3]
     return proj, np.ascontiguousarray(Xc[:, :2] / Xc[:, 2:3])
+
+
+@dataclass
+class BoardSession:
+    """Synthetic input of the extrinsic bootstrap: a planar calibration board seen by a ring rig over many frames --
+    the columns of ``ImagePoints`` (reference core/point_data.py) as arrays, plus the camera tables."""
+
+    cam_ids: np.ndarray  # (n_cams,)
+    cam_k: np.ndarray  # (n_cams, 5) fx fy cx cy skew
+    cam_dist: np.ndarray  # (n_cams, 12)
+    cam_fisheye: np.ndarray  # (n_cams,) int32
+    rvec: np.ndarray  # true world -> camera poses
+    tvec: np.ndarray
+    sync_index: np.ndarray
+    cam_id: np.ndarray
+    object_id: np.ndarray
+    keypoint_id: np.ndarray
+    img_xy: np.ndarray  # (n, 2) distorted pixels + noise
+    obj_xyz: np.ndarray  # (n, 3) board-frame coordinates, z = 0
+
+    @property
+    def n_obs(self) -> int:
+        return len(self.cam_id)
+
+
+def make_board_session(n_cams: int = 64, n_frames: int = 1000, grid=(7, 5), square: float = 0.06, seed: int = 0,
+                       noise_px: float = 0.3) -> BoardSession:  # fmt: skip
+    """A ``grid`` of corners on a board of ``square`` metres moves through the capture volume; in every frame the cameras
+    that look at its front side (normal within 70 degrees of the viewing ray) and have every corner in frame observe all
+    corners.  Pinhole WEBCAM lens (Brown-Conrady), 0.3 px noise."""
+    rng = np.random.default_rng(seed)
+    rvec, tvec = _ring_cameras(n_cams)
+    w, h = WEBCAM_SIZE
+    cx, cy = w / 2.0, h / 2.0
+    gx, gy = np.meshgrid(np.arange(grid[0]), np.arange(grid[1]), indexing="ij")
+    corners = np.stack([gx.ravel() * square, gy.ravel() * square, np.zeros(gx.size)], axis=1)
+    centre = corners.mean(axis=0)
+    Rc = np.array([_rot(r) for r in rvec])
+    cam_pos = np.array([-Rc[c].T @ tvec[c] for c in range(n_cams)])
+    cols = {k: [] for k in ("sync", "cam", "kp", "xy", "obj")}
+    for f in range(n_frames):
+        pos = np.array([rng.uniform(-0.35, 0.35), rng.uniform(-0.35, 0.35), rng.uniform(0.2, 1.0)])
+        az = rng.uniform(0, 2 * np.pi)
+        tilt = rng.normal(0, 0.35, 2)
+        # board z axis roughly horizontal, pointing at azimuth az
+        zb = np.array([np.cos(az), np.sin(az), 0.0])
+        xb = np.cross([0.0, 0.0, 1.0], zb)
+        xb /= np.linalg.norm(xb)
+        yb = np.cross(zb, xb)
+        Rb = np.stack([xb, yb, zb], axis=1) @ _rot(np.array([tilt[0], tilt[1], rng.uniform(-0.5, 0.5)]))
+        Xw = (corners - centre) @ Rb.T + pos
+        normal = Rb[:, 2]
+        for c in range(n_cams):
+            view = cam_pos[c] - pos
+            if normal @ view / np.linalg.norm(view) < np.cos(np.radians(70)):
+                continue
+            uv, z = _project_pinhole(Xw, rvec[c], tvec[c], WEBCAM_F, WEBCAM_F, cx, cy, WEBCAM_DIST)
+            if not ((z > 0).all() and (uv[:, 0] >= 0).all() and (uv[:, 0] < w).all() and (uv[:, 1] >= 0).all() and (uv[:, 1] < h).all()):
+                continue
+            n = len(corners)
+            cols["sync"].append(np.full(n, f, np.int64)); cols["cam"].append(np.full(n, c, np.int64))
+            cols["kp"].append(np.arange(n, dtype=np.int64)); cols["xy"].append(uv + rng.normal(0, noise_px, uv.shape))
+            cols["obj"].append(corners.copy())
+    k = np.tile([WEBCAM_F, WEBCAM_F, cx, cy, 0.0], (n_cams, 1))
+    dist = np.zeros((n_cams, 12))
+    dist[:, :5] = WEBCAM_DIST
+    cat = {kk: np.concatenate(v) for kk, v in cols.items()}
+    return BoardSession(np.arange(n_cams, dtype=np.int64), k, dist, np.zeros(n_cams, np.int32), rvec, tvec, cat["sync"], cat["cam"],
+                        np.zeros(len(cat["cam"]), np.int64), cat["kp"], cat["xy"], cat["obj"])  # fmt: skip

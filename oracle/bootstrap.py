@@ -205,3 +205,62 @@ def fill_network(raw: dict):
                 allp[(a, c)] = best
                 allp[(c, a)] = inv(best)
     return allp
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# The reference's own OpenCV calls, for the CPU baseline of bench.py (test infrastructure; needs cv2).  Same call
+# sequence as pose_network_builder.py:241-321 (undistort per camera, solvePnP + Rodrigues + projectPoints per group) and
+# :638-685 (triangulatePoints + projectPoints per pair), on arrays instead of DataFrames (which only makes it faster).
+# ----------------------------------------------------------------------------------------------------------------
+def reference_calls_cv2(cam_ids, cam_k, cam_dist, cam_fisheye, sync_index, obs_cam_id, object_id, keypoint_id, img_xy, obj_xyz):
+    import cv2
+
+    norm = np.full((len(obs_cam_id), 2), np.nan, np.float32)
+    for i, c in enumerate(cam_ids):
+        sel = obs_cam_id == c
+        if not sel.any():
+            continue
+        K = np.array([[cam_k[i, 0], cam_k[i, 4], cam_k[i, 2]], [0, cam_k[i, 1], cam_k[i, 3]], [0, 0, 1.0]])
+        pts = np.ascontiguousarray(img_xy[sel], dtype=np.float32).reshape(-1, 1, 2)
+        norm[sel] = cv2.undistortPoints(pts, K, cam_dist[i, :5], P=np.identity(3)).reshape(-1, 2)
+    order = np.lexsort((keypoint_id, object_id, sync_index, obs_cam_id))
+    key = np.stack([obs_cam_id[order], sync_index[order], object_id[order]], axis=1)
+    brk = np.flatnonzero(np.any(np.diff(key, axis=0) != 0, axis=1)) + 1
+    starts = np.concatenate([[0], brk, [len(order)]])
+    Kp, Dp = np.identity(3), np.zeros(5)
+    poses = {}
+    for s, e in zip(starts[:-1], starts[1:]):
+        rows = order[s:e]
+        if len(rows) < 4:
+            continue
+        obj = obj_xyz[rows].astype(np.float32)
+        img = norm[rows]
+        ok, rvec, tvec = cv2.solvePnP(obj, img, cameraMatrix=Kp, distCoeffs=Dp, flags=cv2.SOLVEPNP_IPPE)
+        if not ok:
+            ok, rvec, tvec = cv2.solvePnP(obj, img, cameraMatrix=Kp, distCoeffs=Dp, flags=cv2.SOLVEPNP_ITERATIVE)
+        if ok:
+            R, _ = cv2.Rodrigues(rvec)
+            proj, _ = cv2.projectPoints(obj, rvec, tvec, Kp, Dp)
+            rmse = np.sqrt(np.mean(np.sum((img - proj.reshape(-1, 2)) ** 2, axis=1)))
+            poses[tuple(int(v) for v in key[s])] = (R, tvec.flatten(), float(rmse))
+    rel = relative_poses(poses, cam_ids, np.zeros(len(cam_ids), bool))
+    agg = aggregate(reject_outliers(rel, 1.5))
+    # stereo RMSE with cv2, pair by pair
+    kk = sync_index * (int(object_id.max()) + 1) * (int(keypoint_id.max()) + 1) + object_id * (int(keypoint_id.max()) + 1) + keypoint_id
+    by_cam = {int(c): (kk[obs_cam_id == c], np.flatnonzero(obs_cam_id == c)) for c in cam_ids}
+    out = {}
+    for (a, b), (R, t) in agg.items():
+        ka, ia = by_cam[a]
+        kb, ib = by_cam[b]
+        common, xa, xb = np.intersect1d(ka, kb, return_indices=True)
+        if len(common) < 4:
+            continue
+        na, nb = norm[ia[xa]], norm[ib[xb]]
+        P2 = np.hstack((R, t.reshape(3, 1)))
+        p4 = cv2.triangulatePoints(np.eye(3, 4), P2, na.T, nb.T)
+        p3 = p4[:3] / p4[3]
+        pa, _ = cv2.projectPoints(p3.T, np.zeros(3), np.zeros(3), np.eye(3), np.zeros(5))
+        pb, _ = cv2.projectPoints(p3.T, cv2.Rodrigues(R)[0], t, np.eye(3), np.zeros(5))
+        err = np.vstack([na - pa.reshape(-1, 2), nb - pb.reshape(-1, 2)])
+        out[(a, b)] = (R, t, float(np.sqrt(np.mean(np.sum(err**2, axis=1)))))
+    return poses, out
