@@ -272,6 +272,7 @@ class EnginePeerGroup:
         L.check(self._lib.cb_peer_create(rank, world, int(device), cap, C.byref(h), mine), "peer_create")
         self.handle = h.value
         self.capacity = cap
+        self.poisoned = False  # set when a solve on this group failed part-way (see BAProblem.solve)
         self.rank, self.world_size = rank, world
         send = torch.frombuffer(bytearray(mine.raw), dtype=torch.uint8).to(f"cuda:{device}")
         recv = [torch.empty(64, dtype=torch.uint8, device=f"cuda:{device}") for _ in range(world)]
@@ -306,7 +307,7 @@ def engine_peer_group(device: int, n_camera_dims: int, group=None) -> EnginePeer
     key = (int(device), id(group))
     g = _PEERS.get(key)
     need = int(n_camera_dims) ** 2 + 3 * int(n_camera_dims) + 65
-    if g is None or g.handle is None or g.capacity < need:
+    if g is None or g.handle is None or g.capacity < need or getattr(g, "poisoned", False):
         if g is not None:
             g.close()
         g = _PEERS[key] = EnginePeerGroup(device, n_camera_dims, group)

@@ -326,7 +326,14 @@ class BAProblem:
             opt.peer_group = C.c_void_p(getattr(peer_group, "handle", peer_group))
         opt.rank, opt.world_size = int(rank), int(world_size)
         res = L.Result()
-        L.check(self._lib.cb_ba_solve(self._h, C.byref(opt), _ptr(x), C.byref(res), C.c_void_p(stream)), "solve")
+        try:
+            L.check(self._lib.cb_ba_solve(self._h, C.byref(opt), _ptr(x), C.byref(res), C.c_void_p(stream)), "solve")
+        except Exception:
+            # a sharded solve that fails part-way leaves the ranks' reduction sequence numbers out of step: the engine
+            # refuses further solves on this peer group; make the Python cache re-create it (collectively) next time
+            if peer_group is not None and hasattr(peer_group, "poisoned"):
+                peer_group.poisoned = True
+            raise
         del cb
         return SolveResult(
             x=x, status=res.status, nfev=res.nfev, njev=res.njev, nit=res.nit, cost=res.cost,

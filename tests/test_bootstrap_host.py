@@ -51,3 +51,31 @@ def test_quaternions_round_trip():
     back = np.array([B._quat_to_matrix(v) for v in q])
     assert np.abs(back - Rs).max() < 1e-12
     assert np.abs(np.linalg.norm(q, axis=1) - 1).max() < 1e-12
+
+
+def test_board_session_chain_recovers_the_rig():
+    """Synthetic board session -> oracle PnP -> this package's relative / IQR / average stages: the aggregated relative poses
+    are the generator's cameras (sub-millimetre, sub-milliradian at 0.3 px noise); checks the bench workload's generator and the
+    array stages together, without a GPU."""
+    from caliscope_b200 import synthetic
+    from oracle import bootstrap as OB
+
+    s = synthetic.make_board_session(12, 80, seed=4)
+    norm = OB.undistort_all(s.cam_ids, s.cam_k, s.cam_dist, s.cam_fisheye, s.cam_id, s.img_xy)
+    poses = OB.pnp_poses(s.cam_ids, norm, s.sync_index, s.cam_id, s.object_id, s.obj_xyz)
+    keys = np.array(list(poses), np.int64)
+    R = np.array([v[0] for v in poses.values()])
+    t = np.array([v[1] for v in poses.values()])
+    tab = B.CameraTables(s.cam_ids, {int(c): i for i, c in enumerate(s.cam_ids)}, s.cam_k, s.cam_dist, s.cam_fisheye,
+                         np.zeros(12, bool), np.ones(12, bool))  # fmt: skip
+    rel = B.relative_pose_arrays(keys, R, t, tab)
+    pairs, keep, Ra, ta, cnt = B.filter_and_aggregate(rel, 1.5)
+    assert len(pairs) > 20 and keep.sum() > 0.7 * len(keep)
+    worst_R = worst_t = 0.0
+    for k, (a, b) in enumerate(pairs):
+        if cnt[k] < 5:
+            continue
+        RA, RB = synthetic._rot(s.rvec[a]), synthetic._rot(s.rvec[b])
+        worst_R = max(worst_R, np.abs(Ra[k] - RB @ RA.T).max())
+        worst_t = max(worst_t, np.abs(ta[k] - (s.tvec[b] - RB @ RA.T @ s.tvec[a])).max())
+    assert worst_R < 5e-3 and worst_t < 2e-2

@@ -180,3 +180,30 @@ def test_sharded_cull_thresholds_equal_the_single_process_filter():
         assert np.array_equal(err <= thr0[cam], ref), key
         untouched = np.array([np.sum((cam == c) & (err <= base[c])) >= min(floor, np.sum(cam == c)) for c in range(n_cams)])
         assert np.array_equal(thr0[untouched], base[untouched])  # bit-identical to np.percentile where no floor applies
+
+
+def test_camera_order_groups_cameras_that_share_points():
+    """distributed.camera_order: on a rig with local visibility numbered ring by ring, the chosen order must cut the number of
+    (point, tile pair) incidences the Schur product has to visit; on dense rigs and small rigs it is the identity; it is a
+    pure function of the observation list (every rank computes the same order)."""
+    from caliscope_b200 import distributed as D
+    from caliscope_b200 import synthetic
+
+    r = synthetic.make_rig(64, 20_000, 160_000, cams_per_point=8, seed=2)
+    o = D.camera_order(r.obs_cam, r.obs_pt, 64, r.n_pts)
+    assert sorted(o.tolist()) == list(range(64)) and not np.array_equal(o, np.arange(64))
+    assert np.array_equal(o, D.camera_order(r.obs_cam.copy(), r.obs_pt.copy(), 64, r.n_pts))
+
+    def incidences(order):
+        slot = np.empty(64, np.int64)
+        slot[order] = np.arange(64)
+        m = np.zeros((r.n_pts, 4), bool)
+        m[r.obs_pt, slot[r.obs_cam] // 16] = True
+        k = m.sum(1)
+        return float((k * (k + 1) / 2).mean())
+
+    assert incidences(o) < 0.4 * incidences(np.arange(64))
+    dense = synthetic.make_rig(64, 2000, 80_000, seed=1)
+    assert np.array_equal(D.camera_order(dense.obs_cam, dense.obs_pt, 64, dense.n_pts), np.arange(64))
+    small = synthetic.cfg2()
+    assert np.array_equal(D.camera_order(small.obs_cam, small.obs_pt, 8, small.n_pts), np.arange(8))
