@@ -8,6 +8,7 @@
 // the step itself is a damped Gauss-Newton step from the Schur-complement reduced camera system.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>  // header-only; ranges show up in ncu / nsys timelines, no-ops otherwise
 
 #include <algorithm>
 #include <atomic>
@@ -32,6 +33,11 @@
 namespace {
 
 thread_local std::string g_last_error;
+
+struct NvtxRange {  // scoped NVTX range
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 std::atomic<long long> g_launches{0};
 
 #define CB_CUDA(expr)                                                                              \
@@ -944,6 +950,7 @@ int ensure_loop_graph(CbBaProblem* p, const CbBaOptions* opt) {
 // ------------------------------------------------------------------------------------------
 template <int P>
 int lm_solve(CbBaProblem* p, const CbBaOptions* opt, double* x_inout, CbBaResult* res, cudaStream_t st) {
+  NvtxRange nvtx_solve("cb_ba_solve");
   const long long max_nfev = opt->max_nfev > 0 ? opt->max_nfev : 100ll * p->n_params;
   const bool verbose = opt->verbose >= 2 && opt->rank == 0;
   const long long launches0 = g_launches.load();
@@ -996,10 +1003,17 @@ int lm_solve(CbBaProblem* p, const CbBaOptions* opt, double* x_inout, CbBaResult
   if (use_loop) {
     // the whole LM loop is one graph launch; the state comes back once
     cudaError_t e = cudaGraphLaunch(p->loop_exec, st);
-    if (e != cudaSuccess) { g_last_error = std::string("cudaGraphLaunch(loop): ") + cudaGetErrorString(e); rc = CB_E_CUDA; }
-    cudaMemcpyAsync(&p->h_state[1], p->d_state, sizeof(cb::LmState), cudaMemcpyDeviceToHost, st);
-    t = 2;  // final state in slot (t - 1) & 1
-    done = true;
+    if (e != cudaSuccess) {
+      // nothing of the loop ran: remember that this configuration cannot be launched and run the trials directly
+      cudaGetLastError();
+      p->loop_failed = true;
+      p->loop_valid = false;
+      use_loop = false;
+    } else {
+      cudaMemcpyAsync(&p->h_state[1], p->d_state, sizeof(cb::LmState), cudaMemcpyDeviceToHost, st);
+      t = 2;  // final state in slot (t - 1) & 1
+      done = true;
+    }
   }
   while (!done) {
     if (use_graph) {
@@ -1007,6 +1021,7 @@ int lm_solve(CbBaProblem* p, const CbBaOptions* opt, double* x_inout, CbBaResult
       if (e != cudaSuccess) { g_last_error = std::string("cudaGraphLaunch: ") + cudaGetErrorString(e); rc = CB_E_CUDA; break; }
       g_launches.fetch_add(p->tg[t & 1].n_kernels);
     } else {
+      NvtxRange nvtx_trial("lm_trial (direct launches)");
       rc = enqueue_trial<P>(p, opt, st, p->ev_pp[t & 1]);
       if (rc != CB_OK) break;
     }
@@ -1425,9 +1440,33 @@ static int build_schur_items(CbBaProblem* p, cudaStream_t st) {
   std::vector<cb::SyItem> items;
   std::vector<std::vector<int>> slots_of(nt);
   int slot = 0;
-  for (auto& g : groups) {
-    int n = (int)std::floor(p->num_sms * (g.w * g.chunks) / std::max(W, 1.0));
-    n = std::max(1, std::min(n, g.chunks));
+  // CTAs per group: proportional share rounded down, then the SMs left over go one by one to the group whose CTAs carry
+  // the most work (6 tiles at P = 9: 18 groups, floor alone leaves 10 of 148 SMs idle)
+  std::vector<int> n_of(groups.size(), 1);
+  {
+    int used = 0;
+    for (size_t gi = 0; gi < groups.size(); ++gi) {
+      const Group& g = groups[gi];
+      int n = (int)std::floor(p->num_sms * (g.w * g.chunks) / std::max(W, 1.0));
+      n_of[gi] = std::max(1, std::min(n, g.chunks));
+      used += n_of[gi];
+    }
+    while (used < p->num_sms) {
+      int best = -1;
+      double load = 0.0;
+      for (size_t gi = 0; gi < groups.size(); ++gi) {
+        if (n_of[gi] >= groups[gi].chunks) continue;
+        const double l = groups[gi].w * groups[gi].chunks / n_of[gi];
+        if (l > load) { load = l; best = (int)gi; }
+      }
+      if (best < 0) break;
+      ++n_of[(size_t)best];
+      ++used;
+    }
+  }
+  for (size_t gi = 0; gi < groups.size(); ++gi) {
+    const Group& g = groups[gi];
+    const int n = n_of[gi];
     for (int s2 = 0; s2 < n; ++s2) {
       cb::SyItem it;
       it.kind = g.kind; it.I = g.I; it.J = g.J; it.koff = g.koff;
@@ -1474,6 +1513,7 @@ static int build_schur_items(CbBaProblem* p, cudaStream_t st) {
 }
 
 static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_t st, CbBaProblem* p) {
+  NvtxRange nvtx_create("cb_ba_problem_create (upload + index build)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();

@@ -156,6 +156,22 @@ def uninstall() -> None:
         _original_bootstrap.clear()
 
 
+def install_from_env() -> bool:
+    """Install the seam when the environment asks for it: ``CALISCOPE_BA_BACKEND=b200`` (seam S1: the solver call only) or
+    ``CALISCOPE_BA_BACKEND=b200-full`` (S1-S5).  Returns whether anything was installed.  Meant to be called once by the
+    application that owns the process (e.g. at the top of a calibration script); nothing in this package calls it."""
+    import os
+
+    mode = os.environ.get("CALISCOPE_BA_BACKEND", "").strip().lower()
+    if mode == "b200":
+        install(False)
+        return True
+    if mode in ("b200-full", "b200_full"):
+        install(True)
+        return True
+    return False
+
+
 @contextlib.contextmanager
 def installed(full: bool = False):
     install(full)

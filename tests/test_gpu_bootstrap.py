@@ -97,3 +97,93 @@ def test_chain_end_to_end(case):
             assert np.isnan(rmse[k])
         elif not (int(a) in touched or int(b) in touched):
             assert abs(rmse[k] - g["rmse_pair"][i]) < 1e-4 * g["rmse_pair"][i]
+
+
+def _tiny_tables(n=3):
+    from caliscope_b200 import bootstrap as B
+
+    ids = np.arange(n, dtype=np.int64)
+    k = np.tile([1000.0, 1000.0, 640.0, 360.0, 0.0], (n, 1))
+    return B.CameraTables(ids, {i: i for i in range(n)}, k, np.zeros((n, 12)), np.zeros(n, np.int32), np.zeros(n, bool), np.ones(n, bool))
+
+
+def _project(obj, rvec, t, k):
+    from oracle.ippe import _rodrigues
+
+    Xc = obj @ _rodrigues(np.asarray(rvec, float)).T + t
+    return np.stack([k[0] * Xc[:, 0] / Xc[:, 2] + k[2], k[1] * Xc[:, 1] / Xc[:, 2] + k[3]], axis=1)
+
+
+def test_pnp_edge_cases_too_few_collinear_nonplanar_unknown_camera():
+    """The reference's group rules (pose_network_builder.py:272-298): fewer than min_points rows -> no pose; all model points
+    on a line -> cv2 reports success with a NaN pose, kept; NaN obj_loc_z counts as 0; a camera without intrinsics is skipped;
+    a non-planar group is refused (the reference switches to SQPNP)."""
+    from caliscope_b200 import bootstrap as B
+
+    tab = _tiny_tables(3)
+    tab.has_intrinsics[2] = False
+    k = tab.k[0]
+    board = np.array([[0, 0, 0], [0.1, 0, 0], [0.1, 0.1, 0], [0, 0.1, 0], [0.05, 0.05, 0]], float)
+    line = np.array([[0, 0, 0], [0.1, 0, 0], [0.2, 0, 0], [0.3, 0, 0]], float)
+    rows = []
+
+    def add(cam, sync, obj):
+        xy = _project(obj, [0.2, -0.1, 0.05], np.array([0.05, -0.02, 2.0]), k)
+        for kp, (o, p) in enumerate(zip(obj, xy)):
+            rows.append((cam, sync, 0, kp, p[0], p[1], o[0], o[1], o[2]))
+
+    add(0, 0, board)           # well posed
+    add(0, 1, board[:3])       # too few
+    add(1, 0, line)            # collinear
+    nan_z = board.copy()
+    add(1, 1, nan_z)           # z given as NaN below
+    add(2, 0, board)           # camera without intrinsics
+    a = np.array(rows)
+    obj = a[:, 6:9].copy()
+    obj[(a[:, 0] == 1) & (a[:, 1] == 1), 2] = np.nan
+    res = B.pnp_arrays(tab, a[:, 0].astype(np.int64), a[:, 1].astype(np.int64), a[:, 2].astype(np.int64), a[:, 4:6], obj)
+    st = {tuple(int(v) for v in kk[:2]): int(s) for kk, s in zip(res.keys, res.status)}
+    assert st == {(0, 0): B.PNP_OK, (0, 1): B.PNP_TOO_FEW, (1, 0): B.PNP_DEGENERATE, (1, 1): B.PNP_OK}
+    poses = B.poses_dict(res)
+    assert set(poses) == {(0, 0, 0), (1, 0, 0), (1, 1, 0)}
+    assert np.isnan(poses[(1, 0, 0)][0]).all()
+    from oracle.ippe import _rodrigues
+
+    for key in ((0, 0, 0), (1, 1, 0)):
+        R, t, rm = poses[key]
+        assert np.abs(R - _rodrigues(np.array([0.2, -0.1, 0.05]))).max() < 1e-6 and np.abs(t - [0.05, -0.02, 2.0]).max() < 1e-5
+        assert rm < 1e-6
+    # non-planar target
+    cube = np.array([[0, 0, 0], [0.1, 0, 0], [0.1, 0.1, 0.05], [0, 0.1, 0], [0.05, 0.05, 0.1], [0.02, 0.07, 0.03]], float)
+    xy = _project(cube, [0.1, 0.2, 0.0], np.array([0.0, 0.0, 2.0]), k)
+    res2 = B.pnp_arrays(tab, np.zeros(6, np.int64), np.zeros(6, np.int64), np.zeros(6, np.int64), xy, cube)
+    assert int(res2.status[0]) == B.PNP_NON_PLANAR
+    with pytest.raises(NotImplementedError):
+        B.poses_dict(res2)
+
+
+def test_stereo_rmse_exact_geometry_and_missing_pairs():
+    """Noise-free two-view geometry gives an RMSE at float32 rounding level; a pair without min_common common observations
+    comes back NaN (the reference returns None there, pose_network_builder.py:656-659)."""
+    from caliscope_b200 import bootstrap as B
+    from oracle.ippe import _rodrigues
+
+    tab = _tiny_tables(3)
+    k = tab.k[0]
+    rng = np.random.default_rng(0)
+    X = np.stack([rng.uniform(-0.3, 0.3, 40), rng.uniform(-0.3, 0.3, 40), rng.uniform(1.5, 2.5, 40)], axis=1)
+    R = _rodrigues(np.array([0.0, 0.4, 0.05]))
+    t = np.array([-0.8, 0.02, 0.2])
+    xa = np.stack([k[0] * X[:, 0] / X[:, 2] + k[2], k[1] * X[:, 1] / X[:, 2] + k[3]], axis=1)
+    Xb = X @ R.T + t
+    xb = np.stack([k[0] * Xb[:, 0] / Xb[:, 2] + k[2], k[1] * Xb[:, 1] / Xb[:, 2] + k[3]], axis=1)
+    cam = np.concatenate([np.zeros(40), np.ones(40), np.full(3, 2)]).astype(np.int64)
+    sync = np.concatenate([np.arange(40), np.arange(40), np.arange(3)]).astype(np.int64)
+    z = np.zeros(len(cam), np.int64)
+    xy = np.concatenate([xa, xb, xa[:3]])
+    pairs = np.array([[0, 1], [0, 2]])
+    Rs = np.stack([R, np.eye(3)])
+    ts = np.stack([t, np.array([0.1, 0.0, 0.0])])
+    rmse, cnt = B.stereo_rmse_arrays(tab, pairs, Rs, ts, cam, sync, z, z, xy)
+    assert cnt.tolist() == [40, 3]
+    assert rmse[0] < 5e-7 and np.isnan(rmse[1])

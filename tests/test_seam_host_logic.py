@@ -387,3 +387,19 @@ def test_s5_point_tables_round_trip_through_the_seam(session_volume, tmp_path):
 
     pd.testing.assert_frame_equal(ip.df, pd_mod.ImagePoints.from_csv(ref_xy).df, check_exact=True)
     pd.testing.assert_frame_equal(wp.df, pd_mod.WorldPoints.from_csv(ref_xyz).df, check_exact=True)
+
+
+def test_install_from_env(monkeypatch):
+    import caliscope.core.capture_volume as mod
+    import caliscope_b200.seam as seam
+    from caliscope_b200 import solver
+
+    before = mod.least_squares
+    monkeypatch.delenv("CALISCOPE_BA_BACKEND", raising=False)
+    assert seam.install_from_env() is False and mod.least_squares is before
+    monkeypatch.setenv("CALISCOPE_BA_BACKEND", "b200")
+    try:
+        assert seam.install_from_env() is True and mod.least_squares is solver.least_squares
+    finally:
+        seam.uninstall()
+    assert mod.least_squares is before
