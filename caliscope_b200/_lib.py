@@ -65,6 +65,8 @@ class Options(C.Structure):
         ("peer_group", C.c_void_p),
         ("rank", C.c_int32),
         ("world_size", C.c_int32),
+        ("time_kernels", C.c_int32),
+        ("pad_", C.c_int32),
     ]
 
 

@@ -956,17 +956,19 @@ int lm_solve(CbBaProblem* p, const CbBaOptions* opt, double* x_inout, CbBaResult
   const long long launches0 = g_launches.load();
   std::memset(res, 0, sizeof(*res));
 
-  // Replay from CUDA graphs from the second solve on a problem (capture + instantiation cost about as much as the
-  // launches of one short solve save), never when a host callback carries the all-reduce (it cannot be captured).
-  // CB_LM_GRAPH = 0: direct launches, 1 (default): from the second solve: device loop (WHILE graph) on one GPU, per-trial
-  // graphs when sharded, 2: per-trial graphs always, 3: device loop always.
+  // The trials are replayed from CUDA graphs: one GPU -> device loop (ONE graph launch per solve: a WHILE node around the
+  // trial); sharded -> one graph per trial (the host keeps one trial ahead).  Capture + instantiation cost less than the
+  // launch gaps and host round trips of even one 3-iteration solve (measured: the first solve on a fresh problem is ~1 ms
+  // faster end to end with graphs at 2 M observations, 2x at 40 k).  Direct launches: a host callback carries the
+  // all-reduce (cannot be captured), verbose >= 2, opt->time_kernels, or graph construction failed.
+  // CB_LM_GRAPH = 0: direct launches, 1 (default): as above, 2: per-trial graphs always, 3: device loop always.
   int graph_mode = 1;
   if (const char* e = std::getenv("CB_LM_GRAPH")) graph_mode = std::atoi(e);
+  if (opt->time_kernels) graph_mode = 0;
   ++p->n_solves;
-  const bool later = p->n_solves >= 2 || p->graph_valid || p->loop_valid;
-  bool use_loop = opt->allreduce == nullptr && (graph_mode == 3 || (graph_mode == 1 && later && !sharded(opt))) && opt->verbose < 2;
+  bool use_loop = opt->allreduce == nullptr && (graph_mode == 3 || (graph_mode == 1 && !sharded(opt))) && opt->verbose < 2;
   if (use_loop && ensure_loop_graph<P>(p, opt) != CB_OK) { cudaGetLastError(); use_loop = false; }
-  bool use_graph = !use_loop && opt->allreduce == nullptr && (graph_mode >= 2 || (graph_mode == 1 && later));
+  bool use_graph = !use_loop && opt->allreduce == nullptr && graph_mode >= 1 && opt->verbose < 2;
   if (use_graph) {
     int rc = ensure_graphs<P>(p, opt);
     if (rc != CB_OK) {
@@ -1200,6 +1202,7 @@ void cb_ba_default_options(CbBaOptions* o) {
   o->peer_group = nullptr;
   o->rank = 0;
   o->world_size = 1;
+  o->time_kernels = 0;
 }
 
 int64_t cb_ba_launch_count(void) { return (int64_t)g_launches.load(); }

@@ -302,6 +302,7 @@ class BAProblem:
         rank: int = 0,
         world_size: int = 1,
         stream: int = 0,
+        time_kernels: bool = False,
     ) -> SolveResult:
         if loss not in L.LOSS_IDS:
             raise ValueError(f"`loss` must be one of {list(L.LOSS_IDS)}")
@@ -325,6 +326,7 @@ class BAProblem:
         if peer_group is not None:
             opt.peer_group = C.c_void_p(getattr(peer_group, "handle", peer_group))
         opt.rank, opt.world_size = int(rank), int(world_size)
+        opt.time_kernels = 1 if time_kernels else 0
         res = L.Result()
         try:
             L.check(self._lib.cb_ba_solve(self._h, C.byref(opt), _ptr(x), C.byref(res), C.c_void_p(stream)), "solve")

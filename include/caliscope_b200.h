@@ -113,6 +113,10 @@ typedef struct {
                                the Schur finalize kernel (takes precedence over nccl_comm / allreduce) */
   int32_t rank;       /* informational (verbose output only on rank 0) */
   int32_t world_size; /* 1 if allreduce is NULL */
+  int32_t time_kernels; /* diagnostic: launch every trial directly with CUDA events around the point pass and the Schur
+                           product (CbBaResult.rj_ms / syrk_ms); 0 (default): the loop is replayed from CUDA graphs, where
+                           events cannot be read back */
+  int32_t pad_;
 } CbBaOptions;
 
 /* mirrors scipy.optimize.OptimizeResult fields the reference reads
