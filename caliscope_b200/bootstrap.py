@@ -74,10 +74,34 @@ def camera_tables(camera_array) -> CameraTables:
     return CameraTables(np.asarray(ids, dtype=np.int64), {int(c): i for i, c in enumerate(ids)}, k, dist, fish, ign, has)
 
 
-def _rank(values: np.ndarray):
-    """Dense ranks preserving order (so packed keys sort like the tuples) + the sorted unique values."""
-    uniq, inv = np.unique(values, return_inverse=True)
-    return inv.astype(np.int64), uniq
+def _offset(values: np.ndarray):
+    """(values - min, span): an order-preserving non-negative code without sorting the column (np.unique on a 2 M-row column
+    costs more than the PnP kernel)."""
+    values = np.asarray(values, dtype=np.int64)
+    lo = int(values.min()) if len(values) else 0
+    return values - lo, (int(values.max()) - lo + 1 if len(values) else 1)
+
+
+def _pack(*cols) -> np.ndarray:
+    """Lexicographic key of integer columns (most significant first); raises if it does not fit 63 bits."""
+    key = None
+    bits = 0.0
+    for c in cols:
+        code, span = _offset(c)
+        bits += np.log2(max(span, 1))
+        key = code if key is None else key * span + code
+    if bits > 62.0:
+        raise ValueError("identifier ranges too wide to pack (sync_index, object_id, keypoint_id) into a 63-bit key")
+    return np.ascontiguousarray(key)
+
+
+def _slots(tab: CameraTables, cam_id: np.ndarray) -> np.ndarray:
+    """camera id -> row of the camera tables, through a small lookup array."""
+    lo = int(min(tab.cam_ids.min(), cam_id.min()))
+    hi = int(max(tab.cam_ids.max(), cam_id.max()))
+    lut = np.full(hi - lo + 1, -1, dtype=np.int32)
+    lut[tab.cam_ids - lo] = np.arange(len(tab.cam_ids), dtype=np.int32)
+    return lut[cam_id - lo]
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -101,23 +125,27 @@ def pnp_arrays(tab: CameraTables, cam_id, sync_index, object_id, img_xy, obj_xyz
     """Array-level ``compute_camera_to_object_poses_pnp``: every group of the frame in one ``cb_pnp_ippe`` call."""
     lib = L.load()
     cam_id = np.asarray(cam_id, dtype=np.int64)
-    known = np.array([int(c) in tab.index_of and tab.has_intrinsics[tab.index_of[int(c)]] for c in np.unique(cam_id)])
-    ok_ids = np.unique(cam_id)[known] if len(known) else np.zeros(0, np.int64)
-    sel = np.isin(cam_id, ok_ids)
-    cam_id = cam_id[sel]
-    sync = np.asarray(sync_index, dtype=np.int64)[sel]
-    obj_id = np.asarray(object_id, dtype=np.int64)[sel]
-    px = np.ascontiguousarray(np.asarray(img_xy, dtype=np.float64).reshape(-1, 2)[sel])
-    obj = np.ascontiguousarray(np.asarray(obj_xyz, dtype=np.float64).reshape(-1, 3)[sel])
+    if len(cam_id) == 0:
+        raise ValueError("No valid camera data found for PnP")
+    slot_all = _slots(tab, cam_id)
+    sel = (slot_all >= 0) & tab.has_intrinsics[np.maximum(slot_all, 0)]
+    if not sel.all():
+        cam_id, slot_all = cam_id[sel], slot_all[sel]
+        sync = np.asarray(sync_index, dtype=np.int64)[sel]
+        obj_id = np.asarray(object_id, dtype=np.int64)[sel]
+        px = np.ascontiguousarray(np.asarray(img_xy, dtype=np.float64).reshape(-1, 2)[sel])
+        obj = np.ascontiguousarray(np.asarray(obj_xyz, dtype=np.float64).reshape(-1, 3)[sel])
+    else:
+        sync = np.asarray(sync_index, dtype=np.int64)
+        obj_id = np.asarray(object_id, dtype=np.int64)
+        px = np.ascontiguousarray(np.asarray(img_xy, dtype=np.float64).reshape(-1, 2))
+        obj = np.ascontiguousarray(np.asarray(obj_xyz, dtype=np.float64).reshape(-1, 3))
     n = len(cam_id)
     if n == 0:
         raise ValueError("No valid camera data found for PnP")
-    rc, uc = _rank(cam_id)
-    rs, us = _rank(sync)
-    ro, uo = _rank(obj_id)
-    key = np.ascontiguousarray((rc * len(us) + rs) * len(uo) + ro)
-    cam_slot = np.ascontiguousarray(np.array([tab.index_of[int(c)] for c in uc], dtype=np.int32)[rc])
-    max_groups = int(len(np.unique(key)))
+    key = _pack(cam_id, sync, obj_id)
+    cam_slot = np.ascontiguousarray(slot_all, dtype=np.int32)
+    max_groups = n  # upper bound (one group per row); the untouched tail of the outputs costs address space only
     R = np.empty((max_groups, 3, 3))
     t = np.empty((max_groups, 3))
     rmse = np.empty(max_groups)
@@ -264,53 +292,114 @@ def quaternion_average(quaternions: np.ndarray) -> np.ndarray:
     return quaternions[0] if nrm < 1e-10 else q / nrm
 
 
+def _segment_percentiles(values: np.ndarray, seg: np.ndarray, n_seg: int, qs=(25.0, 75.0)):
+    """np.percentile(values[seg == p], qs) for every segment p at once (default 'linear' rule, reproduced with NumPy's own
+    interpolation formula so the numbers are the ones the reference's per-pair np.percentile calls give)."""
+    from .filtering import _numpy_linear_interp
+
+    order = np.lexsort((values, seg))
+    v = values[order]
+    cnt = np.bincount(seg, minlength=n_seg).astype(np.int64)
+    start = np.concatenate([[0], np.cumsum(cnt)[:-1]])
+    out = []
+    for q in qs:
+        vi = (cnt - 1).astype(np.float64) * (q / 100.0)
+        lo = np.floor(np.maximum(vi, 0)).astype(np.int64)
+        hi = np.minimum(lo + 1, np.maximum(cnt - 1, 0))
+        has = cnt > 0
+        a = np.zeros(n_seg)
+        b = np.zeros(n_seg)
+        a[has] = v[(start + lo)[has]]
+        b[has] = v[(start + hi)[has]]
+        out.append(_numpy_linear_interp(a, b, vi - np.floor(vi)))
+    return out
+
+
+def _segment_quaternion_average(quats: np.ndarray, seg: np.ndarray, n_seg: int) -> np.ndarray:
+    """quaternion_average of every segment at once: eigenvector of sum q q^T for the largest eigenvalue, w >= 0.
+    `seg` must be sorted ascending (rows of a segment contiguous) and every segment non-empty."""
+    outer = quats[:, :, None] * quats[:, None, :]
+    starts = np.flatnonzero(np.concatenate([[True], np.diff(seg) != 0]))
+    M = np.add.reduceat(outer, starts, axis=0)
+    assert len(M) == n_seg
+    _, V = np.linalg.eigh(M)
+    q = V[:, :, -1]
+    q = np.where(q[:, :1] < 0, -q, q)
+    nrm = np.linalg.norm(q, axis=1, keepdims=True)
+    single = np.bincount(seg, minlength=n_seg) == 1
+    q = q / np.where(nrm < 1e-10, 1.0, nrm)
+    if single.any():  # the reference returns the lone quaternion itself
+        q[single] = quats[starts[single]]
+    return q
+
+
+def _quats_to_matrices(q: np.ndarray) -> np.ndarray:
+    q = q / np.linalg.norm(q, axis=1, keepdims=True)
+    w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R = np.empty((len(q), 3, 3))
+    R[:, 0, 0] = 1 - 2 * (y * y + z * z); R[:, 0, 1] = 2 * (x * y - z * w); R[:, 0, 2] = 2 * (x * z + y * w)
+    R[:, 1, 0] = 2 * (x * y + z * w); R[:, 1, 1] = 1 - 2 * (x * x + z * z); R[:, 1, 2] = 2 * (y * z - x * w)
+    R[:, 2, 0] = 2 * (x * z - y * w); R[:, 2, 1] = 2 * (y * z + x * w); R[:, 2, 2] = 1 - 2 * (x * x + y * y)
+    return R
+
+
 def filter_and_aggregate(rel: RelativePoses, threshold: float = DEFAULT_OUTLIER_THRESHOLD,
                          rotation_threshold_multiplier: float | None = None,
                          translation_threshold_multiplier: float | None = None):  # fmt: skip
-    """``reject_outliers`` + ``aggregate_poses`` on arrays.  Returns (pairs (p, 2), kept mask over rel rows or None where
-    a pair was below 5 samples, aggregated R (p, 3, 3), t (p, 3), kept count (p,)); pairs in first-appearance order of the
-    reference's dict (combination order of the cameras, which is the order ``rel`` would be built in)."""
+    """``reject_outliers`` + ``aggregate_poses`` on arrays, every camera pair at once (no per-pair Python loop: percentiles
+    by one two-key sort, quaternion averages by one batched 4x4 eigen-decomposition).  Returns (pairs (p, 2), kept mask over
+    the rows of ``rel``, aggregated R (p, 3, 3), t (p, 3), kept count (p,)), pairs in ascending (a, b) order."""
     rot_m = rotation_threshold_multiplier if rotation_threshold_multiplier is not None else threshold
     tr_m = translation_threshold_multiplier if translation_threshold_multiplier is not None else threshold
     m = len(rel.pair_a)
     keep = np.zeros(m, bool)
-    pair_key = rel.pair_a * (int(rel.pair_b.max(initial=0)) + 1) + rel.pair_b
-    order = np.argsort(pair_key, kind="stable")
-    pk = pair_key[order]
-    brk = np.flatnonzero(np.diff(pk) != 0) + 1
-    starts = np.concatenate([[0], brk, [m]]) if m else np.zeros(1, np.int64)
-    pairs, Rs, ts, counts = [], [], [], []
-    quats = _quat_wxyz(rel.R) if m else np.zeros((0, 4))
-    tmag = np.linalg.norm(rel.t, axis=1) if m else np.zeros(0)
-    finite = np.isfinite(rel.R).all(axis=(1, 2)) & np.isfinite(rel.t).all(axis=1) if m else np.zeros(0, bool)
-    for s, e in zip(starts[:-1], starts[1:]):
-        rows = order[s:e]
-        rows = rows[finite[rows]]
-        a, b = int(rel.pair_a[order[s]]), int(rel.pair_b[order[s]])
-        if len(rows) >= 5:
-            t_q1, t_q3 = np.percentile(tmag[rows], [25, 75])
-            t_lo, t_hi = t_q1 - tr_m * (t_q3 - t_q1), t_q3 + tr_m * (t_q3 - t_q1)
-            Rm = _quat_to_matrix(quaternion_average(quats[rows]))
-            tr = np.clip(np.einsum("nij,ij->n", rel.R[rows], Rm), -1.0, 3.0)  # trace(R Rm^T)
-            ang = np.degrees(np.arccos((tr - 1) / 2))
-            r_q1, r_q3 = np.percentile(ang, [25, 75])
-            r_hi = r_q3 + rot_m * (r_q3 - r_q1)
-            ok = ~((tmag[rows] < t_lo) | (tmag[rows] > t_hi) | (ang > r_hi))
-            rows = rows[ok]
-        keep[rows] = True
-        if len(rows) == 0:
-            continue
-        pairs.append((a, b))
-        counts.append(len(rows))
-        if len(rows) == 1:
-            Rs.append(rel.R[rows[0]])
-            ts.append(rel.t[rows[0]])
-        else:
-            Rs.append(_quat_to_matrix(quaternion_average(quats[rows])))
-            ts.append(rel.t[rows].mean(axis=0))
-    if not pairs:
-        return np.zeros((0, 2), np.int64), keep, np.zeros((0, 3, 3)), np.zeros((0, 3)), np.zeros(0, np.int64)
-    return np.asarray(pairs, np.int64), keep, np.asarray(Rs), np.asarray(ts), np.asarray(counts, np.int64)
+    empty = (np.zeros((0, 2), np.int64), keep, np.zeros((0, 3, 3)), np.zeros((0, 3)), np.zeros(0, np.int64))
+    if m == 0:
+        return empty
+    finite = np.isfinite(rel.R).all(axis=(1, 2)) & np.isfinite(rel.t).all(axis=1)  # the reference's NaN filter (:364-367)
+    rows = np.flatnonzero(finite)
+    if len(rows) == 0:
+        return empty
+    span = int(rel.pair_b.max()) + 1
+    pk = rel.pair_a[rows] * span + rel.pair_b[rows]
+    o = np.argsort(pk, kind="stable")
+    rows, pk = rows[o], pk[o]
+    uniq, seg = np.unique(pk, return_inverse=True)  # seg ascending: rows of a pair contiguous
+    n_seg = len(uniq)
+    cnt = np.bincount(seg, minlength=n_seg)
+    R, t = rel.R[rows], rel.t[rows]
+    quats = _quat_wxyz(R)
+    tmag = np.linalg.norm(t, axis=1)
+    # IQR rule on pairs with at least 5 valid samples (:369-372)
+    big = cnt >= 5
+    ok = np.ones(len(rows), bool)
+    if big.any():
+        t_q1, t_q3 = _segment_percentiles(tmag, seg, n_seg)
+        t_lo, t_hi = t_q1 - tr_m * (t_q3 - t_q1), t_q3 + tr_m * (t_q3 - t_q1)
+        Rm = _quats_to_matrices(_segment_quaternion_average(quats, seg, n_seg))
+        tr = np.clip(np.einsum("nij,nij->n", R, Rm[seg]), -1.0, 3.0)  # trace(R Rm^T)
+        ang = np.degrees(np.arccos((tr - 1) / 2))
+        r_q1, r_q3 = _segment_percentiles(ang, seg, n_seg)
+        r_hi = r_q3 + rot_m * (r_q3 - r_q1)
+        bad = (tmag < t_lo[seg]) | (tmag > t_hi[seg]) | (ang > r_hi[seg])
+        ok = ~(bad & big[seg])
+    keep[rows[ok]] = True
+    rows, seg2, R, t, quats = rows[ok], seg[ok], R[ok], t[ok], quats[ok]
+    if len(rows) == 0:
+        return empty
+    uniq2, seg3 = np.unique(seg2, return_inverse=True)
+    n2 = len(uniq2)
+    cnt2 = np.bincount(seg3, minlength=n2)
+    starts = np.flatnonzero(np.concatenate([[True], np.diff(seg3) != 0]))
+    R_agg = _quats_to_matrices(_segment_quaternion_average(quats, seg3, n2))
+    t_agg = np.add.reduceat(t, starts, axis=0) / cnt2[:, None]
+    one = cnt2 == 1
+    if one.any():  # a single survivor is passed through untouched (:551-553)
+        R_agg[one] = R[starts[one]]
+        t_agg[one] = t[starts[one]]
+    pk2 = uniq[uniq2]
+    pairs = np.stack([pk2 // span, pk2 % span], axis=1).astype(np.int64)
+    return pairs, keep, R_agg, t_agg, cnt2.astype(np.int64)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -329,16 +418,15 @@ def stereo_rmse_arrays(tab: CameraTables, pairs: np.ndarray, R: np.ndarray, t: n
     if p == 0:
         return rmse, cnt
     cam_id = np.asarray(cam_id, dtype=np.int64)
-    sel = np.array([int(c) in tab.index_of for c in np.unique(cam_id)])
-    ok_ids = np.unique(cam_id)[sel]
-    m = np.isin(cam_id, ok_ids)
-    cam_id = cam_id[m]
-    rs, us = _rank(np.asarray(sync_index, dtype=np.int64)[m])
-    ro, uo = _rank(np.asarray(object_id, dtype=np.int64)[m])
-    rk, uk = _rank(np.asarray(keypoint_id, dtype=np.int64)[m])
-    key = np.ascontiguousarray((rs * len(uo) + ro) * len(uk) + rk)
-    slot = np.ascontiguousarray(np.array([tab.index_of[int(c)] for c in np.unique(cam_id)], dtype=np.int32)[_rank(cam_id)[0]])
-    px = np.ascontiguousarray(np.asarray(img_xy, dtype=np.float64).reshape(-1, 2)[m])
+    slot = _slots(tab, cam_id)
+    m = slot >= 0
+    sync_index, object_id, keypoint_id = (np.asarray(a, dtype=np.int64) for a in (sync_index, object_id, keypoint_id))
+    px = np.asarray(img_xy, dtype=np.float64).reshape(-1, 2)
+    if not m.all():
+        slot, sync_index, object_id, keypoint_id, px = slot[m], sync_index[m], object_id[m], keypoint_id[m], px[m]
+    key = _pack(sync_index, object_id, keypoint_id)
+    slot = np.ascontiguousarray(slot, dtype=np.int32)
+    px = np.ascontiguousarray(px)
     # device pairs are (slot_lo, slot_hi); a pose given for (a, b) must be inverted when slot[a] > slot[b]
     sa = np.array([tab.index_of[int(a)] for a in pairs[:, 0]], dtype=np.int32)
     sb = np.array([tab.index_of[int(b)] for b in pairs[:, 1]], dtype=np.int32)

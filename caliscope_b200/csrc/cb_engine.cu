@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -1517,6 +1518,16 @@ static int build_schur_items(CbBaProblem* p, cudaStream_t st) {
 
 static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_t st, CbBaProblem* p) {
   NvtxRange nvtx_create("cb_ba_problem_create (upload + index build)");
+  // CB_PROFILE_CREATE=1: host wall-clock of the stages of problem creation on stderr (diagnostic)
+  const bool prof = std::getenv("CB_PROFILE_CREATE") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!prof) return;
+    cudaStreamSynchronize(st);
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[create] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();
@@ -1612,6 +1623,7 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
   p->d_obs_cam = d_cam; p->d_obs_pt = d_pt; p->d_obs_xy = d_xy;
   p->h_cam_flags.assign(d->cam_flags, d->cam_flags + p->n_cams);
   p->h_cam_const.assign(d->cam_const, d->cam_const + 9 * (size_t)p->n_cams);
+  lap("alloc + staged upload");
   int rc = build_indices(p, d_cam, d_pt, d_xy, d->cam_order, st, xy_ready);
   if (xy_ready) cudaEventDestroy(xy_ready);
   CB_TRY(rc);
@@ -1632,7 +1644,9 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
     CB_CUDA(cudaStreamSynchronize(st));
   }
 
+  lap("index build + camera tables");
   CB_TRY(build_schur_items(p, st));
+  lap("schur work items");
   std::vector<unsigned char> act((size_t)p->nP, 0);
   for (int c = 0; c < p->n_cams; ++c)
     for (int a = 0; a < ((p->h_iflags[c] & CB_CAM_FREE_INTRINSICS) ? 9 : 6); ++a) act[(size_t)c * p->P + a] = 1;
@@ -1700,8 +1714,10 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
 #undef CB_SMEM_ATTR
     CB_CUDA(cudaGetLastError());
   }
+  lap("work buffers + memsets");
   CB_TRY(choose_pcg_config(p));
   CB_CUDA(cudaStreamSynchronize(st));
+  lap("pcg config");
   return CB_OK;
 }
 
@@ -2592,20 +2608,19 @@ int group_by_key(const long long* d_key, int n, cudaStream_t st, ScopedFree& sf,
   CB_TRY(dalloc(&d_head, (size_t)n)); sf.dev.push_back(d_head);
   CB_TRY(dalloc(&d_gid, (size_t)n)); sf.dev.push_back(d_gid);
   CB_TRY(dalloc(&dstart, (size_t)n + 1)); sf.dev.push_back(dstart);
-  size_t tb_sort = 0, tb_scan = 0;
+  size_t tb_sort = 0, tb_scan = 0, tb_red = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, tb_sort, (const unsigned long long*)d_key, k_out, v_in, v_out, n, 0, 64, st);
   cub::DeviceScan::InclusiveSum(nullptr, tb_scan, d_head, d_gid, n, st);
+  cub::DeviceReduce::Max(nullptr, tb_red, (const unsigned long long*)d_key, (unsigned long long*)nullptr, n, st);
   void* d_tmp = nullptr;
-  size_t tb = std::max(tb_sort, tb_scan);
+  size_t tb = std::max(std::max(tb_sort, tb_scan), tb_red);
   CB_TRY(cached_malloc(&d_tmp, std::max<size_t>(tb, 16)));
   sf.dev.push_back(d_tmp);
   CB_LAUNCH(cb::tri_iota_kernel, G, TB, 0, st, v_in, (long long)n);
   // radix passes only over the key's significant bits (a packed (sync, object, keypoint) key of a 50k-point rig has 16)
   unsigned long long* d_max = nullptr;
   CB_TRY(dalloc(&d_max, 1)); sf.dev.push_back(d_max);
-  size_t tb_max = 0;
-  cub::DeviceReduce::Max(nullptr, tb_max, (const unsigned long long*)d_key, d_max, n, st);
-  if (tb_max > tb) { g_last_error = "group_by_key: scratch too small"; return CB_E_CUDA; }
+  size_t tb_max = tb;
   CB_CUDA(cub::DeviceReduce::Max(d_tmp, tb_max, (const unsigned long long*)d_key, d_max, n, st));
   unsigned long long h_max = 0;
   CB_CUDA(cudaMemcpyAsync(&h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost, st));

@@ -89,9 +89,15 @@ pt_pass_kernel(const LmState* __restrict__ st, const int* __restrict__ pt_start,
     double v[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) v[k] = 0.0;
+    // (index / pixel of the next row are requested before the current one is evaluated: the kernel is latency bound --
+    // 16 warps per SM, long_scoreboard 60 % of the stalls in the first version)
+    int cam_n = 0;
+    double2 xy_n = make_double2(0.0, 0.0);
+    if (s + gl < e) { cam_n = pm_cam[s + gl]; xy_n = pm_xy[s + gl]; }
     for (int pos = s + gl; pos < e; pos += LANES) {
-      const int cam = pm_cam[pos];
-      const double2 xy = pm_xy[pos];
+      const int cam = cam_n;
+      const double2 xy = xy_n;
+      if (pos + LANES < e) { cam_n = pm_cam[pos + LANES]; xy_n = pm_xy[pos + LANES]; }
       double f[2], JX[6];
       obs_res_jx(ctab + (size_t)cam * cstride, X0, X1, X2, xy.x, xy.y, loss, fscale, f, JX);
       v[0] += JX[0] * JX[0] + JX[3] * JX[3]; v[1] += JX[0] * JX[1] + JX[3] * JX[4]; v[2] += JX[0] * JX[2] + JX[3] * JX[5];
@@ -123,13 +129,15 @@ pt_pass_kernel(const LmState* __restrict__ st, const int* __restrict__ pt_start,
       }
     }
     // ---- phase 2: Z = (Jc^T Jp) Linv^T per (camera, point) pair, rows 3j..3j+2 of the k-major factor
+    if (s + gl < e) { cam_n = pm_cam[s + gl]; xy_n = pm_xy[s + gl]; }
     for (int pos = s + gl; pos < e; pos += LANES) {
       int cam;
       double f[2], JX[6], Jc[2 * P];
       double z[3][P];
       if constexpr (!DUPS) {
-        cam = pm_cam[pos];
-        const double2 xy = pm_xy[pos];
+        cam = cam_n;
+        const double2 xy = xy_n;
+        if (pos + LANES < e) { cam_n = pm_cam[pos + LANES]; xy_n = pm_xy[pos + LANES]; }
         obs_jac<P>(ctab + (size_t)cam * cstride, X0, X1, X2, xy.x, xy.y, loss, fscale, f, JX, Jc);
         const double q00 = JX[0] * Li[0], q01 = JX[0] * Li[1] + JX[1] * Li[2], q02 = JX[0] * Li[3] + JX[1] * Li[4] + JX[2] * Li[5];
         const double q10 = JX[3] * Li[0], q11 = JX[3] * Li[1] + JX[4] * Li[2], q12 = JX[3] * Li[3] + JX[4] * Li[4] + JX[5] * Li[5];
@@ -238,9 +246,13 @@ pt_backsub_kernel(const LmState* __restrict__ st, const int* __restrict__ pt_sta
     }
     (void)X3;
     double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+    int cam_n = 0;
+    double2 xy_n = make_double2(0.0, 0.0);
+    if (s + gl < e) { cam_n = pm_cam[s + gl]; xy_n = pm_xy[s + gl]; }
     for (int pos = s + gl; pos < e; pos += LANES) {
-      const int cam = pm_cam[pos];
-      const double2 xy = pm_xy[pos];
+      const int cam = cam_n;
+      const double2 xy = xy_n;
+      if (pos + LANES < e) { cam_n = pm_cam[pos + LANES]; xy_n = pm_xy[pos + LANES]; }
       double f[2], JX[6], Jc[2 * P];
       obs_jac<P>(ctab + (size_t)cam * cstride, X0, X1, X2, xy.x, xy.y, loss, fscale, f, JX, Jc);
       const double* d = dcs + cam * P;
