@@ -547,8 +547,28 @@ int choose_camera_order(CbBaProblem* p, const int* cam_order, cudaStream_t st) {
   return CB_OK;
 }
 
+// The image coordinates (two thirds of an upload from host memory) are only needed by the LAST index-build kernels: a
+// background thread stages them through pinned memory on a side stream while the calling thread queues the index sorts.
+struct XyUpload {
+  std::thread th;
+  cudaEvent_t ev = nullptr;
+  int rc = CB_OK;
+  std::string err;
+  // join the staging thread, then make `st` wait for the copies it queued
+  int wait(cudaStream_t st) {
+    if (th.joinable()) th.join();
+    if (rc != CB_OK) { g_last_error = err; return rc; }
+    if (ev) CB_CUDA(cudaStreamWaitEvent(st, ev, 0));
+    return CB_OK;
+  }
+  ~XyUpload() {
+    if (th.joinable()) th.join();
+    if (ev) { cudaEventSynchronize(ev); cudaEventDestroy(ev); }  // the pinned staging block outlives its DMA on every path
+  }
+};
+
 int build_indices(CbBaProblem* p, const int* d_obs_cam, const int* d_obs_pt, const double* d_obs_xy,
-                  const int* cam_order, cudaStream_t st, cudaEvent_t xy_ready) {
+                  const int* cam_order, cudaStream_t st, XyUpload* xy_upload) {
   const int n = p->n_obs;
   const int TB = 256, G = cdiv(std::max(n, 1), TB);
   ScopedFree sf;
@@ -589,7 +609,7 @@ int build_indices(CbBaProblem* p, const int* d_obs_cam, const int* d_obs_pt, con
   g_launches.fetch_add(4);
   CB_LAUNCH(cb::split_keys_kernel, G, TB, 0, st, k_out, (long long)p->n_pts, n, cm_cam, v_in);
   CB_LAUNCH(cb::lower_bound_kernel, cdiv(p->n_cams + 1, TB), TB, 0, st, cm_cam, n, p->n_cams, p->d_cam_start);
-  if (xy_ready) CB_CUDA(cudaStreamWaitEvent(st, xy_ready, 0));
+  if (xy_upload) CB_TRY(xy_upload->wait(st));
   CB_LAUNCH(cb::cm_gather_kernel, G, TB, 0, st, v_out, p->d_pm_orig, pm_pt,
             reinterpret_cast<const double2*>(d_obs_xy), n, p->d_cm_pt, p->d_cm_orig, p->d_cm_xy);
   CB_LAUNCH(cb::pm_gather_kernel, G, TB, 0, st, p->d_pm_orig, reinterpret_cast<const double2*>(d_obs_xy), n, p->d_pm_xy);
@@ -651,23 +671,26 @@ void launch_resjac(CbBaProblem* p, const cb::LmState* st_dev, int flip, int loss
 
 template <int P>
 void launch_pt_pass(CbBaProblem* p, cudaStream_t st) {
-#define CB_PT_PASS(LANES, DUPS)                                                                                       \
-  CB_LAUNCH((cb::pt_pass_kernel<P, LANES, DUPS>), p->pt_grid, cb::PT_WARPS * 32, p->pt_smem, st, p->d_state,          \
+#define CB_PT_PASS(LANES, DUPS, SM)                                                                                   \
+  CB_LAUNCH((cb::pt_pass_kernel<P, LANES, DUPS, SM>), p->pt_grid, cb::PT_WARPS * 32, p->pt_smem, st, p->d_state,      \
             p->d_pt_start, p->d_pm_cam, p->d_pm_xy, p->d_pt_comp, p->n_pts, p->n_cams, p->c_camtab(), p->c_xp(),       \
-            p->d_V6, p->d_gp, p->d_Dp2, p->d_Linv6, p->d_tvec, p->d_Zt, (size_t)p->LD, p->d_gmax, p->cam_in_smem)
-  if (p->pt_lanes == 8) { if (p->n_dups) CB_PT_PASS(8, true); else CB_PT_PASS(8, false); }
-  else { if (p->n_dups) CB_PT_PASS(32, true); else CB_PT_PASS(32, false); }
+            p->d_V6, p->d_gp, p->d_Dp2, p->d_Linv6, p->d_tvec, p->d_Zt, (size_t)p->LD, p->d_gmax)
+#define CB_PT_PASS2(LANES, DUPS) do { if (p->cam_in_smem) CB_PT_PASS(LANES, DUPS, true); else CB_PT_PASS(LANES, DUPS, false); } while (0)
+  if (p->pt_lanes == 8) { if (p->n_dups) CB_PT_PASS2(8, true); else CB_PT_PASS2(8, false); }
+  else { if (p->n_dups) CB_PT_PASS2(32, true); else CB_PT_PASS2(32, false); }
+#undef CB_PT_PASS2
 #undef CB_PT_PASS
 }
 
 template <int P>
 void launch_pt_backsub(CbBaProblem* p, double* dp_out, cudaStream_t st) {
   const int bstride = p->pt_grid + p->n_comp;
-#define CB_PT_BACK(LANES)                                                                                             \
-  CB_LAUNCH((cb::pt_backsub_kernel<P, LANES>), p->pt_grid, cb::PT_WARPS * 32, p->bs_smem, st, p->d_state,             \
+#define CB_PT_BACK(LANES, SM)                                                                                         \
+  CB_LAUNCH((cb::pt_backsub_kernel<P, LANES, SM>), p->pt_grid, cb::PT_WARPS * 32, p->bs_smem, st, p->d_state,         \
             p->d_pt_start, p->d_pm_cam, p->d_pm_xy, p->d_pt_comp, p->n_pts, p->n_cams, p->nP, p->c_camtab(),           \
-            p->m_xp(), p->d_dc, p->d_Linv6, p->d_tvec, p->d_gp, p->d_Dp2, dp_out, p->d_bpart, bstride, p->cam_in_smem)
-  if (p->pt_lanes == 8) CB_PT_BACK(8); else CB_PT_BACK(32);
+            p->m_xp(), p->d_dc, p->d_Linv6, p->d_tvec, p->d_gp, p->d_Dp2, dp_out, p->d_bpart, bstride)
+  if (p->pt_lanes == 8) { if (p->cam_in_smem) CB_PT_BACK(8, true); else CB_PT_BACK(8, false); }
+  else { if (p->cam_in_smem) CB_PT_BACK(32, true); else CB_PT_BACK(32, false); }
 #undef CB_PT_BACK
 }
 
@@ -1371,27 +1394,17 @@ static int build_schur_items(CbBaProblem* p, cudaStream_t st) {
     CB_TRY(dalloc(&d_mask, (size_t)p->n_pts));
     ScopedFree sf; sf.dev.push_back(d_mask);
     CB_LAUNCH(cb::pt_tile_mask_kernel, cdiv(p->n_pts, 256), 256, 0, st, p->d_pt_start, p->d_pm_cam, p->n_pts, p->P, d_mask);
-    std::vector<unsigned long long> mask((size_t)p->n_pts);
-    CB_CUDA(cudaMemcpyAsync(mask.data(), d_mask, sizeof(unsigned long long) * p->n_pts, cudaMemcpyDeviceToHost, st));
+    // incidence counts per tile pair (dense rigs stop here: no mask download, no host pass over the points)
+    unsigned long long* d_cnt;
+    CB_TRY(dalloc(&d_cnt, (size_t)nt));
+    sf.dev.push_back(d_cnt);
+    CB_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * nt, st));
+    CB_LAUNCH(cb::tile_pair_count_kernel, cdiv(p->n_pts, 256), 256, sizeof(unsigned) * nt, st, d_mask, p->n_pts, nb, d_cnt);
+    std::vector<unsigned long long> cnt_u((size_t)nt);
+    CB_CUDA(cudaMemcpyAsync(cnt_u.data(), d_cnt, sizeof(unsigned long long) * nt, cudaMemcpyDeviceToHost, st));
     CB_CUDA(cudaStreamSynchronize(st));
-    // incidence counts per tile pair, through the histogram of distinct masks (dense rigs: one mask, all tiles)
-    std::vector<long long> cnt(nt, 0);
-    {
-      std::map<unsigned long long, long long> hist;
-      unsigned long long last = ~0ull;
-      long long run = 0;
-      for (int j = 0; j < p->n_pts; ++j) {  // run-length first: neighbouring points usually share their mask
-        if (mask[j] == last) { ++run; continue; }
-        if (run) hist[last] += run;
-        last = mask[j]; run = 1;
-      }
-      if (run) hist[last] += run;
-      for (auto& kv : hist)
-        for (unsigned long long a = kv.first; a; a &= a - 1) {
-          const int I = __builtin_ctzll(a);
-          for (unsigned long long b2 = a; b2; b2 &= b2 - 1) cnt[tof[(size_t)I * nb + __builtin_ctzll(b2)]] += kv.second;
-        }
-    }
+    std::vector<long long> cnt(cnt_u.begin(), cnt_u.end());
+    std::vector<unsigned long long> mask;
     double listed = 0.0, dense = 0.0;
     for (int I = 0; I < nb; ++I)
       for (int J = I; J < nb; ++J) {
@@ -1402,6 +1415,9 @@ static int build_schur_items(CbBaProblem* p, cudaStream_t st) {
     p->schur_rows_dense = 3.0 * dense; p->schur_rows_listed = 3.0 * listed;
     sparse = want_sparse == 1 || listed < 0.7 * dense;
     if (sparse) {
+      mask.resize((size_t)p->n_pts);
+      CB_CUDA(cudaMemcpyAsync(mask.data(), d_mask, sizeof(unsigned long long) * p->n_pts, cudaMemcpyDeviceToHost, st));
+      CB_CUDA(cudaStreamSynchronize(st));
       plist.resize(nt);
       for (int t = 0; t < nt; ++t) plist[t].reserve((size_t)cnt[t]);
       for (int j = 0; j < p->n_pts; ++j) {
@@ -1446,20 +1462,25 @@ static int build_schur_items(CbBaProblem* p, cudaStream_t st) {
   int slot = 0;
   // CTAs per group: proportional share rounded down, then the SMs left over go one by one to the group whose CTAs carry
   // the most work (6 tiles at P = 9: 18 groups, floor alone leaves 10 of 148 SMs idle)
+  // A CTA gets at least SY_MIN_CHUNKS k-chunks: every split-K slot is a 96x96 partial tile the finalize kernel reads back
+  // serially, and on a small rig (4 cameras x 2000 points: 188 chunks in ONE tile) 148 slots of 1-2 chunks each made the
+  // finalize kernel (78 us) cost 5x the product it reduces.
+  constexpr int SY_MIN_CHUNKS = 8;
+  auto cap_of = [&](const Group& g) { return std::max(1, g.chunks / SY_MIN_CHUNKS); };
   std::vector<int> n_of(groups.size(), 1);
   {
     int used = 0;
     for (size_t gi = 0; gi < groups.size(); ++gi) {
       const Group& g = groups[gi];
       int n = (int)std::floor(p->num_sms * (g.w * g.chunks) / std::max(W, 1.0));
-      n_of[gi] = std::max(1, std::min(n, g.chunks));
+      n_of[gi] = std::max(1, std::min(n, cap_of(g)));
       used += n_of[gi];
     }
     while (used < p->num_sms) {
       int best = -1;
       double load = 0.0;
       for (size_t gi = 0; gi < groups.size(); ++gi) {
-        if (n_of[gi] >= groups[gi].chunks) continue;
+        if (n_of[gi] >= cap_of(groups[gi])) continue;
         const double l = groups[gi].w * groups[gi].chunks / n_of[gi];
         if (l > load) { load = l; best = (int)gi; }
       }
@@ -1592,8 +1613,8 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
   const double* d_xy = d->obs_xy;
   int *t_cam = nullptr, *t_pt = nullptr;
   double* t_xy = nullptr;
-  cudaEvent_t xy_ready = nullptr;
   ScopedFree stage;  // pinned staging blocks: released when this function returns (it synchronises before)
+  XyUpload xy_up;    // declared after `stage`: its destructor joins the staging thread before the pinned blocks go
   if (!d->obs_on_device) {
     CB_TRY(dalloc(&t_cam, n)); CB_TRY(dalloc(&t_pt, n)); CB_TRY(dalloc(&t_xy, 2 * (size_t)n));
     p->allocs.push_back(t_cam); p->allocs.push_back(t_pt); p->allocs.push_back(t_xy);  // kept: the cull path compacts them
@@ -1607,12 +1628,23 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
       CB_TRY(staged_h2d(t_cam, d->obs_cam, sizeof(int) * (size_t)n, st, stage));
     }
     CB_TRY(staged_h2d(t_pt, d->obs_pt, sizeof(int) * (size_t)n, st, stage));
-    // the image coordinates (two thirds of the upload) are only needed by the last index-build kernel:
-    // copy them on a side stream while the sorts run
-    CB_CUDA(cudaEventCreateWithFlags(&xy_ready, cudaEventDisableTiming));
-    int rc_xy = staged_h2d(t_xy, d->obs_xy, sizeof(double) * 2 * (size_t)n, side_stream(), stage);
-    if (rc_xy != CB_OK) { cudaEventDestroy(xy_ready); return rc_xy; }
-    CB_CUDA(cudaEventRecord(xy_ready, side_stream()));
+    CB_CUDA(cudaEventCreateWithFlags(&xy_up.ev, cudaEventDisableTiming));
+    {
+      cudaStream_t side = side_stream();
+      const double* src = d->obs_xy;
+      const size_t bytes = sizeof(double) * 2 * (size_t)n;
+      const int dev = p->device;
+      xy_up.th = std::thread([&xy_up, &stage_xy = stage, t_xy, src, bytes, side, dev] {
+        cudaSetDevice(dev);
+        ScopedFree local;
+        xy_up.rc = staged_h2d(t_xy, src, bytes, side, local, 8);
+        if (xy_up.rc == CB_OK && cudaEventRecord(xy_up.ev, side) != cudaSuccess) xy_up.rc = CB_E_CUDA;
+        if (xy_up.rc != CB_OK) xy_up.err = "staged upload of obs_xy failed";
+        // hand the pinned block to the caller's scope (freed after the stream has drained)
+        for (void* q : local.host) stage_xy.host.push_back(q);
+        local.host.clear();
+      });
+    }
     d_cam = t_cam; d_pt = t_pt; d_xy = t_xy;
   } else if (d->obs_cam_bits == 16) {
     CB_TRY(dalloc(&t_cam, n));
@@ -1624,9 +1656,7 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
   p->h_cam_flags.assign(d->cam_flags, d->cam_flags + p->n_cams);
   p->h_cam_const.assign(d->cam_const, d->cam_const + 9 * (size_t)p->n_cams);
   lap("alloc + staged upload");
-  int rc = build_indices(p, d_cam, d_pt, d_xy, d->cam_order, st, xy_ready);
-  if (xy_ready) cudaEventDestroy(xy_ready);
-  CB_TRY(rc);
+  CB_TRY(build_indices(p, d_cam, d_pt, d_xy, d->cam_order, st, xy_up.th.joinable() ? &xy_up : nullptr));
   // camera tables by internal slot
   {
     std::vector<int> xoff(p->n_cams);
@@ -1703,12 +1733,14 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
     const int a = (int)p->pt_smem, b2 = (int)p->bs_smem;
 #define CB_SMEM_ATTR(PP)                                                                                           \
     do {                                                                                                             \
-      cudaFuncSetAttribute(cb::pt_pass_kernel<PP, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);       \
-      cudaFuncSetAttribute(cb::pt_pass_kernel<PP, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);        \
-      cudaFuncSetAttribute(cb::pt_pass_kernel<PP, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);      \
-      cudaFuncSetAttribute(cb::pt_pass_kernel<PP, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);       \
-      cudaFuncSetAttribute(cb::pt_backsub_kernel<PP, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, b2);          \
-      cudaFuncSetAttribute(cb::pt_backsub_kernel<PP, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, b2);         \
+      cudaFuncSetAttribute(cb::pt_pass_kernel<PP, 8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);  \
+      cudaFuncSetAttribute(cb::pt_pass_kernel<PP, 8, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);   \
+      cudaFuncSetAttribute(cb::pt_pass_kernel<PP, 32, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, a); \
+      cudaFuncSetAttribute(cb::pt_pass_kernel<PP, 32, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);  \
+      cudaFuncSetAttribute(cb::pt_backsub_kernel<PP, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b2);     \
+      cudaFuncSetAttribute(cb::pt_backsub_kernel<PP, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, b2);    \
+      cudaFuncSetAttribute(cb::pt_backsub_kernel<PP, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b2);    \
+      cudaFuncSetAttribute(cb::pt_backsub_kernel<PP, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, b2);   \
     } while (0)
     if (p->P == 6) CB_SMEM_ATTR(6); else CB_SMEM_ATTR(9);
 #undef CB_SMEM_ATTR

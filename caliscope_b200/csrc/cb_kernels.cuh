@@ -558,7 +558,9 @@ __device__ __forceinline__ void finalize_elem(size_t idx, int nP, int n_blk, con
     if (I == J && li / 24 > lj / 24) { int t = li; li = lj; lj = t; }
     const int tile = tile_of[I * n_blk + J];
     double s = 0.0;
-    for (int q = tile_slot_start[tile]; q < tile_slot_start[tile + 1]; ++q)
+    const int q1 = tile_slot_start[tile + 1];
+#pragma unroll 8
+    for (int q = tile_slot_start[tile]; q < q1; ++q)  // fixed slot order: the sum is reproducible run to run
       s += part[(size_t)tile_slots[q] * (SY_TILE * SY_TILE) + li * SY_TILE + lj];
     double u = 0.0;
     const int ci = i / P, cj = j / P;
@@ -573,7 +575,9 @@ __device__ __forceinline__ void finalize_elem(size_t idx, int nP, int n_blk, con
     const int I = i / SY_TILE, li = i % SY_TILE;
     const int tile = tile_of[I * n_blk + I];
     double s = 0.0;
-    for (int q = tile_slot_start[tile]; q < tile_slot_start[tile + 1]; ++q)
+    const int q1 = tile_slot_start[tile + 1];
+#pragma unroll 8
+    for (int q = tile_slot_start[tile]; q < q1; ++q)
       s += tpart[(size_t)tile_slots[q] * SY_TILE + li];
     red[nn + i] = gc[i] - s;
     red[nn + nP + i] = gc[i];
@@ -927,6 +931,32 @@ __global__ void pt_tile_mask_kernel(const int* __restrict__ pt_start, const int*
     m |= 1ull << ((c0 + P - 1) / SY_TILE);
   }
   mask[j] = m;
+}
+// cnt[tile(I,J)] = number of points whose mask has bits I and J (I <= J; tile(I,J) = I*nb - I(I-1)/2 + J-I): what the host
+// needs to choose between the dense and the k-list Schur product, without downloading the masks.  Lanes holding the same
+// mask (the usual case: neighbouring points are seen by the same cameras) are counted once per warp.
+__global__ void tile_pair_count_kernel(const unsigned long long* __restrict__ mask, int n_pts, int nb,
+                                       unsigned long long* __restrict__ cnt) {
+  extern __shared__ unsigned int tp_cnt[];
+  const int nt = nb * (nb + 1) / 2;
+  for (int i = threadIdx.x; i < nt; i += blockDim.x) tp_cnt[i] = 0u;
+  __syncthreads();
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long m = j < n_pts ? mask[j] : 0ull;
+  const unsigned peers = __match_any_sync(0xffffffffu, m);
+  if (m && (threadIdx.x & 31) == __ffs(peers) - 1) {
+    const unsigned k = __popc(peers);
+    for (unsigned long long a = m; a; a &= a - 1) {
+      const int I = __ffsll((long long)a) - 1;
+      for (unsigned long long b = a; b; b &= b - 1) {
+        const int J = __ffsll((long long)b) - 1;
+        atomicAdd(&tp_cnt[I * nb - I * (I - 1) / 2 + (J - I)], k);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nt; i += blockDim.x)
+    if (tp_cnt[i]) atomicAdd(&cnt[i], (unsigned long long)tp_cnt[i]);
 }
 // point-major pixel list
 __global__ void pm_gather_kernel(const int* __restrict__ pm_orig, const double2* __restrict__ obs_xy, int n,

@@ -47,13 +47,16 @@ __device__ __forceinline__ double group_sum(double v) {
 // Points tied by rigid-distance constraints (pt_comp >= 0) only get V, g and the untransformed W = Jc^T Jp written to
 // their Zt rows; comp_build_kernel eliminates the component.
 // ---------------------------------------------------------------------------------------------
-template <int P, int LANES, bool DUPS>
+// CAMSM: the camera table is staged in shared memory (it fits: <= 64 KB).  A template parameter, not a run-time pointer
+// select: with a pointer that may be shared or global the compiler emits GENERIC loads (LD.E) for the ~36 table reads per
+// observation, which wait on the long scoreboard like global loads (ncu: 55 % of the stalls of the first version).
+template <int P, int LANES, bool DUPS, bool CAMSM>
 __global__ void __launch_bounds__(PT_WARPS * 32, 2)
 pt_pass_kernel(const LmState* __restrict__ st, const int* __restrict__ pt_start, const int* __restrict__ pm_cam,
                const double2* __restrict__ pm_xy, const int* __restrict__ pt_comp, int n_pts, int n_cams,
                CPtr2 camtab2, CPtr2 xp2, double* __restrict__ V6, double* __restrict__ gp,
                double* __restrict__ Dp2, double* __restrict__ Linv6, double* __restrict__ tvec,
-               double* __restrict__ Zt, size_t LD, unsigned long long* __restrict__ gmax_bits, int cam_in_smem) {
+               double* __restrict__ Zt, size_t LD, unsigned long long* __restrict__ gmax_bits) {
   extern __shared__ __align__(16) double pt_sm[];
   __shared__ double wmax[PT_WARPS];
   if (st->done) return;
@@ -61,15 +64,18 @@ pt_pass_kernel(const LmState* __restrict__ st, const int* __restrict__ pt_start,
   const double lam = st->lam;
   const int loss = st->loss;
   const double fscale = st->fscale;
-  const double* ctab = camtab2.p[cur];
+  const double* __restrict__ gtab = camtab2.p[cur];
   const double* xp4 = xp2.p[cur];
-  int cstride = CT_SIZE;
-  if (cam_in_smem) {
-    for (int i = threadIdx.x; i < n_cams * CT_SIZE; i += blockDim.x) pt_sm[(i / CT_SIZE) * CT_SMEM + i % CT_SIZE] = ctab[i];
+  constexpr int cstride = CAMSM ? CT_SMEM : CT_SIZE;
+  if constexpr (CAMSM) {
+    for (int i = threadIdx.x; i < n_cams * CT_SIZE; i += blockDim.x) pt_sm[(i / CT_SIZE) * CT_SMEM + i % CT_SIZE] = gtab[i];
     __syncthreads();
-    ctab = pt_sm;
-    cstride = CT_SMEM;
   }
+  // camera table entry of camera c: shared (LDS) or global (LDG), decided at compile time
+  auto cam_entry = [&](int c) -> const double* {
+    if constexpr (CAMSM) return pt_sm + (size_t)c * cstride;
+    else return gtab + (size_t)c * cstride;
+  };
   constexpr int GPW = 32 / LANES;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int gl = lane % LANES, grp = lane / LANES;
@@ -99,7 +105,7 @@ pt_pass_kernel(const LmState* __restrict__ st, const int* __restrict__ pt_start,
       const double2 xy = xy_n;
       if (pos + LANES < e) { cam_n = pm_cam[pos + LANES]; xy_n = pm_xy[pos + LANES]; }
       double f[2], JX[6];
-      obs_res_jx(ctab + (size_t)cam * cstride, X0, X1, X2, xy.x, xy.y, loss, fscale, f, JX);
+      obs_res_jx(cam_entry(cam), X0, X1, X2, xy.x, xy.y, loss, fscale, f, JX);
       v[0] += JX[0] * JX[0] + JX[3] * JX[3]; v[1] += JX[0] * JX[1] + JX[3] * JX[4]; v[2] += JX[0] * JX[2] + JX[3] * JX[5];
       v[3] += JX[1] * JX[1] + JX[4] * JX[4]; v[4] += JX[1] * JX[2] + JX[4] * JX[5]; v[5] += JX[2] * JX[2] + JX[5] * JX[5];
       v[6] += JX[0] * f[0] + JX[3] * f[1]; v[7] += JX[1] * f[0] + JX[4] * f[1]; v[8] += JX[2] * f[0] + JX[5] * f[1];
@@ -138,7 +144,7 @@ pt_pass_kernel(const LmState* __restrict__ st, const int* __restrict__ pt_start,
         cam = cam_n;
         const double2 xy = xy_n;
         if (pos + LANES < e) { cam_n = pm_cam[pos + LANES]; xy_n = pm_xy[pos + LANES]; }
-        obs_jac<P>(ctab + (size_t)cam * cstride, X0, X1, X2, xy.x, xy.y, loss, fscale, f, JX, Jc);
+        obs_jac<P>(cam_entry(cam), X0, X1, X2, xy.x, xy.y, loss, fscale, f, JX, Jc);
         const double q00 = JX[0] * Li[0], q01 = JX[0] * Li[1] + JX[1] * Li[2], q02 = JX[0] * Li[3] + JX[1] * Li[4] + JX[2] * Li[5];
         const double q10 = JX[3] * Li[0], q11 = JX[3] * Li[1] + JX[4] * Li[2], q12 = JX[3] * Li[3] + JX[4] * Li[4] + JX[5] * Li[5];
 #pragma unroll
@@ -157,7 +163,7 @@ pt_pass_kernel(const LmState* __restrict__ st, const int* __restrict__ pt_start,
         int r = pos;
         do {
           const double2 xy = pm_xy[r];
-          obs_jac<P>(ctab + (size_t)cam * cstride, X0, X1, X2, xy.x, xy.y, loss, fscale, f, JX, Jc);
+          obs_jac<P>(cam_entry(cam), X0, X1, X2, xy.x, xy.y, loss, fscale, f, JX, Jc);
           const double q00 = JX[0] * Li[0], q01 = JX[0] * Li[1] + JX[1] * Li[2], q02 = JX[0] * Li[3] + JX[1] * Li[4] + JX[2] * Li[5];
           const double q10 = JX[3] * Li[0], q11 = JX[3] * Li[1] + JX[4] * Li[2], q12 = JX[3] * Li[3] + JX[4] * Li[4] + JX[5] * Li[5];
 #pragma unroll
@@ -203,14 +209,14 @@ pt_pass_kernel(const LmState* __restrict__ st, const int* __restrict__ pt_start,
 // recomputed from the observation list (24 B / observation) instead of streaming the dense factor.
 // Per-CTA partial sums of the predicted reduction / step / x norms (fixed grid => deterministic).
 // ---------------------------------------------------------------------------------------------
-template <int P, int LANES>
+template <int P, int LANES, bool CAMSM>
 __global__ void __launch_bounds__(PT_WARPS * 32, 2)
 pt_backsub_kernel(const LmState* __restrict__ st, const int* __restrict__ pt_start, const int* __restrict__ pm_cam,
                   const double2* __restrict__ pm_xy, const int* __restrict__ pt_comp, int n_pts, int n_cams, int nP,
                   CPtr2 camtab2, Ptr2 xp2, const double* __restrict__ dc,
                   const double* __restrict__ Linv6, const double* __restrict__ tvec, const double* __restrict__ gp,
                   const double* __restrict__ Dp2, double* __restrict__ dp_out, double* __restrict__ bpart,
-                  int bpart_stride, int cam_in_smem) {
+                  int bpart_stride) {
   extern __shared__ __align__(16) double bs_sm[];
   __shared__ double wsum[3][PT_WARPS];
   if (st->done) return;
@@ -219,18 +225,19 @@ pt_backsub_kernel(const LmState* __restrict__ st, const int* __restrict__ pt_sta
   const int loss = st->loss;
   const double fscale = st->fscale;
   double* dcs = bs_sm;
-  const double* ctab = camtab2.p[cur];
+  const double* __restrict__ gtab = camtab2.p[cur];
   const double* xp4 = xp2.p[cur];
   double* xp4_new = xp2.p[cur ^ 1];
   for (int i = threadIdx.x; i < nP; i += blockDim.x) dcs[i] = dc[i];
-  int cstride = CT_SIZE;
-  if (cam_in_smem) {
-    double* cs = bs_sm + ((nP + 3) & ~3);
-    for (int i = threadIdx.x; i < n_cams * CT_SIZE; i += blockDim.x) cs[(i / CT_SIZE) * CT_SMEM + i % CT_SIZE] = ctab[i];
-    ctab = cs;
-    cstride = CT_SMEM;
-  }
+  constexpr int cstride = CAMSM ? CT_SMEM : CT_SIZE;
+  double* cs = bs_sm + ((nP + 3) & ~3);
+  if constexpr (CAMSM)
+    for (int i = threadIdx.x; i < n_cams * CT_SIZE; i += blockDim.x) cs[(i / CT_SIZE) * CT_SMEM + i % CT_SIZE] = gtab[i];
   __syncthreads();
+  auto cam_entry = [&](int c) -> const double* {
+    if constexpr (CAMSM) return cs + (size_t)c * cstride;
+    else return gtab + (size_t)c * cstride;
+  };
   constexpr int GPW = 32 / LANES;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int gl = lane % LANES, grp = lane / LANES;
@@ -254,7 +261,7 @@ pt_backsub_kernel(const LmState* __restrict__ st, const int* __restrict__ pt_sta
       const double2 xy = xy_n;
       if (pos + LANES < e) { cam_n = pm_cam[pos + LANES]; xy_n = pm_xy[pos + LANES]; }
       double f[2], JX[6], Jc[2 * P];
-      obs_jac<P>(ctab + (size_t)cam * cstride, X0, X1, X2, xy.x, xy.y, loss, fscale, f, JX, Jc);
+      obs_jac<P>(cam_entry(cam), X0, X1, X2, xy.x, xy.y, loss, fscale, f, JX, Jc);
       const double* d = dcs + cam * P;
       double s0 = 0.0, s1 = 0.0;
 #pragma unroll
