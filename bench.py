@@ -25,6 +25,10 @@ from pathlib import Path
 
 import numpy as np
 
+# NCCL's version banner (NCCL_DEBUG=VERSION, set by some images) goes to stdout ahead of the JSON line
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 ROOT = Path(__file__).resolve().parent
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))

@@ -13,6 +13,6 @@ python - <<'PY'
 import json,glob
 for f in sorted(glob.glob('gpurun_out/r02/scale_n*.json'))+['gpurun_out/r02/cfg5_n8.json']:
     try:
-        d=json.load(open(f)); print(f, d['n_gpus'], round(d['value'],1), round(d['ms_per_step'],3), 'e2e', round(d['e2e']['ms_per_step'],3), d.get('parity',{}).get('abs_diff_px'), json.dumps(d.get('selfcheck',{}))[:400], d.get('allreduce_transport'))
+        d=[json.loads(l) for l in open(f) if l.startswith('{')][-1]; print(f, d['n_gpus'], round(d['value'],1), round(d['ms_per_step'],3), 'e2e', round(d['e2e']['ms_per_step'],3), d.get('parity',{}).get('abs_diff_px'), json.dumps(d.get('selfcheck',{}))[:400], d.get('allreduce_transport'))
     except Exception as e: print(f,'ERR',e)
 PY
