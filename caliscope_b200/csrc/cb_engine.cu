@@ -17,8 +17,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <cub/cub.cuh>
+#include <deque>
+#include <functional>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -258,9 +262,54 @@ struct ScopedFree {
   }
 };
 
+// A few long-lived host threads for staging copies.  Creating threads per call costs ~50 us each and a first CUDA call on
+// a fresh thread binds the context again; the pool is started on first use and lives as long as the process.
+class WorkerPool {
+ public:
+  static WorkerPool& get() {
+    static WorkerPool* pool = new WorkerPool();  // never destroyed: workers may outlive static destruction order
+    return *pool;
+  }
+  int size() const { return (int)threads_.size(); }
+  void submit(std::function<void()> f) {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      q_.push_back(std::move(f));
+    }
+    cv_.notify_one();
+  }
+
+ private:
+  WorkerPool() {
+    unsigned hw = std::thread::hardware_concurrency();
+    int n = (int)std::min<unsigned>(hw > 2 ? hw - 1 : 1, 12u);
+    if (const char* e = std::getenv("CB_STAGE_THREADS")) n = std::max(1, std::atoi(e));
+    for (int i = 0; i < n; ++i) {
+      threads_.emplace_back([this] {
+        for (;;) {
+          std::function<void()> f;
+          {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [this] { return !q_.empty(); });
+            f = std::move(q_.front());
+            q_.pop_front();
+          }
+          f();
+        }
+      });
+      threads_.back().detach();
+    }
+  }
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<std::function<void()>> q_;
+  std::vector<std::thread> threads_;
+};
+
 // Pageable host memory -> device at PCIe speed: cudaMemcpyAsync from pageable memory goes through one driver staging
-// buffer at ~6-10 GB/s, so the caller's arrays (NumPy, pageable) are copied by several threads into a pinned block in
-// chunks, each chunk's DMA queued the moment it is staged.  Returns once the source has been read completely (the caller
+// buffer at ~6-10 GB/s, so the caller's arrays (NumPy, pageable) are copied by pool threads into a pinned block in
+// chunks; the calling thread queues each chunk's DMA in order as soon as it is staged (one thread talks to the driver)
+// and copies chunks itself while it would otherwise wait.  Returns once the source has been read completely (the caller
 // may free it); the pinned block must stay alive until `st` has drained (sf.host frees it at scope exit of the caller,
 // which synchronises first).
 int staged_h2d(void* d_dst, const void* h_src, size_t bytes, cudaStream_t st, ScopedFree& sf, int n_threads = 6) {
@@ -268,32 +317,33 @@ int staged_h2d(void* d_dst, const void* h_src, size_t bytes, cudaStream_t st, Sc
   void* pin = nullptr;
   CB_TRY(cached_malloc_host(&pin, bytes));
   sf.host.push_back(pin);
-  const size_t chunk = (size_t)2 << 20;
+  const size_t chunk = (size_t)1 << 20;
   const size_t n_chunks = (bytes + chunk - 1) / chunk;
-  n_threads = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_threads, n_chunks));
-  int dev = 0;
-  cudaGetDevice(&dev);
-  std::atomic<size_t> next{0};
-  std::atomic<int> err{0};
-  auto work = [&]() {
-    cudaSetDevice(dev);
-    for (;;) {
-      const size_t c = next.fetch_add(1);
-      if (c >= n_chunks) break;
-      const size_t off = c * chunk, sz = std::min(chunk, bytes - off);
-      std::memcpy((char*)pin + off, (const char*)h_src + off, sz);
-      if (cudaMemcpyAsync((char*)d_dst + off, (char*)pin + off, sz, cudaMemcpyHostToDevice, st) != cudaSuccess) err.store(1);
-    }
+  struct Shared {
+    std::atomic<size_t> next{0};
+    std::vector<std::atomic<unsigned char>> done;
+    explicit Shared(size_t n) : done(n) { for (auto& d : done) d.store(0, std::memory_order_relaxed); }
   };
-  if (n_threads == 1) {
-    work();
-  } else {
-    std::vector<std::thread> th;
-    for (int t = 0; t < n_threads - 1; ++t) th.emplace_back(work);
-    work();
-    for (auto& t : th) t.join();
+  auto sh = std::make_shared<Shared>(n_chunks);
+  auto copy_one = [sh, pin, h_src, bytes, chunk, n_chunks]() -> bool {
+    const size_t c = sh->next.fetch_add(1);
+    if (c >= n_chunks) return false;
+    const size_t off = c * chunk, sz = std::min(chunk, bytes - off);
+    std::memcpy((char*)pin + off, (const char*)h_src + off, sz);
+    sh->done[c].store(1, std::memory_order_release);
+    return true;
+  };
+  const int helpers = (int)std::min<size_t>((size_t)std::max(0, std::min(n_threads, WorkerPool::get().size())), n_chunks > 1 ? n_chunks - 1 : 0);
+  for (int t = 0; t < helpers; ++t)
+    WorkerPool::get().submit([copy_one] { while (copy_one()) {} });
+  bool failed = false;
+  for (size_t c = 0; c < n_chunks; ++c) {
+    while (!sh->done[c].load(std::memory_order_acquire))
+      if (!copy_one()) std::this_thread::yield();
+    const size_t off = c * chunk, sz = std::min(chunk, bytes - off);
+    if (!failed && cudaMemcpyAsync((char*)d_dst + off, (char*)pin + off, sz, cudaMemcpyHostToDevice, st) != cudaSuccess) failed = true;
   }
-  if (err.load()) { g_last_error = std::string("staged host-to-device copy: ") + cudaGetErrorString(cudaGetLastError()); return CB_E_CUDA; }
+  if (failed) { g_last_error = std::string("staged host-to-device copy: ") + cudaGetErrorString(cudaGetLastError()); return CB_E_CUDA; }
   return CB_OK;
 }
 
@@ -391,6 +441,8 @@ struct CbBaProblem {
   int loop_kernels = 0;
   // pcg launch configuration
   int pcg_cs = 1, pcg_rows = 0, pcg_mode = 0, pcg_cl = 1, pcg_npa = 0;
+  bool direct_solve = false;  // n_camera_params <= DIRECT_MAX_N: dense LDL^T in one CTA instead of the cluster PCG
+  size_t direct_smem = 0;
   size_t pcg_smem = 0;
   // rigid-distance constraints (optional)
   int n_c = 0, n_comp = 0, n_dim_max = 0, n_cblk = 0;
@@ -550,19 +602,26 @@ int choose_camera_order(CbBaProblem* p, const int* cam_order, cudaStream_t st) {
 // The image coordinates (two thirds of an upload from host memory) are only needed by the LAST index-build kernels: a
 // background thread stages them through pinned memory on a side stream while the calling thread queues the index sorts.
 struct XyUpload {
-  std::thread th;
+  bool started = false;
+  std::atomic<int> finished{0};
   cudaEvent_t ev = nullptr;
   int rc = CB_OK;
   std::string err;
-  // join the staging thread, then make `st` wait for the copies it queued
+  ScopedFree pinned;  // the staging block: released after the destructor body has waited for its DMA
+  // wait for the staging task, then make `st` wait for the copies it queued
+  void join() {
+    if (!started) return;
+    while (!finished.load(std::memory_order_acquire)) std::this_thread::yield();
+    started = false;
+  }
   int wait(cudaStream_t st) {
-    if (th.joinable()) th.join();
+    join();
     if (rc != CB_OK) { g_last_error = err; return rc; }
     if (ev) CB_CUDA(cudaStreamWaitEvent(st, ev, 0));
     return CB_OK;
   }
   ~XyUpload() {
-    if (th.joinable()) th.join();
+    join();
     if (ev) { cudaEventSynchronize(ev); cudaEventDestroy(ev); }  // the pinned staging block outlives its DMA on every path
   }
 };
@@ -710,6 +769,11 @@ PcgFn pcg_fn(int mode, int P, int cl) {
 }
 
 int launch_pcg(CbBaProblem* p, const cb::LmState* st_dev, double tol2, int max_iter, cudaStream_t st) {
+  if (p->direct_solve) {
+    CB_LAUNCH(cb::dense_ldlt_kernel, 1, cb::DIRECT_THREADS, p->direct_smem, st, st_dev, (const double*)p->d_red,
+              (const double*)(p->d_red + (size_t)p->nP * p->nP), p->nP, p->d_dc, p->d_sc);
+    return CB_OK;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(p->pcg_cs);
   cfg.blockDim = dim3(cb::PCG_THREADS);
@@ -1167,6 +1231,18 @@ int choose_pcg_config(CbBaProblem* p) {
   };
   int force_mode = -1;
   if (const char* ev = std::getenv("CB_PCG_MODE")) force_mode = std::atoi(ev);
+  // (0) small rigs: direct LDL^T in one CTA (force_mode 3, or automatically when it fits)
+  p->direct_solve = false;
+  if (nP <= cb::DIRECT_MAX_N && (force_mode < 0 || force_mode == 3)) {
+    const size_t smem = ((size_t)(nP + 1) * (nP | 1) + nP) * sizeof(double);
+    if (smem <= budget &&
+        cudaFuncSetAttribute(cb::dense_ldlt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) {
+      p->direct_solve = true;
+      p->direct_smem = smem;
+    } else {
+      cudaGetLastError();
+    }
+  }
   // (1) slab in registers: 3 rows x (32 cl) columns per warp; up to 384 reduced parameters in one portable cluster (<= 8
   //     CTAs), up to 576 (64 cameras with free intrinsics) in a 12-CTA cluster (non-portable size, allowed up to 16)
   if (nP <= 576 && (force_mode < 0 || force_mode == 2)) {
@@ -1618,6 +1694,22 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
   if (!d->obs_on_device) {
     CB_TRY(dalloc(&t_cam, n)); CB_TRY(dalloc(&t_pt, n)); CB_TRY(dalloc(&t_xy, 2 * (size_t)n));
     p->allocs.push_back(t_cam); p->allocs.push_back(t_pt); p->allocs.push_back(t_xy);  // kept: the cull path compacts them
+    // the pixel upload (two thirds of the bytes) starts first and runs beside everything up to the last index kernels
+    CB_CUDA(cudaEventCreateWithFlags(&xy_up.ev, cudaEventDisableTiming));
+    {
+      cudaStream_t side = side_stream();
+      const double* src = d->obs_xy;
+      const size_t bytes = sizeof(double) * 2 * (size_t)n;
+      const int dev = p->device;
+      xy_up.started = true;
+      WorkerPool::get().submit([&xy_up, t_xy, src, bytes, side, dev] {
+        cudaSetDevice(dev);
+        xy_up.rc = staged_h2d(t_xy, src, bytes, side, xy_up.pinned, 8);
+        if (xy_up.rc == CB_OK && cudaEventRecord(xy_up.ev, side) != cudaSuccess) xy_up.rc = CB_E_CUDA;
+        if (xy_up.rc != CB_OK) xy_up.err = "staged upload of obs_xy failed";
+        xy_up.finished.store(1, std::memory_order_release);
+      });
+    }
     if (d->obs_cam_bits == 16) {
       short* t16 = nullptr;
       CB_TRY(dalloc(&t16, n));
@@ -1628,23 +1720,6 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
       CB_TRY(staged_h2d(t_cam, d->obs_cam, sizeof(int) * (size_t)n, st, stage));
     }
     CB_TRY(staged_h2d(t_pt, d->obs_pt, sizeof(int) * (size_t)n, st, stage));
-    CB_CUDA(cudaEventCreateWithFlags(&xy_up.ev, cudaEventDisableTiming));
-    {
-      cudaStream_t side = side_stream();
-      const double* src = d->obs_xy;
-      const size_t bytes = sizeof(double) * 2 * (size_t)n;
-      const int dev = p->device;
-      xy_up.th = std::thread([&xy_up, &stage_xy = stage, t_xy, src, bytes, side, dev] {
-        cudaSetDevice(dev);
-        ScopedFree local;
-        xy_up.rc = staged_h2d(t_xy, src, bytes, side, local, 8);
-        if (xy_up.rc == CB_OK && cudaEventRecord(xy_up.ev, side) != cudaSuccess) xy_up.rc = CB_E_CUDA;
-        if (xy_up.rc != CB_OK) xy_up.err = "staged upload of obs_xy failed";
-        // hand the pinned block to the caller's scope (freed after the stream has drained)
-        for (void* q : local.host) stage_xy.host.push_back(q);
-        local.host.clear();
-      });
-    }
     d_cam = t_cam; d_pt = t_pt; d_xy = t_xy;
   } else if (d->obs_cam_bits == 16) {
     CB_TRY(dalloc(&t_cam, n));
@@ -1656,7 +1731,7 @@ static int problem_create_impl(const CbBaProblemDesc* d, int device, cudaStream_
   p->h_cam_flags.assign(d->cam_flags, d->cam_flags + p->n_cams);
   p->h_cam_const.assign(d->cam_const, d->cam_const + 9 * (size_t)p->n_cams);
   lap("alloc + staged upload");
-  CB_TRY(build_indices(p, d_cam, d_pt, d_xy, d->cam_order, st, xy_up.th.joinable() ? &xy_up : nullptr));
+  CB_TRY(build_indices(p, d_cam, d_pt, d_xy, d->cam_order, st, xy_up.started ? &xy_up : nullptr));
   // camera tables by internal slot
   {
     std::vector<int> xoff(p->n_cams);

@@ -45,7 +45,7 @@ class PointShard:
 
 def point_ranges(obs_pt: np.ndarray, n_pts: int, world_size: int) -> np.ndarray:
     """Contiguous point ranges balanced by observation count: bounds[r] .. bounds[r+1]."""
-    counts = np.bincount(np.asarray(obs_pt, dtype=np.int64), minlength=n_pts)
+    counts = np.bincount(np.asarray(obs_pt), minlength=n_pts)
     csum = np.concatenate([[0], np.cumsum(counts)])
     total = csum[-1]
     bounds = [0]
@@ -89,10 +89,24 @@ def shard_points(obs_cam, obs_pt, obs_xy, n_pts: int, rank: int, world_size: int
     split across ranks (each rank eliminates its components locally); units are dealt in order of their
     first point to the rank whose cumulative observation count they fall into."""
     obs_pt = np.asarray(obs_pt)
-    counts = np.bincount(obs_pt.astype(np.int64), minlength=n_pts)
     if constraints is None or constraints[0] is None or len(constraints[0]) == 0:
+        # contiguous ranges: membership is two comparisons per observation, the local index a subtraction (this runs inside
+        # every sharded call on every rank; the general path below costs ~25 ms on 2 M observations)
         bounds = point_ranges(obs_pt, n_pts, world_size)
-        owner = np.searchsorted(bounds[1:], np.arange(n_pts), side="right")
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        sel = np.flatnonzero((obs_pt >= lo) & (obs_pt < hi))
+        return PointShard(
+            rank=rank,
+            world_size=world_size,
+            pt_index=np.arange(lo, hi, dtype=np.int64),
+            obs_index=sel,
+            obs_cam=np.ascontiguousarray(np.asarray(obs_cam)[sel], dtype=np.int32),
+            obs_pt=np.ascontiguousarray(obs_pt[sel] - lo, dtype=np.int32),
+            obs_xy=np.ascontiguousarray(np.asarray(obs_xy, dtype=np.float64).reshape(-1, 2)[sel]),
+        )
+    counts = np.bincount(obs_pt.astype(np.int64), minlength=n_pts)
+    if False:
+        pass
     else:
         ga, gb = np.asarray(constraints[0]).reshape(-1, 4), np.asarray(constraints[1]).reshape(-1, 4)
         label = _component_labels(n_pts, ga, gb)

@@ -61,6 +61,18 @@ def solve_filter_resolve_sharded(cam_flags, cam_const, n_pts, obs_cam, obs_pt, o
     from . import distributed as D
 
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+    import os
+    import time
+
+    prof = rank == 0 and bool(os.environ.get("CB_PROFILE_PIPELINE"))
+    t_last = [time.perf_counter()]
+
+    def lap(what: str) -> None:
+        if prof:
+            now = time.perf_counter()
+            print(f"[pipeline] {what:<42s}{1e3 * (now - t_last[0]):9.3f} ms", flush=True)
+            t_last[0] = now
+
     obs_cam = np.ascontiguousarray(obs_cam, dtype=np.int32)
     obs_pt = np.ascontiguousarray(obs_pt, dtype=np.int32)
     obs_xy = np.ascontiguousarray(obs_xy, dtype=np.float64).reshape(-1, 2)
@@ -80,28 +92,43 @@ def solve_filter_resolve_sharded(cam_flags, cam_const, n_pts, obs_cam, obs_pt, o
         dist.all_reduce(acc, group=group)
         return float(np.sqrt(acc[0].item() / max(acc[1].item(), 1.0)))
 
+    lap("shard + transport")
     order = D.camera_order(obs_cam, obs_pt, len(cam_flags), n_pts, 9 if np.any(cam_flags & 1) else 6)
+    lap("camera order")
     with BAProblem(cam_flags, cam_const, shard.n_pts, shard.obs_cam, shard.obs_pt, shard.obs_xy, device=device,
                    cam_order=order) as prob:
+        lap("problem create")
         dist.barrier(group=group)
+        lap("barrier")
         s1 = prob.solve(D.local_x(np.asarray(x0, dtype=np.float64), ncp, shard), ftol=ftol, **kw)
         stages.append(s1)
+        lap("solve 1")
         rmse.append(global_rmse(prob, s1.x))
+        lap("rmse 1")
         s2 = prob.solve(s1.x, loss="soft_l1", f_scale=1.0 / f_median, ftol=1e-4, max_nfev=2000, **kw)
         stages.append(s2)
+        lap("solve 2")
         e = prob.reproj_errors_px(s2.x)
         err = np.sqrt(np.sum(e * e, axis=1))
         rmse.append(global_rmse(prob, s2.x))
+        lap("errors + rmse 2")
         thr = D.global_cull_thresholds(err, shard.obs_cam, len(cam_flags), filter_percentile, min_per_camera, group)
+        lap("global thresholds")
         prob2, keep_local = prob.cull(s2.x, thr, 0, want_mask=True)
+        lap("cull")
     with prob2:
         s3 = prob2.solve(s2.x, ftol=ftol, **kw)
         stages.append(s3)
+        lap("solve 3")
         rmse.append(global_rmse(prob2, s3.x))
+        lap("rmse 3")
     x = D.gather_points(s3.x, ncp, n_pts, shard, group)
+    lap("gather points")
     # full keep mask: every rank contributes its observations' flags at their global positions
     dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
     full = torch.zeros(len(obs_cam), dtype=torch.int32, device=dev)
     full[torch.as_tensor(shard.obs_index, device=dev)] = torch.as_tensor(keep_local.astype(np.int32), device=dev)
     dist.all_reduce(full, group=group)
-    return PipelineResult(x=x, keep=full.cpu().numpy().astype(bool), stages=stages, rmse_px=rmse)
+    keep = full.cpu().numpy().astype(bool)
+    lap("keep mask")
+    return PipelineResult(x=x, keep=keep, stages=stages, rmse_px=rmse)
