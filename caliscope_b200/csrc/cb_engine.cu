@@ -441,6 +441,7 @@ struct CbBaProblem {
   int loop_kernels = 0;
   // pcg launch configuration
   int pcg_cs = 1, pcg_rows = 0, pcg_mode = 0, pcg_cl = 1, pcg_npa = 0;
+  bool fuse_small = true;      // direct_solve: prep + solve + camera step in one kernel (CB_FUSE_SMALL=0 keeps them apart)
   bool direct_solve = false;  // n_camera_params <= DIRECT_MAX_N: dense LDL^T in one CTA instead of the cluster PCG
   size_t direct_smem = 0;
   size_t pcg_smem = 0;
@@ -813,7 +814,7 @@ int camera_pass(CbBaProblem* p, int flip, int mode, cudaStream_t st) {
 // damped system at the current point: point pass, Schur product, reduced system (+ all-reduce), head-of-iteration tests
 template <int P>
 int build_system(CbBaProblem* p, const CbBaOptions* opt, cudaStream_t st, cudaEvent_t ev_a, cudaEvent_t ev_b,
-                 cudaEvent_t ev_c = nullptr, cudaEvent_t ev_d = nullptr) {
+                 cudaEvent_t ev_c = nullptr, cudaEvent_t ev_d = nullptr, bool fuse_small = false) {
   if (ev_a) CB_CUDA(cudaEventRecord(ev_a, st));
   launch_pt_pass<P>(p, st);
   if (ev_b) CB_CUDA(cudaEventRecord(ev_b, st));
@@ -850,18 +851,25 @@ int build_system(CbBaProblem* p, const CbBaOptions* opt, cudaStream_t st, cudaEv
               p->d_red);
     if (sharded(opt)) CB_TRY(do_allreduce(opt, p->d_red, (long long)p->red_len(), st));
   }
-  CB_LAUNCH((cb::reduced_prep_kernel<P>), 1, 256, 0, st, p->d_state, p->nP, p->n_cams, p->red_slots, p->d_red, p->d_Dc2,
-            p->d_active, p->d_Minv, p->d_gmax, p->d_sc);
+  if (!(fuse_small && p->direct_solve))  // small rigs: prep runs at the head of small_rig_step_kernel (solve_step)
+    CB_LAUNCH((cb::reduced_prep_kernel<P>), 1, 256, 0, st, p->d_state, p->nP, p->n_cams, p->red_slots, p->d_red, p->d_Dc2,
+              p->d_active, p->d_Minv, p->d_gmax, p->d_sc);
   return CB_OK;
 }
 
 template <int P>
-int solve_step(CbBaProblem* p, double* dp_out, cudaStream_t st) {
-  CB_TRY(launch_pcg(p, p->d_state, 0.0, 0, st));  // tolerance and iteration cap come from the device state
+int solve_step(CbBaProblem* p, double* dp_out, cudaStream_t st, bool fuse_small = false) {
   const size_t nn = (size_t)p->nP * p->nP;
-  CB_LAUNCH(cb::cam_step_kernel, 1, 256, 0, st, (const cb::LmState*)p->d_state, p->nP, p->n_cams, p->P, p->m_xc(), p->d_dc,
-            p->d_lo, p->d_hi, p->d_red + nn + p->nP, p->d_Dc2, p->d_active, p->d_cam_flags, p->d_cam_const, p->m_camtab(),
-            p->d_sc);
+  if (fuse_small && p->direct_solve) {
+    CB_LAUNCH((cb::small_rig_step_kernel<P>), 1, cb::DIRECT_THREADS, p->direct_smem, st, p->d_state, p->nP, p->n_cams,
+              p->red_slots, p->d_red, p->d_Dc2, p->d_active, p->d_gmax, p->d_sc, p->m_xc(), p->d_dc, p->d_lo, p->d_hi,
+              p->d_cam_flags, p->d_cam_const, p->m_camtab());
+  } else {
+    CB_TRY(launch_pcg(p, p->d_state, 0.0, 0, st));  // tolerance and iteration cap come from the device state
+    CB_LAUNCH(cb::cam_step_kernel, 1, 256, 0, st, (const cb::LmState*)p->d_state, p->nP, p->n_cams, p->P, p->m_xc(), p->d_dc,
+              p->d_lo, p->d_hi, p->d_red + nn + p->nP, p->d_Dc2, p->d_active, p->d_cam_flags, p->d_cam_const, p->m_camtab(),
+              p->d_sc);
+  }
   launch_pt_backsub<P>(p, dp_out, st);
   if (p->n_c)
     CB_LAUNCH(cb::comp_backsub_kernel, p->n_comp, cb::CC_THREADS, p->comp_back_smem, st, (const cb::LmState*)p->d_state,
@@ -873,8 +881,8 @@ int solve_step(CbBaProblem* p, double* dp_out, cudaStream_t st) {
 // one whole LM trial: the same launches every time, all decisions on the device
 template <int P>
 int enqueue_trial(CbBaProblem* p, const CbBaOptions* opt, cudaStream_t st, cudaEvent_t* ev) {
-  CB_TRY(build_system<P>(p, opt, st, ev[0], ev[1], ev[2], ev[3]));
-  CB_TRY(solve_step<P>(p, nullptr, st));
+  CB_TRY(build_system<P>(p, opt, st, ev[0], ev[1], ev[2], ev[3], p->fuse_small));
+  CB_TRY(solve_step<P>(p, nullptr, st, p->fuse_small));
   const bool multi = sharded(opt);
   CB_TRY(camera_pass<P>(p, 1, multi ? 2 : 1, st));
   if (multi) {
@@ -1239,6 +1247,9 @@ int choose_pcg_config(CbBaProblem* p) {
         cudaFuncSetAttribute(cb::dense_ldlt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) {
       p->direct_solve = true;
       p->direct_smem = smem;
+      if (const char* ev = std::getenv("CB_FUSE_SMALL")) p->fuse_small = std::atoi(ev) != 0;
+      if (p->P == 6) cudaFuncSetAttribute(cb::small_rig_step_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      else cudaFuncSetAttribute(cb::small_rig_step_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     } else {
       cudaGetLastError();
     }

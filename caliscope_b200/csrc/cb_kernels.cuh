@@ -860,12 +860,9 @@ pcg_cluster_kernel(const LmState* __restrict__ st, const double* __restrict__ S,
 // ---------------------------------------------------------------------------------------------
 constexpr int DIRECT_MAX_N = 96;
 constexpr int DIRECT_THREADS = 256;
-__global__ void __launch_bounds__(DIRECT_THREADS, 1)
-dense_ldlt_kernel(const LmState* __restrict__ st, const double* __restrict__ S, const double* __restrict__ bvec, int n,
-                  double* __restrict__ xout, double* __restrict__ sc) {
-  extern __shared__ __align__(16) double dsm[];
-  __shared__ int s_flag;
-  if (st != nullptr && st->done) return;
+__device__ __forceinline__ void dense_ldlt_body(double* __restrict__ dsm, const double* __restrict__ S,
+                                                const double* __restrict__ bvec, int n, double* __restrict__ xout,
+                                                double* __restrict__ sc) {
   const int ld = n | 1;  // odd row stride: a warp touching two rows spreads over all banks
   double* A = dsm;                  // (n + 1) x ld, lower triangle used
   double* dinv = dsm + (size_t)(n + 1) * ld;
@@ -875,7 +872,6 @@ dense_ldlt_kernel(const LmState* __restrict__ st, const double* __restrict__ S, 
     if (j <= i) A[i * ld + j] = S[(size_t)i * n + j];
   }
   for (int j = tid; j < n; j += DIRECT_THREADS) A[n * ld + j] = -bvec[j];
-  if (tid == 0) s_flag = 0;
   const int tx = tid & 15, ty = tid >> 4;
   int flag = 0;
   for (int k = 0; k < n; ++k) {
@@ -925,6 +921,13 @@ dense_ldlt_kernel(const LmState* __restrict__ st, const double* __restrict__ S, 
     sc[SC_PCG_REL] = 0.0;
     sc[SC_PCG_FLAG] = (double)flag;
   }
+}
+__global__ void __launch_bounds__(DIRECT_THREADS, 1)
+dense_ldlt_kernel(const LmState* __restrict__ st, const double* __restrict__ S, const double* __restrict__ bvec, int n,
+                  double* __restrict__ xout, double* __restrict__ sc) {
+  extern __shared__ __align__(16) double dsm[];
+  if (st != nullptr && st->done) return;
+  dense_ldlt_body(dsm, S, bvec, n, xout, sc);
 }
 
 // ---------------------------------------------------------------------------------------------

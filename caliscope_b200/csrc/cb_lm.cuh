@@ -344,13 +344,12 @@ __device__ __forceinline__ void block_inverse_one(const double* __restrict__ S, 
     }
 }
 
-template <int P>
-__global__ void __launch_bounds__(256)
-reduced_prep_kernel(LmState* __restrict__ st, int nP, int n_cams, int red_slots, double* __restrict__ red,
-                    double* __restrict__ Dc2, const unsigned char* __restrict__ active, double* __restrict__ Minv,
-                    unsigned long long* __restrict__ gmax_bits, double* __restrict__ sc) {
+template <int P, bool WANT_MINV>
+__device__ __forceinline__ void reduced_prep_body(LmState* __restrict__ st, int nP, int n_cams, int red_slots,
+                                                  double* __restrict__ red, double* __restrict__ Dc2,
+                                                  const unsigned char* __restrict__ active, double* __restrict__ Minv,
+                                                  unsigned long long* __restrict__ gmax_bits, double* __restrict__ sc) {
   __shared__ double sh[32];
-  if (st->done) return;
   const size_t nn = (size_t)nP * nP;
   const double lam = st->lam;
   double gm = 0.0;
@@ -388,21 +387,29 @@ reduced_prep_kernel(LmState* __restrict__ st, int nP, int n_cams, int red_slots,
     if (done) st->done = 1;
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < n_cams; c += blockDim.x) block_inverse_one<P>(red, nP, c, Minv + (size_t)c * P * P);
+  if constexpr (WANT_MINV)
+    for (int c = threadIdx.x; c < n_cams; c += blockDim.x) block_inverse_one<P>(red, nP, c, Minv + (size_t)c * P * P);
+}
+template <int P>
+__global__ void __launch_bounds__(256)
+reduced_prep_kernel(LmState* __restrict__ st, int nP, int n_cams, int red_slots, double* __restrict__ red,
+                    double* __restrict__ Dc2, const unsigned char* __restrict__ active, double* __restrict__ Minv,
+                    unsigned long long* __restrict__ gmax_bits, double* __restrict__ sc) {
+  if (st->done) return;
+  reduced_prep_body<P, true>(st, nP, n_cams, red_slots, red, Dc2, active, Minv, gmax_bits, sc);
 }
 
 // ---------------------------------------------------------------------------------------------
 // camera step: bounds clamp, effective step back into dc, predicted reduction (camera part), then the camera
 // table of the trial point.  One CTA.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-cam_step_kernel(const LmState* __restrict__ st, int nP, int n_cams, int P, Ptr2 xc2, double* __restrict__ dc,
-                const double* __restrict__ lo, const double* __restrict__ hi, const double* __restrict__ gc_total,
-                const double* __restrict__ Dc2, const unsigned char* __restrict__ active,
-                const int* __restrict__ cam_flags, const double* __restrict__ cam_const, Ptr2 camtab2,
-                double* __restrict__ sc) {
+__device__ __forceinline__ void cam_step_body(const LmState* __restrict__ st, int nP, int n_cams, int P, Ptr2 xc2,
+                                              double* __restrict__ dc, const double* __restrict__ lo,
+                                              const double* __restrict__ hi, const double* __restrict__ gc_total,
+                                              const double* __restrict__ Dc2, const unsigned char* __restrict__ active,
+                                              const int* __restrict__ cam_flags, const double* __restrict__ cam_const,
+                                              Ptr2 camtab2, double* __restrict__ sc) {
   __shared__ double sh[3][32];
-  if (st->done) return;
   const int cur = st->cur;
   const double lam = st->lam;
   const double* xc = xc2.p[cur];
@@ -434,6 +441,35 @@ cam_step_kernel(const LmState* __restrict__ st, int nP, int n_cams, int P, Ptr2 
   }
   for (int c = threadIdx.x; c < n_cams; c += blockDim.x)
     cam_prep_one(xc_new + (size_t)c * P, cam_const + (size_t)c * 9, cam_flags[c], camtab2.p[cur ^ 1] + (size_t)c * CT_SIZE);
+}
+__global__ void __launch_bounds__(256)
+cam_step_kernel(const LmState* __restrict__ st, int nP, int n_cams, int P, Ptr2 xc2, double* __restrict__ dc,
+                const double* __restrict__ lo, const double* __restrict__ hi, const double* __restrict__ gc_total,
+                const double* __restrict__ Dc2, const unsigned char* __restrict__ active,
+                const int* __restrict__ cam_flags, const double* __restrict__ cam_const, Ptr2 camtab2,
+                double* __restrict__ sc) {
+  if (st->done) return;
+  cam_step_body(st, nP, n_cams, P, xc2, dc, lo, hi, gc_total, Dc2, active, cam_flags, cam_const, camtab2, sc);
+}
+
+// Small rigs (n_camera_params <= DIRECT_MAX_N): damping + head-of-iteration tests, the direct reduced solve and the camera
+// step in ONE single-CTA kernel -- three launches and two kernel boundaries (~3.5 us each inside a graph) become one.
+template <int P>
+__global__ void __launch_bounds__(DIRECT_THREADS, 1)
+small_rig_step_kernel(LmState* __restrict__ st, int nP, int n_cams, int red_slots, double* __restrict__ red,
+                      double* __restrict__ Dc2, const unsigned char* __restrict__ active,
+                      unsigned long long* __restrict__ gmax_bits, double* __restrict__ sc, Ptr2 xc2,
+                      double* __restrict__ dc, const double* __restrict__ lo, const double* __restrict__ hi,
+                      const int* __restrict__ cam_flags, const double* __restrict__ cam_const, Ptr2 camtab2) {
+  extern __shared__ __align__(16) double dsm[];
+  if (st->done) return;
+  reduced_prep_body<P, false>(st, nP, n_cams, red_slots, red, Dc2, active, nullptr, gmax_bits, sc);
+  __syncthreads();
+  if (st->done) return;  // set by thread 0 before the barrier: gtol / max_nfev / non-finite start (uniform)
+  const size_t nn = (size_t)nP * nP;
+  dense_ldlt_body(dsm, red, red + nn, nP, dc, sc);
+  __syncthreads();
+  cam_step_body(st, nP, n_cams, P, xc2, dc, lo, hi, red + nn + nP, Dc2, active, cam_flags, cam_const, camtab2, sc);
 }
 
 // ---------------------------------------------------------------------------------------------
