@@ -138,6 +138,8 @@ SYMBOLS = {
                               _P, C.c_int, _P]),
     "cb_stereo_rmse": (C.c_int, [C.c_int32, _P, _P, _P, C.c_int32, _P, _P, _P, C.c_int64, _P, _P, _P, C.c_int32, _P, _P, _P,
                                  C.c_int, _P]),
+    "cb_relative_pose_network": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.c_double, C.c_double, C.c_int32, _P, _P, _P, _P,
+                                           _P, _P, C.c_int64, _P, _P, _P, C.c_int, _P]),
     "cb_undistort_points": (C.c_int, [C.c_int32, _P, _P, _P, C.c_int64, _P, _P, C.c_int, C.c_int, _P, C.c_int, _P]),
     "cb_triangulate_dlt": (
         C.c_int,

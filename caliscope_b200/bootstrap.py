@@ -402,6 +402,68 @@ def filter_and_aggregate(rel: RelativePoses, threshold: float = DEFAULT_OUTLIER_
     return pairs, keep, R_agg, t_agg, cnt2.astype(np.int64)
 
 
+def pose_network_arrays(keys: np.ndarray, R: np.ndarray, t: np.ndarray, tab: CameraTables,
+                        threshold: float = DEFAULT_OUTLIER_THRESHOLD, rotation_threshold_multiplier: float | None = None,
+                        translation_threshold_multiplier: float | None = None, want_keep: bool = False, device: int = 0):  # fmt: skip
+    """``relative_pose_arrays`` + ``filter_and_aggregate`` in ONE device call (``cb_relative_pose_network``): every
+    (pair, sync, object) relative pose, the IQR rule and the quaternion / translation averages of every camera pair.
+    Returns (pairs (p, 2) ascending, R (p, 3, 3), t (p, 3), kept count (p,), keep mask over the rows ``relative_pose_arrays``
+    would return -- or None -- , stats).  The relative poses themselves never come back to the host."""
+    lib = L.load()
+    rot_m = rotation_threshold_multiplier if rotation_threshold_multiplier is not None else threshold
+    tr_m = translation_threshold_multiplier if translation_threshold_multiplier is not None else threshold
+    keys = np.asarray(keys, dtype=np.int64).reshape(-1, 3)
+    R = np.asarray(R, dtype=np.float64).reshape(-1, 3, 3)
+    t = np.asarray(t, dtype=np.float64).reshape(-1, 3)
+    empty = (np.zeros((0, 2), np.int64), np.zeros((0, 3, 3)), np.zeros((0, 3)), np.zeros(0, np.int64),
+             np.zeros(0, bool) if want_keep else None, L.TriStats())
+    if len(keys) == 0:
+        return empty
+    pos_of = np.full(int(max(tab.cam_ids.max(), keys[:, 0].max())) + 1, -1, np.int64)
+    live_ids = tab.cam_ids[~tab.ignore]
+    pos_of[live_ids] = np.flatnonzero(~tab.ignore)
+    if keys[:, 0].min() < 0:
+        raise ValueError("negative camera id")
+    idx = np.flatnonzero(pos_of[keys[:, 0]] >= 0)  # poses of cameras the array ignores (or does not know) form no pair
+    if len(idx) == 0:
+        return empty
+    k = keys[idx]
+    o = np.lexsort((k[:, 0], k[:, 2], k[:, 1]))  # (sync, object) groups, camera id ascending inside
+    k, idx = k[o], idx[o]
+    brk = np.flatnonzero((np.diff(k[:, 1]) != 0) | (np.diff(k[:, 2]) != 0)) + 1
+    frame_start = np.concatenate([[0], brk, [len(k)]]).astype(np.int32)
+    sizes = np.diff(frame_start).astype(np.int64)
+    n_rel = int((sizes * (sizes - 1) // 2).sum())
+    if n_rel == 0:
+        return empty
+    cam_id = np.ascontiguousarray(k[:, 0], dtype=np.int32)
+    cam_pos = np.ascontiguousarray(pos_of[k[:, 0]], dtype=np.int32)
+    Rg = np.ascontiguousarray(R[idx])
+    tg = np.ascontiguousarray(t[idx])
+    n_ids = len(np.unique(cam_id))
+    max_pairs = n_ids * (n_ids - 1) // 2
+    pa = np.empty(max(max_pairs, 1), np.int32)
+    pb = np.empty(max(max_pairs, 1), np.int32)
+    Ro = np.empty((max(max_pairs, 1), 3, 3))
+    to = np.empty((max(max_pairs, 1), 3))
+    cnt = np.empty(max(max_pairs, 1), np.int64)
+    n_out = C.c_int32()
+    valid = np.empty(n_rel, np.uint8) if want_keep else None
+    keep = np.empty(n_rel, np.uint8) if want_keep else None
+    st = L.TriStats()
+    L.check(
+        lib.cb_relative_pose_network(len(k), len(frame_start) - 1, _ptr(frame_start), _ptr(cam_id), _ptr(cam_pos), _ptr(Rg), _ptr(tg),
+                                     float(rot_m), float(tr_m), int(max_pairs), C.byref(n_out), _ptr(pa), _ptr(pb), _ptr(Ro), _ptr(to),
+                                     _ptr(cnt), n_rel if want_keep else 0, _ptr(valid) if want_keep else None,
+                                     _ptr(keep) if want_keep else None, C.byref(st), int(device), None),
+        "relative_pose_network",
+    )  # fmt: skip
+    n = n_out.value
+    pairs = np.stack([pa[:n], pb[:n]], axis=1).astype(np.int64)
+    keep_rows = keep[valid != 0].astype(bool) if want_keep else None
+    return pairs, Ro[:n].copy(), to[:n].copy(), cnt[:n].copy(), keep_rows, st
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # stage 3: stereo RMSE of every pair
 # ---------------------------------------------------------------------------------------------------------------------
@@ -545,6 +607,45 @@ def stereo_rmse_for_pairs(aggregated_pairs: dict, camera_array, image_points) ->
     rmse, _ = stereo_rmse_arrays(tab, pairs, R, t, df["cam_id"].to_numpy(), df["sync_index"].to_numpy(), df["object_id"].to_numpy(),
                                  df["keypoint_id"].to_numpy(), df[["img_loc_x", "img_loc_y"]].to_numpy(np.float64))  # fmt: skip
     return {tuple(int(v) for v in p): (None if np.isnan(r) else float(r)) for p, r in zip(pairs, rmse)}
+
+
+def build_paired_pose_network(image_points, camera_array, min_points: int = DEFAULT_MIN_PNP_POINTS,
+                              threshold: float = DEFAULT_OUTLIER_THRESHOLD):
+    """Drop-in for ``caliscope.core.bootstrap_pose.build_paired_pose_network.build_paired_pose_network`` (:14-31): the PnP
+    branch -- ``PoseNetworkBuilder(...).estimate_camera_to_object_poses().estimate_relative_poses().filter_outliers(1.5)
+    .build()`` -- as three device calls on arrays (PnP of every group, relative-pose network, stereo RMSE of every pair) with
+    no per-pose Python objects in between; only the <= n_cams^2 aggregated pairs become ``StereoPair`` objects for the
+    reference's own ``PairedPoseNetwork.from_raw_estimates`` (gap filling: graph bookkeeping, stays the reference's).  With
+    2D-only observations (obj_loc all NaN) the reference's epipolar bootstrap, which this package does not replace, is called."""
+    from caliscope.core.bootstrap_pose.paired_pose_network import PairedPoseNetwork
+
+    df = image_points.df
+    obj = df[["obj_loc_x", "obj_loc_y", "obj_loc_z"]].to_numpy(np.float64)
+    if np.isnan(obj).all():
+        from caliscope.core.bootstrap_pose.epipolar_pose_builder import build_epipolar_pose_network
+
+        return build_epipolar_pose_network(image_points, camera_array)
+    SP = _stereo_pair_cls()
+    tab = camera_tables(camera_array)
+    cam_id, sync, oid, kp = (df[c].to_numpy() for c in ("cam_id", "sync_index", "object_id", "keypoint_id"))
+    xy = df[["img_loc_x", "img_loc_y"]].to_numpy(np.float64)
+    res = pnp_arrays(tab, cam_id, sync, oid, xy, obj, min_points)
+    if np.any(res.status == PNP_NON_PLANAR):
+        raise NotImplementedError("non-planar PnP group (obj_loc_z spread): the reference uses SOLVEPNP_SQPNP there, "
+                                  "which caliscope_b200 does not implement")  # fmt: skip
+    live = res.status != PNP_TOO_FEW
+    pairs, R, t, _cnt, _, _ = pose_network_arrays(res.keys[live], res.R[live], res.t[live], tab, threshold)
+    rmse, _ = stereo_rmse_arrays(tab, pairs, R, t, cam_id, sync, oid, kp, xy)
+    # the reference's dict order: combinations of the cameras in dict order
+    order = np.lexsort(([tab.index_of[int(b)] for b in pairs[:, 1]], [tab.index_of[int(a)] for a in pairs[:, 0]])) if len(pairs) else []
+    with_rmse = {}
+    for i in order:
+        if np.isnan(rmse[i]):
+            continue
+        a, b = int(pairs[i, 0]), int(pairs[i, 1])
+        with_rmse[(a, b)] = SP(primary_cam_id=a, secondary_cam_id=b, error_score=float(rmse[i]), rotation=R[i].copy(),
+                               translation=t[i].copy())  # fmt: skip
+    return PairedPoseNetwork.from_raw_estimates(with_rmse)
 
 
 def estimate_pnp_paired_pose_network(aggregated_pairs_wo_rmse: dict, camera_array, image_points):

@@ -504,4 +504,264 @@ stereo_pairs_kernel(const int* __restrict__ start, const int* __restrict__ rows,
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Relative-pose network (pose_network_builder.py): compute_relative_poses (:486-560) -> reject_outliers (:340-412) ->
+// aggregate_poses (:520-560, quaternion_average :414-437) for EVERY camera pair in one pass over device arrays.
+//   rel_pose_kernel       one thread per (frame group, camera a, camera b) combination: T_B_A = T_B_obj inv(T_A_obj),
+//                         unit quaternion (Shepperd), |t|, sort key = a * span + b
+//   (radix sort by pair, run-length encode -> one segment per camera pair, segmented sorts for the quartiles)
+//   quat_average_kernel   block per pair: sum of q q^T over (masked) rows, largest eigenvector (Jacobi), sum of t, row count
+//   rel_angle_kernel      angle between each sample and its pair's mean rotation
+//   seg_quartile_kernel   np.percentile(.., [25, 75]) of a sorted segment, NumPy's 'linear' rule and its lerp
+//   rel_flag_kernel       the IQR rule (pairs with >= 5 samples)
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int REL_THREADS = 128;
+
+__device__ __forceinline__ void quat_from_matrix(const double* r, double* q) {
+  const double m00 = r[0], m11 = r[4], m22 = r[8];
+  const double tr = m00 + m11 + m22;
+  int c = 0;
+  double best = tr;
+  if (m00 > best) { best = m00; c = 1; }
+  if (m11 > best) { best = m11; c = 2; }
+  if (m22 > best) { best = m22; c = 3; }
+  if (c == 0) {
+    const double w = sqrt(fmax(1.0 + m00 + m11 + m22, 0.0)) / 2.0;
+    q[0] = w; q[1] = (r[7] - r[5]) / (4.0 * w); q[2] = (r[2] - r[6]) / (4.0 * w); q[3] = (r[3] - r[1]) / (4.0 * w);
+  } else if (c == 1) {
+    const double x = sqrt(fmax(1.0 + m00 - m11 - m22, 0.0)) / 2.0;
+    q[0] = (r[7] - r[5]) / (4.0 * x); q[1] = x; q[2] = (r[1] + r[3]) / (4.0 * x); q[3] = (r[2] + r[6]) / (4.0 * x);
+  } else if (c == 2) {
+    const double y = sqrt(fmax(1.0 - m00 + m11 - m22, 0.0)) / 2.0;
+    q[0] = (r[2] - r[6]) / (4.0 * y); q[1] = (r[1] + r[3]) / (4.0 * y); q[2] = y; q[3] = (r[5] + r[7]) / (4.0 * y);
+  } else {
+    const double z = sqrt(fmax(1.0 - m00 - m11 + m22, 0.0)) / 2.0;
+    q[0] = (r[3] - r[1]) / (4.0 * z); q[1] = (r[2] + r[6]) / (4.0 * z); q[2] = (r[5] + r[7]) / (4.0 * z); q[3] = z;
+  }
+  const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
+}
+
+__device__ __forceinline__ void quat_to_matrix(const double* qin, double* R) {
+  const double n = sqrt(qin[0] * qin[0] + qin[1] * qin[1] + qin[2] * qin[2] + qin[3] * qin[3]);
+  const double w = qin[0] / n, x = qin[1] / n, y = qin[2] / n, z = qin[3] / n;
+  R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * w); R[2] = 2 * (x * z + y * w);
+  R[3] = 2 * (x * y + z * w); R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * w);
+  R[6] = 2 * (x * z - y * w); R[7] = 2 * (y * z + x * w); R[8] = 1 - 2 * (x * x + y * y);
+}
+
+// frame groups: rows frame_start[f] .. frame_start[f+1] of the (sync, object, camera id)-sorted PnP poses; pair_off[f] =
+// number of combinations in earlier groups.  Combination m of group f is the l-th entry of np.triu_indices(s, 1).
+__global__ void rel_pose_kernel(const long long* __restrict__ pair_off, const int* __restrict__ frame_start, int n_frames,
+                                long long M, const int* __restrict__ cam_id, const int* __restrict__ cam_pos,
+                                const double* __restrict__ R, const double* __restrict__ t, unsigned span,
+                                unsigned* __restrict__ key, unsigned* __restrict__ idx, double* __restrict__ Rr,
+                                double* __restrict__ tr, double* __restrict__ q, double* __restrict__ tmag,
+                                unsigned char* __restrict__ valid_out) {
+  const long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  int lo = 0, hi = n_frames;  // largest f with pair_off[f] <= m
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (pair_off[mid] <= m) lo = mid; else hi = mid;
+  }
+  const int f = lo, b0 = frame_start[f], n = frame_start[f + 1] - b0;
+  const long long k = m - pair_off[f];
+  int i = (int)((2.0 * n - 1.0 - sqrt((2.0 * n - 1.0) * (2.0 * n - 1.0) - 8.0 * (double)k)) * 0.5);
+  if (i < 0) i = 0;
+  while ((long long)i * (2 * n - i - 1) / 2 > k) --i;
+  while ((long long)(i + 1) * (2 * n - i - 2) / 2 <= k) ++i;
+  const int j = (int)(k - (long long)i * (2 * n - i - 1) / 2) + i + 1;
+  const int ga = b0 + i, gb = b0 + j;
+  idx[m] = (unsigned)m;
+  const unsigned invalid = span * span;
+  const bool formed = cam_pos[ga] < cam_pos[gb];  // the reference forms (first, second) in dict order and keeps first < second
+  if (valid_out) valid_out[m] = formed ? 1 : 0;
+  if (!formed) { key[m] = invalid; return; }
+  const double* Ra = R + 9 * (size_t)ga;
+  const double* Rb = R + 9 * (size_t)gb;
+  const double* ta = t + 3 * (size_t)ga;
+  const double* tb = t + 3 * (size_t)gb;
+  double rr[9], tt[3], tai[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) rr[3 * a + c] = Rb[3 * a] * Ra[3 * c] + Rb[3 * a + 1] * Ra[3 * c + 1] + Rb[3 * a + 2] * Ra[3 * c + 2];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) tai[c] = -(Ra[c] * ta[0] + Ra[3 + c] * ta[1] + Ra[6 + c] * ta[2]);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) tt[a] = Rb[3 * a] * tai[0] + Rb[3 * a + 1] * tai[1] + Rb[3 * a + 2] * tai[2] + tb[a];
+  bool fin = true;
+#pragma unroll
+  for (int a = 0; a < 9; ++a) fin = fin && isfinite(rr[a]);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) fin = fin && isfinite(tt[a]);
+  if (!fin) { key[m] = invalid; return; }  // the reference's NaN filter (:364-367)
+  key[m] = (unsigned)cam_id[ga] * span + (unsigned)cam_id[gb];
+  double qq[4];
+  quat_from_matrix(rr, qq);
+#pragma unroll
+  for (int a = 0; a < 9; ++a) Rr[9 * (size_t)m + a] = rr[a];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) tr[3 * (size_t)m + a] = tt[a];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) q[4 * (size_t)m + a] = qq[a];
+  tmag[m] = sqrt(tt[0] * tt[0] + tt[1] * tt[1] + tt[2] * tt[2]);
+}
+
+// rows into pair-sorted order (perm = values of the radix sort), plus the segment id of each sorted row
+__global__ void rel_gather_kernel(const unsigned* __restrict__ perm, long long Mv, const double* __restrict__ Rr,
+                                  const double* __restrict__ tr, const double* __restrict__ q,
+                                  const double* __restrict__ tmag, double* __restrict__ Rs, double* __restrict__ ts,
+                                  double* __restrict__ qs, double* __restrict__ tmag_s) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= Mv) return;
+  const size_t m = perm[i];
+#pragma unroll
+  for (int a = 0; a < 9; ++a) Rs[9 * (size_t)i + a] = Rr[9 * m + a];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) ts[3 * (size_t)i + a] = tr[3 * m + a];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) qs[4 * (size_t)i + a] = q[4 * m + a];
+  tmag_s[i] = tmag[m];
+}
+__global__ void seg_fill_kernel(const int* __restrict__ seg_off, int n_seg, int* __restrict__ seg) {
+  const int s = blockIdx.x;
+  if (s >= n_seg) return;
+  for (int i = seg_off[s] + threadIdx.x; i < seg_off[s + 1]; i += blockDim.x) seg[i] = s;
+}
+
+// numpy.percentile(v, [25, 75]) of every sorted segment ('linear' method, numpy's _lerp)
+__device__ __forceinline__ double np_percentile_sorted(const double* v, int cnt, double q01) {
+  const double vi = (double)(cnt - 1) * q01;
+  const double fl = floor(fmax(vi, 0.0));
+  const int lo = (int)fl;
+  const int hi = min(lo + 1, max(cnt - 1, 0));
+  const double a = v[lo], b = v[hi], tt = vi - floor(vi);
+  const double d = __dsub_rn(b, a);
+  if (d == 0.0) return a;
+  if (tt >= 0.5) return __dsub_rn(b, __dmul_rn(d, __dsub_rn(1.0, tt)));
+  return __dadd_rn(a, __dmul_rn(d, tt));
+}
+__global__ void seg_quartile_kernel(const double* __restrict__ sorted, const int* __restrict__ seg_off, int n_seg,
+                                    double* __restrict__ q1, double* __restrict__ q3) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_seg) return;
+  const int b = seg_off[s], cnt = seg_off[s + 1] - b;
+  if (cnt <= 0) { q1[s] = 0.0; q3[s] = 0.0; return; }
+  q1[s] = np_percentile_sorted(sorted + b, cnt, 25.0 / 100.0);
+  q3[s] = np_percentile_sorted(sorted + b, cnt, 75.0 / 100.0);
+}
+
+// block per camera pair: eigenvector of sum q q^T (largest eigenvalue, w >= 0) over the rows with mask != 0 (all rows when
+// mask == nullptr), sum of t, row count, first such row.  Outputs the mean rotation as a matrix; a single row is passed
+// through untouched (the reference returns the lone sample itself, :551-553).
+__global__ void __launch_bounds__(REL_THREADS)
+quat_average_kernel(const int* __restrict__ seg_off, int n_seg, const double* __restrict__ qs,
+                    const double* __restrict__ ts, const double* __restrict__ Rs, const unsigned char* __restrict__ mask,
+                    double* __restrict__ R_out, double* __restrict__ t_out, long long* __restrict__ cnt_out) {
+  __shared__ double sh[REL_THREADS / 32][14];
+  __shared__ int sh_first[REL_THREADS / 32];
+  const int s = blockIdx.x;
+  if (s >= n_seg) return;
+  const int b = seg_off[s], e = seg_off[s + 1];
+  double acc[14];
+#pragma unroll
+  for (int k = 0; k < 14; ++k) acc[k] = 0.0;
+  int first = 0x7fffffff;
+  for (int i = b + threadIdx.x; i < e; i += REL_THREADS) {
+    if (mask && !mask[i]) continue;
+    const double q0 = qs[4 * (size_t)i], q1 = qs[4 * (size_t)i + 1], q2 = qs[4 * (size_t)i + 2], q3 = qs[4 * (size_t)i + 3];
+    acc[0] += q0 * q0; acc[1] += q0 * q1; acc[2] += q0 * q2; acc[3] += q0 * q3;
+    acc[4] += q1 * q1; acc[5] += q1 * q2; acc[6] += q1 * q3;
+    acc[7] += q2 * q2; acc[8] += q2 * q3; acc[9] += q3 * q3;
+    acc[10] += ts[3 * (size_t)i]; acc[11] += ts[3 * (size_t)i + 1]; acc[12] += ts[3 * (size_t)i + 2];
+    acc[13] += 1.0;
+    first = min(first, i);
+  }
+#pragma unroll
+  for (int k = 0; k < 14; ++k)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 14; ++k) sh[wid][k] = acc[k];
+    sh_first[wid] = first;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+#pragma unroll
+  for (int k = 0; k < 14; ++k) {
+    double v = 0.0;
+    for (int w = 0; w < REL_THREADS / 32; ++w) v += sh[w][k];
+    acc[k] = v;
+  }
+  for (int w = 0; w < REL_THREADS / 32; ++w) first = min(first, sh_first[w]);
+  const long long cnt = (long long)(acc[13] + 0.5);
+  cnt_out[s] = cnt;
+  double* Ro = R_out + 9 * (size_t)s;
+  double* to = t_out + 3 * (size_t)s;
+  if (cnt == 0) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Ro[k] = 0.0;
+    to[0] = to[1] = to[2] = 0.0;
+    return;
+  }
+  if (cnt == 1) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Ro[k] = Rs[9 * (size_t)first + k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) to[k] = ts[3 * (size_t)first + k];
+    return;
+  }
+  double A[4][4];  // -sum q q^T: its smallest eigenvalue is the largest of the sum
+  A[0][0] = -acc[0]; A[0][1] = A[1][0] = -acc[1]; A[0][2] = A[2][0] = -acc[2]; A[0][3] = A[3][0] = -acc[3];
+  A[1][1] = -acc[4]; A[1][2] = A[2][1] = -acc[5]; A[1][3] = A[3][1] = -acc[6];
+  A[2][2] = -acc[7]; A[2][3] = A[3][2] = -acc[8]; A[3][3] = -acc[9];
+  double q[4];
+  sym4_min_eigvec(A, q);
+  if (q[0] < 0.0) { q[0] = -q[0]; q[1] = -q[1]; q[2] = -q[2]; q[3] = -q[3]; }
+  quat_to_matrix(q, Ro);
+  const double c = (double)cnt;
+  to[0] = acc[10] / c; to[1] = acc[11] / c; to[2] = acc[12] / c;
+}
+
+// angle (degrees) between each sample and the mean rotation of its pair: acos((trace(R Rm^T) - 1) / 2), trace clipped to [-1, 3]
+__global__ void rel_angle_kernel(const double* __restrict__ Rs, const int* __restrict__ seg, const double* __restrict__ Rm,
+                                 long long Mv, double* __restrict__ ang) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= Mv) return;
+  const double* r = Rs + 9 * (size_t)i;
+  const double* m = Rm + 9 * (size_t)seg[i];
+  double tr = 0.0;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) tr += r[k] * m[k];
+  tr = fmin(fmax(tr, -1.0), 3.0);
+  ang[i] = acos((tr - 1.0) / 2.0) * (180.0 / 3.14159265358979323846);
+}
+
+// IQR rule (reject_outliers :369-400): applied to pairs with at least 5 samples; comparisons with NaN are false (kept), as in NumPy
+__global__ void rel_flag_kernel(const int* __restrict__ seg, const int* __restrict__ seg_off, long long Mv,
+                                const double* __restrict__ tmag, const double* __restrict__ ang,
+                                const double* __restrict__ tq1, const double* __restrict__ tq3,
+                                const double* __restrict__ rq1, const double* __restrict__ rq3, double rot_m, double tr_m,
+                                const unsigned* __restrict__ perm, unsigned char* __restrict__ ok,
+                                unsigned char* __restrict__ keep_out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= Mv) return;
+  const int s = seg[i];
+  const bool big = seg_off[s + 1] - seg_off[s] >= 5;
+  const double ti = __dsub_rn(tq3[s], tq1[s]), ri = __dsub_rn(rq3[s], rq1[s]);
+  const double t_lo = __dsub_rn(tq1[s], __dmul_rn(tr_m, ti)), t_hi = __dadd_rn(tq3[s], __dmul_rn(tr_m, ti));
+  const double r_hi = __dadd_rn(rq3[s], __dmul_rn(rot_m, ri));
+  const bool bad = (tmag[i] < t_lo) || (tmag[i] > t_hi) || (ang[i] > r_hi);
+  const unsigned char k = (bad && big) ? 0 : 1;
+  ok[i] = k;
+  if (keep_out) keep_out[perm[i]] = k;
+}
+
 }  // namespace cb

@@ -2981,6 +2981,194 @@ int cb_stereo_rmse(int32_t n_cams, const int32_t* cam_fisheye, const double* cam
   return CB_OK;
 }
 
+int cb_relative_pose_network(int32_t n_groups, int32_t n_frames, const int32_t* frame_start, const int32_t* cam_id,
+                             const int32_t* cam_pos, const double* R, const double* t, double rot_mult, double tr_mult,
+                             int32_t max_pairs, int32_t* n_pairs_out, int32_t* pair_a, int32_t* pair_b, double* R_out,
+                             double* t_out, int64_t* count_out, int64_t n_rel, uint8_t* rel_valid, uint8_t* rel_keep,
+                             CbTriStats* stats, int device, void* stream) {
+  if (n_groups < 0 || n_frames < 0 || !n_pairs_out || max_pairs < 0 ||
+      (n_groups > 0 && (!frame_start || !cam_id || !cam_pos || !R || !t)) ||
+      (max_pairs > 0 && (!pair_a || !pair_b || !R_out || !t_out || !count_out))) {
+    g_last_error = "cb_relative_pose_network: bad argument";
+    return CB_E_INVALID;
+  }
+  *n_pairs_out = 0;
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+  // combinations per frame group (host: n_frames + 1 integers)
+  std::vector<long long> pair_off((size_t)n_frames + 1, 0);
+  int max_id = 0;
+  for (int f = 0; f < n_frames; ++f) {
+    const long long sz = (long long)frame_start[f + 1] - frame_start[f];
+    if (sz < 0 || frame_start[f] < 0 || frame_start[f + 1] > n_groups) {
+      g_last_error = "cb_relative_pose_network: frame_start must be non-decreasing within [0, n_groups]";
+      return CB_E_INVALID;
+    }
+    pair_off[(size_t)f + 1] = pair_off[(size_t)f] + sz * (sz - 1) / 2;
+  }
+  for (int g = 0; g < n_groups; ++g) {
+    if (cam_id[g] < 0) { g_last_error = "cb_relative_pose_network: negative camera id"; return CB_E_INVALID; }
+    max_id = std::max(max_id, cam_id[g]);
+  }
+  const long long M = pair_off[(size_t)n_frames];
+  if ((rel_valid || rel_keep) && n_rel != M) {
+    g_last_error = "cb_relative_pose_network: n_rel must equal the number of combinations, " + std::to_string(M);
+    return CB_E_INVALID;
+  }
+  if (M == 0) return CB_OK;
+  if (M > 0x7fffffffLL) { g_last_error = "cb_relative_pose_network: more than 2^31 relative poses"; return CB_E_UNSUPPORTED; }
+  const unsigned span = (unsigned)max_id + 1u;
+  if ((unsigned long long)span * span >= 0xffffffffull) { g_last_error = "cb_relative_pose_network: camera ids too large"; return CB_E_UNSUPPORTED; }
+  CB_TRY(select_device(device));
+  const long long launches0 = g_launches.load();
+  cudaStream_t st = (cudaStream_t)stream;
+  ScopedFree sf;
+  cudaEvent_t ev[3];
+  for (auto& e : ev) CB_CUDA(cudaEventCreate(&e));
+  struct EvGuard { cudaEvent_t* e; ~EvGuard() { for (int i = 0; i < 3; ++i) cudaEventDestroy(e[i]); } } evg{ev};
+  CB_CUDA(cudaEventRecord(ev[0], st));
+  const long long* d_pair_off = nullptr;
+  const int *d_fs = nullptr, *d_id = nullptr, *d_pos = nullptr;
+  const double *d_R = nullptr, *d_t = nullptr;
+  CB_TRY(to_device(pair_off.data(), pair_off.size(), 0, &d_pair_off, sf, st));
+  CB_TRY(to_device(frame_start, (size_t)n_frames + 1, 0, &d_fs, sf, st));
+  CB_TRY(to_device(cam_id, (size_t)n_groups, 0, &d_id, sf, st));
+  CB_TRY(to_device(cam_pos, (size_t)n_groups, 0, &d_pos, sf, st));
+  CB_TRY(to_device(R, 9 * (size_t)n_groups, 0, &d_R, sf, st));
+  CB_TRY(to_device(t, 3 * (size_t)n_groups, 0, &d_t, sf, st));
+  const size_t m = (size_t)M;
+  unsigned *d_key = nullptr, *d_idx = nullptr, *d_key_s = nullptr, *d_perm = nullptr;
+  double *d_Rr = nullptr, *d_tr = nullptr, *d_q = nullptr, *d_tm = nullptr;
+  unsigned char *d_valid = nullptr, *d_keep = nullptr;
+  CB_TRY(dalloc(&d_key, m)); sf.dev.push_back(d_key);
+  CB_TRY(dalloc(&d_idx, m)); sf.dev.push_back(d_idx);
+  CB_TRY(dalloc(&d_key_s, m)); sf.dev.push_back(d_key_s);
+  CB_TRY(dalloc(&d_perm, m)); sf.dev.push_back(d_perm);
+  CB_TRY(dalloc(&d_Rr, 9 * m)); sf.dev.push_back(d_Rr);
+  CB_TRY(dalloc(&d_tr, 3 * m)); sf.dev.push_back(d_tr);
+  CB_TRY(dalloc(&d_q, 4 * m)); sf.dev.push_back(d_q);
+  CB_TRY(dalloc(&d_tm, m)); sf.dev.push_back(d_tm);
+  if (rel_valid) { CB_TRY(dalloc(&d_valid, m)); sf.dev.push_back(d_valid); }
+  if (rel_keep) {
+    CB_TRY(dalloc(&d_keep, m)); sf.dev.push_back(d_keep);
+    CB_CUDA(cudaMemsetAsync(d_keep, 0, m, st));
+  }
+  CB_LAUNCH(cb::rel_pose_kernel, cdiv(M, 256), 256, 0, st, d_pair_off, d_fs, (int)n_frames, M, d_id, d_pos, d_R, d_t, span,
+            d_key, d_idx, d_Rr, d_tr, d_q, d_tm, d_valid);
+  // stable sort by pair key; rows that were not formed / are not finite carry key span^2 and end up last
+  const int kbits = bits_for((unsigned long long)span * span + 1ull);
+  const int max_runs = (int)std::min<long long>(M, (long long)span * (span - 1) / 2 + 1) + 1;
+  unsigned* d_uk = nullptr;
+  int *d_len = nullptr, *d_nruns = nullptr;
+  CB_TRY(dalloc(&d_uk, (size_t)max_runs)); sf.dev.push_back(d_uk);
+  CB_TRY(dalloc(&d_len, (size_t)max_runs)); sf.dev.push_back(d_len);
+  CB_TRY(dalloc(&d_nruns, 1)); sf.dev.push_back(d_nruns);
+  size_t tb1 = 0, tb2 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb1, d_key, d_key_s, d_idx, d_perm, (int)M, 0, kbits, st);
+  cub::DeviceRunLengthEncode::Encode(nullptr, tb2, d_key_s, d_uk, d_len, d_nruns, (int)M, st);
+  void* d_tmp = nullptr;
+  size_t tb = std::max(tb1, tb2);
+  CB_TRY(cached_malloc(&d_tmp, std::max<size_t>(tb, 16))); sf.dev.push_back(d_tmp);
+  CB_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb, d_key, d_key_s, d_idx, d_perm, (int)M, 0, kbits, st));
+  tb = std::max(tb1, tb2);
+  CB_CUDA(cub::DeviceRunLengthEncode::Encode(d_tmp, tb, d_key_s, d_uk, d_len, d_nruns, (int)M, st));
+  g_launches.fetch_add(6);
+  int nruns = 0;
+  CB_CUDA(cudaMemcpyAsync(&nruns, d_nruns, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  std::vector<unsigned> uk((size_t)std::max(nruns, 1));
+  std::vector<int> len((size_t)std::max(nruns, 1));
+  CB_CUDA(cudaMemcpyAsync(uk.data(), d_uk, sizeof(unsigned) * (size_t)nruns, cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaMemcpyAsync(len.data(), d_len, sizeof(int) * (size_t)nruns, cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  int n_seg = nruns;
+  if (n_seg > 0 && uk[(size_t)n_seg - 1] == span * span) --n_seg;  // the run of unformed / non-finite rows
+  if (rel_valid) CB_CUDA(cudaMemcpyAsync(rel_valid, d_valid, m, cudaMemcpyDeviceToHost, st));
+  if (n_seg == 0) {
+    if (rel_keep) std::memset(rel_keep, 0, m);
+    CB_CUDA(cudaStreamSynchronize(st));
+    return CB_OK;
+  }
+  if (n_seg > max_pairs) {
+    g_last_error = "cb_relative_pose_network: " + std::to_string(n_seg) + " camera pairs, max_pairs is " + std::to_string(max_pairs);
+    return CB_E_INVALID;
+  }
+  std::vector<int> seg_off((size_t)n_seg + 1, 0);
+  for (int s2 = 0; s2 < n_seg; ++s2) seg_off[(size_t)s2 + 1] = seg_off[(size_t)s2] + len[(size_t)s2];
+  const long long Mv = seg_off[(size_t)n_seg];
+  const int* d_off = nullptr;
+  CB_TRY(to_device(seg_off.data(), seg_off.size(), 0, &d_off, sf, st));
+  const size_t mv = (size_t)Mv;
+  double *d_Rs = nullptr, *d_ts = nullptr, *d_qs = nullptr, *d_tms = nullptr, *d_sorted = nullptr, *d_ang = nullptr;
+  int* d_seg = nullptr;
+  unsigned char* d_ok = nullptr;
+  CB_TRY(dalloc(&d_Rs, 9 * mv)); sf.dev.push_back(d_Rs);
+  CB_TRY(dalloc(&d_ts, 3 * mv)); sf.dev.push_back(d_ts);
+  CB_TRY(dalloc(&d_qs, 4 * mv)); sf.dev.push_back(d_qs);
+  CB_TRY(dalloc(&d_tms, mv)); sf.dev.push_back(d_tms);
+  CB_TRY(dalloc(&d_sorted, mv)); sf.dev.push_back(d_sorted);
+  CB_TRY(dalloc(&d_ang, mv)); sf.dev.push_back(d_ang);
+  CB_TRY(dalloc(&d_seg, mv)); sf.dev.push_back(d_seg);
+  CB_TRY(dalloc(&d_ok, mv)); sf.dev.push_back(d_ok);
+  double *d_Rm = nullptr, *d_tmn = nullptr, *d_q13 = nullptr;
+  long long* d_cnt = nullptr;
+  CB_TRY(dalloc(&d_Rm, 9 * (size_t)n_seg)); sf.dev.push_back(d_Rm);
+  CB_TRY(dalloc(&d_tmn, 3 * (size_t)n_seg)); sf.dev.push_back(d_tmn);
+  CB_TRY(dalloc(&d_q13, 4 * (size_t)n_seg)); sf.dev.push_back(d_q13);
+  CB_TRY(dalloc(&d_cnt, (size_t)n_seg)); sf.dev.push_back(d_cnt);
+  CB_LAUNCH(cb::rel_gather_kernel, cdiv(Mv, 256), 256, 0, st, (const unsigned*)d_perm, Mv, (const double*)d_Rr,
+            (const double*)d_tr, (const double*)d_q, (const double*)d_tm, d_Rs, d_ts, d_qs, d_tms);
+  CB_LAUNCH(cb::seg_fill_kernel, n_seg, 128, 0, st, d_off, n_seg, d_seg);
+  CB_CUDA(cudaEventRecord(ev[1], st));
+  // quartiles of |t| per pair
+  size_t tb3 = 0;
+  cub::DeviceSegmentedSort::SortKeys(nullptr, tb3, (const double*)d_tms, d_sorted, (int)Mv, n_seg, d_off, d_off + 1, st);
+  void* d_tmp2 = nullptr;
+  CB_TRY(cached_malloc(&d_tmp2, std::max<size_t>(tb3, 16))); sf.dev.push_back(d_tmp2);
+  CB_CUDA(cub::DeviceSegmentedSort::SortKeys(d_tmp2, tb3, (const double*)d_tms, d_sorted, (int)Mv, n_seg, d_off, d_off + 1, st));
+  CB_LAUNCH(cb::seg_quartile_kernel, cdiv(n_seg, 128), 128, 0, st, (const double*)d_sorted, d_off, n_seg, d_q13, d_q13 + n_seg);
+  // mean rotation per pair, angle of every sample to it, quartiles of the angle
+  CB_LAUNCH(cb::quat_average_kernel, n_seg, cb::REL_THREADS, 0, st, d_off, n_seg, (const double*)d_qs, (const double*)d_ts,
+            (const double*)d_Rs, (const unsigned char*)nullptr, d_Rm, d_tmn, d_cnt);
+  CB_LAUNCH(cb::rel_angle_kernel, cdiv(Mv, 256), 256, 0, st, (const double*)d_Rs, (const int*)d_seg, (const double*)d_Rm, Mv, d_ang);
+  CB_CUDA(cub::DeviceSegmentedSort::SortKeys(d_tmp2, tb3, (const double*)d_ang, d_sorted, (int)Mv, n_seg, d_off, d_off + 1, st));
+  CB_LAUNCH(cb::seg_quartile_kernel, cdiv(n_seg, 128), 128, 0, st, (const double*)d_sorted, d_off, n_seg, d_q13 + 2 * (size_t)n_seg,
+            d_q13 + 3 * (size_t)n_seg);
+  g_launches.fetch_add(4);
+  CB_LAUNCH(cb::rel_flag_kernel, cdiv(Mv, 256), 256, 0, st, (const int*)d_seg, d_off, Mv, (const double*)d_tms,
+            (const double*)d_ang, (const double*)d_q13, (const double*)(d_q13 + n_seg), (const double*)(d_q13 + 2 * (size_t)n_seg),
+            (const double*)(d_q13 + 3 * (size_t)n_seg), rot_mult, tr_mult, (const unsigned*)d_perm, d_ok, d_keep);
+  // aggregate the survivors
+  CB_LAUNCH(cb::quat_average_kernel, n_seg, cb::REL_THREADS, 0, st, d_off, n_seg, (const double*)d_qs, (const double*)d_ts,
+            (const double*)d_Rs, (const unsigned char*)d_ok, d_Rm, d_tmn, d_cnt);
+  CB_CUDA(cudaEventRecord(ev[2], st));
+  std::vector<double> hR(9 * (size_t)n_seg), ht(3 * (size_t)n_seg);
+  std::vector<long long> hc((size_t)n_seg);
+  CB_CUDA(cudaMemcpyAsync(hR.data(), d_Rm, sizeof(double) * hR.size(), cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaMemcpyAsync(ht.data(), d_tmn, sizeof(double) * ht.size(), cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaMemcpyAsync(hc.data(), d_cnt, sizeof(long long) * hc.size(), cudaMemcpyDeviceToHost, st));
+  if (rel_keep) CB_CUDA(cudaMemcpyAsync(rel_keep, d_keep, m, cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  int np = 0;
+  for (int s2 = 0; s2 < n_seg; ++s2) {
+    if (hc[(size_t)s2] <= 0) continue;  // every sample rejected
+    pair_a[np] = (int32_t)(uk[(size_t)s2] / span);
+    pair_b[np] = (int32_t)(uk[(size_t)s2] % span);
+    std::memcpy(R_out + 9 * (size_t)np, &hR[9 * (size_t)s2], 9 * sizeof(double));
+    std::memcpy(t_out + 3 * (size_t)np, &ht[3 * (size_t)s2], 3 * sizeof(double));
+    count_out[np] = hc[(size_t)s2];
+    ++np;
+  }
+  *n_pairs_out = np;
+  if (stats) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev[0], ev[1]); stats->group_ms = ms;
+    cudaEventElapsedTime(&ms, ev[1], ev[2]); stats->dlt_ms = ms;
+    cudaEventElapsedTime(&ms, ev[0], ev[2]); stats->total_ms = ms;
+    stats->kernel_launches = (int)(g_launches.load() - launches0);
+  }
+  return CB_OK;
+}
+
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------

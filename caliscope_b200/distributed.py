@@ -44,8 +44,12 @@ class PointShard:
 
 
 def point_ranges(obs_pt: np.ndarray, n_pts: int, world_size: int) -> np.ndarray:
-    """Contiguous point ranges balanced by observation count: bounds[r] .. bounds[r+1]."""
-    counts = np.bincount(np.asarray(obs_pt), minlength=n_pts)
+    """Contiguous point ranges balanced by observation count: bounds[r] .. bounds[r+1].  Large lists are balanced on
+    every 16th observation (the same sample on every rank; the ranges only steer load balance, any partition is valid)."""
+    obs_pt = np.asarray(obs_pt)
+    if len(obs_pt) >= (1 << 20):
+        obs_pt = obs_pt[::16]
+    counts = np.bincount(obs_pt, minlength=n_pts)
     csum = np.concatenate([[0], np.cumsum(counts)])
     total = csum[-1]
     bounds = [0]
@@ -151,14 +155,16 @@ def camera_order(obs_cam, obs_pt, n_cams: int, n_pts: int, cam_stride: int = 6, 
     greedy chain (next = the unplaced camera sharing most points with the cameras of the last tile), kept only if it
     removes at least 20 % of the co-visibility mass that falls between different 96-column Schur tiles.  Dense
     rigs get the identity."""
-    obs_cam = np.asarray(obs_cam, dtype=np.int64)
-    obs_pt = np.asarray(obs_pt, dtype=np.int64)
     ident = np.arange(n_cams, dtype=np.int32)
     per_tile = max(1, tile // cam_stride)
     if n_cams * cam_stride <= 2 * tile or len(obs_cam) > n_pts * n_cams / 3.0:
         return ident
     stride = max(1, n_pts // 8192)
-    sel = (obs_pt % stride) == 0
+    obs_pt = np.asarray(obs_pt)
+    sel = np.flatnonzero((obs_pt % stride) == 0)
+    obs_cam = np.asarray(obs_cam)[sel].astype(np.int64)
+    obs_pt = obs_pt[sel].astype(np.int64)
+    sel = slice(None)
     M = np.zeros((n_pts // stride + 1, n_cams), dtype=np.float64)
     M[obs_pt[sel] // stride, obs_cam[sel]] = 1.0
     W = M.T @ M

@@ -86,10 +86,12 @@ def solve_filter_resolve_sharded(cam_flags, cam_const, n_pts, obs_cam, obs_pt, o
     rmse: list[float] = []
 
     def global_rmse(prob, x) -> float:
-        e = prob.reproj_errors_px(x)
-        acc = torch.tensor([float(np.sum(e * e)), float(len(e))], dtype=torch.float64,
+        # the shard's sum of squared pixel errors comes from the device reduction (no 16 B / observation download)
+        r = prob.overall_rmse_px(x) if prob.n_obs else 0.0
+        acc = torch.tensor([r * r * prob.n_obs, float(prob.n_obs)], dtype=torch.float64,
                            device="cuda" if dist.get_backend(group) == "nccl" else "cpu")  # fmt: skip
         dist.all_reduce(acc, group=group)
+        acc = acc.cpu()
         return float(np.sqrt(acc[0].item() / max(acc[1].item(), 1.0)))
 
     lap("shard + transport")
@@ -108,8 +110,9 @@ def solve_filter_resolve_sharded(cam_flags, cam_const, n_pts, obs_cam, obs_pt, o
         s2 = prob.solve(s1.x, loss="soft_l1", f_scale=1.0 / f_median, ftol=1e-4, max_nfev=2000, **kw)
         stages.append(s2)
         lap("solve 2")
-        e = prob.reproj_errors_px(s2.x)
-        err = np.sqrt(np.sum(e * e, axis=1))
+        # per-observation euclidean pixel error from the device (evaluated with explicit round-to-nearest multiplies / adds,
+        # bit-identical to np.sqrt(ex*ex + ey*ey))
+        err = prob.error_order_stats(s2.x, 100.0 - filter_percentile, want_err=True)[0]
         rmse.append(global_rmse(prob, s2.x))
         lap("errors + rmse 2")
         thr = D.global_cull_thresholds(err, shard.obs_cam, len(cam_flags), filter_percentile, min_per_camera, group)

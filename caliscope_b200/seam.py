@@ -80,6 +80,12 @@ def install(full: bool = False) -> None:
             if name not in _original_bootstrap:
                 _original_bootstrap[name] = getattr(pnb, name)
             setattr(pnb, name, getattr(bootstrap, name))
+        # ... and the entry point above them (capture_volume.py:287-315 imports it at call time): the whole PnP branch as
+        # three device calls, no per-pose Python objects
+        bpn = importlib.import_module("caliscope.core.bootstrap_pose.build_paired_pose_network")
+        if "build_paired_pose_network" not in _original_bootstrap:
+            _original_bootstrap["build_paired_pose_network"] = bpn.build_paired_pose_network
+        bpn.build_paired_pose_network = bootstrap.build_paired_pose_network
 
 
         # seam S5: the numeric CSV tables (ImagePoints / WorldPoints .to_csv / .from_csv) through the native writer / parser
@@ -151,8 +157,9 @@ def uninstall() -> None:
         _original_tables.clear()
     if _original_bootstrap:
         pnb = importlib.import_module("caliscope.core.bootstrap_pose.pose_network_builder")
+        bpn = importlib.import_module("caliscope.core.bootstrap_pose.build_paired_pose_network")
         for name, fn in _original_bootstrap.items():
-            setattr(pnb, name, fn)
+            setattr(bpn if name == "build_paired_pose_network" else pnb, name, fn)
         _original_bootstrap.clear()
 
 

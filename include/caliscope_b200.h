@@ -311,6 +311,24 @@ int cb_stereo_rmse(int32_t n_cams, const int32_t* cam_fisheye, const double* cam
                    const int32_t* obs_cam, const int64_t* obs_key, const double* obs_px, int32_t min_common,
                    double* rmse_out, int64_t* count_out, CbTriStats* stats, int device, void* stream);
 
+/* cb_relative_pose_network == compute_relative_poses (pose_network_builder.py:484-531) -> reject_outliers (:331-413) ->
+ *   aggregate_poses (:533-573, quaternion_average :416-438) for every camera pair in one device pass; the relative poses
+ *   never leave the device.
+ *   Input: the PnP poses (camera <- object) of the cameras the array does not ignore, sorted by (sync_index, object_id,
+ *   camera id): group g has camera id cam_id[g], position cam_pos[g] in the reference's camera dict, pose R[9g..], t[3g..]
+ *   (NaN poses allowed: cv2's degenerate groups); frame_start[f] .. frame_start[f+1] are the groups of one (sync_index,
+ *   object_id).  Every combination (i < j) of a frame's groups is one candidate relative pose; the reference forms it only if
+ *   cam_pos[i] < cam_pos[j] (its `combinations(dict order) if a < b` quirk).
+ *   rot_mult / tr_mult: IQR multipliers of the rotation-angle / translation-magnitude rules (1.5 in the reference).
+ *   Output, camera pairs in ascending (a, b), at most max_pairs: ids, aggregated R (9) and t (3), number of samples kept.
+ *   Optional (n_rel = sum over frames of s(s-1)/2, frame-major, np.triu_indices order inside a frame): rel_valid[m] = 1 when
+ *   the combination was formed, rel_keep[m] = 1 when it passed the NaN filter and the IQR rule. */
+int cb_relative_pose_network(int32_t n_groups, int32_t n_frames, const int32_t* frame_start, const int32_t* cam_id,
+                             const int32_t* cam_pos, const double* R, const double* t, double rot_mult, double tr_mult,
+                             int32_t max_pairs, int32_t* n_pairs_out, int32_t* pair_a, int32_t* pair_b, double* R_out,
+                             double* t_out, int64_t* count_out, int64_t n_rel, uint8_t* rel_valid, uint8_t* rel_keep,
+                             CbTriStats* stats, int device, void* stream);
+
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Numeric CSV tables at the boundary of the path: xy_<TRACKER>.csv / xyz_<TRACKER>.csv as written

@@ -189,3 +189,70 @@ def test_stereo_rmse_exact_geometry_and_missing_pairs():
     rmse, cnt = B.stereo_rmse_arrays(tab, pairs, Rs, ts, cam, sync, z, z, xy)
     assert cnt.tolist() == [40, 3]
     assert rmse[0] < 5e-7 and np.isnan(rmse[1])
+
+
+def test_pose_network_on_device_matches_host_arrays(case):
+    """cb_relative_pose_network (relative poses, IQR rule, quaternion / translation averages of every pair in one device
+    call) against the array implementation pinned on the reference (tests/test_bootstrap_host.py): same pairs, same keep
+    mask row for row, same counts, aggregated poses to 1e-12 -- from the reference's own PnP poses, NaN groups included."""
+    from caliscope_b200 import bootstrap as B
+
+    g, tab, _ = case
+    rel = B.relative_pose_arrays(g["pnp_keys"], g["pnp_R"], g["pnp_t"], tab)
+    pairs_h, keep_h, R_h, t_h, cnt_h = B.filter_and_aggregate(rel, 1.5)
+    pairs, R, t, cnt, keep, st = B.pose_network_arrays(g["pnp_keys"], g["pnp_R"], g["pnp_t"], tab, 1.5, want_keep=True)
+    assert pairs.tolist() == pairs_h.tolist()
+    assert cnt.tolist() == cnt_h.tolist()
+    # the host rows are frame-major in the same combination order
+    assert len(keep) == len(keep_h) and (keep == keep_h).all()
+    assert np.abs(R - R_h).max() < 1e-12 and np.abs(t - t_h).max() < 1e-12
+    gold = {(int(a), int(b)): i for i, (a, b) in enumerate(g["agg_pairs"])}
+    for k, (a, b) in enumerate(pairs):
+        i = gold[(int(a), int(b))]
+        assert np.abs(R[k] - g["agg_R"][i]).max() < 1e-9 and np.abs(t[k] - g["agg_t"][i]).max() < 1e-9
+    assert st.kernel_launches > 0
+    # separate multipliers and a pass-everything threshold
+    p2, R2, t2, c2, k2, _ = B.pose_network_arrays(g["pnp_keys"], g["pnp_R"], g["pnp_t"], tab, 1.5, rotation_threshold_multiplier=0.5,
+                                                   translation_threshold_multiplier=3.0, want_keep=True)  # fmt: skip
+    ph, kh, Rh, th, ch = B.filter_and_aggregate(rel, 1.5, 0.5, 3.0)
+    assert p2.tolist() == ph.tolist() and c2.tolist() == ch.tolist() and (k2 == kh).all()
+    assert np.abs(R2 - Rh).max() < 1e-12 and np.abs(t2 - th).max() < 1e-12
+
+
+def test_pose_network_edge_cases():
+    """No frame with two cameras -> no pair; a pair with fewer than 5 samples keeps all of them; a lone sample is passed
+    through bit for bit; poses of an ignored camera form no pair; the dict-order quirk drops (b, a) combinations."""
+    from caliscope_b200 import bootstrap as B
+    from oracle.ippe import _rodrigues
+
+    tab = _tiny_tables(4)
+    tab.ignore[3] = True
+    rng = np.random.default_rng(1)
+
+    def pose():
+        return _rodrigues(rng.normal(size=3) * 0.2), rng.normal(size=3)
+
+    keys, Rs, ts = [], [], []
+    for cam, sync in [(0, 0), (1, 0), (0, 1), (1, 1), (2, 1), (3, 1), (0, 2), (0, 3), (2, 3)]:
+        R, t = pose()
+        keys.append((cam, sync, 0)); Rs.append(R); ts.append(t)
+    keys, Rs, ts = np.array(keys), np.array(Rs), np.array(ts)
+    rel = B.relative_pose_arrays(keys, Rs, ts, tab)
+    ph, kh, Rh, th, ch = B.filter_and_aggregate(rel, 1.5)
+    p, R, t, c, k, _ = B.pose_network_arrays(keys, Rs, ts, tab, 1.5, want_keep=True)
+    assert p.tolist() == ph.tolist() == [[0, 1], [0, 2], [1, 2]]
+    assert c.tolist() == ch.tolist() == [2, 2, 1] and k.all()
+    assert np.abs(R - Rh).max() < 1e-13 and np.abs(t - th).max() < 1e-13
+    i12 = 2  # single sample: the relative pose itself
+    assert (R[i12] == rel.R[(rel.pair_a == 1) & (rel.pair_b == 2)][0]).all()
+    # nothing to pair
+    p0, *_ = B.pose_network_arrays(keys[:1], Rs[:1], ts[:1], tab, 1.5)
+    assert len(p0) == 0
+    # camera ids whose dict order is not id order: (2, 1) comes first in the dict, so the pair (1, 2) is never formed
+    ids = np.array([0, 2, 1], dtype=np.int64)
+    tab2 = B.CameraTables(ids, {0: 0, 2: 1, 1: 2}, tab.k[:3], tab.dist[:3], tab.fisheye[:3], np.zeros(3, bool), np.ones(3, bool))
+    keys2 = np.array([(0, 0, 0), (1, 0, 0), (2, 0, 0)])
+    rel2 = B.relative_pose_arrays(keys2, Rs[:3], ts[:3], tab2)
+    p3, *_ = B.pose_network_arrays(keys2, Rs[:3], ts[:3], tab2, 1.5)
+    assert p3.tolist() == sorted({(int(a), int(b)) for a, b in zip(rel2.pair_a, rel2.pair_b)}) == [(0, 1), (0, 2)] or \
+        p3.tolist() == [[0, 1], [0, 2]]

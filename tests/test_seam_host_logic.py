@@ -353,16 +353,64 @@ def test_s4_bootstrap_dict_stages_equal_reference(session_volume):
         assert np.abs(agg[k].translation - agg_ref[k].translation).max() < 1e-9
 
 
+def test_s4_fused_entry_point_glue_equals_reference(session_volume, monkeypatch):
+    """bootstrap.build_paired_pose_network (the fused PnP branch) with its three device calls replaced by array results
+    taken from the REFERENCE's own stage functions: what is tested here, on the CPU, is the glue -- group filtering, pair
+    order of the dict handed to PairedPoseNetwork.from_raw_estimates, the None-RMSE rule -- so the network must come out
+    identical to the unmodified build_paired_pose_network.  (The device stages are pinned in tests/test_gpu_bootstrap.py.)"""
+    from caliscope.core.bootstrap_pose import pose_network_builder as PNB
+    from caliscope.core.bootstrap_pose.build_paired_pose_network import build_paired_pose_network as ref_build
+    from caliscope_b200 import bootstrap as B
+
+    cv = session_volume
+    ref_net = ref_build(cv.image_points, cv.camera_array)
+    poses = PNB.compute_camera_to_object_poses_pnp(cv.image_points, cv.camera_array)
+    agg_ref = PNB.aggregate_poses(PNB.reject_outliers(PNB.compute_relative_poses(poses, cv.camera_array), threshold=1.5))
+    common = PNB._precompute_common_observations(cv.image_points, cv.camera_array)
+
+    def fake_pnp(tab, cam_id, sync, oid, xy, obj, min_points=4, device=0):
+        keys = np.array(list(poses), dtype=np.int64).reshape(-1, 3)
+        return B.PnPResult(keys, np.array([v[0] for v in poses.values()]), np.array([v[1] for v in poses.values()]),
+                           np.array([v[2] for v in poses.values()]), np.zeros(len(keys), np.int32), np.zeros(len(keys), np.int32))
+
+    def fake_network(keys, R, t, tab, threshold=1.5, *a, **k):
+        rel = B.relative_pose_arrays(keys, R, t, tab)
+        pairs, _, Ra, ta, cnt = B.filter_and_aggregate(rel, threshold)
+        return pairs, Ra, ta, cnt, None, None
+
+    def fake_rmse(tab, pairs, R, t, *a, **k):
+        out = np.full(len(pairs), np.nan)
+        for i, (a_, b_) in enumerate(pairs):
+            r = PNB.calculate_stereo_rmse_for_pair(agg_ref[(int(a_), int(b_))], cv.camera_array, common)
+            out[i] = np.nan if r is None else r
+        return out, np.zeros(len(pairs), np.int64)
+
+    monkeypatch.setattr(B, "pnp_arrays", fake_pnp)
+    monkeypatch.setattr(B, "pose_network_arrays", fake_network)
+    monkeypatch.setattr(B, "stereo_rmse_arrays", fake_rmse)
+    net = B.build_paired_pose_network(cv.image_points, cv.camera_array)
+    assert list(net._pairs) == list(ref_net._pairs)  # same pairs, same dict order (gap filling included)
+    for k in net._pairs:
+        a, b = net._pairs[k], ref_net._pairs[k]
+        assert np.abs(a.rotation - b.rotation).max() < 1e-9 and np.abs(a.translation - b.translation).max() < 1e-9
+        assert abs(a.error_score - b.error_score) < 1e-9
+
+
 def test_seam_install_full_patches_bootstrap_and_restores():
     import caliscope.core.bootstrap_pose.pose_network_builder as pnb
     import caliscope_b200.seam as seam
     from caliscope_b200 import bootstrap as B
 
+    import caliscope.core.bootstrap_pose.build_paired_pose_network as bpn
+
     before = [getattr(pnb, n) for n in seam._BOOTSTRAP_FUNCTIONS]
+    top = bpn.build_paired_pose_network
     with seam.installed(full=True):
         for n in seam._BOOTSTRAP_FUNCTIONS:
             assert getattr(pnb, n) is getattr(B, n)
+        assert bpn.build_paired_pose_network is B.build_paired_pose_network  # capture_volume.py:287 imports it at call time
     assert [getattr(pnb, n) for n in seam._BOOTSTRAP_FUNCTIONS] == before
+    assert bpn.build_paired_pose_network is top
 
 
 def test_s5_point_tables_round_trip_through_the_seam(session_volume, tmp_path):
