@@ -114,6 +114,7 @@ SYMBOLS = {
     "cb_ba_problem_create": (C.c_int, [C.POINTER(ProblemDesc), C.c_int, _P, C.POINTER(_P)]),
     "cb_ba_problem_destroy": (C.c_int, [_P]),
     "cb_ba_problem_n_params": (C.c_int64, [_P]),
+    "cb_ba_problem_stat": (C.c_double, [_P, C.c_int]),
     "cb_ba_problem_set_constraints": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P]),
     "cb_ba_problem_n_constraints": (C.c_int64, [_P]),
     "cb_ba_constraint_rows": (C.c_int, [_P, _P, _P, _P, _P]),
@@ -131,6 +132,7 @@ SYMBOLS = {
     "cb_ba_cull": (C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(_P), _P, _P, _P]),
     "cb_ba_debug_pcg_time": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "cb_debug_fp64_peak": (C.c_int, [C.c_int, _P, _P]),
+    "cb_shard_select": (C.c_int, [C.c_int64, _P, _P, _P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P, _P, _P, C.c_int32]),
     "cb_csv_write_numeric": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int64, C.c_int32, _P, _P, C.c_int32]),
     "cb_csv_scan": (C.c_int, [C.c_char_p, _P, _P]),
     "cb_csv_parse_numeric": (C.c_int, [C.c_char_p, C.c_int64, C.c_int32, _P, _P, _P, C.c_int32]),

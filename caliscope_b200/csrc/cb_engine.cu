@@ -317,31 +317,63 @@ int staged_h2d(void* d_dst, const void* h_src, size_t bytes, cudaStream_t st, Sc
   void* pin = nullptr;
   CB_TRY(cached_malloc_host(&pin, bytes));
   sf.host.push_back(pin);
-  const size_t chunk = (size_t)1 << 20;
-  const size_t n_chunks = (bytes + chunk - 1) / chunk;
+  // Two granularities.  Host threads copy 512 KB units (enough units to keep 6-8 threads busy on a 4 MB array); the DMA is
+  // queued in 4 MB blocks: every cudaMemcpyAsync costs ~40 us of copy-engine time on top of its bytes (measured: 1 MB
+  // copies reach 14 GB/s, one 32 MB copy 47 GB/s), so small blocks throttle the engine and large ones expose the staging.
+  const size_t unit = (size_t)512 << 10, units_per_block = 8;
+  const size_t n_units = (bytes + unit - 1) / unit;
+  const size_t n_blocks = (n_units + units_per_block - 1) / units_per_block;
   struct Shared {
     std::atomic<size_t> next{0};
     std::vector<std::atomic<unsigned char>> done;
     explicit Shared(size_t n) : done(n) { for (auto& d : done) d.store(0, std::memory_order_relaxed); }
   };
-  auto sh = std::make_shared<Shared>(n_chunks);
-  auto copy_one = [sh, pin, h_src, bytes, chunk, n_chunks]() -> bool {
+  auto sh = std::make_shared<Shared>(n_units);
+  auto copy_one = [sh, pin, h_src, bytes, unit, n_units]() -> bool {
     const size_t c = sh->next.fetch_add(1);
-    if (c >= n_chunks) return false;
-    const size_t off = c * chunk, sz = std::min(chunk, bytes - off);
+    if (c >= n_units) return false;
+    const size_t off = c * unit, sz = std::min(unit, bytes - off);
     std::memcpy((char*)pin + off, (const char*)h_src + off, sz);
     sh->done[c].store(1, std::memory_order_release);
     return true;
   };
-  const int helpers = (int)std::min<size_t>((size_t)std::max(0, std::min(n_threads, WorkerPool::get().size())), n_chunks > 1 ? n_chunks - 1 : 0);
+  static const bool prof = std::getenv("CB_PROFILE_CREATE") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
+  const int helpers = (int)std::min<size_t>((size_t)std::max(0, std::min(n_threads, WorkerPool::get().size())), n_units > 1 ? n_units - 1 : 0);
   for (int t = 0; t < helpers; ++t)
     WorkerPool::get().submit([copy_one] { while (copy_one()) {} });
   bool failed = false;
-  for (size_t c = 0; c < n_chunks; ++c) {
-    while (!sh->done[c].load(std::memory_order_acquire))
-      if (!copy_one()) std::this_thread::yield();
-    const size_t off = c * chunk, sz = std::min(chunk, bytes - off);
+  double wait_ms = 0.0, issue_ms = 0.0;
+  size_t own = 0;
+  cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+  if (prof) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, st); }
+  for (size_t blk = 0; blk < n_blocks; ++blk) {
+    const size_t u0 = blk * units_per_block, u1 = std::min(n_units, u0 + units_per_block);
+    const auto a = std::chrono::steady_clock::now();
+    for (size_t c = u0; c < u1; ++c)
+      while (!sh->done[c].load(std::memory_order_acquire)) {
+        if (copy_one()) ++own; else std::this_thread::yield();
+      }
+    const auto b = std::chrono::steady_clock::now();
+    const size_t off = u0 * unit, sz = std::min(bytes, u1 * unit) - off;
     if (!failed && cudaMemcpyAsync((char*)d_dst + off, (char*)pin + off, sz, cudaMemcpyHostToDevice, st) != cudaSuccess) failed = true;
+    if (prof) {
+      const auto e = std::chrono::steady_clock::now();
+      wait_ms += std::chrono::duration<double, std::milli>(b - a).count();
+      issue_ms += std::chrono::duration<double, std::milli>(e - b).count();
+    }
+  }
+  if (prof) {
+    const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    cudaEventRecord(pe1, st);
+    cudaEventSynchronize(pe1);
+    float dma_ms = 0.f;
+    cudaEventElapsedTime(&dma_ms, pe0, pe1);
+    const double all_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    cudaEventDestroy(pe0); cudaEventDestroy(pe1);
+    std::fprintf(stderr, "[stage] %6.1f MB, %d helpers, %zu DMA blocks: host %.3f ms (units %.3f, %zu by the issuer; cudaMemcpyAsync calls %.3f); "
+                         "device first->last copy %.3f ms = %.1f GB/s; staged + landed %.3f ms\n",
+                 bytes / 1e6, helpers, n_blocks, host_ms, wait_ms, own, issue_ms, dma_ms, bytes / 1e6 / std::max(dma_ms, 1e-3f), all_ms);
   }
   if (failed) { g_last_error = std::string("staged host-to-device copy: ") + cudaGetErrorString(cudaGetLastError()); return CB_E_CUDA; }
   return CB_OK;
@@ -388,6 +420,7 @@ struct CbBaProblem {
   int ncp = 0;                  // total camera parameters in x
   int *d_cam_xoff = nullptr, *d_cam_slot = nullptr, *d_klist = nullptr;
   bool schur_sparse = false;
+  double schur_flop_issued = 0.0;  // flops one schur_syrk_kernel launch issues (dense tiles or compacted lists)
   double schur_rows_dense = 0.0, schur_rows_listed = 0.0;  // weighted k rows the Schur product streams: all vs listed
   std::vector<void*> allocs;
   // problem tables
@@ -1456,6 +1489,16 @@ int cb_ba_problem_destroy(CbBaProblem* p) {
 
 int64_t cb_ba_problem_n_params(const CbBaProblem* p) { return p ? p->n_params : -1; }
 int cb_ba_cam_stride(const CbBaProblem* p) { return p ? p->P : -1; }
+double cb_ba_problem_stat(const CbBaProblem* p, int what) {
+  if (!p) return -1.0;
+  switch (what) {
+    case 0: return p->schur_sparse ? 1.0 : 0.0;
+    case 1: return p->schur_flop_issued;
+    case 2: return p->direct_solve ? 1.0 : 0.0;
+    case 3: return (double)p->n_items;
+    default: return -1.0;
+  }
+}
 
 // Schur work items.  Dense visibility: off-diagonal tiles and pairs of diagonal tiles, each split over k so that the
 // grid is one CTA per SM with equal DMMA work (a diagonal pair costs 45/36 of a full tile per chunk).  Sparse
@@ -1544,6 +1587,13 @@ static int build_schur_items(CbBaProblem* p, cudaStream_t st) {
   }
   double W = 0.0;
   for (auto& g : groups) W += g.w * g.chunks;
+  // flops the product issues per launch: an off-diagonal tile is 96 x 96 outputs per k row, a diagonal tile its 10
+  // upper-triangular 24 x 24 blocks
+  p->schur_flop_issued = 0.0;
+  for (auto& g : groups) {
+    const double cols2 = g.kind == 0 ? 96.0 * 96.0 : (g.J >= 0 ? 2.0 : 1.0) * 10.0 * 24.0 * 24.0;
+    p->schur_flop_issued += 2.0 * cols2 * (double)g.chunks * cb::SY_KC;
+  }
   std::vector<cb::SyItem> items;
   std::vector<std::vector<int>> slots_of(nt);
   int slot = 0;
@@ -3268,6 +3318,49 @@ int cb_csv_write_numeric(const char* path, const char* header, int64_t n_rows, i
     std::remove(tmp.c_str());
     return CB_E_INVALID;
   }
+  return CB_OK;
+}
+
+// Host-side shard selection of a sharded solve: the observations whose point lies in [pt_lo, pt_hi), in the caller's
+// order, with the point index made local.  Two passes over obs_pt by all host threads (count, then write at the prefix
+// offsets); the NumPy version of the same selection (mask, flatnonzero, three fancy-index gathers) costs ~15 ms on a
+// 2 M-observation list and sits inside every sharded call on every rank.
+int cb_shard_select(int64_t n_obs, const int32_t* obs_cam, const int32_t* obs_pt, const double* obs_xy, int32_t pt_lo,
+                    int32_t pt_hi, int64_t capacity, int64_t* n_sel_out, int64_t* sel_index, int32_t* cam_out,
+                    int32_t* pt_out, double* xy_out, int32_t n_threads) {
+  if (n_obs < 0 || !n_sel_out || (n_obs > 0 && (!obs_cam || !obs_pt || !obs_xy))) {
+    g_last_error = "cb_shard_select: bad argument";
+    return CB_E_INVALID;
+  }
+  const int nt = cbio::n_workers(n_threads, (size_t)n_obs, (size_t)1 << 16);
+  std::vector<int64_t> cnt((size_t)nt + 1, 0);
+  auto slice = [&](int t, int64_t* b, int64_t* e) { *b = n_obs * t / nt; *e = n_obs * (t + 1) / nt; };
+  cbio::parallel_for(nt, [&](int t) {
+    int64_t b, e, c = 0;
+    slice(t, &b, &e);
+    for (int64_t i = b; i < e; ++i) c += (obs_pt[i] >= pt_lo) & (obs_pt[i] < pt_hi);
+    cnt[(size_t)t + 1] = c;
+  });
+  for (int t = 0; t < nt; ++t) cnt[(size_t)t + 1] += cnt[(size_t)t];
+  *n_sel_out = cnt[(size_t)nt];
+  if (!sel_index && !cam_out && !pt_out && !xy_out) return CB_OK;  // size query
+  if (cnt[(size_t)nt] > capacity) {
+    g_last_error = "cb_shard_select: capacity " + std::to_string(capacity) + " < " + std::to_string(cnt[(size_t)nt]) + " selected rows";
+    return CB_E_INVALID;
+  }
+  cbio::parallel_for(nt, [&](int t) {
+    int64_t b, e, o = cnt[(size_t)t];
+    slice(t, &b, &e);
+    for (int64_t i = b; i < e; ++i) {
+      const int32_t pt = obs_pt[i];
+      if (pt < pt_lo || pt >= pt_hi) continue;
+      if (sel_index) sel_index[o] = i;
+      if (cam_out) cam_out[o] = obs_cam[i];
+      if (pt_out) pt_out[o] = pt - pt_lo;
+      if (xy_out) { xy_out[2 * o] = obs_xy[2 * i]; xy_out[2 * o + 1] = obs_xy[2 * i + 1]; }
+      ++o;
+    }
+  });
   return CB_OK;
 }
 

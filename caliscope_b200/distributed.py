@@ -85,6 +85,34 @@ def _component_labels(n_pts: int, groups_a: np.ndarray, groups_b: np.ndarray) ->
     return np.array([find(int(j)) for j in range(n_pts)], dtype=np.int64)
 
 
+def _native_shard_select(obs_cam, obs_pt, obs_xy, lo: int, hi: int):
+    """The selection through the library's multi-threaded ``cb_shard_select`` when the inputs already have the ABI's
+    dtypes (int32 / int32 / float64, contiguous) and the list is large; None otherwise (the NumPy path below is the same
+    selection)."""
+    import ctypes as C
+
+    obs_cam, obs_xy = np.asarray(obs_cam), np.asarray(obs_xy)
+    if (len(obs_pt) < (1 << 18) or obs_cam.dtype != np.int32 or obs_pt.dtype != np.int32 or obs_xy.dtype != np.float64
+            or not (obs_cam.flags.c_contiguous and obs_pt.flags.c_contiguous and obs_xy.flags.c_contiguous)):  # fmt: skip
+        return None
+    from . import _lib as L
+
+    lib = L.load()
+    n = len(obs_pt)
+    n_sel = C.c_int64()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    L.check(lib.cb_shard_select(n, p(obs_cam), p(obs_pt), p(obs_xy), lo, hi, 0, C.addressof(n_sel), None, None, None, None, 0),
+            "shard_select")  # fmt: skip
+    m = n_sel.value
+    sel = np.empty(m, np.int64)
+    cam_l = np.empty(m, np.int32)
+    pt_l = np.empty(m, np.int32)
+    xy_l = np.empty((m, 2), np.float64)
+    L.check(lib.cb_shard_select(n, p(obs_cam), p(obs_pt), p(obs_xy), lo, hi, m, C.addressof(n_sel), p(sel), p(cam_l), p(pt_l),
+                                p(xy_l), 0), "shard_select")  # fmt: skip
+    return sel, cam_l, pt_l, xy_l
+
+
 def shard_points(obs_cam, obs_pt, obs_xy, n_pts: int, rank: int, world_size: int, constraints=None) -> PointShard:
     """Partition the points (and with them the observations and constraint rows) over the ranks.
 
@@ -98,6 +126,11 @@ def shard_points(obs_cam, obs_pt, obs_xy, n_pts: int, rank: int, world_size: int
         # every sharded call on every rank; the general path below costs ~25 ms on 2 M observations)
         bounds = point_ranges(obs_pt, n_pts, world_size)
         lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        native = _native_shard_select(obs_cam, obs_pt, obs_xy, lo, hi)
+        if native is not None:
+            sel, cam_l, pt_l, xy_l = native
+            return PointShard(rank=rank, world_size=world_size, pt_index=np.arange(lo, hi, dtype=np.int64), obs_index=sel,
+                              obs_cam=cam_l, obs_pt=pt_l, obs_xy=xy_l)  # fmt: skip
         sel = np.flatnonzero((obs_pt >= lo) & (obs_pt < hi))
         return PointShard(
             rank=rank,

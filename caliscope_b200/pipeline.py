@@ -129,8 +129,8 @@ def solve_filter_resolve_sharded(cam_flags, cam_const, n_pts, obs_cam, obs_pt, o
     lap("gather points")
     # full keep mask: every rank contributes its observations' flags at their global positions
     dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
-    full = torch.zeros(len(obs_cam), dtype=torch.int32, device=dev)
-    full[torch.as_tensor(shard.obs_index, device=dev)] = torch.as_tensor(keep_local.astype(np.int32), device=dev)
+    full = torch.zeros(len(obs_cam), dtype=torch.uint8, device=dev)  # one byte per observation: every row has one owner
+    full[torch.as_tensor(shard.obs_index, device=dev)] = torch.as_tensor(keep_local.astype(np.uint8), device=dev)
     dist.all_reduce(full, group=group)
     keep = full.cpu().numpy().astype(bool)
     lap("keep mask")

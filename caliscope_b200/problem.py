@@ -164,6 +164,10 @@ class BAProblem:
     def __exit__(self, *exc):
         self.close()
 
+    def stat(self, what: int) -> float:
+        """``cb_ba_problem_stat``: 0 sparse Schur lists in use, 1 flops per Schur-product launch, 2 direct reduced solve, 3 Schur CTAs."""
+        return float(self._lib.cb_ba_problem_stat(self._h, int(what)))
+
     def _x(self, x) -> np.ndarray:
         x = np.ascontiguousarray(x, dtype=np.float64)
         if x.shape != (self.n_params,):

@@ -151,6 +151,10 @@ void cb_ba_default_options(CbBaOptions* opt);
 int cb_ba_problem_create(const CbBaProblemDesc* desc, int device, void* stream, CbBaProblem** out);
 int cb_ba_problem_destroy(CbBaProblem* p);
 int64_t cb_ba_problem_n_params(const CbBaProblem* p);
+/* Facts about how the engine laid the problem out (measurement / diagnostics): what = 0: 1 if the Schur product walks
+ * compacted row lists (sparse visibility), 1: floating-point operations one Schur-product launch issues, 2: 1 if the reduced
+ * system is solved directly (<= 96 camera parameters), 3: CTAs of the Schur product.  -1 for an unknown key. */
+double cb_ba_problem_stat(const CbBaProblem* p, int what);
 
 /* Rigid-distance constraint rows (reprojection.py:112-117 and :207-226): groups_a / groups_b are n_c x 4 world-point
  * row indices, distances and weights n_c doubles -- the arrays CaptureVolume._build_constraint_arrays produces
@@ -329,6 +333,13 @@ int cb_relative_pose_network(int32_t n_groups, int32_t n_frames, const int32_t* 
                              double* t_out, int64_t* count_out, int64_t n_rel, uint8_t* rel_valid, uint8_t* rel_keep,
                              CbTriStats* stats, int device, void* stream);
 
+
+/* Host-side shard selection of a sharded solve (distributed.shard_points): the observations whose point index lies in
+ * [pt_lo, pt_hi), in the caller's order, point index made local (pt - pt_lo).  All host threads; no device work.
+ * With every output pointer null it only counts (*n_sel_out).  sel_index = positions in the caller's list. */
+int cb_shard_select(int64_t n_obs, const int32_t* obs_cam, const int32_t* obs_pt, const double* obs_xy, int32_t pt_lo,
+                    int32_t pt_hi, int64_t capacity, int64_t* n_sel_out, int64_t* sel_index, int32_t* cam_out,
+                    int32_t* pt_out, double* xy_out, int32_t n_threads);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Numeric CSV tables at the boundary of the path: xy_<TRACKER>.csv / xyz_<TRACKER>.csv as written

@@ -243,8 +243,8 @@ def test_pose_network_edge_cases():
     assert p.tolist() == ph.tolist() == [[0, 1], [0, 2], [1, 2]]
     assert c.tolist() == ch.tolist() == [2, 2, 1] and k.all()
     assert np.abs(R - Rh).max() < 1e-13 and np.abs(t - th).max() < 1e-13
-    i12 = 2  # single sample: the relative pose itself
-    assert (R[i12] == rel.R[(rel.pair_a == 1) & (rel.pair_b == 2)][0]).all()
+    i12 = 2  # single sample: the relative pose itself, not a quaternion round trip (products contracted to FMAs on the device)
+    assert np.abs(R[i12] - rel.R[(rel.pair_a == 1) & (rel.pair_b == 2)][0]).max() < 1e-15
     # nothing to pair
     p0, *_ = B.pose_network_arrays(keys[:1], Rs[:1], ts[:1], tab, 1.5)
     assert len(p0) == 0
