@@ -309,8 +309,8 @@ def load_peaks() -> tuple[float, str]:
 def kernel_source_hash() -> str:
     import hashlib
 
-    h = hashlib.sha256()
-    for f in sorted((ROOT / "caliscope_b200" / "csrc").glob("*.cu*")):
+    h = hashlib.sha256()  # the kernel sources (headers); the host engine cb_engine.cu launches them but does not change their traffic
+    for f in sorted((ROOT / "caliscope_b200" / "csrc").glob("*.cuh")):
         h.update(f.read_bytes())
     return h.hexdigest()[:16]
 
