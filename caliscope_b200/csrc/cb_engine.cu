@@ -2554,16 +2554,16 @@ int to_device(const T* src, size_t n, int on_device, const T** out, ScopedFree& 
   T* d = nullptr;
   CB_TRY(dalloc(&d, n));
   sf.dev.push_back(d);
+  if (sizeof(T) * n >= ((size_t)2 << 20)) {  // large arrays: pool threads stage, the DMA is queued block by block
+    CB_TRY(staged_h2d(d, src, sizeof(T) * n, st, sf, 8));
+    *out = d;
+    return CB_OK;
+  }
   T* h = nullptr;
   CB_TRY(cached_malloc_host((void**)&h, sizeof(T) * std::max<size_t>(n, 1)));
   sf.host.push_back(h);
-  // chunked so the DMA of one chunk overlaps the host memcpy of the next
-  const size_t bytes = sizeof(T) * n, chunk = (size_t)4 << 20;
-  for (size_t off = 0; off < bytes; off += chunk) {
-    const size_t sz = std::min(chunk, bytes - off);
-    stream_copy((char*)h + off, (const char*)src + off, sz);  // non-temporal: the DMA reads it next (see stream_copy)
-    CB_CUDA(cudaMemcpyAsync((char*)d + off, (char*)h + off, sz, cudaMemcpyHostToDevice, st));
-  }
+  stream_copy(h, src, sizeof(T) * n);  // non-temporal: the DMA reads it next (see stream_copy)
+  CB_CUDA(cudaMemcpyAsync(d, h, sizeof(T) * n, cudaMemcpyHostToDevice, st));
   *out = d;
   return CB_OK;
 }
