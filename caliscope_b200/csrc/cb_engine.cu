@@ -1545,8 +1545,8 @@ static int build_schur_items(CbBaProblem* p, cudaStream_t st) {
   if (const char* ev = std::getenv("CB_SY_PAIR_W")) w_pair = std::atof(ev);
   const double w_single = 0.75;
 
-  // per-pair point lists, if sparse
-  std::vector<std::vector<int>> plist;  // indexed by tile id (tof)
+  // per-pair row lists, if sparse: offset of each tile pair's list in d_klist (-1: no common point) and its point count
+  std::vector<long long> pair_koff, pair_cnt;
   bool sparse = false;
   int want_sparse = -1;
   if (const char* ev = std::getenv("CB_SY_SPARSE")) want_sparse = std::atoi(ev);
@@ -1565,7 +1565,6 @@ static int build_schur_items(CbBaProblem* p, cudaStream_t st) {
     CB_CUDA(cudaMemcpyAsync(cnt_u.data(), d_cnt, sizeof(unsigned long long) * nt, cudaMemcpyDeviceToHost, st));
     CB_CUDA(cudaStreamSynchronize(st));
     std::vector<long long> cnt(cnt_u.begin(), cnt_u.end());
-    std::vector<unsigned long long> mask;
     double listed = 0.0, dense = 0.0;
     for (int I = 0; I < nb; ++I)
       for (int J = I; J < nb; ++J) {
@@ -1576,25 +1575,58 @@ static int build_schur_items(CbBaProblem* p, cudaStream_t st) {
     p->schur_rows_dense = 3.0 * dense; p->schur_rows_listed = 3.0 * listed;
     sparse = want_sparse == 1 || listed < 0.7 * dense;
     if (sparse) {
-      mask.resize((size_t)p->n_pts);
-      CB_CUDA(cudaMemcpyAsync(mask.data(), d_mask, sizeof(unsigned long long) * p->n_pts, cudaMemcpyDeviceToHost, st));
-      CB_CUDA(cudaStreamSynchronize(st));
-      plist.resize(nt);
-      for (int t = 0; t < nt; ++t) plist[t].reserve((size_t)cnt[t]);
-      for (int j = 0; j < p->n_pts; ++j) {
-        unsigned long long m = mask[j];
-        for (unsigned long long a = m; a; a &= a - 1) {
-          const int I = __builtin_ctzll(a);
-          for (unsigned long long b2 = a; b2; b2 &= b2 - 1) plist[tof[(size_t)I * nb + __builtin_ctzll(b2)]].push_back(j);
-        }
+      // the row lists are built on the device (inc_count .. klist_expand in cb_kernels.cuh); the host only lays out where each
+      // tile pair's list starts
+      const int zero_row = p->K_pad;  // rows K_pad .. K_pad + SY_KC - 1 of Zt / tvec are never written
+      std::vector<long long> pair_start((size_t)nt + 1, 0), koff_h((size_t)nt, -1);
+      long long klen = 0;
+      for (int t = 0; t < nt; ++t) {
+        pair_start[(size_t)t + 1] = pair_start[(size_t)t] + cnt[(size_t)t];
+        if (cnt[(size_t)t] == 0) continue;
+        koff_h[(size_t)t] = klen;
+        klen += cdiv(3 * cnt[(size_t)t], (long long)cb::SY_KC) * cb::SY_KC;
       }
+      const long long n_inc = pair_start[(size_t)nt];
+      if (klen > 0x7fffffffLL || n_inc > 0x7fffffffLL) { g_last_error = "Schur row lists exceed 2^31 entries"; return CB_E_UNSUPPORTED; }
+      pair_koff.assign(koff_h.begin(), koff_h.end());
+      pair_cnt.assign(cnt.begin(), cnt.end());
+      int *d_ninc = nullptr, *d_incoff = nullptr;
+      unsigned long long *d_keys = nullptr, *d_keys_s = nullptr;
+      long long *d_pair_start = nullptr, *d_koff = nullptr;
+      CB_TRY(dalloc(&d_ninc, (size_t)p->n_pts + 1)); sf.dev.push_back(d_ninc);
+      CB_TRY(dalloc(&d_incoff, (size_t)p->n_pts + 1)); sf.dev.push_back(d_incoff);
+      CB_TRY(dalloc(&d_keys, (size_t)n_inc)); sf.dev.push_back(d_keys);
+      CB_TRY(dalloc(&d_keys_s, (size_t)n_inc)); sf.dev.push_back(d_keys_s);
+      CB_TRY(dalloc(&d_pair_start, (size_t)nt + 1)); sf.dev.push_back(d_pair_start);
+      CB_TRY(dalloc(&d_koff, (size_t)nt)); sf.dev.push_back(d_koff);
+      CB_TRY(palloc(p, &p->d_klist, (size_t)klen));
+      CB_CUDA(cudaMemsetAsync(d_ninc + p->n_pts, 0, sizeof(int), st));
+      CB_LAUNCH(cb::inc_count_kernel, cdiv(p->n_pts, 256), 256, 0, st, (const unsigned long long*)d_mask, p->n_pts, d_ninc);
+      size_t tb_a = 0, tb_b = 0;
+      const int key_bits = bits_for((unsigned long long)nt * (unsigned long long)p->n_pts);
+      cub::DeviceScan::ExclusiveSum(nullptr, tb_a, d_ninc, d_incoff, p->n_pts + 1, st);
+      cub::DeviceRadixSort::SortKeys(nullptr, tb_b, d_keys, d_keys_s, (int)n_inc, 0, key_bits, st);
+      void* d_tmp = nullptr;
+      size_t tbm = std::max(tb_a, tb_b);
+      CB_TRY(cached_malloc(&d_tmp, std::max<size_t>(tbm, 16))); sf.dev.push_back(d_tmp);
+      CB_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tbm, d_ninc, d_incoff, p->n_pts + 1, st));
+      CB_LAUNCH(cb::inc_emit_kernel, cdiv(p->n_pts, 256), 256, 0, st, (const unsigned long long*)d_mask, (const int*)d_incoff,
+                p->n_pts, nb, d_keys);
+      tbm = std::max(tb_a, tb_b);
+      CB_CUDA(cub::DeviceRadixSort::SortKeys(d_tmp, tbm, d_keys, d_keys_s, (int)n_inc, 0, key_bits, st));
+      g_launches.fetch_add(5);
+      CB_CUDA(cudaMemcpyAsync(d_pair_start, pair_start.data(), sizeof(long long) * pair_start.size(), cudaMemcpyHostToDevice, st));
+      CB_CUDA(cudaMemcpyAsync(d_koff, koff_h.data(), sizeof(long long) * koff_h.size(), cudaMemcpyHostToDevice, st));
+      CB_LAUNCH(cb::fill_int_kernel, cdiv(klen, 256), 256, 0, st, p->d_klist, klen, zero_row);
+      CB_LAUNCH(cb::klist_expand_kernel, cdiv(n_inc, 256), 256, 0, st, (const unsigned long long*)d_keys_s, n_inc, p->n_pts,
+                (const long long*)d_pair_start, (const long long*)d_koff, p->d_klist);
+      CB_CUDA(cudaStreamSynchronize(st));  // pair_start / koff_h are host temporaries of this scope
     }
   }
   p->schur_sparse = sparse;
 
   struct Group { int kind, I, J; double w; int chunks; int koff; };
   std::vector<Group> groups;
-  std::vector<int> klist;
   if (!sparse) {
     for (int I = 0; I < nb; ++I)
       for (int J = I + 1; J < nb; ++J) groups.push_back({0, I, J, 1.0, p->k_chunks, -1});
@@ -1603,15 +1635,12 @@ static int build_schur_items(CbBaProblem* p, cudaStream_t st) {
       else groups.push_back({1, I, -1, w_single, p->k_chunks, -1});
     }
   } else {
-    const int zero_row = p->K_pad;  // rows K_pad .. K_pad + SY_KC - 1 of Zt / tvec are never written
     for (int I = 0; I < nb; ++I)
       for (int J = I; J < nb; ++J) {
-        const std::vector<int>& pl = plist[tof[(size_t)I * nb + J]];
-        if (pl.empty()) continue;
-        const int koff = (int)klist.size();
-        for (int j : pl) { klist.push_back(3 * j); klist.push_back(3 * j + 1); klist.push_back(3 * j + 2); }
-        while (klist.size() % cb::SY_KC) klist.push_back(zero_row);
-        const int chunks = (int)((klist.size() - koff) / cb::SY_KC);
+        const int t = tof[(size_t)I * nb + J];
+        if (pair_cnt[(size_t)t] == 0) continue;
+        const int koff = (int)pair_koff[(size_t)t];
+        const int chunks = (int)cdiv(3 * pair_cnt[(size_t)t], (long long)cb::SY_KC);
         if (I == J) groups.push_back({1, I, -1, w_single, chunks, koff});
         else groups.push_back({0, I, J, 1.0, chunks, koff});
       }
@@ -1691,10 +1720,6 @@ static int build_schur_items(CbBaProblem* p, cudaStream_t st) {
   CB_TRY(palloc(p, &p->d_tile_of, tof.size()));
   CB_TRY(palloc(p, &p->d_tile_slot_start, sstart.size()));
   CB_TRY(palloc(p, &p->d_tile_slots, std::max<size_t>(sflat.size(), 1)));
-  if (!klist.empty()) {
-    CB_TRY(palloc(p, &p->d_klist, klist.size()));
-    CB_CUDA(cudaMemcpyAsync(p->d_klist, klist.data(), sizeof(int) * klist.size(), cudaMemcpyHostToDevice, st));
-  }
   if (!items.empty())
     CB_CUDA(cudaMemcpyAsync(p->d_items, items.data(), sizeof(cb::SyItem) * items.size(), cudaMemcpyHostToDevice, st));
   CB_CUDA(cudaMemcpyAsync(p->d_tile_of, tof.data(), sizeof(int) * tof.size(), cudaMemcpyHostToDevice, st));

@@ -1040,6 +1040,46 @@ __global__ void tile_pair_count_kernel(const unsigned long long* __restrict__ ma
   for (int i = threadIdx.x; i < nt; i += blockDim.x)
     if (tp_cnt[i]) atomicAdd(&cnt[i], (unsigned long long)tp_cnt[i]);
 }
+// Compacted row lists of the sparse Schur product, built on the device.  Every (tile pair, point) incidence becomes one
+// 64-bit key  tile(I,J) * n_pts + point  (inc_count / exclusive scan / inc_emit: no atomics, fixed positions); a radix sort
+// leaves each tile pair's points contiguous and ascending; klist_expand writes rows 3j..3j+2 at the pair's offset.  Padding
+// entries (to a multiple of SY_KC per pair) keep the fill value = the index of an all-zero row.
+__global__ void inc_count_kernel(const unsigned long long* __restrict__ mask, int n_pts, int* __restrict__ n_inc) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_pts) return;
+  const int b = __popcll(mask[j]);
+  n_inc[j] = b * (b + 1) / 2;
+}
+__global__ void inc_emit_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ inc_off, int n_pts,
+                                int nb, unsigned long long* __restrict__ keys) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_pts) return;
+  int o = inc_off[j];
+  for (unsigned long long a = mask[j]; a; a &= a - 1) {
+    const int I = __ffsll((long long)a) - 1;
+    for (unsigned long long b = a; b; b &= b - 1) {
+      const int J = __ffsll((long long)b) - 1;
+      keys[o++] = (unsigned long long)(I * nb - I * (I - 1) / 2 + (J - I)) * (unsigned long long)n_pts + (unsigned long long)j;
+    }
+  }
+}
+__global__ void fill_int_kernel(int* __restrict__ a, long long n, int v) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) a[i] = v;
+}
+__global__ void klist_expand_kernel(const unsigned long long* __restrict__ keys_sorted, long long n_inc, int n_pts,
+                                    const long long* __restrict__ pair_start, const long long* __restrict__ koff,
+                                    int* __restrict__ klist) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n_inc) return;
+  const unsigned long long key = keys_sorted[i];
+  const int t = (int)(key / (unsigned long long)n_pts);
+  const int j = (int)(key - (unsigned long long)t * (unsigned long long)n_pts);
+  const long long base = koff[t] + 3 * (i - pair_start[t]);
+  klist[base] = 3 * j;
+  klist[base + 1] = 3 * j + 1;
+  klist[base + 2] = 3 * j + 2;
+}
 // point-major pixel list
 __global__ void pm_gather_kernel(const int* __restrict__ pm_orig, const double2* __restrict__ obs_xy, int n,
                                  double2* __restrict__ pm_xy) {

@@ -420,6 +420,34 @@ def test_solve_with_many_cameras_and_sparse_visibility():
     assert abs(rm - O.overall_rmse_px(ref.x, rig)) < 1e-6
 
 
+def test_sparse_schur_lists_equal_the_dense_product(monkeypatch):
+    """Local visibility (each point seen by 6 neighbouring cameras of 40): the Schur product walks compacted row lists built
+    on the device (one per pair of 96-column tiles, only the points both tiles see).  Forced on and forced off, the reduced
+    system, the step and the solve must agree to rounding; the lists must actually be in use."""
+    from caliscope_b200 import synthetic
+
+    r = synthetic.make_rig(40, 6000, 36000, seed=5, cams_per_point=6)
+    rig = O.Rig(r.cam_flags, r.cam_const, r.n_pts, r.obs_cam, r.obs_pt, r.obs_xy)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("CB_SY_SPARSE", mode)
+        with make_problem(rig) as p:
+            assert bool(p.stat(0)) == (mode == "1")
+            ne = p.normal_equations(r.x0, 1e-3)
+            res = p.solve(r.x0)
+            out[mode] = (ne, res, p.stat(1))
+    (ne1, res1, flop1), (ne0, res0, flop0) = out["1"], out["0"]
+    scale = np.abs(ne0["S"]).max()
+    assert np.abs(ne1["S"] - ne0["S"]).max() < 1e-12 * scale
+    assert np.abs(ne1["b"] - ne0["b"]).max() < 1e-12 * np.abs(ne0["b"]).max()
+    assert np.abs(ne1["dc"] - ne0["dc"]).max() < 1e-9 * np.abs(ne0["dc"]).max()
+    assert res1.nfev == res0.nfev and abs(res1.cost - res0.cost) < 1e-12 * res0.cost
+    assert np.abs(res1.x - res0.x).max() < 1e-9
+    assert flop1 < 0.7 * flop0  # the lists skip the tile pairs (and points) without common visibility
+    ref = O.solve_scipy(rig, r.x0)
+    assert res1.cost <= ref.cost * (1 + 1e-8)
+
+
 def test_solve_is_bitwise_reproducible():
     """All reductions are ordered (no floating-point atomics): two solves give identical bits."""
     from caliscope_b200 import synthetic
