@@ -207,3 +207,32 @@ def test_camera_order_groups_cameras_that_share_points():
     assert np.array_equal(D.camera_order(dense.obs_cam, dense.obs_pt, 64, dense.n_pts), np.arange(64))
     small = synthetic.cfg2()
     assert np.array_equal(D.camera_order(small.obs_cam, small.obs_pt, 8, small.n_pts), np.arange(8))
+
+
+def test_native_shard_selection_equals_numpy_path(monkeypatch):
+    """distributed.shard_points cuts a rank's point range out of the caller's arrays through the library's multi-threaded
+    cb_shard_select when the list is large and already has the ABI's dtypes; the NumPy path is the same selection.  Both must
+    give identical shards (rows in the caller's order, local point indices), for every rank, and the shards must partition
+    the list."""
+    from caliscope_b200 import distributed as D
+    from caliscope_b200 import synthetic
+
+    r = synthetic.make_rig(16, 40_000, 400_000, seed=3)
+    xy = np.ascontiguousarray(r.obs_xy)
+    world = 5
+    seen = np.zeros(len(r.obs_cam), np.int64)
+    for rank in range(world):
+        a = D.shard_points(r.obs_cam, r.obs_pt, xy, r.n_pts, rank, world)
+        assert D._native_shard_select(r.obs_cam, r.obs_pt, xy, int(a.pt_index[0]), int(a.pt_index[-1]) + 1) is not None
+        with monkeypatch.context() as m:
+            m.setattr(D, "_native_shard_select", lambda *args: None)
+            b = D.shard_points(r.obs_cam, r.obs_pt, xy, r.n_pts, rank, world)
+        for f in ("pt_index", "obs_index", "obs_cam", "obs_pt", "obs_xy"):
+            assert np.array_equal(getattr(a, f), getattr(b, f)), (rank, f)
+        assert a.obs_cam.dtype == np.int32 and a.obs_pt.dtype == np.int32 and a.obs_xy.dtype == np.float64
+        assert np.array_equal(r.obs_pt[a.obs_index] - a.pt_index[0], a.obs_pt)
+        seen[a.obs_index] += 1
+    assert (seen == 1).all()
+    # lists that are small, or not in the ABI's dtypes, take the NumPy path
+    assert D._native_shard_select(r.obs_cam[:1000], r.obs_pt[:1000], xy[:1000], 0, 10) is None
+    assert D._native_shard_select(r.obs_cam.astype(np.int64), r.obs_pt, xy, 0, 10) is None
