@@ -83,15 +83,25 @@ def _offset(values: np.ndarray):
 
 
 def _pack(*cols) -> np.ndarray:
-    """Lexicographic key of integer columns (most significant first); raises if it does not fit 63 bits."""
-    key = None
+    """Lexicographic key of integer columns (most significant first); raises if it does not fit 63 bits.  One output array,
+    updated in place (these columns have millions of rows; every temporary is a pass over memory)."""
+    cols = [np.asarray(c, dtype=np.int64) for c in cols]
+    los, spans = [], []
     bits = 0.0
     for c in cols:
-        code, span = _offset(c)
+        lo = int(c.min()) if len(c) else 0
+        span = int(c.max()) - lo + 1 if len(c) else 1
+        los.append(lo)
+        spans.append(span)
         bits += np.log2(max(span, 1))
-        key = code if key is None else key * span + code
     if bits > 62.0:
         raise ValueError("identifier ranges too wide to pack (sync_index, object_id, keypoint_id) into a 63-bit key")
+    key = cols[0] - los[0]
+    for c, lo, span in zip(cols[1:], los[1:], spans[1:]):
+        key *= span
+        key += c
+        if lo:
+            key -= lo
     return np.ascontiguousarray(key)
 
 
@@ -128,8 +138,11 @@ def pnp_arrays(tab: CameraTables, cam_id, sync_index, object_id, img_xy, obj_xyz
     if len(cam_id) == 0:
         raise ValueError("No valid camera data found for PnP")
     slot_all = _slots(tab, cam_id)
-    sel = (slot_all >= 0) & tab.has_intrinsics[np.maximum(slot_all, 0)]
-    if not sel.all():
+    if tab.has_intrinsics.all() and int(slot_all.min()) >= 0:
+        sel = None  # every row belongs to a calibrated camera of the array: nothing to drop (the usual case)
+    else:
+        sel = (slot_all >= 0) & tab.has_intrinsics[np.maximum(slot_all, 0)]
+    if sel is not None and not sel.all():
         cam_id, slot_all = cam_id[sel], slot_all[sel]
         sync = np.asarray(sync_index, dtype=np.int64)[sel]
         obj_id = np.asarray(object_id, dtype=np.int64)[sel]
