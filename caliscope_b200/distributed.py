@@ -85,7 +85,7 @@ def _component_labels(n_pts: int, groups_a: np.ndarray, groups_b: np.ndarray) ->
     return np.array([find(int(j)) for j in range(n_pts)], dtype=np.int64)
 
 
-def _native_shard_select(obs_cam, obs_pt, obs_xy, lo: int, hi: int):
+def _native_shard_select(obs_cam, obs_pt, obs_xy, lo: int, hi: int, n_threads: int = 0):
     """The selection through the library's multi-threaded ``cb_shard_select`` when the inputs already have the ABI's
     dtypes (int32 / int32 / float64, contiguous) and the list is large; None otherwise (the NumPy path below is the same
     selection)."""
@@ -101,15 +101,15 @@ def _native_shard_select(obs_cam, obs_pt, obs_xy, lo: int, hi: int):
     n = len(obs_pt)
     n_sel = C.c_int64()
     p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
-    L.check(lib.cb_shard_select(n, p(obs_cam), p(obs_pt), p(obs_xy), lo, hi, 0, C.addressof(n_sel), None, None, None, None, 0),
-            "shard_select")  # fmt: skip
+    L.check(lib.cb_shard_select(n, p(obs_cam), p(obs_pt), p(obs_xy), lo, hi, 0, C.addressof(n_sel), None, None, None, None,
+                                int(n_threads)), "shard_select")  # fmt: skip
     m = n_sel.value
     sel = np.empty(m, np.int64)
     cam_l = np.empty(m, np.int32)
     pt_l = np.empty(m, np.int32)
     xy_l = np.empty((m, 2), np.float64)
     L.check(lib.cb_shard_select(n, p(obs_cam), p(obs_pt), p(obs_xy), lo, hi, m, C.addressof(n_sel), p(sel), p(cam_l), p(pt_l),
-                                p(xy_l), 0), "shard_select")  # fmt: skip
+                                p(xy_l), int(n_threads)), "shard_select")  # fmt: skip
     return sel, cam_l, pt_l, xy_l
 
 
@@ -126,7 +126,8 @@ def shard_points(obs_cam, obs_pt, obs_xy, n_pts: int, rank: int, world_size: int
         # every sharded call on every rank; the general path below costs ~25 ms on 2 M observations)
         bounds = point_ranges(obs_pt, n_pts, world_size)
         lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-        native = _native_shard_select(obs_cam, obs_pt, obs_xy, lo, hi)
+        # every rank of the node runs this at the same moment: share the host cores instead of oversubscribing them
+        native = _native_shard_select(obs_cam, obs_pt, obs_xy, lo, hi, max(2, min(8, 24 // max(world_size, 1))))
         if native is not None:
             sel, cam_l, pt_l, xy_l = native
             return PointShard(rank=rank, world_size=world_size, pt_index=np.arange(lo, hi, dtype=np.int64), obs_index=sel,
