@@ -233,13 +233,13 @@ def run_reference(args) -> None:
         if wall > budget_s:
             break
     value = its / wall
-    cores = os.cpu_count()
+    cores = 1  # threads the solve actually uses: scipy.sparse products and LSMR are single-threaded (os.cpu_count() are visible)
     sample = (
         f"{args.workload} full rig, scipy TRF+LSMR "
         + (f"capped at max_nfev={args.ref_max_nfev}" if args.ref_max_nfev > 0 else "run to convergence (ftol 1e-8)")
         + f" per step ({last['nit']} LM iteration(s), nfev {last['nfev']}, {last['wall_s']:.1f} s each); "
         f"{steps} of {args.steps} requested steps "
-        f"timed within the {budget_s:.0f} s budget; warm-up on cfg2"
+        f"timed within the {budget_s:.0f} s budget; warm-up on cfg2; {os.cpu_count()} host cores visible, the SciPy path uses one"
     )
     line = {
         "impl": "reference",
@@ -675,7 +675,7 @@ def run_ours(args) -> None:
         line["cpu_baseline"] = {
             "value": cpu["nit"] / cpu["wall_s"],
             "unit": UNIT,
-            "cores": os.cpu_count(),
+            "cores": 1,  # scipy.sparse matvec / LSMR are single-threaded; os.cpu_count() cores are visible
             "kind": "port",
             "sample": f"{args.workload} full rig, one scipy TRF+LSMR solve on the NumPy oracle port "
             + (f"capped at max_nfev={args.ref_max_nfev}" if args.ref_max_nfev > 0 else "to convergence (ftol 1e-8)")

@@ -1660,7 +1660,7 @@ static int build_schur_items(CbBaProblem* p, cudaStream_t st) {
   // CTAs per group: proportional share rounded down, then the SMs left over go one by one to the group whose CTAs carry
   // the most work (6 tiles at P = 9: 18 groups, floor alone leaves 10 of 148 SMs idle)
   // A CTA gets at least SY_MIN_CHUNKS k-chunks: every split-K slot is a 96x96 partial tile the finalize kernel reads back
-  // serially, and on a small rig (4 cameras x 2000 points: 188 chunks in ONE tile) 148 slots of 1-2 chunks each made the
+  // serially, and on a small rig (8 cameras x 2000 points: 188 chunks in ONE tile) 148 slots of 1-2 chunks each made the
   // finalize kernel (78 us) cost 5x the product it reduces.
   constexpr int SY_MIN_CHUNKS = 8;
   auto cap_of = [&](const Group& g) { return std::max(1, g.chunks / SY_MIN_CHUNKS); };
