@@ -90,3 +90,66 @@ def test_pack_keys_groups_exactly_like_lexsort(seed, n, lo, span):
     same_key = key[:, None] == key[None, :]
     same_tuple = (s[:, None] == s[None, :]) & (o[:, None] == o[None, :]) & (k[:, None] == k[None, :])
     assert np.array_equal(same_key, same_tuple)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# bootstrap bookkeeping (host array versions; the device versions are compared with them in tests/test_gpu_bootstrap.py)
+# ---------------------------------------------------------------------------------------------------------------------
+@settings(max_examples=30, deadline=None)
+@given(seed=st.integers(0, 10_000), n=st.integers(1, 400), n_seg=st.integers(1, 9))
+def test_segment_percentiles_equal_numpy_per_segment(seed, n, n_seg):
+    """bootstrap._segment_percentiles == np.percentile(values[seg == p], [25, 75]) for every segment, bit for bit (the IQR
+    thresholds of reject_outliers, pose_network_builder.py:369-400, are compared with < and >)."""
+    from caliscope_b200 import bootstrap as B
+
+    rng = np.random.default_rng(seed)
+    seg = np.sort(rng.integers(0, n_seg, n))
+    vals = rng.normal(size=n) * 10.0
+    vals[rng.uniform(size=n) < 0.1] = np.round(vals[rng.uniform(size=n) < 0.1][:1].sum())  # some ties
+    q1, q3 = B._segment_percentiles(vals, seg, n_seg)
+    for p in range(n_seg):
+        v = vals[seg == p]
+        if len(v) == 0:
+            continue
+        a, b = np.percentile(v, [25, 75])
+        assert q1[p] == a and q3[p] == b
+
+
+@settings(max_examples=20, deadline=None)
+@given(seed=st.integers(0, 10_000), n=st.integers(2, 60), n_seg=st.integers(1, 5))
+def test_segment_quaternion_average_equals_per_segment_eigenvector(seed, n, n_seg):
+    """One batched 4x4 eigen-decomposition per pair == quaternion_average (pose_network_builder.py:416-438) of each pair's
+    samples; a lone sample is returned itself."""
+    from caliscope_b200 import bootstrap as B
+    from oracle.ippe import _rodrigues
+
+    rng = np.random.default_rng(seed)
+    seg = np.sort(np.concatenate([np.arange(n_seg), rng.integers(0, n_seg, n)]))  # every segment non-empty
+    base = rng.normal(size=3) * 0.5
+    R = np.array([_rodrigues(base + rng.normal(size=3) * 0.05) for _ in seg])
+    q = B._quat_wxyz(R)
+    out = B._segment_quaternion_average(q, seg, n_seg)
+    for p in range(n_seg):
+        qs = q[seg == p]
+        ref = B.quaternion_average(qs)
+        assert np.abs(out[p] - ref).max() < 1e-12 or np.abs(out[p] + ref).max() < 1e-12
+        if len(qs) == 1:
+            assert (out[p] == qs[0]).all()
+
+
+@settings(max_examples=40, deadline=None)
+@given(seed=st.integers(0, 10_000), n=st.integers(1, 300))
+def test_bootstrap_key_packing_is_an_order_isomorphism(seed, n):
+    """bootstrap._pack maps (a, b, c) rows to one integer whose order is the lexicographic order of the rows and whose
+    equality is row equality (what the device grouping sorts and compares)."""
+    from caliscope_b200 import bootstrap as B
+
+    rng = np.random.default_rng(seed)
+    cols = [rng.integers(-5, 40, n), rng.integers(1000, 1030, n), rng.integers(0, 4, n)]
+    key = B._pack(*cols)
+    order = np.lexsort((cols[2], cols[1], cols[0]))
+    assert (np.diff(key[order]) >= 0).all()
+    rows = np.stack(cols, axis=1)
+    same_key = key[:, None] == key[None, :]
+    same_row = (rows[:, None, :] == rows[None, :, :]).all(axis=2)
+    assert (same_key == same_row).all()
